@@ -1,0 +1,1298 @@
+// forge2d_b200 — implementation of the C ABI declared in include/forge2d_b200.h.
+// Included by exactly one translation unit per library:
+//   * forge2d_b200/csrc/f2d_cuda.cu   (the product: steps run as CUDA kernels, no CPU path)
+//   * tests/emu/f2d_emu.cpp           (test-only host emulation of the same step code, never shipped)
+// The including TU provides the backend hooks declared below.
+#include "f2d_image.h"
+#include "f2d_step.h"
+
+#include "../../include/forge2d_b200.h"
+#include "../../include/forge2d_b200_debug.h"
+
+#include <stdio.h>
+#include <string>
+
+namespace f2d
+{
+
+constexpr int kMaxWorlds = 128; // B2_MAX_WORLDS, constants.h:26-28
+constexpr int kSecretCookie = 1152023; // core.h:116
+
+enum SyncState
+{
+	kInSync,
+	kHostNewer,
+	kDeviceNewer
+};
+
+struct HostWorld
+{
+	World* img = nullptr; // host image (pinned when the CUDA backend is active)
+	Caps caps{};
+	SyncState state = kInSync;
+	bool inUse = false;
+	uint16_t generation = 0;
+	int launchMode = -1;
+	void* backend = nullptr; // device mirror, streams, events
+	bool eventsFresh = true; // event arrays of `img` reflect the last step
+	bool headerFresh = true;
+};
+
+static HostWorld g_worlds[kMaxWorlds];
+static std::string g_lastError;
+static long long g_launchCount = 0;
+
+static void reportError( const char* fmt, int a = 0, int b = 0 )
+{
+	char buf[512];
+	snprintf( buf, sizeof( buf ), fmt, a, b );
+	g_lastError = buf;
+	fprintf( stderr, "forge2d_b200: %s\n", buf );
+}
+
+// ---- backend hooks (defined by the including translation unit) ------------------------------------------------
+static void* backendHostAlloc( size_t bytes );
+static void backendHostFree( void* p );
+static bool backendAvailable();
+/// Runs one step on the authoritative copy; after return `hw.img`'s HEADER (sizeof(World)) is current.
+static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous );
+static void backendSynchronize( HostWorld& hw );
+/// Makes the full host image current (device -> host) when the device copy is newer.
+static void backendDownload( HostWorld& hw );
+/// Makes one byte range of the host image current.
+static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes );
+static void backendRelease( HostWorld& hw );
+static void backendStepTimes( HostWorld& hw, float* out5 );
+static void backendEnableTiming( HostWorld& hw, bool flag );
+
+static HostWorld* worldFromIndex0( int index0 )
+{
+	if ( index0 < 0 || index0 >= kMaxWorlds || g_worlds[index0].inUse == false )
+		return nullptr;
+	return g_worlds + index0;
+}
+static HostWorld* worldFromId( b2WorldId id )
+{
+	HostWorld* hw = worldFromIndex0( (int)id.index1 - 1 );
+	if ( hw == nullptr || hw->generation != id.generation )
+		return nullptr;
+	return hw;
+}
+
+// Host image current and writable
+static World* hostImage( HostWorld& hw )
+{
+	if ( hw.state == kDeviceNewer )
+	{
+		backendDownload( hw );
+		hw.state = kInSync;
+		hw.eventsFresh = true;
+		hw.headerFresh = true;
+	}
+	return hw.img;
+}
+static World* mutableImage( HostWorld& hw )
+{
+	World* w = hostImage( hw );
+	hw.state = kHostNewer;
+	return w;
+}
+
+static Caps capsWith( const World* w, int B, int S, int C, int J )
+{
+	Caps c;
+	c.bodies = B;
+	c.shapes = S;
+	c.contacts = C;
+	c.joints = J;
+	c.contactEvents = w != nullptr && w->contactEventCapable > 0 ? C : 16;
+	c.hitEvents = w != nullptr && w->hitEventCapable > 0 ? C : 16;
+	return c;
+}
+
+// Grows the image when any entity array is short of `need*` free slots.
+static void reserve( HostWorld& hw, int needBodies, int needShapes, int needContacts, int needJoints )
+{
+	World* w = hw.img;
+	Caps c = hw.caps;
+	bool grow = false;
+	int wantB = w->bodyIds.next + needBodies;
+	int wantS = w->shapeIds.next + needShapes;
+	int wantC = w->contactIds.next + needContacts;
+	int wantJ = w->jointIds.next + needJoints;
+	if ( wantB > c.bodies )
+	{
+		c.bodies = roundCap( wantB, 64 );
+		grow = true;
+	}
+	if ( wantS > c.shapes )
+	{
+		c.shapes = roundCap( wantS, 64 );
+		grow = true;
+	}
+	if ( wantC > c.contacts )
+	{
+		c.contacts = roundCap( wantC, 256 );
+		grow = true;
+	}
+	if ( wantJ > c.joints )
+	{
+		c.joints = roundCap( wantJ, 64 );
+		grow = true;
+	}
+	Caps ev = capsWith( w, c.bodies, c.shapes, c.contacts, c.joints );
+	if ( ev.contactEvents != c.contactEvents || ev.hitEvents != c.hitEvents )
+	{
+		c.contactEvents = ev.contactEvents;
+		c.hitEvents = ev.hitEvents;
+		grow = true;
+	}
+	if ( grow )
+	{
+		hw.img = imageRelayout( w, c, backendHostAlloc, backendHostFree );
+		hw.caps = c;
+	}
+}
+
+static BodyId toBodyId( b2BodyId id ) { return BodyId{ id.index1, id.world0, id.generation }; }
+
+static bool checkWorldError( HostWorld& hw, const char* where )
+{
+	World* w = hw.img;
+	if ( w->error != 0 )
+	{
+		char buf[256];
+		snprintf( buf, sizeof( buf ), "%s: world error flags 0x%x (detail line %d)%s", where, w->error, w->errorDetail,
+				  ( w->error & kErrCapacity ) ? " [capacity exceeded inside the step]" : "" );
+		g_lastError = buf;
+		fprintf( stderr, "forge2d_b200: %s\n", buf );
+		return true;
+	}
+	return false;
+}
+
+} // namespace f2d
+
+using namespace f2d;
+
+extern "C" {
+
+// ---- defaults (B2/src/types.c:9-88) ---------------------------------------------------------------------------
+b2WorldDef b2DefaultWorldDef( void )
+{
+	b2WorldDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.gravity.x = 0.0f;
+	def.gravity.y = -10.0f;
+	def.hitEventThreshold = 1.0f;
+	def.restitutionThreshold = 1.0f;
+	def.maxContactPushSpeed = 3.0f;
+	def.contactHertz = 30.0;
+	def.contactDampingRatio = 10.0f;
+	def.maximumLinearSpeed = 400.0f;
+	def.enableSleep = true;
+	def.enableContinuous = true;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2BodyDef b2DefaultBodyDef( void )
+{
+	b2BodyDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.type = b2_staticBody;
+	def.rotation.c = 1.0f;
+	def.rotation.s = 0.0f;
+	def.sleepThreshold = 0.05f;
+	def.gravityScale = 1.0f;
+	def.enableSleep = true;
+	def.isAwake = true;
+	def.isEnabled = true;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2Filter b2DefaultFilter( void )
+{
+	b2Filter f = { 1, UINT64_MAX, 0 };
+	return f;
+}
+b2SurfaceMaterial b2DefaultSurfaceMaterial( void )
+{
+	b2SurfaceMaterial m;
+	memset( &m, 0, sizeof( m ) );
+	m.friction = 0.6f;
+	return m;
+}
+b2ShapeDef b2DefaultShapeDef( void )
+{
+	b2ShapeDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.material.friction = 0.6f;
+	def.density = 1.0f;
+	def.filter = b2DefaultFilter();
+	def.updateBodyMass = true;
+	def.invokeContactCreation = true;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2RevoluteJointDef b2DefaultRevoluteJointDef( void )
+{
+	b2RevoluteJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.drawSize = 0.25f;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+
+// ---- geometry helpers (B2/src/geometry.c:133-203) --------------------------------------------------------------
+b2Polygon b2MakeBox( float hx, float hy )
+{
+	b2Polygon s;
+	memset( &s, 0, sizeof( s ) );
+	s.count = 4;
+	s.vertices[0] = b2Vec2{ -hx, -hy };
+	s.vertices[1] = b2Vec2{ hx, -hy };
+	s.vertices[2] = b2Vec2{ hx, hy };
+	s.vertices[3] = b2Vec2{ -hx, hy };
+	s.normals[0] = b2Vec2{ 0.0f, -1.0f };
+	s.normals[1] = b2Vec2{ 1.0f, 0.0f };
+	s.normals[2] = b2Vec2{ 0.0f, 1.0f };
+	s.normals[3] = b2Vec2{ -1.0f, 0.0f };
+	s.radius = 0.0f;
+	s.centroid = b2Vec2{ 0.0f, 0.0f };
+	return s;
+}
+b2Polygon b2MakeSquare( float h )
+{
+	return b2MakeBox( h, h );
+}
+b2Polygon b2MakeOffsetRoundedBox( float hx, float hy, b2Vec2 center, b2Rot rotation, float radius )
+{
+	Xf xf = { { center.x, center.y }, { rotation.c, rotation.s } };
+	b2Polygon s;
+	memset( &s, 0, sizeof( s ) );
+	s.count = 4;
+	const V2 lv[4] = { { -hx, -hy }, { hx, -hy }, { hx, hy }, { -hx, hy } };
+	const V2 ln[4] = { { 0.0f, -1.0f }, { 1.0f, 0.0f }, { 0.0f, 1.0f }, { -1.0f, 0.0f } };
+	for ( int i = 0; i < 4; ++i )
+	{
+		V2 v = xfPoint( xf, lv[i] );
+		V2 n = rotate( xf.q, ln[i] );
+		s.vertices[i] = b2Vec2{ v.x, v.y };
+		s.normals[i] = b2Vec2{ n.x, n.y };
+	}
+	s.radius = radius;
+	s.centroid = center;
+	return s;
+}
+// geometry.c:41-75 (+ centroid :17-39)
+b2Polygon b2MakePolygon( const b2Hull* hull, float radius )
+{
+	if ( hull->count < 3 )
+		return b2MakeSquare( 0.5f );
+	b2Polygon s;
+	memset( &s, 0, sizeof( s ) );
+	s.count = hull->count;
+	s.radius = radius;
+	for ( int i = 0; i < s.count; ++i )
+		s.vertices[i] = hull->points[i];
+	for ( int i = 0; i < s.count; ++i )
+	{
+		int i2 = i + 1 < s.count ? i + 1 : 0;
+		V2 edge = sub( V2{ s.vertices[i2].x, s.vertices[i2].y }, V2{ s.vertices[i].x, s.vertices[i].y } );
+		V2 n = normalize( crossVS( edge, 1.0f ) );
+		s.normals[i] = b2Vec2{ n.x, n.y };
+	}
+	V2 center = { 0.0f, 0.0f };
+	float area = 0.0f;
+	V2 origin = { s.vertices[0].x, s.vertices[0].y };
+	const float inv3 = 1.0f / 3.0f;
+	for ( int i = 1; i < s.count - 1; ++i )
+	{
+		V2 e1 = sub( V2{ s.vertices[i].x, s.vertices[i].y }, origin );
+		V2 e2 = sub( V2{ s.vertices[i + 1].x, s.vertices[i + 1].y }, origin );
+		float a = 0.5f * cross( e1, e2 );
+		center = mulAdd( center, a * inv3, add( e1, e2 ) );
+		area += a;
+	}
+	float invArea = 1.0f / area;
+	center.x *= invArea;
+	center.y *= invArea;
+	center = add( origin, center );
+	s.centroid = b2Vec2{ center.x, center.y };
+	return s;
+}
+
+// ---- world -----------------------------------------------------------------------------------------------------
+b2WorldId b2CreateWorld( const b2WorldDef* def )
+{
+	int index = -1;
+	for ( int i = 0; i < kMaxWorlds; ++i )
+	{
+		if ( g_worlds[i].inUse == false )
+		{
+			index = i;
+			break;
+		}
+	}
+	if ( index < 0 )
+		return b2WorldId{ 0, 0 };
+	HostWorld& hw = g_worlds[index];
+	uint16_t generation = hw.generation;
+	hw = HostWorld();
+	hw.generation = generation;
+	hw.inUse = true;
+	hw.caps = capsWith( nullptr, 64, 64, 256, 64 );
+	hw.img = imageCreate( hw.caps, backendHostAlloc );
+	World* w = hw.img;
+	w->worldId = (uint16_t)index;
+	w->generation = generation;
+	w->inUse = true;
+	w->gravity = V2{ def->gravity.x, def->gravity.y };
+	w->hitEventThreshold = def->hitEventThreshold;
+	w->restitutionThreshold = def->restitutionThreshold;
+	w->maxLinearSpeed = def->maximumLinearSpeed;
+	w->maxContactPushSpeed = def->maxContactPushSpeed;
+	w->contactHertz = def->contactHertz;
+	w->contactDampingRatio = def->contactDampingRatio;
+	w->enableSleep = def->enableSleep;
+	w->enableContinuous = def->enableContinuous;
+	if ( def->frictionCallback != nullptr || def->restitutionCallback != nullptr )
+	{
+		reportError( "b2CreateWorld: host friction/restitution callbacks cannot run inside the device step; default mixing is used" );
+		w->hasHostCallbacks = true;
+	}
+	hw.state = kHostNewer;
+	return b2WorldId{ (uint16_t)( index + 1 ), hw.generation };
+}
+
+void b2DestroyWorld( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	backendRelease( *hw );
+	backendHostFree( hw->img );
+	uint16_t generation = hw->generation;
+	*hw = HostWorld();
+	hw->generation = (uint16_t)( generation + 1 );
+}
+
+bool b2World_IsValid( b2WorldId id )
+{
+	return worldFromId( id ) != nullptr;
+}
+
+} // extern "C"
+namespace f2d
+{
+static void prepareStep( HostWorld& hw )
+{
+	// capacity headroom for what the step itself may create (contacts from buffered moves)
+	World* w = hw.img; // header is current in every sync state
+	int needContacts = 4 * w->moveArray.count + 64;
+	if ( w->contactIds.next + needContacts > hw.caps.contacts )
+	{
+		hostImage( hw );
+		reserve( hw, 0, 0, needContacts, 0 );
+		hw.state = kHostNewer;
+	}
+}
+
+} // namespace f2d
+extern "C" {
+void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	if ( backendAvailable() == false )
+	{
+		reportError( "b2World_Step: no CUDA device available - this library has no CPU fallback" );
+		return;
+	}
+	if ( hw->img->error & kErrUnsupported )
+	{
+		checkWorldError( *hw, "b2World_Step refused" );
+		return;
+	}
+	prepareStep( *hw );
+	backendStep( *hw, timeStep, subStepCount, true );
+	hw->eventsFresh = ( hw->state != kDeviceNewer );
+	checkWorldError( *hw, "b2World_Step" );
+}
+
+void f2dWorld_StepAsync( b2WorldId worldId, float timeStep, int subStepCount )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || backendAvailable() == false )
+		return;
+	backendStep( *hw, timeStep, subStepCount, false );
+	hw->eventsFresh = false;
+	hw->headerFresh = false;
+}
+void f2dWorld_Synchronize( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	backendSynchronize( *hw );
+	hw->headerFresh = true;
+	checkWorldError( *hw, "f2dWorld_Synchronize" );
+}
+
+} // extern "C"
+// Event arrays: pointers into the host image, refreshed by range downloads (B2/src/world.c:1491-1555)
+template <class T> static void refreshArray( HostWorld& hw, const Arr<T>& a )
+{
+	if ( hw.state == kDeviceNewer && a.count > 0 )
+		backendDownloadRange( hw, a.off, (uint64_t)a.count * sizeof( T ) );
+}
+extern "C" {
+
+b2BodyEvents b2World_GetBodyEvents( b2WorldId worldId )
+{
+	b2BodyEvents ev = { nullptr, 0 };
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return ev;
+	World* w = hw->img;
+	refreshArray( *hw, w->moveEvents );
+	ev.moveEvents = reinterpret_cast<b2BodyMoveEvent*>( ptr( w, w->moveEvents ) );
+	ev.moveCount = w->moveEvents.count;
+	return ev;
+}
+b2SensorEvents b2World_GetSensorEvents( b2WorldId worldId )
+{
+	b2SensorEvents ev = { nullptr, nullptr, 0, 0 };
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return ev;
+	World* w = hw->img;
+	int endIndex = 1 - w->endEventArrayIndex;
+	ev.beginEvents = reinterpret_cast<b2SensorBeginTouchEvent*>( ptr( w, w->sensorBeginEvents ) );
+	ev.endEvents = reinterpret_cast<b2SensorEndTouchEvent*>( ptr( w, w->sensorEndEvents[endIndex] ) );
+	ev.beginCount = w->sensorBeginEvents.count;
+	ev.endCount = w->sensorEndEvents[endIndex].count;
+	return ev;
+}
+b2ContactEvents b2World_GetContactEvents( b2WorldId worldId )
+{
+	b2ContactEvents ev = { nullptr, nullptr, nullptr, 0, 0, 0 };
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return ev;
+	World* w = hw->img;
+	int endIndex = 1 - w->endEventArrayIndex; // previous buffer is exposed (world.c:1538)
+	refreshArray( *hw, w->beginEvents );
+	refreshArray( *hw, w->endEvents[endIndex] );
+	refreshArray( *hw, w->hitEvents );
+	ev.beginEvents = reinterpret_cast<b2ContactBeginTouchEvent*>( ptr( w, w->beginEvents ) );
+	ev.endEvents = reinterpret_cast<b2ContactEndTouchEvent*>( ptr( w, w->endEvents[endIndex] ) );
+	ev.hitEvents = reinterpret_cast<b2ContactHitEvent*>( ptr( w, w->hitEvents ) );
+	ev.beginCount = w->beginEvents.count;
+	ev.endCount = w->endEvents[endIndex].count;
+	ev.hitCount = w->hitEvents.count;
+	return ev;
+}
+
+void b2World_EnableSleeping( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	if ( flag == w->enableSleep )
+		return;
+	w->enableSleep = flag;
+	if ( flag == false )
+	{
+		// world.c:1710-1732: wake every sleeping set
+		int setCount = w->sets.count;
+		for ( int i = kFirstSleepingSet; i < setCount; ++i )
+		{
+			SolverSet& s = ptr( w, w->sets )[i];
+			if ( s.setIndex != kNull && s.bodyCount > 0 )
+			{
+				reserve( *hw, 0, 0, 0, 0 );
+				w = hw->img;
+				wakeSolverSet( w, i );
+			}
+		}
+	}
+}
+bool b2World_IsSleepingEnabled( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	return hw ? hw->img->enableSleep : false;
+}
+void b2World_EnableContinuous( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw )
+		mutableImage( *hw )->enableContinuous = flag;
+}
+bool b2World_IsContinuousEnabled( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	return hw ? hw->img->enableContinuous : false;
+}
+void b2World_EnableWarmStarting( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw )
+		mutableImage( *hw )->enableWarmStarting = flag;
+}
+void b2World_SetGravity( b2WorldId worldId, b2Vec2 gravity )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw )
+		mutableImage( *hw )->gravity = V2{ gravity.x, gravity.y };
+}
+b2Vec2 b2World_GetGravity( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return b2Vec2{ 0, 0 };
+	return b2Vec2{ hw->img->gravity.x, hw->img->gravity.y };
+}
+b2Counters b2World_GetCounters( b2WorldId worldId )
+{
+	b2Counters s;
+	memset( &s, 0, sizeof( s ) );
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return s;
+	World* w = hostImage( *hw );
+	s.bodyCount = idCount( w->bodyIds );
+	s.shapeCount = idCount( w->shapeIds );
+	s.contactCount = idCount( w->contactIds );
+	s.jointCount = idCount( w->jointIds );
+	s.islandCount = idCount( w->islandIds );
+	s.staticTreeHeight = treeHeight( w, w->trees[kStaticBody] );
+	s.treeHeight = maxi( treeHeight( w, w->trees[kDynamicBody] ), treeHeight( w, w->trees[kKinematicBody] ) );
+	s.byteCount = (int)w->imageBytes;
+	s.taskCount = w->taskCount;
+	for ( int i = 0; i < kColorCount; ++i )
+		s.colorCounts[i] = w->colorContacts[i].count + w->colorJoints[i].count;
+	return s;
+}
+int b2World_GetAwakeBodyCount( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	return hw ? hw->img->awakeBodies.count : 0;
+}
+
+// ---- bodies ----------------------------------------------------------------------------------------------------
+b2BodyId b2CreateBody( b2WorldId worldId, const b2BodyDef* def )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || def->internalValue != kSecretCookie )
+		return b2BodyId{ 0, 0, 0 };
+	mutableImage( *hw );
+	reserve( *hw, 2, 0, 0, 0 );
+	World* w = hw->img;
+	if ( w->locked )
+		return b2BodyId{ 0, 0, 0 };
+	BodyParams p;
+	p.type = (int)def->type;
+	p.position = V2{ def->position.x, def->position.y };
+	p.rotation = Rot{ def->rotation.c, def->rotation.s };
+	p.linearVelocity = V2{ def->linearVelocity.x, def->linearVelocity.y };
+	p.angularVelocity = def->angularVelocity;
+	p.linearDamping = def->linearDamping;
+	p.angularDamping = def->angularDamping;
+	p.gravityScale = def->gravityScale;
+	p.sleepThreshold = def->sleepThreshold;
+	p.name = def->name;
+	p.userData = (uint64_t)(uintptr_t)def->userData;
+	p.enableSleep = def->enableSleep;
+	p.isAwake = def->isAwake;
+	p.fixedRotation = def->fixedRotation;
+	p.isBullet = def->isBullet;
+	p.isEnabled = def->isEnabled;
+	p.allowFastRotation = def->allowFastRotation;
+	int bodyId = createBody( w, p );
+	return b2BodyId{ bodyId + 1, w->worldId, ptr( w, w->bodies )[bodyId].generation };
+}
+
+static Body* bodyFromId( b2BodyId id, HostWorld** outWorld, bool forWrite )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return nullptr;
+	World* w = forWrite ? mutableImage( *hw ) : hostImage( *hw );
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= w->bodies.count )
+		return nullptr;
+	Body* b = ptr( w, w->bodies ) + index;
+	if ( b->setIndex == kNull || b->id != index || b->generation != id.generation )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return b;
+}
+
+bool b2Body_IsValid( b2BodyId id )
+{
+	return bodyFromId( id, nullptr, false ) != nullptr;
+}
+b2BodyType b2Body_GetType( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? (b2BodyType)b->type : b2_staticBody;
+}
+b2Transform b2Body_GetTransform( b2BodyId id )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, false );
+	b2Transform t = { { 0, 0 }, { 1, 0 } };
+	if ( b == nullptr )
+		return t;
+	const BodySim& s = ptr( hw->img, hw->img->sims )[b->id];
+	t.p = b2Vec2{ s.transform.p.x, s.transform.p.y };
+	t.q = b2Rot{ s.transform.q.c, s.transform.q.s };
+	return t;
+}
+b2Vec2 b2Body_GetPosition( b2BodyId id )
+{
+	return b2Body_GetTransform( id ).p;
+}
+b2Rot b2Body_GetRotation( b2BodyId id )
+{
+	return b2Body_GetTransform( id ).q;
+}
+b2Vec2 b2Body_GetLinearVelocity( b2BodyId id )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, false );
+	if ( b == nullptr || b->setIndex != kAwakeSet )
+		return b2Vec2{ 0, 0 };
+	const BodyState& s = ptr( hw->img, hw->img->states )[b->localIndex];
+	return b2Vec2{ s.v.x, s.v.y };
+}
+float b2Body_GetAngularVelocity( b2BodyId id )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, false );
+	if ( b == nullptr || b->setIndex != kAwakeSet )
+		return 0.0f;
+	return ptr( hw->img, hw->img->states )[b->localIndex].w;
+}
+// body.c:~1000 b2Body_SetLinearVelocity: wakes the body when the velocity is non-zero
+void b2Body_SetLinearVelocity( b2BodyId id, b2Vec2 v )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, true );
+	if ( b == nullptr || b->type == kStaticBody )
+		return;
+	World* w = hw->img;
+	if ( v.x * v.x + v.y * v.y > 0.0f )
+		wakeBody( w, *b );
+	if ( b->setIndex != kAwakeSet )
+		return;
+	ptr( w, w->states )[b->localIndex].v = V2{ v.x, v.y };
+}
+void b2Body_SetAngularVelocity( b2BodyId id, float wv )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, true );
+	if ( b == nullptr || b->type == kStaticBody || b->fixedRotation )
+		return;
+	World* w = hw->img;
+	if ( wv != 0.0f )
+		wakeBody( w, *b );
+	if ( b->setIndex != kAwakeSet )
+		return;
+	ptr( w, w->states )[b->localIndex].w = wv;
+}
+float b2Body_GetMass( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? b->mass : 0.0f;
+}
+float b2Body_GetRotationalInertia( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? b->inertia : 0.0f;
+}
+b2Vec2 b2Body_GetLocalCenterOfMass( b2BodyId id )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	const BodySim& s = ptr( hw->img, hw->img->sims )[b->id];
+	return b2Vec2{ s.localCenter.x, s.localCenter.y };
+}
+b2Vec2 b2Body_GetWorldCenterOfMass( b2BodyId id )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( id, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	const BodySim& s = ptr( hw->img, hw->img->sims )[b->id];
+	return b2Vec2{ s.center.x, s.center.y };
+}
+bool b2Body_IsAwake( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? b->setIndex == kAwakeSet : false;
+}
+int b2Body_GetShapeCount( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? b->shapeCount : 0;
+}
+int b2Body_GetContactCapacity( b2BodyId id )
+{
+	Body* b = bodyFromId( id, nullptr, false );
+	return b ? b->contactCount : 0;
+}
+
+// ---- shapes ----------------------------------------------------------------------------------------------------
+static b2ShapeId createShapeCommon( b2BodyId bodyId, const b2ShapeDef* def, const void* geometry, int type )
+{
+	if ( def->internalValue != kSecretCookie )
+		return b2ShapeId{ 0, 0, 0 };
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return b2ShapeId{ 0, 0, 0 };
+	int bodyIndex = b->id;
+	reserve( *hw, 0, 2, 0, 0 );
+	World* w = hw->img;
+	if ( w->locked )
+		return b2ShapeId{ 0, 0, 0 };
+	ShapeParams p;
+	p.userData = (uint64_t)(uintptr_t)def->userData;
+	p.friction = def->material.friction;
+	p.restitution = def->material.restitution;
+	p.rollingResistance = def->material.rollingResistance;
+	p.tangentSpeed = def->material.tangentSpeed;
+	p.userMaterialId = def->material.userMaterialId;
+	p.customColor = def->material.customColor;
+	p.density = def->density;
+	p.filter = Filter{ def->filter.categoryBits, def->filter.maskBits, def->filter.groupIndex };
+	p.isSensor = def->isSensor;
+	p.enableSensorEvents = def->enableSensorEvents;
+	p.enableContactEvents = def->enableContactEvents;
+	p.enableHitEvents = def->enableHitEvents;
+	p.enablePreSolveEvents = def->enablePreSolveEvents;
+	p.invokeContactCreation = def->invokeContactCreation;
+	p.updateBodyMass = def->updateBodyMass;
+	int before = w->contactEventCapable + w->hitEventCapable;
+	int shapeId = createShape( w, bodyIndex, p, geometry, type );
+	if ( w->contactEventCapable + w->hitEventCapable != before )
+	{
+		reserve( *hw, 0, 0, 0, 0 ); // event arrays grow with the first event-enabled shape
+		w = hw->img;
+	}
+	return b2ShapeId{ shapeId + 1, w->worldId, ptr( w, w->shapes )[shapeId].generation };
+}
+b2ShapeId b2CreateCircleShape( b2BodyId bodyId, const b2ShapeDef* def, const b2Circle* circle )
+{
+	Circle c = { { circle->center.x, circle->center.y }, circle->radius };
+	return createShapeCommon( bodyId, def, &c, kCircle );
+}
+b2ShapeId b2CreateCapsuleShape( b2BodyId bodyId, const b2ShapeDef* def, const b2Capsule* capsule )
+{
+	V2 c1 = { capsule->center1.x, capsule->center1.y }, c2 = { capsule->center2.x, capsule->center2.y };
+	float lengthSqr = distanceSq( c1, c2 );
+	if ( lengthSqr <= kLinearSlop * kLinearSlop ) // shape.c:198-208
+	{
+		Circle c = { lerp( c1, c2, 0.5f ), capsule->radius };
+		return createShapeCommon( bodyId, def, &c, kCircle );
+	}
+	Capsule c = { c1, c2, capsule->radius };
+	return createShapeCommon( bodyId, def, &c, kCapsule );
+}
+b2ShapeId b2CreatePolygonShape( b2BodyId bodyId, const b2ShapeDef* def, const b2Polygon* polygon )
+{
+	static_assert( sizeof( Poly ) == sizeof( b2Polygon ), "polygon layout" );
+	Poly p;
+	memcpy( &p, polygon, sizeof( p ) );
+	return createShapeCommon( bodyId, def, &p, kPolygon );
+}
+b2ShapeId b2CreateSegmentShape( b2BodyId bodyId, const b2ShapeDef* def, const b2Segment* segment )
+{
+	V2 p1 = { segment->point1.x, segment->point1.y }, p2 = { segment->point2.x, segment->point2.y };
+	float lengthSqr = distanceSq( p1, p2 );
+	if ( lengthSqr <= kLinearSlop * kLinearSlop ) // shape.c:215-223
+		return b2ShapeId{ 0, 0, 0 };
+	Segment s = { p1, p2 };
+	return createShapeCommon( bodyId, def, &s, kSegment );
+}
+static Shape* shapeFromId( b2ShapeId id, HostWorld** outWorld )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return nullptr;
+	World* w = hostImage( *hw );
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= w->shapes.count )
+		return nullptr;
+	Shape* s = ptr( w, w->shapes ) + index;
+	if ( s->id != index || s->generation != id.generation )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return s;
+}
+bool b2Shape_IsValid( b2ShapeId id )
+{
+	return shapeFromId( id, nullptr ) != nullptr;
+}
+b2BodyId b2Shape_GetBody( b2ShapeId id )
+{
+	HostWorld* hw = nullptr;
+	Shape* s = shapeFromId( id, &hw );
+	if ( s == nullptr )
+		return b2BodyId{ 0, 0, 0 };
+	World* w = hw->img;
+	return b2BodyId{ s->bodyId + 1, w->worldId, ptr( w, w->bodies )[s->bodyId].generation };
+}
+b2AABB b2Shape_GetAABB( b2ShapeId id )
+{
+	Shape* s = shapeFromId( id, nullptr );
+	b2AABB a = { { 0, 0 }, { 0, 0 } };
+	if ( s )
+	{
+		a.lowerBound = b2Vec2{ s->aabb.lo.x, s->aabb.lo.y };
+		a.upperBound = b2Vec2{ s->aabb.hi.x, s->aabb.hi.y };
+	}
+	return a;
+}
+
+// ---- joints ----------------------------------------------------------------------------------------------------
+b2JointId b2CreateRevoluteJoint( b2WorldId worldId, const b2RevoluteJointDef* def )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || def->internalValue != kSecretCookie )
+		return b2JointId{ 0, 0, 0 };
+	mutableImage( *hw );
+	reserve( *hw, 0, 0, 0, 2 );
+	World* w = hw->img;
+	if ( w->locked )
+		return b2JointId{ 0, 0, 0 };
+	RevoluteParams p;
+	p.bodyIdA = def->bodyIdA.index1 - 1;
+	p.bodyIdB = def->bodyIdB.index1 - 1;
+	p.localAnchorA = V2{ def->localAnchorA.x, def->localAnchorA.y };
+	p.localAnchorB = V2{ def->localAnchorB.x, def->localAnchorB.y };
+	p.referenceAngle = def->referenceAngle;
+	p.targetAngle = def->targetAngle;
+	p.enableSpring = def->enableSpring;
+	p.hertz = def->hertz;
+	p.dampingRatio = def->dampingRatio;
+	p.enableLimit = def->enableLimit;
+	p.lowerAngle = def->lowerAngle;
+	p.upperAngle = def->upperAngle;
+	p.enableMotor = def->enableMotor;
+	p.maxMotorTorque = def->maxMotorTorque;
+	p.motorSpeed = def->motorSpeed;
+	p.drawSize = def->drawSize;
+	p.collideConnected = def->collideConnected;
+	p.userData = (uint64_t)(uintptr_t)def->userData;
+	int jointId = createRevoluteJoint( w, p );
+	return b2JointId{ jointId + 1, w->worldId, ptr( w, w->joints )[jointId].generation };
+}
+bool b2Joint_IsValid( b2JointId id )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return false;
+	World* w = hostImage( *hw );
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= w->joints.count )
+		return false;
+	const Joint& j = ptr( w, w->joints )[index];
+	return j.jointId == index && j.generation == id.generation;
+}
+
+// ---- diagnostics -----------------------------------------------------------------------------------------------
+int f2dHasDevice( void )
+{
+	return backendAvailable() ? 1 : 0;
+}
+const char* f2dGetLastError( void )
+{
+	return g_lastError.c_str();
+}
+void f2dClearLastError( void )
+{
+	g_lastError.clear();
+}
+void f2dWorld_SetLaunchMode( b2WorldId worldId, int mode )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw )
+		hw->launchMode = mode;
+}
+uint32_t f2dWorld_GetErrorFlags( b2WorldId worldId )
+{
+	HostWorld* hw = worldFromId( worldId );
+	return hw ? hw->img->error : 0;
+}
+long long f2dWorld_GetKernelLaunchCount( void )
+{
+	return g_launchCount;
+}
+void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 )
+{
+	HostWorld* hw = worldFromId( worldId );
+	for ( int i = 0; i < 5; ++i )
+		out5[i] = 0.0f;
+	if ( hw )
+		backendStepTimes( *hw, out5 );
+}
+void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw )
+		backendEnableTiming( *hw, flag );
+}
+
+// ---- introspection (same records as oracle/tap.c) ----------------------------------------------------------------
+int f2dDebug_AwakeOrder( b2WorldId id, int* bodyIds, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = w->awakeBodies.count;
+	for ( int i = 0; i < n && i < cap; ++i )
+		bodyIds[i] = ptr( w, w->awakeBodies )[i];
+	return n;
+}
+int f2dDebug_MoveArray( b2WorldId id, int* keys, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = w->moveArray.count;
+	for ( int i = 0; i < n && i < cap; ++i )
+		keys[i] = ptr( w, w->moveArray )[i];
+	return n;
+}
+int f2dDebug_Bodies( b2WorldId id, f2dBodyRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = 0;
+	for ( int i = 0; i < w->bodies.count; ++i )
+	{
+		const Body& b = ptr( w, w->bodies )[i];
+		if ( b.setIndex == kNull || b.id != i )
+			continue;
+		if ( n < cap )
+		{
+			f2dBodyRecord* r = out + n;
+			memset( r, 0, sizeof( *r ) );
+			const BodySim& sim = ptr( w, w->sims )[i];
+			r->id = i;
+			r->setIndex = b.setIndex;
+			r->localIndex = b.localIndex;
+			r->islandId = b.islandId;
+			r->islandPrev = b.islandPrev;
+			r->islandNext = b.islandNext;
+			r->type = b.type;
+			r->headContactKey = b.headContactKey;
+			r->contactCount = b.contactCount;
+			r->headShapeId = b.headShapeId;
+			r->flags = ( sim.isFast ? 1 : 0 ) | ( sim.isBullet ? 2 : 0 ) | ( b.isSpeedCapped ? 4 : 0 ) | ( sim.enlargeAABB ? 8 : 0 );
+			r->px = sim.transform.p.x;
+			r->py = sim.transform.p.y;
+			r->qc = sim.transform.q.c;
+			r->qs = sim.transform.q.s;
+			r->cx = sim.center.x;
+			r->cy = sim.center.y;
+			r->c0x = sim.center0.x;
+			r->c0y = sim.center0.y;
+			r->q0c = sim.rotation0.c;
+			r->q0s = sim.rotation0.s;
+			if ( b.setIndex == kAwakeSet )
+			{
+				const BodyState& s = ptr( w, w->states )[b.localIndex];
+				r->vx = s.v.x;
+				r->vy = s.v.y;
+				r->w = s.w;
+			}
+			r->sleepTime = b.sleepTime;
+			r->invMass = sim.invMass;
+			r->invInertia = sim.invInertia;
+			r->minExtent = sim.minExtent;
+			r->maxExtent = sim.maxExtent;
+			r->lcx = sim.localCenter.x;
+			r->lcy = sim.localCenter.y;
+		}
+		n += 1;
+	}
+	return n;
+}
+int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = 0;
+	for ( int i = 0; i < w->contacts.count; ++i )
+	{
+		const Contact& c = ptr( w, w->contacts )[i];
+		if ( c.contactId != i || c.setIndex == kNull )
+			continue;
+		if ( n < cap )
+		{
+			f2dContactRecord* r = out + n;
+			memset( r, 0, sizeof( *r ) );
+			const ContactSim& s = ptr( w, w->contactSims )[i];
+			r->id = i;
+			r->shapeIdA = c.shapeIdA;
+			r->shapeIdB = c.shapeIdB;
+			r->setIndex = c.setIndex;
+			r->colorIndex = c.colorIndex;
+			r->localIndex = c.localIndex;
+			r->flags = (int)c.flags;
+			r->simFlags = (int)s.simFlags;
+			r->pointCount = s.manifold.pointCount;
+			r->islandId = c.islandId;
+			r->islandPrev = c.islandPrev;
+			r->islandNext = c.islandNext;
+			r->prevKeyA = c.edges[0].prevKey;
+			r->nextKeyA = c.edges[0].nextKey;
+			r->prevKeyB = c.edges[1].prevKey;
+			r->nextKeyB = c.edges[1].nextKey;
+			r->bodySimIndexA = s.bodySimIndexA;
+			r->bodySimIndexB = s.bodySimIndexB;
+			r->nx = s.manifold.normal.x;
+			r->ny = s.manifold.normal.y;
+			for ( int k = 0; k < s.manifold.pointCount && k < 2; ++k )
+			{
+				const ManifoldPoint& mp = s.manifold.points[k];
+				if ( k == 0 )
+					r->id0 = mp.id;
+				else
+					r->id1 = mp.id;
+				r->sep[k] = mp.separation;
+				r->ni[k] = mp.normalImpulse;
+				r->ti[k] = mp.tangentImpulse;
+				r->tni[k] = mp.totalNormalImpulse;
+				r->nv[k] = mp.normalVelocity;
+				r->ax[k] = mp.anchorA.x;
+				r->ay[k] = mp.anchorA.y;
+				r->bx[k] = mp.anchorB.x;
+				r->by[k] = mp.anchorB.y;
+				r->px[k] = mp.point.x;
+				r->py[k] = mp.point.y;
+			}
+			r->friction = s.friction;
+			r->restitution = s.restitution;
+			r->rollingImpulse = s.manifold.rollingImpulse;
+		}
+		n += 1;
+	}
+	return n;
+}
+int f2dDebug_Islands( b2WorldId id, f2dIslandRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = 0;
+	for ( int i = 0; i < w->islands.count; ++i )
+	{
+		const Island& s = ptr( w, w->islands )[i];
+		if ( s.islandId != i || s.setIndex == kNull )
+			continue;
+		if ( n < cap )
+		{
+			f2dIslandRecord* r = out + n;
+			r->id = i;
+			r->setIndex = s.setIndex;
+			r->localIndex = s.localIndex;
+			r->headBody = s.headBody;
+			r->tailBody = s.tailBody;
+			r->bodyCount = s.bodyCount;
+			r->headContact = s.headContact;
+			r->tailContact = s.tailContact;
+			r->contactCount = s.contactCount;
+			r->headJoint = s.headJoint;
+			r->tailJoint = s.tailJoint;
+			r->jointCount = s.jointCount;
+			r->parentIsland = s.parentIsland;
+			r->constraintRemoveCount = s.constraintRemoveCount;
+		}
+		n += 1;
+	}
+	return n;
+}
+int f2dDebug_Shapes( b2WorldId id, f2dShapeRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = 0;
+	for ( int i = 0; i < w->shapes.count; ++i )
+	{
+		const Shape& s = ptr( w, w->shapes )[i];
+		if ( s.id != i )
+			continue;
+		if ( n < cap )
+		{
+			f2dShapeRecord* r = out + n;
+			r->id = i;
+			r->bodyId = s.bodyId;
+			r->proxyKey = s.proxyKey;
+			r->type = s.type;
+			r->enlarged = s.enlargedAABB;
+			r->aabb[0] = s.aabb.lo.x;
+			r->aabb[1] = s.aabb.lo.y;
+			r->aabb[2] = s.aabb.hi.x;
+			r->aabb[3] = s.aabb.hi.y;
+			r->fat[0] = s.fatAABB.lo.x;
+			r->fat[1] = s.fatAABB.lo.y;
+			r->fat[2] = s.fatAABB.hi.x;
+			r->fat[3] = s.fatAABB.hi.y;
+		}
+		n += 1;
+	}
+	return n;
+}
+int f2dDebug_Tree( b2WorldId id, int treeType, f2dTreeLeafRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	const Tree& tree = w->trees[treeType];
+	if ( tree.root == kNull || tree.nodeCount == 0 )
+		return 0;
+	const TreeNode* nodes = ptr( w, tree.nodes );
+	int n = 0;
+	std::vector<int> stack, depth, enl;
+	stack.push_back( tree.root );
+	depth.push_back( 0 );
+	enl.push_back( 0 );
+	while ( stack.empty() == false )
+	{
+		int ni = stack.back(), d = depth.back(), e = enl.back();
+		stack.pop_back();
+		depth.pop_back();
+		enl.pop_back();
+		const TreeNode& node = nodes[ni];
+		if ( node.flags & kNodeLeaf )
+		{
+			if ( n < cap )
+			{
+				out[n].proxyId = ni;
+				out[n].depth = d;
+				out[n].enlargedAncestors = e;
+				out[n].box[0] = node.box.lo.x;
+				out[n].box[1] = node.box.lo.y;
+				out[n].box[2] = node.box.hi.x;
+				out[n].box[3] = node.box.hi.y;
+			}
+			n += 1;
+		}
+		else
+		{
+			int e2 = e + ( ( node.flags & kNodeEnlarged ) ? 1 : 0 );
+			stack.push_back( node.child2 );
+			depth.push_back( d + 1 );
+			enl.push_back( e2 );
+			stack.push_back( node.child1 );
+			depth.push_back( d + 1 );
+			enl.push_back( e2 );
+		}
+	}
+	return n;
+}
+int f2dDebug_Joints( b2WorldId id, f2dJointRecord* out, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int n = 0;
+	for ( int i = 0; i < w->joints.count; ++i )
+	{
+		const Joint& j = ptr( w, w->joints )[i];
+		if ( j.jointId != i || j.setIndex == kNull )
+			continue;
+		if ( n < cap )
+		{
+			f2dJointRecord* r = out + n;
+			memset( r, 0, sizeof( *r ) );
+			const JointSim& s = ptr( w, w->jointSims )[i];
+			r->id = i;
+			r->type = j.type;
+			r->setIndex = j.setIndex;
+			r->colorIndex = j.colorIndex;
+			r->localIndex = j.localIndex;
+			r->bodyIdA = j.edges[0].bodyId;
+			r->bodyIdB = j.edges[1].bodyId;
+			r->islandId = j.islandId;
+			if ( j.type == kRevoluteJoint )
+			{
+				r->impulse[0] = s.revolute.linearImpulse.x;
+				r->impulse[1] = s.revolute.linearImpulse.y;
+				r->impulse[2] = s.revolute.springImpulse;
+				r->impulse[3] = s.revolute.motorImpulse;
+				r->impulse[4] = s.revolute.lowerImpulse;
+				r->impulse[5] = s.revolute.upperImpulse;
+			}
+		}
+		n += 1;
+	}
+	return n;
+}
+void f2dDebug_ColorCounts( b2WorldId id, int* contactCounts, int* jointCounts )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return;
+	World* w = hostImage( *hw );
+	for ( int i = 0; i < kColorCount; ++i )
+	{
+		contactCounts[i] = w->colorContacts[i].count;
+		jointCounts[i] = w->colorJoints[i].count;
+	}
+}
+static int copyIdList( HostWorld* hw, const Arr<int32_t>& a, int* out, int cap )
+{
+	World* w = hw->img;
+	for ( int i = 0; i < a.count && i < cap; ++i )
+		out[i] = ptr( w, a )[i];
+	return a.count;
+}
+int f2dDebug_ColorContacts( b2WorldId id, int colorIndex, int* contactIds, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	return copyIdList( hw, w->colorContacts[colorIndex], contactIds, cap );
+}
+int f2dDebug_AwakeContacts( b2WorldId id, int* contactIds, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	return copyIdList( hw, w->awakeContacts, contactIds, cap );
+}
+int f2dDebug_AwakeIslands( b2WorldId id, int* islandIds, int cap )
+{
+	HostWorld* hw = worldFromId( id );
+	if ( hw == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	return copyIdList( hw, w->awakeIslands, islandIds, cap );
+}
+
+} // extern "C"

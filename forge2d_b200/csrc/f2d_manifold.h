@@ -1,0 +1,717 @@
+// forge2d_b200 — narrowphase manifolds (one function per shape-pair class).
+//
+// Same SAT / clipping / closest-feature decisions and the same floating-point expression order as
+// B2/src/manifold.c (cited per function) so point counts, feature ids and anchors are bit-identical.
+#pragma once
+#include "f2d_types.h"
+
+namespace f2d
+{
+
+F2D_HD uint16_t makeFeatureId( int a, int b ) { return (uint16_t)( ( (uint8_t)a << 8 ) | (uint8_t)b ); } // manifold.c:14
+
+F2D_HD Manifold emptyManifold()
+{
+	Manifold m;
+	memset( &m, 0, sizeof( m ) );
+	return m;
+}
+
+// manifold.c:16-34
+F2D_HD Poly makeCapsulePoly( V2 p1, V2 p2, float radius )
+{
+	Poly s;
+	memset( &s, 0, sizeof( s ) );
+	s.v[0] = p1;
+	s.v[1] = p2;
+	s.centroid = lerp( p1, p2, 0.5f );
+	V2 d = sub( p2, p1 );
+	V2 axis = normalize( d );
+	V2 normal = rightPerp( axis );
+	s.n[0] = normal;
+	s.n[1] = neg( normal );
+	s.count = 2;
+	s.radius = radius;
+	return s;
+}
+
+// Writes the single world-space point shared by the circle-like manifolds (manifold.c:61-73, 126-138, ...)
+F2D_HD void finishSinglePoint( Manifold& m, Xf xfA, Xf xfB, V2 normalLocal, V2 contactPointA, float separation, bool pointOrderAnchorFirst )
+{
+	m.normal = rotate( xfA.q, normalLocal );
+	ManifoldPoint& mp = m.points[0];
+	mp.anchorA = rotate( xfA.q, contactPointA );
+	mp.anchorB = add( mp.anchorA, sub( xfA.p, xfB.p ) );
+	mp.point = pointOrderAnchorFirst ? add( mp.anchorA, xfA.p ) : add( xfA.p, mp.anchorA );
+	mp.separation = separation;
+	mp.id = 0;
+	m.pointCount = 1;
+}
+
+// manifold.c:40-74
+F2D_HDF inline Manifold collideCircles( const Circle& a, Xf xfA, const Circle& b, Xf xfB )
+{
+	Manifold m = emptyManifold();
+	Xf xf = invMulXf( xfA, xfB );
+	V2 pA = a.center;
+	V2 pB = xfPoint( xf, b.center );
+	float dist;
+	V2 normal = lengthAndNormalize( &dist, sub( pB, pA ) );
+	float rA = a.radius, rB = b.radius;
+	float separation = dist - rA - rB;
+	if ( separation > kSpeculative )
+		return m;
+	V2 cA = mulAdd( pA, rA, normal );
+	V2 cB = mulAdd( pB, -rB, normal );
+	V2 contact = lerp( cA, cB, 0.5f );
+	finishSinglePoint( m, xfA, xfB, normal, contact, separation, true );
+	return m;
+}
+
+// manifold.c:77-139
+F2D_HDF inline Manifold collideCapsuleAndCircle( const Capsule& a, Xf xfA, const Circle& b, Xf xfB )
+{
+	Manifold m = emptyManifold();
+	Xf xf = invMulXf( xfA, xfB );
+	V2 pB = xfPoint( xf, b.center );
+	V2 p1 = a.c1, p2 = a.c2;
+	V2 e = sub( p2, p1 );
+	V2 pA;
+	float s1 = dot( sub( pB, p1 ), e );
+	float s2 = dot( sub( p2, pB ), e );
+	if ( s1 < 0.0f )
+		pA = p1;
+	else if ( s2 < 0.0f )
+		pA = p2;
+	else
+	{
+		float s = s1 / dot( e, e );
+		pA = mulAdd( p1, s, e );
+	}
+	float dist;
+	V2 normal = lengthAndNormalize( &dist, sub( pB, pA ) );
+	float rA = a.radius, rB = b.radius;
+	float separation = dist - rA - rB;
+	if ( separation > kSpeculative )
+		return m;
+	V2 cA = mulAdd( pA, rA, normal );
+	V2 cB = mulAdd( pB, -rB, normal );
+	V2 contact = lerp( cA, cB, 0.5f );
+	finishSinglePoint( m, xfA, xfB, normal, contact, separation, false );
+	return m;
+}
+
+// manifold.c:141-257
+F2D_HDF inline Manifold collidePolygonAndCircle( const Poly& a, Xf xfA, const Circle& b, Xf xfB )
+{
+	Manifold m = emptyManifold();
+	Xf xf = invMulXf( xfA, xfB );
+	V2 center = xfPoint( xf, b.center );
+	float rA = a.radius, rB = b.radius;
+	float radius = rA + rB;
+
+	int normalIndex = 0;
+	float separation = -FLT_MAX;
+	int count = a.count;
+	for ( int i = 0; i < count; ++i )
+	{
+		float s = dot( a.n[i], sub( center, a.v[i] ) );
+		if ( s > separation )
+		{
+			separation = s;
+			normalIndex = i;
+		}
+	}
+	if ( separation > radius + kSpeculative )
+		return m;
+
+	int i1 = normalIndex;
+	int i2 = i1 + 1 < count ? i1 + 1 : 0;
+	V2 v1 = a.v[i1], v2 = a.v[i2];
+	float u1 = dot( sub( center, v1 ), sub( v2, v1 ) );
+	float u2 = dot( sub( center, v2 ), sub( v1, v2 ) );
+
+	if ( ( u1 < 0.0f && separation > FLT_EPSILON ) || ( u2 < 0.0f && separation > FLT_EPSILON ) )
+	{
+		// vertex region (v1 tested first, as in the reference's if / else-if)
+		V2 v = ( u1 < 0.0f && separation > FLT_EPSILON ) ? v1 : v2;
+		V2 normal = normalize( sub( center, v ) );
+		separation = dot( sub( center, v ), normal );
+		if ( separation > radius + kSpeculative )
+			return m;
+		V2 cA = mulAdd( v, rA, normal );
+		V2 cB = mulSub( center, rB, normal );
+		V2 contact = lerp( cA, cB, 0.5f );
+		finishSinglePoint( m, xfA, xfB, normal, contact, dot( sub( cB, cA ), normal ), false );
+	}
+	else
+	{
+		V2 normal = a.n[normalIndex];
+		V2 cA = mulAdd( center, rA - dot( sub( center, v1 ), normal ), normal );
+		V2 cB = mulSub( center, rB, normal );
+		V2 contact = lerp( cA, cB, 0.5f );
+		finishSinglePoint( m, xfA, xfB, normal, contact, separation - radius, false );
+	}
+	return m;
+}
+
+// Capsule-capsule with optional two-point clipping: manifold.c:261-530
+F2D_HDF inline Manifold collideCapsules( const Capsule& a, Xf xfA, const Capsule& b, Xf xfB )
+{
+	V2 origin = a.c1;
+	Xf sfA = { add( xfA.p, rotate( xfA.q, origin ) ), xfA.q };
+	Xf xf = invMulXf( sfA, xfB );
+
+	V2 p1 = { 0.0f, 0.0f };
+	V2 q1 = sub( a.c2, origin );
+	V2 p2 = xfPoint( xf, b.c1 );
+	V2 q2 = xfPoint( xf, b.c2 );
+
+	V2 d1 = sub( q1, p1 );
+	V2 d2 = sub( q2, p2 );
+	float dd1 = dot( d1, d1 );
+	float dd2 = dot( d2, d2 );
+	const float epsSqr = FLT_EPSILON * FLT_EPSILON;
+
+	V2 r = sub( p1, p2 );
+	float rd1 = dot( r, d1 );
+	float rd2 = dot( r, d2 );
+	float d12 = dot( d1, d2 );
+	float denom = dd1 * dd2 - d12 * d12;
+
+	float f1 = 0.0f;
+	if ( denom != 0.0f )
+		f1 = clampf( ( d12 * rd2 - rd1 * dd2 ) / denom, 0.0f, 1.0f );
+	float f2 = ( d12 * f1 + rd2 ) / dd2;
+	if ( f2 < 0.0f )
+	{
+		f2 = 0.0f;
+		f1 = clampf( -rd1 / dd1, 0.0f, 1.0f );
+	}
+	else if ( f2 > 1.0f )
+	{
+		f2 = 1.0f;
+		f1 = clampf( ( d12 - rd1 ) / dd1, 0.0f, 1.0f );
+	}
+
+	V2 closest1 = mulAdd( p1, f1, d1 );
+	V2 closest2 = mulAdd( p2, f2, d2 );
+	float distSq = distanceSq( closest1, closest2 );
+
+	Manifold m = emptyManifold();
+	float rA = a.radius, rB = b.radius;
+	float radius = rA + rB;
+	float maxDistance = radius + kSpeculative;
+	if ( distSq > maxDistance * maxDistance )
+		return m;
+
+	float dist = sqrtf( distSq );
+	float length1, length2;
+	V2 u1 = lengthAndNormalize( &length1, d1 );
+	V2 u2 = lengthAndNormalize( &length2, d2 );
+
+	float fp2 = dot( sub( p2, p1 ), u1 );
+	float fq2 = dot( sub( q2, p1 ), u1 );
+	bool outsideA = ( fp2 <= 0.0f && fq2 <= 0.0f ) || ( fp2 >= length1 && fq2 >= length1 );
+	float fp1 = dot( sub( p1, p2 ), u2 );
+	float fq1 = dot( sub( q1, p2 ), u2 );
+	bool outsideB = ( fp1 <= 0.0f && fq1 <= 0.0f ) || ( fp1 >= length2 && fq1 >= length2 );
+
+	if ( outsideA == false && outsideB == false )
+	{
+		V2 normalA;
+		float separationA;
+		{
+			normalA = leftPerp( u1 );
+			float ss1 = dot( sub( p2, p1 ), normalA );
+			float ss2 = dot( sub( q2, p1 ), normalA );
+			float s1p = ss1 < ss2 ? ss1 : ss2;
+			float s1n = -ss1 < -ss2 ? -ss1 : -ss2;
+			if ( s1p > s1n )
+				separationA = s1p;
+			else
+			{
+				separationA = s1n;
+				normalA = neg( normalA );
+			}
+		}
+		V2 normalB;
+		float separationB;
+		{
+			normalB = leftPerp( u2 );
+			float ss1 = dot( sub( p1, p2 ), normalB );
+			float ss2 = dot( sub( q1, p2 ), normalB );
+			float s1p = ss1 < ss2 ? ss1 : ss2;
+			float s1n = -ss1 < -ss2 ? -ss1 : -ss2;
+			if ( s1p > s1n )
+				separationB = s1p;
+			else
+			{
+				separationB = s1n;
+				normalB = neg( normalB );
+			}
+		}
+
+		if ( separationA + 0.1f * kLinearSlop >= separationB )
+		{
+			m.normal = normalA;
+			V2 cp = p2, cq = q2;
+			if ( fp2 < 0.0f && fq2 > 0.0f )
+				cp = lerp( p2, q2, ( 0.0f - fp2 ) / ( fq2 - fp2 ) );
+			else if ( fq2 < 0.0f && fp2 > 0.0f )
+				cq = lerp( q2, p2, ( 0.0f - fq2 ) / ( fp2 - fq2 ) );
+			if ( fp2 > length1 && fq2 < length1 )
+				cp = lerp( p2, q2, ( fp2 - length1 ) / ( fp2 - fq2 ) );
+			else if ( fq2 > length1 && fp2 < length1 )
+				cq = lerp( q2, p2, ( fq2 - length1 ) / ( fq2 - fp2 ) );
+			float sp = dot( sub( cp, p1 ), normalA );
+			float sq = dot( sub( cq, p1 ), normalA );
+			if ( sp <= dist + kLinearSlop || sq <= dist + kLinearSlop )
+			{
+				ManifoldPoint* mp = m.points + 0;
+				mp->anchorA = mulAdd( cp, 0.5f * ( rA - rB - sp ), normalA );
+				mp->separation = sp - radius;
+				mp->id = makeFeatureId( 0, 0 );
+				mp = m.points + 1;
+				mp->anchorA = mulAdd( cq, 0.5f * ( rA - rB - sq ), normalA );
+				mp->separation = sq - radius;
+				mp->id = makeFeatureId( 0, 1 );
+				m.pointCount = 2;
+			}
+		}
+		else
+		{
+			m.normal = neg( normalB );
+			V2 cp = p1, cq = q1;
+			if ( fp1 < 0.0f && fq1 > 0.0f )
+				cp = lerp( p1, q1, ( 0.0f - fp1 ) / ( fq1 - fp1 ) );
+			else if ( fq1 < 0.0f && fp1 > 0.0f )
+				cq = lerp( q1, p1, ( 0.0f - fq1 ) / ( fp1 - fq1 ) );
+			if ( fp1 > length2 && fq1 < length2 )
+				cp = lerp( p1, q1, ( fp1 - length2 ) / ( fp1 - fq1 ) );
+			else if ( fq1 > length2 && fp1 < length2 )
+				cq = lerp( q1, p1, ( fq1 - length2 ) / ( fq1 - fp1 ) );
+			float sp = dot( sub( cp, p2 ), normalB );
+			float sq = dot( sub( cq, p2 ), normalB );
+			if ( sp <= dist + kLinearSlop || sq <= dist + kLinearSlop )
+			{
+				ManifoldPoint* mp = m.points + 0;
+				mp->anchorA = mulAdd( cp, 0.5f * ( rB - rA - sp ), normalB );
+				mp->separation = sp - radius;
+				mp->id = makeFeatureId( 0, 0 );
+				mp = m.points + 1;
+				mp->anchorA = mulAdd( cq, 0.5f * ( rB - rA - sq ), normalB );
+				mp->separation = sq - radius;
+				mp->id = makeFeatureId( 1, 0 );
+				m.pointCount = 2;
+			}
+		}
+	}
+
+	if ( m.pointCount == 0 )
+	{
+		V2 normal = sub( closest2, closest1 );
+		if ( dot( normal, normal ) > epsSqr )
+			normal = normalize( normal );
+		else
+			normal = leftPerp( u1 );
+		V2 c1 = mulAdd( closest1, rA, normal );
+		V2 c2 = mulAdd( closest2, -rB, normal );
+		int i1 = f1 == 0.0f ? 0 : 1;
+		int i2 = f2 == 0.0f ? 0 : 1;
+		m.normal = normal;
+		m.points[0].anchorA = lerp( c1, c2, 0.5f );
+		m.points[0].separation = sqrtf( distSq ) - radius;
+		m.points[0].id = makeFeatureId( i1, i2 );
+		m.pointCount = 1;
+	}
+
+	m.normal = rotate( xfA.q, m.normal );
+	for ( int i = 0; i < m.pointCount; ++i )
+	{
+		ManifoldPoint* mp = m.points + i;
+		mp->anchorA = rotate( xfA.q, add( mp->anchorA, origin ) );
+		mp->anchorB = add( mp->anchorA, sub( xfA.p, xfB.p ) );
+		mp->point = add( xfA.p, mp->anchorA );
+	}
+	return m;
+}
+
+// Segment distance (Ericson 5.1.9): B2/src/distance.c:33-106
+struct SegmentDistance
+{
+	V2 closest1, closest2;
+	float fraction1, fraction2, distanceSquared;
+};
+F2D_HDF inline SegmentDistance segmentDistance( V2 p1, V2 q1, V2 p2, V2 q2 )
+{
+	SegmentDistance res;
+	V2 d1 = sub( q1, p1 );
+	V2 d2 = sub( q2, p2 );
+	V2 r = sub( p1, p2 );
+	float dd1 = dot( d1, d1 );
+	float dd2 = dot( d2, d2 );
+	float rd1 = dot( r, d1 );
+	float rd2 = dot( r, d2 );
+	const float epsSqr = FLT_EPSILON * FLT_EPSILON;
+	if ( dd1 < epsSqr || dd2 < epsSqr )
+	{
+		if ( dd1 >= epsSqr )
+		{
+			res.fraction1 = clampf( -rd1 / dd1, 0.0f, 1.0f );
+			res.fraction2 = 0.0f;
+		}
+		else if ( dd2 >= epsSqr )
+		{
+			res.fraction1 = 0.0f;
+			res.fraction2 = clampf( rd2 / dd2, 0.0f, 1.0f );
+		}
+		else
+		{
+			res.fraction1 = 0.0f;
+			res.fraction2 = 0.0f;
+		}
+	}
+	else
+	{
+		float d12 = dot( d1, d2 );
+		float denominator = dd1 * dd2 - d12 * d12;
+		float f1 = 0.0f;
+		if ( denominator != 0.0f )
+			f1 = clampf( ( d12 * rd2 - rd1 * dd2 ) / denominator, 0.0f, 1.0f );
+		float f2 = ( d12 * f1 + rd2 ) / dd2;
+		if ( f2 < 0.0f )
+		{
+			f2 = 0.0f;
+			f1 = clampf( -rd1 / dd1, 0.0f, 1.0f );
+		}
+		else if ( f2 > 1.0f )
+		{
+			f2 = 1.0f;
+			f1 = clampf( ( d12 - rd1 ) / dd1, 0.0f, 1.0f );
+		}
+		res.fraction1 = f1;
+		res.fraction2 = f2;
+	}
+	res.closest1 = mulAdd( p1, res.fraction1, d1 );
+	res.closest2 = mulAdd( p2, res.fraction2, d2 );
+	res.distanceSquared = distanceSq( res.closest1, res.closest2 );
+	return res;
+}
+
+// Reference-edge / incident-edge clipping: manifold.c:545-677
+F2D_HDF inline Manifold clipPolygons( const Poly& polyA, const Poly& polyB, int edgeA, int edgeB, bool flip )
+{
+	Manifold m = emptyManifold();
+	const Poly* poly1;
+	const Poly* poly2;
+	int i11, i12, i21, i22;
+	if ( flip )
+	{
+		poly1 = &polyB;
+		poly2 = &polyA;
+		i11 = edgeB;
+		i12 = edgeB + 1 < polyB.count ? edgeB + 1 : 0;
+		i21 = edgeA;
+		i22 = edgeA + 1 < polyA.count ? edgeA + 1 : 0;
+	}
+	else
+	{
+		poly1 = &polyA;
+		poly2 = &polyB;
+		i11 = edgeA;
+		i12 = edgeA + 1 < polyA.count ? edgeA + 1 : 0;
+		i21 = edgeB;
+		i22 = edgeB + 1 < polyB.count ? edgeB + 1 : 0;
+	}
+	V2 normal = poly1->n[i11];
+	V2 v11 = poly1->v[i11], v12 = poly1->v[i12];
+	V2 v21 = poly2->v[i21], v22 = poly2->v[i22];
+	V2 tangent = crossSV( 1.0f, normal );
+
+	float lower1 = 0.0f;
+	float upper1 = dot( sub( v12, v11 ), tangent );
+	float upper2 = dot( sub( v21, v11 ), tangent );
+	float lower2 = dot( sub( v22, v11 ), tangent );
+	if ( upper2 < lower1 || upper1 < lower2 )
+		return m;
+
+	V2 vLower;
+	if ( lower2 < lower1 && upper2 - lower2 > FLT_EPSILON )
+		vLower = lerp( v22, v21, ( lower1 - lower2 ) / ( upper2 - lower2 ) );
+	else
+		vLower = v22;
+	V2 vUpper;
+	if ( upper2 > upper1 && upper2 - lower2 > FLT_EPSILON )
+		vUpper = lerp( v22, v21, ( upper1 - lower2 ) / ( upper2 - lower2 ) );
+	else
+		vUpper = v21;
+
+	float separationLower = dot( sub( vLower, v11 ), normal );
+	float separationUpper = dot( sub( vUpper, v11 ), normal );
+	float r1 = poly1->radius, r2 = poly2->radius;
+	vLower = mulAdd( vLower, 0.5f * ( r1 - r2 - separationLower ), normal );
+	vUpper = mulAdd( vUpper, 0.5f * ( r1 - r2 - separationUpper ), normal );
+	float radius = r1 + r2;
+
+	if ( flip == false )
+	{
+		m.normal = normal;
+		m.points[0].anchorA = vLower;
+		m.points[0].separation = separationLower - radius;
+		m.points[0].id = makeFeatureId( i11, i22 );
+		m.points[1].anchorA = vUpper;
+		m.points[1].separation = separationUpper - radius;
+		m.points[1].id = makeFeatureId( i12, i21 );
+		m.pointCount = 2;
+	}
+	else
+	{
+		m.normal = neg( normal );
+		m.points[0].anchorA = vUpper;
+		m.points[0].separation = separationUpper - radius;
+		m.points[0].id = makeFeatureId( i21, i12 );
+		m.points[1].anchorA = vLower;
+		m.points[1].separation = separationLower - radius;
+		m.points[1].id = makeFeatureId( i22, i11 );
+		m.pointCount = 2;
+	}
+	return m;
+}
+
+// manifold.c:680-716
+F2D_HDF inline float findMaxSeparation( int* edgeIndex, const Poly& poly1, const Poly& poly2 )
+{
+	int count1 = poly1.count, count2 = poly2.count;
+	int bestIndex = 0;
+	float maxSeparation = -FLT_MAX;
+	for ( int i = 0; i < count1; ++i )
+	{
+		V2 n = poly1.n[i];
+		V2 v1 = poly1.v[i];
+		float si = FLT_MAX;
+		for ( int j = 0; j < count2; ++j )
+		{
+			float sij = dot( n, sub( poly2.v[j], v1 ) );
+			if ( sij < si )
+				si = sij;
+		}
+		if ( si > maxSeparation )
+		{
+			maxSeparation = si;
+			bestIndex = i;
+		}
+	}
+	*edgeIndex = bestIndex;
+	return maxSeparation;
+}
+
+// manifold.c:736-1075
+F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Poly& polygonB, Xf xfB )
+{
+	V2 origin = polygonA.v[0];
+	Xf sfA = { add( xfA.p, rotate( xfA.q, origin ) ), xfA.q };
+	Xf xf = invMulXf( sfA, xfB );
+
+	Poly localA;
+	localA.count = polygonA.count;
+	localA.radius = polygonA.radius;
+	localA.v[0] = V2{ 0.0f, 0.0f };
+	localA.n[0] = polygonA.n[0];
+	for ( int i = 1; i < localA.count; ++i )
+	{
+		localA.v[i] = sub( polygonA.v[i], origin );
+		localA.n[i] = polygonA.n[i];
+	}
+	Poly localB;
+	localB.count = polygonB.count;
+	localB.radius = polygonB.radius;
+	for ( int i = 0; i < localB.count; ++i )
+	{
+		localB.v[i] = xfPoint( xf, polygonB.v[i] );
+		localB.n[i] = rotate( xf.q, polygonB.n[i] );
+	}
+
+	int edgeA = 0;
+	float separationA = findMaxSeparation( &edgeA, localA, localB );
+	int edgeB = 0;
+	float separationB = findMaxSeparation( &edgeB, localB, localA );
+	float radius = localA.radius + localB.radius;
+	if ( separationA > kSpeculative + radius || separationB > kSpeculative + radius )
+		return emptyManifold();
+
+	bool flip;
+	if ( separationA >= separationB )
+	{
+		flip = false;
+		V2 searchDirection = localA.n[edgeA];
+		int count = localB.count;
+		edgeB = 0;
+		float minDot = FLT_MAX;
+		for ( int i = 0; i < count; ++i )
+		{
+			float d = dot( searchDirection, localB.n[i] );
+			if ( d < minDot )
+			{
+				minDot = d;
+				edgeB = i;
+			}
+		}
+	}
+	else
+	{
+		flip = true;
+		V2 searchDirection = localB.n[edgeB];
+		int count = localA.count;
+		edgeA = 0;
+		float minDot = FLT_MAX;
+		for ( int i = 0; i < count; ++i )
+		{
+			float d = dot( searchDirection, localA.n[i] );
+			if ( d < minDot )
+			{
+				minDot = d;
+				edgeA = i;
+			}
+		}
+	}
+
+	Manifold m = emptyManifold();
+	if ( separationA > 0.1f * kLinearSlop || separationB > 0.1f * kLinearSlop )
+	{
+		int i11 = edgeA;
+		int i12 = edgeA + 1 < localA.count ? edgeA + 1 : 0;
+		int i21 = edgeB;
+		int i22 = edgeB + 1 < localB.count ? edgeB + 1 : 0;
+		V2 v11 = localA.v[i11], v12 = localA.v[i12];
+		V2 v21 = localB.v[i21], v22 = localB.v[i22];
+
+		SegmentDistance result = segmentDistance( v11, v12, v21, v22 );
+		float dist = sqrtf( result.distanceSquared );
+		float separation = dist - radius;
+		if ( dist - radius > kSpeculative )
+			return m;
+
+		m = clipPolygons( localA, localB, edgeA, edgeB, flip );
+		float minSeparation = FLT_MAX;
+		for ( int i = 0; i < m.pointCount; ++i )
+			minSeparation = minf( minSeparation, m.points[i].separation );
+
+		if ( separation + 0.1f * kLinearSlop < minSeparation )
+		{
+			// vertex-vertex: pick the pair of end points the segment distance landed on (manifold.c:870-937)
+			bool f10 = result.fraction1 == 0.0f, f11 = result.fraction1 == 1.0f;
+			bool f20 = result.fraction2 == 0.0f, f21 = result.fraction2 == 1.0f;
+			if ( ( f10 || f11 ) && ( f20 || f21 ) )
+			{
+				V2 va = f10 ? v11 : v12;
+				V2 vb = f20 ? v21 : v22;
+				int ia = f10 ? i11 : i12;
+				int ib = f20 ? i21 : i22;
+				V2 normal = sub( vb, va );
+				float invDistance = 1.0f / dist;
+				normal.x *= invDistance;
+				normal.y *= invDistance;
+				V2 c1 = mulAdd( va, localA.radius, normal );
+				V2 c2 = mulAdd( vb, -localB.radius, normal );
+				m.normal = normal;
+				m.points[0].anchorA = lerp( c1, c2, 0.5f );
+				m.points[0].separation = dist - radius;
+				m.points[0].id = makeFeatureId( ia, ib );
+				m.pointCount = 1;
+			}
+		}
+	}
+	else
+	{
+		m = clipPolygons( localA, localB, edgeA, edgeB, flip );
+	}
+
+	if ( m.pointCount > 0 )
+	{
+		m.normal = rotate( xfA.q, m.normal );
+		for ( int i = 0; i < m.pointCount; ++i )
+		{
+			ManifoldPoint* mp = m.points + i;
+			mp->anchorA = rotate( xfA.q, add( mp->anchorA, origin ) );
+			mp->anchorB = add( mp->anchorA, sub( xfA.p, xfB.p ) );
+			mp->point = add( xfA.p, mp->anchorA );
+		}
+	}
+	return m;
+}
+
+// Dispatch on the (primary-ordered) shape-type pair: B2/src/contact.c:166-184 registers.
+// Returns false when the pair has no manifold function (e.g. segment vs segment).
+F2D_HD bool pairHasManifold( int typeA, int typeB )
+{
+	if ( typeA == kChainSegment || typeB == kChainSegment )
+	{
+		int other = typeA == kChainSegment ? typeB : typeA;
+		return other == kCircle || other == kCapsule || other == kPolygon;
+	}
+	if ( typeA == kSegment && typeB == kSegment )
+		return false;
+	return true;
+}
+// primary[type1][type2] == true when (type1,type2) is the registered order (contact.c:151-164)
+F2D_HD bool pairIsPrimary( int t1, int t2 )
+{
+	if ( t1 == t2 )
+		return true;
+	// registered primaries: capsule-circle, polygon-circle, polygon-capsule, segment-{circle,capsule,polygon},
+	// chainSegment-{circle,capsule,polygon}
+	if ( t1 == kCapsule && t2 == kCircle )
+		return true;
+	if ( t1 == kPolygon && ( t2 == kCircle || t2 == kCapsule ) )
+		return true;
+	if ( t1 == kSegment && ( t2 == kCircle || t2 == kCapsule || t2 == kPolygon ) )
+		return true;
+	if ( t1 == kChainSegment && ( t2 == kCircle || t2 == kCapsule || t2 == kPolygon ) )
+		return true;
+	return false;
+}
+
+F2D_HDF inline Manifold computeManifold( World* w, const Shape& a, Xf xfA, const Shape& b, Xf xfB, SimplexCache* cache )
+{
+	(void)cache;
+	switch ( a.type )
+	{
+		case kCircle:
+			return collideCircles( a.circle, xfA, b.circle, xfB );
+		case kCapsule:
+			if ( b.type == kCircle )
+				return collideCapsuleAndCircle( a.capsule, xfA, b.circle, xfB );
+			return collideCapsules( a.capsule, xfA, b.capsule, xfB );
+		case kPolygon:
+			if ( b.type == kCircle )
+				return collidePolygonAndCircle( a.polygon, xfA, b.circle, xfB );
+			if ( b.type == kCapsule )
+			{
+				Poly polyB = makeCapsulePoly( b.capsule.c1, b.capsule.c2, b.capsule.radius ); // manifold.c:538-542
+				return collidePolygons( a.polygon, xfA, polyB, xfB );
+			}
+			return collidePolygons( a.polygon, xfA, b.polygon, xfB );
+		case kSegment:
+		{
+			if ( b.type == kCircle )
+			{
+				Capsule capA = { a.segment.p1, a.segment.p2, 0.0f }; // manifold.c:1077-1081
+				return collideCapsuleAndCircle( capA, xfA, b.circle, xfB );
+			}
+			if ( b.type == kCapsule )
+			{
+				Capsule capA = { a.segment.p1, a.segment.p2, 0.0f }; // manifold.c:532-536
+				return collideCapsules( capA, xfA, b.capsule, xfB );
+			}
+			Poly polyA = makeCapsulePoly( a.segment.p1, a.segment.p2, 0.0f ); // manifold.c:1083-1087
+			return collidePolygons( polyA, xfA, b.polygon, xfB );
+		}
+		default:
+			// chain segments: not on the device path yet
+			setError( w, kErrUnsupported, __LINE__ );
+			return emptyManifold();
+	}
+}
+
+} // namespace f2d

@@ -1,0 +1,1180 @@
+// forge2d_b200 — the world step as team-parallel phases.
+//
+// Phase order and every serial ordering decision follow b2World_Step (B2/src/world.c:695-812):
+//   stepBegin      clear per-step event arrays / scratch bits                        world.c:709-712
+//   stepPairs      broadphase pair finding + ordered contact creation                broad_phase.c:311-474
+//   stepCollide    tree rebuild | narrowphase | ordered contact-state pass           world.c:488-693
+//   stepSolve      island merge/split, prepare, substep loop, restitution, store     solver.c:1190-1720, :929-1106
+//   stepFinalize   body finalize + continuous, hit events, proxy enlarge, sleep      solver.c:543-726, :1758-2051
+// Parallel loops are `rank()/size()` strided; rank 0 executes the reference's serial sections.
+#pragma once
+#include "f2d_distance.h"
+#include "f2d_joint.h"
+#include "f2d_solver.h"
+
+namespace f2d
+{
+
+// ------------------------------------------------------------------------------------------------ begin
+template <class Team> F2D_HDF inline void stepBegin( World* w, Team& t, float dt, int subStepCount )
+{
+	if ( t.rank() == 0 )
+	{
+		w->moveEvents.count = 0;
+		w->sensorBeginEvents.count = 0;
+		w->beginEvents.count = 0;
+		w->hitEvents.count = 0;
+		w->taskCount = 0;
+		w->locked = true;
+
+		// step context: world.c:742-771
+		StepCtx& s = w->step;
+		s.dt = dt;
+		s.subStepCount = maxi( 1, subStepCount );
+		if ( dt > 0.0f )
+		{
+			s.inv_dt = 1.0f / dt;
+			s.h = dt / s.subStepCount;
+			s.inv_h = s.subStepCount * s.inv_dt;
+		}
+		else
+		{
+			s.inv_dt = 0.0f;
+			s.h = 0.0f;
+			s.inv_h = 0.0f;
+		}
+		w->inv_h = s.inv_h;
+		float contactHertz = minf( w->contactHertz, 0.125f * s.inv_h );
+		s.contactSoftness = makeSoft( contactHertz, w->contactDampingRatio, s.h );
+		s.staticSoftness = makeSoft( 2.0f * contactHertz, w->contactDampingRatio, s.h );
+		w->contactSpeed = w->maxContactPushSpeed / s.staticSoftness.massScale;
+		s.restitutionThreshold = w->restitutionThreshold;
+		s.maxLinearVelocity = w->maxLinearSpeed;
+		s.enableWarmStarting = w->enableWarmStarting ? 1 : 0;
+		s.pairCount = 0;
+		s.bulletCount = 0;
+		s.splitKey = 0;
+	}
+	// contact-state bits are cleared here so the narrowphase can set them right after the tree rebuild starts
+	uint64_t* bits = ptr( w, w->contactBits );
+	for ( int i = t.rank(); i < w->contactBits.cap; i += t.size() )
+		bits[i] = 0;
+	t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ pairs
+// body.c:1861-1895
+F2D_HDF inline bool shouldBodiesCollide( World* w, const Body& bodyA, const Body& bodyB )
+{
+	if ( bodyA.type != kDynamicBody && bodyB.type != kDynamicBody )
+		return false;
+	int jointKey, otherBodyId;
+	if ( bodyA.jointCount < bodyB.jointCount )
+	{
+		jointKey = bodyA.headJointKey;
+		otherBodyId = bodyB.id;
+	}
+	else
+	{
+		jointKey = bodyB.headJointKey;
+		otherBodyId = bodyA.id;
+	}
+	const Joint* joints = ptr( w, w->joints );
+	while ( jointKey != kNull )
+	{
+		int jointId = jointKey >> 1;
+		int edgeIndex = jointKey & 1;
+		const Joint& joint = joints[jointId];
+		if ( joint.collideConnected == false && joint.edges[edgeIndex ^ 1].bodyId == otherBodyId )
+			return false;
+		jointKey = joint.edges[edgeIndex].nextKey;
+	}
+	return true;
+}
+
+// Is there already a contact between these two shapes? Replaces the reference's pairSet hash lookup
+// (broad_phase.c:215-220): a contact for the pair exists iff it hangs off both bodies' contact lists.
+F2D_HDF inline bool pairExists( World* w, const Body& bodyA, const Body& bodyB, int shapeIdA, int shapeIdB )
+{
+	const Contact* contacts = ptr( w, w->contacts );
+	int key = bodyA.contactCount < bodyB.contactCount ? bodyA.headContactKey : bodyB.headContactKey;
+	while ( key != kNull )
+	{
+		const Contact& c = contacts[key >> 1];
+		if ( ( c.shapeIdA == shapeIdA && c.shapeIdB == shapeIdB ) || ( c.shapeIdA == shapeIdB && c.shapeIdB == shapeIdA ) )
+			return true;
+		key = c.edges[key & 1].nextKey;
+	}
+	return false;
+}
+
+// One moved proxy: queries in the reference's tree order and filter order (broad_phase.c:160-302, 311-374)
+F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
+{
+	int32_t* heads = ptr( w, w->moveHeads );
+	heads[moveIndex] = kNull;
+	int queryKey = ptr( w, w->moveArray )[moveIndex];
+	if ( queryKey == kNull )
+		return;
+	int queryType = proxyType( queryKey );
+	int queryProxy = proxyId( queryKey );
+	const TreeNode& queryNode = ptr( w, w->trees[queryType].nodes )[queryProxy];
+	Box fat = queryNode.box;
+	int queryShape = (int)queryNode.userData;
+	const Shape* shapes = ptr( w, w->shapes );
+	const Body* bodies = ptr( w, w->bodies );
+	MovePair* pairs = ptr( w, w->movePairs );
+
+	for ( int pass = 0; pass < 3; ++pass )
+	{
+		int treeType;
+		if ( queryType == kDynamicBody )
+			treeType = pass == 0 ? kKinematicBody : ( pass == 1 ? kStaticBody : kDynamicBody );
+		else
+		{
+			if ( pass != 2 )
+				continue;
+			treeType = kDynamicBody;
+		}
+		const Tree& tree = w->trees[treeType];
+		const TreeNode* treeNodes = ptr( w, tree.nodes );
+		treeQuery( w, tree, fat, UINT64_MAX, [&]( int proxy, uint64_t userData ) -> bool {
+			int shapeId = (int)userData;
+			int key = proxyKey( proxy, treeType );
+			if ( key == queryKey )
+				return true;
+			// both proxies moved: the pair belongs to exactly one of the two queries
+			if ( queryType == kDynamicBody )
+			{
+				if ( treeType == kDynamicBody && key < queryKey )
+				{
+					if ( treeNodes[proxy].flags & kNodeMoved )
+						return true;
+				}
+			}
+			else
+			{
+				if ( treeNodes[proxy].flags & kNodeMoved )
+					return true;
+			}
+			int shapeIdA, shapeIdB;
+			if ( key < queryKey )
+			{
+				shapeIdA = shapeId;
+				shapeIdB = queryShape;
+			}
+			else
+			{
+				shapeIdA = queryShape;
+				shapeIdB = shapeId;
+			}
+			const Shape& shapeA = shapes[shapeIdA];
+			const Shape& shapeB = shapes[shapeIdB];
+			const Body& bodyA = bodies[shapeA.bodyId];
+			const Body& bodyB = bodies[shapeB.bodyId];
+			if ( pairExists( w, bodyA, bodyB, shapeIdA, shapeIdB ) )
+				return true;
+			if ( shapeA.bodyId == shapeB.bodyId )
+				return true;
+			if ( shapeA.sensorIndex != kNull || shapeB.sensorIndex != kNull )
+				return true;
+			if ( shouldShapesCollide( shapeA.filter, shapeB.filter ) == false )
+				return true;
+			if ( shouldBodiesCollide( w, bodyA, bodyB ) == false )
+				return true;
+			int pairIndex = atomAdd( &w->step.pairCount, 1 );
+			if ( pairIndex >= w->movePairs.cap )
+			{
+				setError( w, kErrCapacity, __LINE__ );
+				return true;
+			}
+			MovePair& p = pairs[pairIndex];
+			p.shapeA = shapeIdA;
+			p.shapeB = shapeIdB;
+			p.next = heads[moveIndex]; // push-front: creation order is the reverse of hit order
+			heads[moveIndex] = pairIndex;
+			return true;
+		} );
+	}
+}
+
+template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
+{
+	int moveCount = w->moveArray.count;
+	if ( moveCount == 0 )
+		return;
+	if ( moveCount > w->moveHeads.cap )
+	{
+		if ( t.rank() == 0 )
+			setError( w, kErrCapacity, __LINE__ );
+		return;
+	}
+	for ( int i = t.rank(); i < moveCount; i += t.size() )
+		findPairsForProxy( w, i );
+	t.sync();
+	if ( t.rank() == 0 )
+	{
+		const int32_t* heads = ptr( w, w->moveHeads );
+		const MovePair* pairs = ptr( w, w->movePairs );
+		const int32_t* moves = ptr( w, w->moveArray );
+		for ( int i = 0; i < moveCount; ++i )
+		{
+			for ( int p = heads[i]; p != kNull; p = pairs[p].next )
+				createContact( w, pairs[p].shapeA, pairs[p].shapeB );
+		}
+		// reset move buffer (broad_phase.c:460-462)
+		for ( int i = 0; i < moveCount; ++i )
+		{
+			int key = moves[i];
+			if ( key != kNull )
+				ptr( w, w->trees[proxyType( key )].nodes )[proxyId( key )].flags &= (uint16_t)~kNodeMoved;
+		}
+		w->moveArray.count = 0;
+	}
+	t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ collide
+// world.c:357-445, one contact
+F2D_HDF inline void collideContact( World* w, int contactId )
+{
+	ContactSim& sim = ptr( w, w->contactSims )[contactId];
+	const Shape* shapes = ptr( w, w->shapes );
+	const Shape& shapeA = shapes[sim.shapeIdA];
+	const Shape& shapeB = shapes[sim.shapeIdB];
+	uint64_t* bits = ptr( w, w->contactBits );
+	bool overlap = boxOverlaps( shapeA.fatAABB, shapeB.fatAABB );
+	if ( overlap == false )
+	{
+		sim.simFlags |= kSimDisjoint;
+		sim.simFlags &= ~kSimTouching;
+		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+		return;
+	}
+	bool wasTouching = ( sim.simFlags & kSimTouching ) != 0;
+	const Body* bodies = ptr( w, w->bodies );
+	const BodySim* sims = ptr( w, w->sims );
+	const Body& bodyA = bodies[shapeA.bodyId];
+	const Body& bodyB = bodies[shapeB.bodyId];
+	const BodySim& simA = sims[shapeA.bodyId];
+	const BodySim& simB = sims[shapeB.bodyId];
+	sim.bodySimIndexA = bodyA.setIndex == kAwakeSet ? bodyA.localIndex : kNull;
+	sim.invMassA = simA.invMass;
+	sim.invIA = simA.invInertia;
+	sim.bodySimIndexB = bodyB.setIndex == kAwakeSet ? bodyB.localIndex : kNull;
+	sim.invMassB = simB.invMass;
+	sim.invIB = simB.invInertia;
+	Xf xfA = simA.transform, xfB = simB.transform;
+	V2 centerOffsetA = rotate( xfA.q, simA.localCenter );
+	V2 centerOffsetB = rotate( xfB.q, simB.localCenter );
+	bool touching = updateContact( w, sim, shapeA, xfA, centerOffsetA, shapeB, xfB, centerOffsetB );
+	if ( touching == true && wasTouching == false )
+	{
+		sim.simFlags |= kSimStartedTouching;
+		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+	}
+	else if ( touching == false && wasTouching == true )
+	{
+		sim.simFlags |= kSimStoppedTouching;
+		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+	}
+}
+
+// Ordered contact-state pass, ascending contact id: world.c:587-686
+F2D_HDF inline void contactStatePass( World* w )
+{
+	const uint64_t* bits = ptr( w, w->contactBits );
+	int wordCount = ( w->contactIds.next + 63 ) >> 6;
+	if ( wordCount > w->contactBits.cap )
+		wordCount = w->contactBits.cap;
+	Contact* contacts = ptr( w, w->contacts );
+	ContactSim* sims = ptr( w, w->contactSims );
+	const Shape* shapes = ptr( w, w->shapes );
+	for ( int k = 0; k < wordCount; ++k )
+	{
+		uint64_t word = bits[k];
+		while ( word != 0 )
+		{
+			int bit = 0;
+			{
+				uint64_t tmp = word;
+				while ( ( tmp & 1ull ) == 0 )
+				{
+					tmp >>= 1;
+					bit += 1;
+				}
+			}
+			int contactId = 64 * k + bit;
+			Contact& c = contacts[contactId];
+			ContactSim& sim = sims[contactId];
+			int colorIndex = c.colorIndex;
+			int localIndex = c.localIndex;
+			const Shape& shapeA = shapes[c.shapeIdA];
+			const Shape& shapeB = shapes[c.shapeIdB];
+			uint32_t flags = c.flags;
+			uint32_t simFlags = sim.simFlags;
+
+			if ( simFlags & kSimDisjoint )
+			{
+				destroyContact( w, contactId, false );
+			}
+			else if ( simFlags & kSimStartedTouching )
+			{
+				if ( flags & kContactEnableContactEvents )
+				{
+					BeginTouchEvent ev;
+					ev.a = makeShapeId( w, shapeA );
+					ev.b = makeShapeId( w, shapeB );
+					ev.manifold = sim.manifold;
+					F2D_PUSH( w, w->beginEvents, ev );
+				}
+				c.flags |= kContactTouching;
+				linkContact( w, c );
+				sim.simFlags &= ~kSimStartedTouching;
+				addContactToGraph( w, contactId );
+				// remove from the awake non-touching list (world.c:472-485); c.localIndex now is the colour slot
+				int moved = removeSwap( w, w->awakeContacts, localIndex );
+				if ( moved != kNull )
+					contacts[ptr( w, w->awakeContacts )[localIndex]].localIndex = localIndex;
+			}
+			else if ( simFlags & kSimStoppedTouching )
+			{
+				sim.simFlags &= ~kSimStoppedTouching;
+				c.flags &= ~kContactTouching;
+				if ( c.flags & kContactEnableContactEvents )
+				{
+					EndTouchEvent ev = { makeShapeId( w, shapeA ), makeShapeId( w, shapeB ) };
+					F2D_PUSH( w, w->endEvents[w->endEventArrayIndex], ev );
+				}
+				unlinkContact( w, c );
+				int bodyIdA = c.edges[0].bodyId;
+				int bodyIdB = c.edges[1].bodyId;
+				// back to the awake non-touching list (world.c:461-470)
+				c.colorIndex = kNull;
+				c.localIndex = w->awakeContacts.count;
+				F2D_PUSH( w, w->awakeContacts, contactId );
+				removeContactFromGraph( w, bodyIdA, bodyIdB, colorIndex, localIndex );
+			}
+			word = word & ( word - 1 );
+		}
+	}
+}
+
+template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
+{
+	// work list = colour 0..11 lists then the awake non-touching list (world.c:504-542)
+	int segBase[kColorCount + 2];
+	int total = 0;
+	for ( int i = 0; i < kColorCount; ++i )
+	{
+		segBase[i] = total;
+		total += w->colorContacts[i].count;
+	}
+	segBase[kColorCount] = total;
+	total += w->awakeContacts.count;
+	segBase[kColorCount + 1] = total;
+
+	// rank 0 rebuilds the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492) while the other ranks
+	// run the narrowphase; with a one-thread team both happen in sequence.
+	int workers = t.size() > 1 ? t.size() - 1 : 1;
+	int me = t.size() > 1 ? t.rank() - 1 : 0;
+	if ( t.rank() == 0 )
+	{
+		treeRebuild( w, w->trees[kDynamicBody], false );
+		treeRebuild( w, w->trees[kKinematicBody], false );
+	}
+	if ( t.size() == 1 || t.rank() > 0 )
+	{
+		for ( int i = me; i < total; i += workers )
+		{
+			int seg = 0;
+			while ( i >= segBase[seg + 1] )
+				seg += 1;
+			const Arr<int32_t>& list = seg < kColorCount ? w->colorContacts[seg] : w->awakeContacts;
+			int contactId = ptr( w, list )[i - segBase[seg]];
+			collideContact( w, contactId );
+		}
+	}
+	t.sync();
+	if ( t.rank() == 0 )
+		contactStatePass( w );
+	t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ solve
+// solver.c:65-129
+F2D_HDF inline void integrateVelocity( World* w, int awakeIndex, float h, float maxLinearSpeed, float maxAngularSpeed )
+{
+	BodyState& state = ptr( w, w->states )[awakeIndex];
+	BodySim& sim = ptr( w, w->sims )[ptr( w, w->awakeBodies )[awakeIndex]];
+	V2 v = state.v;
+	float wv = state.w;
+	float maxLinearSpeedSquared = maxLinearSpeed * maxLinearSpeed;
+	float maxAngularSpeedSquared = maxAngularSpeed * maxAngularSpeed;
+	float linearDamping = 1.0f / ( 1.0f + h * sim.linearDamping );
+	float angularDamping = 1.0f / ( 1.0f + h * sim.angularDamping );
+	float gravityScale = sim.invMass > 0.0f ? sim.gravityScale : 0.0f;
+	V2 linearVelocityDelta = add( mulSV( h * sim.invMass, sim.force ), mulSV( h * gravityScale, w->gravity ) );
+	float angularVelocityDelta = h * sim.invInertia * sim.torque;
+	v = mulAdd( linearVelocityDelta, linearDamping, v );
+	wv = angularVelocityDelta + angularDamping * wv;
+	if ( dot( v, v ) > maxLinearSpeedSquared )
+	{
+		float ratio = maxLinearSpeed / length( v );
+		v = mulSV( ratio, v );
+		sim.isSpeedCapped = true;
+	}
+	if ( wv * wv > maxAngularSpeedSquared && sim.allowFastRotation == false )
+	{
+		float ratio = maxAngularSpeed / absf( wv );
+		wv *= ratio;
+		sim.isSpeedCapped = true;
+	}
+	state.v = v;
+	state.w = wv;
+}
+
+// solver.c:182-199
+F2D_HD void integratePosition( BodyState& state, float h )
+{
+	state.dq = integrateRot( state.dq, h * state.w );
+	state.dp = mulAdd( state.dp, h, state.v );
+}
+
+// Colour-parallel constraint stage: joints and contacts of colour `color` (independent inside a colour,
+// solver.c:773-808). stage: 0 warm start, 1 solve(useBias), 2 relax, 3 restitution
+template <class Team> F2D_HDF inline void colorStage( World* w, Team& t, int color, int stage )
+{
+	BodyState* states = ptr( w, w->states );
+	const ConView c = conView( w );
+	int jointCount = w->colorJoints[color].count;
+	int contactCount = w->colorContacts[color].count;
+	int base = w->step.colorBase[color];
+	float inv_h = w->step.inv_h;
+	float contactSpeed = w->contactSpeed;
+	if ( stage != 3 && jointCount > 0 )
+	{
+		const int32_t* jl = ptr( w, w->colorJoints[color] );
+		JointSim* jsims = ptr( w, w->jointSims );
+		for ( int i = t.rank(); i < jointCount; i += t.size() )
+		{
+			JointSim& js = jsims[jl[i]];
+			if ( stage == 0 )
+				warmStartJoint( w, js, states );
+			else
+				solveJoint( w, js, states, stage == 1 );
+		}
+	}
+	for ( int i = t.rank(); i < contactCount; i += t.size() )
+	{
+		int slot = base + i;
+		if ( stage == 0 )
+			warmStartSlot( c, slot, states );
+		else if ( stage == 1 )
+			solveSlot( c, slot, states, true, inv_h, contactSpeed );
+		else if ( stage == 2 )
+			solveSlot( c, slot, states, false, inv_h, contactSpeed );
+		else
+		{
+			// the reference skips a 4-lane group when no lane has restitution (contact_solver.c:1982-1986)
+			int g0 = ( i >> 2 ) << 2;
+			bool any = false;
+			for ( int k = g0; k < g0 + 4 && k < contactCount; ++k )
+				any = any || ( c.f( cfRestitution, base + k ) != 0.0f );
+			if ( any )
+				restitutionSlot( c, slot, states, w->step.restitutionThreshold );
+		}
+	}
+}
+
+// Overflow colour, serial in array order, joints before contacts (solver.c:1008-1009, 1027-1028, 1055-1056, 1077)
+F2D_HDF inline void overflowStage( World* w, int stage )
+{
+	BodyState* states = ptr( w, w->states );
+	const ConView c = conView( w );
+	int base = w->step.colorBase[kOverflow];
+	int jointCount = w->colorJoints[kOverflow].count;
+	int contactCount = w->colorContacts[kOverflow].count;
+	if ( stage != 3 )
+	{
+		const int32_t* jl = ptr( w, w->colorJoints[kOverflow] );
+		JointSim* jsims = ptr( w, w->jointSims );
+		for ( int i = 0; i < jointCount; ++i )
+		{
+			if ( stage == 0 )
+				warmStartJoint( w, jsims[jl[i]], states );
+			else
+				solveJoint( w, jsims[jl[i]], states, stage == 1 );
+		}
+	}
+	for ( int i = 0; i < contactCount; ++i )
+	{
+		if ( stage == 0 )
+			overflowWarmStart( c, base + i, states );
+		else if ( stage == 1 )
+			overflowSolve( c, base + i, states, true, w->step.inv_h, w->maxContactPushSpeed );
+		else if ( stage == 2 )
+			overflowSolve( c, base + i, states, false, w->step.inv_h, w->maxContactPushSpeed );
+		else
+			overflowRestitution( c, base + i, states, w->restitutionThreshold );
+	}
+}
+
+template <class Team> F2D_HDF inline void constraintPass( World* w, Team& t, int stage )
+{
+	bool hasOverflow = w->colorContacts[kOverflow].count + w->colorJoints[kOverflow].count > 0;
+	if ( hasOverflow )
+	{
+		if ( t.rank() == 0 )
+			overflowStage( w, stage );
+		t.sync();
+	}
+	int n = w->step.activeColorCount;
+	for ( int k = 0; k < n; ++k )
+	{
+		colorStage( w, t, w->step.activeColors[k], stage );
+		t.sync();
+	}
+}
+
+template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
+{
+	if ( t.rank() == 0 )
+	{
+		w->stepIndex += 1;
+		mergeAwakeIslands( w );
+		StepCtx& s = w->step;
+		s.awakeBodyCount = w->awakeBodies.count;
+		// colour bases and the active colour list (solver.c:1237-1355); overflow keeps the last base
+		int base = 0;
+		s.activeColorCount = 0;
+		s.awakeJointCount = 0;
+		for ( int i = 0; i < kColorCount; ++i )
+		{
+			s.colorBase[i] = base;
+			base += w->colorContacts[i].count;
+			if ( i < kOverflow )
+			{
+				if ( w->colorContacts[i].count + w->colorJoints[i].count > 0 )
+					s.activeColors[s.activeColorCount++] = i;
+			}
+			s.awakeJointCount += w->colorJoints[i].count;
+		}
+		s.colorBase[kColorCount] = base;
+		s.awakeContactCount = base;
+		if ( base > w->consStride )
+			setError( w, kErrCapacity, __LINE__ );
+		if ( s.awakeBodyCount > w->moveEvents.cap )
+			setError( w, kErrCapacity, __LINE__ );
+		else if ( s.awakeBodyCount > 0 )
+			w->moveEvents.count = s.awakeBodyCount;
+	}
+	t.sync();
+	const int awakeBodyCount = w->step.awakeBodyCount;
+	if ( awakeBodyCount == 0 || ( w->error & kErrCapacity ) != 0 )
+		return;
+
+	// island split squeezed in before the solve (solver.c:1473-1485, 1700-1706); rank 0 only, overlapped with prepare
+	if ( t.rank() == 0 )
+	{
+		if ( w->splitIslandId != kNull )
+			splitIsland( w, w->splitIslandId );
+		w->splitIslandId = kNull;
+	}
+
+	// prepare joints and contacts (all colours incl. overflow: prepare formulas are identical)
+	{
+		JointSim* jsims = ptr( w, w->jointSims );
+		for ( int color = 0; color < kColorCount; ++color )
+		{
+			const int32_t* jl = ptr( w, w->colorJoints[color] );
+			int n = w->colorJoints[color].count;
+			for ( int i = t.rank(); i < n; i += t.size() )
+				prepareJoint( w, jsims[jl[i]] );
+		}
+		const ConView c = conView( w );
+		const BodyState* states = ptr( w, w->states );
+		float warmStartScale = w->enableWarmStarting ? 1.0f : 0.0f;
+		int total = w->step.awakeContactCount;
+		for ( int slot = t.rank(); slot < total; slot += t.size() )
+		{
+			int color = 0;
+			while ( slot >= w->step.colorBase[color + 1] )
+				color += 1;
+			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
+			prepareContactSlot( w, c, slot, contactId, states, warmStartScale );
+		}
+	}
+	t.sync();
+
+	const float h = w->step.h;
+	const float maxLinearSpeed = w->step.maxLinearVelocity;
+	const float maxAngularSpeed = kMaxRotation * w->step.inv_dt;
+	const int subStepCount = w->step.subStepCount;
+	for ( int sub = 0; sub < subStepCount; ++sub )
+	{
+		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+			integrateVelocity( w, i, h, maxLinearSpeed, maxAngularSpeed );
+		t.sync();
+		constraintPass( w, t, 0 );
+		constraintPass( w, t, 1 );
+		{
+			BodyState* states = ptr( w, w->states );
+			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+				integratePosition( states[i], h );
+		}
+		t.sync();
+		constraintPass( w, t, 2 );
+	}
+	constraintPass( w, t, 3 );
+
+	// store impulses (solver.c:1093-1097)
+	{
+		const ConView c = conView( w );
+		int total = w->step.awakeContactCount;
+		int overflowBase = w->step.colorBase[kOverflow];
+		for ( int slot = t.rank(); slot < total; slot += t.size() )
+		{
+			int color = 0;
+			while ( slot >= w->step.colorBase[color + 1] )
+				color += 1;
+			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
+			storeSlot( w, c, slot, contactId, slot >= overflowBase );
+		}
+	}
+	t.sync();
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+struct ContinuousCtx
+{
+	World* w;
+	BodySim* fastSim;
+	const Shape* fastShape;
+	V2 centroid1, centroid2;
+	Sweep sweep;
+	float fraction;
+};
+
+F2D_HD Sweep makeSweep( const BodySim& s )
+{
+	Sweep sw;
+	sw.c1 = s.center0;
+	sw.c2 = s.center;
+	sw.q1 = s.rotation0;
+	sw.q2 = s.transform.q;
+	sw.localCenter = s.localCenter;
+	return sw;
+}
+
+// solver.c:212-387 (custom filter / pre-solve callbacks are rejected at registration on the device path)
+F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
+{
+	World* w = ctx.w;
+	const Shape& fastShape = *ctx.fastShape;
+	if ( shapeId == fastShape.id )
+		return true;
+	const Shape& shape = ptr( w, w->shapes )[shapeId];
+	if ( shape.bodyId == fastShape.bodyId )
+		return true;
+	if ( shape.sensorIndex != kNull )
+		return true;
+	if ( shouldShapesCollide( fastShape.filter, shape.filter ) == false )
+		return true;
+	const Body* bodies = ptr( w, w->bodies );
+	const Body& body = bodies[shape.bodyId];
+	const BodySim& bodySim = ptr( w, w->sims )[shape.bodyId];
+	if ( bodySim.isBullet )
+		return true;
+	const Body& fastBody = bodies[ctx.fastSim->bodyId];
+	if ( shouldBodiesCollide( w, fastBody, body ) == false )
+		return true;
+
+	if ( shape.type == kChainSegment )
+	{
+		Xf transform = bodySim.transform;
+		V2 p1 = xfPoint( transform, shape.chainSegment.segment.p1 );
+		V2 p2 = xfPoint( transform, shape.chainSegment.segment.p2 );
+		V2 e = sub( p2, p1 );
+		float len;
+		e = lengthAndNormalize( &len, e );
+		if ( len > kLinearSlop )
+		{
+			float offset1 = cross( sub( ctx.centroid1, p1 ), e );
+			float offset2 = cross( sub( ctx.centroid2, p1 ), e );
+			const float allowedFraction = 0.25f;
+			if ( offset1 < 0.0f || offset1 - offset2 < allowedFraction * ctx.fastSim->minExtent )
+				return true;
+		}
+	}
+
+	ShapeProxy proxyA = makeShapeProxy( shape );
+	ShapeProxy proxyB = makeShapeProxy( fastShape );
+	Sweep sweepA = makeSweep( bodySim );
+	float hitFraction = ctx.fraction;
+	bool didHit = false;
+	float toi = timeOfImpact( proxyA, proxyB, sweepA, ctx.sweep, ctx.fraction );
+	if ( 0.0f < toi && toi < ctx.fraction )
+	{
+		hitFraction = toi;
+		didHit = true;
+	}
+	else if ( 0.0f == toi )
+	{
+		// fallback to TOI of a small circle around the fast shape centroid
+		V2 centroid = shapeCentroid( fastShape );
+		float mn, mx;
+		shapeExtent( fastShape, centroid, &mn, &mx );
+		float radius = 0.25f * mn;
+		ShapeProxy small = makeProxy( &centroid, 1, radius );
+		toi = timeOfImpact( proxyA, small, sweepA, ctx.sweep, ctx.fraction );
+		if ( 0.0f < toi && toi < ctx.fraction )
+		{
+			hitFraction = toi;
+			didHit = true;
+		}
+	}
+	if ( didHit )
+		ctx.fraction = hitFraction;
+	return true;
+}
+
+// solver.c:390-541
+F2D_HDF inline void solveContinuous( World* w, int awakeIndex )
+{
+	int bodyId = ptr( w, w->awakeBodies )[awakeIndex];
+	BodySim& fastSim = ptr( w, w->sims )[bodyId];
+	const Body& fastBody = ptr( w, w->bodies )[bodyId];
+	Shape* shapes = ptr( w, w->shapes );
+	Sweep sweep = makeSweep( fastSim );
+	Xf xf1;
+	xf1.q = sweep.q1;
+	xf1.p = sub( sweep.c1, rotate( sweep.q1, sweep.localCenter ) );
+	Xf xf2;
+	xf2.q = sweep.q2;
+	xf2.p = sub( sweep.c2, rotate( sweep.q2, sweep.localCenter ) );
+
+	ContinuousCtx ctx;
+	ctx.w = w;
+	ctx.sweep = sweep;
+	ctx.fastSim = &fastSim;
+	ctx.fraction = 1.0f;
+	bool isBullet = fastSim.isBullet;
+
+	int shapeId = fastBody.headShapeId;
+	while ( shapeId != kNull )
+	{
+		Shape& fastShape = shapes[shapeId];
+		shapeId = fastShape.nextShapeId;
+		ctx.fastShape = &fastShape;
+		ctx.centroid1 = xfPoint( xf1, fastShape.localCentroid );
+		ctx.centroid2 = xfPoint( xf2, fastShape.localCentroid );
+		Box box1 = fastShape.aabb;
+		Box box2 = shapeAABB( fastShape, xf2 );
+		Box box = boxUnion( box1, box2 );
+		fastShape.aabb = box2; // no speculative margin here, as in the reference (solver.c:431-436)
+		if ( fastShape.sensorIndex != kNull )
+			continue;
+		auto visit = [&]( int, uint64_t userData ) -> bool { return continuousVisit( ctx, (int)userData ); };
+		treeQuery( w, w->trees[kStaticBody], box, UINT64_MAX, visit );
+		if ( isBullet )
+		{
+			treeQuery( w, w->trees[kKinematicBody], box, UINT64_MAX, visit );
+			treeQuery( w, w->trees[kDynamicBody], box, UINT64_MAX, visit );
+		}
+	}
+
+	if ( ctx.fraction < 1.0f )
+	{
+		Rot q = nlerp( sweep.q1, sweep.q2, ctx.fraction );
+		V2 c = lerp( sweep.c1, sweep.c2, ctx.fraction );
+		V2 origin = sub( c, rotate( q, sweep.localCenter ) );
+		Xf transform = { origin, q };
+		fastSim.transform = transform;
+		fastSim.center = c;
+		fastSim.rotation0 = q;
+		fastSim.center0 = c;
+		ptr( w, w->moveEvents )[awakeIndex].transform = transform;
+
+		shapeId = fastBody.headShapeId;
+		while ( shapeId != kNull )
+		{
+			Shape& shape = shapes[shapeId];
+			Box aabb = inflate( shapeAABB( shape, transform ), kSpeculative );
+			shape.aabb = aabb;
+			if ( boxContains( shape.fatAABB, aabb ) == false )
+			{
+				shape.fatAABB = inflate( aabb, kAabbMargin );
+				shape.enlargedAABB = true;
+				fastSim.enlargeAABB = true;
+			}
+			shapeId = shape.nextShapeId;
+		}
+	}
+	else
+	{
+		fastSim.rotation0 = fastSim.transform.q;
+		fastSim.center0 = fastSim.center;
+		shapeId = fastBody.headShapeId;
+		while ( shapeId != kNull )
+		{
+			Shape& shape = shapes[shapeId];
+			if ( boxContains( shape.fatAABB, shape.aabb ) == false )
+			{
+				shape.fatAABB = inflate( shape.aabb, kAabbMargin );
+				shape.enlargedAABB = true;
+				fastSim.enlargeAABB = true;
+			}
+			shapeId = shape.nextShapeId;
+		}
+	}
+}
+
+// solver.c:543-726, one awake body
+F2D_HDF inline void finalizeBody( World* w, int simIndex )
+{
+	BodyState& state = ptr( w, w->states )[simIndex];
+	int bodyId = ptr( w, w->awakeBodies )[simIndex];
+	BodySim& sim = ptr( w, w->sims )[bodyId];
+	Body& body = ptr( w, w->bodies )[bodyId];
+	const float timeStep = w->step.dt;
+	const float invTimeStep = w->step.inv_dt;
+
+	V2 v = state.v;
+	float wv = state.w;
+	sim.center = add( sim.center, state.dp );
+	sim.transform.q = normalizeRot( mulRot( state.dq, sim.transform.q ) );
+	float maxVelocity = length( v ) + absf( wv ) * sim.maxExtent;
+	float maxDeltaPosition = length( state.dp ) + absf( state.dq.s ) * sim.maxExtent;
+	float positionSleepFactor = 0.5f;
+	float sleepVelocity = maxf( maxVelocity, positionSleepFactor * invTimeStep * maxDeltaPosition );
+	state.dp = V2{ 0.0f, 0.0f };
+	state.dq = Rot{ 1.0f, 0.0f };
+	sim.transform.p = sub( sim.center, rotate( sim.transform.q, sim.localCenter ) );
+
+	body.bodyMoveIndex = simIndex;
+	BodyMoveEvent& ev = ptr( w, w->moveEvents )[simIndex];
+	ev.transform = sim.transform;
+	ev.bodyId = BodyId{ bodyId + 1, w->worldId, body.generation };
+	ev.userData = body.userData;
+	ev.fellAsleep = false;
+
+	sim.force = V2{ 0.0f, 0.0f };
+	sim.torque = 0.0f;
+	body.isSpeedCapped = sim.isSpeedCapped;
+	sim.isSpeedCapped = false;
+	sim.isFast = false;
+
+	if ( w->enableSleep == false || body.enableSleep == false || sleepVelocity > body.sleepThreshold )
+	{
+		body.sleepTime = 0.0f;
+		if ( body.type == kDynamicBody && w->enableContinuous && maxVelocity * timeStep > 0.5f * sim.minExtent )
+		{
+			sim.isFast = true;
+			if ( sim.isBullet )
+			{
+				int bulletIndex = atomAdd( &w->step.bulletCount, 1 );
+				ptr( w, w->bullets )[bulletIndex] = simIndex;
+			}
+			else
+			{
+				solveContinuous( w, simIndex );
+			}
+		}
+		else
+		{
+			sim.center0 = sim.center;
+			sim.rotation0 = sim.transform.q;
+		}
+	}
+	else
+	{
+		sim.center0 = sim.center;
+		sim.rotation0 = sim.transform.q;
+		body.sleepTime += timeStep;
+	}
+
+	const Island& island = ptr( w, w->islands )[body.islandId];
+	if ( body.sleepTime < kTimeToSleep )
+	{
+		int islandIndex = island.localIndex;
+		atomOr64( ptr( w, w->islandBits ) + ( islandIndex >> 6 ), 1ull << ( islandIndex & 63 ) );
+	}
+	else if ( island.constraintRemoveCount > 0 )
+	{
+		// split candidate: largest sleepTime, first body in awake order on ties (solver.c:666-675 with one worker)
+		unsigned long long key = ( (unsigned long long)floatBits( body.sleepTime ) << 32 ) |
+								 (unsigned long long)( 0xFFFFFFFFu - (uint32_t)simIndex );
+		atomMax64( &w->step.splitKey, key );
+	}
+
+	Xf transform = sim.transform;
+	bool isFast = sim.isFast;
+	Shape* shapes = ptr( w, w->shapes );
+	uint64_t* enlargedBits = ptr( w, w->enlargedBits );
+	int shapeId = body.headShapeId;
+	while ( shapeId != kNull )
+	{
+		Shape& shape = shapes[shapeId];
+		if ( isFast )
+		{
+			atomOr64( enlargedBits + ( simIndex >> 6 ), 1ull << ( simIndex & 63 ) );
+		}
+		else
+		{
+			Box aabb = inflate( shapeAABB( shape, transform ), kSpeculative );
+			shape.aabb = aabb;
+			if ( boxContains( shape.fatAABB, aabb ) == false )
+			{
+				shape.fatAABB = inflate( aabb, kAabbMargin );
+				shape.enlargedAABB = true;
+				atomOr64( enlargedBits + ( simIndex >> 6 ), 1ull << ( simIndex & 63 ) );
+			}
+		}
+		shapeId = shape.nextShapeId;
+	}
+}
+
+// Team-parallel enlarge of one leaf: the end state (leaf box replaced; every ancestor box = union with it; every
+// ancestor flagged enlarged) equals what any serial order of b2DynamicTree_EnlargeProxy produces
+// (dynamic_tree.c:827-866), because box growth is a commutative min/max and flags only accumulate.
+F2D_HDF inline void enlargeLeafParallel( World* w, Tree& tree, int leaf, Box box )
+{
+	TreeNode* nodes = ptr( w, tree.nodes );
+	nodes[leaf].box = box;
+	int parent = nodes[leaf].parent;
+	while ( parent != kNull )
+	{
+		TreeNode& n = nodes[parent];
+		atomMinF( &n.box.lo.x, box.lo.x );
+		atomMinF( &n.box.lo.y, box.lo.y );
+		atomMaxF( &n.box.hi.x, box.hi.x );
+		atomMaxF( &n.box.hi.y, box.hi.y );
+		// height (low 16 bits) and flags (high 16 bits) share one 32-bit word
+		atomOr32( reinterpret_cast<uint32_t*>( &n.height ), (uint32_t)kNodeEnlarged << 16 );
+		parent = n.parent;
+	}
+}
+
+// Hit events, colour-major then array order: solver.c:1758-1818
+F2D_HDF inline void reportHitEvents( World* w )
+{
+	float threshold = w->hitEventThreshold;
+	const ContactSim* sims = ptr( w, w->contactSims );
+	const Shape* shapes = ptr( w, w->shapes );
+	for ( int i = 0; i < kColorCount; ++i )
+	{
+		const int32_t* list = ptr( w, w->colorContacts[i] );
+		int n = w->colorContacts[i].count;
+		for ( int j = 0; j < n; ++j )
+		{
+			const ContactSim& sim = sims[list[j]];
+			if ( ( sim.simFlags & kSimEnableHitEvent ) == 0 )
+				continue;
+			HitEvent ev;
+			memset( &ev, 0, sizeof( ev ) );
+			ev.approachSpeed = threshold;
+			bool hit = false;
+			for ( int k = 0; k < sim.manifold.pointCount; ++k )
+			{
+				const ManifoldPoint& mp = sim.manifold.points[k];
+				float approachSpeed = -mp.normalVelocity;
+				if ( approachSpeed > ev.approachSpeed && mp.totalNormalImpulse > 0.0f )
+				{
+					ev.approachSpeed = approachSpeed;
+					ev.point = mp.point;
+					hit = true;
+				}
+			}
+			if ( hit )
+			{
+				ev.normal = sim.manifold.normal;
+				ev.a = makeShapeId( w, shapes[sim.shapeIdA] );
+				ev.b = makeShapeId( w, shapes[sim.shapeIdB] );
+				F2D_PUSH( w, w->hitEvents, ev );
+			}
+		}
+	}
+}
+
+template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
+{
+	const int awakeBodyCount = w->step.awakeBodyCount;
+	const bool solved = awakeBodyCount > 0 && w->step.dt > 0.0f && ( w->error & kErrCapacity ) == 0;
+	if ( solved )
+	{
+		// clear bit sets (solver.c:1724-1733)
+		int bodyWords = ( awakeBodyCount + 63 ) >> 6;
+		int islandWords = ( w->awakeIslands.count + 63 ) >> 6;
+		uint64_t* eb = ptr( w, w->enlargedBits );
+		uint64_t* ib = ptr( w, w->islandBits );
+		for ( int i = t.rank(); i < bodyWords; i += t.size() )
+			eb[i] = 0;
+		for ( int i = t.rank(); i < islandWords; i += t.size() )
+			ib[i] = 0;
+		t.sync();
+
+		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+			finalizeBody( w, i );
+		t.sync();
+
+		if ( t.rank() == 0 && w->hitEventCapable > 0 )
+			reportHitEvents( w );
+
+		// Enlarged proxies -> broadphase, and next step's move array in ascending awake index x shape-list order
+		// (solver.c:1835-1907). Count, scan, then scatter + enlarge in parallel.
+		const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+		const Body* bodies = ptr( w, w->bodies );
+		BodySim* sims = ptr( w, w->sims );
+		Shape* shapes = ptr( w, w->shapes );
+		int32_t* scan = ptr( w, w->scan );
+		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+		{
+			int count = 0;
+			if ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) )
+			{
+				int bodyId = awakeBodies[i];
+				const BodySim& sim = sims[bodyId];
+				bool fastBullet = sim.isBullet && sim.isFast;
+				for ( int s = bodies[bodyId].headShapeId; s != kNull; s = shapes[s].nextShapeId )
+					count += ( fastBullet || shapes[s].enlargedAABB ) ? 1 : 0;
+			}
+			scan[i] = count;
+		}
+		t.sync();
+		int moveTotal = t.exclusiveScan( scan, awakeBodyCount );
+		if ( moveTotal > w->moveArray.cap )
+		{
+			if ( t.rank() == 0 )
+				setError( w, kErrCapacity, __LINE__ );
+			moveTotal = 0;
+		}
+		int32_t* moves = ptr( w, w->moveArray );
+		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+		{
+			if ( ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) ) == 0 || moveTotal == 0 )
+				continue;
+			int bodyId = awakeBodies[i];
+			const BodySim& sim = sims[bodyId];
+			bool fastBullet = sim.isBullet && sim.isFast;
+			int out = scan[i];
+			for ( int s = bodies[bodyId].headShapeId; s != kNull; s = shapes[s].nextShapeId )
+			{
+				Shape& shape = shapes[s];
+				if ( fastBullet )
+				{
+					moves[out++] = shape.proxyKey;
+					ptr( w, w->trees[proxyType( shape.proxyKey )].nodes )[proxyId( shape.proxyKey )].flags |= kNodeMoved;
+				}
+				else if ( shape.enlargedAABB )
+				{
+					int key = shape.proxyKey;
+					Tree& tree = w->trees[proxyType( key )];
+					enlargeLeafParallel( w, tree, proxyId( key ), shape.fatAABB );
+					ptr( w, tree.nodes )[proxyId( key )].flags |= kNodeMoved;
+					moves[out++] = key;
+					shape.enlargedAABB = false;
+				}
+			}
+		}
+		t.sync();
+		if ( t.rank() == 0 )
+			w->moveArray.count = moveTotal;
+
+		// bullets: continuous against everything, then enlarge (solver.c:1915-1988)
+		int bulletCount = w->step.bulletCount;
+		if ( bulletCount > 0 )
+		{
+			const int32_t* bullets = ptr( w, w->bullets );
+			for ( int i = t.rank(); i < bulletCount; i += t.size() )
+				solveContinuous( w, bullets[i] );
+			t.sync();
+			for ( int i = t.rank(); i < bulletCount; i += t.size() )
+			{
+				int bodyId = awakeBodies[bullets[i]];
+				BodySim& sim = sims[bodyId];
+				if ( sim.enlargeAABB == false )
+					continue;
+				sim.enlargeAABB = false;
+				for ( int s = bodies[bodyId].headShapeId; s != kNull; s = shapes[s].nextShapeId )
+				{
+					Shape& shape = shapes[s];
+					if ( shape.enlargedAABB == false )
+						continue;
+					shape.enlargedAABB = false;
+					enlargeLeafParallel( w, w->trees[kDynamicBody], proxyId( shape.proxyKey ), shape.fatAABB );
+				}
+			}
+			t.sync();
+		}
+
+		// island sleep: reverse scan of awake islands (solver.c:1995-2051)
+		if ( t.rank() == 0 )
+		{
+			w->step.bulletCount = 0;
+			if ( w->enableSleep )
+			{
+				unsigned long long key = w->step.splitKey;
+				if ( key != 0 )
+				{
+					int simIndex = (int)( 0xFFFFFFFFu - (uint32_t)( key & 0xFFFFFFFFull ) );
+					w->splitIslandId = bodies[awakeBodies[simIndex]].islandId;
+				}
+				const int32_t* islandList = ptr( w, w->awakeIslands );
+				int count = w->awakeIslands.count;
+				for ( int islandIndex = count - 1; islandIndex >= 0; islandIndex -= 1 )
+				{
+					if ( ib[islandIndex >> 6] & ( 1ull << ( islandIndex & 63 ) ) )
+						continue;
+					trySleepIsland( w, islandList[islandIndex] );
+				}
+			}
+		}
+		t.sync();
+	}
+
+	// sensors would run here (world.c:788-793): no sensor shapes on the device path yet
+
+	if ( t.rank() == 0 )
+	{
+		// swap end-event buffers (world.c:807-811)
+		w->endEventArrayIndex = 1 - w->endEventArrayIndex;
+		w->sensorEndEvents[w->endEventArrayIndex].count = 0;
+		w->endEvents[w->endEventArrayIndex].count = 0;
+		w->locked = false;
+	}
+	t.sync();
+}
+
+// Zero time step: only the event buffers advance (world.c:716-725)
+template <class Team> F2D_HDF inline void stepZeroDt( World* w, Team& t )
+{
+	if ( t.rank() == 0 )
+	{
+		w->moveEvents.count = 0;
+		w->sensorBeginEvents.count = 0;
+		w->beginEvents.count = 0;
+		w->hitEvents.count = 0;
+		w->endEventArrayIndex = 1 - w->endEventArrayIndex;
+		w->sensorEndEvents[w->endEventArrayIndex].count = 0;
+		w->endEvents[w->endEventArrayIndex].count = 0;
+	}
+	t.sync();
+}
+
+// Whole step on one team (used by the CTA-per-world kernel and the host emulation)
+template <class Team> F2D_HDF inline void stepWorld( World* w, Team& t, float dt, int subStepCount )
+{
+	if ( dt == 0.0f )
+	{
+		stepZeroDt( w, t );
+		return;
+	}
+	stepBegin( w, t, dt, subStepCount );
+	stepPairs( w, t );
+	stepCollide( w, t );
+	stepSolve( w, t );
+	stepFinalize( w, t );
+}
+
+} // namespace f2d

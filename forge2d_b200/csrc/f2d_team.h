@@ -1,0 +1,80 @@
+// forge2d_b200 — execution-team abstraction.
+//
+// Every phase of the world step is written once as a team-parallel routine: `for (i = team.rank(); i < n; i +=
+// team.size())` loops separated by `team.sync()`, with the reference's order-defining serial sections run by rank 0.
+// Three teams execute the same code:
+//   * CtaTeam   — one CUDA thread block per world (`__syncthreads`): batches of independent worlds, small worlds;
+//   * GridTeam  — one cooperative grid per world (grid-wide barrier): a single large world across all 148 SMs;
+//   * SerialTeam — one host thread; used by the host-side API paths and by the CPU emulation build in tests/.
+#pragma once
+#include "f2d_types.h"
+
+namespace f2d
+{
+
+#if defined( __CUDA_ARCH__ )
+F2D_HD void atomOr64( uint64_t* p, uint64_t v ) { atomicOr( reinterpret_cast<unsigned long long*>( p ), (unsigned long long)v ); }
+F2D_HD int atomAdd( int32_t* p, int v ) { return atomicAdd( p, v ); }
+F2D_HD void atomMax64( unsigned long long* p, unsigned long long v ) { atomicMax( p, v ); }
+F2D_HD void atomOr32( uint32_t* p, uint32_t v ) { atomicOr( p, v ); }
+// float min/max through the ordered-int trick (valid for any mix of signs, NaN-free inputs)
+F2D_HD void atomMinF( float* p, float v )
+{
+	if ( v >= 0.0f )
+		atomicMin( reinterpret_cast<int*>( p ), __float_as_int( v ) );
+	else
+		atomicMax( reinterpret_cast<unsigned int*>( p ), __float_as_uint( v ) );
+}
+F2D_HD void atomMaxF( float* p, float v )
+{
+	if ( v >= 0.0f )
+		atomicMax( reinterpret_cast<int*>( p ), __float_as_int( v ) );
+	else
+		atomicMin( reinterpret_cast<unsigned int*>( p ), __float_as_uint( v ) );
+}
+#else
+F2D_HD void atomOr64( uint64_t* p, uint64_t v ) { *p |= v; }
+F2D_HD int atomAdd( int32_t* p, int v )
+{
+	int o = *p;
+	*p += v;
+	return o;
+}
+F2D_HD void atomMax64( unsigned long long* p, unsigned long long v )
+{
+	if ( v > *p )
+		*p = v;
+}
+F2D_HD void atomOr32( uint32_t* p, uint32_t v ) { *p |= v; }
+F2D_HD void atomMinF( float* p, float v )
+{
+	if ( v < *p )
+		*p = v;
+}
+F2D_HD void atomMaxF( float* p, float v )
+{
+	if ( *p < v )
+		*p = v;
+}
+#endif
+
+struct SerialTeam
+{
+	F2D_HD int rank() const { return 0; }
+	F2D_HD int size() const { return 1; }
+	F2D_HD void sync() const {}
+	// in-place exclusive scan of data[0..n), returns the total
+	F2D_HD int exclusiveScan( int32_t* data, int n ) const
+	{
+		int sum = 0;
+		for ( int i = 0; i < n; ++i )
+		{
+			int v = data[i];
+			data[i] = sum;
+			sum += v;
+		}
+		return sum;
+	}
+};
+
+} // namespace f2d

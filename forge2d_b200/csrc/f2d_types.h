@@ -1,0 +1,648 @@
+// forge2d_b200 — world image layout.
+//
+// A world is ONE position-independent block of memory ("image"): a World header followed by every array the
+// step touches, addressed by byte offsets from the header. The same bytes are valid on the host and in HBM, so
+//   * host-side API calls (create body/shape/joint ...) mutate a host image with the same code the device runs,
+//   * upload/download is a single memcpy, and
+//   * a batch of N independent worlds is N images at a fixed stride in one HBM allocation (sharded by world).
+//
+// Unlike the reference (B2/src/world.h:44-175, solver_set.h:19-43) simulation records never move between
+// "solver sets": BodySim / ContactSim / JointSim live in stable slots indexed by their id, and the set / colour
+// membership that defines the reference's iteration ORDER (awake body order, colour array order, sleeping-set
+// order) is kept in compact int32 id lists that are appended / swap-removed exactly where the
+// reference appends / swap-removes whole structs. Order-dependent results are therefore identical while the
+// bytes moved per structural edit drop from 100-196 B to 4 B.
+#pragma once
+#include "f2d_math.h"
+#include <string.h>
+
+namespace f2d
+{
+
+template <class T> struct Arr
+{
+	uint64_t off; // bytes from the World header
+	int32_t count;
+	int32_t cap;
+};
+
+// LIFO id pool, semantics of B2/src/id_pool.c:19-38 (contact-id reuse order feeds colouring order).
+struct IdPool
+{
+	Arr<int32_t> free;
+	int32_t next;
+	int32_t pad;
+};
+
+enum : int
+{
+	kStaticSet = 0,
+	kDisabledSet = 1,
+	kAwakeSet = 2,
+	kFirstSleepingSet = 3
+};
+enum : int
+{
+	kStaticBody = 0,
+	kKinematicBody = 1,
+	kDynamicBody = 2
+};
+enum : int
+{
+	kCircle = 0,
+	kCapsule = 1,
+	kSegment = 2,
+	kPolygon = 3,
+	kChainSegment = 4,
+	kShapeTypeCount = 5
+};
+enum : int
+{
+	kDistanceJoint = 0,
+	kFilterJoint,
+	kMotorJoint,
+	kMouseJoint,
+	kPrismaticJoint,
+	kRevoluteJoint,
+	kWeldJoint,
+	kWheelJoint
+};
+
+// --- public-ABI-compatible value types (layouts fixed by B2/include/box2d/collision.h, types.h, id.h) ----------
+struct ShapeId
+{
+	int32_t index1;
+	uint16_t world0, generation;
+};
+struct BodyId
+{
+	int32_t index1;
+	uint16_t world0, generation;
+};
+struct ManifoldPoint // collision.h:498-529, 48 B
+{
+	V2 point, anchorA, anchorB;
+	float separation, normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity;
+	uint16_t id;
+	bool persisted;
+};
+struct Manifold // collision.h:532-552, 112 B
+{
+	V2 normal;
+	float rollingImpulse;
+	ManifoldPoint points[2];
+	int32_t pointCount;
+};
+struct Circle
+{
+	V2 center;
+	float radius;
+};
+struct Capsule
+{
+	V2 c1, c2;
+	float radius;
+};
+struct Poly // b2Polygon, 144 B
+{
+	V2 v[kMaxPolyVerts];
+	V2 n[kMaxPolyVerts];
+	V2 centroid;
+	float radius;
+	int32_t count;
+};
+struct Segment
+{
+	V2 p1, p2;
+};
+struct ChainSegment
+{
+	V2 ghost1;
+	Segment segment;
+	V2 ghost2;
+	int32_t chainId;
+};
+struct Filter // types.h b2Filter
+{
+	uint64_t category, mask;
+	int32_t group;
+};
+struct SimplexCache
+{
+	uint16_t count;
+	uint8_t indexA[3], indexB[3];
+};
+struct BodyMoveEvent // types.h:1136-1142, 40 B
+{
+	Xf transform;
+	BodyId bodyId;
+	uint64_t userData;
+	bool fellAsleep;
+};
+struct BeginTouchEvent // types.h:1050
+{
+	ShapeId a, b;
+	Manifold manifold;
+};
+struct EndTouchEvent
+{
+	ShapeId a, b;
+};
+struct HitEvent // types.h:1082
+{
+	ShapeId a, b;
+	V2 point, normal;
+	float approachSpeed;
+};
+struct SensorEvent
+{
+	ShapeId sensor, visitor;
+};
+
+// --- internal records ---------------------------------------------------------------------------------------
+// Cold body data: B2/src/body.h:14-64
+struct Body
+{
+	char name[32];
+	uint64_t userData;
+	int32_t setIndex, localIndex; // localIndex = position in the owning set's id list
+	int32_t headContactKey, contactCount;
+	int32_t headShapeId, shapeCount, headChainId;
+	int32_t headJointKey, jointCount;
+	int32_t islandId, islandPrev, islandNext;
+	float mass, inertia, sleepThreshold, sleepTime;
+	int32_t bodyMoveIndex, id, type;
+	uint16_t generation;
+	uint16_t colorMask; // per-colour membership bits (replaces the per-colour body bitsets, constraint_graph.h:24-42)
+	bool enableSleep, fixedRotation, isSpeedCapped, isMarked;
+};
+// Body simulation data (stable slot = body id): B2/src/body.h:120-159
+struct BodySim
+{
+	Xf transform;
+	V2 center;
+	Rot rotation0;
+	V2 center0;
+	V2 localCenter;
+	V2 force;
+	float torque, invMass, invInertia, minExtent, maxExtent, linearDamping, angularDamping, gravityScale;
+	int32_t bodyId;
+	bool isFast, isBullet, isSpeedCapped, allowFastRotation, enlargeAABB;
+};
+// Solver state, dense by awake index, 32 B = two float4: B2/src/body.h:66-83
+struct BodyState
+{
+	V2 v;
+	float w;
+	int32_t flags;
+	V2 dp;
+	Rot dq;
+};
+// B2/src/shape.h:13-52
+struct Shape
+{
+	int32_t id, bodyId, prevShapeId, nextShapeId, sensorIndex, type;
+	float density, friction, restitution, rollingResistance, tangentSpeed;
+	int32_t userMaterialId;
+	Box aabb, fatAABB;
+	V2 localCentroid;
+	int32_t proxyKey;
+	Filter filter;
+	uint64_t userData;
+	uint32_t customColor;
+	union
+	{
+		Capsule capsule;
+		Circle circle;
+		Poly polygon;
+		Segment segment;
+		ChainSegment chainSegment;
+	};
+	uint16_t generation;
+	bool enableSensorEvents, enableContactEvents, enableHitEvents, enablePreSolveEvents, enlargedAABB;
+};
+
+enum : uint32_t // contact.h:15-25
+{
+	kContactTouching = 0x1,
+	kContactHitEvent = 0x2,
+	kContactEnableContactEvents = 0x4
+};
+enum : uint32_t // contact.h:74-93
+{
+	kSimTouching = 0x00010000,
+	kSimDisjoint = 0x00020000,
+	kSimStartedTouching = 0x00040000,
+	kSimStoppedTouching = 0x00080000,
+	kSimEnableHitEvent = 0x00100000,
+	kSimEnablePreSolve = 0x00200000
+};
+struct Edge
+{
+	int32_t bodyId, prevKey, nextKey;
+};
+// Cold contact data (slot = contact id): B2/src/contact.h:41-71
+struct Contact
+{
+	int32_t setIndex, colorIndex, localIndex;
+	Edge edges[2];
+	int32_t shapeIdA, shapeIdB;
+	int32_t islandPrev, islandNext, islandId;
+	int32_t contactId;
+	uint32_t flags;
+	bool isMarked;
+};
+// Hot contact data (stable slot = contact id): B2/src/contact.h:98-131
+struct ContactSim
+{
+	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
+	int32_t shapeIdA, shapeIdB;
+	float invMassA, invIA, invMassB, invIB;
+	Manifold manifold;
+	float friction, restitution, rollingResistance, tangentSpeed;
+	uint32_t simFlags;
+	SimplexCache cache;
+};
+// B2/src/island.h:25-57
+struct Island
+{
+	int32_t setIndex, localIndex, islandId;
+	int32_t headBody, tailBody, bodyCount;
+	int32_t headContact, tailContact, contactCount;
+	int32_t headJoint, tailJoint, jointCount;
+	int32_t parentIsland, constraintRemoveCount;
+};
+// B2/src/joint.h:22-50
+struct Joint
+{
+	uint64_t userData;
+	int32_t setIndex, colorIndex, localIndex;
+	Edge edges[2];
+	int32_t jointId, islandId, islandPrev, islandNext;
+	float drawSize;
+	int32_t type;
+	uint16_t generation;
+	bool isMarked, collideConnected;
+};
+// Per-type joint data: B2/src/joint.h:52-245
+struct DistanceJointData
+{
+	float length, hertz, dampingRatio, minLength, maxLength, maxMotorForce, motorSpeed;
+	float impulse, lowerImpulse, upperImpulse, motorImpulse;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, deltaCenter;
+	Soft distanceSoftness;
+	float axialMass;
+	bool enableSpring, enableLimit, enableMotor;
+};
+struct MotorJointData
+{
+	V2 linearOffset;
+	float angularOffset;
+	V2 linearImpulse;
+	float angularImpulse, maxForce, maxTorque, correctionFactor;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, deltaCenter;
+	float deltaAngle;
+	M22 linearMass;
+	float angularMass;
+};
+struct MouseJointData
+{
+	V2 targetA;
+	float hertz, dampingRatio, maxForce;
+	V2 linearImpulse;
+	float angularImpulse;
+	Soft linearSoftness, angularSoftness;
+	int32_t indexB;
+	V2 anchorB, deltaCenter;
+	M22 linearMass;
+};
+struct PrismaticJointData
+{
+	V2 localAxisA, impulse;
+	float springImpulse, motorImpulse, lowerImpulse, upperImpulse;
+	float hertz, dampingRatio, targetTranslation, maxMotorForce, motorSpeed, referenceAngle, lowerTranslation, upperTranslation;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, axisA, deltaCenter;
+	float deltaAngle, axialMass;
+	Soft springSoftness;
+	bool enableSpring, enableLimit, enableMotor;
+};
+struct RevoluteJointData
+{
+	V2 linearImpulse;
+	float springImpulse, motorImpulse, lowerImpulse, upperImpulse;
+	float hertz, dampingRatio, targetAngle, maxMotorTorque, motorSpeed, referenceAngle, lowerAngle, upperAngle;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, deltaCenter;
+	float deltaAngle, axialMass;
+	Soft springSoftness;
+	bool enableSpring, enableMotor, enableLimit;
+};
+struct WeldJointData
+{
+	float referenceAngle, linearHertz, linearDampingRatio, angularHertz, angularDampingRatio;
+	Soft linearSoftness, angularSoftness;
+	V2 linearImpulse;
+	float angularImpulse;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, deltaCenter;
+	float deltaAngle, axialMass;
+};
+struct WheelJointData
+{
+	V2 localAxisA;
+	float perpImpulse, motorImpulse, springImpulse, lowerImpulse, upperImpulse;
+	float maxMotorTorque, motorSpeed, lowerTranslation, upperTranslation, hertz, dampingRatio;
+	int32_t indexA, indexB;
+	V2 anchorA, anchorB, axisA, deltaCenter;
+	float perpMass, motorMass, axialMass;
+	Soft springSoftness;
+	bool enableSpring, enableMotor, enableLimit;
+};
+// Joint simulation data (stable slot = joint id): B2/src/joint.h:247-278
+struct JointSim
+{
+	int32_t jointId, bodyIdA, bodyIdB, type;
+	V2 localOriginAnchorA, localOriginAnchorB;
+	float invMassA, invMassB, invIA, invIB;
+	float constraintHertz, constraintDampingRatio;
+	Soft constraintSoftness;
+	union
+	{
+		DistanceJointData distance;
+		MotorJointData motor;
+		MouseJointData mouse;
+		RevoluteJointData revolute;
+		PrismaticJointData prismatic;
+		WeldJointData weld;
+		WheelJointData wheel;
+	};
+};
+
+// Broadphase BVH node, 48 B = three 16-byte sectors (box | links | category): B2/src/dynamic_tree.c:19-50
+enum : uint16_t
+{
+	kNodeAllocated = 0x1,
+	kNodeEnlarged = 0x2,
+	kNodeLeaf = 0x4,
+	kNodeMoved = 0x8 // replaces the reference's moveSet hash (broad_phase.h:74-82): set while the proxy is in moveArray
+};
+struct TreeNode
+{
+	Box box;
+	union
+	{
+		struct
+		{
+			int32_t child1, child2;
+		};
+		uint64_t userData; // leaf: shape id
+	};
+	int32_t parent; // or free-list next
+	uint16_t height, flags;
+	uint64_t category;
+	uint64_t pad;
+};
+struct Tree
+{
+	Arr<TreeNode> nodes; // nodes.count = high-water mark of ever-used node slots
+	Arr<int32_t> leafIndices;
+	Arr<V2> leafCenters;
+	Arr<int32_t> work; // rebuild stacks (kept in the image: a 1024-deep stack per GPU thread would cost GBs of local memory)
+	int32_t root, nodeCount, freeList, proxyCount;
+};
+struct MovePair
+{
+	int32_t shapeA, shapeB, next;
+};
+
+// Sleeping solver set (id >= 3): four id lists carved from one block of World::sleepPool.
+// Reference: B2/src/solver_set.h:19-43 with b2TrySleepIsland / b2WakeSolverSet (solver_set.c:37-422).
+struct SolverSet
+{
+	int32_t setIndex; // kNull when the slot is free
+	int32_t blockOff; // start in World::sleepPool; layout [bodies | contacts | joints | islands], capacities below
+	int32_t bodyCap, contactCap, jointCap, islandCap;
+	int32_t bodyCount, contactCount, jointCount, islandCount;
+	int32_t prevBlock, nextBlock; // address-ordered block list (set ids) for compaction
+};
+
+// Step constants: B2/src/solver.h:75-138, built in world.c:742-771
+struct StepCtx
+{
+	float dt, inv_dt, h, inv_h;
+	int32_t subStepCount;
+	Soft contactSoftness, staticSoftness;
+	float restitutionThreshold, maxLinearVelocity;
+	int32_t enableWarmStarting;
+	int32_t awakeBodyCount, awakeContactCount, awakeJointCount;
+	int32_t colorBase[kColorCount + 1]; // constraint slot base per colour
+	int32_t activeColorCount;
+	int32_t activeColors[kColorCount];
+	int32_t bulletCount;
+	int32_t hitCandidateCount;
+	int32_t moveCount;
+	int32_t pairCount;
+	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
+};
+
+// Contact constraint storage: structure-of-arrays, field-major, one slot per touching contact, slots of one colour
+// contiguous (slot = colorBase[c] + index in colour). Field meaning follows b2ContactConstraintSIMD
+// (B2/src/contact_solver.c:1034-1064), one lane per slot.
+enum ConField : int
+{
+	cfInvMassA,
+	cfInvMassB,
+	cfInvIA,
+	cfInvIB,
+	cfNormalX,
+	cfNormalY,
+	cfFriction,
+	cfTangentSpeed,
+	cfRollingResistance,
+	cfRollingMass,
+	cfRollingImpulse,
+	cfBiasRate,
+	cfMassScale,
+	cfImpulseScale,
+	cfAnchorA1X,
+	cfAnchorA1Y,
+	cfAnchorB1X,
+	cfAnchorB1Y,
+	cfNormalMass1,
+	cfTangentMass1,
+	cfBaseSeparation1,
+	cfNormalImpulse1,
+	cfTotalNormalImpulse1,
+	cfTangentImpulse1,
+	cfAnchorA2X,
+	cfAnchorA2Y,
+	cfAnchorB2X,
+	cfAnchorB2Y,
+	cfBaseSeparation2,
+	cfNormalImpulse2,
+	cfTotalNormalImpulse2,
+	cfTangentImpulse2,
+	cfNormalMass2,
+	cfTangentMass2,
+	cfRestitution,
+	cfRelativeVelocity1,
+	cfRelativeVelocity2,
+	cfIndexA, // int bits
+	cfIndexB, // int bits
+	cfPointCount, // int bits (overflow path only)
+	cfFieldCount
+};
+
+enum : uint32_t
+{
+	kErrCapacity = 1,		 // a fixed-capacity array overflowed inside the step
+	kErrTreeStack = 2,		 // traversal stack overflow
+	kErrUnsupported = 4,	 // feature not available on the device path
+	kErrSleepPool = 8
+};
+
+// World parameters + every array. Reference: B2/src/world.h:44-175.
+struct World
+{
+	uint64_t magic;
+	uint64_t imageBytes;
+	uint32_t error;
+	int32_t errorDetail;
+
+	V2 gravity;
+	float hitEventThreshold, restitutionThreshold, maxLinearSpeed, maxContactPushSpeed, contactSpeed, contactHertz,
+		contactDampingRatio;
+	float inv_h;
+	uint64_t stepIndex;
+	int32_t splitIslandId, endEventArrayIndex;
+	uint16_t worldId, generation;
+	bool enableSleep, locked, enableWarmStarting, enableContinuous, enableSpeculative, inUse;
+	bool hasHostCallbacks;
+	int32_t taskCount;
+	int32_t hitEventCapable;	 // shapes with enableHitEvents (hit-event scan is skipped when 0)
+	int32_t contactEventCapable; // shapes with enableContactEvents (sizes the begin/end event arrays)
+
+	StepCtx step;
+
+	// entities (slot = id)
+	IdPool bodyIds, shapeIds, contactIds, jointIds, islandIds, setIds, chainIds;
+	Arr<Body> bodies;
+	Arr<BodySim> sims;
+	Arr<Shape> shapes;
+	Arr<Contact> contacts;
+	Arr<ContactSim> contactSims;
+	Arr<Joint> joints;
+	Arr<JointSim> jointSims;
+	Arr<Island> islands;
+	Arr<SolverSet> sets;
+
+	// set membership lists (ids)
+	Arr<int32_t> staticBodies, disabledBodies, awakeBodies;
+	Arr<BodyState> states; // aligned with awakeBodies
+	Arr<int32_t> awakeContacts;	   // awake, non-touching contacts
+	Arr<int32_t> disabledContacts; // non-touching contacts between sleeping bodies
+	Arr<int32_t> disabledJoints;
+	Arr<int32_t> staticJoints; // joints between two static bodies (joint.c:229-239)
+	Arr<int32_t> awakeIslands;
+	Arr<int32_t> sleepPool;
+	int32_t sleepHead, sleepTail, sleepUsed, pad0;
+
+	// constraint graph
+	Arr<int32_t> colorContacts[kColorCount];
+	Arr<int32_t> colorJoints[kColorCount];
+
+	// broadphase
+	Tree trees[3];
+	Arr<int32_t> moveArray;
+	Arr<int32_t> moveHeads;
+	Arr<MovePair> movePairs;
+
+	// events
+	Arr<BodyMoveEvent> moveEvents;
+	Arr<BeginTouchEvent> beginEvents;
+	Arr<EndTouchEvent> endEvents[2];
+	Arr<HitEvent> hitEvents;
+	Arr<SensorEvent> sensorBeginEvents;
+	Arr<SensorEvent> sensorEndEvents[2];
+
+	// per-step scratch
+	Arr<uint64_t> contactBits;	// contact state changes by contact id (world.c:548-553)
+	Arr<uint64_t> enlargedBits; // by awake index (solver.c:1835-1840)
+	Arr<uint64_t> islandBits;	// awake islands kept awake (solver.c:2024-2028)
+	Arr<float> cons;			// cfFieldCount x consStride
+	int32_t consStride, pad1;
+	Arr<int32_t> bullets;
+	Arr<int32_t> scan;	  // scan scratch (awake bodies + 1)
+	Arr<int32_t> scratch; // island split stacks
+};
+
+constexpr uint64_t kWorldMagic = 0x4632444232303042ull; // "F2DB200B"
+
+template <class T> F2D_HD T* ptr( World* w, const Arr<T>& a )
+{
+	return reinterpret_cast<T*>( reinterpret_cast<char*>( w ) + a.off );
+}
+template <class T> F2D_HD const T* ptr( const World* w, const Arr<T>& a )
+{
+	return reinterpret_cast<const T*>( reinterpret_cast<const char*>( w ) + a.off );
+}
+
+F2D_HD void setError( World* w, uint32_t bits, int detail )
+{
+	if ( ( w->error & bits ) == 0 )
+	{
+		w->errorDetail = detail;
+	}
+	w->error |= bits;
+}
+
+// push with capacity guard: on overflow flags the world and returns slot 0 so the caller stays in bounds
+template <class T> F2D_HD int push( World* w, Arr<T>& a, const T& v, int line )
+{
+	if ( a.count >= a.cap )
+	{
+		setError( w, kErrCapacity, line );
+		return a.cap > 0 ? a.cap - 1 : 0;
+	}
+	ptr( w, a )[a.count] = v;
+	return a.count++;
+}
+#define F2D_PUSH( w, arr, v ) ::f2d::push( w, arr, v, __LINE__ )
+
+// swap-remove with the reference's semantics (B2/src/array.h:91-103): returns the index that moved or kNull
+template <class T> F2D_HD int removeSwap( World* w, Arr<T>& a, int index )
+{
+	int moved = kNull;
+	T* d = ptr( w, a );
+	if ( index != a.count - 1 )
+	{
+		moved = a.count - 1;
+		d[index] = d[moved];
+	}
+	a.count -= 1;
+	return moved;
+}
+
+F2D_HD int allocId( World* w, IdPool& p )
+{
+	if ( p.free.count > 0 )
+	{
+		p.free.count -= 1;
+		return ptr( w, p.free )[p.free.count];
+	}
+	return p.next++;
+}
+F2D_HD void freeId( World* w, IdPool& p, int id )
+{
+	F2D_PUSH( w, p.free, id );
+}
+F2D_HD int idCount( const IdPool& p ) { return p.next - p.free.count; }
+
+F2D_HD int proxyType( int key ) { return key & 3; }
+F2D_HD int proxyId( int key ) { return key >> 2; }
+F2D_HD int proxyKey( int id, int type ) { return ( id << 2 ) | type; }
+
+} // namespace f2d

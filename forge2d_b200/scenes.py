@@ -1,0 +1,253 @@
+"""Synthetic scene generators for the five BASELINE.json configurations.
+
+Each builder issues the SAME b2* call sequence against whatever library it is handed (product, host emulation or
+the compiled reference), which is what makes bit-level parity comparisons meaningful.
+"""
+import ctypes as C
+from . import _abi as A
+
+TIME_STEP = 1.0 / 60.0
+SUB_STEPS = 4
+
+
+class Scene:
+    def __init__(self, lib, world, bodies, name):
+        self.lib, self.world, self.bodies, self.name = lib, world, bodies, name
+        self.frame = 0
+
+    def step(self, dt=TIME_STEP, sub=SUB_STEPS):
+        self.lib.b2World_Step(self.world, dt, sub)
+        self.frame += 1
+
+    def destroy(self):
+        self.lib.b2DestroyWorld(self.world)
+
+
+def _world(lib, enable_sleep=True, enable_continuous=True, gravity=(0.0, -10.0), create=None):
+    wd = lib.b2DefaultWorldDef()
+    wd.gravity = A.Vec2(*gravity)
+    wd.enableSleep = enable_sleep
+    wd.enableContinuous = enable_continuous
+    if create is not None:
+        return create(wd)
+    return lib.b2CreateWorld(C.byref(wd))
+
+
+def _static_segment(lib, world, p1, p2, origin=(0.0, 0.0)):
+    bd = lib.b2DefaultBodyDef()
+    bd.position = A.Vec2(*origin)
+    ground = lib.b2CreateBody(world, C.byref(bd))
+    sd = lib.b2DefaultShapeDef()
+    seg = A.Segment(A.Vec2(*p1), A.Vec2(*p2))
+    lib.b2CreateSegmentShape(ground, C.byref(sd), C.byref(seg))
+    return ground
+
+
+def _box(lib, half):
+    # Dart's Polygon.square/box goes through b2MakeOffsetRoundedBox (raw_box2d_ffi.dart:682-690)
+    return lib.b2MakeOffsetRoundedBox(half, half, A.Vec2(0.0, 0.0), A.Rot(1.0, 0.0), 0.0)
+
+
+def bench2d(lib, rows=40, ground_half_width=40.0, create=None, **world_kw):
+    """C1: packages/benchmark/bin/bench2d.dart:29-51 — `rows`-high pyramid of 0.5 half-extent boxes, density 5."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = [_static_segment(lib, world, (-ground_half_width, -30.0), (ground_half_width, -30.0))]
+    box = _box(lib, 0.5)
+    sd = lib.b2DefaultShapeDef()
+    sd.density = 5.0
+    x = [-7.0, 0.75]
+    dxx, dxy = 0.5625, 1.0
+    for i in range(rows):
+        y = list(x)
+        for _j in range(i, rows):
+            bd = lib.b2DefaultBodyDef()
+            bd.type = 2
+            bd.position = A.Vec2(_f32(y[0]), _f32(y[1]))
+            body = lib.b2CreateBody(world, C.byref(bd))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+            bodies.append(body)
+            y[0] = _f32(y[0] + 1.125)
+        x[0] = _f32(x[0] + dxx)
+        x[1] = _f32(x[1] + dxy)
+    return Scene(lib, world, bodies, "bench2d_%d" % rows)
+
+
+def _f32(v):
+    return C.c_float(v).value
+
+
+def large_pyramid(lib, rows=100, create=None, **world_kw):
+    """C2: the bench2d generator with 100 rows (5050 bodies) on a ground widened to +-200."""
+    s = bench2d(lib, rows=rows, ground_half_width=200.0, create=create, **world_kw)
+    s.name = "large_pyramid_%d" % rows
+    return s
+
+
+def many_pyramids(lib, grid=20, base=10, create=None, **world_kw):
+    """C3: grid x grid small pyramids (base `base`, boxes of half-extent 0.5 stacked touching), one ground segment
+    per row; upstream Box2D's many_pyramids layout. grid=20, base=10 -> 22 000 bodies, 400 islands."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = []
+    extent = 0.5
+    box = _box(lib, extent)
+    sd = lib.b2DefaultShapeDef()
+    bd0 = lib.b2DefaultBodyDef()
+    ground = lib.b2CreateBody(world, C.byref(bd0))
+    bodies.append(ground)
+    base_width = 2.0 * extent * base
+    base_y = 0.0
+    delta_x = 2.0 * extent * (base + 1.0)
+    delta_y = 2.0 * extent * (base + 1.0) + 5.0 * extent
+    total_width = delta_x * grid
+    for i in range(grid):
+        seg = A.Segment(A.Vec2(_f32(-0.5 * total_width - base_width), _f32(base_y + i * delta_y)),
+                        A.Vec2(_f32(0.5 * total_width + base_width), _f32(base_y + i * delta_y)))
+        lib.b2CreateSegmentShape(ground, C.byref(sd), C.byref(seg))
+    for i in range(grid):
+        row_y = base_y + i * delta_y
+        for j in range(grid):
+            center_x = -0.5 * total_width + j * delta_x + extent * base
+            for r in range(base):
+                y = (2.0 * r + 1.0) * extent + row_y
+                for c in range(r, base):
+                    x = (r + 1.0) * extent + 2.0 * (c - r) * extent + center_x - extent * base - 0.5
+                    bd = lib.b2DefaultBodyDef()
+                    bd.type = 2
+                    bd.position = A.Vec2(_f32(x), _f32(y))
+                    body = lib.b2CreateBody(world, C.byref(bd))
+                    lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+                    bodies.append(body)
+    return Scene(lib, world, bodies, "many_pyramids_%dx%d_b%d" % (grid, grid, base))
+
+
+class _Lcg:
+    """Fixed LCG so the rain is identical for every library (seed 12345)."""
+
+    def __init__(self, seed=12345):
+        self.s = seed
+
+    def next(self):
+        self.s = (1103515245 * self.s + 12345) & 0x7FFFFFFF
+        return self.s / float(0x7FFFFFFF)
+
+
+class JointGrid(Scene):
+    def __init__(self, lib, world, bodies, name, rain_every):
+        super().__init__(lib, world, bodies, name)
+        self.rng = _Lcg()
+        self.rain_every = rain_every
+        self.n = 0
+
+    def step(self, dt=TIME_STEP, sub=SUB_STEPS):
+        if self.rain_every > 0 and self.frame % self.rain_every == 0:
+            self._rain()
+        super().step(dt, sub)
+
+    def _rain(self):
+        lib, world = self.lib, self.world
+        sd = lib.b2DefaultShapeDef()
+        sd.filter.categoryBits = 1
+        sd.filter.maskBits = 0xFFFFFFFFFFFFFFFF
+        x0 = self.n * 0.5 * self.rng.next()
+        for kind in range(3):
+            bd = lib.b2DefaultBodyDef()
+            bd.type = 2
+            bd.position = A.Vec2(_f32(x0 + 10.0 + 15.0 * kind + 5.0 * self.rng.next()), _f32(5.0 + 2.0 * kind))
+            body = lib.b2CreateBody(world, C.byref(bd))
+            if kind == 0:
+                c = A.Circle(A.Vec2(0.0, 0.0), 0.25)
+                lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+            elif kind == 1:
+                cap = A.Capsule(A.Vec2(-0.25, 0.0), A.Vec2(0.25, 0.0), 0.2)
+                lib.b2CreateCapsuleShape(body, C.byref(sd), C.byref(cap))
+            else:
+                b = _box(lib, 0.3)
+                lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(b))
+            self.bodies.append(body)
+        self.n += 1
+
+
+def joint_grid(lib, n=100, rain_every=4, create=None, **world_kw):
+    """C4: n x n circles (r=0.4) on an integer grid linked to the up/left neighbour by revolute joints, 7 static
+    anchors in the top row, sleeping disabled; plus a rain of circle/capsule/box every `rain_every` frames."""
+    world_kw.setdefault("enable_sleep", False)
+    world = _world(lib, create=create, **world_kw)
+    bodies = []
+    sd = lib.b2DefaultShapeDef()
+    sd.filter.categoryBits = 2
+    sd.filter.maskBits = 0xFFFFFFFFFFFFFFFF & ~2
+    circle = A.Circle(A.Vec2(0.0, 0.0), 0.4)
+    jd = lib.b2DefaultRevoluteJointDef()
+    grid = [[None] * n for _ in range(n)]
+    lo, hi = n // 2 - 3, n // 2 + 3
+    for k in range(n):
+        for i in range(n):
+            bd = lib.b2DefaultBodyDef()
+            if lo <= k <= hi and i == 0:
+                bd.type = 0
+            else:
+                bd.type = 2
+            bd.position = A.Vec2(_f32(float(k)), _f32(float(-i)))
+            body = lib.b2CreateBody(world, C.byref(bd))
+            lib.b2CreateCircleShape(body, C.byref(sd), C.byref(circle))
+            grid[k][i] = body
+            bodies.append(body)
+            if i > 0:
+                jd.bodyIdA = grid[k][i - 1]
+                jd.bodyIdB = body
+                jd.localAnchorA = A.Vec2(0.0, -0.5)
+                jd.localAnchorB = A.Vec2(0.0, 0.5)
+                lib.b2CreateRevoluteJoint(world, C.byref(jd))
+            if k > 0:
+                jd.bodyIdA = grid[k - 1][i]
+                jd.bodyIdB = body
+                jd.localAnchorA = A.Vec2(0.5, 0.0)
+                jd.localAnchorB = A.Vec2(-0.5, 0.0)
+                lib.b2CreateRevoluteJoint(world, C.byref(jd))
+    return JointGrid(lib, world, bodies, "joint_grid_%d" % n, rain_every)
+
+
+def falling_shapes(lib, count=24, create=None, **world_kw):
+    """Small mixed-shape scene (circles, capsules, boxes, rounded boxes on a segment + a static box) used by the
+    parity tests to cover every manifold function on the device path."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = [_static_segment(lib, world, (-30.0, 0.0), (30.0, 0.0))]
+    bd = lib.b2DefaultBodyDef()
+    bd.position = A.Vec2(4.0, 1.0)
+    wall = lib.b2CreateBody(world, C.byref(bd))
+    sd = lib.b2DefaultShapeDef()
+    wbox = lib.b2MakeBox(0.5, 1.0)
+    lib.b2CreatePolygonShape(wall, C.byref(sd), C.byref(wbox))
+    bodies.append(wall)
+    rng = _Lcg(777)
+    sd.material.restitution = 0.3
+    for i in range(count):
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        bd.position = A.Vec2(_f32(-6.0 + 12.0 * rng.next()), _f32(2.0 + 1.2 * i))
+        bd.angularVelocity = _f32(2.0 * rng.next() - 1.0)
+        body = lib.b2CreateBody(world, C.byref(bd))
+        kind = i % 4
+        if kind == 0:
+            c = A.Circle(A.Vec2(0.0, 0.0), _f32(0.3 + 0.2 * rng.next()))
+            lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+        elif kind == 1:
+            cap = A.Capsule(A.Vec2(-0.4, 0.0), A.Vec2(0.4, 0.1), _f32(0.2 + 0.1 * rng.next()))
+            lib.b2CreateCapsuleShape(body, C.byref(sd), C.byref(cap))
+        elif kind == 2:
+            b = _box(lib, _f32(0.3 + 0.2 * rng.next()))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(b))
+        else:
+            b = lib.b2MakeOffsetRoundedBox(0.3, 0.2, A.Vec2(0.0, 0.0), A.Rot(1.0, 0.0), 0.1)
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(b))
+        bodies.append(body)
+    return Scene(lib, world, bodies, "falling_shapes_%d" % count)
+
+
+SCENES = {
+    "bench2d": bench2d,
+    "large_pyramid": large_pyramid,
+    "many_pyramids": many_pyramids,
+    "joint_grid": joint_grid,
+    "falling_shapes": falling_shapes,
+}
