@@ -1,0 +1,596 @@
+// forge2d_b200 — CUDA backend (sm_100a): kernels that run the team-parallel step phases of f2d_step.h on the GPU and
+// the host glue that keeps the device-resident world image in sync with the C ABI.
+//
+// Execution mapping (B200: 148 SMs, 227 KB smem/SM, 126 MB L2):
+//   * batch of worlds  -> one thread block per world (CtaTeam, `__syncthreads` between phases), grid = #worlds;
+//     worlds are independent, so there is no inter-block traffic at all and shards map 1:1 onto GPUs.
+//   * one small world  -> a single 1024-thread block (barrier cost ~tens of ns instead of a multi-us grid barrier;
+//     the whole working set of a bench2d-sized world lives in that SM's L1/L2).
+//   * one large world  -> a cooperative grid of one block per SM (GridTeam, grid-wide barrier between phases).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (no FMA contraction: bit parity with the
+// reference's SSE2 arithmetic).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include "f2d_capi.inl"
+
+namespace cg = cooperative_groups;
+
+namespace f2d
+{
+
+// ------------------------------------------------------------------------------------------------ device teams
+struct CtaTeam
+{
+	int32_t* smem; // blockDim.x + 32 ints of shared scratch
+	__device__ int rank() const { return (int)threadIdx.x; }
+	__device__ int size() const { return (int)blockDim.x; }
+	__device__ void sync() const { __syncthreads(); }
+	// in-place exclusive scan of data[0..n) in global memory; returns the total. Block-wide collective.
+	__device__ int exclusiveScan( int32_t* data, int n ) const
+	{
+		const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+		int32_t* warpSums = smem; // 32 entries
+		int carry = 0;
+		for ( int base = 0; base < n; base += nt )
+		{
+			int i = base + tid;
+			int v = i < n ? data[i] : 0;
+			// warp inclusive scan
+			int x = v;
+			for ( int off = 1; off < 32; off <<= 1 )
+			{
+				int y = __shfl_up_sync( 0xffffffffu, x, off );
+				if ( ( tid & 31 ) >= off )
+					x += y;
+			}
+			if ( ( tid & 31 ) == 31 )
+				warpSums[tid >> 5] = x;
+			__syncthreads();
+			if ( tid < 32 )
+			{
+				int ws = tid < ( nt >> 5 ) ? warpSums[tid] : 0;
+				int s = ws;
+				for ( int off = 1; off < 32; off <<= 1 )
+				{
+					int y = __shfl_up_sync( 0xffffffffu, s, off );
+					if ( tid >= off )
+						s += y;
+				}
+				warpSums[tid] = s - ws; // exclusive prefix of warp sums
+				if ( tid == 31 )
+					smem[32] = s; // chunk total
+			}
+			__syncthreads();
+			int excl = carry + warpSums[tid >> 5] + ( x - v );
+			if ( i < n )
+				data[i] = excl;
+			carry += smem[32];
+			__syncthreads();
+		}
+		return carry;
+	}
+};
+
+struct GridTeam
+{
+	int32_t* smem;
+	int32_t* blockTotals; // gridDim.x ints in global memory
+	__device__ int rank() const { return (int)( blockIdx.x * blockDim.x + threadIdx.x ); }
+	__device__ int size() const { return (int)( gridDim.x * blockDim.x ); }
+	__device__ void sync() const { cg::this_grid().sync(); }
+	__device__ int exclusiveScan( int32_t* data, int n ) const
+	{
+		// each block scans one contiguous tile, then tile offsets are added after a grid barrier
+		const int nb = (int)gridDim.x;
+		const int tile = ( n + nb - 1 ) / nb;
+		const int begin = min( n, (int)blockIdx.x * tile );
+		const int end = min( n, begin + tile );
+		CtaTeam cta{ smem };
+		int total = cta.exclusiveScan( data + begin, end - begin );
+		if ( threadIdx.x == 0 )
+			blockTotals[blockIdx.x] = total;
+		cg::this_grid().sync();
+		int offset = 0, sum = 0;
+		for ( int b = 0; b < nb; ++b )
+		{
+			int v = blockTotals[b];
+			if ( b < (int)blockIdx.x )
+				offset += v;
+			sum += v;
+		}
+		for ( int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x )
+			data[i] += offset;
+		cg::this_grid().sync();
+		return sum;
+	}
+};
+
+// ------------------------------------------------------------------------------------------------ kernels
+enum Phase
+{
+	kPhaseAll = 0,
+	kPhaseBeginPairs = 1,
+	kPhaseCollide = 2,
+	kPhaseSolve = 3,
+	kPhaseFinalize = 4
+};
+
+template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& t, int phase, float dt, int sub )
+{
+	if ( phase == kPhaseAll )
+	{
+		stepWorld( w, t, dt, sub );
+		return;
+	}
+	if ( dt == 0.0f )
+	{
+		if ( phase == kPhaseBeginPairs )
+			stepZeroDt( w, t );
+		return;
+	}
+	switch ( phase )
+	{
+		case kPhaseBeginPairs:
+			stepBegin( w, t, dt, sub );
+			stepPairs( w, t );
+			break;
+		case kPhaseCollide:
+			stepCollide( w, t );
+			break;
+		case kPhaseSolve:
+			stepSolve( w, t );
+			break;
+		case kPhaseFinalize:
+			stepFinalize( w, t );
+			break;
+	}
+}
+
+// One thread block per world; worlds are `stride` bytes apart. Grid-stride over worlds.
+template <int kThreads, int kMinBlocks>
+__global__ void __launch_bounds__( kThreads, kMinBlocks )
+	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps )
+{
+	__shared__ int32_t smem[64];
+	CtaTeam team{ smem };
+	for ( int wi = (int)blockIdx.x; wi < worldCount; wi += (int)gridDim.x )
+	{
+		World* w = reinterpret_cast<World*>( base + (unsigned long long)wi * stride );
+		for ( int s = 0; s < steps; ++s )
+		{
+			if ( w->error & ( kErrCapacity | kErrUnsupported ) )
+				break;
+			runPhase( w, team, phase, dt, sub );
+		}
+	}
+}
+
+// One cooperative grid per world.
+template <int kThreads>
+__global__ void __launch_bounds__( kThreads, 1 ) stepWorldGrid( World* w, int32_t* blockTotals, float dt, int sub, int phase )
+{
+	__shared__ int32_t smem[64];
+	GridTeam team{ smem, blockTotals };
+	if ( w->error & ( kErrCapacity | kErrUnsupported ) )
+		return;
+	runPhase( w, team, phase, dt, sub );
+}
+
+// Gathers the body move events of every world of a batch into one dense buffer (one block per world).
+__global__ void gatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies,
+								  int* counts )
+{
+	int wi = (int)blockIdx.x;
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	int n = min( w->moveEvents.count, maxBodies );
+	const BodyMoveEvent* src = ptr( w, w->moveEvents );
+	// 40-byte records copied as 8-byte words: coalesced, no struct padding games
+	const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>( src );
+	unsigned long long* d8 = reinterpret_cast<unsigned long long*>( out + (size_t)wi * maxBodies );
+	int words = n * (int)( sizeof( BodyMoveEvent ) / 8 );
+	for ( int i = (int)threadIdx.x; i < words; i += (int)blockDim.x )
+		d8[i] = s8[i];
+	if ( threadIdx.x == 0 )
+		counts[wi] = n;
+}
+
+__global__ void gatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out )
+{
+	int wi = (int)( blockIdx.x * blockDim.x + threadIdx.x );
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	if ( w->error )
+		atomicOr( out, w->error );
+}
+
+// ------------------------------------------------------------------------------------------------ host glue
+static int g_deviceState = -1; // -1 unknown, 0 none, 1 ok
+static int g_smCount = 0;
+
+static bool backendAvailable()
+{
+	if ( g_deviceState < 0 )
+	{
+		int n = 0;
+		cudaError_t e = cudaGetDeviceCount( &n );
+		if ( e != cudaSuccess || n == 0 )
+		{
+			cudaGetLastError();
+			g_deviceState = 0;
+		}
+		else
+		{
+			int dev = 0;
+			cudaGetDevice( &dev );
+			cudaDeviceGetAttribute( &g_smCount, cudaDevAttrMultiProcessorCount, dev );
+			g_deviceState = 1;
+		}
+	}
+	return g_deviceState == 1;
+}
+
+static bool cudaOk( cudaError_t e, const char* what )
+{
+	if ( e == cudaSuccess )
+		return true;
+	char buf[400];
+	snprintf( buf, sizeof( buf ), "CUDA error in %s: %s", what, cudaGetErrorString( e ) );
+	g_lastError = buf;
+	fprintf( stderr, "forge2d_b200: %s\n", buf );
+	return false;
+}
+
+// Host images are pinned when a device exists so that uploads/downloads run at full PCIe rate.
+static void* backendHostAlloc( size_t bytes )
+{
+	size_t total = bytes + 256;
+	char* raw = nullptr;
+	bool pinned = false;
+	if ( backendAvailable() )
+	{
+		void* p = nullptr;
+		if ( cudaMallocHost( &p, total ) == cudaSuccess )
+		{
+			raw = static_cast<char*>( p );
+			pinned = true;
+		}
+		else
+			cudaGetLastError();
+	}
+	if ( raw == nullptr )
+		raw = static_cast<char*>( aligned_alloc( 256, ( total + 255 ) / 256 * 256 ) );
+	raw[0] = pinned ? 1 : 0;
+	return raw + 256;
+}
+static void backendHostFree( void* p )
+{
+	if ( p == nullptr )
+		return;
+	char* raw = static_cast<char*>( p ) - 256;
+	if ( raw[0] == 1 )
+		cudaFreeHost( raw );
+	else
+		free( raw );
+}
+
+struct DeviceMirror
+{
+	World* dev = nullptr;
+	size_t devBytes = 0;
+	cudaStream_t stream = nullptr;
+	int32_t* blockTotals = nullptr;
+	cudaEvent_t ev[6] = {};
+	bool timing = false;
+	float times[5] = { 0, 0, 0, 0, 0 };
+};
+
+static DeviceMirror* mirror( HostWorld& hw )
+{
+	if ( hw.backend == nullptr )
+	{
+		DeviceMirror* m = new DeviceMirror();
+		cudaStreamCreateWithFlags( &m->stream, cudaStreamNonBlocking );
+		cudaMalloc( &m->blockTotals, 4096 * sizeof( int32_t ) );
+		for ( int i = 0; i < 6; ++i )
+			cudaEventCreate( &m->ev[i] );
+		hw.backend = m;
+	}
+	return static_cast<DeviceMirror*>( hw.backend );
+}
+
+constexpr int kSingleCtaThreads = 1024;
+constexpr int kBatchCtaThreads = 256;
+constexpr int kGridThreads = 512;
+
+static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int phase )
+{
+	int mode = hw.launchMode;
+	if ( mode < 0 )
+		mode = hw.img->awakeBodies.count + hw.img->shapeIds.next > 4096 ? 1 : 0;
+	g_launchCount += 1;
+	if ( mode == 0 )
+	{
+		stepWorldsCta<kSingleCtaThreads, 1>
+			<<<1, kSingleCtaThreads, 0, m->stream>>>( reinterpret_cast<char*>( m->dev ), 0ull, 1, dt, sub, phase, 1 );
+		return cudaOk( cudaGetLastError(), "stepWorldsCta launch" );
+	}
+	World* dev = m->dev;
+	int32_t* totals = m->blockTotals;
+	void* args[] = { &dev, &totals, &dt, &sub, &phase };
+	int blocks = g_smCount;
+	if ( blocks > 4096 )
+		blocks = 4096;
+	cudaError_t e = cudaLaunchCooperativeKernel( (void*)stepWorldGrid<kGridThreads>, dim3( blocks ), dim3( kGridThreads ), args, 0, m->stream );
+	return cudaOk( e, "stepWorldGrid cooperative launch" );
+}
+
+static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous )
+{
+	DeviceMirror* m = mirror( hw );
+	World* img = hw.img;
+	if ( hw.state == kHostNewer || m->dev == nullptr || m->devBytes != img->imageBytes )
+	{
+		if ( m->devBytes != img->imageBytes )
+		{
+			if ( m->dev )
+				cudaFree( m->dev );
+			m->dev = nullptr;
+			if ( cudaOk( cudaMalloc( &m->dev, img->imageBytes ), "cudaMalloc(world image)" ) == false )
+				return;
+			m->devBytes = img->imageBytes;
+		}
+		if ( cudaOk( cudaMemcpyAsync( m->dev, img, img->imageBytes, cudaMemcpyHostToDevice, m->stream ), "upload world image" ) == false )
+			return;
+	}
+	if ( m->timing )
+	{
+		cudaEventRecord( m->ev[0], m->stream );
+		for ( int p = kPhaseBeginPairs; p <= kPhaseFinalize; ++p )
+		{
+			launchWorld( hw, m, dt, subSteps, p );
+			cudaEventRecord( m->ev[p], m->stream );
+		}
+	}
+	else
+	{
+		launchWorld( hw, m, dt, subSteps, kPhaseAll );
+	}
+	// the header travels back with every step: counters, error flags, event counts, capacities in use
+	cudaMemcpyAsync( img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
+	hw.state = kDeviceNewer;
+	if ( synchronous )
+	{
+		cudaOk( cudaStreamSynchronize( m->stream ), "world step" );
+		if ( m->timing )
+		{
+			float total = 0.0f;
+			for ( int p = 1; p <= 4; ++p )
+			{
+				cudaEventElapsedTime( &m->times[p - 1], m->ev[p - 1], m->ev[p] );
+				total += m->times[p - 1];
+			}
+			m->times[4] = total;
+		}
+	}
+}
+
+static void backendSynchronize( HostWorld& hw )
+{
+	DeviceMirror* m = mirror( hw );
+	cudaOk( cudaStreamSynchronize( m->stream ), "synchronize" );
+}
+
+static void backendDownload( HostWorld& hw )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev == nullptr )
+		return;
+	cudaStreamSynchronize( m->stream );
+	cudaOk( cudaMemcpy( hw.img, m->dev, hw.img->imageBytes, cudaMemcpyDeviceToHost ), "download world image" );
+}
+
+static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev == nullptr || bytes == 0 )
+		return;
+	cudaMemcpyAsync( reinterpret_cast<char*>( hw.img ) + off, reinterpret_cast<const char*>( m->dev ) + off, bytes, cudaMemcpyDeviceToHost,
+					 m->stream );
+	cudaOk( cudaStreamSynchronize( m->stream ), "download range" );
+}
+
+static void backendRelease( HostWorld& hw )
+{
+	if ( hw.backend == nullptr )
+		return;
+	DeviceMirror* m = static_cast<DeviceMirror*>( hw.backend );
+	cudaStreamSynchronize( m->stream );
+	if ( m->dev )
+		cudaFree( m->dev );
+	cudaFree( m->blockTotals );
+	for ( int i = 0; i < 6; ++i )
+		cudaEventDestroy( m->ev[i] );
+	cudaStreamDestroy( m->stream );
+	delete m;
+	hw.backend = nullptr;
+}
+
+static void backendStepTimes( HostWorld& hw, float* out5 )
+{
+	DeviceMirror* m = mirror( hw );
+	for ( int i = 0; i < 5; ++i )
+		out5[i] = m->times[i];
+}
+static void backendEnableTiming( HostWorld& hw, bool flag )
+{
+	mirror( hw )->timing = flag;
+}
+
+} // namespace f2d
+
+// ------------------------------------------------------------------------------------------------ batch extension
+struct f2dBatch
+{
+	char* dev = nullptr;
+	unsigned long long stride = 0;
+	int count = 0;
+	cudaStream_t stream = nullptr;
+	f2d::BodyMoveEvent* devEvents = nullptr;
+	int* devCounts = nullptr;
+	int eventCap = 0;
+	unsigned int* devError = nullptr;
+	f2d::Caps caps{};
+};
+
+extern "C" {
+
+f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count )
+{
+	using namespace f2d;
+	HostWorld* hw = worldFromId( templateWorld );
+	if ( hw == nullptr || count <= 0 )
+		return nullptr;
+	if ( backendAvailable() == false )
+	{
+		reportError( "f2dBatch_Create: no CUDA device available - this library has no CPU fallback" );
+		return nullptr;
+	}
+	hostImage( *hw );
+	// every world of the batch keeps the template's capacities: leave room for the contacts the first steps create
+	reserve( *hw, 0, 0, 4 * hw->img->moveArray.count + hw->img->shapeIds.next + 256, 0 );
+	hw->state = kHostNewer;
+	World* img = hw->img;
+	f2dBatch* b = new f2dBatch();
+	b->count = count;
+	b->caps = hw->caps;
+	b->stride = ( img->imageBytes + 255ull ) / 256ull * 256ull;
+	if ( cudaOk( cudaMalloc( &b->dev, b->stride * (unsigned long long)count ), "cudaMalloc(batch)" ) == false )
+	{
+		delete b;
+		return nullptr;
+	}
+	cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking );
+	cudaMemcpyAsync( b->dev, img, img->imageBytes, cudaMemcpyHostToDevice, b->stream );
+	// replicate by doubling: log2(count) device-to-device copies
+	int have = 1;
+	while ( have < count )
+	{
+		int n = have < count - have ? have : count - have;
+		cudaMemcpyAsync( b->dev + b->stride * (unsigned long long)have, b->dev, b->stride * (unsigned long long)n, cudaMemcpyDeviceToDevice,
+						 b->stream );
+		have += n;
+	}
+	cudaMalloc( &b->devError, sizeof( unsigned int ) );
+	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
+	cudaOk( cudaStreamSynchronize( b->stream ), "batch upload" );
+	return b;
+}
+
+void f2dBatch_Destroy( f2dBatch* b )
+{
+	if ( b == nullptr )
+		return;
+	cudaStreamSynchronize( b->stream );
+	cudaFree( b->dev );
+	cudaFree( b->devEvents );
+	cudaFree( b->devCounts );
+	cudaFree( b->devError );
+	cudaStreamDestroy( b->stream );
+	delete b;
+}
+
+void f2dBatch_StepN( f2dBatch* b, float dt, int sub, int steps )
+{
+	using namespace f2d;
+	if ( b == nullptr )
+		return;
+	// one launch per step keeps every world of the batch in lock-step (and gives ncu one launch per step)
+	for ( int s = 0; s < steps; ++s )
+	{
+		stepWorldsCta<kBatchCtaThreads, 2><<<b->count, kBatchCtaThreads, 0, b->stream>>>( b->dev, b->stride, b->count, dt, sub, kPhaseAll, 1 );
+		g_launchCount += 1;
+	}
+	cudaOk( cudaGetLastError(), "stepWorldsCta(batch) launch" );
+}
+
+void f2dBatch_Step( f2dBatch* b, float dt, int sub )
+{
+	f2dBatch_StepN( b, dt, sub, 1 );
+	f2dBatch_Synchronize( b );
+}
+
+void f2dBatch_Synchronize( f2dBatch* b )
+{
+	if ( b )
+		f2d::cudaOk( cudaStreamSynchronize( b->stream ), "batch step" );
+}
+
+int f2dBatch_GetWorldCount( f2dBatch* b )
+{
+	return b ? b->count : 0;
+}
+
+int f2dBatch_GetBodyEvents( f2dBatch* b, b2BodyMoveEvent* out, int maxBodies, int* counts )
+{
+	using namespace f2d;
+	if ( b == nullptr )
+		return 0;
+	int need = b->count * maxBodies;
+	if ( need > b->eventCap )
+	{
+		cudaFree( b->devEvents );
+		cudaFree( b->devCounts );
+		cudaMalloc( &b->devEvents, (size_t)need * sizeof( BodyMoveEvent ) );
+		cudaMalloc( &b->devCounts, (size_t)b->count * sizeof( int ) );
+		b->eventCap = need;
+	}
+	gatherMoveEvents<<<b->count, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts );
+	g_launchCount += 1;
+	cudaMemcpyAsync( out, b->devEvents, (size_t)need * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost, b->stream );
+	cudaMemcpyAsync( counts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
+	cudaOk( cudaStreamSynchronize( b->stream ), "batch events" );
+	int total = 0;
+	for ( int i = 0; i < b->count; ++i )
+		total += counts[i];
+	return total;
+}
+
+void f2dBatch_DownloadWorld( f2dBatch* b, int index, b2WorldId into )
+{
+	using namespace f2d;
+	HostWorld* hw = worldFromId( into );
+	if ( b == nullptr || hw == nullptr || index < 0 || index >= b->count )
+		return;
+	cudaStreamSynchronize( b->stream );
+	World header;
+	cudaMemcpy( &header, b->dev + b->stride * (unsigned long long)index, sizeof( World ), cudaMemcpyDeviceToHost );
+	uint16_t worldId = hw->img->worldId, generation = hw->img->generation;
+	backendHostFree( hw->img );
+	hw->img = static_cast<World*>( backendHostAlloc( header.imageBytes ) );
+	cudaOk( cudaMemcpy( hw->img, b->dev + b->stride * (unsigned long long)index, header.imageBytes, cudaMemcpyDeviceToHost ),
+			"download batch world" );
+	hw->img->worldId = worldId;
+	hw->img->generation = generation;
+	hw->caps = b->caps;
+	hw->state = kHostNewer;
+}
+
+uint32_t f2dBatch_GetErrorFlags( f2dBatch* b )
+{
+	using namespace f2d;
+	if ( b == nullptr )
+		return 0;
+	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
+	gatherErrors<<<( b->count + 255 ) / 256, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devError );
+	g_launchCount += 1;
+	unsigned int e = 0;
+	cudaMemcpyAsync( &e, b->devError, sizeof( e ), cudaMemcpyDeviceToHost, b->stream );
+	cudaStreamSynchronize( b->stream );
+	return e;
+}
+
+} // extern "C"
