@@ -9,6 +9,7 @@
 #include "../../include/forge2d_b200.h"
 #include "../../include/forge2d_b200_debug.h"
 
+#include <float.h>
 #include <stdio.h>
 #include <string>
 
@@ -320,6 +321,135 @@ b2Polygon b2MakePolygon( const b2Hull* hull, float radius )
 	center = add( origin, center );
 	s.centroid = b2Vec2{ center.x, center.y };
 	return s;
+}
+} // extern "C"
+namespace f2d
+{
+// Quickhull over <= 8 welded points with the decision rules of B2/src/hull.c:13-82 (signed distance to the right of
+// the directed edge a->b, first-maximum tie rule, 2*slop rejection). Emits the chain strictly between a and b, in
+// order, through `emit`; the candidate list is passed by value so both sub-chains filter the same right-hand set.
+struct HullPoints
+{
+	V2 p[B2_MAX_POLYGON_VERTICES];
+	int n;
+};
+static void hullChain( V2 a, V2 b, HullPoints cand, b2Hull& out )
+{
+	if ( cand.n == 0 )
+		return;
+	V2 e = normalize( sub( b, a ) );
+	HullPoints right;
+	right.n = 0;
+	int best = 0;
+	float bestDistance = 0.0f;
+	for ( int i = 0; i < cand.n; ++i )
+	{
+		float d = cross( sub( cand.p[i], a ), e );
+		if ( i == 0 || d > bestDistance )
+		{
+			best = i;
+			bestDistance = d;
+		}
+		if ( d > 0.0f )
+			right.p[right.n++] = cand.p[i];
+	}
+	if ( bestDistance < 2.0f * kLinearSlop )
+		return;
+	V2 apex = cand.p[best];
+	hullChain( a, apex, right, out );
+	out.points[out.count++] = b2Vec2{ apex.x, apex.y };
+	hullChain( apex, b, right, out );
+}
+} // namespace f2d
+extern "C" {
+// collision.h:228, B2/src/hull.c:84-265: weld, pick two extreme points, quickhull both sides, drop collinear points.
+b2Hull b2ComputeHull( const b2Vec2* points, int count )
+{
+	b2Hull hull;
+	memset( &hull, 0, sizeof( hull ) );
+	if ( count < 3 || count > B2_MAX_POLYGON_VERTICES )
+		return hull;
+	const float tolSqr = 16.0f * kLinearSlop * kLinearSlop;
+	V2 lo = { FLT_MAX, FLT_MAX }, hi = { -FLT_MAX, -FLT_MAX };
+	HullPoints ps;
+	ps.n = 0;
+	for ( int i = 0; i < count; ++i )
+	{
+		V2 vi = { points[i].x, points[i].y };
+		lo = V2{ minf( lo.x, vi.x ), minf( lo.y, vi.y ) };
+		hi = V2{ maxf( hi.x, vi.x ), maxf( hi.y, vi.y ) };
+		bool unique = true;
+		for ( int j = 0; j < i && unique; ++j )
+			unique = !( distanceSq( vi, V2{ points[j].x, points[j].y } ) < tolSqr );
+		if ( unique )
+			ps.p[ps.n++] = vi;
+	}
+	if ( ps.n < 3 )
+		return hull;
+	// farthest point from the box centre, then the farthest point from it; each leaves the set by swap-with-last
+	auto takeFarthest = [&]( V2 from ) {
+		int f = 0;
+		float best = distanceSq( from, ps.p[0] );
+		for ( int i = 1; i < ps.n; ++i )
+		{
+			float d = distanceSq( from, ps.p[i] );
+			if ( d > best )
+			{
+				f = i;
+				best = d;
+			}
+		}
+		V2 r = ps.p[f];
+		ps.p[f] = ps.p[ps.n - 1];
+		ps.n -= 1;
+		return r;
+	};
+	V2 center = { 0.5f * ( lo.x + hi.x ), 0.5f * ( lo.y + hi.y ) };
+	V2 p1 = takeFarthest( center );
+	V2 p2 = takeFarthest( p1 );
+	HullPoints right, left;
+	right.n = left.n = 0;
+	V2 e = normalize( sub( p2, p1 ) );
+	for ( int i = 0; i < ps.n; ++i )
+	{
+		float d = cross( sub( ps.p[i], p1 ), e );
+		if ( d >= 2.0f * kLinearSlop )
+			right.p[right.n++] = ps.p[i];
+		else if ( d <= -2.0f * kLinearSlop )
+			left.p[left.n++] = ps.p[i];
+	}
+	b2Hull side1, side2;
+	side1.count = side2.count = 0;
+	hullChain( p1, p2, right, side1 );
+	hullChain( p2, p1, left, side2 );
+	if ( side1.count == 0 && side2.count == 0 )
+		return hull;
+	hull.points[hull.count++] = b2Vec2{ p1.x, p1.y };
+	for ( int i = 0; i < side1.count; ++i )
+		hull.points[hull.count++] = side1.points[i];
+	hull.points[hull.count++] = b2Vec2{ p2.x, p2.y };
+	for ( int i = 0; i < side2.count; ++i )
+		hull.points[hull.count++] = side2.points[i];
+	// remove nearly collinear middle points, restarting the scan after every removal
+	for ( int i = 0; hull.count > 2 && i < hull.count; )
+	{
+		int i2 = ( i + 1 ) % hull.count, i3 = ( i + 2 ) % hull.count;
+		V2 s1 = { hull.points[i].x, hull.points[i].y }, s2 = { hull.points[i2].x, hull.points[i2].y };
+		V2 s3 = { hull.points[i3].x, hull.points[i3].y };
+		V2 r = normalize( sub( s3, s1 ) );
+		if ( cross( sub( s2, s1 ), r ) <= 2.0f * kLinearSlop )
+		{
+			for ( int j = i2; j < hull.count - 1; ++j )
+				hull.points[j] = hull.points[j + 1];
+			hull.count -= 1;
+			i = 0;
+		}
+		else
+			i += 1;
+	}
+	if ( hull.count < 3 )
+		hull.count = 0;
+	return hull;
 }
 
 // ---- world -----------------------------------------------------------------------------------------------------

@@ -141,3 +141,22 @@ def diff(a, b, float_tol=0.0, skip=()):
                 out.append("%s.%s: %d rows differ, first row %d (id %s): %s vs %s" % (
                     key, name, len(rows), r, x[x.dtype.names[0]][r], xa[r], ya[r]))
     return out
+
+
+def state_hash(snap, keys=("bodies", "contacts", "islands", "shapes", "joints", "awake_order", "move_array",
+                           "awake_contacts", "awake_islands", "color_contact_counts", "color_joint_counts",
+                           "overflow_contacts")):
+    """sha256 over the records of a snapshot (floats canonicalised so that -0.0 hashes like +0.0)."""
+    import hashlib
+    h = hashlib.sha256()
+    for key in keys:
+        arr = snap[key]
+        if arr.dtype.names is None:
+            h.update(np.ascontiguousarray(arr).tobytes())
+            continue
+        for name in arr.dtype.names:
+            col = np.ascontiguousarray(arr[name])
+            if col.dtype.kind == "f":
+                col = col + np.float32(0.0)
+            h.update(col.tobytes())
+    return h.hexdigest()
