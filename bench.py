@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py — world-step throughput of the B200-native forge2d step (BASELINE.json metric) on synthetic scenes.
+
+Headline workload (config 5 of BASELINE.json): a batch of independent bench2d worlds (the exact scene of
+packages/benchmark/bin/bench2d.dart: 40-row pyramid, 820 boxes, dt = 1/60 s, 4 sub-steps), every world pre-rolled
+256 frames like the Dart harness's warm-up, sharded by world across the ranks with NO collective on the step path.
+One "step" = one b2World_Step of every world of the batch = one launch of the one-CTA-per-world kernel.
+
+  value     world-steps/s, whole job, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+  e2e       the same through the C ABI with HOST buffers: per step an H2D of the per-world step inputs (gravity) from
+            pinned memory, the step, and a D2H of every body's move event (transform) into pinned host memory
+  roofline  algorithmic bytes of SURVEY §8(d) per world-step x worlds per launch / average launch duration
+  cpu_baseline / --impl reference: the reference's own C (oracle/_ref, unmodified Box2D v3.1.1 as vendored by
+            forge2d) stepping a bounded sample of the same worlds on all host cores, one single-worker world per thread
+
+Extra keys report the single-world configurations (bench2d ms/frame through b2World_Step, large_pyramid and
+many_pyramids body-steps/s) with the reference timed beside them.
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from forge2d_b200 import _abi as A  # noqa: E402
+from forge2d_b200 import scenes  # noqa: E402
+
+DT, SUB = scenes.TIME_STEP, scenes.SUB_STEPS
+PREROLL = 256  # bench2d.dart:53-57 warm-up frames
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbox2d_ref.so")
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def shard(total, rank, world_size):
+    """Contiguous block of worlds for `rank` (world w -> GPU w*G/total)."""
+    lo = total * rank // world_size
+    hi = total * (rank + 1) // world_size
+    return lo, hi
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def algorithmic_bytes(counts):
+    """compulsory bytes of one world-step (each input read once, each output written once)."""
+    nb, ns, nc, nt, nj, moved = (counts[k] for k in ("awake_bodies", "awake_shapes", "awake_contacts", "touching",
+                                                      "joints", "moved"))
+    v_tree = 2 * ns + moved * max(1.0, math.log2(max(ns, 2)))
+    return 176.0 * nb + 104.0 * ns + 360.0 * nc + 156.0 * nt + 140.0 * nj + 40.0 * v_tree
+
+
+def world_counts(lib, world):
+    """Per-step work counters of one world, read through the introspection ABI."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import harness as H
+    snap = H.snapshot(lib, world, trees=False)
+    bodies, contacts = snap["bodies"], snap["contacts"]
+    awake_ids = set(snap["awake_order"].tolist())
+    awake_shapes = int(sum(1 for b in snap["shapes"]["bodyId"] if int(b) in awake_ids))
+    touching = int(snap["color_contact_counts"].sum())
+    return {"awake_bodies": int(len(snap["awake_order"])), "awake_shapes": awake_shapes,
+            "awake_contacts": touching + int(len(snap["awake_contacts"])), "touching": touching,
+            "joints": int(snap["color_joint_counts"].sum()), "moved": int(len(snap["move_array"])),
+            "bodies": int(len(bodies)), "contacts": int(len(contacts))}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_reference():
+    if not os.path.exists(REF_SO):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+        else:
+            raise RuntimeError("oracle/_ref/libbox2d_ref.so missing (build it in the container with /root/reference)")
+    lib = A.Library(REF_SO, "reference")
+    lib.dll.tap_step_worlds.restype = C.c_double
+    lib.dll.tap_step_worlds.argtypes = [C.POINTER(A.WorldId), C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+    lib.dll.tap_pool_create.restype = C.c_void_p
+    lib.dll.tap_pool_create.argtypes = [C.c_int]
+    lib.dll.tap_pool_destroy.argtypes = [C.c_void_p]
+    lib.dll.tap_create_world_mt.restype = A.WorldId
+    lib.dll.tap_create_world_mt.argtypes = [C.POINTER(A.WorldDef), C.c_void_p, C.c_int]
+    lib.dll.tap_step_mt.argtypes = [A.WorldId, C.c_float, C.c_int, C.c_void_p]
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def reference_batch(ref, sample_worlds, steps, warmup, threads):
+    """`sample_worlds` bench2d worlds at frame PREROLL stepped on `threads` host threads, one world per thread at a
+    time (1 Box2D worker each: the best case for the CPU). Returns world-steps/s."""
+    made = [scenes.bench2d(ref) for _ in range(sample_worlds)]
+    ids = (A.WorldId * sample_worlds)(*[s.world for s in made])
+    ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, PREROLL, threads)
+    if warmup > 0:
+        ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, warmup, threads)
+    seconds = ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, steps, threads)
+    for s in made:
+        s.destroy()
+    return sample_worlds * steps / seconds, seconds
+
+
+def reference_single(ref, scene_name, kw, warm, timed, workers):
+    """One world stepped by the reference with `workers` Box2D workers on a persistent pthread pool."""
+    pool = ref.dll.tap_pool_create(workers) if workers > 1 else None
+    create = (lambda wd: ref.dll.tap_create_world_mt(C.byref(wd), pool, workers)) if pool else None
+    s = scenes.SCENES[scene_name](ref, create=create, **kw)
+    step = (lambda: ref.dll.tap_step_mt(s.world, DT, SUB, pool)) if pool else s.step
+    for _ in range(warm):
+        step()
+    samples, awake = [], 0
+    for _ in range(timed):
+        t0 = time.perf_counter()
+        step()
+        samples.append(time.perf_counter() - t0)
+        awake += ref.b2World_GetAwakeBodyCount(s.world)
+    s.destroy()
+    if pool:
+        ref.dll.tap_pool_destroy(pool)
+    return samples, awake
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    ref = load_reference()
+    cores = host_cores()
+    sample = args.ref_worlds or max(cores, min(8 * cores, 512))
+    value, seconds = reference_batch(ref, sample, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_note="reference arm steps a bounded sample of %d worlds" % sample),
+        "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": cores, "kind": "reference",
+                         "sample": "%d bench2d worlds at frame %d, %d steps each, one single-worker world per thread on %d "
+                                   "threads (%s)" % (sample, PREROLL, args.steps, cores, cpu_model())},
+        "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, sample_note=None):
+    cfg = {"workload": "bench2d_batch: %d independent bench2d worlds (40-row pyramid, 820 boxes, dt=1/60, 4 sub-steps) "
+                       "pre-rolled %d frames, sharded by world across ranks" % (args.worlds, PREROLL),
+           "worlds": args.worlds, "bodies_per_world": 821, "substeps": SUB, "parallelism": "world-sharded x%d" % args.gpus,
+           "l2": "inputs larger than L2 (every world image is touched once per step; batch >> 126 MB)"}
+    if sample_note:
+        cfg["sample"] = sample_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def single_world_numbers(lib, ref, name, kw, warm, timed, mode, cores):
+    """Single-world configuration through b2World_Step (synchronous C-ABI call, as World.step makes it), with the
+    reference (1 worker = what forge2d ships; all cores = pthread pool) timed on the same scene."""
+    s = scenes.SCENES[name](lib, **kw)
+    lib.f2dWorld_SetLaunchMode(s.world, mode)
+    for _ in range(warm):
+        s.step()
+    samples, awake = [], 0
+    for _ in range(timed):
+        t0 = time.perf_counter()
+        s.step()
+        samples.append(time.perf_counter() - t0)
+        awake += lib.b2World_GetAwakeBodyCount(s.world)
+    counts = world_counts(lib, s.world)
+    err = lib.f2dGetLastError().decode()
+    s.destroy()
+    out = {"frames": timed, "warmup_frames": warm, "launch_mode": {0: "one CTA", 1: "cooperative grid", -1: "auto"}[mode],
+           "ms_per_frame_mean": 1e3 * sum(samples) / timed, "ms_per_frame_p5": 1e3 * sorted(samples)[int(0.05 * timed)],
+           "ms_per_frame_p95": 1e3 * sorted(samples)[int(0.95 * timed)], "body_steps_per_s": awake / sum(samples),
+           "bodies": counts["bodies"], "contacts": counts["contacts"], "error": err or None}
+    if ref is not None:
+        for label, workers in (("ref_1worker", 1), ("ref_allcores", cores)):
+            rs, ra = reference_single(ref, name, kw, warm, timed, workers)
+            out[label] = {"workers": workers, "ms_per_frame_mean": 1e3 * sum(rs) / timed, "body_steps_per_s": ra / sum(rs)}
+    return out
+
+
+def run_b200_arm(args, rank, world_size, local_rank):
+    import forge2d_b200
+    lib = forge2d_b200.load_library()
+    if not lib.f2dSetDevice(local_rank):
+        raise RuntimeError("bench: CUDA device %d not usable - forge2d_b200 has no CPU fallback" % local_rank)
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    lo, hi = shard(args.worlds, rank, world_size)
+    mine = hi - lo
+
+    # template world pre-rolled like bench2d.dart's warm-up, then replicated into the batch (HBM resident)
+    template = scenes.bench2d(lib)
+    for _ in range(PREROLL):
+        template.step()
+    counts0 = world_counts(lib, template.world)
+    batch = lib.f2dBatch_Create(template.world, mine)
+    if not batch:
+        raise RuntimeError("bench: f2dBatch_Create failed: %s" % lib.f2dGetLastError().decode())
+    world_bytes = lib.f2dBatch_GetWorldBytes(batch)
+
+    lib.f2dBatch_StepN(batch, DT, SUB, args.warmup)
+    lib.f2dBatch_Synchronize(batch)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.f2dWorld_GetKernelLaunchCount()
+    barrier()
+    lib.f2dBatch_Synchronize(batch)
+    lib.f2dBatch_EventRecord(batch, 0)
+    lib.f2dBatch_StepN(batch, DT, SUB, args.steps)
+    lib.f2dBatch_EventRecord(batch, 1)
+    lib.f2dBatch_Synchronize(batch)
+    barrier()
+    ms_local = lib.f2dBatch_EventElapsedMs(batch, 0, 1)
+    launches = lib.f2dWorld_GetKernelLaunchCount() - launches0
+    ms = max_over_ranks(ms_local)
+    clocks = sampler.stop() if rank == 0 else None
+    errors = lib.f2dBatch_GetErrorFlags(batch)
+
+    # counters after the timed region (average with the ones before for the roofline's per-step work)
+    scratch = scenes.bench2d(lib, rows=1)
+    lib.f2dBatch_DownloadWorld(batch, 0, scratch.world)
+    counts1 = world_counts(lib, scratch.world)
+    bytes_per_world_step = 0.5 * (algorithmic_bytes(counts0) + algorithmic_bytes(counts1))
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    nb = counts0["bodies"]
+    gravity = lib.f2dHostAlloc(8 * mine)
+    grav = (A.Vec2 * mine).from_address(gravity)
+    for i in range(mine):
+        grav[i] = A.Vec2(0.0, -10.0)
+    ev_ptr, cnt_ptr = C.POINTER(A.BodyMoveEvent)(), C.POINTER(C.c_int)()
+    lib.f2dBatch_SetGravity(batch, gravity, mine)
+    lib.f2dBatch_Step(batch, DT, SUB)
+    lib.f2dBatch_ReadBodyEvents(batch, nb, C.byref(ev_ptr), C.byref(cnt_ptr))  # allocates the pinned staging
+    barrier()
+    t0 = time.perf_counter()
+    moved = 0
+    for _ in range(e2e_steps):
+        lib.f2dBatch_SetGravity(batch, gravity, mine)
+        lib.f2dBatch_Step(batch, DT, SUB)
+        moved = lib.f2dBatch_ReadBodyEvents(batch, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = args.worlds * e2e_steps / e2e_seconds
+    lib.f2dHostFree(gravity)
+    lib.f2dBatch_Destroy(batch)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ms_per_step = ms / args.steps
+    achieved = bytes_per_world_step * mine / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if prof.get("worlds_per_launch"):
+            traffic = prof["dram_bytes_per_launch"] * mine / prof["worlds_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+
+    line = {
+        "metric": "world_steps_per_s", "value": args.worlds * args.steps / (ms * 1e-3), "unit": "world-steps/s",
+        "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": 8 * mine,
+                "d2h_bytes_per_step": mine * nb * C.sizeof(A.BodyMoveEvent) + 4 * mine, "steps": e2e_steps,
+                "path": "f2dBatch_SetGravity (pinned H2D) + f2dBatch_Step + f2dBatch_ReadBodyEvents (pinned D2H of every "
+                        "body transform), per rank; events read per step: %d" % moved},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "stepWorldsCta<256,2> (whole world step, one CTA per world)",
+                     "algorithmic_bytes_per_world_step": bytes_per_world_step, "worlds_per_launch": mine,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                     "note": "per-world working set (%.1f MB image) is re-touched ~100x per step out of L1/L2, so DRAM "
+                             "bandwidth is not the limiter; the step is bound by serial depth per world" % (world_bytes / 1e6)},
+        "clocks": clocks,
+        "batch": {"worlds_this_rank": mine, "bytes_per_world_image": int(world_bytes), "error_flags": int(errors),
+                  "counts_before": counts0, "counts_after": counts1},
+    }
+
+    ref = None
+    cores = host_cores()
+    if world_size == 1 and not args.no_cpu_baseline:
+        ref = load_reference()
+        sample = args.ref_worlds or max(cores, min(4 * cores, 256))
+        v, seconds = reference_batch(ref, sample, max(8, min(args.steps, 32)), 2, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "reference",
+                                "sample": "%d bench2d worlds at frame %d x %d steps, one single-worker world per thread "
+                                          "on %d threads (%s), %.1f s" % (sample, PREROLL, max(8, min(args.steps, 32)), cores,
+                                                                          cpu_model(), seconds)}
+    if world_size == 1 and not args.no_extras:
+        extras = {}
+        extras["bench2d"] = single_world_numbers(lib, ref, "bench2d", {}, 256, 256, 0, cores)
+        extras["large_pyramid"] = single_world_numbers(lib, ref, "large_pyramid", {}, 32, 64, 1, cores)
+        extras["many_pyramids_awake"] = single_world_numbers(lib, ref, "many_pyramids", {}, 2, 24, 1, cores)
+        extras["joint_grid"] = single_world_numbers(lib, ref, "joint_grid", {}, 8, 32, 1, cores)
+        line["single_world"] = extras
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=8192, help="total worlds of the batch (sharded across ranks)")
+    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--ref-worlds", type=int, default=0, help="worlds in the CPU sample (0 = scaled to the host cores)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the single-world configurations")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup)
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+    else:
+        run_b200_arm(args, rank, world_size, local_rank)
+
+
+if __name__ == "__main__":
+    main()

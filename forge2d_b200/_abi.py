@@ -262,6 +262,14 @@ F2D_FUNCTIONS = {
     "f2dBatch_GetWorldCount": (c_int, [c_void_p]),
     "f2dBatch_GetBodyEvents": (c_int, [c_void_p, C.POINTER(BodyMoveEvent), c_int, C.POINTER(c_int)]),
     "f2dBatch_DownloadWorld": (None, [c_void_p, c_int, WorldId]),
+    "f2dBatch_ReadBodyEvents": (c_int, [c_void_p, c_int, C.POINTER(C.POINTER(BodyMoveEvent)), C.POINTER(C.POINTER(c_int))]),
+    "f2dBatch_SetGravity": (None, [c_void_p, c_void_p, c_int]),
+    "f2dBatch_EventRecord": (None, [c_void_p, c_int]),
+    "f2dBatch_EventElapsedMs": (c_float, [c_void_p, c_int, c_int]),
+    "f2dBatch_GetWorldBytes": (C.c_ulonglong, [c_void_p]),
+    "f2dSetDevice": (c_int, [c_int]),
+    "f2dHostAlloc": (c_void_p, [C.c_ulonglong]),
+    "f2dHostFree": (None, [c_void_p]),
     "f2dBatch_GetErrorFlags": (C.c_uint32, [c_void_p]),
     "f2dHasDevice": (c_int, []),
     "f2dGetLastError": (C.c_char_p, []),

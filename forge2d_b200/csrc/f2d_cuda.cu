@@ -11,6 +11,7 @@
 // reference's SSE2 arithmetic).
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 
 #include "f2d_capi.inl"
 
@@ -444,6 +445,10 @@ struct f2dBatch
 	int eventCap = 0;
 	unsigned int* devError = nullptr;
 	f2d::Caps caps{};
+	cudaEvent_t events[8] = {};
+	b2BodyMoveEvent* hostEvents = nullptr; // pinned staging for f2dBatch_ReadBodyEvents
+	int* hostCounts = nullptr;
+	int hostEventCap = 0;
 };
 
 extern "C" {
@@ -474,6 +479,8 @@ f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count )
 		return nullptr;
 	}
 	cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking );
+	for ( int i = 0; i < 8; ++i )
+		cudaEventCreate( &b->events[i] );
 	cudaMemcpyAsync( b->dev, img, img->imageBytes, cudaMemcpyHostToDevice, b->stream );
 	// replicate by doubling: log2(count) device-to-device copies
 	int have = 1;
@@ -499,6 +506,12 @@ void f2dBatch_Destroy( f2dBatch* b )
 	cudaFree( b->devEvents );
 	cudaFree( b->devCounts );
 	cudaFree( b->devError );
+	if ( b->hostEvents )
+		cudaFreeHost( b->hostEvents );
+	if ( b->hostCounts )
+		cudaFreeHost( b->hostCounts );
+	for ( int i = 0; i < 8; ++i )
+		cudaEventDestroy( b->events[i] );
 	cudaStreamDestroy( b->stream );
 	delete b;
 }
@@ -557,6 +570,100 @@ int f2dBatch_GetBodyEvents( f2dBatch* b, b2BodyMoveEvent* out, int maxBodies, in
 	for ( int i = 0; i < b->count; ++i )
 		total += counts[i];
 	return total;
+}
+
+// Same gather, but into a pinned staging buffer owned by the batch (full PCIe rate); like the reference's event arrays
+// the returned pointers stay valid until the next call (B2/src/world.c:1491-1555 ownership rule).
+int f2dBatch_ReadBodyEvents( f2dBatch* b, int maxBodies, const b2BodyMoveEvent** outEvents, const int** outCounts )
+{
+	using namespace f2d;
+	if ( b == nullptr )
+		return 0;
+	int need = b->count * maxBodies;
+	if ( need > b->eventCap )
+	{
+		cudaFree( b->devEvents );
+		cudaFree( b->devCounts );
+		cudaMalloc( &b->devEvents, (size_t)need * sizeof( BodyMoveEvent ) );
+		cudaMalloc( &b->devCounts, (size_t)b->count * sizeof( int ) );
+		b->eventCap = need;
+	}
+	if ( need > b->hostEventCap )
+	{
+		if ( b->hostEvents )
+			cudaFreeHost( b->hostEvents );
+		if ( b->hostCounts )
+			cudaFreeHost( b->hostCounts );
+		cudaMallocHost( &b->hostEvents, (size_t)need * sizeof( BodyMoveEvent ) );
+		cudaMallocHost( &b->hostCounts, (size_t)b->count * sizeof( int ) );
+		b->hostEventCap = need;
+	}
+	gatherMoveEvents<<<b->count, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts );
+	g_launchCount += 1;
+	cudaMemcpyAsync( b->hostEvents, b->devEvents, (size_t)need * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost, b->stream );
+	cudaMemcpyAsync( b->hostCounts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
+	cudaOk( cudaStreamSynchronize( b->stream ), "batch events" );
+	*outEvents = b->hostEvents;
+	*outCounts = b->hostCounts;
+	int total = 0;
+	for ( int i = 0; i < b->count; ++i )
+		total += b->hostCounts[i];
+	return total;
+}
+
+// Per-world gravity (the batch counterpart of b2World_SetGravity, box2d.h:135): one strided host->device copy that
+// patches World::gravity of every image; queued on the batch stream ahead of the next step.
+void f2dBatch_SetGravity( f2dBatch* b, const b2Vec2* gravity, int count )
+{
+	using namespace f2d;
+	if ( b == nullptr || count <= 0 )
+		return;
+	if ( count > b->count )
+		count = b->count;
+	cudaOk( cudaMemcpy2DAsync( b->dev + offsetof( World, gravity ), b->stride, gravity, sizeof( b2Vec2 ), sizeof( b2Vec2 ), (size_t)count,
+							   cudaMemcpyHostToDevice, b->stream ),
+			"batch gravity upload" );
+}
+
+void f2dBatch_EventRecord( f2dBatch* b, int slot )
+{
+	if ( b && slot >= 0 && slot < 8 )
+		cudaEventRecord( b->events[slot], b->stream );
+}
+float f2dBatch_EventElapsedMs( f2dBatch* b, int from, int to )
+{
+	float ms = -1.0f;
+	if ( b && from >= 0 && from < 8 && to >= 0 && to < 8 )
+	{
+		cudaEventSynchronize( b->events[to] );
+		cudaEventElapsedTime( &ms, b->events[from], b->events[to] );
+	}
+	return ms;
+}
+unsigned long long f2dBatch_GetWorldBytes( f2dBatch* b )
+{
+	return b ? b->stride : 0ull;
+}
+
+int f2dSetDevice( int device )
+{
+	f2d::g_deviceState = -1;
+	return cudaSetDevice( device ) == cudaSuccess && f2d::backendAvailable() ? 1 : 0;
+}
+void* f2dHostAlloc( unsigned long long bytes )
+{
+	void* p = nullptr;
+	if ( cudaMallocHost( &p, (size_t)bytes ) != cudaSuccess )
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+void f2dHostFree( void* p )
+{
+	if ( p )
+		cudaFreeHost( p );
 }
 
 void f2dBatch_DownloadWorld( f2dBatch* b, int index, b2WorldId into )

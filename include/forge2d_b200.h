@@ -240,6 +240,14 @@ F2D_API void f2dBatch_Synchronize( f2dBatch* batch );
 F2D_API int f2dBatch_GetWorldCount( f2dBatch* batch );
 /// Body move events of every world -> host buffer: `out` receives count*maxBodies records, `counts[w]` valid ones.
 F2D_API int f2dBatch_GetBodyEvents( f2dBatch* batch, b2BodyMoveEvent* out, int maxBodiesPerWorld, int* counts );
+/// Same records through a pinned staging buffer owned by the batch; pointers valid until the next call.
+F2D_API int f2dBatch_ReadBodyEvents( f2dBatch* batch, int maxBodiesPerWorld, const b2BodyMoveEvent** outEvents, const int** outCounts );
+/// Per-world gravity: the batch counterpart of b2World_SetGravity (box2d.h:135); `gravity` holds `count` vectors.
+F2D_API void f2dBatch_SetGravity( f2dBatch* batch, const b2Vec2* gravity, int count );
+/// CUDA events on the batch's stream (slots 0..7) so callers can time device work without a torch stream.
+F2D_API void f2dBatch_EventRecord( f2dBatch* batch, int slot );
+F2D_API float f2dBatch_EventElapsedMs( f2dBatch* batch, int fromSlot, int toSlot );
+F2D_API unsigned long long f2dBatch_GetWorldBytes( f2dBatch* batch ); ///< HBM bytes per world image
 /// Copies world `index` of the batch back into an ordinary world (inspection, parity tests).
 F2D_API void f2dBatch_DownloadWorld( f2dBatch* batch, int index, b2WorldId into );
 /// Per-world x-translation of every body by `index * dx` (decorrelates otherwise identical worlds).
@@ -247,6 +255,9 @@ F2D_API uint32_t f2dBatch_GetErrorFlags( f2dBatch* batch );
 
 /// Library diagnostics
 F2D_API int f2dHasDevice( void );			///< 1 when a CUDA device is usable
+F2D_API int f2dSetDevice( int device );		///< selects the CUDA device of the calling thread (one process per GPU)
+F2D_API void* f2dHostAlloc( unsigned long long bytes ); ///< pinned host memory for batch inputs
+F2D_API void f2dHostFree( void* p );
 F2D_API const char* f2dGetLastError( void ); ///< last error message ("" if none)
 F2D_API void f2dClearLastError( void );
 /// 0 = one block per world (default for small worlds), 1 = cooperative grid per world, -1 = automatic

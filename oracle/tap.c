@@ -561,3 +561,48 @@ TAP_API void tap_step_mt( b2WorldId id, float dt, int subSteps, void* pool )
 	tap_pool_begin_step( pool );
 	b2World_Step( id, dt, subSteps );
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Batch-of-worlds CPU baseline ("one single-worker world per thread, round-robin"): `threads`
+// pthreads, thread t steps worlds t, t+threads, ... `steps` times each. Returns the wall time in seconds.
+#include <time.h>
+typedef struct tapBatchArg
+{
+	const b2WorldId* ids;
+	int count, first, stride, steps, subSteps;
+	float dt;
+} tapBatchArg;
+
+static void* tapBatchMain( void* p )
+{
+	tapBatchArg* a = p;
+	for ( int s = 0; s < a->steps; ++s )
+		for ( int i = a->first; i < a->count; i += a->stride )
+			b2World_Step( a->ids[i], a->dt, a->subSteps );
+	return NULL;
+}
+
+TAP_API double tap_step_worlds( const b2WorldId* ids, int count, float dt, int subSteps, int steps, int threads )
+{
+	if ( threads < 1 )
+		threads = 1;
+	if ( threads > TAP_MAX_THREADS )
+		threads = TAP_MAX_THREADS;
+	if ( threads > count )
+		threads = count;
+	pthread_t th[TAP_MAX_THREADS];
+	tapBatchArg args[TAP_MAX_THREADS];
+	struct timespec t0, t1;
+	clock_gettime( CLOCK_MONOTONIC, &t0 );
+	for ( int t = 0; t < threads; ++t )
+	{
+		args[t] = ( tapBatchArg ){ ids, count, t, threads, steps, subSteps, dt };
+		if ( t > 0 )
+			pthread_create( th + t, NULL, tapBatchMain, args + t );
+	}
+	tapBatchMain( args );
+	for ( int t = 1; t < threads; ++t )
+		pthread_join( th[t], NULL );
+	clock_gettime( CLOCK_MONOTONIC, &t1 );
+	return (double)( t1.tv_sec - t0.tv_sec ) + 1e-9 * (double)( t1.tv_nsec - t0.tv_nsec );
+}

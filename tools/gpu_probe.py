@@ -1,0 +1,63 @@
+"""Quick GPU timing probe (development aid): single-world ms/frame per launch mode and batch-step time vs batch size."""
+import ctypes as C
+import sys
+import time
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import forge2d_b200
+from forge2d_b200 import scenes
+
+lib = forge2d_b200.load_library()
+assert lib.f2dHasDevice()
+what = sys.argv[1:] or ["single", "batch"]
+
+
+def single(name, kw, mode, warm, timed):
+    s = scenes.SCENES[name](lib, **kw)
+    lib.f2dWorld_SetLaunchMode(s.world, mode)
+    lib.f2dWorld_EnablePhaseTiming(s.world, True)
+    t0 = time.perf_counter()
+    s.step()
+    first = time.perf_counter() - t0
+    for _ in range(warm):
+        s.step()
+    acc = [0.0] * 5
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        s.step()
+        t = (C.c_float * 5)()
+        lib.f2dWorld_GetLastStepTimes(s.world, t)
+        for i in range(5):
+            acc[i] += t[i]
+    wall = (time.perf_counter() - t0) / timed * 1e3
+    print("%-16s %-22s mode %d: first %.2f ms, wall %.3f ms/frame, device phases [pairs %.3f collide %.3f solve %.3f finalize %.3f] total %.3f ms; err=%r"
+          % (name, kw, mode, first * 1e3, wall, *[a / timed for a in acc], lib.f2dGetLastError()), flush=True)
+    s.destroy()
+
+
+if "single" in what:
+    single("bench2d", {}, 0, 256, 64)
+    single("bench2d", {}, 1, 256, 64)
+    single("bench2d", dict(rows=10), 0, 64, 64)
+    single("large_pyramid", {}, 1, 16, 16)
+    single("large_pyramid", {}, 0, 4, 8)
+    single("many_pyramids", {}, 1, 2, 8)
+    single("joint_grid", {}, 1, 4, 8)
+
+if "batch" in what:
+    t = scenes.bench2d(lib)
+    for _ in range(256):
+        t.step()
+    for count in (148, 296, 592, 1184, 2368):
+        b = lib.f2dBatch_Create(t.world, count)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 2)
+        lib.f2dBatch_Synchronize(b)
+        lib.f2dBatch_EventRecord(b, 0)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 4)
+        lib.f2dBatch_EventRecord(b, 1)
+        lib.f2dBatch_Synchronize(b)
+        ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / 4
+        print("batch %5d worlds: %.3f ms/step -> %.0f world-steps/s (image %.2f MB) err=%x" % (
+            count, ms, count / ms * 1e3, lib.f2dBatch_GetWorldBytes(b) / 1e6, lib.f2dBatch_GetErrorFlags(b)), flush=True)
+        lib.f2dBatch_Destroy(b)
