@@ -281,6 +281,8 @@ def run_b200_arm(args, rank, world_size, local_rank):
     if not batch:
         raise RuntimeError("bench: f2dBatch_Create failed: %s" % lib.f2dGetLastError().decode())
     world_bytes = lib.f2dBatch_GetWorldBytes(batch)
+    if not lib.f2dBatch_SetLaunchConfig(batch, args.batch_threads, args.batch_blocks_per_sm):
+        raise RuntimeError("bench: unknown batch launch config %dx%d" % (args.batch_threads, args.batch_blocks_per_sm))
 
     lib.f2dBatch_StepN(batch, DT, SUB, args.warmup)
     lib.f2dBatch_Synchronize(batch)
@@ -364,7 +366,7 @@ def run_b200_arm(args, rank, world_size, local_rank):
                         "body transform), per rank; events read per step: %d" % moved},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "stepWorldsCta<256,2> (whole world step, one CTA per world)",
+                     "traffic": traffic, "kernel": "stepWorldsCta<%d,%d> (whole world step, one CTA per world)" % (args.batch_threads, args.batch_blocks_per_sm),
                      "algorithmic_bytes_per_world_step": bytes_per_world_step, "worlds_per_launch": mine,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "note": "per-world working set (%.1f MB image) is re-touched ~100x per step out of L1/L2, so DRAM "
@@ -404,6 +406,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=8192, help="total worlds of the batch (sharded across ranks)")
     ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--batch-threads", type=int, default=64, help="threads per world of the batch kernel")
+    ap.add_argument("--batch-blocks-per-sm", type=int, default=16, help="resident worlds per SM the kernel is built for")
     ap.add_argument("--ref-worlds", type=int, default=0, help="worlds in the CPU sample (0 = scaled to the host cores)")
     ap.add_argument("--no-extras", action="store_true", help="skip the single-world configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")

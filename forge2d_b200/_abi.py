@@ -259,6 +259,7 @@ F2D_FUNCTIONS = {
     "f2dBatch_Step": (None, [c_void_p, c_float, c_int]),
     "f2dBatch_StepN": (None, [c_void_p, c_float, c_int, c_int]),
     "f2dBatch_Synchronize": (None, [c_void_p]),
+    "f2dBatch_SetLaunchConfig": (c_int, [c_void_p, c_int, c_int]),
     "f2dBatch_GetWorldCount": (c_int, [c_void_p]),
     "f2dBatch_GetBodyEvents": (c_int, [c_void_p, C.POINTER(BodyMoveEvent), c_int, C.POINTER(c_int)]),
     "f2dBatch_DownloadWorld": (None, [c_void_p, c_int, WorldId]),
@@ -279,6 +280,8 @@ F2D_FUNCTIONS = {
     "f2dWorld_GetKernelLaunchCount": (C.c_longlong, []),
     "f2dWorld_GetLastStepTimes": (None, [WorldId, C.POINTER(c_float)]),
     "f2dWorld_EnablePhaseTiming": (None, [WorldId, c_bool]),
+    "f2dWorld_EnableProfile": (None, [WorldId, c_bool]),
+    "f2dWorld_ReadProfile": (c_int, [WorldId, C.POINTER(C.c_ulonglong), c_int]),
     "f2dWorld_StepAsync": (None, [WorldId, c_float, c_int]),
     "f2dWorld_Synchronize": (None, [WorldId]),
 }

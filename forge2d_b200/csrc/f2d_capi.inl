@@ -1075,6 +1075,25 @@ void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 )
 	if ( hw )
 		backendStepTimes( *hw, out5 );
 }
+// In-kernel profile (nanoseconds per f2d::ProfSlot accumulated by rank 0 since it was enabled / last read)
+void f2dWorld_EnableProfile( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	w->profEnabled = flag ? 1 : 0;
+	memset( w->prof, 0, sizeof( w->prof ) );
+}
+int f2dWorld_ReadProfile( b2WorldId worldId, unsigned long long* out, int cap )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return 0;
+	for ( int i = 0; i < kProfSlots && i < cap; ++i )
+		out[i] = hw->img->prof[i];
+	return kProfSlots;
+}
 void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag )
 {
 	HostWorld* hw = worldFromId( worldId );

@@ -9,204 +9,14 @@
 //   * one large world  -> a cooperative grid of one block per SM (GridTeam, grid-wide barrier between phases).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (no FMA contraction: bit parity with the
 // reference's SSE2 arithmetic).
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
 #include "f2d_capi.inl"
-
-namespace cg = cooperative_groups;
+#include "f2d_launch.h"
 
 namespace f2d
 {
-
-// ------------------------------------------------------------------------------------------------ device teams
-struct CtaTeam
-{
-	int32_t* smem; // blockDim.x + 32 ints of shared scratch
-	__device__ int rank() const { return (int)threadIdx.x; }
-	__device__ int size() const { return (int)blockDim.x; }
-	__device__ void sync() const { __syncthreads(); }
-	// in-place exclusive scan of data[0..n) in global memory; returns the total. Block-wide collective.
-	__device__ int exclusiveScan( int32_t* data, int n ) const
-	{
-		const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
-		int32_t* warpSums = smem; // 32 entries
-		int carry = 0;
-		for ( int base = 0; base < n; base += nt )
-		{
-			int i = base + tid;
-			int v = i < n ? data[i] : 0;
-			// warp inclusive scan
-			int x = v;
-			for ( int off = 1; off < 32; off <<= 1 )
-			{
-				int y = __shfl_up_sync( 0xffffffffu, x, off );
-				if ( ( tid & 31 ) >= off )
-					x += y;
-			}
-			if ( ( tid & 31 ) == 31 )
-				warpSums[tid >> 5] = x;
-			__syncthreads();
-			if ( tid < 32 )
-			{
-				int ws = tid < ( nt >> 5 ) ? warpSums[tid] : 0;
-				int s = ws;
-				for ( int off = 1; off < 32; off <<= 1 )
-				{
-					int y = __shfl_up_sync( 0xffffffffu, s, off );
-					if ( tid >= off )
-						s += y;
-				}
-				warpSums[tid] = s - ws; // exclusive prefix of warp sums
-				if ( tid == 31 )
-					smem[32] = s; // chunk total
-			}
-			__syncthreads();
-			int excl = carry + warpSums[tid >> 5] + ( x - v );
-			if ( i < n )
-				data[i] = excl;
-			carry += smem[32];
-			__syncthreads();
-		}
-		return carry;
-	}
-};
-
-struct GridTeam
-{
-	int32_t* smem;
-	int32_t* blockTotals; // gridDim.x ints in global memory
-	__device__ int rank() const { return (int)( blockIdx.x * blockDim.x + threadIdx.x ); }
-	__device__ int size() const { return (int)( gridDim.x * blockDim.x ); }
-	__device__ void sync() const { cg::this_grid().sync(); }
-	__device__ int exclusiveScan( int32_t* data, int n ) const
-	{
-		// each block scans one contiguous tile, then tile offsets are added after a grid barrier
-		const int nb = (int)gridDim.x;
-		const int tile = ( n + nb - 1 ) / nb;
-		const int begin = min( n, (int)blockIdx.x * tile );
-		const int end = min( n, begin + tile );
-		CtaTeam cta{ smem };
-		int total = cta.exclusiveScan( data + begin, end - begin );
-		if ( threadIdx.x == 0 )
-			blockTotals[blockIdx.x] = total;
-		cg::this_grid().sync();
-		int offset = 0, sum = 0;
-		for ( int b = 0; b < nb; ++b )
-		{
-			int v = blockTotals[b];
-			if ( b < (int)blockIdx.x )
-				offset += v;
-			sum += v;
-		}
-		for ( int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x )
-			data[i] += offset;
-		cg::this_grid().sync();
-		return sum;
-	}
-};
-
-// ------------------------------------------------------------------------------------------------ kernels
-enum Phase
-{
-	kPhaseAll = 0,
-	kPhaseBeginPairs = 1,
-	kPhaseCollide = 2,
-	kPhaseSolve = 3,
-	kPhaseFinalize = 4
-};
-
-template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& t, int phase, float dt, int sub )
-{
-	if ( phase == kPhaseAll )
-	{
-		stepWorld( w, t, dt, sub );
-		return;
-	}
-	if ( dt == 0.0f )
-	{
-		if ( phase == kPhaseBeginPairs )
-			stepZeroDt( w, t );
-		return;
-	}
-	switch ( phase )
-	{
-		case kPhaseBeginPairs:
-			stepBegin( w, t, dt, sub );
-			stepPairs( w, t );
-			break;
-		case kPhaseCollide:
-			stepCollide( w, t );
-			break;
-		case kPhaseSolve:
-			stepSolve( w, t );
-			break;
-		case kPhaseFinalize:
-			stepFinalize( w, t );
-			break;
-	}
-}
-
-// One thread block per world; worlds are `stride` bytes apart. Grid-stride over worlds.
-template <int kThreads, int kMinBlocks>
-__global__ void __launch_bounds__( kThreads, kMinBlocks )
-	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps )
-{
-	__shared__ int32_t smem[64];
-	CtaTeam team{ smem };
-	for ( int wi = (int)blockIdx.x; wi < worldCount; wi += (int)gridDim.x )
-	{
-		World* w = reinterpret_cast<World*>( base + (unsigned long long)wi * stride );
-		for ( int s = 0; s < steps; ++s )
-		{
-			if ( w->error & ( kErrCapacity | kErrUnsupported ) )
-				break;
-			runPhase( w, team, phase, dt, sub );
-		}
-	}
-}
-
-// One cooperative grid per world.
-template <int kThreads>
-__global__ void __launch_bounds__( kThreads, 1 ) stepWorldGrid( World* w, int32_t* blockTotals, float dt, int sub, int phase )
-{
-	__shared__ int32_t smem[64];
-	GridTeam team{ smem, blockTotals };
-	if ( w->error & ( kErrCapacity | kErrUnsupported ) )
-		return;
-	runPhase( w, team, phase, dt, sub );
-}
-
-// Gathers the body move events of every world of a batch into one dense buffer (one block per world).
-__global__ void gatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies,
-								  int* counts )
-{
-	int wi = (int)blockIdx.x;
-	if ( wi >= worldCount )
-		return;
-	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
-	int n = min( w->moveEvents.count, maxBodies );
-	const BodyMoveEvent* src = ptr( w, w->moveEvents );
-	// 40-byte records copied as 8-byte words: coalesced, no struct padding games
-	const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>( src );
-	unsigned long long* d8 = reinterpret_cast<unsigned long long*>( out + (size_t)wi * maxBodies );
-	int words = n * (int)( sizeof( BodyMoveEvent ) / 8 );
-	for ( int i = (int)threadIdx.x; i < words; i += (int)blockDim.x )
-		d8[i] = s8[i];
-	if ( threadIdx.x == 0 )
-		counts[wi] = n;
-}
-
-__global__ void gatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out )
-{
-	int wi = (int)( blockIdx.x * blockDim.x + threadIdx.x );
-	if ( wi >= worldCount )
-		return;
-	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
-	if ( w->error )
-		atomicOr( out, w->error );
-}
 
 // ------------------------------------------------------------------------------------------------ host glue
 static int g_deviceState = -1; // -1 unknown, 0 none, 1 ok
@@ -296,6 +106,7 @@ static DeviceMirror* mirror( HostWorld& hw )
 		DeviceMirror* m = new DeviceMirror();
 		cudaStreamCreateWithFlags( &m->stream, cudaStreamNonBlocking );
 		cudaMalloc( &m->blockTotals, 4096 * sizeof( int32_t ) );
+		cudaMemset( m->blockTotals, 0, 4096 * sizeof( int32_t ) ); // [0,64): GridBarrier, then per-block scan totals
 		for ( int i = 0; i < 6; ++i )
 			cudaEventCreate( &m->ev[i] );
 		hw.backend = m;
@@ -303,9 +114,6 @@ static DeviceMirror* mirror( HostWorld& hw )
 	return static_cast<DeviceMirror*>( hw.backend );
 }
 
-constexpr int kSingleCtaThreads = 1024;
-constexpr int kBatchCtaThreads = 256;
-constexpr int kGridThreads = 512;
 
 static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int phase )
 {
@@ -314,19 +122,11 @@ static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int 
 		mode = hw.img->awakeBodies.count + hw.img->shapeIds.next > 4096 ? 1 : 0;
 	g_launchCount += 1;
 	if ( mode == 0 )
-	{
-		stepWorldsCta<kSingleCtaThreads, 1>
-			<<<1, kSingleCtaThreads, 0, m->stream>>>( reinterpret_cast<char*>( m->dev ), 0ull, 1, dt, sub, phase, 1 );
-		return cudaOk( cudaGetLastError(), "stepWorldsCta launch" );
-	}
-	World* dev = m->dev;
-	int32_t* totals = m->blockTotals;
-	void* args[] = { &dev, &totals, &dt, &sub, &phase };
+		return cudaOk( launchSingleCta( m->dev, dt, sub, phase, m->stream ), "stepWorldsCta launch" );
 	int blocks = g_smCount;
-	if ( blocks > 4096 )
-		blocks = 4096;
-	cudaError_t e = cudaLaunchCooperativeKernel( (void*)stepWorldGrid<kGridThreads>, dim3( blocks ), dim3( kGridThreads ), args, 0, m->stream );
-	return cudaOk( e, "stepWorldGrid cooperative launch" );
+	if ( blocks > 4000 )
+		blocks = 4000;
+	return cudaOk( launchSingleGrid( m->dev, m->blockTotals, blocks, dt, sub, phase, m->stream ), "stepWorldGrid cooperative launch" );
 }
 
 static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous )
@@ -445,6 +245,7 @@ struct f2dBatch
 	int eventCap = 0;
 	unsigned int* devError = nullptr;
 	f2d::Caps caps{};
+	int threads = 256, blocksPerSM = 2; // launch configuration of the batch kernel (f2dBatch_SetLaunchConfig)
 	cudaEvent_t events[8] = {};
 	b2BodyMoveEvent* hostEvents = nullptr; // pinned staging for f2dBatch_ReadBodyEvents
 	int* hostCounts = nullptr;
@@ -524,10 +325,23 @@ void f2dBatch_StepN( f2dBatch* b, float dt, int sub, int steps )
 	// one launch per step keeps every world of the batch in lock-step (and gives ncu one launch per step)
 	for ( int s = 0; s < steps; ++s )
 	{
-		stepWorldsCta<kBatchCtaThreads, 2><<<b->count, kBatchCtaThreads, 0, b->stream>>>( b->dev, b->stride, b->count, dt, sub, kPhaseAll, 1 );
+		if ( launchBatchStep( b->threads, b->blocksPerSM, b->dev, b->stride, b->count, dt, sub, 1, b->stream ) == false )
+		{
+			reportError( "f2dBatch_Step: no batch kernel for %d threads x %d blocks/SM", b->threads, b->blocksPerSM );
+			return;
+		}
 		g_launchCount += 1;
 	}
 	cudaOk( cudaGetLastError(), "stepWorldsCta(batch) launch" );
+}
+
+int f2dBatch_SetLaunchConfig( f2dBatch* b, int threads, int blocksPerSM )
+{
+	if ( b == nullptr || f2d::batchConfigExists( threads, blocksPerSM ) == false )
+		return 0;
+	b->threads = threads;
+	b->blocksPerSM = blocksPerSM;
+	return 1;
 }
 
 void f2dBatch_Step( f2dBatch* b, float dt, int sub )
@@ -561,7 +375,7 @@ int f2dBatch_GetBodyEvents( f2dBatch* b, b2BodyMoveEvent* out, int maxBodies, in
 		cudaMalloc( &b->devCounts, (size_t)b->count * sizeof( int ) );
 		b->eventCap = need;
 	}
-	gatherMoveEvents<<<b->count, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts );
+	launchGatherMoveEvents( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts, b->stream );
 	g_launchCount += 1;
 	cudaMemcpyAsync( out, b->devEvents, (size_t)need * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost, b->stream );
 	cudaMemcpyAsync( counts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
@@ -598,7 +412,7 @@ int f2dBatch_ReadBodyEvents( f2dBatch* b, int maxBodies, const b2BodyMoveEvent**
 		cudaMallocHost( &b->hostCounts, (size_t)b->count * sizeof( int ) );
 		b->hostEventCap = need;
 	}
-	gatherMoveEvents<<<b->count, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts );
+	launchGatherMoveEvents( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts, b->stream );
 	g_launchCount += 1;
 	cudaMemcpyAsync( b->hostEvents, b->devEvents, (size_t)need * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost, b->stream );
 	cudaMemcpyAsync( b->hostCounts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
@@ -692,7 +506,7 @@ uint32_t f2dBatch_GetErrorFlags( f2dBatch* b )
 	if ( b == nullptr )
 		return 0;
 	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
-	gatherErrors<<<( b->count + 255 ) / 256, 256, 0, b->stream>>>( b->dev, b->stride, b->count, b->devError );
+	launchGatherErrors( b->dev, b->stride, b->count, b->devError, b->stream );
 	g_launchCount += 1;
 	unsigned int e = 0;
 	cudaMemcpyAsync( &e, b->devError, sizeof( e ), cudaMemcpyDeviceToHost, b->stream );

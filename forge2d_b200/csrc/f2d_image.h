@@ -72,9 +72,12 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 		add( w.trees[i].leafCenters, S + 4, false );
 		add( w.trees[i].work, kTreeStack * 6, false );
 	}
+	add( w.treeScratch, 17 * ( S + 8 ) + 2 * S + 16 + 8, false );
 	add( w.moveArray, S, true );
 	add( w.moveHeads, S, false );
 	add( w.movePairs, C, false );
+	add( w.pairOffsets, S, false );
+	add( w.pairOrder, C, false );
 	add( w.moveEvents, B, true );
 	add( w.beginEvents, c.contactEvents, true );
 	add( w.endEvents[0], c.contactEvents, true );
@@ -84,6 +87,8 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.sensorEndEvents[0], 4, true );
 	add( w.sensorEndEvents[1], 4, true );
 	add( w.contactBits, C / 64 + 2, false );
+	add( w.stateOffsets, C / 64 + 2, false );
+	add( w.stateList, C, false );
 	add( w.enlargedBits, B / 64 + 2, false );
 	add( w.islandBits, B / 64 + 2, false );
 	add( w.cons, cfFieldCount * C, false );

@@ -1,0 +1,65 @@
+// forge2d_b200 — kernels for ONE world: a single 1024-thread block (small worlds: barrier cost ~tens of ns, working set
+// in that SM's L1/L2) or a cooperative grid of one block per SM (large worlds), plus the batch gather kernels.
+#include "f2d_kernels.cuh"
+
+namespace f2d
+{
+
+// Gathers the body move events of every world of a batch into one dense buffer (one block per world).
+__global__ void gatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies,
+								  int* counts )
+{
+	int wi = (int)blockIdx.x;
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	int n = min( w->moveEvents.count, maxBodies );
+	const BodyMoveEvent* src = ptr( w, w->moveEvents );
+	// 40-byte records copied as 8-byte words: coalesced, no struct padding games
+	const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>( src );
+	unsigned long long* d8 = reinterpret_cast<unsigned long long*>( out + (size_t)wi * maxBodies );
+	int words = n * (int)( sizeof( BodyMoveEvent ) / 8 );
+	for ( int i = (int)threadIdx.x; i < words; i += (int)blockDim.x )
+		d8[i] = s8[i];
+	if ( threadIdx.x == 0 )
+		counts[wi] = n;
+}
+
+__global__ void gatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out )
+{
+	int wi = (int)( blockIdx.x * blockDim.x + threadIdx.x );
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	if ( w->error )
+		atomicOr( out, w->error );
+}
+
+
+
+constexpr int kSingleCtaThreads = 1024;
+constexpr int kGridThreads = 512;
+
+cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream )
+{
+	stepWorldsCta<kSingleCtaThreads, 1><<<1, kSingleCtaThreads, 0, stream>>>( reinterpret_cast<char*>( dev ), 0ull, 1, dt, sub, phase, 1 );
+	return cudaGetLastError();
+}
+
+cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, cudaStream_t stream )
+{
+	void* args[] = { &dev, &blockTotals, &dt, &sub, &phase };
+	return cudaLaunchCooperativeKernel( (void*)stepWorldGrid<kGridThreads>, dim3( blocks ), dim3( kGridThreads ), args, 0, stream );
+}
+
+void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,
+							 cudaStream_t stream )
+{
+	gatherMoveEvents<<<worldCount, 256, 0, stream>>>( base, stride, worldCount, out, maxBodies, counts );
+}
+void launchGatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out, cudaStream_t stream )
+{
+	gatherErrors<<<( worldCount + 255 ) / 256, 256, 0, stream>>>( base, stride, worldCount, out );
+}
+
+} // namespace f2d

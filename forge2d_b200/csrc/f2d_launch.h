@@ -1,0 +1,45 @@
+// forge2d_b200 — host-visible launcher declarations (no device code): implemented by the f2d_kernels_*.cu units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace f2d
+{
+struct World;
+enum Phase
+{
+	kPhaseAll = 0,
+	kPhaseBeginPairs = 1,
+	kPhaseCollide = 2,
+	kPhaseSolve = 3,
+	kPhaseFinalize = 4
+};
+bool launchBatchStepA( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
+					   cudaStream_t stream );
+bool launchBatchStepB( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
+					   cudaStream_t stream );
+bool launchBatchStepC( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
+					   cudaStream_t stream );
+inline bool batchConfigExists( int threads, int blocksPerSM )
+{
+	const int known[][2] = { { 256, 2 }, { 128, 4 }, { 64, 8 }, { 32, 16 }, { 128, 8 }, { 64, 16 } };
+	for ( auto& k : known )
+		if ( k[0] == threads && k[1] == blocksPerSM )
+			return true;
+	return false;
+}
+inline bool launchBatchStep( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub,
+							 int steps, cudaStream_t stream )
+{
+	return launchBatchStepA( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
+		   launchBatchStepB( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
+		   launchBatchStepC( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream );
+}
+cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream );
+cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, cudaStream_t stream );
+// gather kernels of the batch extension
+struct BodyMoveEvent;
+void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,
+							 cudaStream_t stream );
+void launchGatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out, cudaStream_t stream );
+} // namespace f2d

@@ -11,6 +11,7 @@
 #include "f2d_distance.h"
 #include "f2d_joint.h"
 #include "f2d_solver.h"
+#include "f2d_tree_team.h"
 
 namespace f2d
 {
@@ -20,6 +21,8 @@ template <class Team> F2D_HDF inline void stepBegin( World* w, Team& t, float dt
 {
 	if ( t.rank() == 0 )
 	{
+		if ( w->profEnabled )
+			w->profLast = profClock();
 		w->moveEvents.count = 0;
 		w->sensorBeginEvents.count = 0;
 		w->beginEvents.count = 0;
@@ -60,6 +63,7 @@ template <class Team> F2D_HDF inline void stepBegin( World* w, Team& t, float dt
 	for ( int i = t.rank(); i < w->contactBits.cap; i += t.size() )
 		bits[i] = 0;
 	t.sync();
+	F2D_MARK( w, t, pfBegin );
 }
 
 // ------------------------------------------------------------------------------------------------ pairs
@@ -212,26 +216,56 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 	for ( int i = t.rank(); i < moveCount; i += t.size() )
 		findPairsForProxy( w, i );
 	t.sync();
-	if ( t.rank() == 0 )
+	F2D_MARK( w, t, pfPairQuery );
+	// Ordered creation (broad_phase.c:418-453): move-array order x per-proxy list order. Most moved proxies found
+	// nothing new, so the lists are first compacted by the team (count, prefix sum, scatter) into one ordered array
+	// and rank 0 only walks real pairs.
 	{
 		const int32_t* heads = ptr( w, w->moveHeads );
 		const MovePair* pairs = ptr( w, w->movePairs );
-		const int32_t* moves = ptr( w, w->moveArray );
-		for ( int i = 0; i < moveCount; ++i )
+		int32_t* offsets = ptr( w, w->pairOffsets );
+		int32_t* ordered = ptr( w, w->pairOrder );
+		for ( int i = t.rank(); i < moveCount; i += t.size() )
 		{
+			int n = 0;
 			for ( int p = heads[i]; p != kNull; p = pairs[p].next )
-				createContact( w, pairs[p].shapeA, pairs[p].shapeB );
+				n += 1;
+			offsets[i] = n;
 		}
-		// reset move buffer (broad_phase.c:460-462)
-		for ( int i = 0; i < moveCount; ++i )
+		t.sync();
+		int total = t.exclusiveScan( offsets, moveCount );
+		if ( total > 0 && total <= w->pairOrder.cap )
+		{
+			for ( int i = t.rank(); i < moveCount; i += t.size() )
+			{
+				int out = offsets[i];
+				for ( int p = heads[i]; p != kNull; p = pairs[p].next )
+					ordered[out++] = p;
+			}
+			t.sync();
+			if ( t.rank() == 0 )
+			{
+				for ( int k = 0; k < total; ++k )
+					createContact( w, pairs[ordered[k]].shapeA, pairs[ordered[k]].shapeB );
+			}
+		}
+	}
+	t.sync();
+	// reset move buffer (broad_phase.c:460-462)
+	{
+		const int32_t* moves = ptr( w, w->moveArray );
+		for ( int i = t.rank(); i < moveCount; i += t.size() )
 		{
 			int key = moves[i];
 			if ( key != kNull )
 				ptr( w, w->trees[proxyType( key )].nodes )[proxyId( key )].flags &= (uint16_t)~kNodeMoved;
 		}
-		w->moveArray.count = 0;
 	}
 	t.sync();
+	if ( t.rank() == 0 )
+		w->moveArray.count = 0;
+	t.sync();
+	F2D_MARK( w, t, pfPairCreate );
 }
 
 // ------------------------------------------------------------------------------------------------ collide
@@ -280,83 +314,119 @@ F2D_HDF inline void collideContact( World* w, int contactId )
 	}
 }
 
-// Ordered contact-state pass, ascending contact id: world.c:587-686
-F2D_HDF inline void contactStatePass( World* w )
+// One contact of the ordered contact-state pass (world.c:595-684)
+F2D_HDF inline void contactStateChange( World* w, int contactId )
+{
+	Contact* contacts = ptr( w, w->contacts );
+	ContactSim* sims = ptr( w, w->contactSims );
+	const Shape* shapes = ptr( w, w->shapes );
+	Contact& c = contacts[contactId];
+	ContactSim& sim = sims[contactId];
+	int colorIndex = c.colorIndex;
+	int localIndex = c.localIndex;
+	const Shape& shapeA = shapes[c.shapeIdA];
+	const Shape& shapeB = shapes[c.shapeIdB];
+	uint32_t flags = c.flags;
+	uint32_t simFlags = sim.simFlags;
+
+	if ( simFlags & kSimDisjoint )
+	{
+		destroyContact( w, contactId, false );
+	}
+	else if ( simFlags & kSimStartedTouching )
+	{
+		if ( flags & kContactEnableContactEvents )
+		{
+			BeginTouchEvent ev;
+			ev.a = makeShapeId( w, shapeA );
+			ev.b = makeShapeId( w, shapeB );
+			ev.manifold = sim.manifold;
+			F2D_PUSH( w, w->beginEvents, ev );
+		}
+		c.flags |= kContactTouching;
+		linkContact( w, c );
+		sim.simFlags &= ~kSimStartedTouching;
+		addContactToGraph( w, contactId );
+		// remove from the awake non-touching list (world.c:472-485); c.localIndex now is the colour slot
+		int moved = removeSwap( w, w->awakeContacts, localIndex );
+		if ( moved != kNull )
+			contacts[ptr( w, w->awakeContacts )[localIndex]].localIndex = localIndex;
+	}
+	else if ( simFlags & kSimStoppedTouching )
+	{
+		sim.simFlags &= ~kSimStoppedTouching;
+		c.flags &= ~kContactTouching;
+		if ( c.flags & kContactEnableContactEvents )
+		{
+			EndTouchEvent ev = { makeShapeId( w, shapeA ), makeShapeId( w, shapeB ) };
+			F2D_PUSH( w, w->endEvents[w->endEventArrayIndex], ev );
+		}
+		unlinkContact( w, c );
+		int bodyIdA = c.edges[0].bodyId;
+		int bodyIdB = c.edges[1].bodyId;
+		// back to the awake non-touching list (world.c:461-470)
+		c.colorIndex = kNull;
+		c.localIndex = w->awakeContacts.count;
+		F2D_PUSH( w, w->awakeContacts, contactId );
+		removeContactFromGraph( w, bodyIdA, bodyIdB, colorIndex, localIndex );
+	}
+}
+
+// Ordered contact-state pass, ascending contact id (world.c:587-686). The flagged ids are compacted by the whole team
+// (popcount per 64-bit word + prefix sum), then rank 0 applies the order-defining structural edits one by one.
+template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 {
 	const uint64_t* bits = ptr( w, w->contactBits );
 	int wordCount = ( w->contactIds.next + 63 ) >> 6;
 	if ( wordCount > w->contactBits.cap )
 		wordCount = w->contactBits.cap;
-	Contact* contacts = ptr( w, w->contacts );
-	ContactSim* sims = ptr( w, w->contactSims );
-	const Shape* shapes = ptr( w, w->shapes );
-	for ( int k = 0; k < wordCount; ++k )
+	int32_t* offsets = ptr( w, w->stateOffsets );
+	int32_t* list = ptr( w, w->stateList );
+	if ( wordCount > w->stateOffsets.cap )
+	{
+		if ( t.rank() == 0 )
+			setError( w, kErrCapacity, __LINE__ );
+		return;
+	}
+	for ( int k = t.rank(); k < wordCount; k += t.size() )
 	{
 		uint64_t word = bits[k];
+		int n = 0;
 		while ( word != 0 )
 		{
-			int bit = 0;
-			{
-				uint64_t tmp = word;
-				while ( ( tmp & 1ull ) == 0 )
-				{
-					tmp >>= 1;
-					bit += 1;
-				}
-			}
-			int contactId = 64 * k + bit;
-			Contact& c = contacts[contactId];
-			ContactSim& sim = sims[contactId];
-			int colorIndex = c.colorIndex;
-			int localIndex = c.localIndex;
-			const Shape& shapeA = shapes[c.shapeIdA];
-			const Shape& shapeB = shapes[c.shapeIdB];
-			uint32_t flags = c.flags;
-			uint32_t simFlags = sim.simFlags;
-
-			if ( simFlags & kSimDisjoint )
-			{
-				destroyContact( w, contactId, false );
-			}
-			else if ( simFlags & kSimStartedTouching )
-			{
-				if ( flags & kContactEnableContactEvents )
-				{
-					BeginTouchEvent ev;
-					ev.a = makeShapeId( w, shapeA );
-					ev.b = makeShapeId( w, shapeB );
-					ev.manifold = sim.manifold;
-					F2D_PUSH( w, w->beginEvents, ev );
-				}
-				c.flags |= kContactTouching;
-				linkContact( w, c );
-				sim.simFlags &= ~kSimStartedTouching;
-				addContactToGraph( w, contactId );
-				// remove from the awake non-touching list (world.c:472-485); c.localIndex now is the colour slot
-				int moved = removeSwap( w, w->awakeContacts, localIndex );
-				if ( moved != kNull )
-					contacts[ptr( w, w->awakeContacts )[localIndex]].localIndex = localIndex;
-			}
-			else if ( simFlags & kSimStoppedTouching )
-			{
-				sim.simFlags &= ~kSimStoppedTouching;
-				c.flags &= ~kContactTouching;
-				if ( c.flags & kContactEnableContactEvents )
-				{
-					EndTouchEvent ev = { makeShapeId( w, shapeA ), makeShapeId( w, shapeB ) };
-					F2D_PUSH( w, w->endEvents[w->endEventArrayIndex], ev );
-				}
-				unlinkContact( w, c );
-				int bodyIdA = c.edges[0].bodyId;
-				int bodyIdB = c.edges[1].bodyId;
-				// back to the awake non-touching list (world.c:461-470)
-				c.colorIndex = kNull;
-				c.localIndex = w->awakeContacts.count;
-				F2D_PUSH( w, w->awakeContacts, contactId );
-				removeContactFromGraph( w, bodyIdA, bodyIdB, colorIndex, localIndex );
-			}
-			word = word & ( word - 1 );
+			word &= word - 1;
+			n += 1;
 		}
+		offsets[k] = n;
+	}
+	t.sync();
+	int total = t.exclusiveScan( offsets, wordCount );
+	if ( total == 0 )
+		return;
+	if ( total > w->stateList.cap )
+	{
+		if ( t.rank() == 0 )
+			setError( w, kErrCapacity, __LINE__ );
+		return;
+	}
+	for ( int k = t.rank(); k < wordCount; k += t.size() )
+	{
+		uint64_t word = bits[k];
+		int out = offsets[k];
+		int bit = 0;
+		while ( word != 0 )
+		{
+			if ( word & 1ull )
+				list[out++] = 64 * k + bit;
+			word >>= 1;
+			bit += 1;
+		}
+	}
+	t.sync();
+	if ( t.rank() == 0 )
+	{
+		for ( int i = 0; i < total; ++i )
+			contactStateChange( w, list[i] );
 	}
 }
 
@@ -374,18 +444,34 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 	total += w->awakeContacts.count;
 	segBase[kColorCount + 1] = total;
 
-	// rank 0 rebuilds the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492) while the other ranks
-	// run the narrowphase; with a one-thread team both happen in sequence.
-	int workers = t.size() > 1 ? t.size() - 1 : 1;
-	int me = t.size() > 1 ? t.rank() - 1 : 0;
-	if ( t.rank() == 0 )
+	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492), concurrent with the narrowphase
+	// as in the reference when the team can spare a block for it (grid team: block 0 rebuilds with block-level
+	// barriers while the other blocks collide); otherwise one after the other, each fully data-parallel.
+	int collideRank = t.rank(), collideSize = t.size();
+	bool collides = true;
+	if constexpr ( Team::kHasSoloBlock )
 	{
-		treeRebuild( w, w->trees[kDynamicBody], false );
-		treeRebuild( w, w->trees[kKinematicBody], false );
+		collideRank = t.rankOutsideSolo();
+		collideSize = t.sizeOutsideSolo();
+		if ( t.inSoloBlock() )
+		{
+			auto solo = t.soloTeam();
+			treeRebuildTeam( w, solo, w->trees[kDynamicBody] );
+			treeRebuildTeam( w, solo, w->trees[kKinematicBody] );
+			F2D_MARK( w, t, pfTreeRebuild );
+			collides = false;
+		}
 	}
-	if ( t.size() == 1 || t.rank() > 0 )
+	else
 	{
-		for ( int i = me; i < total; i += workers )
+		treeRebuildTeam( w, t, w->trees[kDynamicBody] );
+		treeRebuildTeam( w, t, w->trees[kKinematicBody] );
+		t.sync();
+		F2D_MARK( w, t, pfTreeRebuild );
+	}
+	if ( collides )
+	{
+		for ( int i = collideRank; i < total; i += collideSize )
 		{
 			int seg = 0;
 			while ( i >= segBase[seg + 1] )
@@ -396,9 +482,10 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 		}
 	}
 	t.sync();
-	if ( t.rank() == 0 )
-		contactStatePass( w );
+	F2D_MARK( w, t, pfNarrow );
+	contactStatePass( w, t );
 	t.sync();
+	F2D_MARK( w, t, pfStatePass );
 }
 
 // ------------------------------------------------------------------------------------------------ solve
@@ -537,12 +624,145 @@ template <class Team> F2D_HDF inline void constraintPass( World* w, Team& t, int
 	}
 }
 
+// Prepare, the sub-step loop, restitution and impulse storage (solver.c:929-1106) on `t`: the whole team, or the crew
+// left over when a side worker splits an island at the same time.
+template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
+{
+	const int awakeBodyCount = w->step.awakeBodyCount;
+	// prepare joints and contacts (all colours incl. overflow: prepare formulas are identical)
+	{
+		JointSim* jsims = ptr( w, w->jointSims );
+		for ( int color = 0; color < kColorCount; ++color )
+		{
+			const int32_t* jl = ptr( w, w->colorJoints[color] );
+			int n = w->colorJoints[color].count;
+			for ( int i = t.rank(); i < n; i += t.size() )
+				prepareJoint( w, jsims[jl[i]] );
+		}
+		const ConView c = conView( w );
+		const BodyState* states = ptr( w, w->states );
+		float warmStartScale = w->enableWarmStarting ? 1.0f : 0.0f;
+		int total = w->step.awakeContactCount;
+		for ( int slot = t.rank(); slot < total; slot += t.size() )
+		{
+			int color = 0;
+			while ( slot >= w->step.colorBase[color + 1] )
+				color += 1;
+			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
+			prepareContactSlot( w, c, slot, contactId, states, warmStartScale );
+		}
+	}
+	t.sync();
+	F2D_MARK( w, t, pfPrepare );
+
+	const float h = w->step.h;
+	const float maxLinearSpeed = w->step.maxLinearVelocity;
+	const float maxAngularSpeed = kMaxRotation * w->step.inv_dt;
+	const int subStepCount = w->step.subStepCount;
+	for ( int sub = 0; sub < subStepCount; ++sub )
+	{
+		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+			integrateVelocity( w, i, h, maxLinearSpeed, maxAngularSpeed );
+		t.sync();
+		F2D_MARK( w, t, pfIntegrateVel );
+		constraintPass( w, t, 0 );
+		F2D_MARK( w, t, pfWarmStart );
+		constraintPass( w, t, 1 );
+		F2D_MARK( w, t, pfSolve );
+		{
+			BodyState* states = ptr( w, w->states );
+			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+				integratePosition( states[i], h );
+		}
+		t.sync();
+		F2D_MARK( w, t, pfIntegratePos );
+		constraintPass( w, t, 2 );
+		F2D_MARK( w, t, pfRelax );
+	}
+	constraintPass( w, t, 3 );
+	F2D_MARK( w, t, pfRestitution );
+
+	// store impulses (solver.c:1093-1097)
+	{
+		const ConView c = conView( w );
+		int total = w->step.awakeContactCount;
+		int overflowBase = w->step.colorBase[kOverflow];
+		for ( int slot = t.rank(); slot < total; slot += t.size() )
+		{
+			int color = 0;
+			while ( slot >= w->step.colorBase[color + 1] )
+				color += 1;
+			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
+			storeSlot( w, c, slot, contactId, slot >= overflowBase );
+		}
+	}
+	t.sync();
+	F2D_MARK( w, t, pfStore );
+}
+
+// island.c:539-598. Pass 1 (every awake island ends up pointing straight at its root) is a read-only walk per island
+// followed by one write; pass 2 (the order-defining list concatenations, last island first) stays serial but only runs
+// when some island actually has a parent.
+template <class Team> F2D_HDF inline void mergeAwakeIslandsTeam( World* w, Team& t )
+{
+	Island* islands = ptr( w, w->islands );
+	const int32_t* awake = ptr( w, w->awakeIslands );
+	int count = w->awakeIslands.count;
+	int32_t* roots = ptr( w, w->scan );
+	if ( count > w->scan.cap )
+	{
+		if ( t.rank() == 0 )
+			mergeAwakeIslands( w );
+		t.sync();
+		return;
+	}
+	if ( t.rank() == 0 )
+		w->step.mergeCount = 0;
+	t.sync();
+	for ( int i = t.rank(); i < count; i += t.size() )
+	{
+		int rootId = awake[i];
+		while ( islands[rootId].parentIsland != kNull )
+			rootId = islands[rootId].parentIsland;
+		roots[i] = rootId;
+		if ( rootId != awake[i] )
+			atomAdd( &w->step.mergeCount, 1 );
+	}
+	t.sync();
+	if ( w->step.mergeCount == 0 )
+		return;
+	// every merging island relabels its own bodies / contacts / joints (independent list walks) ...
+	for ( int i = t.rank(); i < count; i += t.size() )
+	{
+		if ( roots[i] != awake[i] )
+		{
+			islands[awake[i]].parentIsland = roots[i];
+			relabelIsland( w, islands[awake[i]], roots[i] );
+		}
+	}
+	t.sync();
+	// ... and rank 0 splices the lists onto the roots, last island first (order-defining)
+	if ( t.rank() == 0 )
+	{
+		for ( int i = count - 1; i >= 0; --i )
+		{
+			int islandId = ptr( w, w->awakeIslands )[i];
+			Island& island = islands[islandId];
+			if ( island.parentIsland == kNull )
+				continue;
+			mergeIsland( w, island, false );
+			destroyIsland( w, islandId );
+		}
+	}
+	t.sync();
+}
+
 template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 {
+	mergeAwakeIslandsTeam( w, t );
 	if ( t.rank() == 0 )
 	{
 		w->stepIndex += 1;
-		mergeAwakeIslands( w );
 		StepCtx& s = w->step;
 		s.awakeBodyCount = w->awakeBodies.count;
 		// colour bases and the active colour list (solver.c:1237-1355); overflow keeps the last base
@@ -571,78 +791,45 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	}
 	t.sync();
 	const int awakeBodyCount = w->step.awakeBodyCount;
+	F2D_MARK( w, t, pfSolveSetup );
 	if ( awakeBodyCount == 0 || ( w->error & kErrCapacity ) != 0 )
 		return;
 
-	// island split squeezed in before the solve (solver.c:1473-1485, 1700-1706); rank 0 only, overlapped with prepare
-	if ( t.rank() == 0 )
+	// Island split (solver.c:1473-1485, 1700-1706): a serial depth-first walk that touches island links only, so, as in
+	// the reference, it runs concurrently with the solver stages when the team can spare a side worker for it.
+	bool fork = false;
+	if constexpr ( Team::kCanFork )
+		fork = w->splitIslandId != kNull && t.canFork();
+	if ( fork )
 	{
-		if ( w->splitIslandId != kNull )
-			splitIsland( w, w->splitIslandId );
-		w->splitIslandId = kNull;
-	}
-
-	// prepare joints and contacts (all colours incl. overflow: prepare formulas are identical)
-	{
-		JointSim* jsims = ptr( w, w->jointSims );
-		for ( int color = 0; color < kColorCount; ++color )
+		if constexpr ( Team::kCanFork )
 		{
-			const int32_t* jl = ptr( w, w->colorJoints[color] );
-			int n = w->colorJoints[color].count;
-			for ( int i = t.rank(); i < n; i += t.size() )
-				prepareJoint( w, jsims[jl[i]] );
-		}
-		const ConView c = conView( w );
-		const BodyState* states = ptr( w, w->states );
-		float warmStartScale = w->enableWarmStarting ? 1.0f : 0.0f;
-		int total = w->step.awakeContactCount;
-		for ( int slot = t.rank(); slot < total; slot += t.size() )
-		{
-			int color = 0;
-			while ( slot >= w->step.colorBase[color + 1] )
-				color += 1;
-			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
-			prepareContactSlot( w, c, slot, contactId, states, warmStartScale );
-		}
-	}
-	t.sync();
-
-	const float h = w->step.h;
-	const float maxLinearSpeed = w->step.maxLinearVelocity;
-	const float maxAngularSpeed = kMaxRotation * w->step.inv_dt;
-	const int subStepCount = w->step.subStepCount;
-	for ( int sub = 0; sub < subStepCount; ++sub )
-	{
-		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
-			integrateVelocity( w, i, h, maxLinearSpeed, maxAngularSpeed );
-		t.sync();
-		constraintPass( w, t, 0 );
-		constraintPass( w, t, 1 );
-		{
-			BodyState* states = ptr( w, w->states );
-			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
-				integratePosition( states[i], h );
+			if ( t.inSide() )
+			{
+				if ( t.isSideLeader() )
+					splitIsland( w, w->splitIslandId );
+			}
+			else
+			{
+				auto crew = t.crew();
+				solveStages( w, crew );
+			}
 		}
 		t.sync();
-		constraintPass( w, t, 2 );
+		// cleared only after the join: every thread decided `fork` from this field
+		if ( t.rank() == 0 )
+			w->splitIslandId = kNull;
 	}
-	constraintPass( w, t, 3 );
-
-	// store impulses (solver.c:1093-1097)
+	else
 	{
-		const ConView c = conView( w );
-		int total = w->step.awakeContactCount;
-		int overflowBase = w->step.colorBase[kOverflow];
-		for ( int slot = t.rank(); slot < total; slot += t.size() )
+		if ( t.rank() == 0 )
 		{
-			int color = 0;
-			while ( slot >= w->step.colorBase[color + 1] )
-				color += 1;
-			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
-			storeSlot( w, c, slot, contactId, slot >= overflowBase );
+			if ( w->splitIslandId != kNull )
+				splitIsland( w, w->splitIslandId );
+			w->splitIslandId = kNull;
 		}
+		solveStages( w, t );
 	}
-	t.sync();
 }
 
 // ------------------------------------------------------------------------------------------------ finalize
@@ -1017,9 +1204,11 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
 			finalizeBody( w, i );
 		t.sync();
+		F2D_MARK( w, t, pfFinalizeBodies );
 
 		if ( t.rank() == 0 && w->hitEventCapable > 0 )
 			reportHitEvents( w );
+		F2D_MARK( w, t, pfHitEvents );
 
 		// Enlarged proxies -> broadphase, and next step's move array in ascending awake index x shape-list order
 		// (solver.c:1835-1907). Count, scan, then scatter + enlarge in parallel.
@@ -1080,6 +1269,7 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		t.sync();
 		if ( t.rank() == 0 )
 			w->moveArray.count = moveTotal;
+		F2D_MARK( w, t, pfEnlarge );
 
 		// bullets: continuous against everything, then enlarge (solver.c:1915-1988)
 		int bulletCount = w->step.bulletCount;
@@ -1108,6 +1298,7 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 			t.sync();
 		}
 
+		F2D_MARK( w, t, pfBullets );
 		// island sleep: reverse scan of awake islands (solver.c:1995-2051)
 		if ( t.rank() == 0 )
 		{
@@ -1131,6 +1322,7 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 			}
 		}
 		t.sync();
+		F2D_MARK( w, t, pfSleep );
 	}
 
 	// sensors would run here (world.c:788-793): no sensor shapes on the device path yet

@@ -20,6 +20,7 @@ F2D_HD void atomOr32( uint32_t* p, uint32_t v ) { atomicOr( p, v ); }
 // float min/max through the ordered-int trick (valid for any mix of signs, NaN-free inputs)
 F2D_HD void atomMinF( float* p, float v )
 {
+	v += 0.0f; // -0.0 -> +0.0: as an int, -0.0 would beat every negative value
 	if ( v >= 0.0f )
 		atomicMin( reinterpret_cast<int*>( p ), __float_as_int( v ) );
 	else
@@ -58,8 +59,33 @@ F2D_HD void atomMaxF( float* p, float v )
 }
 #endif
 
+#if defined( __CUDA_ARCH__ )
+F2D_HD uint64_t profClock()
+{
+	unsigned long long t;
+	asm volatile( "mov.u64 %0, %%globaltimer;" : "=l"( t ) );
+	return t;
+}
+#else
+F2D_HD uint64_t profClock() { return 0; }
+#endif
+
+// Phase mark: rank 0 charges the time since the previous mark to `slot`. Call right after a team.sync().
+#define F2D_MARK( w, t, slot )                                                                                                 \
+	do                                                                                                                         \
+	{                                                                                                                          \
+		if ( ( t ).rank() == 0 && ( w )->profEnabled )                                                                         \
+		{                                                                                                                      \
+			uint64_t now_ = ::f2d::profClock();                                                                                \
+			( w )->prof[slot] += now_ - ( w )->profLast;                                                                       \
+			( w )->profLast = now_;                                                                                            \
+		}                                                                                                                      \
+	} while ( 0 )
+
 struct SerialTeam
 {
+	static constexpr bool kHasSoloBlock = false;
+	static constexpr bool kCanFork = false;
 	F2D_HD int rank() const { return 0; }
 	F2D_HD int size() const { return 1; }
 	F2D_HD void sync() const {}

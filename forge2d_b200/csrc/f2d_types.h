@@ -445,6 +445,8 @@ struct StepCtx
 	int32_t hitCandidateCount;
 	int32_t moveCount;
 	int32_t pairCount;
+	int32_t mergeCount; // awake islands with a parent at the start of the solve
+	int32_t pad;
 	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
 };
 
@@ -496,6 +498,32 @@ enum ConField : int
 	cfFieldCount
 };
 
+enum ProfSlot : int
+{
+	pfBegin,
+	pfPairQuery,
+	pfPairCreate,
+	pfTreeRebuild,
+	pfNarrow,
+	pfStatePass,
+	pfSolveSetup,
+	pfPrepare,
+	pfIntegrateVel,
+	pfWarmStart,
+	pfSolve,
+	pfIntegratePos,
+	pfRelax,
+	pfRestitution,
+	pfStore,
+	pfFinalizeBodies,
+	pfHitEvents,
+	pfEnlarge,
+	pfBullets,
+	pfSleep,
+	pfEnd,
+	kProfSlots = 24
+};
+
 enum : uint32_t
 {
 	kErrCapacity = 1,		 // a fixed-capacity array overflowed inside the step
@@ -527,6 +555,11 @@ struct World
 
 	StepCtx step;
 
+	// in-kernel phase profile: rank 0 accumulates nanoseconds between marks (f2d_step.h F2D_MARK); off unless enabled
+	uint64_t prof[kProfSlots];
+	uint64_t profLast;
+	int32_t profEnabled, pad2;
+
 	// entities (slot = id)
 	IdPool bodyIds, shapeIds, contactIds, jointIds, islandIds, setIds, chainIds;
 	Arr<Body> bodies;
@@ -556,9 +589,12 @@ struct World
 
 	// broadphase
 	Tree trees[3];
+	Arr<int32_t> treeScratch; // team-parallel rebuild work arrays (f2d_tree_team.h)
 	Arr<int32_t> moveArray;
 	Arr<int32_t> moveHeads;
 	Arr<MovePair> movePairs;
+	Arr<int32_t> pairOffsets; // per moved proxy: start of its pairs in pairOrder
+	Arr<int32_t> pairOrder;	  // pair indices in creation order
 
 	// events
 	Arr<BodyMoveEvent> moveEvents;
@@ -570,6 +606,8 @@ struct World
 
 	// per-step scratch
 	Arr<uint64_t> contactBits;	// contact state changes by contact id (world.c:548-553)
+	Arr<int32_t> stateOffsets;	// per word of contactBits: prefix sum of set bits
+	Arr<int32_t> stateList;		// flagged contact ids, ascending
 	Arr<uint64_t> enlargedBits; // by awake index (solver.c:1835-1840)
 	Arr<uint64_t> islandBits;	// awake islands kept awake (solver.c:2024-2028)
 	Arr<float> cons;			// cfFieldCount x consStride

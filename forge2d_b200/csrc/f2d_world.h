@@ -576,20 +576,28 @@ F2D_HDF inline void unlinkJoint( World* w, Joint& j )
 }
 
 // island.c:427-537 b2MergeIsland: child lists are appended to the root's (root-then-child order)
-F2D_HDF inline void mergeIsland( World* w, Island& island )
+F2D_HDF inline void relabelIsland( World* w, const Island& island, int rootId )
 {
-	int rootId = island.parentIsland;
-	Island& root = ptr( w, w->islands )[rootId];
 	Body* bodies = ptr( w, w->bodies );
 	Contact* contacts = ptr( w, w->contacts );
 	Joint* joints = ptr( w, w->joints );
-
 	for ( int id = island.headBody; id != kNull; id = bodies[id].islandNext )
 		bodies[id].islandId = rootId;
 	for ( int id = island.headContact; id != kNull; id = contacts[id].islandNext )
 		contacts[id].islandId = rootId;
 	for ( int id = island.headJoint; id != kNull; id = joints[id].islandNext )
 		joints[id].islandId = rootId;
+}
+
+F2D_HDF inline void mergeIsland( World* w, Island& island, bool relabel = true )
+{
+	int rootId = island.parentIsland;
+	Island& root = ptr( w, w->islands )[rootId];
+	Body* bodies = ptr( w, w->bodies );
+	Contact* contacts = ptr( w, w->contacts );
+	Joint* joints = ptr( w, w->joints );
+	if ( relabel )
+		relabelIsland( w, island, rootId );
 
 	bodies[root.tailBody].islandNext = island.headBody;
 	bodies[island.headBody].islandPrev = root.tailBody;

@@ -237,6 +237,9 @@ F2D_API void f2dBatch_Step( f2dBatch* batch, float timeStep, int subStepCount );
 /// Queues `steps` steps without host synchronisation in between (bench / headless simulation).
 F2D_API void f2dBatch_StepN( f2dBatch* batch, float timeStep, int subStepCount, int steps );
 F2D_API void f2dBatch_Synchronize( f2dBatch* batch );
+/// Threads per world (block size) and resident blocks per SM the batch kernel is compiled for; returns 0 if unknown.
+/// Available: 256x2 (default), 128x4, 64x8, 32x16, 128x8, 64x16.
+F2D_API int f2dBatch_SetLaunchConfig( f2dBatch* batch, int threadsPerWorld, int blocksPerSM );
 F2D_API int f2dBatch_GetWorldCount( f2dBatch* batch );
 /// Body move events of every world -> host buffer: `out` receives count*maxBodies records, `counts[w]` valid ones.
 F2D_API int f2dBatch_GetBodyEvents( f2dBatch* batch, b2BodyMoveEvent* out, int maxBodiesPerWorld, int* counts );
@@ -267,6 +270,9 @@ F2D_API long long f2dWorld_GetKernelLaunchCount( void ); ///< kernels launched b
 /// Times of the last step's phases in ms measured with CUDA events: [pairs, collide, solve, finalize, total]
 F2D_API void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 );
 F2D_API void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag );
+/// In-kernel phase profile: ns per sub-phase (f2d::ProfSlot order) accumulated on the device since enabled
+F2D_API void f2dWorld_EnableProfile( b2WorldId worldId, bool flag );
+F2D_API int f2dWorld_ReadProfile( b2WorldId worldId, unsigned long long* out, int cap );
 /// Device-side step without the per-step host synchronisation / header readback (bench: inputs resident in HBM)
 F2D_API void f2dWorld_StepAsync( b2WorldId worldId, float timeStep, int subStepCount );
 F2D_API void f2dWorld_Synchronize( b2WorldId worldId );

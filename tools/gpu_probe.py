@@ -61,3 +61,53 @@ if "batch" in what:
         print("batch %5d worlds: %.3f ms/step -> %.0f world-steps/s (image %.2f MB) err=%x" % (
             count, ms, count / ms * 1e3, lib.f2dBatch_GetWorldBytes(b) / 1e6, lib.f2dBatch_GetErrorFlags(b)), flush=True)
         lib.f2dBatch_Destroy(b)
+
+PROF_NAMES = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
+              "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
+              "bullets", "sleep", "end"]
+
+
+def profile(name, kw, mode, warm, timed):
+    s = scenes.SCENES[name](lib, **kw)
+    lib.f2dWorld_SetLaunchMode(s.world, mode)
+    for _ in range(warm):
+        s.step()
+    lib.f2dWorld_EnableProfile(s.world, True)
+    t0 = time.perf_counter()
+    for _ in range(timed):
+        s.step()
+    wall = (time.perf_counter() - t0) / timed * 1e3
+    out = (C.c_ulonglong * 24)()
+    lib.f2dWorld_ReadProfile(s.world, out, 24)
+    total = sum(out[:21]) / timed / 1e3
+    print("%s %s mode %d: wall %.3f ms/frame, in-kernel %.1f us: " % (name, kw, mode, wall, total) +
+          " ".join("%s=%.1f" % (n, out[i] / timed / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
+    s.destroy()
+
+
+if "configs" in what:
+    t = scenes.bench2d(lib)
+    for _ in range(256):
+        t.step()
+    for threads, bps in ((256, 2), (128, 4), (64, 8), (32, 16), (128, 8), (64, 16)):
+        count = 148 * bps * 4
+        b = lib.f2dBatch_Create(t.world, count)
+        assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 2)
+        lib.f2dBatch_Synchronize(b)
+        lib.f2dBatch_EventRecord(b, 0)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 4)
+        lib.f2dBatch_EventRecord(b, 1)
+        lib.f2dBatch_Synchronize(b)
+        ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / 4
+        print("config %3d threads x %2d blocks/SM, %5d worlds: %.3f ms/step -> %.0f world-steps/s err=%x" % (
+            threads, bps, count, ms, count / ms * 1e3, lib.f2dBatch_GetErrorFlags(b)), flush=True)
+        lib.f2dBatch_Destroy(b)
+
+if "profile" in what:
+    profile("bench2d", {}, 0, 256, 64)
+    profile("bench2d", {}, 1, 256, 64)
+    profile("large_pyramid", {}, 1, 32, 32)
+    profile("large_pyramid", {}, 0, 32, 32)
+    profile("many_pyramids", {}, 1, 2, 16)
+    profile("joint_grid", {}, 1, 8, 32)
