@@ -72,7 +72,7 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 		add( w.trees[i].leafCenters, S + 4, false );
 		add( w.trees[i].work, kTreeStack * 6, false );
 	}
-	add( w.treeScratch, 17 * ( S + 8 ) + 2 * S + 16 + 8, false );
+	add( w.treeScratch, 24 * ( S + 8 ) + 2 * S + 16 + 8, false );
 	add( w.moveArray, S, true );
 	add( w.moveHeads, S, false );
 	add( w.movePairs, C, false );
@@ -92,6 +92,13 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.enlargedBits, B / 64 + 2, false );
 	add( w.islandBits, B / 64 + 2, false );
 	add( w.cons, cfFieldCount * C, false );
+	add( w.islSlotOff, B + 8, false );
+	add( w.islBodyOff, B + 8, false );
+	add( w.islColorOff, kColorCount * B + 8, false );
+	add( w.islColorFill, kColorCount * B + 8, false );
+	add( w.islBodyFill, B + 8, false );
+	add( w.islSlots, C, false );
+	add( w.islBodies, B, false );
 	add( w.bullets, B, false );
 	add( w.scan, B + 8, false );
 	add( w.scratch, 2 * B + 64, false );

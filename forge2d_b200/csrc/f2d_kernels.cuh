@@ -20,6 +20,11 @@ namespace f2d
 struct CtaCrew
 {
 	int n;
+	__device__ int groupCount() const { return n >> 5; }
+	__device__ int groupIndex() const { return (int)( threadIdx.x >> 5 ); }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
+	__device__ int groupSize() const { return 32; }
+	__device__ void groupSync() const { __syncwarp(); }
 	__device__ int rank() const { return (int)threadIdx.x; }
 	__device__ int size() const { return n; }
 	__device__ void sync() const { asm volatile( "bar.sync 1, %0;" ::"r"( n ) : "memory" ); }
@@ -33,6 +38,11 @@ struct CtaTeam
 	__device__ bool inSide() const { return threadIdx.x >= blockDim.x - 32; }
 	__device__ bool isSideLeader() const { return threadIdx.x == blockDim.x - 32; }
 	__device__ CtaCrew crew() const { return CtaCrew{ (int)blockDim.x - 32 }; }
+	__device__ int groupCount() const { return (int)( blockDim.x >> 5 ); }
+	__device__ int groupIndex() const { return (int)( threadIdx.x >> 5 ); }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
+	__device__ int groupSize() const { return 32; }
+	__device__ void groupSync() const { __syncwarp(); }
 	int32_t* smem; // blockDim.x + 32 ints of shared scratch
 	__device__ int rank() const { return (int)threadIdx.x; }
 	__device__ int size() const { return (int)blockDim.x; }
@@ -109,12 +119,12 @@ __device__ __forceinline__ void gridBarrierWait( GridBarrier* barrier, unsigned 
 	if ( threadIdx.x == 0 )
 	{
 		gen += parts;
-		__threadfence();
-		atomicAdd( &barrier->arrivals, 1u );
+		// release: the block's writes (ordered before this by the bar.sync above) become visible gpu-wide with the
+		// arrival; acquire: the spin load orders the other blocks' writes before everything after the bar.sync below
+		asm volatile( "red.release.gpu.global.add.u32 [%0], 1;" ::"l"( &barrier->arrivals ) : "memory" );
 		while ( (int)( loadAcquire( &barrier->arrivals ) - gen ) < 0 )
 		{
 		}
-		__threadfence();
 	}
 	__syncthreads();
 }
@@ -124,6 +134,11 @@ struct GridCrew
 {
 	GridBarrier* barrier;
 	unsigned int* gen;
+	__device__ int groupCount() const { return (int)( ( ( gridDim.x - 1 ) * blockDim.x ) >> 5 ); }
+	__device__ int groupIndex() const { return (int)( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 ); }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
+	__device__ int groupSize() const { return 32; }
+	__device__ void groupSync() const { __syncwarp(); }
 	__device__ int rank() const { return (int)( blockIdx.x * blockDim.x + threadIdx.x ); }
 	__device__ int size() const { return (int)( ( gridDim.x - 1 ) * blockDim.x ); }
 	__device__ void sync() const { gridBarrierWait( barrier, *gen, gridDim.x - 1 ); }
@@ -138,6 +153,11 @@ struct GridTeam
 	__device__ bool inSide() const { return blockIdx.x == gridDim.x - 1; }
 	__device__ bool isSideLeader() const { return blockIdx.x == gridDim.x - 1 && threadIdx.x == 0; }
 	__device__ GridCrew crew() { return GridCrew{ barrier + 1, &crewGen }; }
+	__device__ int groupCount() const { return (int)( ( gridDim.x * blockDim.x ) >> 5 ); }
+	__device__ int groupIndex() const { return (int)( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 ); }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
+	__device__ int groupSize() const { return 32; }
+	__device__ void groupSync() const { __syncwarp(); }
 	int32_t* smem;
 	int32_t* blockTotals; // gridDim.x ints in global memory
 	GridBarrier* barrier;

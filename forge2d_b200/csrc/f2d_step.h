@@ -444,42 +444,21 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 	total += w->awakeContacts.count;
 	segBase[kColorCount + 1] = total;
 
-	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492), concurrent with the narrowphase
-	// as in the reference when the team can spare a block for it (grid team: block 0 rebuilds with block-level
-	// barriers while the other blocks collide); otherwise one after the other, each fully data-parallel.
-	int collideRank = t.rank(), collideSize = t.size();
-	bool collides = true;
-	if constexpr ( Team::kHasSoloBlock )
+	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492). The reference overlaps it with
+	// the narrowphase on another worker; here the whole team does one after the other, each fully data-parallel
+	// (measured: a single block rebuilding beside the narrowphase is slower than the grid doing both in turn).
+	treeRebuildTeam( w, t, w->trees[kDynamicBody] );
+	treeRebuildTeam( w, t, w->trees[kKinematicBody] );
+	t.sync();
+	F2D_MARK( w, t, pfTreeRebuild );
+	for ( int i = t.rank(); i < total; i += t.size() )
 	{
-		collideRank = t.rankOutsideSolo();
-		collideSize = t.sizeOutsideSolo();
-		if ( t.inSoloBlock() )
-		{
-			auto solo = t.soloTeam();
-			treeRebuildTeam( w, solo, w->trees[kDynamicBody] );
-			treeRebuildTeam( w, solo, w->trees[kKinematicBody] );
-			F2D_MARK( w, t, pfTreeRebuild );
-			collides = false;
-		}
-	}
-	else
-	{
-		treeRebuildTeam( w, t, w->trees[kDynamicBody] );
-		treeRebuildTeam( w, t, w->trees[kKinematicBody] );
-		t.sync();
-		F2D_MARK( w, t, pfTreeRebuild );
-	}
-	if ( collides )
-	{
-		for ( int i = collideRank; i < total; i += collideSize )
-		{
-			int seg = 0;
-			while ( i >= segBase[seg + 1] )
-				seg += 1;
-			const Arr<int32_t>& list = seg < kColorCount ? w->colorContacts[seg] : w->awakeContacts;
-			int contactId = ptr( w, list )[i - segBase[seg]];
-			collideContact( w, contactId );
-		}
+		int seg = 0;
+		while ( i >= segBase[seg + 1] )
+			seg += 1;
+		const Arr<int32_t>& list = seg < kColorCount ? w->colorContacts[seg] : w->awakeContacts;
+		int contactId = ptr( w, list )[i - segBase[seg]];
+		collideContact( w, contactId );
 	}
 	t.sync();
 	F2D_MARK( w, t, pfNarrow );
@@ -624,6 +603,183 @@ template <class Team> F2D_HDF inline void constraintPass( World* w, Team& t, int
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ island-parallel solve
+// When the awake world is many small islands (many_pyramids: 400 piles of 55 boxes) the colour-by-colour solve wastes
+// its time in team-wide barriers: ~100 stages per step, each with a few thousand independent constraints. Islands
+// share no awake body, so every island can run the complete sub-step loop on its own: one group (a warp) per island,
+// colour after colour with warp-level synchronisation only. Inside a colour the constraints of an island touch
+// disjoint bodies, exactly as in the global colour, so the floating-point results are identical to the colour-parallel
+// path (and to the reference) whatever order the warps run in.
+constexpr int kIslandPathMinIslands = 16;
+constexpr int kIslandPathMaxContacts = 1024;
+constexpr int kIslandPathMaxBodies = 512;
+
+template <class Team> F2D_HDF inline void islandPartition( World* w, Team& t )
+{
+	const StepCtx& step = w->step;
+	const int islandCount = w->awakeIslands.count;
+	const int awakeBodyCount = step.awakeBodyCount;
+	const int slotCount = step.awakeContactCount;
+	const Island* islands = ptr( w, w->islands );
+	const int32_t* awakeIslands = ptr( w, w->awakeIslands );
+	const Contact* contacts = ptr( w, w->contacts );
+	const Body* bodies = ptr( w, w->bodies );
+	const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+	int32_t* slotOff = ptr( w, w->islSlotOff );
+	int32_t* bodyOff = ptr( w, w->islBodyOff );
+	int32_t* colorOff = ptr( w, w->islColorOff );
+	int32_t* colorFill = ptr( w, w->islColorFill );
+	int32_t* bodyFill = ptr( w, w->islBodyFill );
+	int32_t* islSlots = ptr( w, w->islSlots );
+	int32_t* islBodies = ptr( w, w->islBodies );
+
+	// ---- group the constraint slots by (island, colour) and the awake bodies by island
+	for ( int i = t.rank(); i < islandCount; i += t.size() )
+	{
+		const Island& is = islands[awakeIslands[i]];
+		slotOff[i] = is.contactCount;
+		bodyOff[i] = is.bodyCount;
+		bodyFill[i] = 0;
+	}
+	for ( int i = t.rank(); i < islandCount * kColorCount; i += t.size() )
+	{
+		colorOff[i] = 0;
+		colorFill[i] = 0;
+	}
+	t.sync();
+	int slotTotal = t.exclusiveScan( slotOff, islandCount );
+	int bodyTotal = t.exclusiveScan( bodyOff, islandCount );
+	if ( slotTotal != slotCount || bodyTotal != awakeBodyCount )
+	{
+		// some constraint or body is not owned by an awake island: keep the colour-parallel path for this step
+		t.sync();
+		if ( t.rank() == 0 )
+			w->step.islandPath = 0;
+		t.sync();
+		return;
+	}
+	for ( int slot = t.rank(); slot < slotCount; slot += t.size() )
+	{
+		int color = 0;
+		while ( slot >= step.colorBase[color + 1] )
+			color += 1;
+		int contactId = ptr( w, w->colorContacts[color] )[slot - step.colorBase[color]];
+		int li = islands[contacts[contactId].islandId].localIndex;
+		atomAdd( colorOff + li * kColorCount + color, 1 );
+	}
+	t.sync();
+	for ( int i = t.rank(); i < islandCount; i += t.size() )
+	{
+		int run = slotOff[i];
+		for ( int c = 0; c < kColorCount; ++c )
+		{
+			int n = colorOff[i * kColorCount + c];
+			colorOff[i * kColorCount + c] = run;
+			run += n;
+		}
+	}
+	t.sync();
+	for ( int slot = t.rank(); slot < slotCount; slot += t.size() )
+	{
+		int color = 0;
+		while ( slot >= step.colorBase[color + 1] )
+			color += 1;
+		int contactId = ptr( w, w->colorContacts[color] )[slot - step.colorBase[color]];
+		int li = islands[contacts[contactId].islandId].localIndex;
+		int k = li * kColorCount + color;
+		islSlots[colorOff[k] + atomAdd( colorFill + k, 1 )] = slot;
+	}
+	for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+	{
+		int li = islands[bodies[awakeBodies[i]].islandId].localIndex;
+		islBodies[bodyOff[li] + atomAdd( bodyFill + li, 1 )] = i;
+	}
+	t.sync();
+}
+
+// One group per island: the whole sub-step loop with group-level synchronisation
+template <class Team> F2D_HDF inline void islandSolve( World* w, Team& t )
+{
+	const StepCtx& step = w->step;
+	const int islandCount = w->awakeIslands.count;
+	const int awakeBodyCount = step.awakeBodyCount;
+	const int slotCount = step.awakeContactCount;
+	const int32_t* slotOff = ptr( w, w->islSlotOff );
+	const int32_t* bodyOff = ptr( w, w->islBodyOff );
+	const int32_t* colorOff = ptr( w, w->islColorOff );
+	const int32_t* islSlots = ptr( w, w->islSlots );
+	const int32_t* islBodies = ptr( w, w->islBodies );
+	BodyState* states = ptr( w, w->states );
+	const ConView c = conView( w );
+	const float h = step.h;
+	const float inv_h = step.inv_h;
+	const float contactSpeed = w->contactSpeed;
+	const float maxLinearSpeed = step.maxLinearVelocity;
+	const float maxAngularSpeed = kMaxRotation * step.inv_dt;
+	const int subStepCount = step.subStepCount;
+	const int lane = t.lane(), lanes = t.groupSize();
+	for ( int i = t.groupIndex(); i < islandCount; i += t.groupCount() )
+	{
+		const int b0 = bodyOff[i];
+		const int b1 = i + 1 < islandCount ? bodyOff[i + 1] : awakeBodyCount;
+		const int32_t* cOff = colorOff + i * kColorCount;
+		const int sEnd = i + 1 < islandCount ? slotOff[i + 1] : slotCount;
+		for ( int sub = 0; sub <= subStepCount; ++sub )
+		{
+			const bool restitutionPass = sub == subStepCount;
+			if ( restitutionPass == false )
+			{
+				for ( int k = b0 + lane; k < b1; k += lanes )
+					integrateVelocity( w, islBodies[k], h, maxLinearSpeed, maxAngularSpeed );
+				t.groupSync();
+			}
+			// stages: warm start, solve | integrate positions | relax  -- or restitution alone after the last sub-step
+			for ( int stage = restitutionPass ? 3 : 0; stage <= 3; ++stage )
+			{
+				if ( restitutionPass == false && stage == 3 )
+					break;
+				if ( stage == 2 )
+				{
+					for ( int k = b0 + lane; k < b1; k += lanes )
+						integratePosition( states[islBodies[k]], h );
+					t.groupSync();
+				}
+				for ( int color = 0; color < kOverflow; ++color )
+				{
+					const int s0 = cOff[color];
+					const int s1 = color + 1 < kColorCount ? cOff[color + 1] : sEnd;
+					if ( s0 == s1 )
+						continue;
+					for ( int k = s0 + lane; k < s1; k += lanes )
+					{
+						int slot = islSlots[k];
+						if ( stage == 0 )
+							warmStartSlot( c, slot, states );
+						else if ( stage == 1 )
+							solveSlot( c, slot, states, true, inv_h, contactSpeed );
+						else if ( stage == 2 )
+							solveSlot( c, slot, states, false, inv_h, contactSpeed );
+						else
+						{
+							// 4-lane group rule of the reference (contact_solver.c:1982-1986), by index in the global colour
+							int base = step.colorBase[color];
+							int count = step.colorBase[color + 1] - base;
+							int g0 = ( ( slot - base ) >> 2 ) << 2;
+							bool any = false;
+							for ( int q = g0; q < g0 + 4 && q < count; ++q )
+								any = any || ( c.f( cfRestitution, base + q ) != 0.0f );
+							if ( any )
+								restitutionSlot( c, slot, states, step.restitutionThreshold );
+						}
+					}
+					t.groupSync();
+				}
+			}
+		}
+	}
+	t.sync();
+}
+
 // Prepare, the sub-step loop, restitution and impulse storage (solver.c:929-1106) on `t`: the whole team, or the crew
 // left over when a side worker splits an island at the same time.
 template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
@@ -655,32 +811,40 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 	t.sync();
 	F2D_MARK( w, t, pfPrepare );
 
-	const float h = w->step.h;
-	const float maxLinearSpeed = w->step.maxLinearVelocity;
-	const float maxAngularSpeed = kMaxRotation * w->step.inv_dt;
-	const int subStepCount = w->step.subStepCount;
-	for ( int sub = 0; sub < subStepCount; ++sub )
+	if ( w->step.islandPath )
 	{
-		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
-			integrateVelocity( w, i, h, maxLinearSpeed, maxAngularSpeed );
-		t.sync();
-		F2D_MARK( w, t, pfIntegrateVel );
-		constraintPass( w, t, 0 );
-		F2D_MARK( w, t, pfWarmStart );
-		constraintPass( w, t, 1 );
+		islandSolve( w, t );
 		F2D_MARK( w, t, pfSolve );
-		{
-			BodyState* states = ptr( w, w->states );
-			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
-				integratePosition( states[i], h );
-		}
-		t.sync();
-		F2D_MARK( w, t, pfIntegratePos );
-		constraintPass( w, t, 2 );
-		F2D_MARK( w, t, pfRelax );
 	}
-	constraintPass( w, t, 3 );
-	F2D_MARK( w, t, pfRestitution );
+	else
+	{
+		const float h = w->step.h;
+		const float maxLinearSpeed = w->step.maxLinearVelocity;
+		const float maxAngularSpeed = kMaxRotation * w->step.inv_dt;
+		const int subStepCount = w->step.subStepCount;
+		for ( int sub = 0; sub < subStepCount; ++sub )
+		{
+			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+				integrateVelocity( w, i, h, maxLinearSpeed, maxAngularSpeed );
+			t.sync();
+			F2D_MARK( w, t, pfIntegrateVel );
+			constraintPass( w, t, 0 );
+			F2D_MARK( w, t, pfWarmStart );
+			constraintPass( w, t, 1 );
+			F2D_MARK( w, t, pfSolve );
+			{
+				BodyState* states = ptr( w, w->states );
+				for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+					integratePosition( states[i], h );
+			}
+			t.sync();
+			F2D_MARK( w, t, pfIntegratePos );
+			constraintPass( w, t, 2 );
+			F2D_MARK( w, t, pfRelax );
+		}
+		constraintPass( w, t, 3 );
+		F2D_MARK( w, t, pfRestitution );
+	}
 
 	// store impulses (solver.c:1093-1097)
 	{
@@ -760,6 +924,30 @@ template <class Team> F2D_HDF inline void mergeAwakeIslandsTeam( World* w, Team&
 template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 {
 	mergeAwakeIslandsTeam( w, t );
+	{
+		// size of the largest awake island (decides between the island-parallel and the colour-parallel solve)
+		if ( t.rank() == 0 )
+		{
+			w->step.maxIslandContacts = 0;
+			w->step.maxIslandBodies = 0;
+		}
+		t.sync();
+		const Island* islands = ptr( w, w->islands );
+		const int32_t* awake = ptr( w, w->awakeIslands );
+		int count = w->awakeIslands.count;
+		int maxC = 0, maxB = 0;
+		for ( int i = t.rank(); i < count; i += t.size() )
+		{
+			const Island& is = islands[awake[i]];
+			maxC = maxi( maxC, is.contactCount );
+			maxB = maxi( maxB, is.bodyCount );
+		}
+		if ( maxC > 0 )
+			atomMax32( &w->step.maxIslandContacts, maxC );
+		if ( maxB > 0 )
+			atomMax32( &w->step.maxIslandBodies, maxB );
+		t.sync();
+	}
 	if ( t.rank() == 0 )
 	{
 		w->stepIndex += 1;
@@ -782,6 +970,13 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 		}
 		s.colorBase[kColorCount] = base;
 		s.awakeContactCount = base;
+		// many small islands and nothing that needs a serial order: solve island by island (islandSolve)
+		int overflowCount = w->colorContacts[kOverflow].count + w->colorJoints[kOverflow].count;
+		s.islandPath = ( s.awakeJointCount == 0 && overflowCount == 0 && w->awakeIslands.count >= kIslandPathMinIslands &&
+						 s.maxIslandContacts <= kIslandPathMaxContacts && s.maxIslandBodies <= kIslandPathMaxBodies &&
+						 w->awakeIslands.count + 1 <= w->islSlotOff.cap )
+						   ? 1
+						   : 0;
 		if ( base > w->consStride )
 			setError( w, kErrCapacity, __LINE__ );
 		if ( s.awakeBodyCount > w->moveEvents.cap )
@@ -794,6 +989,9 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	F2D_MARK( w, t, pfSolveSetup );
 	if ( awakeBodyCount == 0 || ( w->error & kErrCapacity ) != 0 )
 		return;
+
+	if ( w->step.islandPath )
+		islandPartition( w, t );
 
 	// Island split (solver.c:1473-1485, 1700-1706): a serial depth-first walk that touches island links only, so, as in
 	// the reference, it runs concurrently with the solver stages when the team can spare a side worker for it.

@@ -17,6 +17,7 @@ F2D_HD void atomOr64( uint64_t* p, uint64_t v ) { atomicOr( reinterpret_cast<uns
 F2D_HD int atomAdd( int32_t* p, int v ) { return atomicAdd( p, v ); }
 F2D_HD void atomMax64( unsigned long long* p, unsigned long long v ) { atomicMax( p, v ); }
 F2D_HD void atomOr32( uint32_t* p, uint32_t v ) { atomicOr( p, v ); }
+F2D_HD void atomMax32( int32_t* p, int32_t v ) { atomicMax( p, v ); }
 // float min/max through the ordered-int trick (valid for any mix of signs, NaN-free inputs)
 F2D_HD void atomMinF( float* p, float v )
 {
@@ -47,6 +48,11 @@ F2D_HD void atomMax64( unsigned long long* p, unsigned long long v )
 		*p = v;
 }
 F2D_HD void atomOr32( uint32_t* p, uint32_t v ) { *p |= v; }
+F2D_HD void atomMax32( int32_t* p, int32_t v )
+{
+	if ( v > *p )
+		*p = v;
+}
 F2D_HD void atomMinF( float* p, float v )
 {
 	if ( v < *p )
@@ -89,6 +95,12 @@ struct SerialTeam
 	F2D_HD int rank() const { return 0; }
 	F2D_HD int size() const { return 1; }
 	F2D_HD void sync() const {}
+	// groups: independent sub-teams that only need to synchronise among themselves (warps on the device)
+	F2D_HD int groupCount() const { return 1; }
+	F2D_HD int groupIndex() const { return 0; }
+	F2D_HD int lane() const { return 0; }
+	F2D_HD int groupSize() const { return 1; }
+	F2D_HD void groupSync() const {}
 	// in-place exclusive scan of data[0..n), returns the total
 	F2D_HD int exclusiveScan( int32_t* data, int n ) const
 	{

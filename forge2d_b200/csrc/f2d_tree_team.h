@@ -24,50 +24,54 @@ namespace f2d
 
 struct TreeScratch
 {
-	int32_t* segOf;		// [n] start index of the segment a position belongs to
-	int32_t* segEnd;	// [n] by segment start
-	int32_t* segParent; // [n] by segment start: (parent node << 1) | side, kNull for the root segment
-	int32_t* segSplit;	// [n] by segment start
-	int32_t* scanLess;	// [n+1]
-	int32_t* scanBadL;	// [n+1]
-	int32_t* scanBadR;	// [n+1]
-	int32_t* badLPos;	// [n]
-	int32_t* badRPos;	// [n]
-	int32_t* freed;		// [n] dissolved node recycled for boundary m at freed[m-1]
-	int32_t* level;		// [n] build depth of the node at boundary m, at level[m-1]
-	float* loX;			// [n] by segment start: bounds of the item centres
-	float* loY;
-	float* hiX;
-	float* hiY;
+	int32_t* segOf;		   // [n] start index of the segment a position belongs to, kNull once the position is a child
+	int32_t* segEnd[2];	   // [n] by segment start, double-buffered by level parity
+	int32_t* segParent[2]; // [n] by segment start: (parent node << 1) | side, kNull for the root segment
+	int32_t* segSplit;	   // [n] by segment start
+	int32_t* scanLess;	   // [n+1] prefix sums of the "centre < pivot" flags
+	int32_t* lessFlag;	   // [n]
+	int32_t* badLPos;	   // [n] positions of the misplaced items, left part ascending ...
+	int32_t* badRPos;	   // [n] ... right part descending, stored from the segment start
+	int32_t* freed;		   // [n] dissolved node recycled for boundary m at freed[m-1]
+	int32_t* level;		   // [n] build depth of the node at boundary m, at level[m-1]
+	int32_t* posParent;	   // [n] (node << 1) | side of the node a retired position hangs under
+	float* lo[2][2];	   // [parity][axis][n] by segment start: bounds of the item centres
+	float* hi[2][2];
 	int32_t* under; // [nodeCap] items below a dissolved node, by node id
 	int32_t* ctrl;	// [8] loop control
 };
 
-F2D_HD int treeScratchInts( int shapeCap ) { return 17 * ( shapeCap + 8 ) + 2 * shapeCap + 16 + 8; }
+F2D_HD int treeScratchInts( int shapeCap ) { return 22 * ( shapeCap + 8 ) + 2 * shapeCap + 16 + 8; }
 
-F2D_HD TreeScratch treeScratch( World* w, const Tree& t )
+F2D_HD TreeScratch treeScratch( World* w )
 {
 	int n = w->shapes.cap + 8;
 	int32_t* base = ptr( w, w->treeScratch );
 	TreeScratch s;
-	s.segOf = base;
-	s.segEnd = base + n;
-	s.segParent = base + 2 * n;
-	s.segSplit = base + 3 * n;
-	s.scanLess = base + 4 * n;
-	s.scanBadL = base + 5 * n;
-	s.scanBadR = base + 6 * n;
-	s.badLPos = base + 7 * n;
-	s.badRPos = base + 8 * n;
-	s.freed = base + 9 * n;
-	s.level = base + 10 * n;
-	s.loX = reinterpret_cast<float*>( base + 11 * n );
-	s.loY = reinterpret_cast<float*>( base + 12 * n );
-	s.hiX = reinterpret_cast<float*>( base + 13 * n );
-	s.hiY = reinterpret_cast<float*>( base + 14 * n );
-	s.ctrl = base + 15 * n;
-	s.under = base + 15 * n + 8;
-	(void)t;
+	int k = 0;
+	auto take = [&]() { return base + ( k++ ) * n; };
+	s.segOf = take();
+	s.segEnd[0] = take();
+	s.segEnd[1] = take();
+	s.segParent[0] = take();
+	s.segParent[1] = take();
+	s.segSplit = take();
+	s.scanLess = take();
+	k += 1; // scanLess has n + 1 entries
+	s.lessFlag = take();
+	s.badLPos = take();
+	s.badRPos = take();
+	s.freed = take();
+	s.level = take();
+	s.posParent = take();
+	for ( int p = 0; p < 2; ++p )
+		for ( int a = 0; a < 2; ++a )
+		{
+			s.lo[p][a] = reinterpret_cast<float*>( take() );
+			s.hi[p][a] = reinterpret_cast<float*>( take() );
+		}
+	s.ctrl = take();
+	s.under = s.ctrl + 8;
 	return s;
 }
 
@@ -89,13 +93,21 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			setError( w, kErrCapacity, __LINE__ );
 		return;
 	}
-	TreeScratch s = treeScratch( w, tree );
+	TreeScratch s = treeScratch( w );
 	int32_t* leafIndices = ptr( w, tree.leafIndices );
 	V2* leafCenters = ptr( w, tree.leafCenters );
 
 	// ---- collect: items under each dissolved node
 	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 		s.under[i] = 0;
+	if ( t.rank() == 0 )
+	{
+		for ( int a = 0; a < 2; ++a )
+		{
+			s.lo[0][a][0] = FLT_MAX;
+			s.hi[0][a][0] = -FLT_MAX;
+		}
+	}
 	t.sync();
 	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 	{
@@ -140,21 +152,24 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		}
 		else
 		{
+			V2 c = boxCenter( n.box );
 			leafIndices[before] = i;
-			leafCenters[before] = boxCenter( n.box );
+			leafCenters[before] = c;
+			atomMinF( s.lo[0][0], c.x );
+			atomMinF( s.lo[0][1], c.y );
+			atomMaxF( s.hi[0][0], c.x );
+			atomMaxF( s.hi[0][1], c.y );
 		}
 	}
 	t.sync();
 
-	// ---- build, level by level
+	// ---- build, level by level (three passes and one prefix sum per level)
 	for ( int i = t.rank(); i < itemCount; i += t.size() )
 		s.segOf[i] = 0;
 	if ( t.rank() == 0 )
 	{
-		s.segEnd[0] = itemCount;
-		s.segParent[0] = kNull;
-		s.loX[0] = s.loY[0] = FLT_MAX;
-		s.hiX[0] = s.hiY[0] = -FLT_MAX;
+		s.segEnd[0][0] = itemCount;
+		s.segParent[0][0] = kNull;
 		s.ctrl[0] = 1; // a segment with >= 2 items exists at this level (itemCount >= 2 because the root is dissolved)
 		s.ctrl[1] = 0;
 	}
@@ -162,194 +177,191 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 	int level = 0;
 	while ( s.ctrl[level & 1] != 0 )
 	{
-		// P1: centre bounds per segment (segments of 2 split without looking at the centres)
-		for ( int i = t.rank(); i < itemCount; i += t.size() )
-		{
-			int a = s.segOf[i];
-			if ( a == kNull || s.segEnd[a] - a <= 2 )
-				continue;
-			V2 c = leafCenters[i];
-			atomMinF( s.loX + a, c.x );
-			atomMinF( s.loY + a, c.y );
-			atomMaxF( s.hiX + a, c.x );
-			atomMaxF( s.hiY + a, c.y );
-		}
-		if ( t.rank() == 0 )
-			s.ctrl[( level + 1 ) & 1] = 0;
-		t.sync();
-		// P2: which side of the pivot
+		const int cur = level & 1, nxt = cur ^ 1;
+		const int32_t* segEnd = s.segEnd[cur];
+		// pass A: side of the pivot (segments of <= 2 items split in the middle without looking at the centres)
 		for ( int i = t.rank(); i < itemCount; i += t.size() )
 		{
 			int a = s.segOf[i];
 			int less = 0;
-			if ( a != kNull && s.segEnd[a] - a > 2 )
+			if ( a != kNull && segEnd[a] - a > 2 )
 			{
-				float lx = s.loX[a], ly = s.loY[a], hx = s.hiX[a], hy = s.hiY[a];
+				float lx = s.lo[cur][0][a], ly = s.lo[cur][1][a], hx = s.hi[cur][0][a], hy = s.hi[cur][1][a];
 				bool useX = ( hx - lx ) > ( hy - ly );
 				float pivot = useX ? 0.5f * ( lx + hx ) : 0.5f * ( ly + hy );
 				V2 c = leafCenters[i];
 				less = ( useX ? c.x : c.y ) < pivot ? 1 : 0;
 			}
 			s.scanLess[i] = less;
-			s.badLPos[i] = less; // kept for P3 (scanLess is overwritten by its prefix sums)
+			s.lessFlag[i] = less;
 		}
 		t.sync();
 		int totalLess = t.exclusiveScan( s.scanLess, itemCount );
+		// bounds of the next level are accumulated in pass C: clear them (pass A was the last reader of this parity's
+		// predecessor) and the loop flag
+		for ( int i = t.rank(); i < itemCount; i += t.size() )
+		{
+			s.lo[nxt][0][i] = s.lo[nxt][1][i] = FLT_MAX;
+			s.hi[nxt][0][i] = s.hi[nxt][1][i] = -FLT_MAX;
+		}
 		if ( t.rank() == 0 )
+		{
 			s.scanLess[itemCount] = totalLess;
-		t.sync();
-		// P3: split point per segment, misplaced items
-		for ( int i = t.rank(); i < itemCount; i += t.size() )
-		{
-			int a = s.segOf[i];
-			int badL = 0, badR = 0;
-			if ( a != kNull )
-			{
-				int e = s.segEnd[a];
-				int count = e - a;
-				int split = a + count / 2;
-				if ( count > 2 )
-				{
-					int L = s.scanLess[e] - s.scanLess[a];
-					if ( L > 0 && L < count )
-					{
-						split = a + L;
-						int less = s.badLPos[i];
-						badL = ( i < split && less == 0 ) ? 1 : 0;
-						badR = ( i >= split && less != 0 ) ? 1 : 0;
-					}
-				}
-				if ( i == a )
-					s.segSplit[a] = split;
-			}
-			s.scanBadL[i] = badL;
-			s.scanBadR[i] = badR;
+			s.ctrl[nxt] = 0;
 		}
 		t.sync();
-		int totalBadL = t.exclusiveScan( s.scanBadL, itemCount );
-		int totalBadR = t.exclusiveScan( s.scanBadR, itemCount );
-		if ( t.rank() == 0 )
-		{
-			s.scanBadL[itemCount] = totalBadL;
-			s.scanBadR[itemCount] = totalBadR;
-		}
-		t.sync();
-		if ( totalBadL > 0 )
-		{
-			// P4: k-th misplaced-left (ascending) pairs with k-th misplaced-right (descending)
-			for ( int i = t.rank(); i < itemCount; i += t.size() )
-			{
-				int a = s.segOf[i];
-				if ( a == kNull )
-					continue;
-				int e = s.segEnd[a];
-				bool isBadL = s.scanBadL[i + 1] != s.scanBadL[i];
-				bool isBadR = s.scanBadR[i + 1] != s.scanBadR[i];
-				if ( isBadL )
-					s.badLPos[a + ( s.scanBadL[i] - s.scanBadL[a] )] = i;
-				if ( isBadR )
-				{
-					int bad = s.scanBadR[e] - s.scanBadR[a];
-					s.badRPos[a + ( bad - 1 - ( s.scanBadR[i] - s.scanBadR[a] ) )] = i;
-				}
-			}
-			t.sync();
-			// P5: swap
-			for ( int i = t.rank(); i < itemCount; i += t.size() )
-			{
-				int a = s.segOf[i];
-				if ( a == kNull )
-					continue;
-				int bad = s.scanBadL[s.segEnd[a]] - s.scanBadL[a];
-				if ( i - a >= bad )
-					continue;
-				int p = s.badLPos[i], q = s.badRPos[i];
-				int32_t ti = leafIndices[p];
-				leafIndices[p] = leafIndices[q];
-				leafIndices[q] = ti;
-				V2 tc = leafCenters[p];
-				leafCenters[p] = leafCenters[q];
-				leafCenters[q] = tc;
-			}
-			t.sync();
-		}
-		// P6: one internal node per segment; children are items (segments of one) or next-level segments
-		for ( int i = t.rank(); i < itemCount; i += t.size() )
-		{
-			int a = s.segOf[i];
-			if ( a != i )
-				continue;
-			int e = s.segEnd[a];
-			int m = s.segSplit[a];
-			int nodeIndex = s.freed[m - 1];
-			s.level[m - 1] = level;
-			TreeNode& node = nodes[nodeIndex];
-			node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
-			node.category = 1;
-			node.height = 0;
-			node.flags = kNodeAllocated;
-			int parentKey = s.segParent[a];
-			if ( parentKey == kNull )
-			{
-				node.parent = kNull;
-				tree.root = nodeIndex;
-			}
-			else
-			{
-				node.parent = parentKey >> 1;
-				if ( parentKey & 1 )
-					nodes[parentKey >> 1].child2 = nodeIndex;
-				else
-					nodes[parentKey >> 1].child1 = nodeIndex;
-			}
-			bool more = false;
-			if ( m - a == 1 )
-			{
-				int item = leafIndices[a];
-				node.child1 = item;
-				nodes[item].parent = nodeIndex;
-			}
-			else
-			{
-				s.segEnd[a] = m;
-				s.segParent[a] = ( nodeIndex << 1 ) | 0;
-				s.loX[a] = s.loY[a] = FLT_MAX;
-				s.hiX[a] = s.hiY[a] = -FLT_MAX;
-				more = true;
-			}
-			s.segEnd[m] = e;
-			if ( e - m == 1 )
-			{
-				int item = leafIndices[m];
-				node.child2 = item;
-				nodes[item].parent = nodeIndex;
-			}
-			else
-			{
-				s.segParent[m] = ( nodeIndex << 1 ) | 1;
-				s.loX[m] = s.loY[m] = FLT_MAX;
-				s.hiX[m] = s.hiY[m] = -FLT_MAX;
-				more = true;
-			}
-			if ( more )
-				s.ctrl[( level + 1 ) & 1] = 1;
-		}
-		t.sync();
-		// P7: positions move to their new segment (or retire when they became a child directly)
+		// pass B: split point per segment; the k-th misplaced item of the left part (ascending) will swap with the k-th
+		// misplaced item of the right part (descending) - both ranks follow from the one prefix sum
 		for ( int i = t.rank(); i < itemCount; i += t.size() )
 		{
 			int a = s.segOf[i];
 			if ( a == kNull )
 				continue;
+			int e = segEnd[a];
+			int count = e - a;
+			int split = a + count / 2;
+			if ( count > 2 )
+			{
+				int L = s.scanLess[e] - s.scanLess[a];
+				if ( L > 0 && L < count )
+				{
+					split = a + L;
+					int lessRank = s.scanLess[i] - s.scanLess[a];
+					int lessInLeft = s.scanLess[split] - s.scanLess[a];
+					int less = s.lessFlag[i];
+					if ( i < split && less == 0 )
+						s.badLPos[a + ( i - a ) - lessRank] = i;
+					else if ( i >= split && less != 0 )
+						s.badRPos[a + ( L - lessInLeft ) - 1 - ( lessRank - lessInLeft )] = i;
+				}
+			}
+			if ( i == a )
+				s.segSplit[a] = split;
+		}
+		t.sync();
+		// pass C: swap, create the node of every segment, move every position to its child segment (or retire it) and
+		// accumulate the centre bounds of the child segments
+		for ( int i = t.rank(); i < itemCount; i += t.size() )
+		{
+			int a = s.segOf[i];
+			if ( a == kNull )
+				continue;
+			int e = segEnd[a];
 			int m = s.segSplit[a];
-			if ( i < m )
-				s.segOf[i] = ( m - a == 1 ) ? kNull : a;
+			int count = e - a;
+			int bad = 0;
+			bool isBad = false;
+			if ( count > 2 )
+			{
+				int L = s.scanLess[e] - s.scanLess[a];
+				if ( L > 0 && L < count )
+				{
+					bad = L - ( s.scanLess[m] - s.scanLess[a] );
+					int less = s.lessFlag[i];
+					isBad = ( i < m && less == 0 ) || ( i >= m && less != 0 );
+				}
+			}
+			const bool leftGrows = m - a > 2, rightGrows = e - m > 2;
+			if ( i - a < bad )
+			{
+				int p = s.badLPos[i], q = s.badRPos[i];
+				int32_t ti = leafIndices[p];
+				leafIndices[p] = leafIndices[q];
+				leafIndices[q] = ti;
+				V2 cp = leafCenters[q], cq = leafCenters[p]; // centres after the swap
+				leafCenters[p] = cp;
+				leafCenters[q] = cq;
+				if ( leftGrows )
+				{
+					atomMinF( s.lo[nxt][0] + a, cp.x );
+					atomMinF( s.lo[nxt][1] + a, cp.y );
+					atomMaxF( s.hi[nxt][0] + a, cp.x );
+					atomMaxF( s.hi[nxt][1] + a, cp.y );
+				}
+				if ( rightGrows )
+				{
+					atomMinF( s.lo[nxt][0] + m, cq.x );
+					atomMinF( s.lo[nxt][1] + m, cq.y );
+					atomMaxF( s.hi[nxt][0] + m, cq.x );
+					atomMaxF( s.hi[nxt][1] + m, cq.y );
+				}
+			}
+			int nodeIndex = s.freed[m - 1];
+			const bool left = i < m;
+			if ( isBad == false && ( left ? leftGrows : rightGrows ) )
+			{
+				int b = left ? a : m;
+				V2 c = leafCenters[i];
+				atomMinF( s.lo[nxt][0] + b, c.x );
+				atomMinF( s.lo[nxt][1] + b, c.y );
+				atomMaxF( s.hi[nxt][0] + b, c.x );
+				atomMaxF( s.hi[nxt][1] + b, c.y );
+			}
+			if ( left )
+			{
+				bool single = m - a == 1;
+				s.segOf[i] = single ? kNull : a;
+				if ( single )
+					s.posParent[i] = ( nodeIndex << 1 ) | 0;
+			}
 			else
-				s.segOf[i] = ( s.segEnd[m] - m == 1 ) ? kNull : m;
+			{
+				bool single = e - m == 1;
+				s.segOf[i] = single ? kNull : m;
+				if ( single )
+					s.posParent[i] = ( nodeIndex << 1 ) | 1;
+			}
+			if ( i == a )
+			{
+				s.level[m - 1] = level;
+				TreeNode& node = nodes[nodeIndex];
+				node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+				node.category = 1;
+				node.height = 0;
+				node.flags = kNodeAllocated;
+				int parentKey = s.segParent[cur][a];
+				if ( parentKey == kNull )
+				{
+					node.parent = kNull;
+					tree.root = nodeIndex;
+				}
+				else
+				{
+					node.parent = parentKey >> 1;
+					if ( parentKey & 1 )
+						nodes[parentKey >> 1].child2 = nodeIndex;
+					else
+						nodes[parentKey >> 1].child1 = nodeIndex;
+				}
+				if ( m - a > 1 )
+				{
+					s.segEnd[nxt][a] = m;
+					s.segParent[nxt][a] = ( nodeIndex << 1 ) | 0;
+				}
+				if ( e - m > 1 )
+				{
+					s.segEnd[nxt][m] = e;
+					s.segParent[nxt][m] = ( nodeIndex << 1 ) | 1;
+				}
+				if ( m - a > 1 || e - m > 1 )
+					s.ctrl[nxt] = 1;
+			}
 		}
 		t.sync();
 		level += 1;
 	}
+	// every position has retired under some node: hang the items
+	for ( int i = t.rank(); i < itemCount; i += t.size() )
+	{
+		int key = s.posParent[i];
+		int item = leafIndices[i];
+		nodes[item].parent = key >> 1;
+		if ( key & 1 )
+			nodes[key >> 1].child2 = item;
+		else
+			nodes[key >> 1].child1 = item;
+	}
+	t.sync();
 
 	// ---- refit bottom-up, one level at a time
 	for ( int d = level - 1; d >= 0; --d )

@@ -446,6 +446,8 @@ struct StepCtx
 	int32_t moveCount;
 	int32_t pairCount;
 	int32_t mergeCount; // awake islands with a parent at the start of the solve
+	int32_t islandPath; // 1: constraints are solved island by island (one warp each), 0: colour by colour
+	int32_t maxIslandContacts, maxIslandBodies;
 	int32_t pad;
 	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
 };
@@ -612,6 +614,15 @@ struct World
 	Arr<uint64_t> islandBits;	// awake islands kept awake (solver.c:2024-2028)
 	Arr<float> cons;			// cfFieldCount x consStride
 	int32_t consStride, pad1;
+	// island-parallel solve (f2d_step.h islandSolve): per awake island, its constraint slots grouped by colour and its
+	// awake body indices
+	Arr<int32_t> islSlotOff;  // [awake islands + 1]
+	Arr<int32_t> islBodyOff;  // [awake islands + 1]
+	Arr<int32_t> islColorOff; // [awake islands * 12 + 1] start of (island, colour) in islSlots
+	Arr<int32_t> islColorFill;
+	Arr<int32_t> islBodyFill;
+	Arr<int32_t> islSlots;	  // [awake contacts]
+	Arr<int32_t> islBodies;	  // [awake bodies]
 	Arr<int32_t> bullets;
 	Arr<int32_t> scan;	  // scan scratch (awake bodies + 1)
 	Arr<int32_t> scratch; // island split stacks

@@ -270,6 +270,9 @@ F2D_API long long f2dWorld_GetKernelLaunchCount( void ); ///< kernels launched b
 /// Times of the last step's phases in ms measured with CUDA events: [pairs, collide, solve, finalize, total]
 F2D_API void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 );
 F2D_API void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag );
+/// What the last step did: [islandPath, activeColours, awakeContacts, awakeBodies, maxIslandContacts, maxIslandBodies,
+/// awakeIslands, mergedIslands]
+F2D_API int f2dWorld_GetStepInfo( b2WorldId worldId, int* out, int cap );
 /// In-kernel phase profile: ns per sub-phase (f2d::ProfSlot order) accumulated on the device since enabled
 F2D_API void f2dWorld_EnableProfile( b2WorldId worldId, bool flag );
 F2D_API int f2dWorld_ReadProfile( b2WorldId worldId, unsigned long long* out, int cap );

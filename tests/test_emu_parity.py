@@ -36,6 +36,23 @@ def test_emulated_step_is_bit_identical_to_reference(ref, emu, name, kw, frames,
     b.destroy()
 
 
+def test_island_parallel_solve_path_is_used_and_exact(ref, emu):
+    """25 small piles: the solver takes the island-by-island path (one group per island) and stays bit-identical."""
+    import ctypes as C
+    a = scenes.many_pyramids(ref, grid=5, base=5)
+    b = scenes.many_pyramids(emu, grid=5, base=5)
+    used = 0
+    for f in range(50):
+        a.step()
+        b.step()
+        info = (C.c_int * 8)()
+        emu.f2dWorld_GetStepInfo(b.world, info, 8)
+        used += info[0]
+        d = H.diff(H.snapshot(ref, a.world), H.snapshot(emu, b.world))
+        assert d == [], "frame %d: %s" % (f, d[:6])
+    assert used >= 20
+
+
 def test_sleep_and_wake_sequence(ref, emu):
     """Everything falls asleep, then a velocity kick through the API wakes one island (b2WakeSolverSet order)."""
     import ctypes as C

@@ -57,6 +57,26 @@ def test_joint_grid_with_rain(ref, gpu, mode):
     _lockstep(ref, gpu, "joint_grid", dict(n=12, rain_every=4), 120, 3, mode)
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_island_parallel_solve_path(ref, gpu, mode):
+    """100 small piles (36 boxes each): one warp per island runs the whole sub-step loop; bit-identical every frame."""
+    a = scenes.many_pyramids(ref, grid=10, base=8)
+    b = scenes.many_pyramids(gpu, grid=10, base=8)
+    gpu.f2dWorld_SetLaunchMode(b.world, mode)
+    used = 0
+    for f in range(45):
+        a.step()
+        b.step()
+        info = (C.c_int * 8)()
+        gpu.f2dWorld_GetStepInfo(b.world, info, 8)
+        used += info[0]
+        if f % 3 == 0:
+            d = H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, b.world))
+            assert d == [], "frame %d: %s" % (f, d[:6])
+    assert used >= 20
+    assert gpu.f2dGetLastError() == b""
+
+
 def test_large_pyramid_grid_mode(ref, gpu):
     _lockstep(ref, gpu, "large_pyramid", {}, 40, 8, 1, check_events=False)
 
