@@ -399,34 +399,34 @@ F2D_HDF inline SegmentDistance segmentDistance( V2 p1, V2 q1, V2 p2, V2 q2 )
 	return res;
 }
 
-// Reference-edge / incident-edge clipping: manifold.c:545-677
-F2D_HDF inline Manifold clipPolygons( const Poly& polyA, const Poly& polyB, int edgeA, int edgeB, bool flip )
+// Polygon with a compile-time vertex capacity. Every loop over it is fully unrolled and guarded by `count`, and every
+// run-time index goes through pickV (a select chain), so the vertices and normals stay in registers: a per-thread
+// array indexed at run time would live in local memory, which at ~1000 resident threads per SM spills out of L1.
+template <int N> struct PolyR
+{
+	V2 v[N];
+	V2 n[N];
+	float radius;
+	int count;
+};
+
+template <int N> F2D_HD V2 pickV( const V2 ( &a )[N], int index )
+{
+	V2 r = a[0];
+#pragma unroll
+	for ( int k = 1; k < N; ++k )
+	{
+		if ( index == k )
+			r = a[k];
+	}
+	return r;
+}
+
+// Reference-edge / incident-edge clipping: manifold.c:545-677. The four end points, the reference normal and the two
+// radii are already selected by the caller (poly1 = reference polygon, poly2 = incident polygon).
+F2D_HD Manifold clipSegments( V2 normal, V2 v11, V2 v12, V2 v21, V2 v22, float r1, float r2, int i11, int i12, int i21, int i22, bool flip )
 {
 	Manifold m = emptyManifold();
-	const Poly* poly1;
-	const Poly* poly2;
-	int i11, i12, i21, i22;
-	if ( flip )
-	{
-		poly1 = &polyB;
-		poly2 = &polyA;
-		i11 = edgeB;
-		i12 = edgeB + 1 < polyB.count ? edgeB + 1 : 0;
-		i21 = edgeA;
-		i22 = edgeA + 1 < polyA.count ? edgeA + 1 : 0;
-	}
-	else
-	{
-		poly1 = &polyA;
-		poly2 = &polyB;
-		i11 = edgeA;
-		i12 = edgeA + 1 < polyA.count ? edgeA + 1 : 0;
-		i21 = edgeB;
-		i22 = edgeB + 1 < polyB.count ? edgeB + 1 : 0;
-	}
-	V2 normal = poly1->n[i11];
-	V2 v11 = poly1->v[i11], v12 = poly1->v[i12];
-	V2 v21 = poly2->v[i21], v22 = poly2->v[i22];
 	V2 tangent = crossSV( 1.0f, normal );
 
 	float lower1 = 0.0f;
@@ -449,7 +449,6 @@ F2D_HDF inline Manifold clipPolygons( const Poly& polyA, const Poly& polyB, int 
 
 	float separationLower = dot( sub( vLower, v11 ), normal );
 	float separationUpper = dot( sub( vUpper, v11 ), normal );
-	float r1 = poly1->radius, r2 = poly2->radius;
 	vLower = mulAdd( vLower, 0.5f * ( r1 - r2 - separationLower ), normal );
 	vUpper = mulAdd( vUpper, 0.5f * ( r1 - r2 - separationUpper ), normal );
 	float radius = r1 + r2;
@@ -479,54 +478,98 @@ F2D_HDF inline Manifold clipPolygons( const Poly& polyA, const Poly& polyB, int 
 	return m;
 }
 
+// manifold.c:545-585: which polygon is the reference one depends on `flip`
+template <int NA, int NB>
+F2D_HD Manifold clipPolygons( const PolyR<NA>& polyA, const PolyR<NB>& polyB, int edgeA, int edgeB, bool flip )
+{
+	int nextA = edgeA + 1 < polyA.count ? edgeA + 1 : 0;
+	int nextB = edgeB + 1 < polyB.count ? edgeB + 1 : 0;
+	V2 a1 = pickV( polyA.v, edgeA ), a2 = pickV( polyA.v, nextA );
+	V2 b1 = pickV( polyB.v, edgeB ), b2 = pickV( polyB.v, nextB );
+	if ( flip )
+		return clipSegments( pickV( polyB.n, edgeB ), b1, b2, a1, a2, polyB.radius, polyA.radius, edgeB, nextB, edgeA, nextA, true );
+	return clipSegments( pickV( polyA.n, edgeA ), a1, a2, b1, b2, polyA.radius, polyB.radius, edgeA, nextA, edgeB, nextB, false );
+}
+
 // manifold.c:680-716
-F2D_HDF inline float findMaxSeparation( int* edgeIndex, const Poly& poly1, const Poly& poly2 )
+template <int N1, int N2> F2D_HD float findMaxSeparation( int* edgeIndex, const PolyR<N1>& poly1, const PolyR<N2>& poly2 )
 {
 	int count1 = poly1.count, count2 = poly2.count;
 	int bestIndex = 0;
 	float maxSeparation = -FLT_MAX;
-	for ( int i = 0; i < count1; ++i )
+#pragma unroll
+	for ( int i = 0; i < N1; ++i )
 	{
-		V2 n = poly1.n[i];
-		V2 v1 = poly1.v[i];
-		float si = FLT_MAX;
-		for ( int j = 0; j < count2; ++j )
+		if ( i < count1 )
 		{
-			float sij = dot( n, sub( poly2.v[j], v1 ) );
-			if ( sij < si )
-				si = sij;
-		}
-		if ( si > maxSeparation )
-		{
-			maxSeparation = si;
-			bestIndex = i;
+			V2 n = poly1.n[i];
+			V2 v1 = poly1.v[i];
+			float si = FLT_MAX;
+#pragma unroll
+			for ( int j = 0; j < N2; ++j )
+			{
+				if ( j < count2 )
+				{
+					float sij = dot( n, sub( poly2.v[j], v1 ) );
+					if ( sij < si )
+						si = sij;
+				}
+			}
+			if ( si > maxSeparation )
+			{
+				maxSeparation = si;
+				bestIndex = i;
+			}
 		}
 	}
 	*edgeIndex = bestIndex;
 	return maxSeparation;
 }
 
-// manifold.c:736-1075
-F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Poly& polygonB, Xf xfB )
+// Edge of `poly` whose normal is most anti-parallel to `searchDirection` (manifold.c:790-830)
+template <int N> F2D_HD int findIncidentEdge( const PolyR<N>& poly, V2 searchDirection )
+{
+	int edge = 0;
+	float minDot = FLT_MAX;
+#pragma unroll
+	for ( int i = 0; i < N; ++i )
+	{
+		if ( i < poly.count )
+		{
+			float d = dot( searchDirection, poly.n[i] );
+			if ( d < minDot )
+			{
+				minDot = d;
+				edge = i;
+			}
+		}
+	}
+	return edge;
+}
+
+// manifold.c:736-1075 on register-resident polygons. `polygonA`/`polygonB` are in their bodies' frames.
+template <int NA, int NB> F2D_HDF inline Manifold collidePolygonsR( const PolyR<NA>& polygonA, Xf xfA, const PolyR<NB>& polygonB, Xf xfB )
 {
 	V2 origin = polygonA.v[0];
 	Xf sfA = { add( xfA.p, rotate( xfA.q, origin ) ), xfA.q };
 	Xf xf = invMulXf( sfA, xfB );
 
-	Poly localA;
+	PolyR<NA> localA;
 	localA.count = polygonA.count;
 	localA.radius = polygonA.radius;
 	localA.v[0] = V2{ 0.0f, 0.0f };
 	localA.n[0] = polygonA.n[0];
-	for ( int i = 1; i < localA.count; ++i )
+#pragma unroll
+	for ( int i = 1; i < NA; ++i )
 	{
 		localA.v[i] = sub( polygonA.v[i], origin );
 		localA.n[i] = polygonA.n[i];
 	}
-	Poly localB;
+	PolyR<NB> localB;
 	localB.count = polygonB.count;
 	localB.radius = polygonB.radius;
-	for ( int i = 0; i < localB.count; ++i )
+#pragma unroll
+	for ( int i = 0; i < NB; ++i )
 	{
 		localB.v[i] = xfPoint( xf, polygonB.v[i] );
 		localB.n[i] = rotate( xf.q, polygonB.n[i] );
@@ -544,36 +587,12 @@ F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Pol
 	if ( separationA >= separationB )
 	{
 		flip = false;
-		V2 searchDirection = localA.n[edgeA];
-		int count = localB.count;
-		edgeB = 0;
-		float minDot = FLT_MAX;
-		for ( int i = 0; i < count; ++i )
-		{
-			float d = dot( searchDirection, localB.n[i] );
-			if ( d < minDot )
-			{
-				minDot = d;
-				edgeB = i;
-			}
-		}
+		edgeB = findIncidentEdge( localB, pickV( localA.n, edgeA ) );
 	}
 	else
 	{
 		flip = true;
-		V2 searchDirection = localB.n[edgeB];
-		int count = localA.count;
-		edgeA = 0;
-		float minDot = FLT_MAX;
-		for ( int i = 0; i < count; ++i )
-		{
-			float d = dot( searchDirection, localA.n[i] );
-			if ( d < minDot )
-			{
-				minDot = d;
-				edgeA = i;
-			}
-		}
+		edgeA = findIncidentEdge( localA, pickV( localB.n, edgeB ) );
 	}
 
 	Manifold m = emptyManifold();
@@ -583,8 +602,8 @@ F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Pol
 		int i12 = edgeA + 1 < localA.count ? edgeA + 1 : 0;
 		int i21 = edgeB;
 		int i22 = edgeB + 1 < localB.count ? edgeB + 1 : 0;
-		V2 v11 = localA.v[i11], v12 = localA.v[i12];
-		V2 v21 = localB.v[i21], v22 = localB.v[i22];
+		V2 v11 = pickV( localA.v, i11 ), v12 = pickV( localA.v, i12 );
+		V2 v21 = pickV( localB.v, i21 ), v22 = pickV( localB.v, i22 );
 
 		SegmentDistance result = segmentDistance( v11, v12, v21, v22 );
 		float dist = sqrtf( result.distanceSquared );
@@ -594,8 +613,10 @@ F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Pol
 
 		m = clipPolygons( localA, localB, edgeA, edgeB, flip );
 		float minSeparation = FLT_MAX;
-		for ( int i = 0; i < m.pointCount; ++i )
-			minSeparation = minf( minSeparation, m.points[i].separation );
+		if ( m.pointCount > 0 )
+			minSeparation = minf( minSeparation, m.points[0].separation );
+		if ( m.pointCount > 1 )
+			minSeparation = minf( minSeparation, m.points[1].separation );
 
 		if ( separation + 0.1f * kLinearSlop < minSeparation )
 		{
@@ -630,15 +651,77 @@ F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Pol
 	if ( m.pointCount > 0 )
 	{
 		m.normal = rotate( xfA.q, m.normal );
-		for ( int i = 0; i < m.pointCount; ++i )
+#pragma unroll
+		for ( int i = 0; i < 2; ++i )
 		{
-			ManifoldPoint* mp = m.points + i;
-			mp->anchorA = rotate( xfA.q, add( mp->anchorA, origin ) );
-			mp->anchorB = add( mp->anchorA, sub( xfA.p, xfB.p ) );
-			mp->point = add( xfA.p, mp->anchorA );
+			if ( i < m.pointCount )
+			{
+				ManifoldPoint* mp = m.points + i;
+				mp->anchorA = rotate( xfA.q, add( mp->anchorA, origin ) );
+				mp->anchorB = add( mp->anchorA, sub( xfA.p, xfB.p ) );
+				mp->point = add( xfA.p, mp->anchorA );
+			}
 		}
 	}
 	return m;
+}
+
+// Loads the first N vertices / normals of a stored polygon (entries beyond `count` are never used)
+template <int N> F2D_HD PolyR<N> loadPoly( const Poly& p )
+{
+	PolyR<N> r;
+	r.count = p.count;
+	r.radius = p.radius;
+#pragma unroll
+	for ( int i = 0; i < N; ++i )
+	{
+		bool live = i < p.count;
+		r.v[i] = live ? p.v[i] : V2{ 0.0f, 0.0f };
+		r.n[i] = live ? p.n[i] : V2{ 0.0f, 0.0f };
+	}
+	return r;
+}
+
+// manifold.c:16-34 b2MakeCapsule as a two-vertex polygon
+template <int N> F2D_HD PolyR<N> capsulePolyR( V2 p1, V2 p2, float radius )
+{
+	PolyR<N> s;
+#pragma unroll
+	for ( int i = 0; i < N; ++i )
+	{
+		s.v[i] = V2{ 0.0f, 0.0f };
+		s.n[i] = V2{ 0.0f, 0.0f };
+	}
+	s.v[0] = p1;
+	s.v[1] = p2;
+	V2 d = sub( p2, p1 );
+	V2 axis = normalize( d );
+	V2 normal = rightPerp( axis );
+	s.n[0] = normal;
+	s.n[1] = neg( normal );
+	s.count = 2;
+	s.radius = radius;
+	return s;
+}
+
+// Boxes and capsule-polygons (<= 4 vertices) take the small instantiation; anything larger the 8-vertex one.
+F2D_HDF inline Manifold collidePolygons( const Poly& polygonA, Xf xfA, const Poly& polygonB, Xf xfB )
+{
+	if ( polygonA.count <= 4 && polygonB.count <= 4 )
+		return collidePolygonsR( loadPoly<4>( polygonA ), xfA, loadPoly<4>( polygonB ), xfB );
+	return collidePolygonsR( loadPoly<8>( polygonA ), xfA, loadPoly<8>( polygonB ), xfB );
+}
+F2D_HDF inline Manifold collideSegmentAndPolygon( V2 p1, V2 p2, float radius, Xf xfA, const Poly& polygonB, Xf xfB )
+{
+	if ( polygonB.count <= 4 )
+		return collidePolygonsR( capsulePolyR<2>( p1, p2, radius ), xfA, loadPoly<4>( polygonB ), xfB );
+	return collidePolygonsR( capsulePolyR<2>( p1, p2, radius ), xfA, loadPoly<8>( polygonB ), xfB );
+}
+F2D_HDF inline Manifold collidePolygonAndCapsule( const Poly& polygonA, Xf xfA, const Capsule& b, Xf xfB )
+{
+	if ( polygonA.count <= 4 )
+		return collidePolygonsR( loadPoly<4>( polygonA ), xfA, capsulePolyR<2>( b.c1, b.c2, b.radius ), xfB );
+	return collidePolygonsR( loadPoly<8>( polygonA ), xfA, capsulePolyR<2>( b.c1, b.c2, b.radius ), xfB );
 }
 
 // Dispatch on the (primary-ordered) shape-type pair: B2/src/contact.c:166-184 registers.
@@ -687,10 +770,7 @@ F2D_HDF inline Manifold computeManifold( World* w, const Shape& a, Xf xfA, const
 			if ( b.type == kCircle )
 				return collidePolygonAndCircle( a.polygon, xfA, b.circle, xfB );
 			if ( b.type == kCapsule )
-			{
-				Poly polyB = makeCapsulePoly( b.capsule.c1, b.capsule.c2, b.capsule.radius ); // manifold.c:538-542
-				return collidePolygons( a.polygon, xfA, polyB, xfB );
-			}
+				return collidePolygonAndCapsule( a.polygon, xfA, b.capsule, xfB ); // manifold.c:538-542
 			return collidePolygons( a.polygon, xfA, b.polygon, xfB );
 		case kSegment:
 		{
@@ -704,8 +784,7 @@ F2D_HDF inline Manifold computeManifold( World* w, const Shape& a, Xf xfA, const
 				Capsule capA = { a.segment.p1, a.segment.p2, 0.0f }; // manifold.c:532-536
 				return collideCapsules( capA, xfA, b.capsule, xfB );
 			}
-			Poly polyA = makeCapsulePoly( a.segment.p1, a.segment.p2, 0.0f ); // manifold.c:1083-1087
-			return collidePolygons( polyA, xfA, b.polygon, xfB );
+			return collideSegmentAndPolygon( a.segment.p1, a.segment.p2, 0.0f, xfA, b.polygon, xfB ); // manifold.c:1083-1087
 		}
 		default:
 			// chain segments: not on the device path yet

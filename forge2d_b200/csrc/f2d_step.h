@@ -611,8 +611,8 @@ template <class Team> F2D_HDF inline void constraintPass( World* w, Team& t, int
 // disjoint bodies, exactly as in the global colour, so the floating-point results are identical to the colour-parallel
 // path (and to the reference) whatever order the warps run in.
 constexpr int kIslandPathMinIslands = 16;
-constexpr int kIslandPathMaxContacts = 1024;
-constexpr int kIslandPathMaxBodies = 512;
+constexpr int kIslandPathMaxContacts = 256; // ~32 constraints per colour: one pass of a warp
+constexpr int kIslandPathMaxBodies = 128;
 
 template <class Team> F2D_HDF inline void islandPartition( World* w, Team& t )
 {
@@ -895,26 +895,74 @@ template <class Team> F2D_HDF inline void mergeAwakeIslandsTeam( World* w, Team&
 	t.sync();
 	if ( w->step.mergeCount == 0 )
 		return;
-	// every merging island relabels its own bodies / contacts / joints (independent list walks) ...
 	for ( int i = t.rank(); i < count; i += t.size() )
 	{
 		if ( roots[i] != awake[i] )
-		{
 			islands[awake[i]].parentIsland = roots[i];
-			relabelIsland( w, islands[awake[i]], roots[i] );
+	}
+	t.sync();
+	// Relabel (island.c:436-471) without walking the child islands' lists: every awake body, every touching contact
+	// (= every entry of a colour array) and every awake joint looks up whether its island now has a parent.
+	{
+		Body* bodies = ptr( w, w->bodies );
+		Contact* contacts = ptr( w, w->contacts );
+		Joint* joints = ptr( w, w->joints );
+		const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+		int bodyCount = w->awakeBodies.count;
+		for ( int i = t.rank(); i < bodyCount; i += t.size() )
+		{
+			Body& b = bodies[awakeBodies[i]];
+			if ( b.islandId != kNull && islands[b.islandId].parentIsland != kNull )
+				b.islandId = islands[b.islandId].parentIsland;
+		}
+		for ( int color = 0; color < kColorCount; ++color )
+		{
+			const int32_t* cl = ptr( w, w->colorContacts[color] );
+			int n = w->colorContacts[color].count;
+			for ( int i = t.rank(); i < n; i += t.size() )
+			{
+				Contact& c = contacts[cl[i]];
+				if ( c.islandId != kNull && islands[c.islandId].parentIsland != kNull )
+					c.islandId = islands[c.islandId].parentIsland;
+			}
+			const int32_t* jl = ptr( w, w->colorJoints[color] );
+			int nj = w->colorJoints[color].count;
+			for ( int i = t.rank(); i < nj; i += t.size() )
+			{
+				Joint& j = joints[jl[i]];
+				if ( j.islandId != kNull && islands[j.islandId].parentIsland != kNull )
+					j.islandId = islands[j.islandId].parentIsland;
+			}
 		}
 	}
 	t.sync();
-	// ... and rank 0 splices the lists onto the roots, last island first (order-defining)
+	// ... and rank 0 splices the lists onto the roots, last island first (order-defining). The merging islands are
+	// compacted first so the serial loop only visits them. destroyIsland swap-removes from awakeIslands, which only
+	// moves entries from the tail, i.e. islands this descending loop has already passed.
+	int32_t* flags = ptr( w, w->islBodyFill );
+	int32_t* merging = ptr( w, w->islSlotOff );
+	if ( count > w->islBodyFill.cap || count > w->islSlotOff.cap )
+	{
+		if ( t.rank() == 0 )
+			setError( w, kErrCapacity, __LINE__ );
+		return;
+	}
+	for ( int i = t.rank(); i < count; i += t.size() )
+		flags[i] = roots[i] != awake[i] ? 1 : 0;
+	t.sync();
+	int mergeTotal = t.exclusiveScan( flags, count );
+	for ( int i = t.rank(); i < count; i += t.size() )
+	{
+		if ( roots[i] != awake[i] )
+			merging[flags[i]] = awake[i];
+	}
+	t.sync();
 	if ( t.rank() == 0 )
 	{
-		for ( int i = count - 1; i >= 0; --i )
+		for ( int k = mergeTotal - 1; k >= 0; --k )
 		{
-			int islandId = ptr( w, w->awakeIslands )[i];
-			Island& island = islands[islandId];
-			if ( island.parentIsland == kNull )
-				continue;
-			mergeIsland( w, island, false );
+			int islandId = merging[k];
+			mergeIsland( w, islands[islandId], false );
 			destroyIsland( w, islandId );
 		}
 	}
@@ -1331,12 +1379,26 @@ F2D_HDF inline void enlargeLeafParallel( World* w, Tree& tree, int leaf, Box box
 	while ( parent != kNull )
 	{
 		TreeNode& n = nodes[parent];
-		atomMinF( &n.box.lo.x, box.lo.x );
-		atomMinF( &n.box.lo.y, box.lo.y );
-		atomMaxF( &n.box.hi.x, box.hi.x );
-		atomMaxF( &n.box.hi.y, box.hi.y );
-		// height (low 16 bits) and flags (high 16 bits) share one 32-bit word
-		atomOr32( reinterpret_cast<uint32_t*>( &n.height ), (uint32_t)kNodeEnlarged << 16 );
+		// Plain reads first: boxes only grow and flags only accumulate during this phase, so a stale value can only
+		// cause a redundant atomic, never a missed one. Once an ancestor already contains the box AND is flagged,
+		// whoever grew / flagged it is carrying both up to the root (or they were that way before the phase, and the
+		// tree invariants - parent contains child, flags are upward closed - cover the rest of the path).
+		bool contains = n.box.lo.x <= box.lo.x && n.box.lo.y <= box.lo.y && box.hi.x <= n.box.hi.x && box.hi.y <= n.box.hi.y;
+		bool flagged = ( n.flags & kNodeEnlarged ) != 0;
+		if ( contains && flagged )
+			break;
+		if ( contains == false )
+		{
+			atomMinF( &n.box.lo.x, box.lo.x );
+			atomMinF( &n.box.lo.y, box.lo.y );
+			atomMaxF( &n.box.hi.x, box.hi.x );
+			atomMaxF( &n.box.hi.y, box.hi.y );
+		}
+		if ( flagged == false )
+		{
+			// height (low 16 bits) and flags (high 16 bits) share one 32-bit word
+			atomOr32( reinterpret_cast<uint32_t*>( &n.height ), (uint32_t)kNodeEnlarged << 16 );
+		}
 		parent = n.parent;
 	}
 }

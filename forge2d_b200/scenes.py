@@ -244,10 +244,54 @@ def falling_shapes(lib, count=24, create=None, **world_kw):
     return Scene(lib, world, bodies, "falling_shapes_%d" % count)
 
 
+def polygon_soup(lib, count=40, create=None, **world_kw):
+    """Convex polygons with 3..8 vertices (b2ComputeHull + b2MakePolygon, some rounded), capsules and circles dropped
+    into a box of segments: covers the 8-vertex SAT / clipping path and every polygon-vs-other manifold function."""
+    import math
+    world = _world(lib, create=create, **world_kw)
+    bd = lib.b2DefaultBodyDef()
+    ground = lib.b2CreateBody(world, C.byref(bd))
+    sd = lib.b2DefaultShapeDef()
+    for p1, p2 in (((-12.0, 0.0), (12.0, 0.0)), ((-12.0, 0.0), (-14.0, 20.0)), ((12.0, 0.0), (14.0, 20.0))):
+        seg = A.Segment(A.Vec2(*p1), A.Vec2(*p2))
+        lib.b2CreateSegmentShape(ground, C.byref(sd), C.byref(seg))
+    bodies = [ground]
+    rng = _Lcg(4242)
+    sd.material.friction = 0.4
+    for i in range(count):
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        bd.position = A.Vec2(_f32(-8.0 + 16.0 * rng.next()), _f32(1.5 + 0.9 * i))
+        ang = 6.28 * rng.next()
+        bd.rotation = A.Rot(_f32(math.cos(ang)), _f32(math.sin(ang)))
+        bd.angularVelocity = _f32(4.0 * rng.next() - 2.0)
+        body = lib.b2CreateBody(world, C.byref(bd))
+        kind = i % 5
+        if kind == 3:
+            cap = A.Capsule(A.Vec2(-0.5, 0.0), A.Vec2(0.5, 0.0), _f32(0.15 + 0.2 * rng.next()))
+            lib.b2CreateCapsuleShape(body, C.byref(sd), C.byref(cap))
+        elif kind == 4:
+            c = A.Circle(A.Vec2(0.0, 0.0), _f32(0.25 + 0.3 * rng.next()))
+            lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+        else:
+            n = 3 + (i * 7) % 6  # 3..8 vertices
+            r = 0.4 + 0.4 * rng.next()
+            pts = (A.Vec2 * n)()
+            for k in range(n):
+                a = 2.0 * math.pi * (k + 0.3 * rng.next()) / n
+                pts[k] = A.Vec2(_f32(r * math.cos(a)), _f32(0.8 * r * math.sin(a)))
+            hull = lib.b2ComputeHull(pts, n)
+            poly = lib.b2MakePolygon(C.byref(hull), _f32(0.05 if kind == 2 else 0.0))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(poly))
+        bodies.append(body)
+    return Scene(lib, world, bodies, "polygon_soup_%d" % count)
+
+
 SCENES = {
     "bench2d": bench2d,
     "large_pyramid": large_pyramid,
     "many_pyramids": many_pyramids,
     "joint_grid": joint_grid,
     "falling_shapes": falling_shapes,
+    "polygon_soup": polygon_soup,
 }

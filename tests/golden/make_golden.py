@@ -21,6 +21,7 @@ CASES = [
     ("falling_shapes", {"count": 24}, [1, 100, 240]),
     ("many_pyramids", {"grid": 3, "base": 6}, [1, 30, 120]),
     ("joint_grid", {"n": 12}, [1, 30, 120]),
+    ("polygon_soup", {"count": 40}, [1, 60, 200]),
 ]
 
 

@@ -48,6 +48,11 @@ def test_falling_shapes_all_manifold_functions(ref, gpu, mode):
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_polygon_soup_eight_vertex_path(ref, gpu, mode):
+    _lockstep(ref, gpu, "polygon_soup", dict(count=40), 220, 2, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_many_pyramids_sleep(ref, gpu, mode):
     _lockstep(ref, gpu, "many_pyramids", dict(grid=3, base=6), 120, 3, mode)
 

@@ -11,6 +11,9 @@ from forge2d_b200 import scenes
 lib = forge2d_b200.load_library()
 assert lib.f2dHasDevice()
 what = sys.argv[1:] or ["single", "batch"]
+PROF_NAMES = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
+              "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
+              "bullets", "sleep", "end"]
 
 
 def single(name, kw, mode, warm, timed):
@@ -62,7 +65,7 @@ if "batch" in what:
             count, ms, count / ms * 1e3, lib.f2dBatch_GetWorldBytes(b) / 1e6, lib.f2dBatch_GetErrorFlags(b)), flush=True)
         lib.f2dBatch_Destroy(b)
 
-PROF_NAMES = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
+_PROF_NAMES_MOVED = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
               "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
               "bullets", "sleep", "end"]
 
@@ -103,6 +106,31 @@ if "configs" in what:
         print("config %3d threads x %2d blocks/SM, %5d worlds: %.3f ms/step -> %.0f world-steps/s err=%x" % (
             threads, bps, count, ms, count / ms * 1e3, lib.f2dBatch_GetErrorFlags(b)), flush=True)
         lib.f2dBatch_Destroy(b)
+
+if "batchprofile" in what:
+    t = scenes.bench2d(lib)
+    for _ in range(256):
+        t.step()
+    lib.f2dWorld_EnableProfile(t.world, True)
+    for threads, bps, count in ((64, 16, 2368), (128, 8, 1184), (256, 2, 296)):
+        b = lib.f2dBatch_Create(t.world, count)
+        assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
+        steps = 8
+        lib.f2dBatch_EventRecord(b, 0)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, steps)
+        lib.f2dBatch_EventRecord(b, 1)
+        lib.f2dBatch_Synchronize(b)
+        ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
+        scratch = scenes.bench2d(lib, rows=1)
+        lib.f2dBatch_DownloadWorld(b, count // 2, scratch.world)
+        out = (C.c_ulonglong * 24)()
+        lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+        total = sum(out[:21]) / steps / 1e3
+        print("batch %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
+            threads, bps, count, ms, count / ms * 1e3, count // 2, total) +
+            " ".join("%s=%.1f" % (n, out[i] / steps / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
+        lib.f2dBatch_Destroy(b)
+        scratch.destroy()
 
 if "profile" in what:
     profile("bench2d", {}, 0, 256, 64)
