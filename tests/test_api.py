@@ -1,0 +1,158 @@
+"""The reference's own behavioural tests for the step path, transliterated from Dart onto the Python mirror of its API
+(forge2d_b200/api.py). Sources: packages/forge2d/test/api/world_test.dart:8-74, events_test.dart:17-148 (contact
+begin/end/hit, body move events, fellAsleep), packages/forge2d/test/ffi/smoke_test.dart:13-51.
+
+Run twice: on CPU against the host emulation of the step templates (host logic of the API layer), and with `-m gpu`
+against the product library, where every World.step is a CUDA kernel launch."""
+import pytest
+
+from forge2d_b200 import api
+from forge2d_b200.api import (BodyDef, BodyType, Circle, Polygon, ShapeDef, Vector2, World, WorldDef)
+
+
+@pytest.fixture(params=["emu", pytest.param("gpu", marks=pytest.mark.gpu)])
+def backend(request):
+    lib = request.getfixturevalue(request.param)
+    api.initializeForge2D(lib)
+    yield lib
+    api._backend = None
+
+
+@pytest.fixture
+def world(backend):
+    w = World()
+    yield w
+    if w.isValid:
+        w.destroy()
+
+
+def ground(world):
+    body = world.createBody(BodyDef(position=Vector2(0, -1)))
+    shape = body.createShape(Polygon.box(50, 1), ShapeDef(enableContactEvents=True))
+    return body, shape
+
+
+# ---- world_test.dart
+def test_world_starts_valid_and_becomes_invalid_on_destroy(backend):
+    w = World()
+    assert w.isValid
+    w.destroy()
+    assert not w.isValid
+
+
+def test_world_gravity_default_override_and_change(backend):
+    w = World()
+    assert w.gravity == Vector2(0, -10)
+    w.gravity = Vector2(0, -3.5)
+    assert w.gravity == Vector2(0, -3.5)
+    w.destroy()
+    w = World(gravity=Vector2(3, -1.5))
+    assert w.gravity == Vector2(3, -1.5)
+    w.destroy()
+
+
+def test_definition_toggles_are_applied(backend):
+    w = World(definition=WorldDef(enableSleep=False, enableContinuous=False))
+    assert not w.sleepingEnabled and not w.continuousEnabled
+    w.sleepingEnabled = True
+    w.continuousEnabled = True
+    assert w.sleepingEnabled and w.continuousEnabled
+    w.destroy()
+
+
+def test_destroying_a_world_destroys_its_bodies(backend):
+    w = World()
+    body = w.createBody(BodyDef(userData="payload"))
+    assert body.isValid and body.userData == "payload"
+    w.destroy()
+    assert not body.isValid
+
+
+def test_a_falling_box_lands_on_a_static_ground_box(world):
+    world.createBody(BodyDef(position=Vector2(0, -1))).createShape(Polygon.box(50, 1))
+    box = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 10)))
+    box.createShape(Polygon.square(0.5))
+    for _ in range(200):
+        world.step(1 / 60)
+    assert box.position.x == pytest.approx(0, abs=0.01)
+    assert box.position.y == pytest.approx(0.5, abs=0.01)
+    assert not box.isAwake
+
+
+# ---- events_test.dart
+def test_begin_and_end_events_fire_for_a_bouncing_contact(world):
+    _, ground_shape = ground(world)
+    ball = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 2)))
+    ball_shape = ball.createShape(Circle(radius=0.5), ShapeDef(enableContactEvents=True, restitution=0.8))
+    began, ended = [], []
+    for _ in range(120):
+        world.step(1 / 60)
+        events = world.contactEvents
+        began += events.begin
+        ended += events.end
+    assert began
+    touching = {began[0].shapeA, began[0].shapeB}
+    assert ball_shape in touching and ground_shape in touching
+    assert began[0].points
+    assert abs(began[0].normal.y) == pytest.approx(1, abs=0.01)
+    assert ended  # the bouncy ball leaves the ground again
+
+
+def test_hit_events_report_the_approach_speed(world):
+    ground(world)
+    world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 5))).createShape(
+        Circle(radius=0.5), ShapeDef(enableContactEvents=True, enableHitEvents=True))
+    hits = []
+    for _ in range(120):
+        world.step(1 / 60)
+        hits += world.contactEvents.hit
+    assert hits
+    assert hits[0].approachSpeed > 1  # dropped from 5 m: above the default 1 m/s threshold
+
+
+def test_no_events_without_enable_contact_events(world):
+    world.createBody(BodyDef(position=Vector2(0, -1))).createShape(Polygon.box(50, 1), ShapeDef(enableContactEvents=False))
+    world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 2))).createShape(
+        Circle(radius=0.5), ShapeDef(enableContactEvents=False))
+    for _ in range(120):
+        world.step(1 / 60)
+        assert world.contactEvents.begin == []
+
+
+def test_only_moving_bodies_are_reported(world):
+    ground(world)
+    faller = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(10, 5)))
+    faller.createShape(Circle(radius=0.5))
+    world.step(1 / 60)
+    events = world.bodyMoveEvents
+    mine = [e for e in events if e.body == faller]
+    assert len(mine) == 1
+    assert mine[0].transform.p.y < 5
+    assert mine[0].fellAsleep is False
+
+
+def test_fell_asleep_is_reported_when_a_body_comes_to_rest(world):
+    ground(world)
+    world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 0.6))).createShape(Polygon.square(0.5))
+    reported = False
+    for _ in range(300):
+        world.step(1 / 60)
+        if any(e.fellAsleep for e in world.bodyMoveEvents):
+            reported = True
+            break
+    assert reported
+
+
+# ---- locked_world_test.dart: the locked flag only spans step()
+def test_world_is_unlocked_after_step_and_creation_works(world):
+    world.step(1 / 60)
+    assert world.locked is False
+    body = world.createBody(BodyDef(type=BodyType.dynamic))
+    assert body.isValid
+
+
+# ---- smoke_test.dart: stepping an empty world
+def test_stepping_an_empty_world(world):
+    for _ in range(5):
+        world.step(1 / 60)
+    assert world.bodyMoveEvents == []
