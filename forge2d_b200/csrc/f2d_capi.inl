@@ -1076,18 +1076,19 @@ void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 )
 		backendStepTimes( *hw, out5 );
 }
 // What the last step did: [islandPath, activeColorCount, awakeContactCount, awakeBodyCount, maxIslandContacts,
-// maxIslandBodies, awakeIslandCount, mergeCount]
+// maxIslandBodies, awakeIslandCount, mergeCount, splitBodies, splitComponents, splitContacts, splitJoints]
 int f2dWorld_GetStepInfo( b2WorldId worldId, int* out, int cap )
 {
 	HostWorld* hw = worldFromId( worldId );
 	if ( hw == nullptr )
 		return 0;
 	const World* w = hw->img; // the header is current after every step
-	int v[8] = { w->step.islandPath,		w->step.activeColorCount, w->step.awakeContactCount, w->step.awakeBodyCount,
-				 w->step.maxIslandContacts, w->step.maxIslandBodies,  w->awakeIslands.count,	 w->step.mergeCount };
-	for ( int i = 0; i < 8 && i < cap; ++i )
+	int v[12] = { w->step.islandPath,		 w->step.activeColorCount, w->step.awakeContactCount, w->step.awakeBodyCount,
+				  w->step.maxIslandContacts, w->step.maxIslandBodies,  w->awakeIslands.count,	  w->step.mergeCount,
+				  w->step.splitBodies,		 w->step.splitComponents,  w->step.splitContacts,	  w->step.splitJoints };
+	for ( int i = 0; i < 12 && i < cap; ++i )
 		out[i] = v[i];
-	return 8;
+	return 12;
 }
 // In-kernel profile (nanoseconds per f2d::ProfSlot accumulated by rank 0 since it was enabled / last read)
 void f2dWorld_EnableProfile( b2WorldId worldId, bool flag )

@@ -102,6 +102,7 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.bullets, B, false );
 	add( w.scan, B + 8, false );
 	add( w.scratch, 2 * B + 64, false );
+	add( w.splitScratch, 14 * ( B + 8 ) + 7 * ( C + 8 ) + 7 * ( J + 8 ), false );
 }
 
 inline uint64_t alignUp( uint64_t v, uint64_t a ) { return ( v + a - 1 ) / a * a; }

@@ -780,6 +780,337 @@ template <class Team> F2D_HDF inline void islandSolve( World* w, Team& t )
 	t.sync();
 }
 
+// ------------------------------------------------------------------------------------------------ island split
+// b2SplitIsland (island.c:602-840) is a depth-first walk whose visiting order defines the new islands' ids and the
+// order of their body / contact / joint lists, so the walk itself stays serial. Everything around it is data-parallel:
+//   prepare  list-rank the island's body list (pointer doubling) to get the seed order without walking the list, and
+//            flatten every body's contact-edge and joint-edge lists into rows of (constraint id, other body position);
+//   walk     one thread runs the reference's DFS over those dense rows (marks and stack are small dense arrays, so
+//            every hop is an L1 hit instead of a pointer chase through 68..136-byte records) and only records the
+//            visiting order; it also destroys the old island and creates the new ones, in DFS order;
+//   apply    the whole team writes island ids, prev / next links, heads, tails and counts from the recorded order.
+struct SplitView
+{
+	int32_t *next[2], *dist[2]; // list ranking, by body id
+	int32_t* posOf;				// by body id: position in the island's body list
+	int32_t* bodyAt;			// by position: body id
+	int32_t *rowOff, *jrowOff;	// [n + 1] by position
+	int32_t *edges, *jedges;	// (constraint id, other) pairs
+	int32_t *contactMark, *jointMark, *bodyMark;
+	int32_t *bodyOrder, *bodyComp, *contactOrder, *contactComp, *jointOrder, *jointComp;
+	int32_t *compIsland, *stack;
+};
+
+F2D_HD SplitView splitView( World* w )
+{
+	const int B = w->bodies.cap + 8, C = w->contacts.cap + 8, J = w->joints.cap + 8;
+	int32_t* p = ptr( w, w->splitScratch );
+	SplitView v;
+	auto take = [&]( int n ) {
+		int32_t* r = p;
+		p += n;
+		return r;
+	};
+	v.next[0] = take( B );
+	v.next[1] = take( B );
+	v.dist[0] = take( B );
+	v.dist[1] = take( B );
+	v.posOf = take( B );
+	v.bodyAt = take( B );
+	v.rowOff = take( B );
+	v.jrowOff = take( B );
+	v.bodyMark = take( B );
+	v.bodyOrder = take( B );
+	v.bodyComp = take( B );
+	v.compIsland = take( B );
+	v.stack = take( B );
+	take( B );
+	v.edges = take( 4 * C );
+	v.contactMark = take( C );
+	v.contactOrder = take( C );
+	v.contactComp = take( C );
+	v.jedges = take( 4 * J );
+	v.jointMark = take( J );
+	v.jointOrder = take( J );
+	v.jointComp = take( J );
+	return v;
+}
+
+// Team-wide preparation. Leaves step.splitBodies == 0 when there is nothing to split (island.c:610-620).
+template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
+{
+	const int baseId = w->step.splitTarget;
+	if ( baseId == kNull )
+		return;
+	const Island& base = ptr( w, w->islands )[baseId];
+	if ( base.setIndex != kAwakeSet || base.constraintRemoveCount == 0 )
+		return;
+	const int n = base.bodyCount;
+	SplitView v = splitView( w );
+	Body* bodies = ptr( w, w->bodies );
+	const Contact* contacts = ptr( w, w->contacts );
+	const Joint* joints = ptr( w, w->joints );
+	const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+	const int awakeCount = w->awakeBodies.count;
+
+	// list ranking of the body list: dist = number of bodies after this one
+	for ( int i = t.rank(); i < awakeCount; i += t.size() )
+	{
+		int id = awakeBodies[i];
+		if ( bodies[id].islandId != baseId )
+			continue;
+		int nx = bodies[id].islandNext;
+		v.next[0][id] = nx;
+		v.dist[0][id] = nx != kNull ? 1 : 0;
+	}
+	t.sync();
+	int cur = 0;
+	for ( int span = 1; span < n; span <<= 1 )
+	{
+		for ( int i = t.rank(); i < awakeCount; i += t.size() )
+		{
+			int id = awakeBodies[i];
+			if ( bodies[id].islandId != baseId )
+				continue;
+			int nx = v.next[cur][id];
+			int d = v.dist[cur][id];
+			if ( nx != kNull )
+			{
+				d += v.dist[cur][nx];
+				nx = v.next[cur][nx];
+			}
+			v.next[cur ^ 1][id] = nx;
+			v.dist[cur ^ 1][id] = d;
+		}
+		t.sync();
+		cur ^= 1;
+	}
+	// rows: touching contact edges and joint edges per body, in edge-list order
+	for ( int i = t.rank(); i < awakeCount; i += t.size() )
+	{
+		int id = awakeBodies[i];
+		const Body& body = bodies[id];
+		if ( body.islandId != baseId )
+			continue;
+		int pos = n - 1 - v.dist[cur][id];
+		v.posOf[id] = pos;
+		v.bodyAt[pos] = id;
+		v.bodyMark[pos] = 0;
+		int count = 0;
+		for ( int key = body.headContactKey; key != kNull; )
+		{
+			const Contact& c = contacts[key >> 1];
+			if ( c.flags & kContactTouching )
+				count += 1;
+			key = c.edges[key & 1].nextKey;
+		}
+		v.rowOff[pos] = count;
+		int jcount = 0;
+		for ( int key = body.headJointKey; key != kNull; key = joints[key >> 1].edges[key & 1].nextKey )
+			jcount += 1;
+		v.jrowOff[pos] = jcount;
+	}
+	t.sync();
+	int edgeTotal = t.exclusiveScan( v.rowOff, n );
+	int jedgeTotal = t.exclusiveScan( v.jrowOff, n );
+	if ( 2 * edgeTotal > 4 * ( w->contacts.cap + 8 ) || 2 * jedgeTotal > 4 * ( w->joints.cap + 8 ) )
+	{
+		if ( t.rank() == 0 )
+			setError( w, kErrCapacity, __LINE__ );
+		return;
+	}
+	if ( t.rank() == 0 )
+	{
+		v.rowOff[n] = edgeTotal;
+		v.jrowOff[n] = jedgeTotal;
+	}
+	for ( int i = t.rank(); i < awakeCount; i += t.size() )
+	{
+		int id = awakeBodies[i];
+		const Body& body = bodies[id];
+		if ( body.islandId != baseId )
+			continue;
+		int pos = v.posOf[id];
+		int out = v.rowOff[pos];
+		for ( int key = body.headContactKey; key != kNull; )
+		{
+			int contactId = key >> 1;
+			int edgeIndex = key & 1;
+			const Contact& c = contacts[contactId];
+			key = c.edges[edgeIndex].nextKey;
+			if ( ( c.flags & kContactTouching ) == 0 )
+				continue;
+			int otherId = c.edges[edgeIndex ^ 1].bodyId;
+			const Body& other = bodies[otherId];
+			v.edges[2 * out] = contactId;
+			// resolved to a position by the walk; after the island merge both bodies of a touching contact are in this island
+			v.edges[2 * out + 1] = ( other.setIndex != kStaticSet && other.islandId == baseId ) ? otherId : kNull;
+			v.contactMark[contactId] = 0;
+			out += 1;
+		}
+		int jout = v.jrowOff[pos];
+		for ( int key = body.headJointKey; key != kNull; )
+		{
+			int jointId = key >> 1;
+			int edgeIndex = key & 1;
+			const Joint& j = joints[jointId];
+			key = j.edges[edgeIndex].nextKey;
+			int otherId = j.edges[edgeIndex ^ 1].bodyId;
+			const Body& other = bodies[otherId];
+			int code = other.setIndex == kDisabledSet ? -2 : ( ( other.setIndex == kAwakeSet && other.islandId == baseId ) ? otherId : kNull );
+			v.jedges[2 * jout] = jointId;
+			v.jedges[2 * jout + 1] = code;
+			v.jointMark[jointId] = 0;
+			jout += 1;
+		}
+	}
+	t.sync();
+	if ( t.rank() == 0 )
+		w->step.splitBodies = n;
+	t.sync();
+}
+
+// The serial depth-first walk (one thread). Order of everything follows island.c:669-833.
+F2D_HDF inline void splitWalk( World* w )
+{
+	const int n = w->step.splitBodies;
+	if ( n == 0 )
+		return;
+	const int baseId = w->step.splitTarget;
+	SplitView v = splitView( w );
+	destroyIsland( w, baseId );
+	int comp = 0, nb = 0, nc = 0, nj = 0;
+	for ( int seed = 0; seed < n; ++seed )
+	{
+		if ( v.bodyMark[seed] )
+			continue;
+		int sp = 0;
+		v.stack[sp++] = seed;
+		v.bodyMark[seed] = 1;
+		v.compIsland[comp] = createIsland( w, kAwakeSet );
+		while ( sp > 0 )
+		{
+			int pos = v.stack[--sp];
+			v.bodyOrder[nb] = pos;
+			v.bodyComp[nb] = comp;
+			nb += 1;
+			for ( int e = v.rowOff[pos], end = v.rowOff[pos + 1]; e < end; ++e )
+			{
+				int contactId = v.edges[2 * e];
+				if ( v.contactMark[contactId] )
+					continue;
+				v.contactMark[contactId] = 1;
+				int otherId = v.edges[2 * e + 1];
+				if ( otherId != kNull )
+				{
+					int otherPos = v.posOf[otherId];
+					if ( v.bodyMark[otherPos] == 0 )
+					{
+						v.stack[sp++] = otherPos;
+						v.bodyMark[otherPos] = 1;
+					}
+				}
+				v.contactOrder[nc] = contactId;
+				v.contactComp[nc] = comp;
+				nc += 1;
+			}
+			for ( int e = v.jrowOff[pos], end = v.jrowOff[pos + 1]; e < end; ++e )
+			{
+				int jointId = v.jedges[2 * e];
+				if ( v.jointMark[jointId] )
+					continue;
+				v.jointMark[jointId] = 1;
+				int code = v.jedges[2 * e + 1];
+				if ( code == -2 )
+					continue;
+				if ( code != kNull )
+				{
+					int otherPos = v.posOf[code];
+					if ( v.bodyMark[otherPos] == 0 )
+					{
+						v.stack[sp++] = otherPos;
+						v.bodyMark[otherPos] = 1;
+					}
+				}
+				v.jointOrder[nj] = jointId;
+				v.jointComp[nj] = comp;
+				nj += 1;
+			}
+		}
+		comp += 1;
+	}
+	w->step.splitContacts = nc;
+	w->step.splitJoints = nj;
+	w->step.splitComponents = comp;
+}
+
+// Team-wide: island ids, list links, heads, tails and counts from the recorded visiting order.
+template <class Team> F2D_HDF inline void splitApply( World* w, Team& t )
+{
+	const int n = w->step.splitBodies;
+	if ( n == 0 )
+		return;
+	SplitView v = splitView( w );
+	Island* islands = ptr( w, w->islands );
+	Body* bodies = ptr( w, w->bodies );
+	Contact* contacts = ptr( w, w->contacts );
+	Joint* joints = ptr( w, w->joints );
+	for ( int j = t.rank(); j < n; j += t.size() )
+	{
+		int k = v.bodyComp[j];
+		Island& is = islands[v.compIsland[k]];
+		int id = v.bodyAt[v.bodyOrder[j]];
+		bool first = j == 0 || v.bodyComp[j - 1] != k;
+		bool last = j == n - 1 || v.bodyComp[j + 1] != k;
+		Body& b = bodies[id];
+		b.islandId = is.islandId;
+		b.islandPrev = first ? kNull : v.bodyAt[v.bodyOrder[j - 1]];
+		b.islandNext = last ? kNull : v.bodyAt[v.bodyOrder[j + 1]];
+		if ( first )
+			is.headBody = id;
+		if ( last )
+			is.tailBody = id;
+		atomAdd( &is.bodyCount, 1 );
+	}
+	const int nc = w->step.splitContacts;
+	for ( int j = t.rank(); j < nc; j += t.size() )
+	{
+		int k = v.contactComp[j];
+		Island& is = islands[v.compIsland[k]];
+		int id = v.contactOrder[j];
+		bool first = j == 0 || v.contactComp[j - 1] != k;
+		bool last = j == nc - 1 || v.contactComp[j + 1] != k;
+		Contact& c = contacts[id];
+		c.islandId = is.islandId;
+		c.islandPrev = first ? kNull : v.contactOrder[j - 1];
+		c.islandNext = last ? kNull : v.contactOrder[j + 1];
+		if ( first )
+			is.headContact = id;
+		if ( last )
+			is.tailContact = id;
+		atomAdd( &is.contactCount, 1 );
+	}
+	const int nj = w->step.splitJoints;
+	for ( int j = t.rank(); j < nj; j += t.size() )
+	{
+		int k = v.jointComp[j];
+		Island& is = islands[v.compIsland[k]];
+		int id = v.jointOrder[j];
+		bool first = j == 0 || v.jointComp[j - 1] != k;
+		bool last = j == nj - 1 || v.jointComp[j + 1] != k;
+		Joint& jt = joints[id];
+		jt.islandId = is.islandId;
+		jt.islandPrev = first ? kNull : v.jointOrder[j - 1];
+		jt.islandNext = last ? kNull : v.jointOrder[j + 1];
+		if ( first )
+			is.headJoint = id;
+		if ( last )
+			is.tailJoint = id;
+		atomAdd( &is.jointCount, 1 );
+	}
+	t.sync();
+}
+
 // Prepare, the sub-step loop, restitution and impulse storage (solver.c:929-1106) on `t`: the whole team, or the crew
 // left over when a side worker splits an island at the same time.
 template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
@@ -1000,6 +1331,8 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	{
 		w->stepIndex += 1;
 		StepCtx& s = w->step;
+		s.splitTarget = w->splitIslandId;
+		s.splitBodies = 0;
 		s.awakeBodyCount = w->awakeBodies.count;
 		// colour bases and the active colour list (solver.c:1237-1355); overflow keeps the last base
 		int base = 0;
@@ -1041,11 +1374,12 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	if ( w->step.islandPath )
 		islandPartition( w, t );
 
-	// Island split (solver.c:1473-1485, 1700-1706): a serial depth-first walk that touches island links only, so, as in
-	// the reference, it runs concurrently with the solver stages when the team can spare a side worker for it.
+	// Island split (solver.c:1473-1485, 1700-1706). The serial depth-first walk touches island bookkeeping only, so, as
+	// in the reference, it runs concurrently with the solver stages when the team can spare a side worker for it.
+	splitPrepare( w, t );
 	bool fork = false;
 	if constexpr ( Team::kCanFork )
-		fork = w->splitIslandId != kNull && t.canFork();
+		fork = w->step.splitBodies > 0 && t.canFork();
 	if ( fork )
 	{
 		if constexpr ( Team::kCanFork )
@@ -1053,7 +1387,7 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 			if ( t.inSide() )
 			{
 				if ( t.isSideLeader() )
-					splitIsland( w, w->splitIslandId );
+					splitWalk( w );
 			}
 			else
 			{
@@ -1062,20 +1396,17 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 			}
 		}
 		t.sync();
-		// cleared only after the join: every thread decided `fork` from this field
-		if ( t.rank() == 0 )
-			w->splitIslandId = kNull;
 	}
 	else
 	{
 		if ( t.rank() == 0 )
-		{
-			if ( w->splitIslandId != kNull )
-				splitIsland( w, w->splitIslandId );
-			w->splitIslandId = kNull;
-		}
+			splitWalk( w );
 		solveStages( w, t );
+		t.sync();
 	}
+	splitApply( w, t );
+	if ( t.rank() == 0 )
+		w->splitIslandId = kNull;
 }
 
 // ------------------------------------------------------------------------------------------------ finalize

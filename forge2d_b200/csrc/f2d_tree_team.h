@@ -78,6 +78,88 @@ F2D_HD TreeScratch treeScratch( World* w )
 // An item of the rebuild: a leaf, or an internal node that was not enlarged, directly below a dissolved node.
 F2D_HD bool treeNodeIsDissolved( const TreeNode& n ) { return n.height > 0 && ( n.flags & kNodeEnlarged ) != 0; }
 
+// Serial build of one small segment [a, e) of the item array: the reference's explicit-stack top-down build
+// (dynamic_tree.c:1716-1869) with its in-place Hoare partition (treePartitionMid), recycling the dissolved node
+// freed[m-1] for the split at m, and computing boxes / heights / categories on the way back up.
+constexpr int kTreeSerialFinish = 24; // segments at most this long are finished by one thread each
+
+F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
+									   int32_t* levelOf, int a, int e, int parentKey )
+{
+	struct Item
+	{
+		int32_t node, childCount, start, split, end;
+	};
+	Item stack[kTreeSerialFinish + 2];
+	auto makeNode = [&]( int split, int parentNode ) {
+		int nodeIndex = freed[split - 1];
+		levelOf[split - 1] = 0x7fffffff; // refitted here, not by the level-synchronous pass
+		TreeNode& node = nodes[nodeIndex];
+		node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+		node.category = 1;
+		node.height = 0;
+		node.flags = kNodeAllocated;
+		node.parent = parentNode;
+		node.child1 = kNull;
+		node.child2 = kNull;
+		return nodeIndex;
+	};
+	int top = 0;
+	int split0 = a + treePartitionMid( leafIndices + a, leafCenters + a, e - a );
+	stack[0] = Item{ makeNode( split0, parentKey == kNull ? kNull : parentKey >> 1 ), -1, a, split0, e };
+	if ( parentKey == kNull )
+		tree.root = stack[0].node;
+	else if ( parentKey & 1 )
+		nodes[parentKey >> 1].child2 = stack[0].node;
+	else
+		nodes[parentKey >> 1].child1 = stack[0].node;
+	while ( true )
+	{
+		Item& item = stack[top];
+		item.childCount += 1;
+		if ( item.childCount == 2 )
+		{
+			TreeNode& node = nodes[item.node];
+			const TreeNode& c1 = nodes[node.child1];
+			const TreeNode& c2 = nodes[node.child2];
+			node.box = boxUnion( c1.box, c2.box );
+			node.height = (uint16_t)( 1 + maxU16( c1.height, c2.height ) );
+			node.category = c1.category | c2.category;
+			if ( top == 0 )
+				break;
+			top -= 1;
+			continue;
+		}
+		int start = item.childCount == 0 ? item.start : item.split;
+		int end = item.childCount == 0 ? item.split : item.end;
+		if ( end - start == 1 )
+		{
+			int leaf = leafIndices[start];
+			if ( item.childCount == 0 )
+				nodes[item.node].child1 = leaf;
+			else
+				nodes[item.node].child2 = leaf;
+			nodes[leaf].parent = item.node;
+		}
+		else
+		{
+			int split = start + treePartitionMid( leafIndices + start, leafCenters + start, end - start );
+			int child = makeNode( split, item.node );
+			if ( item.childCount == 0 )
+				nodes[item.node].child1 = child;
+			else
+				nodes[item.node].child2 = child;
+			if ( top + 1 >= kTreeSerialFinish + 2 )
+			{
+				setError( w, kErrTreeStack, __LINE__ );
+				return;
+			}
+			top += 1;
+			stack[top] = Item{ child, -1, start, split, end };
+		}
+	}
+}
+
 template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tree& tree )
 {
 	if ( tree.proxyCount == 0 || tree.root == kNull )
@@ -172,10 +254,13 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		s.segParent[0][0] = kNull;
 		s.ctrl[0] = 1; // a segment with >= 2 items exists at this level (itemCount >= 2 because the root is dissolved)
 		s.ctrl[1] = 0;
+		s.ctrl[2] = itemCount; // longest segment of this level
+		s.ctrl[3] = 0;
 	}
 	t.sync();
 	int level = 0;
-	while ( s.ctrl[level & 1] != 0 )
+	// level-synchronous while some segment is long; the short tail is finished per segment (treeFinishSegment)
+	while ( s.ctrl[level & 1] != 0 && s.ctrl[2 + ( level & 1 )] > kTreeSerialFinish )
 	{
 		const int cur = level & 1, nxt = cur ^ 1;
 		const int32_t* segEnd = s.segEnd[cur];
@@ -208,6 +293,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		{
 			s.scanLess[itemCount] = totalLess;
 			s.ctrl[nxt] = 0;
+			s.ctrl[2 + nxt] = 0;
 		}
 		t.sync();
 		// pass B: split point per segment; the k-th misplaced item of the left part (ascending) will swap with the k-th
@@ -344,15 +430,30 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 					s.segParent[nxt][m] = ( nodeIndex << 1 ) | 1;
 				}
 				if ( m - a > 1 || e - m > 1 )
+				{
 					s.ctrl[nxt] = 1;
+					atomMax32( s.ctrl + 2 + nxt, maxi( m - a, e - m ) );
+				}
 			}
 		}
 		t.sync();
 		level += 1;
 	}
-	// every position has retired under some node: hang the items
+	// short segments that are still open: one thread each builds the rest of its subtree serially
+	if ( s.ctrl[level & 1] != 0 )
+	{
+		const int cur = level & 1;
+		for ( int i = t.rank(); i < itemCount; i += t.size() )
+		{
+			if ( s.segOf[i] == i )
+				treeFinishSegment( w, tree, nodes, leafIndices, leafCenters, s.freed, s.level, i, s.segEnd[cur][i], s.segParent[cur][i] );
+		}
+	}
+	// every other position has retired under some node: hang the items
 	for ( int i = t.rank(); i < itemCount; i += t.size() )
 	{
+		if ( s.segOf[i] != kNull )
+			continue;
 		int key = s.posParent[i];
 		int item = leafIndices[i];
 		nodes[item].parent = key >> 1;

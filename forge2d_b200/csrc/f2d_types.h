@@ -446,6 +446,8 @@ struct StepCtx
 	int32_t moveCount;
 	int32_t pairCount;
 	int32_t mergeCount; // awake islands with a parent at the start of the solve
+	int32_t splitTarget; // island to split this step (copy of World::splitIslandId taken before the solve), or kNull
+	int32_t splitBodies, splitContacts, splitJoints, splitComponents; // sizes of the split work arrays
 	int32_t islandPath; // 1: constraints are solved island by island (one warp each), 0: colour by colour
 	int32_t maxIslandContacts, maxIslandBodies;
 	int32_t pad;
@@ -626,6 +628,7 @@ struct World
 	Arr<int32_t> bullets;
 	Arr<int32_t> scan;	  // scan scratch (awake bodies + 1)
 	Arr<int32_t> scratch; // island split stacks
+	Arr<int32_t> splitScratch; // island split work arrays (f2d_step.h SplitView)
 };
 
 constexpr uint64_t kWorldMagic = 0x4632444232303042ull; // "F2DB200B"

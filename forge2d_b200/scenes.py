@@ -287,6 +287,40 @@ def polygon_soup(lib, count=40, create=None, **world_kw):
     return Scene(lib, world, bodies, "polygon_soup_%d" % count)
 
 
+def jointed_piles(lib, chains=6, links=4, create=None, **world_kw):
+    """Chains of boxes linked by revolute joints dropped next to loose boxes, sleeping enabled: islands that contain
+    joints merge, lose contacts, get split (joint edges in the island DFS) and fall asleep."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = [_static_segment(lib, world, (-40.0, 0.0), (40.0, 0.0))]
+    sd = lib.b2DefaultShapeDef()
+    box = _box(lib, 0.25)
+    jd = lib.b2DefaultRevoluteJointDef()
+    for c in range(chains):
+        prev = None
+        x0 = -12.0 + 4.5 * c
+        for k in range(links):
+            bd = lib.b2DefaultBodyDef()
+            bd.type = 2
+            bd.position = A.Vec2(_f32(x0 + 0.55 * k), _f32(1.0 + 0.3 * c))
+            body = lib.b2CreateBody(world, C.byref(bd))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+            bodies.append(body)
+            if prev is not None:
+                jd.bodyIdA, jd.bodyIdB = prev, body
+                jd.localAnchorA = A.Vec2(0.275, 0.0)
+                jd.localAnchorB = A.Vec2(-0.275, 0.0)
+                lib.b2CreateRevoluteJoint(world, C.byref(jd))
+            prev = body
+        for k in range(3):
+            bd = lib.b2DefaultBodyDef()
+            bd.type = 2
+            bd.position = A.Vec2(_f32(x0 + 0.4 * k), _f32(2.5 + 0.7 * k))
+            body = lib.b2CreateBody(world, C.byref(bd))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+            bodies.append(body)
+    return Scene(lib, world, bodies, "jointed_piles_%d" % chains)
+
+
 SCENES = {
     "bench2d": bench2d,
     "large_pyramid": large_pyramid,
@@ -294,4 +328,5 @@ SCENES = {
     "joint_grid": joint_grid,
     "falling_shapes": falling_shapes,
     "polygon_soup": polygon_soup,
+    "jointed_piles": jointed_piles,
 }

@@ -271,7 +271,7 @@ F2D_API long long f2dWorld_GetKernelLaunchCount( void ); ///< kernels launched b
 F2D_API void f2dWorld_GetLastStepTimes( b2WorldId worldId, float* out5 );
 F2D_API void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag );
 /// What the last step did: [islandPath, activeColours, awakeContacts, awakeBodies, maxIslandContacts, maxIslandBodies,
-/// awakeIslands, mergedIslands]
+/// awakeIslands, mergedIslands, splitBodies, splitComponents, splitContacts, splitJoints]
 F2D_API int f2dWorld_GetStepInfo( b2WorldId worldId, int* out, int cap );
 /// In-kernel phase profile: ns per sub-phase (f2d::ProfSlot order) accumulated on the device since enabled
 F2D_API void f2dWorld_EnableProfile( b2WorldId worldId, bool flag );

@@ -15,7 +15,8 @@ CASES = [
     ("many_pyramids", dict(grid=3, base=6), 120, 6),  # islands fall asleep (~frame 35) and stay asleep
     ("joint_grid", dict(n=12, rain_every=4), 120, 6),  # revolute joints + rain of mixed shapes
     ("large_pyramid", dict(rows=30), 60, 10),
-    ("polygon_soup", dict(count=40), 220, 5),       # 3..8-gons, rounded polygons, capsules, circles on sloped segments
+    ("polygon_soup", dict(count=40), 220, 5),
+    ("jointed_piles", dict(chains=6), 300, 5),      # islands with joints: merge, split (joint edges), sleep       # 3..8-gons, rounded polygons, capsules, circles on sloped segments
 ]
 
 

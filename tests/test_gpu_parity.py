@@ -53,6 +53,11 @@ def test_polygon_soup_eight_vertex_path(ref, gpu, mode):
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_jointed_piles_split_with_joint_edges(ref, gpu, mode):
+    _lockstep(ref, gpu, "jointed_piles", dict(chains=6), 300, 3, mode)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_many_pyramids_sleep(ref, gpu, mode):
     _lockstep(ref, gpu, "many_pyramids", dict(grid=3, base=6), 120, 3, mode)
 
