@@ -37,6 +37,9 @@ struct CtaTeam
 	__device__ bool canFork() const { return blockDim.x >= 64; }
 	__device__ bool inSide() const { return threadIdx.x >= blockDim.x - 32; }
 	__device__ bool isSideLeader() const { return threadIdx.x == blockDim.x - 32; }
+	typedef WarpLanes Lanes;
+	__device__ bool inSideGroup() const { return threadIdx.x >= blockDim.x - 32; }
+	__device__ bool inFirstGroup() const { return threadIdx.x < 32; }
 	__device__ CtaCrew crew() const { return CtaCrew{ (int)blockDim.x - 32 }; }
 	__device__ int groupCount() const { return (int)( blockDim.x >> 5 ); }
 	__device__ int groupIndex() const { return (int)( threadIdx.x >> 5 ); }
@@ -152,6 +155,9 @@ struct GridTeam
 	__device__ bool canFork() const { return gridDim.x >= 2; }
 	__device__ bool inSide() const { return blockIdx.x == gridDim.x - 1; }
 	__device__ bool isSideLeader() const { return blockIdx.x == gridDim.x - 1 && threadIdx.x == 0; }
+	typedef WarpLanes Lanes;
+	__device__ bool inSideGroup() const { return blockIdx.x == gridDim.x - 1 && threadIdx.x < 32; }
+	__device__ bool inFirstGroup() const { return blockIdx.x == 0 && threadIdx.x < 32; }
 	__device__ GridCrew crew() { return GridCrew{ barrier + 1, &crewGen }; }
 	__device__ int groupCount() const { return (int)( ( gridDim.x * blockDim.x ) >> 5 ); }
 	__device__ int groupIndex() const { return (int)( ( blockIdx.x * blockDim.x + threadIdx.x ) >> 5 ); }

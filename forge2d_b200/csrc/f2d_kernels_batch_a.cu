@@ -1,4 +1,4 @@
-// forge2d_b200 — batch kernels (one thread block per world), configurations 256x2, 128x4.
+// forge2d_b200 — batch kernels (one thread block per world), configurations 256x2, 256x4.
 // Separate translation unit so the variants compile in parallel.
 #include "f2d_kernels.cuh"
 
@@ -12,9 +12,9 @@ bool launchBatchStepA( int threads, int blocksPerSM, char* base, unsigned long l
 		stepWorldsCta<256, 2><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
 		return true;
 	}
-	if ( threads == 128 && blocksPerSM == 4 )
+	if ( threads == 256 && blocksPerSM == 4 )
 	{
-		stepWorldsCta<128, 4><<<worldCount, 128, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
+		stepWorldsCta<256, 4><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
 		return true;
 	}
 	return false;

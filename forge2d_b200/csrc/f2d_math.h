@@ -22,6 +22,16 @@
 namespace f2d
 {
 
+// Non-binding hint: start fetching the 128-byte line that holds `p` (device only)
+F2D_HD void prefetchLine( const void* p )
+{
+#if defined( __CUDA_ARCH__ )
+	asm volatile( "prefetch.global.L1 [%0];" ::"l"( p ) );
+#else
+	(void)p;
+#endif
+}
+
 constexpr float kPi = 3.14159265359f;		  // math_functions.h:79
 constexpr float kLinearSlop = 0.005f;		  // constants.h:21 (lengthUnitsPerMeter == 1, forge2d never changes it)
 constexpr float kSpeculative = 4.0f * 0.005f; // constants.h:34

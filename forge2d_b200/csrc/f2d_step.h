@@ -269,49 +269,76 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 }
 
 // ------------------------------------------------------------------------------------------------ collide
-// world.c:357-445, one contact
+// world.c:357-445, one contact. The gather is written as two rounds of independent loads (ids and old impulses
+// from the contact record; then shapes, bodies and body sims all at once) because the phase is bound by the
+// latency of dependent loads, not by arithmetic.
 F2D_HDF inline void collideContact( World* w, int contactId )
 {
 	ContactSim& sim = ptr( w, w->contactSims )[contactId];
 	const Shape* shapes = ptr( w, w->shapes );
-	const Shape& shapeA = shapes[sim.shapeIdA];
-	const Shape& shapeB = shapes[sim.shapeIdB];
+	const Body* bodies = ptr( w, w->bodies );
+	const BodySim* sims = ptr( w, w->sims );
 	uint64_t* bits = ptr( w, w->contactBits );
-	bool overlap = boxOverlaps( shapeA.fatAABB, shapeB.fatAABB );
+	// ---- round 1: the contact record
+	const int shapeIdA = sim.shapeIdA, shapeIdB = sim.shapeIdB;
+	const int bodyIdA = sim.bodyIdA, bodyIdB = sim.bodyIdB;
+	uint32_t simFlags = sim.simFlags;
+	OldImpulses old;
+	old.pointCount = sim.manifold.pointCount;
+	old.rollingImpulse = sim.manifold.rollingImpulse;
+	old.id[0] = sim.manifold.points[0].id;
+	old.id[1] = sim.manifold.points[1].id;
+	old.normalImpulse[0] = sim.manifold.points[0].normalImpulse;
+	old.normalImpulse[1] = sim.manifold.points[1].normalImpulse;
+	old.tangentImpulse[0] = sim.manifold.points[0].tangentImpulse;
+	old.tangentImpulse[1] = sim.manifold.points[1].tangentImpulse;
+	// ---- round 2: everything the ids lead to
+	const Shape& shapeA = shapes[shapeIdA];
+	const Shape& shapeB = shapes[shapeIdB];
+	const Body& bodyA = bodies[bodyIdA];
+	const Body& bodyB = bodies[bodyIdB];
+	const BodySim& simA = sims[bodyIdA];
+	const BodySim& simB = sims[bodyIdB];
+	const Box fatA = shapeA.fatAABB, fatB = shapeB.fatAABB;
+	const int setA = bodyA.setIndex, localA = bodyA.localIndex;
+	const int setB = bodyB.setIndex, localB = bodyB.localIndex;
+	const Xf xfA = simA.transform, xfB = simB.transform;
+	const V2 localCenterA = simA.localCenter, localCenterB = simB.localCenter;
+	const float invMassA = simA.invMass, invIA = simA.invInertia;
+	const float invMassB = simB.invMass, invIB = simB.invInertia;
+	prefetchLine( &shapeA.polygon );
+	prefetchLine( &shapeA.polygon.n[0] );
+	prefetchLine( &shapeB.polygon );
+	prefetchLine( &shapeB.polygon.n[0] );
+
+	bool overlap = boxOverlaps( fatA, fatB );
 	if ( overlap == false )
 	{
-		sim.simFlags |= kSimDisjoint;
-		sim.simFlags &= ~kSimTouching;
+		sim.simFlags = ( simFlags | kSimDisjoint ) & ~kSimTouching;
 		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
 		return;
 	}
-	bool wasTouching = ( sim.simFlags & kSimTouching ) != 0;
-	const Body* bodies = ptr( w, w->bodies );
-	const BodySim* sims = ptr( w, w->sims );
-	const Body& bodyA = bodies[shapeA.bodyId];
-	const Body& bodyB = bodies[shapeB.bodyId];
-	const BodySim& simA = sims[shapeA.bodyId];
-	const BodySim& simB = sims[shapeB.bodyId];
-	sim.bodySimIndexA = bodyA.setIndex == kAwakeSet ? bodyA.localIndex : kNull;
-	sim.invMassA = simA.invMass;
-	sim.invIA = simA.invInertia;
-	sim.bodySimIndexB = bodyB.setIndex == kAwakeSet ? bodyB.localIndex : kNull;
-	sim.invMassB = simB.invMass;
-	sim.invIB = simB.invInertia;
-	Xf xfA = simA.transform, xfB = simB.transform;
-	V2 centerOffsetA = rotate( xfA.q, simA.localCenter );
-	V2 centerOffsetB = rotate( xfB.q, simB.localCenter );
-	bool touching = updateContact( w, sim, shapeA, xfA, centerOffsetA, shapeB, xfB, centerOffsetB );
+	bool wasTouching = ( simFlags & kSimTouching ) != 0;
+	sim.bodySimIndexA = setA == kAwakeSet ? localA : kNull;
+	sim.invMassA = invMassA;
+	sim.invIA = invIA;
+	sim.bodySimIndexB = setB == kAwakeSet ? localB : kNull;
+	sim.invMassB = invMassB;
+	sim.invIB = invIB;
+	V2 centerOffsetA = rotate( xfA.q, localCenterA );
+	V2 centerOffsetB = rotate( xfB.q, localCenterB );
+	bool touching = updateContact( w, sim, simFlags, old, shapeA, xfA, centerOffsetA, shapeB, xfB, centerOffsetB );
 	if ( touching == true && wasTouching == false )
 	{
-		sim.simFlags |= kSimStartedTouching;
+		simFlags |= kSimStartedTouching;
 		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
 	}
 	else if ( touching == false && wasTouching == true )
 	{
-		sim.simFlags |= kSimStoppedTouching;
+		simFlags |= kSimStoppedTouching;
 		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
 	}
+	sim.simFlags = simFlags;
 }
 
 // One contact of the ordered contact-state pass (world.c:595-684)
@@ -433,16 +460,9 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 {
 	// work list = colour 0..11 lists then the awake non-touching list (world.c:504-542)
-	int segBase[kColorCount + 2];
-	int total = 0;
+	int total = w->awakeContacts.count;
 	for ( int i = 0; i < kColorCount; ++i )
-	{
-		segBase[i] = total;
 		total += w->colorContacts[i].count;
-	}
-	segBase[kColorCount] = total;
-	total += w->awakeContacts.count;
-	segBase[kColorCount + 1] = total;
 
 	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492). The reference overlaps it with
 	// the narrowphase on another worker; here the whole team does one after the other, each fully data-parallel
@@ -451,14 +471,22 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 	treeRebuildTeam( w, t, w->trees[kKinematicBody] );
 	t.sync();
 	F2D_MARK( w, t, pfTreeRebuild );
-	for ( int i = t.rank(); i < total; i += t.size() )
 	{
-		int seg = 0;
-		while ( i >= segBase[seg + 1] )
-			seg += 1;
-		const Arr<int32_t>& list = seg < kColorCount ? w->colorContacts[seg] : w->awakeContacts;
-		int contactId = ptr( w, list )[i - segBase[seg]];
-		collideContact( w, contactId );
+		// a thread's indices only grow, so the list segment is tracked with a forward cursor (no per-thread table)
+		int seg = -1, segStart = 0, segEnd = 0;
+		const int32_t* list = nullptr;
+		for ( int i = t.rank(); i < total; i += t.size() )
+		{
+			while ( i >= segEnd )
+			{
+				seg += 1;
+				segStart = segEnd;
+				const Arr<int32_t>& a = seg < kColorCount ? w->colorContacts[seg] : w->awakeContacts;
+				segEnd += a.count;
+				list = ptr( w, a );
+			}
+			collideContact( w, list[i - segStart] );
+		}
 	}
 	t.sync();
 	F2D_MARK( w, t, pfNarrow );
@@ -852,16 +880,22 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	const Joint* joints = ptr( w, w->joints );
 	const int32_t* awakeBodies = ptr( w, w->awakeBodies );
 	const int awakeCount = w->awakeBodies.count;
+	constexpr int kNotMember = -2;
 
-	// list ranking of the body list: dist = number of bodies after this one
+	// List ranking of the body list (dist = number of bodies after this one) by pointer doubling on dense arrays
+	// indexed by AWAKE INDEX: the body records are chased once, here, and never again during the rounds.
 	for ( int i = t.rank(); i < awakeCount; i += t.size() )
 	{
-		int id = awakeBodies[i];
-		if ( bodies[id].islandId != baseId )
+		const Body& b = bodies[awakeBodies[i]];
+		if ( b.islandId != baseId )
+		{
+			v.next[0][i] = kNotMember;
+			v.next[1][i] = kNotMember;
 			continue;
-		int nx = bodies[id].islandNext;
-		v.next[0][id] = nx;
-		v.dist[0][id] = nx != kNull ? 1 : 0;
+		}
+		int nx = b.islandNext;
+		v.next[0][i] = nx != kNull ? bodies[nx].localIndex : kNull; // island mates are awake: localIndex = awake index
+		v.dist[0][i] = nx != kNull ? 1 : 0;
 	}
 	t.sync();
 	int cur = 0;
@@ -869,18 +903,17 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	{
 		for ( int i = t.rank(); i < awakeCount; i += t.size() )
 		{
-			int id = awakeBodies[i];
-			if ( bodies[id].islandId != baseId )
+			int nx = v.next[cur][i];
+			if ( nx == kNotMember )
 				continue;
-			int nx = v.next[cur][id];
-			int d = v.dist[cur][id];
+			int d = v.dist[cur][i];
 			if ( nx != kNull )
 			{
 				d += v.dist[cur][nx];
 				nx = v.next[cur][nx];
 			}
-			v.next[cur ^ 1][id] = nx;
-			v.dist[cur ^ 1][id] = d;
+			v.next[cur ^ 1][i] = nx;
+			v.dist[cur ^ 1][i] = d;
 		}
 		t.sync();
 		cur ^= 1;
@@ -888,11 +921,11 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	// rows: touching contact edges and joint edges per body, in edge-list order
 	for ( int i = t.rank(); i < awakeCount; i += t.size() )
 	{
+		if ( v.next[cur][i] == kNotMember )
+			continue;
 		int id = awakeBodies[i];
 		const Body& body = bodies[id];
-		if ( body.islandId != baseId )
-			continue;
-		int pos = n - 1 - v.dist[cur][id];
+		int pos = n - 1 - v.dist[cur][i];
 		v.posOf[id] = pos;
 		v.bodyAt[pos] = id;
 		v.bodyMark[pos] = 0;
@@ -926,10 +959,10 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	}
 	for ( int i = t.rank(); i < awakeCount; i += t.size() )
 	{
+		if ( v.next[cur][i] == kNotMember )
+			continue;
 		int id = awakeBodies[i];
 		const Body& body = bodies[id];
-		if ( body.islandId != baseId )
-			continue;
 		int pos = v.posOf[id];
 		int out = v.rowOff[pos];
 		for ( int key = body.headContactKey; key != kNull; )
@@ -943,8 +976,9 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 			int otherId = c.edges[edgeIndex ^ 1].bodyId;
 			const Body& other = bodies[otherId];
 			v.edges[2 * out] = contactId;
-			// resolved to a position by the walk; after the island merge both bodies of a touching contact are in this island
-			v.edges[2 * out + 1] = ( other.setIndex != kStaticSet && other.islandId == baseId ) ? otherId : kNull;
+			// the other body as a POSITION in the island's body list (posOf of every member was written before the scans);
+			// after the island merge both bodies of a touching contact are in this island unless one is static
+			v.edges[2 * out + 1] = ( other.setIndex != kStaticSet && other.islandId == baseId ) ? v.posOf[otherId] : kNull;
 			v.contactMark[contactId] = 0;
 			out += 1;
 		}
@@ -957,7 +991,7 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 			key = j.edges[edgeIndex].nextKey;
 			int otherId = j.edges[edgeIndex ^ 1].bodyId;
 			const Body& other = bodies[otherId];
-			int code = other.setIndex == kDisabledSet ? -2 : ( ( other.setIndex == kAwakeSet && other.islandId == baseId ) ? otherId : kNull );
+			int code = other.setIndex == kDisabledSet ? -2 : ( ( other.setIndex == kAwakeSet && other.islandId == baseId ) ? v.posOf[otherId] : kNull );
 			v.jedges[2 * jout] = jointId;
 			v.jedges[2 * jout + 1] = code;
 			v.jointMark[jointId] = 0;
@@ -970,78 +1004,119 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	t.sync();
 }
 
-// The serial depth-first walk (one thread). Order of everything follows island.c:669-833.
-F2D_HDF inline void splitWalk( World* w )
+F2D_HD int popCount32( uint32_t x )
+{
+	int n = 0;
+	while ( x != 0 )
+	{
+		x &= x - 1;
+		n += 1;
+	}
+	return n;
+}
+F2D_HD int lowestBit32( uint32_t x )
+{
+	int n = 0;
+	while ( ( x & 1u ) == 0 )
+	{
+		x >>= 1;
+		n += 1;
+	}
+	return n;
+}
+
+// The depth-first walk. Order of everything follows island.c:669-833: the visiting order is serial by nature (it
+// defines the new islands' ids and list orders), but the edges of ONE popped body are independent tests against the
+// marks, so the lanes of a warp take one edge each: an edge is new iff its constraint is unmarked (ballot -> ranks
+// give the order slots), and among the new edges the first one (lowest lane) that leads to an unmarked body pushes it.
+// Every lane keeps the same counters; lane 0 performs the island pool edits.
+template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 {
 	const int n = w->step.splitBodies;
 	if ( n == 0 )
 		return;
 	const int baseId = w->step.splitTarget;
 	SplitView v = splitView( w );
-	destroyIsland( w, baseId );
+	const int lane = L.lane();
+	const uint32_t below = lane == 0 ? 0u : ( 0xffffffffu >> ( 32 - lane ) );
+	if ( lane == 0 )
+		destroyIsland( w, baseId );
 	int comp = 0, nb = 0, nc = 0, nj = 0;
 	for ( int seed = 0; seed < n; ++seed )
 	{
 		if ( v.bodyMark[seed] )
 			continue;
-		int sp = 0;
-		v.stack[sp++] = seed;
-		v.bodyMark[seed] = 1;
-		v.compIsland[comp] = createIsland( w, kAwakeSet );
+		if ( lane == 0 )
+		{
+			v.stack[0] = seed;
+			v.bodyMark[seed] = 1;
+			v.compIsland[comp] = createIsland( w, kAwakeSet );
+		}
+		int sp = 1;
+		L.sync();
 		while ( sp > 0 )
 		{
 			int pos = v.stack[--sp];
-			v.bodyOrder[nb] = pos;
-			v.bodyComp[nb] = comp;
-			nb += 1;
-			for ( int e = v.rowOff[pos], end = v.rowOff[pos + 1]; e < end; ++e )
+			if ( lane == 0 )
 			{
-				int contactId = v.edges[2 * e];
-				if ( v.contactMark[contactId] )
-					continue;
-				v.contactMark[contactId] = 1;
-				int otherId = v.edges[2 * e + 1];
-				if ( otherId != kNull )
-				{
-					int otherPos = v.posOf[otherId];
-					if ( v.bodyMark[otherPos] == 0 )
-					{
-						v.stack[sp++] = otherPos;
-						v.bodyMark[otherPos] = 1;
-					}
-				}
-				v.contactOrder[nc] = contactId;
-				v.contactComp[nc] = comp;
-				nc += 1;
+				v.bodyOrder[nb] = pos;
+				v.bodyComp[nb] = comp;
 			}
-			for ( int e = v.jrowOff[pos], end = v.jrowOff[pos + 1]; e < end; ++e )
+			nb += 1;
+			for ( int pass = 0; pass < 2; ++pass )
 			{
-				int jointId = v.jedges[2 * e];
-				if ( v.jointMark[jointId] )
-					continue;
-				v.jointMark[jointId] = 1;
-				int code = v.jedges[2 * e + 1];
-				if ( code == -2 )
-					continue;
-				if ( code != kNull )
+				// pass 0: contact edges, pass 1: joint edges (island.c:700-767 then :769-812)
+				const int32_t* rowOff = pass == 0 ? v.rowOff : v.jrowOff;
+				const int32_t* rows = pass == 0 ? v.edges : v.jedges;
+				int32_t* mark = pass == 0 ? v.contactMark : v.jointMark;
+				int32_t* order = pass == 0 ? v.contactOrder : v.jointOrder;
+				int32_t* orderComp = pass == 0 ? v.contactComp : v.jointComp;
+				int& filled = pass == 0 ? nc : nj;
+				const int end = rowOff[pos + 1];
+				for ( int chunk = rowOff[pos]; chunk < end; chunk += L.count() )
 				{
-					int otherPos = v.posOf[code];
-					if ( v.bodyMark[otherPos] == 0 )
+					const int e = chunk + lane;
+					const bool live = e < end;
+					const int id = live ? rows[2 * e] : 0;
+					const int other = live ? rows[2 * e + 1] : kNull;
+					bool fresh = live && mark[id] == 0;
+					// a constraint listed twice in one row (both ends on this body) counts once, at its first edge
+					uint32_t same = L.matchAny( fresh ? id : -2 - lane );
+					fresh = fresh && lowestBit32( same ) == lane;
+					if ( fresh )
+						mark[id] = 1;
+					// joints to a disabled body are marked but neither recorded nor followed (island.c:785-789)
+					const bool recorded = fresh && other != -2;
+					const uint32_t recordedMask = L.ballot( recorded );
+					if ( recorded )
 					{
-						v.stack[sp++] = otherPos;
-						v.bodyMark[otherPos] = 1;
+						int slot = filled + popCount32( recordedMask & below );
+						order[slot] = id;
+						orderComp[slot] = comp;
 					}
+					filled += popCount32( recordedMask );
+					const bool reach = recorded && other != kNull && v.bodyMark[other] == 0;
+					uint32_t peers = L.matchAny( reach ? other : -2 - lane );
+					const bool pusher = reach && lowestBit32( peers ) == lane;
+					const uint32_t pushMask = L.ballot( pusher );
+					if ( pusher )
+					{
+						v.stack[sp + popCount32( pushMask & below )] = other;
+						v.bodyMark[other] = 1;
+					}
+					sp += popCount32( pushMask );
+					L.sync();
 				}
-				v.jointOrder[nj] = jointId;
-				v.jointComp[nj] = comp;
-				nj += 1;
 			}
 		}
 		comp += 1;
 	}
-	w->step.splitContacts = nc;
-	w->step.splitJoints = nj;
-	w->step.splitComponents = comp;
+	if ( lane == 0 )
+	{
+		w->step.splitContacts = nc;
+		w->step.splitJoints = nj;
+		w->step.splitComponents = comp;
+	}
 }
 
 // Team-wide: island ids, list links, heads, tails and counts from the recorded visiting order.
@@ -1130,13 +1205,18 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 		const BodyState* states = ptr( w, w->states );
 		float warmStartScale = w->enableWarmStarting ? 1.0f : 0.0f;
 		int total = w->step.awakeContactCount;
+		int color = -1, colorStart = 0, colorEnd = 0;
+		const int32_t* list = nullptr;
 		for ( int slot = t.rank(); slot < total; slot += t.size() )
 		{
-			int color = 0;
-			while ( slot >= w->step.colorBase[color + 1] )
+			while ( slot >= colorEnd )
+			{
 				color += 1;
-			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
-			prepareContactSlot( w, c, slot, contactId, states, warmStartScale );
+				colorStart = colorEnd;
+				colorEnd = w->step.colorBase[color + 1];
+				list = ptr( w, w->colorContacts[color] );
+			}
+			prepareContactSlot( w, c, slot, list[slot - colorStart], states, warmStartScale );
 		}
 	}
 	t.sync();
@@ -1182,13 +1262,18 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 		const ConView c = conView( w );
 		int total = w->step.awakeContactCount;
 		int overflowBase = w->step.colorBase[kOverflow];
+		int color = -1, colorStart = 0, colorEnd = 0;
+		const int32_t* list = nullptr;
 		for ( int slot = t.rank(); slot < total; slot += t.size() )
 		{
-			int color = 0;
-			while ( slot >= w->step.colorBase[color + 1] )
+			while ( slot >= colorEnd )
+			{
 				color += 1;
-			int contactId = ptr( w, w->colorContacts[color] )[slot - w->step.colorBase[color]];
-			storeSlot( w, c, slot, contactId, slot >= overflowBase );
+				colorStart = colorEnd;
+				colorEnd = w->step.colorBase[color + 1];
+				list = ptr( w, w->colorContacts[color] );
+			}
+			storeSlot( w, c, slot, list[slot - colorStart], slot >= overflowBase );
 		}
 	}
 	t.sync();
@@ -1386,8 +1471,8 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 		{
 			if ( t.inSide() )
 			{
-				if ( t.isSideLeader() )
-					splitWalk( w );
+				if ( t.inSideGroup() )
+					splitWalk( w, typename Team::Lanes{} );
 			}
 			else
 			{
@@ -1399,8 +1484,8 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	}
 	else
 	{
-		if ( t.rank() == 0 )
-			splitWalk( w );
+		if ( t.inFirstGroup() )
+			splitWalk( w, typename Team::Lanes{} );
 		solveStages( w, t );
 		t.sync();
 	}
@@ -1601,6 +1686,16 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 	int bodyId = ptr( w, w->awakeBodies )[simIndex];
 	BodySim& sim = ptr( w, w->sims )[bodyId];
 	Body& body = ptr( w, w->bodies )[bodyId];
+	{
+		// the island and the first shape are needed at the end of this routine: start fetching them now, so that the
+		// body -> island and body -> shape hops overlap with the arithmetic instead of following it
+		const int islandId = body.islandId, headShapeId = body.headShapeId;
+		prefetchLine( ptr( w, w->islands ) + islandId );
+		const char* shapeBytes = reinterpret_cast<const char*>( ptr( w, w->shapes ) + headShapeId );
+		prefetchLine( shapeBytes );
+		prefetchLine( shapeBytes + 128 );
+		prefetchLine( shapeBytes + 256 );
+	}
 	const float timeStep = w->step.dt;
 	const float invTimeStep = w->step.inv_dt;
 

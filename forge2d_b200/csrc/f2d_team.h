@@ -88,8 +88,32 @@ F2D_HD uint64_t profClock() { return 0; }
 		}                                                                                                                      \
 	} while ( 0 )
 
+// The lanes that walk a graph together (island split): one host thread, or the 32 lanes of a warp.
+struct SoloLanes
+{
+	F2D_HD int lane() const { return 0; }
+	F2D_HD int count() const { return 1; }
+	F2D_HD uint32_t ballot( bool p ) const { return p ? 1u : 0u; }
+	F2D_HD uint32_t matchAny( int ) const { return 1u; }
+	F2D_HD void sync() const {}
+};
+#if defined( __CUDA_ARCH__ )
+struct WarpLanes
+{
+	F2D_HD int lane() const { return (int)( threadIdx.x & 31 ); }
+	F2D_HD int count() const { return 32; }
+	F2D_HD uint32_t ballot( bool p ) const { return __ballot_sync( 0xffffffffu, p ); }
+	F2D_HD uint32_t matchAny( int key ) const { return __match_any_sync( 0xffffffffu, key ); }
+	F2D_HD void sync() const { __syncwarp(); }
+};
+#else
+typedef SoloLanes WarpLanes;
+#endif
+
 struct SerialTeam
 {
+	typedef SoloLanes Lanes;
+	F2D_HD bool inFirstGroup() const { return true; }
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = false;
 	F2D_HD int rank() const { return 0; }

@@ -258,6 +258,8 @@ struct ContactSim
 	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
 	int32_t shapeIdA, shapeIdB;
 	float invMassA, invIA, invMassB, invIB;
+	int32_t bodyIdA, bodyIdB; // owners of the two shapes (ours: saves the shape -> body hop of the narrowphase gather)
+	int32_t pad0, pad1;
 	Manifold manifold;
 	float friction, restitution, rollingResistance, tangentSpeed;
 	uint32_t simFlags;

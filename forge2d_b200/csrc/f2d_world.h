@@ -1038,6 +1038,10 @@ F2D_HDF inline int createContact( World* w, int shapeIdA, int shapeIdB )
 	sim.invIB = 0.0f;
 	sim.shapeIdA = shapeIdA;
 	sim.shapeIdB = shapeIdB;
+	sim.bodyIdA = shapeA.bodyId;
+	sim.bodyIdB = shapeB.bodyId;
+	sim.pad0 = 0;
+	sim.pad1 = 0;
 	memset( &sim.cache, 0, sizeof( sim.cache ) );
 	memset( &sim.manifold, 0, sizeof( sim.manifold ) );
 	sim.friction = sqrtf( shapeA.friction * shapeB.friction );			  // world.c:88-92 default mixing
@@ -1117,13 +1121,22 @@ F2D_HDF inline void destroyContact( World* w, int contactId, bool wakeBodies )
 	}
 }
 
-// Narrowphase update of one contact: contact.c:472-633 (pre-solve callback path excluded: host callbacks are
-// rejected at registration on the device path).
-F2D_HDF inline bool updateContact( World* w, ContactSim& sim, const Shape& shapeA, Xf xfA, V2 centerOffsetA, const Shape& shapeB,
-								   Xf xfB, V2 centerOffsetB )
+// What the narrowphase keeps of the previous manifold: feature ids and accumulated impulses (contact.c:552-586)
+struct OldImpulses
 {
-	Manifold old = sim.manifold;
-	sim.manifold = computeManifold( w, shapeA, xfA, shapeB, xfB, &sim.cache );
+	int32_t pointCount;
+	float rollingImpulse;
+	uint16_t id[2];
+	float normalImpulse[2], tangentImpulse[2];
+};
+
+// Narrowphase update of one contact: contact.c:472-633 (pre-solve callback path excluded: host callbacks are
+// rejected at registration on the device path). `old` was read together with the ids of the contact, so this
+// routine issues no load that depends on another one.
+F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags, OldImpulses old, const Shape& shapeA, Xf xfA,
+								   V2 centerOffsetA, const Shape& shapeB, Xf xfB, V2 centerOffsetB )
+{
+	Manifold m = computeManifold( w, shapeA, xfA, shapeB, xfB, &sim.cache );
 
 	sim.friction = sqrtf( shapeA.friction * shapeB.friction );
 	sim.restitution = maxf( shapeA.restitution, shapeB.restitution );
@@ -1138,34 +1151,37 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, const Shape& shape
 	}
 	sim.tangentSpeed = shapeA.tangentSpeed + shapeB.tangentSpeed;
 
-	int pointCount = sim.manifold.pointCount;
+	int pointCount = m.pointCount;
 	bool touching = pointCount > 0;
 
 	if ( w->enableSpeculative == false && pointCount == 2 )
 	{
-		if ( sim.manifold.points[0].separation > 1.5f * kLinearSlop )
+		if ( m.points[0].separation > 1.5f * kLinearSlop )
 		{
-			sim.manifold.points[0] = sim.manifold.points[1];
-			sim.manifold.pointCount = 1;
+			m.points[0] = m.points[1];
+			m.pointCount = 1;
 		}
-		else if ( sim.manifold.points[0].separation > 1.5f * kLinearSlop )
+		else if ( m.points[0].separation > 1.5f * kLinearSlop )
 		{
-			sim.manifold.pointCount = 1;
+			m.pointCount = 1;
 		}
-		pointCount = sim.manifold.pointCount;
+		pointCount = m.pointCount;
 	}
 
 	if ( touching && ( shapeA.enableHitEvents || shapeB.enableHitEvents ) )
-		sim.simFlags |= kSimEnableHitEvent;
+		simFlags |= kSimEnableHitEvent;
 	else
-		sim.simFlags &= ~kSimEnableHitEvent;
+		simFlags &= ~kSimEnableHitEvent;
 
 	if ( pointCount > 0 )
-		sim.manifold.rollingImpulse = old.rollingImpulse;
+		m.rollingImpulse = old.rollingImpulse;
 
-	for ( int i = 0; i < pointCount; ++i )
+#pragma unroll
+	for ( int i = 0; i < 2; ++i )
 	{
-		ManifoldPoint& mp2 = sim.manifold.points[i];
+		if ( i >= pointCount )
+			break;
+		ManifoldPoint& mp2 = m.points[i];
 		mp2.anchorA = sub( mp2.anchorA, centerOffsetA );
 		mp2.anchorB = sub( mp2.anchorB, centerOffsetB );
 		mp2.normalImpulse = 0.0f;
@@ -1174,26 +1190,27 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, const Shape& shape
 		mp2.normalVelocity = 0.0f;
 		mp2.persisted = false;
 		uint16_t id2 = mp2.id;
-		for ( int j = 0; j < old.pointCount; ++j )
+#pragma unroll
+		for ( int j = 0; j < 2; ++j )
 		{
-			ManifoldPoint& mp1 = old.points[j];
-			if ( mp1.id == id2 )
+			if ( j < old.pointCount && old.id[j] == id2 )
 			{
-				mp2.normalImpulse = mp1.normalImpulse;
-				mp2.tangentImpulse = mp1.tangentImpulse;
+				mp2.normalImpulse = old.normalImpulse[j];
+				mp2.tangentImpulse = old.tangentImpulse[j];
 				mp2.persisted = true;
-				mp1.normalImpulse = 0.0f;
-				mp1.tangentImpulse = 0.0f;
+				old.normalImpulse[j] = 0.0f;
+				old.tangentImpulse[j] = 0.0f;
 				break;
 			}
 		}
 	}
+	sim.manifold = m;
 
 	if ( touching )
-		sim.simFlags |= kSimTouching;
+		simFlags |= kSimTouching;
 	else
-		sim.simFlags &= ~kSimTouching;
-	return touching;
+		simFlags &= ~kSimTouching;
+	return touching; // the caller stores simFlags once, after adding the transition bits
 }
 
 // ------------------------------------------------------------------------------------------------ sleeping sets
