@@ -406,8 +406,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=8192, help="total worlds of the batch (sharded across ranks)")
     ap.add_argument("--e2e-steps", type=int, default=8)
-    ap.add_argument("--batch-threads", type=int, default=64, help="threads per world of the batch kernel")
-    ap.add_argument("--batch-blocks-per-sm", type=int, default=16, help="resident worlds per SM the kernel is built for")
+    ap.add_argument("--batch-threads", type=int, default=128, help="threads per world of the batch kernel")
+    ap.add_argument("--batch-blocks-per-sm", type=int, default=8, help="resident worlds per SM the kernel is built for")
     ap.add_argument("--ref-worlds", type=int, default=0, help="worlds in the CPU sample (0 = scaled to the host cores)")
     ap.add_argument("--no-extras", action="store_true", help="skip the single-world configurations")
     ap.add_argument("--no-cpu-baseline", action="store_true")

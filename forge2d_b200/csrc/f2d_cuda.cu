@@ -9,6 +9,7 @@
 //   * one large world  -> a cooperative grid of one block per SM (GridTeam, grid-wide barrier between phases).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (no FMA contraction: bit parity with the
 // reference's SSE2 arithmetic).
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 
@@ -245,7 +246,7 @@ struct f2dBatch
 	int eventCap = 0;
 	unsigned int* devError = nullptr;
 	f2d::Caps caps{};
-	int threads = 256, blocksPerSM = 2; // launch configuration of the batch kernel (f2dBatch_SetLaunchConfig)
+	int threads = 128, blocksPerSM = 8; // launch configuration of the batch kernel (f2dBatch_SetLaunchConfig)
 	cudaEvent_t events[8] = {};
 	b2BodyMoveEvent* hostEvents = nullptr; // pinned staging for f2dBatch_ReadBodyEvents
 	int* hostCounts = nullptr;

@@ -100,6 +100,7 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.islSlots, C, false );
 	add( w.islBodies, B, false );
 	add( w.bullets, B, false );
+	add( w.integ, 6 * B, false );
 	add( w.scan, B + 8, false );
 	add( w.scratch, 2 * B + 64, false );
 	add( w.splitScratch, 14 * ( B + 8 ) + 7 * ( C + 8 ) + 7 * ( J + 8 ), false );

@@ -34,7 +34,9 @@ struct CtaTeam
 {
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = true;
-	__device__ bool canFork() const { return blockDim.x >= 64; }
+	// Forking pays when the crew keeps most of the block: with two warps the solver would run on one while the other
+	// walks (measured: the walking warp then waits ~2x its walk for the crew), so small blocks walk first, then solve.
+	__device__ bool canFork() const { return blockDim.x >= 256; }
 	__device__ bool inSide() const { return threadIdx.x >= blockDim.x - 32; }
 	__device__ bool isSideLeader() const { return threadIdx.x == blockDim.x - 32; }
 	typedef WarpLanes Lanes;
@@ -192,6 +194,7 @@ struct GridTeam
 	__device__ void sync() { gridBarrierWait( barrier, gen, gridDim.x ); }
 	// the tree rebuild runs on block 0 alone (block-level barriers) while the other blocks do the narrowphase
 	__device__ bool inSoloBlock() const { return blockIdx.x == 0; }
+	__device__ bool hasOutsideSolo() const { return gridDim.x > 1; }
 	__device__ CtaTeam soloTeam() const { return CtaTeam{ smem }; }
 	__device__ int rankOutsideSolo() const { return (int)( ( blockIdx.x - 1 ) * blockDim.x + threadIdx.x ); }
 	__device__ int sizeOutsideSolo() const { return (int)( ( gridDim.x - 1 ) * blockDim.x ); }
@@ -255,22 +258,35 @@ template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& 
 	}
 }
 
-// One thread block per world; worlds are `stride` bytes apart. Grid-stride over worlds.
+// One thread block per world; worlds are `stride` bytes apart. Grid-stride over worlds. The block steps a copy of the
+// World header held in shared memory (see World::deviceBase) and writes it back when the world is done.
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__( kThreads, kMinBlocks )
 	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps )
 {
 	__shared__ int32_t smem[64];
+	__shared__ uint4 header[sizeof( World ) / 16];
 	CtaTeam team{ smem };
+	World* w = reinterpret_cast<World*>( header );
 	for ( int wi = (int)blockIdx.x; wi < worldCount; wi += (int)gridDim.x )
 	{
-		World* w = reinterpret_cast<World*>( base + (unsigned long long)wi * stride );
+		uint4* image = reinterpret_cast<uint4*>( base + (unsigned long long)wi * stride );
+		for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
+			header[i] = image[i];
+		__syncthreads();
+		if ( threadIdx.x == 0 )
+			w->deviceBase = reinterpret_cast<uint64_t>( image );
+		__syncthreads();
 		for ( int s = 0; s < steps; ++s )
 		{
 			if ( w->error & ( kErrCapacity | kErrUnsupported ) )
 				break;
 			runPhase( w, team, phase, dt, sub );
 		}
+		__syncthreads();
+		for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
+			image[i] = header[i];
+		__syncthreads();
 	}
 }
 
@@ -280,6 +296,10 @@ __global__ void __launch_bounds__( kThreads, 1 ) stepWorldGrid( World* w, int32_
 {
 	__shared__ int32_t smem[64];
 	GridTeam team{ 0u, smem, blockTotals + 128, reinterpret_cast<GridBarrier*>( blockTotals ), 0u };
+	// the grid shares the header in HBM; every block stores the same address, so each may rely on it after its own barrier
+	if ( threadIdx.x == 0 )
+		w->deviceBase = reinterpret_cast<uint64_t>( w );
+	__syncthreads();
 	if ( w->error & ( kErrCapacity | kErrUnsupported ) )
 		return;
 	team.begin();

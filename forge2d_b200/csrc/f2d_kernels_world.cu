@@ -14,7 +14,8 @@ __global__ void gatherMoveEvents( const char* base, unsigned long long stride, i
 		return;
 	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
 	int n = min( w->moveEvents.count, maxBodies );
-	const BodyMoveEvent* src = ptr( w, w->moveEvents );
+	// not ptr(): a batch that was uploaded but never stepped has no deviceBase yet
+	const BodyMoveEvent* src = reinterpret_cast<const BodyMoveEvent*>( reinterpret_cast<const char*>( w ) + w->moveEvents.off );
 	// 40-byte records copied as 8-byte words: coalesced, no struct padding games
 	const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>( src );
 	unsigned long long* d8 = reinterpret_cast<unsigned long long*>( out + (size_t)wi * maxBodies );

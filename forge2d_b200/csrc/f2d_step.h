@@ -467,15 +467,11 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492). The reference overlaps it with
 	// the narrowphase on another worker; here the whole team does one after the other, each fully data-parallel
 	// (measured: a single block rebuilding beside the narrowphase is slower than the grid doing both in turn).
-	treeRebuildTeam( w, t, w->trees[kDynamicBody] );
-	treeRebuildTeam( w, t, w->trees[kKinematicBody] );
-	t.sync();
-	F2D_MARK( w, t, pfTreeRebuild );
-	{
+	auto narrowphase = [&]( int rank, int size ) {
 		// a thread's indices only grow, so the list segment is tracked with a forward cursor (no per-thread table)
 		int seg = -1, segStart = 0, segEnd = 0;
 		const int32_t* list = nullptr;
-		for ( int i = t.rank(); i < total; i += t.size() )
+		for ( int i = rank; i < total; i += size )
 		{
 			while ( i >= segEnd )
 			{
@@ -487,7 +483,12 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 			}
 			collideContact( w, list[i - segStart] );
 		}
-	}
+	};
+	treeRebuildTeam( w, t, w->trees[kDynamicBody] );
+	treeRebuildTeam( w, t, w->trees[kKinematicBody] );
+	t.sync();
+	F2D_MARK( w, t, pfTreeRebuild );
+	narrowphase( t.rank(), t.size() );
 	t.sync();
 	F2D_MARK( w, t, pfNarrow );
 	contactStatePass( w, t );
@@ -496,34 +497,59 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 }
 
 // ------------------------------------------------------------------------------------------------ solve
-// solver.c:65-129
-F2D_HDF inline void integrateVelocity( World* w, int awakeIndex, float h, float maxLinearSpeed, float maxAngularSpeed )
+// solver.c:65-129. Everything the velocity integration reads from the body record is constant during a step (forces
+// and torques are only cleared by finalize), so the damping factors and velocity deltas - the reference recomputes
+// them, from the same inputs, in every sub-step - are evaluated once per step into a dense field-major table by awake
+// index: the sub-steps then read 24 coalesced bytes per body instead of gathering a 100-byte record.
+F2D_HDF inline void prepareIntegrate( World* w, int awakeIndex, float h )
 {
-	BodyState& state = ptr( w, w->states )[awakeIndex];
-	BodySim& sim = ptr( w, w->sims )[ptr( w, w->awakeBodies )[awakeIndex]];
-	V2 v = state.v;
-	float wv = state.w;
-	float maxLinearSpeedSquared = maxLinearSpeed * maxLinearSpeed;
-	float maxAngularSpeedSquared = maxAngularSpeed * maxAngularSpeed;
+	const BodySim& sim = ptr( w, w->sims )[ptr( w, w->awakeBodies )[awakeIndex]];
+	float* c = ptr( w, w->integ ) + awakeIndex;
+	const int stride = w->integ.cap / 6;
 	float linearDamping = 1.0f / ( 1.0f + h * sim.linearDamping );
 	float angularDamping = 1.0f / ( 1.0f + h * sim.angularDamping );
 	float gravityScale = sim.invMass > 0.0f ? sim.gravityScale : 0.0f;
 	V2 linearVelocityDelta = add( mulSV( h * sim.invMass, sim.force ), mulSV( h * gravityScale, w->gravity ) );
 	float angularVelocityDelta = h * sim.invInertia * sim.torque;
+	c[0] = linearVelocityDelta.x;
+	c[stride] = linearVelocityDelta.y;
+	c[2 * stride] = angularVelocityDelta;
+	c[3 * stride] = linearDamping;
+	c[4 * stride] = angularDamping;
+	c[5 * stride] = sim.allowFastRotation ? 1.0f : 0.0f;
+}
+
+F2D_HDF inline void integrateVelocity( World* w, int awakeIndex, float h, float maxLinearSpeed, float maxAngularSpeed )
+{
+	(void)h;
+	BodyState& state = ptr( w, w->states )[awakeIndex];
+	const float* c = ptr( w, w->integ ) + awakeIndex;
+	const int stride = w->integ.cap / 6;
+	V2 v = state.v;
+	float wv = state.w;
+	float maxLinearSpeedSquared = maxLinearSpeed * maxLinearSpeed;
+	float maxAngularSpeedSquared = maxAngularSpeed * maxAngularSpeed;
+	V2 linearVelocityDelta = { c[0], c[stride] };
+	float angularVelocityDelta = c[2 * stride];
+	float linearDamping = c[3 * stride];
+	float angularDamping = c[4 * stride];
 	v = mulAdd( linearVelocityDelta, linearDamping, v );
 	wv = angularVelocityDelta + angularDamping * wv;
+	bool capped = false;
 	if ( dot( v, v ) > maxLinearSpeedSquared )
 	{
 		float ratio = maxLinearSpeed / length( v );
 		v = mulSV( ratio, v );
-		sim.isSpeedCapped = true;
+		capped = true;
 	}
-	if ( wv * wv > maxAngularSpeedSquared && sim.allowFastRotation == false )
+	if ( wv * wv > maxAngularSpeedSquared && c[5 * stride] == 0.0f )
 	{
 		float ratio = maxAngularSpeed / absf( wv );
 		wv *= ratio;
-		sim.isSpeedCapped = true;
+		capped = true;
 	}
+	if ( capped )
+		ptr( w, w->sims )[ptr( w, w->awakeBodies )[awakeIndex]].isSpeedCapped = true;
 	state.v = v;
 	state.w = wv;
 }
@@ -1004,27 +1030,6 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	t.sync();
 }
 
-F2D_HD int popCount32( uint32_t x )
-{
-	int n = 0;
-	while ( x != 0 )
-	{
-		x &= x - 1;
-		n += 1;
-	}
-	return n;
-}
-F2D_HD int lowestBit32( uint32_t x )
-{
-	int n = 0;
-	while ( ( x & 1u ) == 0 )
-	{
-		x >>= 1;
-		n += 1;
-	}
-	return n;
-}
-
 // The depth-first walk. Order of everything follows island.c:669-833: the visiting order is serial by nature (it
 // defines the new islands' ids and list orders), but the edges of ONE popped body are independent tests against the
 // marks, so the lanes of a warp take one edge each: an edge is new iff its constraint is unmarked (ballot -> ranks
@@ -1200,6 +1205,11 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 			int n = w->colorJoints[color].count;
 			for ( int i = t.rank(); i < n; i += t.size() )
 				prepareJoint( w, jsims[jl[i]] );
+		}
+		{
+			const float h = w->step.h;
+			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+				prepareIntegrate( w, i, h );
 		}
 		const ConView c = conView( w );
 		const BodyState* states = ptr( w, w->states );
@@ -1805,27 +1815,40 @@ F2D_HDF inline void enlargeLeafParallel( World* w, Tree& tree, int leaf, Box box
 	while ( parent != kNull )
 	{
 		TreeNode& n = nodes[parent];
-		// Plain reads first: boxes only grow and flags only accumulate during this phase, so a stale value can only
-		// cause a redundant atomic, never a missed one. Once an ancestor already contains the box AND is flagged,
-		// whoever grew / flagged it is carrying both up to the root (or they were that way before the phase, and the
-		// tree invariants - parent contains child, flags are upward closed - cover the rest of the path).
-		bool contains = n.box.lo.x <= box.lo.x && n.box.lo.y <= box.lo.y && box.hi.x <= n.box.hi.x && box.hi.y <= n.box.hi.y;
-		bool flagged = ( n.flags & kNodeEnlarged ) != 0;
+		// Reads that bypass L1 (the atomics below are performed in L2, a line cached in L1 would never show them):
+		// boxes only grow and flags only accumulate during this phase, so an old value can only cause a redundant
+		// atomic, never a missed one - but a FRESH value is what makes the early exit below bite. Once an ancestor
+		// already contains the box AND is flagged, whoever grew / flagged it is carrying both up to the root (or they
+		// were that way before the phase, and the tree invariants - parent contains child, flags are upward closed -
+		// cover the rest of the path).
+#if defined( __CUDA_ARCH__ )
+		const float4 nb = __ldcg( reinterpret_cast<const float4*>( &n.box ) );
+		const int4 links = __ldcg( reinterpret_cast<const int4*>( &n.child1 ) ); // child1, child2, parent, height | flags << 16
+		const Box nbox = { { nb.x, nb.y }, { nb.z, nb.w } };
+		const int next = links.z;
+		const bool flagged = ( ( (uint32_t)links.w >> 16 ) & kNodeEnlarged ) != 0;
+#else
+		const Box nbox = n.box;
+		const int next = n.parent;
+		const bool flagged = ( n.flags & kNodeEnlarged ) != 0;
+#endif
+		const bool contains = nbox.lo.x <= box.lo.x && nbox.lo.y <= box.lo.y && box.hi.x <= nbox.hi.x && box.hi.y <= nbox.hi.y;
 		if ( contains && flagged )
 			break;
-		if ( contains == false )
-		{
+		if ( box.lo.x < nbox.lo.x )
 			atomMinF( &n.box.lo.x, box.lo.x );
+		if ( box.lo.y < nbox.lo.y )
 			atomMinF( &n.box.lo.y, box.lo.y );
+		if ( nbox.hi.x < box.hi.x )
 			atomMaxF( &n.box.hi.x, box.hi.x );
+		if ( nbox.hi.y < box.hi.y )
 			atomMaxF( &n.box.hi.y, box.hi.y );
-		}
 		if ( flagged == false )
 		{
 			// height (low 16 bits) and flags (high 16 bits) share one 32-bit word
 			atomOr32( reinterpret_cast<uint32_t*>( &n.height ), (uint32_t)kNodeEnlarged << 16 );
 		}
-		parent = n.parent;
+		parent = next;
 	}
 }
 

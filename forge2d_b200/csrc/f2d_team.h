@@ -65,6 +65,9 @@ F2D_HD void atomMaxF( float* p, float v )
 }
 #endif
 
+F2D_HD int loadVolatile( const int32_t* p ) { return *reinterpret_cast<const volatile int32_t*>( p ); }
+F2D_HD void storeVolatile( int32_t* p, int v ) { *reinterpret_cast<volatile int32_t*>( p ) = v; }
+
 #if defined( __CUDA_ARCH__ )
 F2D_HD uint64_t profClock()
 {
@@ -88,6 +91,36 @@ F2D_HD uint64_t profClock() { return 0; }
 		}                                                                                                                      \
 	} while ( 0 )
 
+F2D_HD int popCount32( uint32_t x )
+{
+#if defined( __CUDA_ARCH__ )
+	return __popc( x );
+#else
+	int n = 0;
+	while ( x != 0 )
+	{
+		x &= x - 1;
+		n += 1;
+	}
+	return n;
+#endif
+}
+// index of the lowest set bit (x != 0)
+F2D_HD int lowestBit32( uint32_t x )
+{
+#if defined( __CUDA_ARCH__ )
+	return __ffs( (int)x ) - 1;
+#else
+	int n = 0;
+	while ( ( x & 1u ) == 0 )
+	{
+		x >>= 1;
+		n += 1;
+	}
+	return n;
+#endif
+}
+
 // The lanes that walk a graph together (island split): one host thread, or the 32 lanes of a warp.
 struct SoloLanes
 {
@@ -96,6 +129,11 @@ struct SoloLanes
 	F2D_HD uint32_t ballot( bool p ) const { return p ? 1u : 0u; }
 	F2D_HD uint32_t matchAny( int ) const { return 1u; }
 	F2D_HD void sync() const {}
+	F2D_HD int broadcast( int v ) const { return v; }
+	F2D_HD int reduceAdd( int v ) const { return v; }
+	F2D_HD float reduceMin( float v ) const { return v; }
+	F2D_HD float reduceMax( float v ) const { return v; }
+	F2D_HD void fence() const {}
 };
 #if defined( __CUDA_ARCH__ )
 struct WarpLanes
@@ -105,6 +143,33 @@ struct WarpLanes
 	F2D_HD uint32_t ballot( bool p ) const { return __ballot_sync( 0xffffffffu, p ); }
 	F2D_HD uint32_t matchAny( int key ) const { return __match_any_sync( 0xffffffffu, key ); }
 	F2D_HD void sync() const { __syncwarp(); }
+	F2D_HD int broadcast( int v ) const { return __shfl_sync( 0xffffffffu, v, 0 ); }
+	F2D_HD int reduceAdd( int v ) const
+	{
+		for ( int off = 16; off > 0; off >>= 1 )
+			v += __shfl_xor_sync( 0xffffffffu, v, off );
+		return v;
+	}
+	// min / max in the reference's `a < b ? a : b` / `a > b ? a : b` forms (every lane ends with the same value)
+	F2D_HD float reduceMin( float v ) const
+	{
+		for ( int off = 16; off > 0; off >>= 1 )
+		{
+			float o = __shfl_xor_sync( 0xffffffffu, v, off );
+			v = o < v ? o : v;
+		}
+		return v;
+	}
+	F2D_HD float reduceMax( float v ) const
+	{
+		for ( int off = 16; off > 0; off >>= 1 )
+		{
+			float o = __shfl_xor_sync( 0xffffffffu, v, off );
+			v = o > v ? o : v;
+		}
+		return v;
+	}
+	F2D_HD void fence() const { __threadfence(); }
 };
 #else
 typedef SoloLanes WarpLanes;

@@ -7,11 +7,14 @@
 //             DFS is the number of items that precede it = sum over its ancestors, when it hangs under child2, of the
 //             item count under child1. Counts come from one walk to the root per item (integer atomics), ranks from
 //             a second walk. No traversal stack, no serial DFS.
-//   build     level-synchronous top-down median split. The reference's Hoare partition has a closed form: with L =
-//             #(centre < pivot), the k-th misplaced item of the left part (ascending) swaps with the k-th misplaced item
-//             of the right part (descending); degenerate splits (L == 0 or L == n) leave the order untouched and cut
-//             at n/2. Flags + prefix sums give every swap pair directly, all segments of a level at once.
-//   refit     boxes, heights and categories bottom-up, one pass per level.
+//   build     top-down median split without levels or team barriers: a long segment of the item array is split by the
+//             lanes of one warp (centre bounds by shuffle reduction, then the reference's Hoare partition in closed form:
+//             with L = #(centre < pivot), the k-th misplaced item of the left part (ascending) swaps with the k-th
+//             misplaced item of the right part (descending); degenerate splits (L == 0 or L == n) leave the order
+//             untouched and cut at n/2) and its two halves go back to a work queue that the warps drain together;
+//             short segments are finished serially by one thread each.
+//   refit     boxes, heights and categories bottom-up by last arrival: the second child subtree to complete refits
+//             the node above it and carries on upwards.
 // Internal nodes are recycled in place: the dissolved nodes are exactly as many as the build needs, so the free list
 // and the node count are unchanged (the reference frees and re-allocates the same set; which internal node lands
 // where is unobservable: proxies are leaves, queries follow child links).
@@ -82,6 +85,7 @@ F2D_HD bool treeNodeIsDissolved( const TreeNode& n ) { return n.height > 0 && ( 
 // (dynamic_tree.c:1716-1869) with its in-place Hoare partition (treePartitionMid), recycling the dissolved node
 // freed[m-1] for the split at m, and computing boxes / heights / categories on the way back up.
 constexpr int kTreeSerialFinish = 24; // segments at most this long are finished by one thread each
+constexpr int kTreeQueueBuildMaxTeam = 256; // teams up to this size use the work-queue build (treeSplitSegment)
 
 F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
 									   int32_t* levelOf, int a, int e, int parentKey )
@@ -160,6 +164,187 @@ F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, in
 	}
 }
 
+// A child subtree of the long-segment node `nodeIndex` is complete. The second arrival refits the node from its two
+// children and carries on to the node above (bottom-up refit without levels or barriers).
+F2D_HDF inline void treeArrive( TreeNode* nodes, int32_t* arrivals, int nodeIndex )
+{
+	while ( nodeIndex != kNull )
+	{
+#if defined( __CUDA_ARCH__ )
+		__threadfence();
+#endif
+		if ( atomAdd( arrivals + nodeIndex, 1 ) == 0 )
+			return;
+#if defined( __CUDA_ARCH__ )
+		__threadfence();
+#endif
+		TreeNode& node = nodes[nodeIndex];
+		const int c1i = loadVolatile( &node.child1 ), c2i = loadVolatile( &node.child2 );
+		const TreeNode& c1 = nodes[c1i];
+		const TreeNode& c2 = nodes[c2i];
+		node.box = boxUnion( c1.box, c2.box );
+		node.height = (uint16_t)( 1 + maxU16( c1.height, c2.height ) );
+		node.category = c1.category | c2.category;
+		nodeIndex = node.parent;
+	}
+}
+
+// One long segment [a, e) of the item array, split by the lanes of a warp: centre bounds, pivot, the reference's
+// Hoare partition in closed form (with L = #(centre < pivot), the k-th misplaced item of the left part, ascending,
+// swaps with the k-th misplaced item of the right part, descending; L == 0 or L == n leaves the order untouched and
+// cuts at n/2), node creation, and the two child segments handed on: single items are hung at once, short segments
+// go to the short list, long ones back to the queue.
+template <class Lanes>
+F2D_HDF inline void treeSplitSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const TreeScratch& s,
+									  int32_t* queue, int32_t* smallList, int a, Lanes L )
+{
+	const int lane = L.lane(), W = L.count();
+	const uint32_t below = lane == 0 ? 0u : ( 0xffffffffu >> ( 32 - lane ) );
+	const int e = s.segEnd[0][a];
+	const int parentKey = s.segParent[0][a];
+	const int count = e - a;
+	int split = a + count / 2;
+	if ( count > 2 )
+	{
+		float lx = FLT_MAX, ly = FLT_MAX, hx = -FLT_MAX, hy = -FLT_MAX;
+		for ( int i = a + lane; i < e; i += W )
+		{
+			V2 c = leafCenters[i];
+			lx = c.x < lx ? c.x : lx;
+			ly = c.y < ly ? c.y : ly;
+			hx = c.x > hx ? c.x : hx;
+			hy = c.y > hy ? c.y : hy;
+		}
+		lx = L.reduceMin( lx );
+		ly = L.reduceMin( ly );
+		hx = L.reduceMax( hx );
+		hy = L.reduceMax( hy );
+		const bool useX = ( hx - lx ) > ( hy - ly );
+		const float pivot = useX ? 0.5f * ( lx + hx ) : 0.5f * ( ly + hy );
+		int lessCount = 0;
+		for ( int i = a + lane; i < e; i += W )
+		{
+			V2 c = leafCenters[i];
+			lessCount += ( useX ? c.x : c.y ) < pivot ? 1 : 0;
+		}
+		lessCount = L.reduceAdd( lessCount );
+		if ( lessCount > 0 && lessCount < count )
+		{
+			split = a + lessCount;
+			// misplaced positions, both sides ascending
+			int32_t* badL = s.badLPos + a;
+			int32_t* badR = s.badRPos + a;
+			int nl = 0, nr = 0;
+			for ( int chunk = a; chunk < split; chunk += W )
+			{
+				int i = chunk + lane;
+				bool bad = false;
+				if ( i < split )
+				{
+					V2 c = leafCenters[i];
+					bad = ( ( useX ? c.x : c.y ) < pivot ) == false;
+				}
+				uint32_t mask = L.ballot( bad );
+				if ( bad )
+					badL[nl + popCount32( mask & below )] = i;
+				nl += popCount32( mask );
+			}
+			for ( int chunk = split; chunk < e; chunk += W )
+			{
+				int i = chunk + lane;
+				bool bad = false;
+				if ( i < e )
+				{
+					V2 c = leafCenters[i];
+					bad = ( useX ? c.x : c.y ) < pivot;
+				}
+				uint32_t mask = L.ballot( bad );
+				if ( bad )
+					badR[nr + popCount32( mask & below )] = i;
+				nr += popCount32( mask );
+			}
+			L.sync();
+			for ( int k = lane; k < nl; k += W )
+			{
+				int p = badL[k], q = badR[nr - 1 - k];
+				int32_t ti = leafIndices[p];
+				leafIndices[p] = leafIndices[q];
+				leafIndices[q] = ti;
+				V2 tc = leafCenters[p];
+				leafCenters[p] = leafCenters[q];
+				leafCenters[q] = tc;
+			}
+			L.sync();
+		}
+	}
+	if ( lane == 0 )
+	{
+		const int nodeIndex = s.freed[split - 1];
+		TreeNode& node = nodes[nodeIndex];
+		node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+		node.category = 1;
+		node.height = 0;
+		node.flags = kNodeAllocated;
+		if ( parentKey == kNull )
+		{
+			node.parent = kNull;
+			tree.root = nodeIndex;
+		}
+		else
+		{
+			node.parent = parentKey >> 1;
+			if ( parentKey & 1 )
+				nodes[parentKey >> 1].child2 = nodeIndex;
+			else
+				nodes[parentKey >> 1].child1 = nodeIndex;
+		}
+		int leafChildren = 0;
+		int longChildren = 0;
+		int longStart[2];
+		for ( int side = 0; side < 2; ++side )
+		{
+			const int start = side == 0 ? a : split;
+			const int end = side == 0 ? split : e;
+			const int n = end - start;
+			if ( n == 1 )
+			{
+				int item = leafIndices[start];
+				if ( side == 0 )
+					node.child1 = item;
+				else
+					node.child2 = item;
+				nodes[item].parent = nodeIndex;
+				leafChildren += 1;
+			}
+			else
+			{
+				s.segEnd[0][start] = end;
+				s.segParent[0][start] = ( nodeIndex << 1 ) | side;
+				if ( n > kTreeSerialFinish )
+					longStart[longChildren++] = start;
+				else
+					smallList[atomAdd( s.ctrl + 3, 1 )] = start;
+			}
+		}
+		s.under[nodeIndex] = leafChildren; // arrivals so far (treeArrive)
+		if ( longChildren > 0 )
+		{
+			atomAdd( s.ctrl + 2, longChildren );
+			int slot = atomAdd( s.ctrl + 1, longChildren );
+#if defined( __CUDA_ARCH__ )
+			__threadfence();
+#endif
+			for ( int k = 0; k < longChildren; ++k )
+				storeVolatile( queue + slot + k, longStart[k] );
+		}
+#if defined( __CUDA_ARCH__ )
+		__threadfence();
+#endif
+		atomAdd( s.ctrl + 2, -1 );
+	}
+	L.sync();
+}
+
 template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tree& tree )
 {
 	if ( tree.proxyCount == 0 || tree.root == kNull )
@@ -182,14 +367,6 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 	// ---- collect: items under each dissolved node
 	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 		s.under[i] = 0;
-	if ( t.rank() == 0 )
-	{
-		for ( int a = 0; a < 2; ++a )
-		{
-			s.lo[0][a][0] = FLT_MAX;
-			s.hi[0][a][0] = -FLT_MAX;
-		}
-	}
 	t.sync();
 	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 	{
@@ -237,14 +414,106 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			V2 c = boxCenter( n.box );
 			leafIndices[before] = i;
 			leafCenters[before] = c;
-			atomMinF( s.lo[0][0], c.x );
-			atomMinF( s.lo[0][1], c.y );
-			atomMaxF( s.hi[0][0], c.x );
-			atomMaxF( s.hi[0][1], c.y );
 		}
 	}
 	t.sync();
 
+	// Two builds of the same tree. Small teams (a few warps per world: batches) are bound by instructions per warp and
+	// use the work-queue build; large teams (one 1024-thread block or a cooperative grid per world) have the threads to
+	// take every item of a level at once and use the level-synchronous build.
+	if ( t.size() <= kTreeQueueBuildMaxTeam )
+	{
+		// ---- build: long segments by warps from a work queue, short ones by single threads, refit by last arrival
+		int32_t* queue = s.scanLess; // n + 1 entries
+		int32_t* smallList = s.segOf;
+		for ( int i = t.rank(); i < itemCount; i += t.size() )
+			queue[i] = kNull;
+		if ( t.rank() == 0 )
+		{
+			s.ctrl[0] = 0; // next ticket
+			s.ctrl[1] = 0; // queue tail
+			s.ctrl[2] = 0; // long segments published and not yet split
+			s.ctrl[3] = 0; // short segments
+			s.segEnd[0][0] = itemCount;
+			s.segParent[0][0] = kNull;
+		}
+		t.sync();
+		if ( t.rank() == 0 )
+		{
+			if ( itemCount > kTreeSerialFinish )
+			{
+				s.ctrl[1] = 1;
+				s.ctrl[2] = 1;
+				queue[0] = 0;
+			}
+			else
+			{
+				s.ctrl[3] = 1;
+				smallList[0] = 0;
+			}
+		}
+		t.sync();
+		{
+			typename Team::Lanes L;
+			while ( true )
+			{
+				int ticket = 0;
+				if ( L.lane() == 0 )
+					ticket = atomAdd( s.ctrl + 0, 1 );
+				ticket = L.broadcast( ticket );
+				int a = kNull;
+				if ( L.lane() == 0 )
+				{
+					while ( true )
+					{
+						a = ticket < itemCount ? loadVolatile( queue + ticket ) : kNull;
+						if ( a != kNull || loadVolatile( s.ctrl + 2 ) == 0 )
+							break;
+					}
+				}
+				a = L.broadcast( a );
+				if ( a == kNull )
+					break;
+				L.fence();
+				treeSplitSegment( w, tree, nodes, leafIndices, leafCenters, s, queue, smallList, a, L );
+			}
+		}
+		t.sync();
+		// short segments: one thread each builds and refits its subtree serially, then reports to the node above
+		{
+			const int smallCount = s.ctrl[3];
+			for ( int k = t.rank(); k < smallCount; k += t.size() )
+			{
+				int a0 = smallList[k];
+				int parentKey = s.segParent[0][a0];
+				treeFinishSegment( w, tree, nodes, leafIndices, leafCenters, s.freed, s.level, a0, s.segEnd[0][a0], parentKey );
+				if ( parentKey != kNull )
+					treeArrive( nodes, s.under, parentKey >> 1 );
+			}
+		}
+		t.sync();
+		return;
+	}
+
+	// root bounds of the item centres for the first level
+	if ( t.rank() == 0 )
+	{
+		for ( int a = 0; a < 2; ++a )
+		{
+			s.lo[0][a][0] = FLT_MAX;
+			s.hi[0][a][0] = -FLT_MAX;
+		}
+	}
+	t.sync();
+	for ( int i = t.rank(); i < itemCount; i += t.size() )
+	{
+		V2 c = leafCenters[i];
+		atomMinF( s.lo[0][0], c.x );
+		atomMinF( s.lo[0][1], c.y );
+		atomMaxF( s.hi[0][0], c.x );
+		atomMaxF( s.hi[0][1], c.y );
+	}
+	t.sync();
 	// ---- build, level by level (three passes and one prefix sum per level)
 	for ( int i = t.rank(); i < itemCount; i += t.size() )
 		s.segOf[i] = 0;

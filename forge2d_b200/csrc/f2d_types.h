@@ -264,7 +264,9 @@ struct ContactSim
 	float friction, restitution, rollingResistance, tangentSpeed;
 	uint32_t simFlags;
 	SimplexCache cache;
+	int32_t pad2; // 192 bytes: records start on 16-byte boundaries
 };
+static_assert( sizeof( ContactSim ) == 192, "ContactSim layout" );
 // B2/src/island.h:25-57
 struct Island
 {
@@ -628,20 +630,36 @@ struct World
 	Arr<int32_t> islSlots;	  // [awake contacts]
 	Arr<int32_t> islBodies;	  // [awake bodies]
 	Arr<int32_t> bullets;
+	Arr<float> integ;	  // 6 x bodies.cap, field-major by awake index: this step's velocity-integration constants
 	Arr<int32_t> scan;	  // scan scratch (awake bodies + 1)
 	Arr<int32_t> scratch; // island split stacks
 	Arr<int32_t> splitScratch; // island split work arrays (f2d_step.h SplitView)
+
+	// Device only: address of the image in HBM. The one-block-per-world kernels work on a copy of this header in
+	// SHARED memory (every count, offset and step constant is then a shared-memory load instead of a global one), so
+	// array addresses cannot be derived from the header's own address there; the kernels set this at entry. Host code
+	// never reads it (ptr() below uses the header address itself on the host).
+	uint64_t deviceBase;
 };
+static_assert( sizeof( World ) % 16 == 0, "the header is copied to shared memory in 16-byte words" );
 
 constexpr uint64_t kWorldMagic = 0x4632444232303042ull; // "F2DB200B"
 
 template <class T> F2D_HD T* ptr( World* w, const Arr<T>& a )
 {
+#if defined( __CUDA_ARCH__ )
+	return reinterpret_cast<T*>( w->deviceBase + a.off );
+#else
 	return reinterpret_cast<T*>( reinterpret_cast<char*>( w ) + a.off );
+#endif
 }
 template <class T> F2D_HD const T* ptr( const World* w, const Arr<T>& a )
 {
+#if defined( __CUDA_ARCH__ )
+	return reinterpret_cast<const T*>( w->deviceBase + a.off );
+#else
 	return reinterpret_cast<const T*>( reinterpret_cast<const char*>( w ) + a.off );
+#endif
 }
 
 F2D_HD void setError( World* w, uint32_t bits, int detail )

@@ -92,7 +92,7 @@ if "configs" in what:
     t = scenes.bench2d(lib)
     for _ in range(256):
         t.step()
-    for threads, bps in ((256, 2), (256, 4), (512, 2), (32, 32), (128, 8), (64, 16)):
+    for threads, bps in ((256, 2), (256, 4), (32, 32), (128, 8), (64, 16)):
         count = 148 * bps * (2 if threads <= 64 else 4)
         b = lib.f2dBatch_Create(t.world, count)
         assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)

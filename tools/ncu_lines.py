@@ -153,3 +153,24 @@ if "--functions" in sys.argv:
     print("%-52s %9s %6s %12s %6s %12s %12s" % ("function", "samples", "%", "warp-inst", "%", "L2 global", "L2 local"))
     for key, v in sorted(ft.items(), key=lambda kv: -kv[1][0])[:top]:
         print("%-52s %9d %6.2f %12d %6.2f %12d %12d" % (key, v[0], 100.0 * v[0] / max(1, tot[0]), v[1], 100.0 * v[1] / max(1, tot[1]), v[2], v[3]))
+
+# optional: --callers file:line -> who calls into that frame (next outer frame), by samples
+if "--callers" in sys.argv:
+    f, l = sys.argv[sys.argv.index("--callers") + 1].split(":")
+    want = (f, int(l))
+    sub = defaultdict(lambda: [0, 0, 0, 0])
+    for r in body:
+        if len(r) < 5:
+            continue
+        off = int(r[0], 16) - base
+        chain = chains.get(off, [("?", 0)])
+        if want not in chain:
+            continue
+        k = chain.index(want)
+        key = chain[k + 1] if k + 1 < len(chain) else ("<top>", 0)
+        vals = [num(r, "Warp Stall Sampling (All Samples)"), num(r, "Instructions Executed"), num(r, "L2 Theoretical Sectors Global"), 0]
+        for q in range(4):
+            sub[key][q] += vals[q]
+    print("\n== callers of %s:%d" % want)
+    for key, v in sorted(sub.items(), key=lambda kv: -kv[1][0])[:top]:
+        print("%-28s %9d %12d %12d" % ("%s:%d" % key, v[0], v[1], v[2]))
