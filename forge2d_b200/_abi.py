@@ -114,6 +114,67 @@ class RevoluteJointDef(C.Structure):
                 ("collideConnected", c_bool), ("userData", c_void_p), ("internalValue", c_int)]
 
 
+class MassData(C.Structure):
+    _fields_ = [("mass", c_float), ("center", Vec2), ("rotationalInertia", c_float)]
+
+
+class ChainSegment(C.Structure):
+    _fields_ = [("ghost1", Vec2), ("segment", Segment), ("ghost2", Vec2), ("chainId", c_int)]
+
+
+class DistanceJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("localAnchorA", Vec2), ("localAnchorB", Vec2),
+                ("length", c_float), ("enableSpring", c_bool), ("hertz", c_float), ("dampingRatio", c_float),
+                ("enableLimit", c_bool), ("minLength", c_float), ("maxLength", c_float), ("enableMotor", c_bool),
+                ("maxMotorForce", c_float), ("motorSpeed", c_float), ("collideConnected", c_bool),
+                ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class MotorJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("linearOffset", Vec2), ("angularOffset", c_float),
+                ("maxForce", c_float), ("maxTorque", c_float), ("correctionFactor", c_float),
+                ("collideConnected", c_bool), ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class MouseJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("target", Vec2), ("hertz", c_float),
+                ("dampingRatio", c_float), ("maxForce", c_float), ("collideConnected", c_bool),
+                ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class FilterJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class PrismaticJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("localAnchorA", Vec2), ("localAnchorB", Vec2),
+                ("localAxisA", Vec2), ("referenceAngle", c_float), ("targetTranslation", c_float),
+                ("enableSpring", c_bool), ("hertz", c_float), ("dampingRatio", c_float), ("enableLimit", c_bool),
+                ("lowerTranslation", c_float), ("upperTranslation", c_float), ("enableMotor", c_bool),
+                ("maxMotorForce", c_float), ("motorSpeed", c_float), ("collideConnected", c_bool),
+                ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class WeldJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("localAnchorA", Vec2), ("localAnchorB", Vec2),
+                ("referenceAngle", c_float), ("linearHertz", c_float), ("angularHertz", c_float),
+                ("linearDampingRatio", c_float), ("angularDampingRatio", c_float), ("collideConnected", c_bool),
+                ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class WheelJointDef(C.Structure):
+    _fields_ = [("bodyIdA", BodyId), ("bodyIdB", BodyId), ("localAnchorA", Vec2), ("localAnchorB", Vec2),
+                ("localAxisA", Vec2), ("enableSpring", c_bool), ("hertz", c_float), ("dampingRatio", c_float),
+                ("enableLimit", c_bool), ("lowerTranslation", c_float), ("upperTranslation", c_float),
+                ("enableMotor", c_bool), ("maxMotorTorque", c_float), ("motorSpeed", c_float),
+                ("collideConnected", c_bool), ("userData", c_void_p), ("internalValue", c_int)]
+
+
+class ExplosionDef(C.Structure):
+    _fields_ = [("maskBits", C.c_uint64), ("position", Vec2), ("radius", c_float), ("falloff", c_float),
+                ("impulsePerLength", c_float)]
+
+
 class Counters(C.Structure):
     _fields_ = [("bodyCount", c_int), ("shapeCount", c_int), ("contactCount", c_int), ("jointCount", c_int),
                 ("islandCount", c_int), ("stackUsed", c_int), ("staticTreeHeight", c_int), ("treeHeight", c_int),
@@ -250,7 +311,118 @@ B2_FUNCTIONS = {
     "b2Shape_GetAABB": (AABB, [ShapeId]),
     "b2CreateRevoluteJoint": (JointId, [WorldId, C.POINTER(RevoluteJointDef)]),
     "b2Joint_IsValid": (c_bool, [JointId]),
+    # ---- the rest of the body / shape / joint surface (f2d_capi_ext.inl)
+    "b2DestroyBody": (None, [BodyId]),
+    "b2Body_GetLocalPoint": (Vec2, [BodyId, Vec2]),
+    "b2Body_GetWorldPoint": (Vec2, [BodyId, Vec2]),
+    "b2Body_GetLocalVector": (Vec2, [BodyId, Vec2]),
+    "b2Body_GetWorldVector": (Vec2, [BodyId, Vec2]),
+    "b2Body_SetTransform": (None, [BodyId, Vec2, Rot]),
+    "b2Body_ApplyForce": (None, [BodyId, Vec2, Vec2, c_bool]),
+    "b2Body_ApplyForceToCenter": (None, [BodyId, Vec2, c_bool]),
+    "b2Body_ApplyTorque": (None, [BodyId, c_float, c_bool]),
+    "b2Body_ApplyLinearImpulse": (None, [BodyId, Vec2, Vec2, c_bool]),
+    "b2Body_ApplyLinearImpulseToCenter": (None, [BodyId, Vec2, c_bool]),
+    "b2Body_ApplyAngularImpulse": (None, [BodyId, c_float, c_bool]),
+    "b2Body_SetType": (None, [BodyId, c_int]),
+    "b2Body_SetName": (None, [BodyId, C.c_char_p]),
+    "b2Body_GetName": (C.c_char_p, [BodyId]),
+    "b2Body_SetUserData": (None, [BodyId, c_void_p]),
+    "b2Body_GetUserData": (c_void_p, [BodyId]),
+    "b2Body_SetMassData": (None, [BodyId, MassData]),
+    "b2Body_GetMassData": (MassData, [BodyId]),
+    "b2Body_ApplyMassFromShapes": (None, [BodyId]),
+    "b2Body_SetLinearDamping": (None, [BodyId, c_float]),
+    "b2Body_GetLinearDamping": (c_float, [BodyId]),
+    "b2Body_SetAngularDamping": (None, [BodyId, c_float]),
+    "b2Body_GetAngularDamping": (c_float, [BodyId]),
+    "b2Body_SetGravityScale": (None, [BodyId, c_float]),
+    "b2Body_GetGravityScale": (c_float, [BodyId]),
+    "b2Body_SetAwake": (None, [BodyId, c_bool]),
+    "b2Body_IsEnabled": (c_bool, [BodyId]),
+    "b2Body_IsSleepEnabled": (c_bool, [BodyId]),
+    "b2Body_SetSleepThreshold": (None, [BodyId, c_float]),
+    "b2Body_GetSleepThreshold": (c_float, [BodyId]),
+    "b2Body_EnableSleep": (None, [BodyId, c_bool]),
+    "b2Body_Disable": (None, [BodyId]),
+    "b2Body_Enable": (None, [BodyId]),
+    "b2Body_SetFixedRotation": (None, [BodyId, c_bool]),
+    "b2Body_IsFixedRotation": (c_bool, [BodyId]),
+    "b2Body_SetBullet": (None, [BodyId, c_bool]),
+    "b2Body_IsBullet": (c_bool, [BodyId]),
+    "b2Body_EnableContactEvents": (None, [BodyId, c_bool]),
+    "b2Body_EnableHitEvents": (None, [BodyId, c_bool]),
+    "b2Body_GetWorld": (WorldId, [BodyId]),
+    "b2Body_GetShapes": (c_int, [BodyId, C.POINTER(ShapeId), c_int]),
+    "b2Body_GetJointCount": (c_int, [BodyId]),
+    "b2Body_GetJoints": (c_int, [BodyId, C.POINTER(JointId), c_int]),
+    "b2DestroyShape": (None, [ShapeId, c_bool]),
+    "b2Shape_GetWorld": (WorldId, [ShapeId]),
+    "b2Shape_SetUserData": (None, [ShapeId, c_void_p]),
+    "b2Shape_GetUserData": (c_void_p, [ShapeId]),
+    "b2Shape_IsSensor": (c_bool, [ShapeId]),
+    "b2Shape_TestPoint": (c_bool, [ShapeId, Vec2]),
+    "b2Shape_SetDensity": (None, [ShapeId, c_float, c_bool]),
+    "b2Shape_GetDensity": (c_float, [ShapeId]),
+    "b2Shape_SetFriction": (None, [ShapeId, c_float]),
+    "b2Shape_GetFriction": (c_float, [ShapeId]),
+    "b2Shape_SetRestitution": (None, [ShapeId, c_float]),
+    "b2Shape_GetRestitution": (c_float, [ShapeId]),
+    "b2Shape_GetFilter": (Filter, [ShapeId]),
+    "b2Shape_SetFilter": (None, [ShapeId, Filter]),
+    "b2Shape_EnableSensorEvents": (None, [ShapeId, c_bool]),
+    "b2Shape_AreSensorEventsEnabled": (c_bool, [ShapeId]),
+    "b2Shape_EnableContactEvents": (None, [ShapeId, c_bool]),
+    "b2Shape_AreContactEventsEnabled": (c_bool, [ShapeId]),
+    "b2Shape_EnablePreSolveEvents": (None, [ShapeId, c_bool]),
+    "b2Shape_ArePreSolveEventsEnabled": (c_bool, [ShapeId]),
+    "b2Shape_EnableHitEvents": (None, [ShapeId, c_bool]),
+    "b2Shape_AreHitEventsEnabled": (c_bool, [ShapeId]),
+    "b2Shape_GetType": (c_int, [ShapeId]),
+    "b2Shape_GetCircle": (Circle, [ShapeId]),
+    "b2Shape_GetSegment": (Segment, [ShapeId]),
+    "b2Shape_GetChainSegment": (ChainSegment, [ShapeId]),
+    "b2Shape_GetCapsule": (Capsule, [ShapeId]),
+    "b2Shape_GetPolygon": (Polygon, [ShapeId]),
+    "b2DefaultDistanceJointDef": (DistanceJointDef, []),
+    "b2DefaultMotorJointDef": (MotorJointDef, []),
+    "b2DefaultMouseJointDef": (MouseJointDef, []),
+    "b2DefaultFilterJointDef": (FilterJointDef, []),
+    "b2DefaultPrismaticJointDef": (PrismaticJointDef, []),
+    "b2DefaultWeldJointDef": (WeldJointDef, []),
+    "b2DefaultWheelJointDef": (WheelJointDef, []),
+    "b2DefaultExplosionDef": (ExplosionDef, []),
+    "b2CreateDistanceJoint": (JointId, [WorldId, C.POINTER(DistanceJointDef)]),
+    "b2CreateMotorJoint": (JointId, [WorldId, C.POINTER(MotorJointDef)]),
+    "b2CreateMouseJoint": (JointId, [WorldId, C.POINTER(MouseJointDef)]),
+    "b2CreateFilterJoint": (JointId, [WorldId, C.POINTER(FilterJointDef)]),
+    "b2CreatePrismaticJoint": (JointId, [WorldId, C.POINTER(PrismaticJointDef)]),
+    "b2CreateWeldJoint": (JointId, [WorldId, C.POINTER(WeldJointDef)]),
+    "b2CreateWheelJoint": (JointId, [WorldId, C.POINTER(WheelJointDef)]),
+    "b2DestroyJoint": (None, [JointId]),
+    "b2Joint_GetType": (c_int, [JointId]),
+    "b2Joint_GetBodyA": (BodyId, [JointId]),
+    "b2Joint_GetBodyB": (BodyId, [JointId]),
+    "b2Joint_GetWorld": (WorldId, [JointId]),
+    "b2Joint_GetLocalAnchorA": (Vec2, [JointId]),
+    "b2Joint_GetLocalAnchorB": (Vec2, [JointId]),
+    "b2Joint_SetLocalAnchorA": (None, [JointId, Vec2]),
+    "b2Joint_SetLocalAnchorB": (None, [JointId, Vec2]),
+    "b2Joint_SetCollideConnected": (None, [JointId, c_bool]),
+    "b2Joint_GetCollideConnected": (c_bool, [JointId]),
+    "b2Joint_SetUserData": (None, [JointId, c_void_p]),
+    "b2Joint_GetUserData": (c_void_p, [JointId]),
+    "b2Joint_WakeBodies": (None, [JointId]),
+    "b2Joint_GetConstraintForce": (Vec2, [JointId]),
+    "b2Joint_GetConstraintTorque": (c_float, [JointId]),
 }
+
+# per-joint-type accessors (generated table; names resolved to the classes above)
+from ._abi_joints import JOINT_ACCESSORS as _JA  # noqa: E402
+
+_NAMES = {"JointId": JointId, "Vec2": Vec2, "c_float": c_float, "c_bool": c_bool, None: None}
+for _name, (_res, _args) in _JA.items():
+    B2_FUNCTIONS[_name] = (_NAMES[_res], [_NAMES[a] for a in _args])
 
 # the additive f2d* extension (product + emulation only)
 F2D_FUNCTIONS = {

@@ -4,6 +4,7 @@
 //   * tests/emu/f2d_emu.cpp           (test-only host emulation of the same step code, never shipped)
 // The including TU provides the backend hooks declared below.
 #include "f2d_image.h"
+#include "f2d_mutate.h"
 #include "f2d_step.h"
 
 #include "../../include/forge2d_b200.h"
@@ -1039,6 +1040,8 @@ bool b2Joint_IsValid( b2JointId id )
 	return j.jointId == index && j.generation == id.generation;
 }
 
+#include "f2d_capi_ext.inl"
+
 // ---- diagnostics -----------------------------------------------------------------------------------------------
 int f2dHasDevice( void )
 {
@@ -1401,14 +1404,54 @@ int f2dDebug_Joints( b2WorldId id, f2dJointRecord* out, int cap )
 			r->bodyIdA = j.edges[0].bodyId;
 			r->bodyIdB = j.edges[1].bodyId;
 			r->islandId = j.islandId;
-			if ( j.type == kRevoluteJoint )
+			switch ( j.type )
 			{
-				r->impulse[0] = s.revolute.linearImpulse.x;
-				r->impulse[1] = s.revolute.linearImpulse.y;
-				r->impulse[2] = s.revolute.springImpulse;
-				r->impulse[3] = s.revolute.motorImpulse;
-				r->impulse[4] = s.revolute.lowerImpulse;
-				r->impulse[5] = s.revolute.upperImpulse;
+				case kRevoluteJoint:
+					r->impulse[0] = s.revolute.linearImpulse.x;
+					r->impulse[1] = s.revolute.linearImpulse.y;
+					r->impulse[2] = s.revolute.springImpulse;
+					r->impulse[3] = s.revolute.motorImpulse;
+					r->impulse[4] = s.revolute.lowerImpulse;
+					r->impulse[5] = s.revolute.upperImpulse;
+					break;
+				case kDistanceJoint:
+					r->impulse[0] = s.distance.impulse;
+					r->impulse[1] = s.distance.lowerImpulse;
+					r->impulse[2] = s.distance.upperImpulse;
+					r->impulse[3] = s.distance.motorImpulse;
+					break;
+				case kMotorJoint:
+					r->impulse[0] = s.motor.linearImpulse.x;
+					r->impulse[1] = s.motor.linearImpulse.y;
+					r->impulse[2] = s.motor.angularImpulse;
+					break;
+				case kMouseJoint:
+					r->impulse[0] = s.mouse.linearImpulse.x;
+					r->impulse[1] = s.mouse.linearImpulse.y;
+					r->impulse[2] = s.mouse.angularImpulse;
+					break;
+				case kPrismaticJoint:
+					r->impulse[0] = s.prismatic.impulse.x;
+					r->impulse[1] = s.prismatic.impulse.y;
+					r->impulse[2] = s.prismatic.springImpulse;
+					r->impulse[3] = s.prismatic.motorImpulse;
+					r->impulse[4] = s.prismatic.lowerImpulse;
+					r->impulse[5] = s.prismatic.upperImpulse;
+					break;
+				case kWeldJoint:
+					r->impulse[0] = s.weld.linearImpulse.x;
+					r->impulse[1] = s.weld.linearImpulse.y;
+					r->impulse[2] = s.weld.angularImpulse;
+					break;
+				case kWheelJoint:
+					r->impulse[0] = s.wheel.perpImpulse;
+					r->impulse[1] = s.wheel.motorImpulse;
+					r->impulse[2] = s.wheel.springImpulse;
+					r->impulse[3] = s.wheel.lowerImpulse;
+					r->impulse[4] = s.wheel.upperImpulse;
+					break;
+				default:
+					break;
 			}
 		}
 		n += 1;

@@ -1,0 +1,1131 @@
+// forge2d_b200 — the rest of the b2* surface forge2d's FFI backend binds: body / shape / joint accessors
+// and mutators, destruction, the seven other joint types. Included by f2d_capi.inl inside its extern "C" block.
+// Everything here edits or reads the HOST image (see hostImage / mutableImage): the next b2World_Step uploads it.
+// Reference behaviour is cited per function (B2 = packages/forge2d/third_party/box2d/src).
+
+// ---------------------------------------------------------------------------------------------------------------- bodies
+static BodySim* simOf( HostWorld* hw, const Body* b ) { return ptr( hw->img, hw->img->sims ) + b->id; }
+static BodyState* stateOf( HostWorld* hw, const Body* b )
+{
+	return b->setIndex == kAwakeSet ? ptr( hw->img, hw->img->states ) + b->localIndex : nullptr;
+}
+// Mutators refuse to run while a step is in flight (world.c:62-74 b2GetWorldLocked)
+static Body* writableBody( b2BodyId id, HostWorld** hw )
+{
+	Body* b = bodyFromId( id, hw, true );
+	if ( b == nullptr || ( *hw )->img->locked )
+		return nullptr;
+	return b;
+}
+
+void b2DestroyBody( b2BodyId bodyId ) // body.c:343-444
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	destroyBody( hw->img, b->id );
+}
+b2Vec2 b2Body_GetLocalPoint( b2BodyId bodyId, b2Vec2 worldPoint ) // body.c:656-662
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	Xf t = simOf( hw, b )->transform;
+	V2 r = invRotate( t.q, sub( V2{ worldPoint.x, worldPoint.y }, t.p ) );
+	return b2Vec2{ r.x, r.y };
+}
+b2Vec2 b2Body_GetWorldPoint( b2BodyId bodyId, b2Vec2 localPoint ) // body.c:664-670
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	V2 r = xfPoint( simOf( hw, b )->transform, V2{ localPoint.x, localPoint.y } );
+	return b2Vec2{ r.x, r.y };
+}
+b2Vec2 b2Body_GetLocalVector( b2BodyId bodyId, b2Vec2 worldVector ) // body.c:672-678
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	V2 r = invRotate( simOf( hw, b )->transform.q, V2{ worldVector.x, worldVector.y } );
+	return b2Vec2{ r.x, r.y };
+}
+b2Vec2 b2Body_GetWorldVector( b2BodyId bodyId, b2Vec2 localVector ) // body.c:680-686
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return b2Vec2{ 0, 0 };
+	V2 r = rotate( simOf( hw, b )->transform.q, V2{ localVector.x, localVector.y } );
+	return b2Vec2{ r.x, r.y };
+}
+void b2Body_SetTransform( b2BodyId bodyId, b2Vec2 position, b2Rot rotation ) // body.c:688-741
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	setBodyTransform( hw->img, *b, V2{ position.x, position.y }, Rot{ rotation.c, rotation.s } );
+}
+void b2Body_ApplyForce( b2BodyId bodyId, b2Vec2 force, b2Vec2 point, bool wake ) // body.c:900-916
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+	{
+		BodySim* s = simOf( hw, b );
+		V2 f = { force.x, force.y };
+		s->force = add( s->force, f );
+		s->torque += cross( sub( V2{ point.x, point.y }, s->center ), f );
+	}
+}
+void b2Body_ApplyForceToCenter( b2BodyId bodyId, b2Vec2 force, bool wake ) // body.c:918-933
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+	{
+		BodySim* s = simOf( hw, b );
+		s->force = add( s->force, V2{ force.x, force.y } );
+	}
+}
+void b2Body_ApplyTorque( b2BodyId bodyId, float torque, bool wake ) // body.c:935-950
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+		simOf( hw, b )->torque += torque;
+}
+void b2Body_ApplyLinearImpulse( b2BodyId bodyId, b2Vec2 impulse, b2Vec2 point, bool wake ) // body.c:952-973
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+	{
+		BodyState* st = stateOf( hw, b );
+		BodySim* s = simOf( hw, b );
+		V2 P = { impulse.x, impulse.y };
+		st->v = mulAdd( st->v, s->invMass, P );
+		st->w += s->invInertia * cross( sub( V2{ point.x, point.y }, s->center ), P );
+		limitVelocity( *st, hw->img->maxLinearSpeed );
+	}
+}
+void b2Body_ApplyLinearImpulseToCenter( b2BodyId bodyId, b2Vec2 impulse, bool wake ) // body.c:975-995
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+	{
+		BodyState* st = stateOf( hw, b );
+		st->v = mulAdd( st->v, simOf( hw, b )->invMass, V2{ impulse.x, impulse.y } );
+		limitVelocity( *st, hw->img->maxLinearSpeed );
+	}
+}
+void b2Body_ApplyAngularImpulse( b2BodyId bodyId, float impulse, bool wake ) // body.c:997-1020
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	if ( wake && b->setIndex >= kFirstSleepingSet )
+		wakeBody( hw->img, *b );
+	if ( b->setIndex == kAwakeSet )
+		stateOf( hw, b )->w += simOf( hw, b )->invInertia * impulse;
+}
+void b2Body_SetName( b2BodyId bodyId, const char* name ) // body.c:1286-1304
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	memset( b->name, 0, sizeof( b->name ) );
+	if ( name != nullptr )
+	{
+		for ( int i = 0; i < 31 && name[i] != 0; ++i )
+			b->name[i] = name[i];
+	}
+}
+const char* b2Body_GetName( b2BodyId bodyId ) // body.c:1306-1311 (pointer into the world's memory, valid until the next call)
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->name : "";
+}
+void b2Body_SetUserData( b2BodyId bodyId, void* userData )
+{
+	Body* b = bodyFromId( bodyId, nullptr, true );
+	if ( b )
+		b->userData = (uint64_t)(uintptr_t)userData;
+}
+void* b2Body_GetUserData( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? (void*)(uintptr_t)b->userData : nullptr;
+}
+void b2Body_SetMassData( b2BodyId bodyId, b2MassData massData ) // body.c:1357-1382
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	BodySim* s = simOf( hw, b );
+	b->mass = massData.mass;
+	b->inertia = massData.rotationalInertia;
+	s->localCenter = V2{ massData.center.x, massData.center.y };
+	V2 center = xfPoint( s->transform, s->localCenter );
+	s->center = center;
+	s->center0 = center;
+	s->invMass = b->mass > 0.0f ? 1.0f / b->mass : 0.0f;
+	s->invInertia = b->inertia > 0.0f ? 1.0f / b->inertia : 0.0f;
+}
+b2MassData b2Body_GetMassData( b2BodyId bodyId ) // body.c:1384-1391
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	b2MassData m = { 0.0f, { 0.0f, 0.0f }, 0.0f };
+	if ( b )
+	{
+		const BodySim* s = simOf( hw, b );
+		m.mass = b->mass;
+		m.center = b2Vec2{ s->localCenter.x, s->localCenter.y };
+		m.rotationalInertia = b->inertia;
+	}
+	return m;
+}
+void b2Body_ApplyMassFromShapes( b2BodyId bodyId ) // body.c:1393-1403
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b )
+		updateBodyMassData( hw->img, *b );
+}
+void b2Body_SetLinearDamping( b2BodyId bodyId, float linearDamping ) // body.c:1405-1418
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b )
+		simOf( hw, b )->linearDamping = linearDamping;
+}
+float b2Body_GetLinearDamping( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	return b ? simOf( hw, b )->linearDamping : 0.0f;
+}
+void b2Body_SetAngularDamping( b2BodyId bodyId, float angularDamping ) // body.c:1428-1441
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b )
+		simOf( hw, b )->angularDamping = angularDamping;
+}
+float b2Body_GetAngularDamping( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	return b ? simOf( hw, b )->angularDamping : 0.0f;
+}
+void b2Body_SetGravityScale( b2BodyId bodyId, float gravityScale ) // body.c:1451-1465
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b )
+		simOf( hw, b )->gravityScale = gravityScale;
+}
+float b2Body_GetGravityScale( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	return b ? simOf( hw, b )->gravityScale : 0.0f;
+}
+void b2Body_SetAwake( b2BodyId bodyId, bool awake ) // body.c:1483-1508
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	World* w = hw->img;
+	if ( awake && b->setIndex >= kFirstSleepingSet )
+	{
+		wakeBody( w, *b );
+	}
+	else if ( awake == false && b->setIndex == kAwakeSet )
+	{
+		int islandId = b->islandId;
+		if ( ptr( w, w->islands )[islandId].constraintRemoveCount > 0 )
+			splitIsland( w, islandId );
+		// splitting relabels the body (the island it started in is gone)
+		trySleepIsland( w, ptr( w, w->bodies )[bodyId.index1 - 1].islandId );
+	}
+}
+bool b2Body_IsEnabled( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->setIndex != kDisabledSet : false;
+}
+bool b2Body_IsSleepEnabled( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->enableSleep : false;
+}
+void b2Body_SetSleepThreshold( b2BodyId bodyId, float sleepThreshold )
+{
+	Body* b = bodyFromId( bodyId, nullptr, true );
+	if ( b )
+		b->sleepThreshold = sleepThreshold;
+}
+float b2Body_GetSleepThreshold( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->sleepThreshold : 0.0f;
+}
+void b2Body_EnableSleep( b2BodyId bodyId, bool enableSleep ) // body.c:1538-1553
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	b->enableSleep = enableSleep;
+	if ( enableSleep == false )
+		wakeBody( hw->img, *b );
+}
+void b2Body_SetFixedRotation( b2BodyId bodyId, bool flag ) // body.c:1722-1742
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr || b->fixedRotation == flag )
+		return;
+	b->fixedRotation = flag;
+	BodyState* st = stateOf( hw, b );
+	if ( st )
+		st->w = 0.0f;
+	updateBodyMassData( hw->img, *b );
+}
+bool b2Body_IsFixedRotation( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->fixedRotation : false;
+}
+void b2Body_SetBullet( b2BodyId bodyId, bool flag ) // body.c:1751-1762
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b )
+		simOf( hw, b )->isBullet = flag;
+}
+bool b2Body_IsBullet( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	return b ? simOf( hw, b )->isBullet : false;
+}
+static void growEventArrays( HostWorld* hw )
+{
+	reserve( *hw, 0, 0, 0, 0 ); // event arrays grow with the first event-enabled shape
+}
+void b2Body_EnableContactEvents( b2BodyId bodyId, bool flag ) // body.c:1772-1783
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	World* w = hw->img;
+	for ( int s = b->headShapeId; s != kNull; s = ptr( w, w->shapes )[s].nextShapeId )
+	{
+		Shape& shape = ptr( w, w->shapes )[s];
+		if ( flag && shape.enableContactEvents == false )
+			w->contactEventCapable += 1;
+		shape.enableContactEvents = flag;
+	}
+	growEventArrays( hw );
+}
+void b2Body_EnableHitEvents( b2BodyId bodyId, bool flag ) // body.c:1785-1796
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, true );
+	if ( b == nullptr )
+		return;
+	World* w = hw->img;
+	for ( int s = b->headShapeId; s != kNull; s = ptr( w, w->shapes )[s].nextShapeId )
+	{
+		Shape& shape = ptr( w, w->shapes )[s];
+		if ( flag && shape.enableHitEvents == false )
+			w->hitEventCapable += 1;
+		shape.enableHitEvents = flag;
+	}
+	growEventArrays( hw );
+}
+b2WorldId b2Body_GetWorld( b2BodyId bodyId ) // body.c:1798-1802
+{
+	HostWorld* hw = worldFromIndex0( bodyId.world0 );
+	return hw ? b2WorldId{ (uint16_t)( bodyId.world0 + 1 ), hw->generation } : b2WorldId{ 0, 0 };
+}
+int b2Body_GetShapes( b2BodyId bodyId, b2ShapeId* shapeArray, int capacity ) // body.c:1811-1828
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return 0;
+	World* w = hw->img;
+	int n = 0;
+	for ( int s = b->headShapeId; s != kNull && n < capacity; s = ptr( w, w->shapes )[s].nextShapeId )
+	{
+		const Shape& shape = ptr( w, w->shapes )[s];
+		shapeArray[n++] = b2ShapeId{ shape.id + 1, bodyId.world0, shape.generation };
+	}
+	return n;
+}
+int b2Body_GetJointCount( b2BodyId bodyId )
+{
+	Body* b = bodyFromId( bodyId, nullptr, false );
+	return b ? b->jointCount : 0;
+}
+int b2Body_GetJoints( b2BodyId bodyId, b2JointId* jointArray, int capacity ) // body.c:1837-1859
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromId( bodyId, &hw, false );
+	if ( b == nullptr )
+		return 0;
+	World* w = hw->img;
+	int n = 0;
+	int key = b->headJointKey;
+	while ( key != kNull && n < capacity )
+	{
+		const Joint& j = ptr( w, w->joints )[key >> 1];
+		jointArray[n++] = b2JointId{ ( key >> 1 ) + 1, bodyId.world0, j.generation };
+		key = j.edges[key & 1].nextKey;
+	}
+	return n;
+}
+// body.c:1036-1284 / :1557-1720. Moving a body between the static / awake / disabled sets re-homes its joints through the
+// constraint graph; that bookkeeping is not on the image path yet, so the calls fail loudly instead of approximating.
+void b2Body_SetType( b2BodyId bodyId, b2BodyType type )
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr || b->type == (int)type )
+		return;
+	reportError( "b2Body_SetType: changing a body's type after creation is not supported by forge2d_b200 yet" );
+	setError( hw->img, kErrUnsupported, __LINE__ );
+}
+void b2Body_Disable( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr || b->setIndex == kDisabledSet )
+		return;
+	reportError( "b2Body_Disable: disabling a body after creation is not supported by forge2d_b200 yet" );
+	setError( hw->img, kErrUnsupported, __LINE__ );
+}
+void b2Body_Enable( b2BodyId bodyId )
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr || b->setIndex != kDisabledSet )
+		return;
+	reportError( "b2Body_Enable: enabling a disabled body is not supported by forge2d_b200 yet" );
+	setError( hw->img, kErrUnsupported, __LINE__ );
+}
+
+// ---------------------------------------------------------------------------------------------------------------- shapes
+static Shape* writableShape( b2ShapeId id, HostWorld** hw )
+{
+	Shape* s = shapeFromId( id, hw );
+	if ( s == nullptr || ( *hw )->img->locked )
+		return nullptr;
+	int index = s->id;
+	mutableImage( **hw );
+	return ptr( ( *hw )->img, ( *hw )->img->shapes ) + index;
+}
+void b2DestroyShape( b2ShapeId shapeId, bool updateBodyMass ) // shape.c:318-337
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		destroyShape( hw->img, s->id, updateBodyMass );
+}
+b2WorldId b2Shape_GetWorld( b2ShapeId shapeId )
+{
+	HostWorld* hw = worldFromIndex0( shapeId.world0 );
+	return hw ? b2WorldId{ (uint16_t)( shapeId.world0 + 1 ), hw->generation } : b2WorldId{ 0, 0 };
+}
+void b2Shape_SetUserData( b2ShapeId shapeId, void* userData )
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		s->userData = (uint64_t)(uintptr_t)userData;
+}
+void* b2Shape_GetUserData( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? (void*)(uintptr_t)s->userData : nullptr;
+}
+bool b2Shape_IsSensor( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->sensorIndex != kNull : false;
+}
+bool b2Shape_TestPoint( b2ShapeId shapeId, b2Vec2 point ) // shape.c:979-1002
+{
+	HostWorld* hw = nullptr;
+	Shape* s = shapeFromId( shapeId, &hw );
+	if ( s == nullptr )
+		return false;
+	Xf t = ptr( hw->img, hw->img->sims )[s->bodyId].transform;
+	V2 local = invRotate( t.q, sub( V2{ point.x, point.y }, t.p ) );
+	return pointInShape( *s, local );
+}
+void b2Shape_SetDensity( b2ShapeId shapeId, float density, bool updateBodyMass ) // shape.c:1055-1079
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s == nullptr || density == s->density )
+		return;
+	s->density = density;
+	if ( updateBodyMass )
+		updateBodyMassData( hw->img, ptr( hw->img, hw->img->bodies )[s->bodyId] );
+}
+float b2Shape_GetDensity( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->density : 0.0f;
+}
+void b2Shape_SetFriction( b2ShapeId shapeId, float friction ) // shape.c:1088-1101
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		s->friction = friction;
+}
+float b2Shape_GetFriction( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->friction : 0.0f;
+}
+void b2Shape_SetRestitution( b2ShapeId shapeId, float restitution ) // shape.c:1110-1123
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		s->restitution = restitution;
+}
+float b2Shape_GetRestitution( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->restitution : 0.0f;
+}
+b2Filter b2Shape_GetFilter( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? b2Filter{ s->filter.category, s->filter.mask, s->filter.group } : b2Filter{ 0, 0, 0 };
+}
+void b2Shape_SetFilter( b2ShapeId shapeId, b2Filter filter ) // shape.c:1235-1261
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s == nullptr )
+		return;
+	if ( filter.maskBits == s->filter.mask && filter.categoryBits == s->filter.category && filter.groupIndex == s->filter.group )
+		return;
+	bool destroyProxy = filter.categoryBits != s->filter.category;
+	s->filter = Filter{ filter.categoryBits, filter.maskBits, filter.groupIndex };
+	resetProxy( hw->img, *s, true, destroyProxy );
+}
+void b2Shape_EnableSensorEvents( b2ShapeId shapeId, bool flag ) // shape.c:1263-1273
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		s->enableSensorEvents = flag;
+}
+bool b2Shape_AreSensorEventsEnabled( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->enableSensorEvents : false;
+}
+void b2Shape_EnableContactEvents( b2ShapeId shapeId, bool flag ) // shape.c:1282-1292
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s == nullptr )
+		return;
+	if ( flag && s->enableContactEvents == false )
+		hw->img->contactEventCapable += 1;
+	s->enableContactEvents = flag;
+	growEventArrays( hw );
+}
+bool b2Shape_AreContactEventsEnabled( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->enableContactEvents : false;
+}
+void b2Shape_EnablePreSolveEvents( b2ShapeId shapeId, bool flag ) // shape.c:1301-1311
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s )
+		s->enablePreSolveEvents = flag;
+}
+bool b2Shape_ArePreSolveEventsEnabled( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->enablePreSolveEvents : false;
+}
+void b2Shape_EnableHitEvents( b2ShapeId shapeId, bool flag ) // shape.c:1320-1330
+{
+	HostWorld* hw = nullptr;
+	Shape* s = writableShape( shapeId, &hw );
+	if ( s == nullptr )
+		return;
+	if ( flag && s->enableHitEvents == false )
+		hw->img->hitEventCapable += 1;
+	s->enableHitEvents = flag;
+	growEventArrays( hw );
+}
+bool b2Shape_AreHitEventsEnabled( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? s->enableHitEvents : false;
+}
+b2ShapeType b2Shape_GetType( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	return s ? (b2ShapeType)s->type : b2_circleShape;
+}
+b2Circle b2Shape_GetCircle( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	b2Circle c = { { 0, 0 }, 0 };
+	if ( s && s->type == kCircle )
+		c = b2Circle{ { s->circle.center.x, s->circle.center.y }, s->circle.radius };
+	return c;
+}
+b2Segment b2Shape_GetSegment( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	b2Segment g = { { 0, 0 }, { 0, 0 } };
+	if ( s && s->type == kSegment )
+		g = b2Segment{ { s->segment.p1.x, s->segment.p1.y }, { s->segment.p2.x, s->segment.p2.y } };
+	return g;
+}
+b2ChainSegment b2Shape_GetChainSegment( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	b2ChainSegment g;
+	memset( &g, 0, sizeof( g ) );
+	if ( s && s->type == kChainSegment )
+	{
+		const ChainSegment& c = s->chainSegment;
+		g.ghost1 = b2Vec2{ c.ghost1.x, c.ghost1.y };
+		g.segment = b2Segment{ { c.segment.p1.x, c.segment.p1.y }, { c.segment.p2.x, c.segment.p2.y } };
+		g.ghost2 = b2Vec2{ c.ghost2.x, c.ghost2.y };
+		g.chainId = c.chainId;
+	}
+	return g;
+}
+b2Capsule b2Shape_GetCapsule( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	b2Capsule c = { { 0, 0 }, { 0, 0 }, 0 };
+	if ( s && s->type == kCapsule )
+		c = b2Capsule{ { s->capsule.c1.x, s->capsule.c1.y }, { s->capsule.c2.x, s->capsule.c2.y }, s->capsule.radius };
+	return c;
+}
+b2Polygon b2Shape_GetPolygon( b2ShapeId shapeId )
+{
+	Shape* s = shapeFromId( shapeId, nullptr );
+	b2Polygon p;
+	memset( &p, 0, sizeof( p ) );
+	if ( s && s->type == kPolygon )
+		memcpy( &p, &s->polygon, sizeof( p ) );
+	return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- joints
+static Joint* jointFromId( b2JointId id, HostWorld** outWorld, bool forWrite )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return nullptr;
+	World* w = forWrite ? mutableImage( *hw ) : hostImage( *hw );
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= w->joints.count )
+		return nullptr;
+	Joint* j = ptr( w, w->joints ) + index;
+	if ( j->jointId != index || j->generation != id.generation )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return j;
+}
+// joint.c:122-144 b2GetJointSimCheckType (a type mismatch is an assert there; here the accessor becomes a no-op)
+static JointSim* jointSimOfType( b2JointId id, int type, HostWorld** outWorld, bool forWrite )
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( id, &hw, forWrite );
+	if ( j == nullptr || j->type != type )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return ptr( hw->img, hw->img->jointSims ) + j->jointId;
+}
+static b2BodyId makeBodyId( World* w, int bodyId )
+{
+	return b2BodyId{ bodyId + 1, w->worldId, ptr( w, w->bodies )[bodyId].generation };
+}
+void b2DestroyJoint( b2JointId jointId ) // joint.c:809-822
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, true );
+	if ( j == nullptr || hw->img->locked )
+		return;
+	destroyJointInternal( hw->img, j->jointId, true );
+}
+b2JointType b2Joint_GetType( b2JointId jointId )
+{
+	Joint* j = jointFromId( jointId, nullptr, false );
+	return j ? (b2JointType)j->type : b2_distanceJoint;
+}
+b2BodyId b2Joint_GetBodyA( b2JointId jointId )
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	return j ? makeBodyId( hw->img, j->edges[0].bodyId ) : b2BodyId{ 0, 0, 0 };
+}
+b2BodyId b2Joint_GetBodyB( b2JointId jointId )
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	return j ? makeBodyId( hw->img, j->edges[1].bodyId ) : b2BodyId{ 0, 0, 0 };
+}
+b2WorldId b2Joint_GetWorld( b2JointId jointId )
+{
+	HostWorld* hw = worldFromIndex0( jointId.world0 );
+	return hw ? b2WorldId{ (uint16_t)( jointId.world0 + 1 ), hw->generation } : b2WorldId{ 0, 0 };
+}
+b2Vec2 b2Joint_GetLocalAnchorA( b2JointId jointId )
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	if ( j == nullptr )
+		return b2Vec2{ 0, 0 };
+	V2 a = ptr( hw->img, hw->img->jointSims )[j->jointId].localOriginAnchorA;
+	return b2Vec2{ a.x, a.y };
+}
+b2Vec2 b2Joint_GetLocalAnchorB( b2JointId jointId )
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	if ( j == nullptr )
+		return b2Vec2{ 0, 0 };
+	V2 a = ptr( hw->img, hw->img->jointSims )[j->jointId].localOriginAnchorB;
+	return b2Vec2{ a.x, a.y };
+}
+void b2Joint_SetLocalAnchorA( b2JointId jointId, b2Vec2 localAnchor ) // joint.c:851-859
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, true );
+	if ( j )
+		ptr( hw->img, hw->img->jointSims )[j->jointId].localOriginAnchorA = V2{ localAnchor.x, localAnchor.y };
+}
+void b2Joint_SetLocalAnchorB( b2JointId jointId, b2Vec2 localAnchor ) // joint.c:869-877
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, true );
+	if ( j )
+		ptr( hw->img, hw->img->jointSims )[j->jointId].localOriginAnchorB = V2{ localAnchor.x, localAnchor.y };
+}
+void b2Joint_SetCollideConnected( b2JointId jointId, bool shouldCollide ) // joint.c:979-1022
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, true );
+	if ( j == nullptr || hw->img->locked || j->collideConnected == shouldCollide )
+		return;
+	World* w = hw->img;
+	j->collideConnected = shouldCollide;
+	const Body& bodyA = ptr( w, w->bodies )[j->edges[0].bodyId];
+	const Body& bodyB = ptr( w, w->bodies )[j->edges[1].bodyId];
+	if ( shouldCollide )
+	{
+		// the broadphase must look for pairs again: re-buffer the proxies of the body with fewer shapes
+		int shapeId = bodyA.shapeCount < bodyB.shapeCount ? bodyA.headShapeId : bodyB.headShapeId;
+		while ( shapeId != kNull )
+		{
+			const Shape& shape = ptr( w, w->shapes )[shapeId];
+			if ( shape.proxyKey != kNull )
+				bufferMove( w, shape.proxyKey );
+			shapeId = shape.nextShapeId;
+		}
+	}
+	else
+	{
+		destroyContactsBetweenBodies( w, j->edges[0].bodyId, j->edges[1].bodyId );
+	}
+}
+bool b2Joint_GetCollideConnected( b2JointId jointId )
+{
+	Joint* j = jointFromId( jointId, nullptr, false );
+	return j ? j->collideConnected : false;
+}
+void b2Joint_SetUserData( b2JointId jointId, void* userData )
+{
+	Joint* j = jointFromId( jointId, nullptr, true );
+	if ( j )
+		j->userData = (uint64_t)(uintptr_t)userData;
+}
+void* b2Joint_GetUserData( b2JointId jointId )
+{
+	Joint* j = jointFromId( jointId, nullptr, false );
+	return j ? (void*)(uintptr_t)j->userData : nullptr;
+}
+void b2Joint_WakeBodies( b2JointId jointId ) // joint.c:1045-1059
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, true );
+	if ( j == nullptr || hw->img->locked )
+		return;
+	World* w = hw->img;
+	int idA = j->edges[0].bodyId, idB = j->edges[1].bodyId;
+	wakeBody( w, ptr( w, w->bodies )[idA] );
+	wakeBody( w, ptr( w, w->bodies )[idB] );
+}
+b2Vec2 b2Joint_GetConstraintForce( b2JointId jointId ) // joint.c:1061-1097 and the b2Get*JointForce of each type
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	if ( j == nullptr )
+		return b2Vec2{ 0, 0 };
+	World* w = hw->img;
+	const JointSim& s = ptr( w, w->jointSims )[j->jointId];
+	const BodySim* sims = ptr( w, w->sims );
+	const float inv_h = w->inv_h;
+	V2 f = { 0.0f, 0.0f };
+	switch ( j->type )
+	{
+		case kDistanceJoint:
+		{
+			V2 pA = xfPoint( sims[s.bodyIdA].transform, s.localOriginAnchorA );
+			V2 pB = xfPoint( sims[s.bodyIdB].transform, s.localOriginAnchorB );
+			V2 axis = normalize( sub( pB, pA ) );
+			const DistanceJointData& d = s.distance;
+			float force = ( d.impulse + d.lowerImpulse - d.upperImpulse + d.motorImpulse ) * inv_h;
+			f = mulSV( force, axis );
+			break;
+		}
+		case kMotorJoint:
+			f = mulSV( inv_h, s.motor.linearImpulse );
+			break;
+		case kMouseJoint:
+			f = mulSV( inv_h, s.mouse.linearImpulse );
+			break;
+		case kPrismaticJoint:
+		{
+			V2 axisA = rotate( sims[s.bodyIdA].transform.q, s.prismatic.localAxisA );
+			V2 perpA = leftPerp( axisA );
+			float perpForce = inv_h * s.prismatic.impulse.x;
+			float axialForce = inv_h * ( s.prismatic.motorImpulse + s.prismatic.lowerImpulse - s.prismatic.upperImpulse );
+			f = add( mulSV( perpForce, perpA ), mulSV( axialForce, axisA ) );
+			break;
+		}
+		case kRevoluteJoint:
+			f = mulSV( inv_h, s.revolute.linearImpulse );
+			break;
+		case kWeldJoint:
+			f = mulSV( inv_h, s.weld.linearImpulse );
+			break;
+		case kWheelJoint:
+		{
+			V2 axisA = s.wheel.axisA;
+			V2 perpA = leftPerp( axisA );
+			float perpForce = inv_h * s.wheel.perpImpulse;
+			float axialForce = inv_h * ( s.wheel.springImpulse + s.wheel.lowerImpulse - s.wheel.upperImpulse );
+			f = add( mulSV( perpForce, perpA ), mulSV( axialForce, axisA ) );
+			break;
+		}
+		default:
+			break;
+	}
+	return b2Vec2{ f.x, f.y };
+}
+float b2Joint_GetConstraintTorque( b2JointId jointId ) // joint.c:1099-1135
+{
+	HostWorld* hw = nullptr;
+	Joint* j = jointFromId( jointId, &hw, false );
+	if ( j == nullptr )
+		return 0.0f;
+	World* w = hw->img;
+	const JointSim& s = ptr( w, w->jointSims )[j->jointId];
+	const float inv_h = w->inv_h;
+	switch ( j->type )
+	{
+		case kMotorJoint:
+			return inv_h * s.motor.angularImpulse;
+		case kMouseJoint:
+			return inv_h * s.mouse.angularImpulse;
+		case kPrismaticJoint:
+			return inv_h * s.prismatic.impulse.y;
+		case kRevoluteJoint:
+			return inv_h * ( s.revolute.motorImpulse + s.revolute.lowerImpulse - s.revolute.upperImpulse );
+		case kWeldJoint:
+			return inv_h * s.weld.angularImpulse;
+		case kWheelJoint:
+			return inv_h * s.wheel.motorImpulse;
+		default:
+			return 0.0f;
+	}
+}
+
+// ---- creation of the other joint types: joint.c:353-700 ------------------------------------------------------------
+b2DistanceJointDef b2DefaultDistanceJointDef( void ) // joint.c:24-31
+{
+	b2DistanceJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.length = 1.0f;
+	def.maxLength = kHuge;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2MotorJointDef b2DefaultMotorJointDef( void ) // joint.c:33-41
+{
+	b2MotorJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.maxForce = 1.0f;
+	def.maxTorque = 1.0f;
+	def.correctionFactor = 0.3f;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2MouseJointDef b2DefaultMouseJointDef( void ) // joint.c:43-51
+{
+	b2MouseJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.hertz = 4.0f;
+	def.dampingRatio = 1.0f;
+	def.maxForce = 1.0f;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2FilterJointDef b2DefaultFilterJointDef( void ) // joint.c:53-58
+{
+	b2FilterJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2PrismaticJointDef b2DefaultPrismaticJointDef( void ) // joint.c:60-66
+{
+	b2PrismaticJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.localAxisA = b2Vec2{ 1.0f, 0.0f };
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2WeldJointDef b2DefaultWeldJointDef( void ) // joint.c:76-81
+{
+	b2WeldJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2WheelJointDef b2DefaultWheelJointDef( void ) // joint.c:83-92
+{
+	b2WheelJointDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.localAxisA.y = 1.0f;
+	def.enableSpring = true;
+	def.hertz = 1.0f;
+	def.dampingRatio = 0.7f;
+	def.internalValue = kSecretCookie;
+	return def;
+}
+b2ExplosionDef b2DefaultExplosionDef( void ) // joint.c:94-99
+{
+	b2ExplosionDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.maskBits = UINT64_MAX; // B2_DEFAULT_MASK_BITS
+	return def;
+}
+
+// Common head of every b2Create*Joint: validates, grows the image, creates the base joint (joint.c:146-311)
+struct JointCreation
+{
+	World* w;
+	int jointId;
+	JointSim* sim;
+};
+static bool beginJoint( b2WorldId worldId, int cookie, b2BodyId bodyIdA, b2BodyId bodyIdB, void* userData, float drawSize, int type,
+						bool collideConnected, JointCreation* out )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || cookie != kSecretCookie )
+		return false;
+	mutableImage( *hw );
+	reserve( *hw, 0, 0, 0, 2 );
+	World* w = hw->img;
+	if ( w->locked )
+		return false;
+	int a = bodyIdA.index1 - 1, b = bodyIdB.index1 - 1;
+	if ( a < 0 || b < 0 || a >= w->bodies.count || b >= w->bodies.count )
+		return false;
+	out->w = w;
+	out->jointId = createJointBase( w, a, b, (uint64_t)(uintptr_t)userData, drawSize, type, collideConnected );
+	out->sim = ptr( w, w->jointSims ) + out->jointId;
+	out->sim->type = type;
+	return true;
+}
+static b2JointId finishJoint( const JointCreation& c, bool collideConnected )
+{
+	if ( collideConnected == false )
+		destroyContactsBetweenBodies( c.w, c.sim->bodyIdA, c.sim->bodyIdB );
+	return b2JointId{ c.jointId + 1, c.w->worldId, ptr( c.w, c.w->joints )[c.jointId].generation };
+}
+b2JointId b2CreateDistanceJoint( b2WorldId worldId, const b2DistanceJointDef* def ) // joint.c:353-404
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kDistanceJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ def->localAnchorA.x, def->localAnchorA.y };
+	c.sim->localOriginAnchorB = V2{ def->localAnchorB.x, def->localAnchorB.y };
+	DistanceJointData& j = c.sim->distance;
+	memset( &j, 0, sizeof( j ) );
+	j.length = maxf( def->length, kLinearSlop );
+	j.hertz = def->hertz;
+	j.dampingRatio = def->dampingRatio;
+	j.minLength = maxf( def->minLength, kLinearSlop );
+	j.maxLength = maxf( def->minLength, def->maxLength );
+	j.maxMotorForce = def->maxMotorForce;
+	j.motorSpeed = def->motorSpeed;
+	j.enableSpring = def->enableSpring;
+	j.enableLimit = def->enableLimit;
+	j.enableMotor = def->enableMotor;
+	return finishJoint( c, def->collideConnected );
+}
+b2JointId b2CreateMotorJoint( b2WorldId worldId, const b2MotorJointDef* def ) // joint.c:406-442
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kMotorJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ 0.0f, 0.0f };
+	c.sim->localOriginAnchorB = V2{ 0.0f, 0.0f };
+	MotorJointData& j = c.sim->motor;
+	memset( &j, 0, sizeof( j ) );
+	j.linearOffset = V2{ def->linearOffset.x, def->linearOffset.y };
+	j.angularOffset = def->angularOffset;
+	j.maxForce = def->maxForce;
+	j.maxTorque = def->maxTorque;
+	j.correctionFactor = clampf( def->correctionFactor, 0.0f, 1.0f );
+	return finishJoint( c, def->collideConnected );
+}
+b2JointId b2CreateMouseJoint( b2WorldId worldId, const b2MouseJointDef* def ) // joint.c:444-478
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kMouseJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	const BodySim* sims = ptr( c.w, c.w->sims );
+	Xf xfA = sims[c.sim->bodyIdA].transform, xfB = sims[c.sim->bodyIdB].transform;
+	V2 target = { def->target.x, def->target.y };
+	c.sim->localOriginAnchorA = invRotate( xfA.q, sub( target, xfA.p ) );
+	c.sim->localOriginAnchorB = invRotate( xfB.q, sub( target, xfB.p ) );
+	MouseJointData& j = c.sim->mouse;
+	memset( &j, 0, sizeof( j ) );
+	j.targetA = target;
+	j.hertz = def->hertz;
+	j.dampingRatio = def->dampingRatio;
+	j.maxForce = def->maxForce;
+	return finishJoint( c, true ); // the reference never destroys contacts for a mouse joint (joint.c:444-478)
+}
+b2JointId b2CreateFilterJoint( b2WorldId worldId, const b2FilterJointDef* def ) // joint.c:480-505
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kFilterJoint, false, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ 0.0f, 0.0f };
+	c.sim->localOriginAnchorB = V2{ 0.0f, 0.0f };
+	return finishJoint( c, true ); // joint.c:480-505: no contact destruction here either
+}
+b2JointId b2CreatePrismaticJoint( b2WorldId worldId, const b2PrismaticJointDef* def ) // joint.c:559-607
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kPrismaticJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ def->localAnchorA.x, def->localAnchorA.y };
+	c.sim->localOriginAnchorB = V2{ def->localAnchorB.x, def->localAnchorB.y };
+	PrismaticJointData& j = c.sim->prismatic;
+	memset( &j, 0, sizeof( j ) );
+	j.localAxisA = normalize( V2{ def->localAxisA.x, def->localAxisA.y } );
+	j.referenceAngle = def->referenceAngle;
+	j.targetTranslation = def->targetTranslation;
+	j.hertz = def->hertz;
+	j.dampingRatio = def->dampingRatio;
+	j.lowerTranslation = def->lowerTranslation;
+	j.upperTranslation = def->upperTranslation;
+	j.maxMotorForce = def->maxMotorForce;
+	j.motorSpeed = def->motorSpeed;
+	j.enableSpring = def->enableSpring;
+	j.enableLimit = def->enableLimit;
+	j.enableMotor = def->enableMotor;
+	return finishJoint( c, def->collideConnected );
+}
+b2JointId b2CreateWeldJoint( b2WorldId worldId, const b2WeldJointDef* def ) // joint.c:609-649
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kWeldJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ def->localAnchorA.x, def->localAnchorA.y };
+	c.sim->localOriginAnchorB = V2{ def->localAnchorB.x, def->localAnchorB.y };
+	WeldJointData& j = c.sim->weld;
+	memset( &j, 0, sizeof( j ) );
+	j.referenceAngle = def->referenceAngle;
+	j.linearHertz = def->linearHertz;
+	j.linearDampingRatio = def->linearDampingRatio;
+	j.angularHertz = def->angularHertz;
+	j.angularDampingRatio = def->angularDampingRatio;
+	return finishJoint( c, def->collideConnected );
+}
+b2JointId b2CreateWheelJoint( b2WorldId worldId, const b2WheelJointDef* def ) // joint.c:651-700
+{
+	JointCreation c;
+	if ( beginJoint( worldId, def->internalValue, def->bodyIdA, def->bodyIdB, def->userData, 1.0f, kWheelJoint, def->collideConnected, &c ) == false )
+		return b2JointId{ 0, 0, 0 };
+	c.sim->localOriginAnchorA = V2{ def->localAnchorA.x, def->localAnchorA.y };
+	c.sim->localOriginAnchorB = V2{ def->localAnchorB.x, def->localAnchorB.y };
+	WheelJointData& j = c.sim->wheel;
+	memset( &j, 0, sizeof( j ) );
+	j.localAxisA = normalize( V2{ def->localAxisA.x, def->localAxisA.y } );
+	j.lowerTranslation = def->lowerTranslation;
+	j.upperTranslation = def->upperTranslation;
+	j.maxMotorTorque = def->maxMotorTorque;
+	j.motorSpeed = def->motorSpeed;
+	j.hertz = def->hertz;
+	j.dampingRatio = def->dampingRatio;
+	j.enableSpring = def->enableSpring;
+	j.enableLimit = def->enableLimit;
+	j.enableMotor = def->enableMotor;
+	return finishJoint( c, def->collideConnected );
+}
+
+#include "f2d_capi_joints.inl"

@@ -321,7 +321,120 @@ def jointed_piles(lib, chains=6, links=4, create=None, **world_kw):
     return Scene(lib, world, bodies, "jointed_piles_%d" % chains)
 
 
+def joint_zoo(lib, sets=3, create=None, **world_kw):
+    """Every joint type with its options exercised (springs, limits, motors, soft welds): `sets` copies side by side,
+    each a static anchor bar plus dynamic boxes / circles hanging, sliding, rolling or being dragged from it."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = [_static_segment(lib, world, (-60.0, -6.0), (60.0, -6.0))]
+    joints = []
+    sd = lib.b2DefaultShapeDef()
+    box = _box(lib, 0.3)
+    wheel = A.Circle(A.Vec2(0.0, 0.0), 0.35)
+
+    def dyn(x, y, shape="box", angle=0.0):
+        import math
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        bd.position = A.Vec2(_f32(x), _f32(y))
+        bd.rotation = A.Rot(_f32(math.cos(angle)), _f32(math.sin(angle)))
+        b = lib.b2CreateBody(world, C.byref(bd))
+        if shape == "box":
+            lib.b2CreatePolygonShape(b, C.byref(sd), C.byref(box))
+        else:
+            lib.b2CreateCircleShape(b, C.byref(sd), C.byref(wheel))
+        bodies.append(b)
+        return b
+
+    for k in range(sets):
+        x0 = -30.0 + 20.0 * k
+        bd = lib.b2DefaultBodyDef()
+        bd.position = A.Vec2(_f32(x0), 4.0)
+        anchor = lib.b2CreateBody(world, C.byref(bd))
+        bodies.append(anchor)
+        # distance: rigid rod, spring with limits, motorised spring
+        for i, (spring, limit, motor) in enumerate(((False, False, False), (True, True, False), (True, False, True))):
+            b = dyn(x0 - 6.0 + 1.5 * i, 2.0 - 0.2 * k)
+            d = lib.b2DefaultDistanceJointDef()
+            d.bodyIdA, d.bodyIdB = anchor, b
+            d.localAnchorA = A.Vec2(_f32(-6.0 + 1.5 * i), 0.0)
+            d.localAnchorB = A.Vec2(0.0, 0.25)
+            d.length = _f32(1.75 + 0.1 * k)
+            d.enableSpring, d.hertz, d.dampingRatio = spring, 2.0, 0.3
+            d.enableLimit, d.minLength, d.maxLength = limit, 1.5, 2.25
+            d.enableMotor, d.maxMotorForce, d.motorSpeed = motor, 40.0, _f32(0.5 - 0.25 * k)
+            joints.append(lib.b2CreateDistanceJoint(world, C.byref(d)))
+        # prismatic: limited slider with a spring, motorised slider on a tilted axis
+        for i, (spring, motor, axis) in enumerate(((True, False, (1.0, 0.0)), (False, True, (0.8, 0.6)))):
+            b = dyn(x0 - 1.0 + 2.0 * i, 3.0)
+            d = lib.b2DefaultPrismaticJointDef()
+            d.bodyIdA, d.bodyIdB = anchor, b
+            d.localAnchorA = A.Vec2(_f32(-1.0 + 2.0 * i), -1.0)
+            d.localAnchorB = A.Vec2(0.0, 0.0)
+            d.localAxisA = A.Vec2(*axis)
+            d.enableSpring, d.hertz, d.dampingRatio, d.targetTranslation = spring, 1.5, 0.2, 0.25
+            d.enableLimit, d.lowerTranslation, d.upperTranslation = True, -1.0, 1.25
+            d.enableMotor, d.maxMotorForce, d.motorSpeed = motor, 30.0, _f32(1.0 + 0.5 * k)
+            joints.append(lib.b2CreatePrismaticJoint(world, C.byref(d)))
+        # weld: rigid and soft (both frequencies)
+        prev = anchor
+        for i, (lh, ah) in enumerate(((0.0, 0.0), (3.0, 2.0), (0.0, 4.0))):
+            b = dyn(x0 + 3.0 + 0.7 * i, 4.0)
+            d = lib.b2DefaultWeldJointDef()
+            d.bodyIdA, d.bodyIdB = prev, b
+            d.localAnchorA = A.Vec2(3.0 if i == 0 else 0.35, 0.0)
+            d.localAnchorB = A.Vec2(-0.35, 0.0)
+            d.linearHertz, d.linearDampingRatio = lh, 0.5
+            d.angularHertz, d.angularDampingRatio = ah, 0.7
+            joints.append(lib.b2CreateWeldJoint(world, C.byref(d)))
+            prev = b
+        # wheel: a two-wheeled cart on the ground, spring suspension, one driven wheel, limits
+        chassis = dyn(x0, -4.9)
+        for i, side in enumerate((-0.6, 0.6)):
+            wb = dyn(x0 + side, -5.5, "wheel")
+            d = lib.b2DefaultWheelJointDef()
+            d.bodyIdA, d.bodyIdB = chassis, wb
+            d.localAnchorA = A.Vec2(side, -0.5)
+            d.localAnchorB = A.Vec2(0.0, 0.0)
+            d.localAxisA = A.Vec2(0.0, 1.0)
+            d.enableSpring, d.hertz, d.dampingRatio = True, 4.0, 0.7
+            d.enableLimit, d.lowerTranslation, d.upperTranslation = True, -0.25, 0.25
+            d.enableMotor, d.maxMotorTorque, d.motorSpeed = i == 0, 5.0, _f32(-3.0 - k)
+            joints.append(lib.b2CreateWheelJoint(world, C.byref(d)))
+        # motor joint holding a box at an offset from the anchor; mouse joint dragging a loose box; filter joint
+        b = dyn(x0 + 6.0, 2.5)
+        d = lib.b2DefaultMotorJointDef()
+        d.bodyIdA, d.bodyIdB = anchor, b
+        d.linearOffset = A.Vec2(6.0, -1.0)
+        d.angularOffset = _f32(0.25 * (k + 1))
+        d.maxForce, d.maxTorque, d.correctionFactor = 200.0, 20.0, 0.3
+        joints.append(lib.b2CreateMotorJoint(world, C.byref(d)))
+        b = dyn(x0 + 8.0, 1.0, angle=0.3)
+        d = lib.b2DefaultMouseJointDef()
+        d.bodyIdA, d.bodyIdB = anchor, b
+        d.target = A.Vec2(_f32(x0 + 7.5), 2.0)
+        d.hertz, d.dampingRatio, d.maxForce = 5.0, 0.7, 300.0
+        joints.append(lib.b2CreateMouseJoint(world, C.byref(d)))
+        b1, b2 = dyn(x0 - 8.0, -5.6), dyn(x0 - 8.1, -5.0)
+        d = lib.b2DefaultFilterJointDef()
+        d.bodyIdA, d.bodyIdB = b1, b2
+        joints.append(lib.b2CreateFilterJoint(world, C.byref(d)))
+        # revolute with spring + limit + motor for completeness
+        b = dyn(x0 + 9.5, 3.5)
+        d = lib.b2DefaultRevoluteJointDef()
+        d.bodyIdA, d.bodyIdB = anchor, b
+        d.localAnchorA = A.Vec2(9.5, 0.0)
+        d.localAnchorB = A.Vec2(0.0, 0.5)
+        d.enableSpring, d.hertz, d.dampingRatio = True, 1.0, 0.1
+        d.enableLimit, d.lowerAngle, d.upperAngle = True, -0.5, 0.75
+        d.enableMotor, d.maxMotorTorque, d.motorSpeed = True, 2.0, 1.0
+        joints.append(lib.b2CreateRevoluteJoint(world, C.byref(d)))
+    scene = Scene(lib, world, bodies, "joint_zoo_%d" % sets)
+    scene.joints = joints
+    return scene
+
+
 SCENES = {
+    "joint_zoo": joint_zoo,
     "bench2d": bench2d,
     "large_pyramid": large_pyramid,
     "many_pyramids": many_pyramids,

@@ -131,6 +131,95 @@ typedef struct b2RevoluteJointDef // types.h:760-826
 	int internalValue;
 } b2RevoluteJointDef;
 
+// collision.h:91-101, types.h:514-524, collision.h:56-70 + shape types (collision.h / types.h b2ShapeType)
+typedef struct b2MassData { float mass; b2Vec2 center; float rotationalInertia; } b2MassData;
+typedef enum b2ShapeType { b2_circleShape, b2_capsuleShape, b2_segmentShape, b2_polygonShape, b2_chainSegmentShape, b2_shapeTypeCount } b2ShapeType;
+typedef enum b2JointType
+{
+	b2_distanceJoint, b2_filterJoint, b2_motorJoint, b2_mouseJoint, b2_prismaticJoint, b2_revoluteJoint, b2_weldJoint, b2_wheelJoint
+} b2JointType;
+typedef struct b2ChainSegment { b2Vec2 ghost1; b2Segment segment; b2Vec2 ghost2; int chainId; } b2ChainSegment;
+
+// ---- joint definitions: types.h:526-900 ------------------------------------------------------------------------
+typedef struct b2DistanceJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 localAnchorA, localAnchorB;
+	float length;
+	bool enableSpring;
+	float hertz, dampingRatio;
+	bool enableLimit;
+	float minLength, maxLength;
+	bool enableMotor;
+	float maxMotorForce, motorSpeed;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2DistanceJointDef;
+typedef struct b2MotorJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 linearOffset;
+	float angularOffset, maxForce, maxTorque, correctionFactor;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2MotorJointDef;
+typedef struct b2MouseJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 target;
+	float hertz, dampingRatio, maxForce;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2MouseJointDef;
+typedef struct b2FilterJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	void* userData;
+	int internalValue;
+} b2FilterJointDef;
+typedef struct b2PrismaticJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 localAnchorA, localAnchorB, localAxisA;
+	float referenceAngle, targetTranslation;
+	bool enableSpring;
+	float hertz, dampingRatio;
+	bool enableLimit;
+	float lowerTranslation, upperTranslation;
+	bool enableMotor;
+	float maxMotorForce, motorSpeed;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2PrismaticJointDef;
+typedef struct b2WeldJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 localAnchorA, localAnchorB;
+	float referenceAngle, linearHertz, angularHertz, linearDampingRatio, angularDampingRatio;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2WeldJointDef;
+typedef struct b2WheelJointDef
+{
+	b2BodyId bodyIdA, bodyIdB;
+	b2Vec2 localAnchorA, localAnchorB, localAxisA;
+	bool enableSpring;
+	float hertz, dampingRatio;
+	bool enableLimit;
+	float lowerTranslation, upperTranslation;
+	bool enableMotor;
+	float maxMotorTorque, motorSpeed;
+	bool collideConnected;
+	void* userData;
+	int internalValue;
+} b2WheelJointDef;
+typedef struct b2ExplosionDef { uint64_t maskBits; b2Vec2 position; float radius, falloff, impulsePerLength; } b2ExplosionDef;
+
 typedef struct b2Counters // types.h:492-505
 {
 	int bodyCount, shapeCount, contactCount, jointCount, islandCount, stackUsed, staticTreeHeight, treeHeight, byteCount, taskCount;
@@ -224,6 +313,114 @@ F2D_API b2AABB b2Shape_GetAABB( b2ShapeId shapeId );
 // ---- joints: B2/include/box2d/box2d.h:760-1250 ----------------------------------------------------------------
 F2D_API b2JointId b2CreateRevoluteJoint( b2WorldId worldId, const b2RevoluteJointDef* def ); // box2d.h:~1050
 F2D_API bool b2Joint_IsValid( b2JointId id );
+
+// ---- the rest of the body / shape / joint surface (forge2d_b200/csrc/f2d_capi_ext.inl; reference lines cited there) --
+F2D_API void b2DestroyBody( b2BodyId bodyId );													  // body.c:343
+F2D_API b2Vec2 b2Body_GetLocalPoint( b2BodyId bodyId, b2Vec2 worldPoint );						  // body.c:656
+F2D_API b2Vec2 b2Body_GetWorldPoint( b2BodyId bodyId, b2Vec2 localPoint );						  // body.c:664
+F2D_API b2Vec2 b2Body_GetLocalVector( b2BodyId bodyId, b2Vec2 worldVector );						  // body.c:672
+F2D_API b2Vec2 b2Body_GetWorldVector( b2BodyId bodyId, b2Vec2 localVector );						  // body.c:680
+F2D_API void b2Body_SetTransform( b2BodyId bodyId, b2Vec2 position, b2Rot rotation );				  // body.c:688
+F2D_API void b2Body_ApplyForce( b2BodyId bodyId, b2Vec2 force, b2Vec2 point, bool wake );			  // body.c:900
+F2D_API void b2Body_ApplyForceToCenter( b2BodyId bodyId, b2Vec2 force, bool wake );				  // body.c:918
+F2D_API void b2Body_ApplyTorque( b2BodyId bodyId, float torque, bool wake );						  // body.c:935
+F2D_API void b2Body_ApplyLinearImpulse( b2BodyId bodyId, b2Vec2 impulse, b2Vec2 point, bool wake ); // body.c:952
+F2D_API void b2Body_ApplyLinearImpulseToCenter( b2BodyId bodyId, b2Vec2 impulse, bool wake );		  // body.c:975
+F2D_API void b2Body_ApplyAngularImpulse( b2BodyId bodyId, float impulse, bool wake );				  // body.c:997
+F2D_API void b2Body_SetType( b2BodyId bodyId, b2BodyType type );									  // body.c:1036 (reports unsupported)
+F2D_API void b2Body_SetName( b2BodyId bodyId, const char* name );									  // body.c:1286
+F2D_API const char* b2Body_GetName( b2BodyId bodyId );											  // body.c:1306
+F2D_API void b2Body_SetUserData( b2BodyId bodyId, void* userData );
+F2D_API void* b2Body_GetUserData( b2BodyId bodyId );
+F2D_API void b2Body_SetMassData( b2BodyId bodyId, b2MassData massData );							  // body.c:1357
+F2D_API b2MassData b2Body_GetMassData( b2BodyId bodyId );											  // body.c:1384
+F2D_API void b2Body_ApplyMassFromShapes( b2BodyId bodyId );										  // body.c:1393
+F2D_API void b2Body_SetLinearDamping( b2BodyId bodyId, float linearDamping );
+F2D_API float b2Body_GetLinearDamping( b2BodyId bodyId );
+F2D_API void b2Body_SetAngularDamping( b2BodyId bodyId, float angularDamping );
+F2D_API float b2Body_GetAngularDamping( b2BodyId bodyId );
+F2D_API void b2Body_SetGravityScale( b2BodyId bodyId, float gravityScale );
+F2D_API float b2Body_GetGravityScale( b2BodyId bodyId );
+F2D_API void b2Body_SetAwake( b2BodyId bodyId, bool awake );										  // body.c:1483
+F2D_API bool b2Body_IsEnabled( b2BodyId bodyId );
+F2D_API bool b2Body_IsSleepEnabled( b2BodyId bodyId );
+F2D_API void b2Body_SetSleepThreshold( b2BodyId bodyId, float sleepThreshold );
+F2D_API float b2Body_GetSleepThreshold( b2BodyId bodyId );
+F2D_API void b2Body_EnableSleep( b2BodyId bodyId, bool enableSleep );								  // body.c:1538
+F2D_API void b2Body_Disable( b2BodyId bodyId );													  // body.c:1557 (reports unsupported)
+F2D_API void b2Body_Enable( b2BodyId bodyId );													  // body.c:1628 (reports unsupported)
+F2D_API void b2Body_SetFixedRotation( b2BodyId bodyId, bool flag );								  // body.c:1722
+F2D_API bool b2Body_IsFixedRotation( b2BodyId bodyId );
+F2D_API void b2Body_SetBullet( b2BodyId bodyId, bool flag );
+F2D_API bool b2Body_IsBullet( b2BodyId bodyId );
+F2D_API void b2Body_EnableContactEvents( b2BodyId bodyId, bool flag );
+F2D_API void b2Body_EnableHitEvents( b2BodyId bodyId, bool flag );
+F2D_API b2WorldId b2Body_GetWorld( b2BodyId bodyId );
+F2D_API int b2Body_GetShapes( b2BodyId bodyId, b2ShapeId* shapeArray, int capacity );				  // body.c:1811
+F2D_API int b2Body_GetJointCount( b2BodyId bodyId );
+F2D_API int b2Body_GetJoints( b2BodyId bodyId, b2JointId* jointArray, int capacity );				  // body.c:1837
+
+F2D_API void b2DestroyShape( b2ShapeId shapeId, bool updateBodyMass );							  // shape.c:318
+F2D_API b2WorldId b2Shape_GetWorld( b2ShapeId shapeId );
+F2D_API void b2Shape_SetUserData( b2ShapeId shapeId, void* userData );
+F2D_API void* b2Shape_GetUserData( b2ShapeId shapeId );
+F2D_API bool b2Shape_IsSensor( b2ShapeId shapeId );
+F2D_API bool b2Shape_TestPoint( b2ShapeId shapeId, b2Vec2 point );								  // shape.c:979
+F2D_API void b2Shape_SetDensity( b2ShapeId shapeId, float density, bool updateBodyMass );			  // shape.c:1055
+F2D_API float b2Shape_GetDensity( b2ShapeId shapeId );
+F2D_API void b2Shape_SetFriction( b2ShapeId shapeId, float friction );
+F2D_API float b2Shape_GetFriction( b2ShapeId shapeId );
+F2D_API void b2Shape_SetRestitution( b2ShapeId shapeId, float restitution );
+F2D_API float b2Shape_GetRestitution( b2ShapeId shapeId );
+F2D_API b2Filter b2Shape_GetFilter( b2ShapeId shapeId );
+F2D_API void b2Shape_SetFilter( b2ShapeId shapeId, b2Filter filter );								  // shape.c:1235
+F2D_API void b2Shape_EnableSensorEvents( b2ShapeId shapeId, bool flag );
+F2D_API bool b2Shape_AreSensorEventsEnabled( b2ShapeId shapeId );
+F2D_API void b2Shape_EnableContactEvents( b2ShapeId shapeId, bool flag );
+F2D_API bool b2Shape_AreContactEventsEnabled( b2ShapeId shapeId );
+F2D_API void b2Shape_EnablePreSolveEvents( b2ShapeId shapeId, bool flag );
+F2D_API bool b2Shape_ArePreSolveEventsEnabled( b2ShapeId shapeId );
+F2D_API void b2Shape_EnableHitEvents( b2ShapeId shapeId, bool flag );
+F2D_API bool b2Shape_AreHitEventsEnabled( b2ShapeId shapeId );
+F2D_API b2ShapeType b2Shape_GetType( b2ShapeId shapeId );
+F2D_API b2Circle b2Shape_GetCircle( b2ShapeId shapeId );
+F2D_API b2Segment b2Shape_GetSegment( b2ShapeId shapeId );
+F2D_API b2ChainSegment b2Shape_GetChainSegment( b2ShapeId shapeId );
+F2D_API b2Capsule b2Shape_GetCapsule( b2ShapeId shapeId );
+F2D_API b2Polygon b2Shape_GetPolygon( b2ShapeId shapeId );
+
+F2D_API b2DistanceJointDef b2DefaultDistanceJointDef( void );   // joint.c:24
+F2D_API b2MotorJointDef b2DefaultMotorJointDef( void );		   // joint.c:33
+F2D_API b2MouseJointDef b2DefaultMouseJointDef( void );		   // joint.c:43
+F2D_API b2FilterJointDef b2DefaultFilterJointDef( void );	   // joint.c:53
+F2D_API b2PrismaticJointDef b2DefaultPrismaticJointDef( void ); // joint.c:60
+F2D_API b2WeldJointDef b2DefaultWeldJointDef( void );		   // joint.c:76
+F2D_API b2WheelJointDef b2DefaultWheelJointDef( void );		   // joint.c:83
+F2D_API b2ExplosionDef b2DefaultExplosionDef( void );		   // joint.c:94
+F2D_API b2JointId b2CreateDistanceJoint( b2WorldId worldId, const b2DistanceJointDef* def );	 // joint.c:353
+F2D_API b2JointId b2CreateMotorJoint( b2WorldId worldId, const b2MotorJointDef* def );		 // joint.c:406
+F2D_API b2JointId b2CreateMouseJoint( b2WorldId worldId, const b2MouseJointDef* def );		 // joint.c:444
+F2D_API b2JointId b2CreateFilterJoint( b2WorldId worldId, const b2FilterJointDef* def );		 // joint.c:480
+F2D_API b2JointId b2CreatePrismaticJoint( b2WorldId worldId, const b2PrismaticJointDef* def ); // joint.c:559
+F2D_API b2JointId b2CreateWeldJoint( b2WorldId worldId, const b2WeldJointDef* def );			 // joint.c:609
+F2D_API b2JointId b2CreateWheelJoint( b2WorldId worldId, const b2WheelJointDef* def );		 // joint.c:651
+F2D_API void b2DestroyJoint( b2JointId jointId );												 // joint.c:809
+F2D_API b2JointType b2Joint_GetType( b2JointId jointId );
+F2D_API b2BodyId b2Joint_GetBodyA( b2JointId jointId );
+F2D_API b2BodyId b2Joint_GetBodyB( b2JointId jointId );
+F2D_API b2WorldId b2Joint_GetWorld( b2JointId jointId );
+F2D_API b2Vec2 b2Joint_GetLocalAnchorA( b2JointId jointId );
+F2D_API b2Vec2 b2Joint_GetLocalAnchorB( b2JointId jointId );
+F2D_API void b2Joint_SetLocalAnchorA( b2JointId jointId, b2Vec2 localAnchor );
+F2D_API void b2Joint_SetLocalAnchorB( b2JointId jointId, b2Vec2 localAnchor );
+F2D_API void b2Joint_SetCollideConnected( b2JointId jointId, bool shouldCollide );			 // joint.c:979
+F2D_API bool b2Joint_GetCollideConnected( b2JointId jointId );
+F2D_API void b2Joint_SetUserData( b2JointId jointId, void* userData );
+F2D_API void* b2Joint_GetUserData( b2JointId jointId );
+F2D_API void b2Joint_WakeBodies( b2JointId jointId );											 // joint.c:1045
+F2D_API b2Vec2 b2Joint_GetConstraintForce( b2JointId jointId );								 // joint.c:1061
+F2D_API float b2Joint_GetConstraintTorque( b2JointId jointId );								 // joint.c:1099
+#include "forge2d_b200_joints.h"
 
 // ---------------------------------------------------------------------------------------------------------------
 // Extension (additive, `f2d` prefix): batches of independent worlds, sharded by world — config 5 of BASELINE.json.

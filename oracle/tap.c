@@ -323,14 +323,54 @@ TAP_API int tap_joints( b2WorldId id, f2dJointRecord* out, int cap )
 			r->bodyIdA = j->edges[0].bodyId;
 			r->bodyIdB = j->edges[1].bodyId;
 			r->islandId = j->islandId;
-			if ( j->type == b2_revoluteJoint )
+			switch ( j->type )
 			{
-				r->impulse[0] = s->revoluteJoint.linearImpulse.x;
-				r->impulse[1] = s->revoluteJoint.linearImpulse.y;
-				r->impulse[2] = s->revoluteJoint.springImpulse;
-				r->impulse[3] = s->revoluteJoint.motorImpulse;
-				r->impulse[4] = s->revoluteJoint.lowerImpulse;
-				r->impulse[5] = s->revoluteJoint.upperImpulse;
+				case b2_revoluteJoint:
+					r->impulse[0] = s->revoluteJoint.linearImpulse.x;
+					r->impulse[1] = s->revoluteJoint.linearImpulse.y;
+					r->impulse[2] = s->revoluteJoint.springImpulse;
+					r->impulse[3] = s->revoluteJoint.motorImpulse;
+					r->impulse[4] = s->revoluteJoint.lowerImpulse;
+					r->impulse[5] = s->revoluteJoint.upperImpulse;
+					break;
+				case b2_distanceJoint:
+					r->impulse[0] = s->distanceJoint.impulse;
+					r->impulse[1] = s->distanceJoint.lowerImpulse;
+					r->impulse[2] = s->distanceJoint.upperImpulse;
+					r->impulse[3] = s->distanceJoint.motorImpulse;
+					break;
+				case b2_motorJoint:
+					r->impulse[0] = s->motorJoint.linearImpulse.x;
+					r->impulse[1] = s->motorJoint.linearImpulse.y;
+					r->impulse[2] = s->motorJoint.angularImpulse;
+					break;
+				case b2_mouseJoint:
+					r->impulse[0] = s->mouseJoint.linearImpulse.x;
+					r->impulse[1] = s->mouseJoint.linearImpulse.y;
+					r->impulse[2] = s->mouseJoint.angularImpulse;
+					break;
+				case b2_prismaticJoint:
+					r->impulse[0] = s->prismaticJoint.impulse.x;
+					r->impulse[1] = s->prismaticJoint.impulse.y;
+					r->impulse[2] = s->prismaticJoint.springImpulse;
+					r->impulse[3] = s->prismaticJoint.motorImpulse;
+					r->impulse[4] = s->prismaticJoint.lowerImpulse;
+					r->impulse[5] = s->prismaticJoint.upperImpulse;
+					break;
+				case b2_weldJoint:
+					r->impulse[0] = s->weldJoint.linearImpulse.x;
+					r->impulse[1] = s->weldJoint.linearImpulse.y;
+					r->impulse[2] = s->weldJoint.angularImpulse;
+					break;
+				case b2_wheelJoint:
+					r->impulse[0] = s->wheelJoint.perpImpulse;
+					r->impulse[1] = s->wheelJoint.motorImpulse;
+					r->impulse[2] = s->wheelJoint.springImpulse;
+					r->impulse[3] = s->wheelJoint.lowerImpulse;
+					r->impulse[4] = s->wheelJoint.upperImpulse;
+					break;
+				default:
+					break;
 			}
 		}
 		n += 1;
