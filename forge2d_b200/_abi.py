@@ -170,6 +170,23 @@ class WheelJointDef(C.Structure):
                 ("collideConnected", c_bool), ("userData", c_void_p), ("internalValue", c_int)]
 
 
+class QueryFilter(C.Structure):
+    _fields_ = [("categoryBits", C.c_uint64), ("maskBits", C.c_uint64)]
+
+
+class RayResult(C.Structure):
+    _fields_ = [("shapeId", ShapeId), ("point", Vec2), ("normal", Vec2), ("fraction", c_float), ("nodeVisits", c_int),
+                ("leafVisits", c_int), ("hit", c_bool)]
+
+
+class TreeStats(C.Structure):
+    _fields_ = [("nodeVisits", c_int), ("leafVisits", c_int)]
+
+
+OverlapResultFcn = C.CFUNCTYPE(c_bool, ShapeId, c_void_p)
+CastResultFcn = C.CFUNCTYPE(c_float, ShapeId, Vec2, Vec2, c_float, c_void_p)
+
+
 class ExplosionDef(C.Structure):
     _fields_ = [("maskBits", C.c_uint64), ("position", Vec2), ("radius", c_float), ("falloff", c_float),
                 ("impulsePerLength", c_float)]
@@ -415,6 +432,13 @@ B2_FUNCTIONS = {
     "b2Joint_WakeBodies": (None, [JointId]),
     "b2Joint_GetConstraintForce": (Vec2, [JointId]),
     "b2Joint_GetConstraintTorque": (c_float, [JointId]),
+    "b2DefaultQueryFilter": (QueryFilter, []),
+    "b2World_OverlapAABB": (TreeStats, [WorldId, AABB, QueryFilter, OverlapResultFcn, c_void_p]),
+    "b2World_CastRay": (TreeStats, [WorldId, Vec2, Vec2, QueryFilter, CastResultFcn, c_void_p]),
+    "b2World_CastRayClosest": (RayResult, [WorldId, Vec2, Vec2, QueryFilter]),
+    "b2World_Explode": (None, [WorldId, C.POINTER(ExplosionDef)]),
+    "b2World_SetCustomFilterCallback": (None, [WorldId, c_void_p, c_void_p]),
+    "b2World_SetPreSolveCallback": (None, [WorldId, c_void_p, c_void_p]),
 }
 
 # per-joint-type accessors (generated table; names resolved to the classes above)

@@ -5,6 +5,7 @@
 // The including TU provides the backend hooks declared below.
 #include "f2d_image.h"
 #include "f2d_mutate.h"
+#include "f2d_query.h"
 #include "f2d_step.h"
 
 #include "../../include/forge2d_b200.h"

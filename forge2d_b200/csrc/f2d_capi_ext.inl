@@ -1128,4 +1128,179 @@ b2JointId b2CreateWheelJoint( b2WorldId worldId, const b2WheelJointDef* def ) //
 	return finishJoint( c, def->collideConnected );
 }
 
+// ---------------------------------------------------------------------------------------------------------------- queries
+// world.c:2040-2310. The world's state lives on the device; a query first makes the host image current (one download
+// after a step, none between consecutive queries), then walks the trees on the host because every candidate is handed
+// to a synchronous host callback whose answer clips or stops the walk.
+static b2ShapeId publicShapeId( World* w, int shapeId )
+{
+	return b2ShapeId{ shapeId + 1, w->worldId, ptr( w, w->shapes )[shapeId].generation };
+}
+b2QueryFilter b2DefaultQueryFilter( void ) // types.c
+{
+	return b2QueryFilter{ 1ull, UINT64_MAX };
+}
+b2TreeStats b2World_OverlapAABB( b2WorldId worldId, b2AABB aabb, b2QueryFilter filter, b2OverlapResultFcn* fcn, void* context )
+{
+	b2TreeStats total = { 0, 0 };
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return total;
+	World* w = hostImage( *hw );
+	if ( w->locked )
+		return total;
+	Box box = { { aabb.lowerBound.x, aabb.lowerBound.y }, { aabb.upperBound.x, aabb.upperBound.y } };
+	for ( int i = 0; i < 3; ++i )
+	{
+		TreeStats st = treeQueryStats( w, w->trees[i], box, filter.maskBits, [&]( int, uint64_t userData ) -> bool {
+			int shapeId = (int)userData;
+			const Shape& shape = ptr( w, w->shapes )[shapeId];
+			if ( shouldQueryCollide( shape.filter, filter.categoryBits, filter.maskBits ) == false )
+				return true;
+			return fcn( publicShapeId( w, shapeId ), context );
+		} );
+		total.nodeVisits += st.nodeVisits;
+		total.leafVisits += st.leafVisits;
+	}
+	return total;
+}
+static b2TreeStats castRayCommon( HostWorld* hw, b2Vec2 origin, b2Vec2 translation, b2QueryFilter filter, b2CastResultFcn* fcn, void* context )
+{
+	b2TreeStats total = { 0, 0 };
+	World* w = hostImage( *hw );
+	if ( w->locked )
+		return total;
+	RayInput input = { { origin.x, origin.y }, { translation.x, translation.y }, 1.0f };
+	float worldFraction = 1.0f;
+	for ( int i = 0; i < 3; ++i )
+	{
+		TreeStats st = treeRayCast( w, w->trees[i], input, filter.maskBits, [&]( const RayInput& sub, int, uint64_t userData ) -> float {
+			int shapeId = (int)userData;
+			const Shape& shape = ptr( w, w->shapes )[shapeId];
+			if ( shouldQueryCollide( shape.filter, filter.categoryBits, filter.maskBits ) == false )
+				return sub.maxFraction;
+			Xf transform = ptr( w, w->sims )[shape.bodyId].transform;
+			bool supported = true;
+			CastOutput out = rayCastShape( sub, shape, transform, &supported );
+			if ( supported == false )
+			{
+				reportError( "b2World_CastRay: ray casts against rounded polygons are not supported by forge2d_b200 yet" );
+				return sub.maxFraction;
+			}
+			if ( out.hit )
+			{
+				float fraction = fcn( publicShapeId( w, shapeId ), b2Vec2{ out.point.x, out.point.y }, b2Vec2{ out.normal.x, out.normal.y },
+									  out.fraction, context );
+				if ( 0.0f <= fraction && fraction <= 1.0f )
+					worldFraction = fraction;
+				return fraction;
+			}
+			return sub.maxFraction;
+		} );
+		total.nodeVisits += st.nodeVisits;
+		total.leafVisits += st.leafVisits;
+		if ( worldFraction == 0.0f )
+			return total;
+		input.maxFraction = worldFraction;
+	}
+	return total;
+}
+b2TreeStats b2World_CastRay( b2WorldId worldId, b2Vec2 origin, b2Vec2 translation, b2QueryFilter filter, b2CastResultFcn* fcn, void* context )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return b2TreeStats{ 0, 0 };
+	return castRayCommon( hw, origin, translation, filter, fcn, context );
+}
+static float closestHit( b2ShapeId shapeId, b2Vec2 point, b2Vec2 normal, float fraction, void* context ) // world.c:2260-2275
+{
+	if ( fraction == 0.0f )
+		return -1.0f;
+	b2RayResult* r = (b2RayResult*)context;
+	r->shapeId = shapeId;
+	r->point = point;
+	r->normal = normal;
+	r->fraction = fraction;
+	r->hit = true;
+	return fraction;
+}
+b2RayResult b2World_CastRayClosest( b2WorldId worldId, b2Vec2 origin, b2Vec2 translation, b2QueryFilter filter ) // world.c:2277-2308
+{
+	b2RayResult result;
+	memset( &result, 0, sizeof( result ) );
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return result;
+	b2TreeStats st = castRayCommon( hw, origin, translation, filter, closestHit, &result );
+	result.nodeVisits = st.nodeVisits;
+	result.leafVisits = st.leafVisits;
+	return result;
+}
+void b2World_Explode( b2WorldId worldId, const b2ExplosionDef* def ) // world.c:2640-2745
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	if ( w->locked )
+		return;
+	V2 position = { def->position.x, def->position.y };
+	float radius = def->radius, falloff = def->falloff, impulsePerLength = def->impulsePerLength;
+	Box box = { { position.x - ( radius + falloff ), position.y - ( radius + falloff ) },
+				{ position.x + ( radius + falloff ), position.y + ( radius + falloff ) } };
+	treeQueryStats( w, w->trees[kDynamicBody], box, def->maskBits, [&]( int, uint64_t userData ) -> bool {
+		const Shape& shape = ptr( w, w->shapes )[(int)userData];
+		Body& body = ptr( w, w->bodies )[shape.bodyId];
+		BodySim& sim = ptr( w, w->sims )[shape.bodyId];
+		Xf transform = sim.transform;
+		Xf identity = { { 0.0f, 0.0f }, { 1.0f, 0.0f } };
+		SimplexCache cache;
+		memset( &cache, 0, sizeof( cache ) );
+		DistanceOutput out = shapeDistance( makeShapeProxy( shape ), makeProxy( &position, 1, 0.0f ), transform, identity, true, &cache );
+		if ( out.distance > radius + falloff )
+			return true;
+		wakeBody( w, body );
+		if ( body.setIndex != kAwakeSet )
+			return true;
+		V2 closestPoint = out.pointA;
+		if ( out.distance == 0.0f )
+			closestPoint = xfPoint( transform, shapeCentroid( shape ) );
+		V2 direction = sub( closestPoint, position );
+		if ( lengthSq( direction ) > 100.0f * FLT_EPSILON * FLT_EPSILON )
+			direction = normalize( direction );
+		else
+			direction = V2{ 1.0f, 0.0f };
+		V2 localLine = invRotate( transform.q, leftPerp( direction ) );
+		float perimeter = shapeProjectedPerimeter( shape, localLine );
+		float scale = 1.0f;
+		if ( out.distance > radius && falloff > 0.0f )
+			scale = clampf( ( radius + falloff - out.distance ) / falloff, 0.0f, 1.0f );
+		float magnitude = impulsePerLength * perimeter * scale;
+		V2 impulse = mulSV( magnitude, direction );
+		BodyState& state = ptr( w, w->states )[body.localIndex];
+		state.v = mulAdd( state.v, sim.invMass, impulse );
+		state.w += sim.invInertia * cross( sub( closestPoint, sim.center ), impulse );
+		return true;
+	} );
+}
+// world.c:1710-1740: callbacks into host code from inside the step cannot run on the device path
+void b2World_SetCustomFilterCallback( b2WorldId worldId, b2CustomFilterFcn* fcn, void* context )
+{
+	(void)context;
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || fcn == nullptr )
+		return;
+	reportError( "b2World_SetCustomFilterCallback: host callbacks inside the step are not supported by forge2d_b200 (the step runs on the GPU)" );
+	setError( mutableImage( *hw ), kErrUnsupported, __LINE__ );
+}
+void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn, void* context )
+{
+	(void)context;
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr || fcn == nullptr )
+		return;
+	reportError( "b2World_SetPreSolveCallback: host callbacks inside the step are not supported by forge2d_b200 (the step runs on the GPU)" );
+	setError( mutableImage( *hw ), kErrUnsupported, __LINE__ );
+}
+
 #include "f2d_capi_joints.inl"

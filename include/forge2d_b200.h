@@ -220,6 +220,15 @@ typedef struct b2WheelJointDef
 } b2WheelJointDef;
 typedef struct b2ExplosionDef { uint64_t maskBits; b2Vec2 position; float radius, falloff, impulsePerLength; } b2ExplosionDef;
 
+// ---- queries: types.h:291-305 (b2QueryFilter), :67-76 (b2RayResult), collision.h:658-665 (b2TreeStats), callbacks types.h:1180-1220
+typedef struct b2QueryFilter { uint64_t categoryBits, maskBits; } b2QueryFilter;
+typedef struct b2RayResult { b2ShapeId shapeId; b2Vec2 point, normal; float fraction; int nodeVisits, leafVisits; bool hit; } b2RayResult;
+typedef struct b2TreeStats { int nodeVisits, leafVisits; } b2TreeStats;
+typedef bool b2OverlapResultFcn( b2ShapeId shapeId, void* context );
+typedef float b2CastResultFcn( b2ShapeId shapeId, b2Vec2 point, b2Vec2 normal, float fraction, void* context );
+typedef bool b2CustomFilterFcn( b2ShapeId shapeIdA, b2ShapeId shapeIdB, void* context );
+typedef bool b2PreSolveFcn( b2ShapeId shapeIdA, b2ShapeId shapeIdB, b2Manifold* manifold, void* context );
+
 typedef struct b2Counters // types.h:492-505
 {
 	int bodyCount, shapeCount, contactCount, jointCount, islandCount, stackUsed, staticTreeHeight, treeHeight, byteCount, taskCount;
@@ -420,6 +429,16 @@ F2D_API void* b2Joint_GetUserData( b2JointId jointId );
 F2D_API void b2Joint_WakeBodies( b2JointId jointId );											 // joint.c:1045
 F2D_API b2Vec2 b2Joint_GetConstraintForce( b2JointId jointId );								 // joint.c:1061
 F2D_API float b2Joint_GetConstraintTorque( b2JointId jointId );								 // joint.c:1099
+// ---- queries and explosion (run on the host image of the device state: forge2d_b200/csrc/f2d_query.h) ---------------
+F2D_API b2QueryFilter b2DefaultQueryFilter( void );
+F2D_API b2TreeStats b2World_OverlapAABB( b2WorldId worldId, b2AABB aabb, b2QueryFilter filter, b2OverlapResultFcn* fcn, void* context ); // world.c:2071
+F2D_API b2TreeStats b2World_CastRay( b2WorldId worldId, b2Vec2 origin, b2Vec2 translation, b2QueryFilter filter, b2CastResultFcn* fcn,
+									 void* context );																				 // world.c:2222
+F2D_API b2RayResult b2World_CastRayClosest( b2WorldId worldId, b2Vec2 origin, b2Vec2 translation, b2QueryFilter filter );			 // world.c:2277
+F2D_API void b2World_Explode( b2WorldId worldId, const b2ExplosionDef* explosionDef );												 // world.c:2718
+/// Host callbacks from inside the step cannot run on the device path: registering one reports an error (loudly).
+F2D_API void b2World_SetCustomFilterCallback( b2WorldId worldId, b2CustomFilterFcn* fcn, void* context );
+F2D_API void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn, void* context );
 #include "forge2d_b200_joints.h"
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -65,3 +65,89 @@ def test_scripted_session_matches_reference_gpu(ref, gpu):
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_all_joint_types_bit_identical_gpu(ref, gpu, mode):
     _joint_zoo(ref, gpu, 300, 5, mode)
+
+
+# ---- queries -------------------------------------------------------------------------------------------------
+def _query_session(lib, frames=90):
+    """Ray casts (all hits in callback order, clipped, closest), AABB overlaps and an explosion on a mixed scene."""
+    import ctypes as C
+    from forge2d_b200 import _abi as A
+    s = scenes.falling_shapes(lib, count=24) if False else scenes.bench2d(lib, rows=10, ground_half_width=14.0)
+    world = s.world
+    sd = lib.b2DefaultShapeDef()
+    bd = lib.b2DefaultBodyDef()
+    bd.type = 2
+    for k, (x, y) in enumerate(((-9.0, -20.0), (-8.0, -12.0), (9.0, -18.0))):
+        bd.position = A.Vec2(x, y)
+        b = lib.b2CreateBody(world, C.byref(bd))
+        if k == 0:
+            c = A.Circle(A.Vec2(0.0, 0.0), 0.6)
+            lib.b2CreateCircleShape(b, C.byref(sd), C.byref(c))
+        elif k == 1:
+            c = A.Capsule(A.Vec2(-0.5, 0.0), A.Vec2(0.5, 0.2), 0.3)
+            lib.b2CreateCapsuleShape(b, C.byref(sd), C.byref(c))
+        else:
+            sd2 = lib.b2DefaultShapeDef()
+            sd2.filter.categoryBits = 2
+            box = lib.b2MakeBox(0.7, 0.3)
+            lib.b2CreatePolygonShape(b, C.byref(sd2), C.byref(box))
+    out = []
+
+    def bits(x):
+        import numpy as np
+        return int(np.float32(x).view(np.uint32))
+
+    rays = [((-20.0, -29.5), (40.0, 0.0)), ((-6.0, 5.0), (3.0, -40.0)), ((0.0, -10.0), (0.0, -25.0)),
+            ((-12.0, -25.0), (30.0, 9.0)), ((2.0, -28.0), (0.0, 0.0)), ((-9.0, -20.0), (1.0, 1.0))]
+    for f in range(frames):
+        s.step()
+        if f % 15 != 14:
+            continue
+        flt = lib.b2DefaultQueryFilter()
+        for ri, (o, t) in enumerate(rays):
+            for mode in ("all", "clip", "first"):
+                hits = []
+
+                def cb(shape, point, normal, fraction, ctx, hits=hits, mode=mode):
+                    hits.append((shape.index1, bits(point.x), bits(point.y), bits(normal.x), bits(normal.y), bits(fraction)))
+                    return {"all": 1.0, "clip": fraction, "first": 0.0}[mode]
+
+                st = lib.b2World_CastRay(world, A.Vec2(*o), A.Vec2(*t), flt, A.CastResultFcn(cb), None)
+                out.append(("ray%d.%s.f%d" % (ri, mode, f), hits, st.nodeVisits, st.leafVisits))
+            r = lib.b2World_CastRayClosest(world, A.Vec2(*o), A.Vec2(*t), flt)
+            out.append(("closest%d.f%d" % (ri, f), r.hit, r.shapeId.index1 if r.hit else 0, bits(r.fraction), bits(r.point.x),
+                        bits(r.normal.y), r.nodeVisits, r.leafVisits))
+        flt2 = lib.b2DefaultQueryFilter()
+        flt2.maskBits = 2
+        for box, fl in ((A.AABB(A.Vec2(-3.0, -30.5), A.Vec2(3.0, -27.0)), flt), (A.AABB(A.Vec2(-20.0, -31.0), A.Vec2(20.0, 0.0)), flt2)):
+            found = []
+
+            def ocb(shape, ctx, found=found):
+                found.append(shape.index1)
+                return len(found) < 25
+
+            st = lib.b2World_OverlapAABB(world, box, fl, A.OverlapResultFcn(ocb), None)
+            out.append(("overlap.f%d" % f, found, st.nodeVisits, st.leafVisits))
+        if f == 44:
+            ex = lib.b2DefaultExplosionDef()
+            ex.position = A.Vec2(0.0, -29.0)
+            ex.radius, ex.falloff, ex.impulsePerLength = 3.0, 2.0, 8.0
+            lib.b2World_Explode(world, C.byref(ex))
+    snap = H.snapshot(lib, world)
+    s.destroy()
+    return out, snap
+
+
+def test_queries_match_reference_emu(ref, emu):
+    a, sa = _query_session(ref)
+    b, sb = _query_session(emu)
+    assert a == b
+    assert H.diff(sa, sb) == []
+
+
+@pytest.mark.gpu
+def test_queries_match_reference_gpu(ref, gpu):
+    a, sa = _query_session(ref)
+    b, sb = _query_session(gpu)
+    assert a == b
+    assert H.diff(sa, sb) == []
