@@ -380,11 +380,12 @@ def run_b200_arm(args, rank, world_size, local_rank):
     cores = host_cores()
     if world_size == 1 and not args.no_cpu_baseline:
         ref = load_reference()
-        sample = args.ref_worlds or max(cores, min(4 * cores, 256))
-        v, seconds = reference_batch(ref, sample, max(8, min(args.steps, 32)), 2, cores)
+        sample = args.ref_worlds or max(cores, min(16 * cores, 256))
+        cpu_steps = 256  # bounded sample: ~64k world-steps, a few seconds on 16 cores after the pre-roll
+        v, seconds = reference_batch(ref, sample, cpu_steps, 2, cores)
         line["cpu_baseline"] = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "reference",
                                 "sample": "%d bench2d worlds at frame %d x %d steps, one single-worker world per thread "
-                                          "on %d threads (%s), %.1f s" % (sample, PREROLL, max(8, min(args.steps, 32)), cores,
+                                          "on %d threads (%s), %.1f s" % (sample, PREROLL, cpu_steps, cores,
                                                                           cpu_model(), seconds)}
     if world_size == 1 and not args.no_extras:
         extras = {}

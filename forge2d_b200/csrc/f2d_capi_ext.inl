@@ -420,34 +420,36 @@ int b2Body_GetJoints( b2BodyId bodyId, b2JointId* jointArray, int capacity ) // 
 	}
 	return n;
 }
-// body.c:1036-1284 / :1557-1720. Moving a body between the static / awake / disabled sets re-homes its joints through the
-// constraint graph; that bookkeeping is not on the image path yet, so the calls fail loudly instead of approximating.
-void b2Body_SetType( b2BodyId bodyId, b2BodyType type )
+static void reportSleepingJointTarget( World* w, bool ok )
 {
-	HostWorld* hw = nullptr;
-	Body* b = writableBody( bodyId, &hw );
-	if ( b == nullptr || b->type == (int)type )
+	if ( ok )
 		return;
-	reportError( "b2Body_SetType: changing a body's type after creation is not supported by forge2d_b200 yet" );
-	setError( hw->img, kErrUnsupported, __LINE__ );
+	reportError( "forge2d_b200: a joint would have to move into a sleeping solver set (not supported yet)" );
+	setError( w, kErrUnsupported, __LINE__ );
 }
-void b2Body_Disable( b2BodyId bodyId )
+void b2Body_SetType( b2BodyId bodyId, b2BodyType type ) // body.c:1036-1284
 {
 	HostWorld* hw = nullptr;
 	Body* b = writableBody( bodyId, &hw );
-	if ( b == nullptr || b->setIndex == kDisabledSet )
+	if ( b == nullptr )
 		return;
-	reportError( "b2Body_Disable: disabling a body after creation is not supported by forge2d_b200 yet" );
-	setError( hw->img, kErrUnsupported, __LINE__ );
+	reportSleepingJointTarget( hw->img, setBodyType( hw->img, *b, (int)type ) );
 }
-void b2Body_Enable( b2BodyId bodyId )
+void b2Body_Disable( b2BodyId bodyId ) // body.c:1557-1626
 {
 	HostWorld* hw = nullptr;
 	Body* b = writableBody( bodyId, &hw );
-	if ( b == nullptr || b->setIndex != kDisabledSet )
+	if ( b == nullptr )
 		return;
-	reportError( "b2Body_Enable: enabling a disabled body is not supported by forge2d_b200 yet" );
-	setError( hw->img, kErrUnsupported, __LINE__ );
+	reportSleepingJointTarget( hw->img, disableBody( hw->img, *b ) );
+}
+void b2Body_Enable( b2BodyId bodyId ) // body.c:1628-1720
+{
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return;
+	reportSleepingJointTarget( hw->img, enableBody( hw->img, *b ) );
 }
 
 // ---------------------------------------------------------------------------------------------------------------- shapes

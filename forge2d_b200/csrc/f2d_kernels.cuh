@@ -35,8 +35,9 @@ struct CtaTeam
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = true;
 	// Forking pays when the crew keeps most of the block: with two warps the solver would run on one while the other
-	// walks (measured: the walking warp then waits ~2x its walk for the crew), so small blocks walk first, then solve.
-	__device__ bool canFork() const { return blockDim.x >= 256; }
+	// walks (measured: the walking warp then waits ~2x its walk for the crew), so two-warp blocks walk first, then solve;
+	// from four warps up the crew of three or more hides the walk (measured at 128 threads: 8 % of warp time idle otherwise).
+	__device__ bool canFork() const { return blockDim.x >= 128; }
 	__device__ bool inSide() const { return threadIdx.x >= blockDim.x - 32; }
 	__device__ bool isSideLeader() const { return threadIdx.x == blockDim.x - 32; }
 	typedef WarpLanes Lanes;

@@ -38,7 +38,7 @@ inline void removeBodyFromIsland( World* w, Body& body )
 
 // Swap-removes the body from the id list of the set that owns it (body.c:408-433: b2BodySimArray_RemoveSwap plus the
 // moved body's index fix; the awake set also drops the aligned state; an emptied sleeping set is destroyed).
-inline void removeBodyFromSet( World* w, Body& body )
+inline void removeBodyFromSet( World* w, Body& body, bool destroyOrphanSet = true )
 {
 	Body* bodies = ptr( w, w->bodies );
 	const int setIndex = body.setIndex, localIndex = body.localIndex;
@@ -72,7 +72,7 @@ inline void removeBodyFromSet( World* w, Body& body )
 			bodies[list[localIndex]].localIndex = localIndex;
 		}
 		set.bodyCount -= 1;
-		if ( set.bodyCount == 0 )
+		if ( set.bodyCount == 0 && destroyOrphanSet )
 			destroySolverSet( w, setIndex );
 	}
 }
@@ -170,14 +170,6 @@ inline void destroyShapeProxy( World* w, Shape& shape )
 	}
 }
 
-inline void noteShapeEventFlags( World* w, const Shape& shape, int sign )
-{
-	if ( shape.enableContactEvents )
-		w->contactEventCapable += sign;
-	if ( shape.enableHitEvents )
-		w->hitEventCapable += sign;
-}
-
 // body.c:343-444 b2DestroyBody (chains and sensors are not on this path: they cannot be created)
 inline void destroyBody( World* w, int bodyId )
 {
@@ -199,7 +191,6 @@ inline void destroyBody( World* w, int bodyId )
 	{
 		Shape& shape = shapes[shapeId];
 		destroyShapeProxy( w, shape );
-		noteShapeEventFlags( w, shape, -1 );
 		freeId( w, w->shapeIds, shapeId );
 		shape.id = kNull;
 		shapeId = shape.nextShapeId;
@@ -210,6 +201,262 @@ inline void destroyBody( World* w, int bodyId )
 	body.setIndex = kNull;
 	body.localIndex = kNull;
 	body.id = kNull;
+}
+
+// solver_set.c b2TransferBody: the body's id moves from its set's list to the end of the target list (the sim record
+// itself lives in a stable slot here). Only the static, disabled and awake sets are targets on this path.
+inline void transferBody( World* w, int targetSet, Body& body )
+{
+	const int sourceSet = body.setIndex;
+	removeBodyFromSet( w, body, false );
+	if ( targetSet == kAwakeSet )
+	{
+		body.localIndex = w->awakeBodies.count;
+		F2D_PUSH( w, w->awakeBodies, body.id );
+		F2D_PUSH( w, w->states, identityState() );
+	}
+	else
+	{
+		Arr<int32_t>& list = targetSet == kStaticSet ? w->staticBodies : w->disabledBodies;
+		body.localIndex = list.count;
+		F2D_PUSH( w, list, body.id );
+	}
+	(void)sourceSet;
+	body.setIndex = targetSet;
+}
+
+// solver_set.c b2TransferJoint: add to the target first (the graph picks a colour from the bodies' current types), then
+// remove from the source. Returns false when the target is a sleeping set (its joint list has no room to grow here).
+inline bool transferJoint( World* w, int targetSet, Joint& joint )
+{
+	Joint* joints = ptr( w, w->joints );
+	const int sourceSet = joint.setIndex, localIndex = joint.localIndex, colorIndex = joint.colorIndex;
+	if ( targetSet >= kFirstSleepingSet )
+		return false;
+	if ( targetSet == kAwakeSet )
+	{
+		addJointToGraph( w, joint.jointId );
+		joint.setIndex = kAwakeSet;
+	}
+	else
+	{
+		Arr<int32_t>& list = targetSet == kStaticSet ? w->staticJoints : w->disabledJoints;
+		joint.setIndex = targetSet;
+		joint.localIndex = list.count;
+		joint.colorIndex = kNull;
+		F2D_PUSH( w, list, joint.jointId );
+	}
+	if ( sourceSet == kAwakeSet )
+	{
+		removeJointFromGraph( w, joint.edges[0].bodyId, joint.edges[1].bodyId, colorIndex, localIndex );
+	}
+	else if ( sourceSet == kStaticSet || sourceSet == kDisabledSet )
+	{
+		Arr<int32_t>& list = sourceSet == kStaticSet ? w->staticJoints : w->disabledJoints;
+		int moved = removeSwap( w, list, localIndex );
+		if ( moved != kNull )
+			joints[ptr( w, list )[localIndex]].localIndex = localIndex;
+	}
+	else
+	{
+		SolverSet& set = ptr( w, w->sets )[sourceSet];
+		int32_t* list = setJointList( w, set );
+		int last = set.jointCount - 1;
+		if ( localIndex != last )
+		{
+			list[localIndex] = list[last];
+			joints[list[localIndex]].localIndex = localIndex;
+		}
+		set.jointCount -= 1;
+	}
+	return true;
+}
+
+// body.c:1557-1626 b2Body_Disable
+inline bool disableBody( World* w, Body& body )
+{
+	if ( body.setIndex == kDisabledSet )
+		return true;
+	destroyBodyContacts( w, body, true );
+	removeBodyFromIsland( w, body );
+	Shape* shapes = ptr( w, w->shapes );
+	for ( int s = body.headShapeId; s != kNull; s = shapes[s].nextShapeId )
+		destroyShapeProxy( w, shapes[s] );
+	transferBody( w, kDisabledSet, body );
+	Joint* joints = ptr( w, w->joints );
+	int jointKey = body.headJointKey;
+	bool ok = true;
+	while ( jointKey != kNull )
+	{
+		Joint& joint = joints[jointKey >> 1];
+		jointKey = joint.edges[jointKey & 1].nextKey;
+		if ( joint.setIndex == kDisabledSet )
+			continue;
+		if ( joint.islandId != kNull )
+			unlinkJoint( w, joint );
+		ok = transferJoint( w, kDisabledSet, joint ) && ok;
+	}
+	return ok;
+}
+
+// body.c:1628-1720 b2Body_Enable
+inline bool enableBody( World* w, Body& body )
+{
+	if ( body.setIndex != kDisabledSet )
+		return true;
+	const int setId = body.type == kStaticBody ? kStaticSet : kAwakeSet;
+	transferBody( w, setId, body );
+	Xf transform = ptr( w, w->sims )[body.id].transform;
+	Shape* shapes = ptr( w, w->shapes );
+	for ( int s = body.headShapeId; s != kNull; s = shapes[s].nextShapeId )
+		createShapeProxy( w, shapes[s], body.type, transform, true );
+	if ( setId != kStaticSet )
+		createIslandForBody( w, setId, body );
+	Joint* joints = ptr( w, w->joints );
+	Body* bodies = ptr( w, w->bodies );
+	bool ok = true;
+	int jointKey = body.headJointKey;
+	while ( jointKey != kNull )
+	{
+		Joint& joint = joints[jointKey >> 1];
+		jointKey = joint.edges[jointKey & 1].nextKey;
+		const Body& bodyA = bodies[joint.edges[0].bodyId];
+		const Body& bodyB = bodies[joint.edges[1].bodyId];
+		if ( bodyA.setIndex == kDisabledSet || bodyB.setIndex == kDisabledSet )
+			continue;
+		int jointSetId;
+		if ( bodyA.setIndex == kStaticSet && bodyB.setIndex == kStaticSet )
+			jointSetId = kStaticSet;
+		else if ( bodyA.setIndex == kStaticSet )
+			jointSetId = bodyB.setIndex;
+		else
+			jointSetId = bodyA.setIndex;
+		if ( transferJoint( w, jointSetId, joint ) == false )
+		{
+			ok = false;
+			continue;
+		}
+		if ( jointSetId != kStaticSet )
+			linkJoint( w, joint, false );
+	}
+	mergeAwakeIslands( w );
+	return ok;
+}
+
+// body.c:1036-1284 b2Body_SetType
+inline bool setBodyType( World* w, Body& body, int type )
+{
+	const int originalType = body.type;
+	if ( originalType == type )
+		return true;
+	if ( body.setIndex == kDisabledSet )
+	{
+		body.type = type;
+		updateBodyMassData( w, body );
+		return true;
+	}
+	destroyBodyContacts( w, body, false );
+	wakeBody( w, body );
+	Joint* joints = ptr( w, w->joints );
+	Body* bodies = ptr( w, w->bodies );
+	Shape* shapes = ptr( w, w->shapes );
+	bool ok = true;
+	{
+		int jointKey = body.headJointKey;
+		while ( jointKey != kNull )
+		{
+			Joint& joint = joints[jointKey >> 1];
+			int edgeIndex = jointKey & 1;
+			if ( joint.islandId != kNull )
+				unlinkJoint( w, joint );
+			wakeBody( w, bodies[joint.edges[0].bodyId] );
+			wakeBody( w, bodies[joint.edges[1].bodyId] );
+			jointKey = joint.edges[edgeIndex].nextKey;
+		}
+	}
+	body.type = type;
+	auto recreateProxies = [&]( int proxyType ) {
+		Xf transform = ptr( w, w->sims )[body.id].transform;
+		int shapeId = body.headShapeId;
+		while ( shapeId != kNull )
+		{
+			Shape& shape = shapes[shapeId];
+			shapeId = shape.nextShapeId;
+			destroyShapeProxy( w, shape );
+			createShapeProxy( w, shape, proxyType, transform, true );
+		}
+	};
+	if ( originalType == kStaticBody )
+	{
+		transferBody( w, kAwakeSet, body );
+		createIslandForBody( w, kAwakeSet, body );
+		int jointKey = body.headJointKey;
+		while ( jointKey != kNull )
+		{
+			Joint& joint = joints[jointKey >> 1];
+			int edgeIndex = jointKey & 1;
+			if ( joint.setIndex == kStaticSet )
+			{
+				ok = transferJoint( w, kAwakeSet, joint ) && ok;
+			}
+			else if ( joint.setIndex == kAwakeSet )
+			{
+				// through the static list and back, so the graph colours it for the bodies' new types
+				transferJoint( w, kStaticSet, joint );
+				transferJoint( w, kAwakeSet, joint );
+			}
+			jointKey = joint.edges[edgeIndex].nextKey;
+		}
+		recreateProxies( type );
+	}
+	else if ( type == kStaticBody )
+	{
+		transferBody( w, kStaticSet, body );
+		removeBodyFromIsland( w, body );
+		ptr( w, w->sims )[body.id].isFast = false;
+		int jointKey = body.headJointKey;
+		while ( jointKey != kNull )
+		{
+			Joint& joint = joints[jointKey >> 1];
+			int edgeIndex = jointKey & 1;
+			jointKey = joint.edges[edgeIndex].nextKey;
+			const Body& other = bodies[joint.edges[edgeIndex ^ 1].bodyId];
+			if ( joint.setIndex == kDisabledSet )
+				continue;
+			if ( other.setIndex == kStaticSet )
+			{
+				transferJoint( w, kStaticSet, joint );
+			}
+			else
+			{
+				transferJoint( w, kStaticSet, joint );
+				transferJoint( w, kAwakeSet, joint );
+			}
+		}
+		recreateProxies( kStaticBody );
+	}
+	else
+	{
+		recreateProxies( type );
+	}
+	{
+		int jointKey = body.headJointKey;
+		while ( jointKey != kNull )
+		{
+			Joint& joint = joints[jointKey >> 1];
+			int edgeIndex = jointKey & 1;
+			jointKey = joint.edges[edgeIndex].nextKey;
+			const Body& other = bodies[joint.edges[edgeIndex ^ 1].bodyId];
+			if ( other.setIndex == kDisabledSet )
+				continue;
+			if ( body.type == kStaticBody && other.type == kStaticBody )
+				continue;
+			linkJoint( w, joint, false );
+		}
+		mergeAwakeIslands( w );
+	}
+	updateBodyMassData( w, body );
+	return ok;
 }
 
 // shape.c:230-316 b2DestroyShapeInternal + :318-337 b2DestroyShape
@@ -237,7 +484,6 @@ inline void destroyShape( World* w, int shapeId, bool updateBodyMass )
 		if ( c.shapeIdA == shapeId || c.shapeIdB == shapeId )
 			destroyContact( w, contactId, true );
 	}
-	noteShapeEventFlags( w, shape, -1 );
 	freeId( w, w->shapeIds, shapeId );
 	shape.id = kNull;
 	if ( updateBodyMass )

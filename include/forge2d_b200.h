@@ -336,7 +336,7 @@ F2D_API void b2Body_ApplyTorque( b2BodyId bodyId, float torque, bool wake );				
 F2D_API void b2Body_ApplyLinearImpulse( b2BodyId bodyId, b2Vec2 impulse, b2Vec2 point, bool wake ); // body.c:952
 F2D_API void b2Body_ApplyLinearImpulseToCenter( b2BodyId bodyId, b2Vec2 impulse, bool wake );		  // body.c:975
 F2D_API void b2Body_ApplyAngularImpulse( b2BodyId bodyId, float impulse, bool wake );				  // body.c:997
-F2D_API void b2Body_SetType( b2BodyId bodyId, b2BodyType type );									  // body.c:1036 (reports unsupported)
+F2D_API void b2Body_SetType( b2BodyId bodyId, b2BodyType type );									  // body.c:1036
 F2D_API void b2Body_SetName( b2BodyId bodyId, const char* name );									  // body.c:1286
 F2D_API const char* b2Body_GetName( b2BodyId bodyId );											  // body.c:1306
 F2D_API void b2Body_SetUserData( b2BodyId bodyId, void* userData );
@@ -356,8 +356,8 @@ F2D_API bool b2Body_IsSleepEnabled( b2BodyId bodyId );
 F2D_API void b2Body_SetSleepThreshold( b2BodyId bodyId, float sleepThreshold );
 F2D_API float b2Body_GetSleepThreshold( b2BodyId bodyId );
 F2D_API void b2Body_EnableSleep( b2BodyId bodyId, bool enableSleep );								  // body.c:1538
-F2D_API void b2Body_Disable( b2BodyId bodyId );													  // body.c:1557 (reports unsupported)
-F2D_API void b2Body_Enable( b2BodyId bodyId );													  // body.c:1628 (reports unsupported)
+F2D_API void b2Body_Disable( b2BodyId bodyId );													  // body.c:1557
+F2D_API void b2Body_Enable( b2BodyId bodyId );													  // body.c:1628
 F2D_API void b2Body_SetFixedRotation( b2BodyId bodyId, bool flag );								  // body.c:1722
 F2D_API bool b2Body_IsFixedRotation( b2BodyId bodyId );
 F2D_API void b2Body_SetBullet( b2BodyId bodyId, bool flag );

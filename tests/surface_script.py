@@ -167,6 +167,17 @@ def run(lib, frames=200, on_frame=None):
             lib.b2Joint_SetCollideConnected(rj[0], False)
             lib.b2Body_ApplyMassFromShapes(pile[11])
             lib.b2Body_EnableSleep(pile[13], False)
+        if f == 100:
+            lib.b2Body_Disable(pile[15])              # contacts destroyed, proxies removed, joints (none) re-homed
+            lib.b2Body_Disable(chain[0])              # a jointed body: its two joints move to the disabled list
+            lib.b2Body_SetType(pile[16], 0)           # dynamic -> static
+            lib.b2Body_SetType(slider, 1)             # dynamic -> kinematic, joint stays in the graph
+        if f == 120:
+            lib.b2Body_Enable(pile[15])
+            lib.b2Body_Enable(chain[0])
+            lib.b2Body_SetType(pile[16], 2)           # static -> dynamic
+            lib.b2Body_SetType(slider, 2)
+            lib.b2Body_SetType(bar, 2)                # the static anchor bar becomes dynamic: every joint re-coloured
         if f == 150:
             lib.b2Body_SetAwake(pile[14], False)      # force an island to sleep (split first if it lost constraints)
         if f == 160:
@@ -176,7 +187,7 @@ def run(lib, frames=200, on_frame=None):
         if on_frame is not None:
             on_frame(f, s)
         s.step()
-        if f % 10 == 4 or f in (60, 61, 75, 76, 90, 150, 151, 160, 161):
+        if f % 10 == 4 or f in (60, 61, 75, 76, 90, 100, 101, 120, 121, 150, 151, 160, 161):
             observe("f%d." % f)
             snaps.append((f, H.snapshot(lib, world)))
     ev = H.events(lib, world)

@@ -48,10 +48,11 @@ def test_all_joint_types_bit_identical_emu(ref, emu):
     _joint_zoo(ref, emu, 300, 5)
 
 
-def test_unsupported_mutators_fail_loudly(emu):
+def test_in_step_host_callbacks_fail_loudly(emu):
+    import ctypes as C
     s = scenes.bench2d(emu, rows=2)
     emu.f2dClearLastError()
-    emu.b2Body_SetType(s.bodies[1], 0)
+    emu.b2World_SetPreSolveCallback(s.world, C.c_void_p(1), None)
     assert b"not supported" in emu.f2dGetLastError()
     s.destroy()
 
