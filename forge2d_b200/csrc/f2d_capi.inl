@@ -110,11 +110,12 @@ static Caps capsWith( const World* w, int B, int S, int C, int J )
 	c.joints = J;
 	c.contactEvents = w != nullptr && w->contactEventCapable > 0 ? C : 16;
 	c.hitEvents = w != nullptr && w->hitEventCapable > 0 ? C : 16;
+	c.sensors = 0;
 	return c;
 }
 
 // Grows the image when any entity array is short of `need*` free slots.
-static void reserve( HostWorld& hw, int needBodies, int needShapes, int needContacts, int needJoints )
+static void reserve( HostWorld& hw, int needBodies, int needShapes, int needContacts, int needJoints, int needSensors = 0 )
 {
 	World* w = hw.img;
 	Caps c = hw.caps;
@@ -141,6 +142,11 @@ static void reserve( HostWorld& hw, int needBodies, int needShapes, int needCont
 	if ( wantJ > c.joints )
 	{
 		c.joints = roundCap( wantJ, 64 );
+		grow = true;
+	}
+	if ( w->sensors.count + needSensors > c.sensors )
+	{
+		c.sensors = roundCap( w->sensors.count + needSensors, 8 );
 		grow = true;
 	}
 	Caps ev = capsWith( w, c.bodies, c.shapes, c.contacts, c.joints );
@@ -601,6 +607,8 @@ b2SensorEvents b2World_GetSensorEvents( b2WorldId worldId )
 		return ev;
 	World* w = hw->img;
 	int endIndex = 1 - w->endEventArrayIndex;
+	refreshArray( *hw, w->sensorBeginEvents );
+	refreshArray( *hw, w->sensorEndEvents[endIndex] );
 	ev.beginEvents = reinterpret_cast<b2SensorBeginTouchEvent*>( ptr( w, w->sensorBeginEvents ) );
 	ev.endEvents = reinterpret_cast<b2SensorEndTouchEvent*>( ptr( w, w->sensorEndEvents[endIndex] ) );
 	ev.beginCount = w->sensorBeginEvents.count;
@@ -891,7 +899,7 @@ static b2ShapeId createShapeCommon( b2BodyId bodyId, const b2ShapeDef* def, cons
 	if ( b == nullptr )
 		return b2ShapeId{ 0, 0, 0 };
 	int bodyIndex = b->id;
-	reserve( *hw, 0, 2, 0, 0 );
+	reserve( *hw, 0, 2, 0, 0, def->isSensor ? 1 : 0 );
 	World* w = hw->img;
 	if ( w->locked )
 		return b2ShapeId{ 0, 0, 0 };

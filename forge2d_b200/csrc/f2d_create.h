@@ -316,8 +316,18 @@ inline int createShape( World* w, int bodyId, const ShapeParams& def, const void
 	shape.sensorIndex = kNull;
 	if ( def.isSensor )
 	{
-		// sensors are not on the device path yet: flagged so that stepping refuses loudly instead of ignoring them
-		setError( w, kErrUnsupported, __LINE__ );
+		// shape.c:84-95: a sensor record with two empty overlap lists
+		if ( w->sensors.count >= w->sensors.cap )
+		{
+			setError( w, kErrCapacity, __LINE__ );
+		}
+		else
+		{
+			shape.sensorIndex = w->sensors.count;
+			Sensor sensor = { shapeId, 0, 0, 0 };
+			F2D_PUSH( w, w->sensors, sensor );
+			w->sensorRefs.count = 2 * kSensorOverlapCap * w->sensors.count; // slots in use (kept for re-layout copies)
+		}
 	}
 	if ( def.updateBodyMass )
 		updateBodyMassData( w, body );

@@ -13,6 +13,7 @@ struct Caps
 {
 	int bodies, shapes, contacts, joints;
 	int contactEvents, hitEvents; // event array capacities
+	int sensors;				  // sensor shapes
 };
 
 struct ArraySlot
@@ -49,6 +50,10 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.jointSims, J, true );
 	add( w.islands, B, true );
 	add( w.sets, B + 8, true );
+	const int N = c.sensors < 1 ? 1 : c.sensors;
+	add( w.sensors, N, true );
+	add( w.sensorRefs, 2 * kSensorOverlapCap * N, true );
+	add( w.sensorBits, N / 64 + 2, false );
 	add( w.staticBodies, B, true );
 	add( w.disabledBodies, B, true );
 	add( w.awakeBodies, B, true );
@@ -83,9 +88,11 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.endEvents[0], c.contactEvents, true );
 	add( w.endEvents[1], c.contactEvents, true );
 	add( w.hitEvents, c.hitEvents, true );
-	add( w.sensorBeginEvents, 4, true );
-	add( w.sensorEndEvents[0], 4, true );
-	add( w.sensorEndEvents[1], 4, true );
+	// a step can begin or end at most one overlap per list slot of every sensor
+	const int SE = c.sensors < 1 ? 4 : 2 * kSensorOverlapCap * c.sensors;
+	add( w.sensorBeginEvents, SE, true );
+	add( w.sensorEndEvents[0], SE, true );
+	add( w.sensorEndEvents[1], SE, true );
 	add( w.contactBits, C / 64 + 2, false );
 	add( w.stateOffsets, C / 64 + 2, false );
 	add( w.stateList, C, false );

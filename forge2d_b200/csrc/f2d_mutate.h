@@ -170,7 +170,35 @@ inline void destroyShapeProxy( World* w, Shape& shape )
 	}
 }
 
-// body.c:343-444 b2DestroyBody (chains and sensors are not on this path: they cannot be created)
+// sensor.c:353-390 b2DestroySensor: end events for the current overlaps, then swap-remove the sensor slot (the moved
+// sensor's two list blocks travel with it)
+inline void destroySensor( World* w, Shape& sensorShape )
+{
+	const int index = sensorShape.sensorIndex;
+	Sensor* sensors = ptr( w, w->sensors );
+	ShapeRef* refs = ptr( w, w->sensorRefs );
+	const Sensor& sensor = sensors[index];
+	const ShapeRef* refs2 = refs + (size_t)( 2 * index + sensor.flip ) * kSensorOverlapCap;
+	for ( int i = 0; i < sensor.count2; ++i )
+	{
+		SensorEvent ev = { ShapeId{ sensorShape.id + 1, w->worldId, sensorShape.generation },
+						   ShapeId{ refs2[i].shapeId + 1, w->worldId, refs2[i].generation } };
+		F2D_PUSH( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
+	}
+	const int last = w->sensors.count - 1;
+	if ( index != last )
+	{
+		sensors[index] = sensors[last];
+		memcpy( refs + (size_t)( 2 * index ) * kSensorOverlapCap, refs + (size_t)( 2 * last ) * kSensorOverlapCap,
+				sizeof( ShapeRef ) * 2 * kSensorOverlapCap );
+		ptr( w, w->shapes )[sensors[index].shapeId].sensorIndex = index;
+	}
+	w->sensors.count -= 1;
+	w->sensorRefs.count = 2 * kSensorOverlapCap * w->sensors.count;
+	sensorShape.sensorIndex = kNull;
+}
+
+// body.c:343-444 b2DestroyBody (chains cannot be created on this path)
 inline void destroyBody( World* w, int bodyId )
 {
 	Body& body = ptr( w, w->bodies )[bodyId];
@@ -190,6 +218,8 @@ inline void destroyBody( World* w, int bodyId )
 	while ( shapeId != kNull )
 	{
 		Shape& shape = shapes[shapeId];
+		if ( shape.sensorIndex != kNull )
+			destroySensor( w, shape );
 		destroyShapeProxy( w, shape );
 		freeId( w, w->shapeIds, shapeId );
 		shape.id = kNull;
@@ -484,6 +514,8 @@ inline void destroyShape( World* w, int shapeId, bool updateBodyMass )
 		if ( c.shapeIdA == shapeId || c.shapeIdB == shapeId )
 			destroyContact( w, contactId, true );
 	}
+	if ( shape.sensorIndex != kNull )
+		destroySensor( w, shape );
 	freeId( w, w->shapeIds, shapeId );
 	shape.id = kNull;
 	if ( updateBodyMass )

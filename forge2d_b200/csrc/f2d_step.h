@@ -1893,6 +1893,172 @@ F2D_HDF inline void reportHitEvents( World* w )
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ sensors
+F2D_HD ShapeRef* sensorList( World* w, int sensorIndex, int which )
+{
+	return ptr( w, w->sensorRefs ) + (size_t)( 2 * sensorIndex + which ) * kSensorOverlapCap;
+}
+
+// One sensor shape: sensor.c:101-212. Swaps its overlap lists, queries the three trees with the shape's AABB, keeps
+// the visitors whose GJK distance is (numerically) zero, sorts them by (shape id, generation) and flags the sensor when
+// the set differs from the previous step's.
+F2D_HDF inline void sensorTask( World* w, int sensorIndex )
+{
+	Sensor& sensor = ptr( w, w->sensors )[sensorIndex];
+	const Shape* shapes = ptr( w, w->shapes );
+	const Shape& sensorShape = shapes[sensor.shapeId];
+	uint64_t* bits = ptr( w, w->sensorBits );
+	sensor.flip ^= 1;
+	sensor.count1 = sensor.count2;
+	sensor.count2 = 0;
+	const ShapeRef* refs1 = sensorList( w, sensorIndex, sensor.flip ^ 1 );
+	ShapeRef* refs2 = sensorList( w, sensorIndex, sensor.flip );
+	const Body& body = ptr( w, w->bodies )[sensorShape.bodyId];
+	if ( body.setIndex == kDisabledSet || sensorShape.enableSensorEvents == false )
+	{
+		if ( sensor.count1 != 0 )
+			atomOr64( bits + ( sensorIndex >> 6 ), 1ull << ( sensorIndex & 63 ) );
+		return;
+	}
+	const BodySim* sims = ptr( w, w->sims );
+	const Xf transform = sims[sensorShape.bodyId].transform;
+	const ShapeProxy sensorProxy = makeShapeProxy( sensorShape );
+	int count2 = 0;
+	auto visit = [&]( int, uint64_t userData ) -> bool {
+		int shapeId = (int)userData;
+		if ( shapeId == sensor.shapeId )
+			return true;
+		const Shape& other = shapes[shapeId];
+		if ( other.enableSensorEvents == false )
+			return true;
+		if ( other.bodyId == sensorShape.bodyId )
+			return true;
+		if ( shouldShapesCollide( sensorShape.filter, other.filter ) == false )
+			return true;
+		Xf otherTransform = sims[other.bodyId].transform;
+		SimplexCache cache;
+		memset( &cache, 0, sizeof( cache ) );
+		DistanceOutput out = shapeDistance( sensorProxy, makeShapeProxy( other ), transform, otherTransform, true, &cache );
+		if ( ( out.distance < 10.0f * FLT_EPSILON ) == false )
+			return true;
+		if ( count2 >= kSensorOverlapCap )
+		{
+			setError( w, kErrCapacity, __LINE__ );
+			return true;
+		}
+		refs2[count2].shapeId = shapeId;
+		refs2[count2].generation = other.generation;
+		refs2[count2].pad = 0;
+		count2 += 1;
+		return true;
+	};
+	for ( int tree = 0; tree < 3; ++tree )
+		treeQuery( w, w->trees[tree], sensorShape.aabb, sensorShape.filter.mask, visit );
+	// (shape id, generation) ascending: keys are unique, so any sort reproduces qsort's result (sensor.c:185)
+	for ( int i = 1; i < count2; ++i )
+	{
+		ShapeRef key = refs2[i];
+		int j = i - 1;
+		while ( j >= 0 && ( refs2[j].shapeId > key.shapeId || ( refs2[j].shapeId == key.shapeId && refs2[j].generation > key.generation ) ) )
+		{
+			refs2[j + 1] = refs2[j];
+			j -= 1;
+		}
+		refs2[j + 1] = key;
+	}
+	sensor.count2 = count2;
+	bool changed = sensor.count1 != count2;
+	for ( int i = 0; i < count2 && changed == false; ++i )
+		changed = refs1[i].shapeId != refs2[i].shapeId || refs1[i].generation != refs2[i].generation;
+	if ( changed )
+		atomOr64( bits + ( sensorIndex >> 6 ), 1ull << ( sensorIndex & 63 ) );
+}
+
+// Begin / end events of one flagged sensor: ordered merge of the two sorted lists (sensor.c:264-345)
+F2D_HDF inline void sensorEvents( World* w, int sensorIndex )
+{
+	const Sensor& sensor = ptr( w, w->sensors )[sensorIndex];
+	const Shape& sensorShape = ptr( w, w->shapes )[sensor.shapeId];
+	const ShapeId sensorId = { sensor.shapeId + 1, w->worldId, sensorShape.generation };
+	const ShapeRef* refs1 = sensorList( w, sensorIndex, sensor.flip ^ 1 );
+	const ShapeRef* refs2 = sensorList( w, sensorIndex, sensor.flip );
+	auto ended = [&]( const ShapeRef& r ) {
+		SensorEvent ev = { sensorId, ShapeId{ r.shapeId + 1, w->worldId, r.generation } };
+		F2D_PUSH( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
+	};
+	auto began = [&]( const ShapeRef& r ) {
+		SensorEvent ev = { sensorId, ShapeId{ r.shapeId + 1, w->worldId, r.generation } };
+		F2D_PUSH( w, w->sensorBeginEvents, ev );
+	};
+	int i1 = 0, i2 = 0;
+	while ( i1 < sensor.count1 && i2 < sensor.count2 )
+	{
+		const ShapeRef& r1 = refs1[i1];
+		const ShapeRef& r2 = refs2[i2];
+		if ( r1.shapeId == r2.shapeId )
+		{
+			if ( r1.generation < r2.generation )
+			{
+				ended( r1 );
+				i1 += 1;
+			}
+			else if ( r1.generation > r2.generation )
+			{
+				began( r2 );
+				i2 += 1;
+			}
+			else
+			{
+				i1 += 1;
+				i2 += 1;
+			}
+		}
+		else if ( r1.shapeId < r2.shapeId )
+		{
+			ended( r1 );
+			i1 += 1;
+		}
+		else
+		{
+			began( r2 );
+			i2 += 1;
+		}
+	}
+	for ( ; i1 < sensor.count1; ++i1 )
+		ended( refs1[i1] );
+	for ( ; i2 < sensor.count2; ++i2 )
+		began( refs2[i2] );
+}
+
+// sensor.c:215-351 b2OverlapSensors
+template <class Team> F2D_HDF inline void overlapSensors( World* w, Team& t )
+{
+	const int sensorCount = w->sensors.count;
+	if ( sensorCount == 0 )
+		return;
+	uint64_t* bits = ptr( w, w->sensorBits );
+	const int words = ( sensorCount + 63 ) >> 6;
+	for ( int k = t.rank(); k < words; k += t.size() )
+		bits[k] = 0;
+	t.sync();
+	for ( int i = t.rank(); i < sensorCount; i += t.size() )
+		sensorTask( w, i );
+	t.sync();
+	if ( t.rank() == 0 )
+	{
+		for ( int k = 0; k < words; ++k )
+		{
+			uint64_t word = bits[k];
+			for ( int b = 0; word != 0; ++b, word >>= 1 )
+			{
+				if ( word & 1ull )
+					sensorEvents( w, 64 * k + b );
+			}
+		}
+	}
+	t.sync();
+}
+
 template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 {
 	const int awakeBodyCount = w->step.awakeBodyCount;
@@ -2034,7 +2200,8 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		F2D_MARK( w, t, pfSleep );
 	}
 
-	// sensors would run here (world.c:788-793): no sensor shapes on the device path yet
+	// world.c:788-793
+	overlapSensors( w, t );
 
 	if ( t.rank() == 0 )
 	{

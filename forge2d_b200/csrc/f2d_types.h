@@ -267,6 +267,20 @@ struct ContactSim
 	int32_t pad2; // 192 bytes: records start on 16-byte boundaries
 };
 static_assert( sizeof( ContactSim ) == 192, "ContactSim layout" );
+// B2/src/sensor.h:11-24. The two overlap lists of a sensor are fixed-capacity blocks of World::sensorRefs
+// (block = sensor index * 2 * kSensorOverlapCap, second list kSensorOverlapCap further); `flip` says which is "overlaps2".
+constexpr int kSensorOverlapCap = 64;
+struct ShapeRef
+{
+	int32_t shapeId;
+	uint16_t generation, pad;
+};
+struct Sensor
+{
+	int32_t shapeId;
+	int32_t count1, count2; // overlaps1 = previous step, overlaps2 = this step
+	int32_t flip;			// 0: overlaps2 is the first half of the block, 1: the second half
+};
 // B2/src/island.h:25-57
 struct Island
 {
@@ -579,6 +593,9 @@ struct World
 	Arr<JointSim> jointSims;
 	Arr<Island> islands;
 	Arr<SolverSet> sets;
+	Arr<Sensor> sensors;	   // dense, swap-removed (shape.c:283-305); Shape::sensorIndex points here
+	Arr<ShapeRef> sensorRefs;  // 2 * kSensorOverlapCap per sensor slot
+	Arr<uint64_t> sensorBits;  // sensors whose overlap set changed this step (sensor.c:250-262)
 
 	// set membership lists (ids)
 	Arr<int32_t> staticBodies, disabledBodies, awakeBodies;

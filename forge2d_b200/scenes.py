@@ -433,7 +433,76 @@ def joint_zoo(lib, sets=3, create=None, **world_kw):
     return scene
 
 
+def sensor_field(lib, count=30, create=None, **world_kw):
+    """Sensor shapes (static zones, a kinematic sweeper, a sensor riding on a dynamic body) with boxes, circles and
+    capsules raining through them; some visitors opt out of sensor events."""
+    world = _world(lib, create=create, **world_kw)
+    bodies = [_static_segment(lib, world, (-30.0, 0.0), (30.0, 0.0))]
+    sensors = []
+    sd = lib.b2DefaultShapeDef()
+    ssd = lib.b2DefaultShapeDef()
+    ssd.isSensor = True
+    ssd.enableSensorEvents = True
+    # static zones
+    for k, x in enumerate((-8.0, 0.0, 8.0)):
+        bd = lib.b2DefaultBodyDef()
+        bd.position = A.Vec2(x, 3.0 + k)
+        zone = lib.b2CreateBody(world, C.byref(bd))
+        bodies.append(zone)
+        if k == 1:
+            c = A.Circle(A.Vec2(0.0, 0.0), 1.5)
+            sensors.append(lib.b2CreateCircleShape(zone, C.byref(ssd), C.byref(c)))
+        else:
+            box = lib.b2MakeBox(2.0, 0.75)
+            sensors.append(lib.b2CreatePolygonShape(zone, C.byref(ssd), C.byref(box)))
+    # kinematic sweeper
+    bd = lib.b2DefaultBodyDef()
+    bd.type = 1
+    bd.position = A.Vec2(-12.0, 1.5)
+    bd.linearVelocity = A.Vec2(3.0, 0.0)
+    sweeper = lib.b2CreateBody(world, C.byref(bd))
+    bodies.append(sweeper)
+    cap = A.Capsule(A.Vec2(0.0, -1.0), A.Vec2(0.0, 1.0), 0.4)
+    sensors.append(lib.b2CreateCapsuleShape(sweeper, C.byref(ssd), C.byref(cap)))
+    # a dynamic carrier with a solid box and a larger sensor halo
+    bd = lib.b2DefaultBodyDef()
+    bd.type = 2
+    bd.position = A.Vec2(4.0, 9.0)
+    carrier = lib.b2CreateBody(world, C.byref(bd))
+    bodies.append(carrier)
+    lib.b2CreatePolygonShape(carrier, C.byref(sd), C.byref(_box(lib, 0.4)))
+    halo = A.Circle(A.Vec2(0.0, 0.0), 1.6)
+    sensors.append(lib.b2CreateCircleShape(carrier, C.byref(ssd), C.byref(halo)))
+    state = [12345]
+
+    def rnd():
+        state[0] = (1103515245 * state[0] + 12345) & 0x7FFFFFFF
+        return state[0] / float(0x7FFFFFFF)
+
+    for i in range(count):
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        bd.position = A.Vec2(_f32(-12.0 + 24.0 * rnd()), _f32(6.0 + 10.0 * rnd()))
+        b = lib.b2CreateBody(world, C.byref(bd))
+        bodies.append(b)
+        vsd = lib.b2DefaultShapeDef()
+        vsd.enableSensorEvents = (i % 5) != 0
+        kind = i % 3
+        if kind == 0:
+            lib.b2CreatePolygonShape(b, C.byref(vsd), C.byref(_box(lib, 0.3)))
+        elif kind == 1:
+            c = A.Circle(A.Vec2(0.0, 0.0), 0.3)
+            lib.b2CreateCircleShape(b, C.byref(vsd), C.byref(c))
+        else:
+            c = A.Capsule(A.Vec2(-0.3, 0.0), A.Vec2(0.3, 0.0), 0.2)
+            lib.b2CreateCapsuleShape(b, C.byref(vsd), C.byref(c))
+    scene = Scene(lib, world, bodies, "sensor_field_%d" % count)
+    scene.sensors = sensors
+    return scene
+
+
 SCENES = {
+    "sensor_field": sensor_field,
     "joint_zoo": joint_zoo,
     "bench2d": bench2d,
     "large_pyramid": large_pyramid,

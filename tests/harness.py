@@ -103,7 +103,12 @@ def events(lib, world):
     for i in range(be.moveCount):
         m = be.moveEvents[i]
         moves[i] = (m.transform.p.x, m.transform.p.y, m.transform.q.c, m.transform.q.s, m.bodyId.index1, m.fellAsleep)
-    return {"begin": begin, "end": end, "hit": hit, "moves": moves}
+    se = lib.b2World_GetSensorEvents(world)
+    sbegin = [(se.beginEvents[i].sensorShapeId.index1, se.beginEvents[i].visitorShapeId.index1,
+               se.beginEvents[i].visitorShapeId.generation) for i in range(se.beginCount)]
+    send = [(se.endEvents[i].sensorShapeId.index1, se.endEvents[i].visitorShapeId.index1,
+             se.endEvents[i].visitorShapeId.generation) for i in range(se.endCount)]
+    return {"begin": begin, "end": end, "hit": hit, "moves": moves, "sensor_begin": sbegin, "sensor_end": send}
 
 
 FLOAT_KINDS = "f"

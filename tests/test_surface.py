@@ -21,6 +21,7 @@ def _compare_sessions(ref, lib):
 
 
 def _joint_zoo(ref, lib, frames, every, mode=None):
+    lib.f2dClearLastError()
     a = scenes.joint_zoo(ref, sets=3)
     b = scenes.joint_zoo(lib, sets=3)
     if mode is not None:
@@ -152,3 +153,46 @@ def test_queries_match_reference_gpu(ref, gpu):
     b, sb = _query_session(gpu)
     assert a == b
     assert H.diff(sa, sb) == []
+
+
+# ---- sensors -------------------------------------------------------------------------------------------------
+def _sensor_session(ref, lib, frames=260, mode=None):
+    a = scenes.sensor_field(ref)
+    b = scenes.sensor_field(lib)
+    lib.f2dClearLastError()
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(b.world, mode)
+    seen = 0
+    for f in range(frames):
+        if f == 90:      # a visitor and a sensor shape disappear mid-run; a visitor opts out
+            for s, L in ((a, ref), (b, lib)):
+                L.b2DestroyBody(s.bodies[9])
+                L.b2DestroyShape(s.sensors[0], False)
+                import ctypes as C
+                from forge2d_b200 import _abi as A
+                arr = (A.ShapeId * 2)()
+                L.b2Body_GetShapes(s.bodies[12], arr, 2)
+                L.b2Shape_EnableSensorEvents(arr[0], False)
+        a.step()
+        b.step()
+        ea, eb = H.events(ref, a.world), H.events(lib, b.world)
+        assert ea["sensor_begin"] == eb["sensor_begin"], "sensor begin events, frame %d" % f
+        assert ea["sensor_end"] == eb["sensor_end"], "sensor end events, frame %d" % f
+        seen += len(ea["sensor_begin"]) + len(ea["sensor_end"])
+        if f % 20 == 0 or f == frames - 1:
+            d = H.diff(H.snapshot(ref, a.world), H.snapshot(lib, b.world))
+            assert d == [], "frame %d: %s" % (f, d[:6])
+    assert seen > 40, "the scene is supposed to produce sensor traffic (saw %d events)" % seen
+    assert lib.f2dGetLastError() == b""
+    a.destroy()
+    b.destroy()
+
+
+def test_sensor_events_match_reference_emu(ref, emu):
+    _sensor_session(ref, emu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_sensor_events_match_reference_gpu(ref, gpu, mode):
+    _sensor_session(ref, gpu, mode=mode)
