@@ -170,6 +170,16 @@ class WheelJointDef(C.Structure):
                 ("collideConnected", c_bool), ("userData", c_void_p), ("internalValue", c_int)]
 
 
+class ChainId(C.Structure):
+    _fields_ = [("index1", C.c_int32), ("world0", C.c_uint16), ("generation", C.c_uint16)]
+
+
+class ChainDef(C.Structure):
+    _fields_ = [("userData", c_void_p), ("points", C.POINTER(Vec2)), ("count", c_int),
+                ("materials", C.POINTER(SurfaceMaterial)), ("materialCount", c_int), ("filter", Filter),
+                ("isLoop", c_bool), ("enableSensorEvents", c_bool), ("internalValue", c_int)]
+
+
 class QueryFilter(C.Structure):
     _fields_ = [("categoryBits", C.c_uint64), ("maskBits", C.c_uint64)]
 
@@ -432,6 +442,17 @@ B2_FUNCTIONS = {
     "b2Joint_WakeBodies": (None, [JointId]),
     "b2Joint_GetConstraintForce": (Vec2, [JointId]),
     "b2Joint_GetConstraintTorque": (c_float, [JointId]),
+    "b2DefaultChainDef": (ChainDef, []),
+    "b2CreateChain": (ChainId, [BodyId, C.POINTER(ChainDef)]),
+    "b2DestroyChain": (None, [ChainId]),
+    "b2Chain_IsValid": (c_bool, [ChainId]),
+    "b2Chain_GetWorld": (WorldId, [ChainId]),
+    "b2Chain_GetSegmentCount": (c_int, [ChainId]),
+    "b2Chain_GetSegments": (c_int, [ChainId, C.POINTER(ShapeId), c_int]),
+    "b2Chain_SetFriction": (None, [ChainId, c_float]),
+    "b2Chain_GetFriction": (c_float, [ChainId]),
+    "b2Chain_SetRestitution": (None, [ChainId, c_float]),
+    "b2Chain_GetRestitution": (c_float, [ChainId]),
     "b2DefaultQueryFilter": (QueryFilter, []),
     "b2World_OverlapAABB": (TreeStats, [WorldId, AABB, QueryFilter, OverlapResultFcn, c_void_p]),
     "b2World_CastRay": (TreeStats, [WorldId, Vec2, Vec2, QueryFilter, CastResultFcn, c_void_p]),

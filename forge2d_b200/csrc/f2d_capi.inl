@@ -14,6 +14,7 @@
 #include <float.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 namespace f2d
 {
@@ -38,6 +39,15 @@ struct HostWorld
 	int launchMode = -1;
 	void* backend = nullptr; // device mirror, streams, events
 	bool eventsFresh = true; // event arrays of `img` reflect the last step
+	// Chain records (shape.h b2ChainShape): host-only bookkeeping — the step only ever sees the chain-SEGMENT shapes
+	struct Chain
+	{
+		int id = -1, bodyId = -1, nextChainId = -1;
+		uint16_t generation = 0;
+		std::vector<int> shapeIndices;
+		std::vector<b2SurfaceMaterial> materials;
+	};
+	std::vector<Chain> chains;
 	bool headerFresh = true;
 };
 

@@ -24,6 +24,16 @@ void b2DestroyBody( b2BodyId bodyId ) // body.c:343-444
 	Body* b = writableBody( bodyId, &hw );
 	if ( b == nullptr )
 		return;
+	// body.c:392-405: the attached chain records go with the body (their segment shapes are destroyed as shapes)
+	for ( int chainId = b->headChainId; chainId != kNull; )
+	{
+		HostWorld::Chain& chain = hw->chains[chainId];
+		freeId( hw->img, hw->img->chainIds, chainId );
+		chain.id = kNull;
+		chain.shapeIndices.clear();
+		chain.materials.clear();
+		chainId = chain.nextChainId;
+	}
 	destroyBody( hw->img, b->id );
 }
 b2Vec2 b2Body_GetLocalPoint( b2BodyId bodyId, b2Vec2 worldPoint ) // body.c:656-662
@@ -1128,6 +1138,210 @@ b2JointId b2CreateWheelJoint( b2WorldId worldId, const b2WheelJointDef* def ) //
 	j.enableLimit = def->enableLimit;
 	j.enableMotor = def->enableMotor;
 	return finishJoint( c, def->collideConnected );
+}
+
+// ---------------------------------------------------------------------------------------------------------------- chains
+// shape.c:339-577, :1476-1576. A chain is a run of one-sided chain-segment shapes with ghost vertices; the record that
+// ties them together is only needed by these API calls and stays on the host (HostWorld::chains).
+b2ChainDef b2DefaultChainDef( void ) // types.c:76-88
+{
+	static b2SurfaceMaterial defaultMaterial = { 0.6f, 0.0f, 0.0f, 0.0f, 0, 0 };
+	b2ChainDef def;
+	memset( &def, 0, sizeof( def ) );
+	def.materials = &defaultMaterial;
+	def.materialCount = 1;
+	def.filter = b2DefaultFilter();
+	def.internalValue = kSecretCookie;
+	return def;
+}
+static HostWorld::Chain* chainFromId( b2ChainId id, HostWorld** outWorld )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return nullptr;
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= (int)hw->chains.size() )
+		return nullptr;
+	HostWorld::Chain& c = hw->chains[index];
+	if ( c.id != index || c.generation != id.generation )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return &c;
+}
+b2ChainId b2CreateChain( b2BodyId bodyId, const b2ChainDef* def ) // shape.c:339-477
+{
+	if ( def->internalValue != kSecretCookie || def->count < 4 || def->materialCount < 1 )
+		return b2ChainId{ 0, 0, 0 };
+	HostWorld* hw = nullptr;
+	Body* b = writableBody( bodyId, &hw );
+	if ( b == nullptr )
+		return b2ChainId{ 0, 0, 0 };
+	const int bodyIndex = b->id;
+	const int n = def->count;
+	reserve( *hw, 0, n + 2, 0, 0 );
+	World* w = hw->img;
+	int chainId = allocId( w, w->chainIds );
+	if ( chainId == (int)hw->chains.size() )
+		hw->chains.push_back( HostWorld::Chain() );
+	HostWorld::Chain& chain = hw->chains[chainId];
+	Body& body = ptr( w, w->bodies )[bodyIndex];
+	chain.id = chainId;
+	chain.bodyId = bodyIndex;
+	chain.nextChainId = body.headChainId;
+	chain.generation += 1;
+	chain.materials.assign( def->materials, def->materials + def->materialCount );
+	chain.shapeIndices.clear();
+	body.headChainId = chainId;
+
+	ShapeParams p;
+	{
+		b2ShapeDef sd = b2DefaultShapeDef();
+		p.userData = (uint64_t)(uintptr_t)def->userData;
+		p.density = sd.density;
+		p.filter = Filter{ def->filter.categoryBits, def->filter.maskBits, def->filter.groupIndex };
+		p.isSensor = false;
+		p.enableSensorEvents = def->enableSensorEvents;
+		p.enableContactEvents = false;
+		p.enableHitEvents = false;
+		p.enablePreSolveEvents = sd.enablePreSolveEvents;
+		p.invokeContactCreation = sd.invokeContactCreation;
+		p.updateBodyMass = sd.updateBodyMass;
+	}
+	const int materialCount = def->materialCount;
+	const b2Vec2* pts = def->points;
+	auto segment = [&]( int g1, int a, int c, int g2, int materialIndex ) {
+		const b2SurfaceMaterial& mat = def->materials[materialCount == 1 ? 0 : materialIndex];
+		p.friction = mat.friction;
+		p.restitution = mat.restitution;
+		p.rollingResistance = mat.rollingResistance;
+		p.tangentSpeed = mat.tangentSpeed;
+		p.userMaterialId = mat.userMaterialId;
+		p.customColor = mat.customColor;
+		ChainSegment cs;
+		cs.ghost1 = V2{ pts[g1].x, pts[g1].y };
+		cs.segment.p1 = V2{ pts[a].x, pts[a].y };
+		cs.segment.p2 = V2{ pts[c].x, pts[c].y };
+		cs.ghost2 = V2{ pts[g2].x, pts[g2].y };
+		cs.chainId = chainId;
+		chain.shapeIndices.push_back( createShape( w, bodyIndex, p, &cs, kChainSegment ) );
+	};
+	if ( def->isLoop )
+	{
+		int prev = n - 1;
+		for ( int i = 0; i < n - 2; ++i )
+		{
+			segment( prev, i, i + 1, i + 2, i );
+			prev = i;
+		}
+		segment( n - 3, n - 2, n - 1, 0, n - 2 );
+		segment( n - 2, n - 1, 0, 1, n - 1 );
+	}
+	else
+	{
+		for ( int i = 0; i < n - 3; ++i )
+			segment( i, i + 1, i + 2, i + 3, i + 1 );
+	}
+	return b2ChainId{ chainId + 1, w->worldId, chain.generation };
+}
+void b2DestroyChain( b2ChainId chainId ) // shape.c:488-537
+{
+	HostWorld* hw = nullptr;
+	HostWorld::Chain* chain = chainFromId( chainId, &hw );
+	if ( chain == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	if ( w->locked )
+		return;
+	Body& body = ptr( w, w->bodies )[chain->bodyId];
+	// unlink from the body's singly linked chain list
+	int* link = &body.headChainId;
+	bool found = false;
+	while ( *link != kNull )
+	{
+		if ( *link == chain->id )
+		{
+			*link = chain->nextChainId;
+			found = true;
+			break;
+		}
+		link = &hw->chains[*link].nextChainId;
+	}
+	if ( found == false )
+		return;
+	for ( int shapeId : chain->shapeIndices )
+		destroyShape( w, shapeId, false );
+	chain->shapeIndices.clear();
+	chain->materials.clear();
+	freeId( w, w->chainIds, chain->id );
+	chain->id = kNull;
+}
+bool b2Chain_IsValid( b2ChainId id )
+{
+	return chainFromId( id, nullptr ) != nullptr;
+}
+b2WorldId b2Chain_GetWorld( b2ChainId chainId )
+{
+	HostWorld* hw = worldFromIndex0( chainId.world0 );
+	return hw ? b2WorldId{ (uint16_t)( chainId.world0 + 1 ), hw->generation } : b2WorldId{ 0, 0 };
+}
+int b2Chain_GetSegmentCount( b2ChainId chainId )
+{
+	HostWorld::Chain* chain = chainFromId( chainId, nullptr );
+	return chain ? (int)chain->shapeIndices.size() : 0;
+}
+int b2Chain_GetSegments( b2ChainId chainId, b2ShapeId* segmentArray, int capacity ) // shape.c:557-576
+{
+	HostWorld* hw = nullptr;
+	HostWorld::Chain* chain = chainFromId( chainId, &hw );
+	if ( chain == nullptr )
+		return 0;
+	World* w = hostImage( *hw );
+	int count = mini( (int)chain->shapeIndices.size(), capacity );
+	for ( int i = 0; i < count; ++i )
+	{
+		int shapeId = chain->shapeIndices[i];
+		segmentArray[i] = b2ShapeId{ shapeId + 1, chainId.world0, ptr( w, w->shapes )[shapeId].generation };
+	}
+	return count;
+}
+void b2Chain_SetFriction( b2ChainId chainId, float friction ) // shape.c:1476-1502
+{
+	HostWorld* hw = nullptr;
+	HostWorld::Chain* chain = chainFromId( chainId, &hw );
+	if ( chain == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	if ( w->locked )
+		return;
+	for ( b2SurfaceMaterial& m : chain->materials )
+		m.friction = friction;
+	for ( int shapeId : chain->shapeIndices )
+		ptr( w, w->shapes )[shapeId].friction = friction;
+}
+float b2Chain_GetFriction( b2ChainId chainId )
+{
+	HostWorld::Chain* chain = chainFromId( chainId, nullptr );
+	return chain && chain->materials.empty() == false ? chain->materials[0].friction : 0.0f;
+}
+void b2Chain_SetRestitution( b2ChainId chainId, float restitution ) // shape.c:1511-1537
+{
+	HostWorld* hw = nullptr;
+	HostWorld::Chain* chain = chainFromId( chainId, &hw );
+	if ( chain == nullptr )
+		return;
+	World* w = mutableImage( *hw );
+	if ( w->locked )
+		return;
+	for ( b2SurfaceMaterial& m : chain->materials )
+		m.restitution = restitution;
+	for ( int shapeId : chain->shapeIndices )
+		ptr( w, w->shapes )[shapeId].restitution = restitution;
+}
+float b2Chain_GetRestitution( b2ChainId chainId )
+{
+	HostWorld::Chain* chain = chainFromId( chainId, nullptr );
+	return chain && chain->materials.empty() == false ? chain->materials[0].restitution : 0.0f;
 }
 
 // ---------------------------------------------------------------------------------------------------------------- queries

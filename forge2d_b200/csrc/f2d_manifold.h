@@ -3,6 +3,7 @@
 // Same SAT / clipping / closest-feature decisions and the same floating-point expression order as
 // B2/src/manifold.c (cited per function) so point counts, feature ids and anchors are bit-identical.
 #pragma once
+#include "f2d_distance.h"
 #include "f2d_types.h"
 
 namespace f2d
@@ -724,6 +725,389 @@ F2D_HDF inline Manifold collidePolygonAndCapsule( const Poly& polygonA, Xf xfA, 
 	return collidePolygonsR( loadPoly<8>( polygonA ), xfA, capsulePolyR<2>( b.c1, b.c2, b.radius ), xfB );
 }
 
+// ------------------------------------------------------------------------------------------------ chain segments
+// manifold.c:16-34 b2MakeCapsule as a stored polygon (the chain-segment path indexes vertices dynamically)
+F2D_HD Poly capsuleAsPoly( V2 p1, V2 p2, float radius )
+{
+	Poly shape;
+	memset( &shape, 0, sizeof( shape ) );
+	shape.v[0] = p1;
+	shape.v[1] = p2;
+	shape.centroid = lerp( p1, p2, 0.5f );
+	V2 axis = normalize( sub( p2, p1 ) );
+	V2 normal = rightPerp( axis );
+	shape.n[0] = normal;
+	shape.n[1] = neg( normal );
+	shape.count = 2;
+	shape.radius = radius;
+	return shape;
+}
+
+// manifold.c:1089-1168: one-sided segment with ghost vertices against a circle
+F2D_HDF inline Manifold collideChainSegmentAndCircle( const ChainSegment& segmentA, Xf xfA, const Circle& circleB, Xf xfB )
+{
+	Manifold m = emptyManifold();
+	Xf xf = invMulXf( xfA, xfB );
+	V2 pB = xfPoint( xf, circleB.center );
+	V2 p1 = segmentA.segment.p1, p2 = segmentA.segment.p2;
+	V2 e = sub( p2, p1 );
+	float offset = dot( rightPerp( e ), sub( pB, p1 ) );
+	if ( offset < 0.0f )
+		return m; // behind the one-sided segment
+	float u = dot( e, sub( p2, pB ) );
+	float v = dot( e, sub( pB, p1 ) );
+	V2 pA;
+	if ( v <= 0.0f )
+	{
+		// region of p1: the previous segment owns the contact when the circle is on its side
+		V2 prevEdge = sub( p1, segmentA.ghost1 );
+		float uPrev = dot( prevEdge, sub( pB, p1 ) );
+		if ( uPrev <= 0.0f )
+			return m;
+		pA = p1;
+	}
+	else if ( u <= 0.0f )
+	{
+		V2 nextEdge = sub( segmentA.ghost2, p2 );
+		float vNext = dot( nextEdge, sub( pB, p2 ) );
+		if ( vNext > 0.0f )
+			return m;
+		pA = p2;
+	}
+	else
+	{
+		float ee = dot( e, e );
+		pA = V2{ u * p1.x + v * p2.x, u * p1.y + v * p2.y };
+		pA = ee > 0.0f ? mulSV( 1.0f / ee, pA ) : p1;
+	}
+	float distance;
+	V2 normal = lengthAndNormalize( &distance, sub( pB, pA ) );
+	float radius = circleB.radius;
+	float separation = distance - radius;
+	if ( separation > kSpeculative )
+		return m;
+	V2 cA = pA;
+	V2 cB = mulAdd( pB, -radius, normal );
+	V2 contactPointA = lerp( cA, cB, 0.5f );
+	m.normal = rotate( xfA.q, normal );
+	ManifoldPoint* mp = m.points + 0;
+	mp->anchorA = rotate( xfA.q, contactPointA );
+	mp->anchorB = add( mp->anchorA, sub( xfA.p, xfB.p ) );
+	mp->point = add( xfA.p, mp->anchorA );
+	mp->separation = separation;
+	mp->id = 0;
+	m.pointCount = 1;
+	return m;
+}
+
+// manifold.c:1177-1249 b2ClipSegments: segment b clipped to the extent of segment a along the tangent of `normal`
+F2D_HDF inline Manifold clipSegments( V2 a1, V2 a2, V2 b1, V2 b2, V2 normal, float ra, float rb, uint16_t id1, uint16_t id2 )
+{
+	Manifold m = emptyManifold();
+	V2 tangent = leftPerp( normal );
+	float lower1 = 0.0f;
+	float upper1 = dot( sub( a2, a1 ), tangent );
+	float upper2 = dot( sub( b1, a1 ), tangent );
+	float lower2 = dot( sub( b2, a1 ), tangent );
+	if ( upper2 < lower1 || upper1 < lower2 )
+		return m;
+	V2 vLower;
+	if ( lower2 < lower1 && upper2 - lower2 > FLT_EPSILON )
+		vLower = lerp( b2, b1, ( lower1 - lower2 ) / ( upper2 - lower2 ) );
+	else
+		vLower = b2;
+	V2 vUpper;
+	if ( upper2 > upper1 && upper2 - lower2 > FLT_EPSILON )
+		vUpper = lerp( b2, b1, ( upper1 - lower2 ) / ( upper2 - lower2 ) );
+	else
+		vUpper = b1;
+	float separationLower = dot( sub( vLower, a1 ), normal );
+	float separationUpper = dot( sub( vUpper, a1 ), normal );
+	vLower = mulAdd( vLower, 0.5f * ( ra - rb - separationLower ), normal );
+	vUpper = mulAdd( vUpper, 0.5f * ( ra - rb - separationUpper ), normal );
+	float radius = ra + rb;
+	m.normal = normal;
+	m.points[0].anchorA = vLower;
+	m.points[0].separation = separationLower - radius;
+	m.points[0].id = id1;
+	m.points[1].anchorA = vUpper;
+	m.points[1].separation = separationUpper - radius;
+	m.points[1].id = id2;
+	m.pointCount = 2;
+	return m;
+}
+
+// manifold.c:1251-1304: may a contact normal be used, given the neighbouring segments (smooth collision)?
+enum NormalType
+{
+	kNormalSkip,
+	kNormalAdmit,
+	kNormalSnap
+};
+struct ChainSegmentParams
+{
+	V2 edge1, normal0, normal2;
+	bool convex1, convex2;
+};
+F2D_HD NormalType classifyNormal( const ChainSegmentParams& params, V2 normal )
+{
+	const float sinTol = 0.01f;
+	if ( dot( normal, params.edge1 ) <= 0.0f )
+	{
+		if ( params.convex1 )
+			return cross( normal, params.normal0 ) > sinTol ? kNormalSkip : kNormalAdmit;
+		return kNormalSnap;
+	}
+	if ( params.convex2 )
+		return cross( params.normal2, normal ) > sinTol ? kNormalSkip : kNormalAdmit;
+	return kNormalSnap;
+}
+
+// two-point manifolds of this family are produced in A's local frame: rotate / translate them out (manifold.c:1480-1492)
+F2D_HD void chainManifoldToWorld( Manifold& m, V2 localNormal, Xf xfA, Xf xfB )
+{
+	if ( m.pointCount != 2 )
+		return;
+	m.normal = rotate( xfA.q, localNormal );
+	m.points[0].anchorA = rotate( xfA.q, m.points[0].anchorA );
+	m.points[1].anchorA = rotate( xfA.q, m.points[1].anchorA );
+	V2 pAB = sub( xfA.p, xfB.p );
+	m.points[0].anchorB = add( m.points[0].anchorA, pAB );
+	m.points[1].anchorB = add( m.points[1].anchorA, pAB );
+	m.points[0].point = add( xfA.p, m.points[0].anchorA );
+	m.points[1].point = add( xfA.p, m.points[1].anchorA );
+}
+
+// manifold.c:1306-1726
+F2D_HDF inline Manifold collideChainSegmentAndPolygon( const ChainSegment& segmentA, Xf xfA, const Poly& polygonB, Xf xfB, SimplexCache* cache )
+{
+	Manifold m = emptyManifold();
+	Xf xf = invMulXf( xfA, xfB );
+	V2 centroidB = xfPoint( xf, polygonB.centroid );
+	float radiusB = polygonB.radius;
+	V2 p1 = segmentA.segment.p1, p2 = segmentA.segment.p2;
+	V2 edge1 = normalize( sub( p2, p1 ) );
+	ChainSegmentParams smooth;
+	smooth.edge1 = edge1;
+	const float convexTol = 0.01f;
+	V2 edge0 = normalize( sub( p1, segmentA.ghost1 ) );
+	smooth.normal0 = rightPerp( edge0 );
+	smooth.convex1 = cross( edge0, edge1 ) >= convexTol;
+	V2 edge2 = normalize( sub( segmentA.ghost2, p2 ) );
+	smooth.normal2 = rightPerp( edge2 );
+	smooth.convex2 = cross( edge1, edge2 ) >= convexTol;
+	V2 normal1 = rightPerp( edge1 );
+	bool behind1 = dot( normal1, sub( centroidB, p1 ) ) < 0.0f;
+	bool behind0 = true, behind2 = true;
+	if ( smooth.convex1 )
+		behind0 = dot( smooth.normal0, sub( centroidB, p1 ) ) < 0.0f;
+	if ( smooth.convex2 )
+		behind2 = dot( smooth.normal2, sub( centroidB, p2 ) ) < 0.0f;
+	if ( behind1 && behind0 && behind2 )
+		return m;
+
+	const int count = polygonB.count;
+	V2 vertices[kMaxPolyVerts], normals[kMaxPolyVerts];
+	for ( int i = 0; i < count; ++i )
+	{
+		vertices[i] = xfPoint( xf, polygonB.v[i] );
+		normals[i] = rotate( xf.q, polygonB.n[i] );
+	}
+	const Xf identity = { { 0.0f, 0.0f }, { 1.0f, 0.0f } };
+	DistanceOutput output = shapeDistance( makeProxy( &segmentA.segment.p1, 2, 0.0f ), makeProxy( vertices, count, 0.0f ), identity, identity,
+										   false, cache );
+	if ( output.distance > radiusB + kSpeculative )
+		return m;
+
+	V2 n0 = smooth.convex1 ? smooth.normal0 : normal1;
+	V2 n2 = smooth.convex2 ? smooth.normal2 : normal1;
+	int incidentIndex = -1;
+	int incidentNormal = -1;
+	// a polygon edge chosen as reference face must not face away from the neighbouring segment it hangs over
+	auto neighbourRejects = [&]( V2 n, V2 a1 ) {
+		float dot1 = dot( n, sub( p1, a1 ) );
+		float dot2 = dot( n, sub( p2, a1 ) );
+		if ( dot1 < dot2 )
+			return dot( n0, n ) < dot( normal1, n );
+		return dot( n2, n ) < dot( normal1, n );
+	};
+
+	if ( behind1 == false && output.distance > 0.1f * kLinearSlop )
+	{
+		// separated: the GJK witness features decide
+		if ( cache->count == 1 )
+		{
+			V2 pA = output.pointA, pB = output.pointB;
+			V2 normal = normalize( sub( pB, pA ) );
+			NormalType type = classifyNormal( smooth, normal );
+			if ( type == kNormalSkip )
+				return m;
+			if ( type == kNormalAdmit )
+			{
+				m.normal = rotate( xfA.q, normal );
+				ManifoldPoint* cp = m.points + 0;
+				cp->anchorA = rotate( xfA.q, pA );
+				cp->anchorB = add( cp->anchorA, sub( xfA.p, xfB.p ) );
+				cp->point = add( xfA.p, cp->anchorA );
+				cp->separation = output.distance - radiusB;
+				cp->id = makeFeatureId( cache->indexA[0], cache->indexB[0] );
+				m.pointCount = 1;
+				return m;
+			}
+			incidentIndex = cache->indexB[0];
+		}
+		else
+		{
+			int ia1 = cache->indexA[0], ia2 = cache->indexA[1];
+			int ib1 = cache->indexB[0], ib2 = cache->indexB[1];
+			if ( ia1 == ia2 )
+			{
+				// one segment vertex against a polygon edge: the better aligned of the two edge normals is the reference
+				V2 normalB = sub( output.pointA, output.pointB );
+				float dot1 = dot( normalB, normals[ib1] );
+				float dot2 = dot( normalB, normals[ib2] );
+				int ib = dot1 > dot2 ? ib1 : ib2;
+				normalB = normals[ib];
+				NormalType type = classifyNormal( smooth, neg( normalB ) );
+				if ( type == kNormalSkip )
+					return m;
+				if ( type == kNormalAdmit )
+				{
+					ib1 = ib;
+					ib2 = ib < count - 1 ? ib + 1 : 0;
+					V2 b1 = vertices[ib1], b2 = vertices[ib2];
+					if ( neighbourRejects( normalB, b1 ) )
+						return m;
+					m = clipSegments( b1, b2, p1, p2, normalB, radiusB, 0.0f, makeFeatureId( ib1, 1 ), makeFeatureId( ib2, 0 ) );
+					chainManifoldToWorld( m, neg( normalB ), xfA, xfB );
+					return m;
+				}
+				incidentNormal = ib;
+			}
+			else
+			{
+				// segment edge against one polygon vertex region
+				float dot1 = dot( normal1, sub( vertices[ib1], p1 ) );
+				float dot2 = dot( normal1, sub( vertices[ib2], p2 ) );
+				incidentIndex = dot1 < dot2 ? ib1 : ib2;
+			}
+		}
+	}
+	else
+	{
+		// overlapping (or the polygon centre is behind the segment): separating-axis search
+		float edgeSeparation = FLT_MAX;
+		for ( int i = 0; i < count; ++i )
+		{
+			float s = dot( normal1, sub( vertices[i], p1 ) );
+			if ( s < edgeSeparation )
+			{
+				edgeSeparation = s;
+				incidentIndex = i;
+			}
+		}
+		if ( smooth.convex1 )
+		{
+			float s0 = FLT_MAX;
+			for ( int i = 0; i < count; ++i )
+			{
+				float s = dot( smooth.normal0, sub( vertices[i], p1 ) );
+				if ( s < s0 )
+					s0 = s;
+			}
+			if ( s0 > edgeSeparation )
+			{
+				edgeSeparation = s0;
+				incidentIndex = -1;
+			}
+		}
+		if ( smooth.convex2 )
+		{
+			float s2 = FLT_MAX;
+			for ( int i = 0; i < count; ++i )
+			{
+				float s = dot( smooth.normal2, sub( vertices[i], p2 ) );
+				if ( s < s2 )
+					s2 = s;
+			}
+			if ( s2 > edgeSeparation )
+			{
+				edgeSeparation = s2;
+				incidentIndex = -1;
+			}
+		}
+		float polygonSeparation = -FLT_MAX;
+		int referenceIndex = -1;
+		for ( int i = 0; i < count; ++i )
+		{
+			V2 n = normals[i];
+			if ( classifyNormal( smooth, neg( n ) ) != kNormalAdmit )
+				continue;
+			V2 p = vertices[i];
+			float s = minf( dot( n, sub( p2, p ) ), dot( n, sub( p1, p ) ) );
+			if ( s > polygonSeparation )
+			{
+				polygonSeparation = s;
+				referenceIndex = i;
+			}
+		}
+		if ( polygonSeparation > edgeSeparation )
+		{
+			int ia1 = referenceIndex;
+			int ia2 = ia1 < count - 1 ? ia1 + 1 : 0;
+			V2 a1 = vertices[ia1], a2 = vertices[ia2];
+			V2 n = normals[ia1];
+			if ( neighbourRejects( n, a1 ) )
+				return m;
+			m = clipSegments( a1, a2, p1, p2, normals[ia1], radiusB, 0.0f, makeFeatureId( ia1, 1 ), makeFeatureId( ia2, 0 ) );
+			chainManifoldToWorld( m, neg( normals[ia1] ), xfA, xfB );
+			return m;
+		}
+		if ( incidentIndex == -1 )
+			return m;
+	}
+
+	// the segment is the reference face: pick the incident polygon edge and clip it
+	V2 b1, b2;
+	int ib1, ib2;
+	if ( incidentNormal != -1 )
+	{
+		ib1 = incidentNormal;
+		ib2 = ib1 < count - 1 ? ib1 + 1 : 0;
+		b1 = vertices[ib1];
+		b2 = vertices[ib2];
+	}
+	else
+	{
+		int i2 = incidentIndex;
+		int i1 = i2 > 0 ? i2 - 1 : count - 1;
+		float d1 = dot( normal1, normals[i1] );
+		float d2 = dot( normal1, normals[i2] );
+		if ( d1 < d2 )
+		{
+			ib1 = i1;
+			ib2 = i2;
+		}
+		else
+		{
+			ib1 = i2;
+			ib2 = i2 < count - 1 ? i2 + 1 : 0;
+		}
+		b1 = vertices[ib1];
+		b2 = vertices[ib2];
+	}
+	m = clipSegments( p1, p2, b1, b2, normal1, 0.0f, radiusB, makeFeatureId( 0, ib2 ), makeFeatureId( 1, ib1 ) );
+	chainManifoldToWorld( m, m.normal, xfA, xfB );
+	return m;
+}
+
+// manifold.c:1170-1175
+F2D_HDF inline Manifold collideChainSegmentAndCapsule( const ChainSegment& segmentA, Xf xfA, const Capsule& capsuleB, Xf xfB, SimplexCache* cache )
+{
+	Poly polyB = capsuleAsPoly( capsuleB.c1, capsuleB.c2, capsuleB.radius );
+	return collideChainSegmentAndPolygon( segmentA, xfA, polyB, xfB, cache );
+}
+
 // Dispatch on the (primary-ordered) shape-type pair: B2/src/contact.c:166-184 registers.
 // Returns false when the pair has no manifold function (e.g. segment vs segment).
 F2D_HD bool pairHasManifold( int typeA, int typeB )
@@ -757,7 +1141,6 @@ F2D_HD bool pairIsPrimary( int t1, int t2 )
 
 F2D_HDF inline Manifold computeManifold( World* w, const Shape& a, Xf xfA, const Shape& b, Xf xfB, SimplexCache* cache )
 {
-	(void)cache;
 	switch ( a.type )
 	{
 		case kCircle:
@@ -786,8 +1169,13 @@ F2D_HDF inline Manifold computeManifold( World* w, const Shape& a, Xf xfA, const
 			}
 			return collideSegmentAndPolygon( a.segment.p1, a.segment.p2, 0.0f, xfA, b.polygon, xfB ); // manifold.c:1083-1087
 		}
+		case kChainSegment:
+			if ( b.type == kCircle )
+				return collideChainSegmentAndCircle( a.chainSegment, xfA, b.circle, xfB );
+			if ( b.type == kCapsule )
+				return collideChainSegmentAndCapsule( a.chainSegment, xfA, b.capsule, xfB, cache );
+			return collideChainSegmentAndPolygon( a.chainSegment, xfA, b.polygon, xfB, cache );
 		default:
-			// chain segments: not on the device path yet
 			setError( w, kErrUnsupported, __LINE__ );
 			return emptyManifold();
 	}

@@ -748,6 +748,8 @@ template <class Team> F2D_HDF inline void islandPartition( World* w, Team& t )
 		int li = islands[bodies[awakeBodies[i]].islandId].localIndex;
 		islBodies[bodyOff[li] + atomAdd( bodyFill + li, 1 )] = i;
 	}
+	if ( t.rank() == 0 )
+		w->step.islandSolveCount = islandCount;
 	t.sync();
 }
 
@@ -755,7 +757,9 @@ template <class Team> F2D_HDF inline void islandPartition( World* w, Team& t )
 template <class Team> F2D_HDF inline void islandSolve( World* w, Team& t )
 {
 	const StepCtx& step = w->step;
-	const int islandCount = w->awakeIslands.count;
+	// NOT w->awakeIslands.count: the island split (which runs beside or before these stages) destroys one island and
+	// creates its pieces; the buckets below describe the islands as they were when islandPartition ran
+	const int islandCount = step.islandSolveCount;
 	const int awakeBodyCount = step.awakeBodyCount;
 	const int slotCount = step.awakeContactCount;
 	const int32_t* slotOff = ptr( w, w->islSlotOff );

@@ -468,7 +468,7 @@ struct StepCtx
 	int32_t splitBodies, splitContacts, splitJoints, splitComponents; // sizes of the split work arrays
 	int32_t islandPath; // 1: constraints are solved island by island (one warp each), 0: colour by colour
 	int32_t maxIslandContacts, maxIslandBodies;
-	int32_t pad;
+	int32_t islandSolveCount; // awake islands when the island-parallel partition was built (a split may add islands later)
 	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
 };
 

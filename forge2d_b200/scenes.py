@@ -501,7 +501,75 @@ def sensor_field(lib, count=30, create=None, **world_kw):
     return scene
 
 
+def chain_terrain(lib, count=36, create=None, **world_kw):
+    """Chain shapes: an open terrain polyline with convex and concave corners and a closed (loop) basin, with boxes,
+    circles, capsules and a rounded polygon dropped on them: every chain-segment manifold function, ghost-vertex
+    (smooth collision) decisions and the persistent GJK cache."""
+    world = _world(lib, create=create, **world_kw)
+    bd = lib.b2DefaultBodyDef()
+    ground = lib.b2CreateBody(world, C.byref(bd))
+    bodies = [ground]
+    # open chain: ghost, then the terrain right to left (chain normals point to the right of the travel direction)
+    pts = [(22.0, 3.0), (18.0, 0.0), (13.0, 0.0), (10.0, 1.5), (7.0, 0.5), (4.0, 0.5), (2.0, -1.0), (-2.0, -1.0),
+           (-4.0, 0.25), (-8.0, 0.0), (-11.0, 2.0), (-14.0, 0.0), (-18.0, 0.0), (-22.0, 4.0)]
+    arr = (A.Vec2 * len(pts))(*[A.Vec2(_f32(x), _f32(y)) for x, y in pts])
+    cd = lib.b2DefaultChainDef()
+    cd.points = arr
+    cd.count = len(pts)
+    cd.isLoop = False
+    chains = [lib.b2CreateChain(ground, C.byref(cd))]
+    # closed basin above the terrain (counter-clockwise loop = solid outside, bodies live inside)
+    loop = [(-3.0, 6.0), (3.0, 6.0), (4.0, 9.0), (0.0, 8.0), (-4.0, 9.0)]
+    mats = (A.SurfaceMaterial * len(loop))()
+    for i in range(len(loop)):
+        mats[i].friction = _f32(0.2 + 0.15 * i)
+        mats[i].restitution = _f32(0.05 * i)
+    larr = (A.Vec2 * len(loop))(*[A.Vec2(_f32(x), _f32(y)) for x, y in reversed(loop)])
+    cd2 = lib.b2DefaultChainDef()
+    cd2.points = larr
+    cd2.count = len(loop)
+    cd2.materials = mats
+    cd2.materialCount = len(loop)
+    cd2.isLoop = True
+    chains.append(lib.b2CreateChain(ground, C.byref(cd2)))
+    state = [2024]
+
+    def rnd():
+        state[0] = (1103515245 * state[0] + 12345) & 0x7FFFFFFF
+        return state[0] / float(0x7FFFFFFF)
+
+    sd = lib.b2DefaultShapeDef()
+    for i in range(count):
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        inside = i % 6 == 0
+        if inside:
+            bd.position = A.Vec2(_f32(-2.0 + 4.0 * rnd()), _f32(6.8 + 0.8 * rnd()))
+        else:
+            bd.position = A.Vec2(_f32(-19.0 + 38.0 * rnd()), _f32(5.0 + 8.0 * rnd()))
+        bd.angularVelocity = _f32(4.0 * rnd() - 2.0)
+        b = lib.b2CreateBody(world, C.byref(bd))
+        bodies.append(b)
+        kind = i % 4
+        if kind == 0:
+            lib.b2CreatePolygonShape(b, C.byref(sd), C.byref(_box(lib, 0.25 if inside else 0.4)))
+        elif kind == 1:
+            c = A.Circle(A.Vec2(0.0, 0.0), 0.3)
+            lib.b2CreateCircleShape(b, C.byref(sd), C.byref(c))
+        elif kind == 2:
+            c = A.Capsule(A.Vec2(-0.35, 0.0), A.Vec2(0.35, 0.0), 0.2)
+            lib.b2CreateCapsuleShape(b, C.byref(sd), C.byref(c))
+        else:
+            poly = lib.b2MakeOffsetRoundedBox(0.3, 0.2, A.Vec2(0.0, 0.0), A.Rot(1.0, 0.0), 0.1)
+            lib.b2CreatePolygonShape(b, C.byref(sd), C.byref(poly))
+    scene = Scene(lib, world, bodies, "chain_terrain_%d" % count)
+    scene.chains = chains
+    scene._keep = (arr, larr, mats)
+    return scene
+
+
 SCENES = {
+    "chain_terrain": chain_terrain,
     "sensor_field": sensor_field,
     "joint_zoo": joint_zoo,
     "bench2d": bench2d,

@@ -28,6 +28,7 @@ typedef struct b2WorldId { uint16_t index1, generation; } b2WorldId;
 typedef struct b2BodyId { int32_t index1; uint16_t world0, generation; } b2BodyId;
 typedef struct b2ShapeId { int32_t index1; uint16_t world0, generation; } b2ShapeId;
 typedef struct b2JointId { int32_t index1; uint16_t world0, generation; } b2JointId;
+typedef struct b2ChainId { int32_t index1; uint16_t world0, generation; } b2ChainId;
 
 // ---- geometry: B2/include/box2d/collision.h:24-186 ------------------------------------------------------------
 #define B2_MAX_POLYGON_VERTICES 8
@@ -218,6 +219,17 @@ typedef struct b2WheelJointDef
 	void* userData;
 	int internalValue;
 } b2WheelJointDef;
+typedef struct b2ChainDef // types.h:429-458
+{
+	void* userData;
+	const b2Vec2* points;
+	int count;
+	const b2SurfaceMaterial* materials;
+	int materialCount;
+	b2Filter filter;
+	bool isLoop, enableSensorEvents;
+	int internalValue;
+} b2ChainDef;
 typedef struct b2ExplosionDef { uint64_t maskBits; b2Vec2 position; float radius, falloff, impulsePerLength; } b2ExplosionDef;
 
 // ---- queries: types.h:291-305 (b2QueryFilter), :67-76 (b2RayResult), collision.h:658-665 (b2TreeStats), callbacks types.h:1180-1220
@@ -429,6 +441,19 @@ F2D_API void* b2Joint_GetUserData( b2JointId jointId );
 F2D_API void b2Joint_WakeBodies( b2JointId jointId );											 // joint.c:1045
 F2D_API b2Vec2 b2Joint_GetConstraintForce( b2JointId jointId );								 // joint.c:1061
 F2D_API float b2Joint_GetConstraintTorque( b2JointId jointId );								 // joint.c:1099
+// ---- chains: shape.c:339-577, :1476-1576 -------------------------------------------------------------------------
+F2D_API b2ChainDef b2DefaultChainDef( void );													 // types.c:76
+F2D_API b2ChainId b2CreateChain( b2BodyId bodyId, const b2ChainDef* def );					 // shape.c:339
+F2D_API void b2DestroyChain( b2ChainId chainId );												 // shape.c:488
+F2D_API bool b2Chain_IsValid( b2ChainId id );
+F2D_API b2WorldId b2Chain_GetWorld( b2ChainId chainId );
+F2D_API int b2Chain_GetSegmentCount( b2ChainId chainId );
+F2D_API int b2Chain_GetSegments( b2ChainId chainId, b2ShapeId* segmentArray, int capacity );	 // shape.c:557
+F2D_API void b2Chain_SetFriction( b2ChainId chainId, float friction );						 // shape.c:1476
+F2D_API float b2Chain_GetFriction( b2ChainId chainId );
+F2D_API void b2Chain_SetRestitution( b2ChainId chainId, float restitution );					 // shape.c:1511
+F2D_API float b2Chain_GetRestitution( b2ChainId chainId );
+
 // ---- queries and explosion (run on the host image of the device state: forge2d_b200/csrc/f2d_query.h) ---------------
 F2D_API b2QueryFilter b2DefaultQueryFilter( void );
 F2D_API b2TreeStats b2World_OverlapAABB( b2WorldId worldId, b2AABB aabb, b2QueryFilter filter, b2OverlapResultFcn* fcn, void* context ); // world.c:2071

@@ -196,3 +196,48 @@ def test_sensor_events_match_reference_emu(ref, emu):
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_sensor_events_match_reference_gpu(ref, gpu, mode):
     _sensor_session(ref, gpu, mode=mode)
+
+
+# ---- chains --------------------------------------------------------------------------------------------------
+def _chain_session(ref, lib, frames=300, mode=None):
+    import ctypes as C
+    from forge2d_b200 import _abi as A
+    lib.f2dClearLastError()
+    a = scenes.chain_terrain(ref)
+    b = scenes.chain_terrain(lib)
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(b.world, mode)
+    for s, L in ((a, ref), (b, lib)):
+        assert L.b2Chain_IsValid(s.chains[0]) and L.b2Chain_GetSegmentCount(s.chains[0]) == 11
+        assert L.b2Chain_GetSegmentCount(s.chains[1]) == 5
+    segs_a, segs_b = (A.ShapeId * 16)(), (A.ShapeId * 16)()
+    assert ref.b2Chain_GetSegments(a.chains[1], segs_a, 16) == lib.b2Chain_GetSegments(b.chains[1], segs_b, 16)
+    assert [segs_a[i].index1 for i in range(5)] == [segs_b[i].index1 for i in range(5)]
+    assert ref.b2Chain_GetFriction(a.chains[1]) == lib.b2Chain_GetFriction(b.chains[1])
+    for f in range(frames):
+        if f == 120:
+            for s, L in ((a, ref), (b, lib)):
+                L.b2Chain_SetFriction(s.chains[0], 0.05)
+                L.b2Chain_SetRestitution(s.chains[0], 0.4)
+        if f == 200:
+            for s, L in ((a, ref), (b, lib)):
+                L.b2DestroyChain(s.chains[1])     # the basin vanishes, its contents fall onto the terrain
+                assert not L.b2Chain_IsValid(s.chains[1])
+        a.step()
+        b.step()
+        if f % 6 == 0 or f == frames - 1:
+            d = H.diff(H.snapshot(ref, a.world), H.snapshot(lib, b.world))
+            assert d == [], "frame %d: %s" % (f, d[:6])
+    assert lib.f2dGetLastError() == b""
+    a.destroy()
+    b.destroy()
+
+
+def test_chain_shapes_match_reference_emu(ref, emu):
+    _chain_session(ref, emu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_chain_shapes_match_reference_gpu(ref, gpu, mode):
+    _chain_session(ref, gpu, mode=mode)
