@@ -213,8 +213,24 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 			setError( w, kErrCapacity, __LINE__ );
 		return;
 	}
-	for ( int i = t.rank(); i < moveCount; i += t.size() )
-		findPairsForProxy( w, i );
+	{
+		const int32_t* moves = ptr( w, w->moveArray );
+		for ( int i = t.rank(); i < moveCount; i += t.size() )
+		{
+			// the leaf this thread queries next (its box and shape id start the next chain of dependent loads)
+			if ( i + t.size() < moveCount )
+			{
+				int key = moves[i + t.size()];
+				if ( key != kNull )
+				{
+					const char* leaf = reinterpret_cast<const char*>( ptr( w, w->trees[proxyType( key )].nodes ) + proxyId( key ) );
+					prefetchL2( leaf );
+					prefetchL2( leaf + sizeof( TreeNode ) - 1 );
+				}
+			}
+			findPairsForProxy( w, i );
+		}
+	}
 	t.sync();
 	F2D_MARK( w, t, pfPairQuery );
 	// Ordered creation (broad_phase.c:418-453): move-array order x per-proxy list order. Most moved proxies found
@@ -471,8 +487,9 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 		// a thread's indices only grow, so the list segment is tracked with a forward cursor (no per-thread table)
 		int seg = -1, segStart = 0, segEnd = 0;
 		const int32_t* list = nullptr;
-		for ( int i = rank; i < total; i += size )
-		{
+		auto contactAt = [&]( int i ) -> int {
+			if ( i >= total )
+				return kNull;
 			while ( i >= segEnd )
 			{
 				seg += 1;
@@ -481,7 +498,23 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 				segEnd += a.count;
 				list = ptr( w, a );
 			}
-			collideContact( w, list[i - segStart] );
+			return list[i - segStart];
+		};
+		// A contact is a chain of dependent gathers (id -> contact record -> shapes / bodies / body sims) and a thread
+		// owns several contacts: while one is processed, the record of the thread's next contact is requested into L2.
+		const ContactSim* csims = ptr( w, w->contactSims );
+		int id0 = contactAt( rank );
+		for ( int i = rank; i < total; i += size )
+		{
+			int id1 = contactAt( i + size );
+			if ( id1 != kNull )
+			{
+				const ContactSim& n = csims[id1];
+				prefetchL2( &n );
+				prefetchL2( &n.manifold.points[1] );
+			}
+			collideContact( w, id0 );
+			id0 = id1;
 		}
 	};
 	treeRebuildTeam( w, t, w->trees[kDynamicBody] );
@@ -1212,11 +1245,22 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 		}
 		{
 			const float h = w->step.h;
+			const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+			const BodySim* bsims = ptr( w, w->sims );
 			for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+			{
+				if ( i + t.size() < awakeBodyCount )
+				{
+					const BodySim& n = bsims[awakeBodies[i + t.size()]];
+					prefetchL2( &n.force );
+					prefetchL2( &n.gravityScale );
+				}
 				prepareIntegrate( w, i, h );
+			}
 		}
 		const ConView c = conView( w );
 		const BodyState* states = ptr( w, w->states );
+		const ContactSim* csims = ptr( w, w->contactSims );
 		float warmStartScale = w->enableWarmStarting ? 1.0f : 0.0f;
 		int total = w->step.awakeContactCount;
 		int color = -1, colorStart = 0, colorEnd = 0;
@@ -1229,6 +1273,13 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 				colorStart = colorEnd;
 				colorEnd = w->step.colorBase[color + 1];
 				list = ptr( w, w->colorContacts[color] );
+			}
+			// request the record of this thread's next slot while this one is prepared (same colour only: cheap to find)
+			if ( slot + t.size() < colorEnd )
+			{
+				const ContactSim& n = csims[list[slot + t.size() - colorStart]];
+				prefetchL2( &n );
+				prefetchL2( &n.manifold.points[1] );
 			}
 			prepareContactSlot( w, c, slot, list[slot - colorStart], states, warmStartScale );
 		}
@@ -1856,6 +1907,98 @@ F2D_HDF inline void enlargeLeafParallel( World* w, Tree& tree, int leaf, Box box
 	}
 }
 
+// The same end state for up to kEnlargeWalks leaves of one thread at a time. A walk is a chain of dependent loads (box
+// and links of the parent, then of its parent ...) as long as the tree is high (23-25 levels at 820 proxies), and a
+// thread owns several walks, so it advances them in lockstep: the loads of one level of all its walks are issued
+// together and cost one round trip instead of one each. `keys[first + k * stride]` are the proxy keys (kNull: skip);
+// the leaf boxes have been written already.
+constexpr int kEnlargeWalks = 4;
+F2D_HDF inline void enlargeWalks( World* w, const int32_t* keys, int first, int stride, int total )
+{
+	TreeNode* nodes[kEnlargeWalks];
+	int cur[kEnlargeWalks];
+	Box box[kEnlargeWalks];
+	bool any = false;
+#if defined( __CUDA_ARCH__ )
+#pragma unroll
+#endif
+	for ( int k = 0; k < kEnlargeWalks; ++k )
+	{
+		int m = first + k * stride;
+		int key = m < total ? keys[m] : kNull;
+		cur[k] = kNull;
+		nodes[k] = nullptr;
+		box[k] = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+		if ( key != kNull )
+		{
+			nodes[k] = ptr( w, w->trees[proxyType( key )].nodes );
+			const TreeNode& leaf = nodes[k][proxyId( key )];
+			box[k] = leaf.box;
+			cur[k] = leaf.parent;
+			any = any || cur[k] != kNull;
+		}
+	}
+	while ( any )
+	{
+		any = false;
+		Box nbox[kEnlargeWalks];
+		int next[kEnlargeWalks];
+		bool flagged[kEnlargeWalks];
+#if defined( __CUDA_ARCH__ )
+#pragma unroll
+#endif
+		for ( int k = 0; k < kEnlargeWalks; ++k )
+		{
+			nbox[k] = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+			next[k] = kNull;
+			flagged[k] = true;
+			if ( cur[k] == kNull )
+				continue;
+			TreeNode& n = nodes[k][cur[k]];
+			// L1-bypassing reads for the same reason as in enlargeLeafParallel
+#if defined( __CUDA_ARCH__ )
+			const float4 nb = __ldcg( reinterpret_cast<const float4*>( &n.box ) );
+			const int4 links = __ldcg( reinterpret_cast<const int4*>( &n.child1 ) );
+			nbox[k] = Box{ { nb.x, nb.y }, { nb.z, nb.w } };
+			next[k] = links.z;
+			flagged[k] = ( ( (uint32_t)links.w >> 16 ) & kNodeEnlarged ) != 0;
+#else
+			nbox[k] = n.box;
+			next[k] = n.parent;
+			flagged[k] = ( n.flags & kNodeEnlarged ) != 0;
+#endif
+		}
+#if defined( __CUDA_ARCH__ )
+#pragma unroll
+#endif
+		for ( int k = 0; k < kEnlargeWalks; ++k )
+		{
+			if ( cur[k] == kNull )
+				continue;
+			TreeNode& n = nodes[k][cur[k]];
+			const Box b = box[k], nb = nbox[k];
+			const bool contains = nb.lo.x <= b.lo.x && nb.lo.y <= b.lo.y && b.hi.x <= nb.hi.x && b.hi.y <= nb.hi.y;
+			if ( contains && flagged[k] )
+			{
+				cur[k] = kNull;
+				continue;
+			}
+			if ( b.lo.x < nb.lo.x )
+				atomMinF( &n.box.lo.x, b.lo.x );
+			if ( b.lo.y < nb.lo.y )
+				atomMinF( &n.box.lo.y, b.lo.y );
+			if ( nb.hi.x < b.hi.x )
+				atomMaxF( &n.box.hi.x, b.hi.x );
+			if ( nb.hi.y < b.hi.y )
+				atomMaxF( &n.box.hi.y, b.hi.y );
+			if ( flagged[k] == false )
+				atomOr32( reinterpret_cast<uint32_t*>( &n.height ), (uint32_t)kNodeEnlarged << 16 );
+			cur[k] = next[k];
+			any = any || cur[k] != kNull;
+		}
+	}
+}
+
 // Hit events, colour-major then array order: solver.c:1758-1818
 F2D_HDF inline void reportHitEvents( World* w )
 {
@@ -2080,8 +2223,24 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 			ib[i] = 0;
 		t.sync();
 
-		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
-			finalizeBody( w, i );
+		{
+			// the body and sim records of this thread's next body are requested into L2 while the current one is finalized
+			const int32_t* awake = ptr( w, w->awakeBodies );
+			const Body* bodyArr = ptr( w, w->bodies );
+			const BodySim* simArr = ptr( w, w->sims );
+			const int stride = t.size();
+			for ( int i = t.rank(); i < awakeBodyCount; i += stride )
+			{
+				if ( i + stride < awakeBodyCount )
+				{
+					int next = awake[i + stride];
+					prefetchL2( &simArr[next] );
+					prefetchL2( &simArr[next].invMass );
+					prefetchL2( &bodyArr[next].userData );
+				}
+				finalizeBody( w, i );
+			}
+		}
 		t.sync();
 		F2D_MARK( w, t, pfFinalizeBodies );
 
@@ -2118,6 +2277,13 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 			moveTotal = 0;
 		}
 		int32_t* moves = ptr( w, w->moveArray );
+		int32_t* walks = ptr( w, w->moveHeads ); // pair-finding scratch, free here: proxy keys whose ancestors must grow
+		if ( moveTotal > w->moveHeads.cap )
+		{
+			if ( t.rank() == 0 )
+				setError( w, kErrCapacity, __LINE__ );
+			moveTotal = 0;
+		}
 		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
 		{
 			if ( ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) ) == 0 || moveTotal == 0 )
@@ -2131,23 +2297,29 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 				Shape& shape = shapes[s];
 				if ( fastBullet )
 				{
+					walks[out] = kNull; // enlarged after the bullet's own continuous pass
 					moves[out++] = shape.proxyKey;
 					ptr( w, w->trees[proxyType( shape.proxyKey )].nodes )[proxyId( shape.proxyKey )].flags |= kNodeMoved;
 				}
 				else if ( shape.enlargedAABB )
 				{
 					int key = shape.proxyKey;
-					Tree& tree = w->trees[proxyType( key )];
-					enlargeLeafParallel( w, tree, proxyId( key ), shape.fatAABB );
-					ptr( w, tree.nodes )[proxyId( key )].flags |= kNodeMoved;
+					TreeNode& leaf = ptr( w, w->trees[proxyType( key )].nodes )[proxyId( key )];
+					leaf.box = shape.fatAABB;
+					leaf.flags |= kNodeMoved;
+					walks[out] = key;
 					moves[out++] = key;
 					shape.enlargedAABB = false;
 				}
 			}
 		}
 		t.sync();
+		// the walks to the root, four per thread in lockstep (see enlargeWalks)
+		for ( int first = t.rank(); first < moveTotal; first += kEnlargeWalks * t.size() )
+			enlargeWalks( w, walks, first, t.size(), moveTotal );
 		if ( t.rank() == 0 )
 			w->moveArray.count = moveTotal;
+		t.sync();
 		F2D_MARK( w, t, pfEnlarge );
 
 		// bullets: continuous against everything, then enlarge (solver.c:1915-1988)

@@ -643,6 +643,10 @@ template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box b
 			{
 				stack[sp++] = n.child1;
 				stack[sp++] = n.child2;
+				// child2 is popped next; child1 waits for that whole subtree: request it now (48-byte nodes can straddle a line)
+				const char* later = reinterpret_cast<const char*>( nodes + n.child1 );
+				prefetchLine( later );
+				prefetchLine( later + sizeof( TreeNode ) - 1 );
 			}
 			else
 			{
