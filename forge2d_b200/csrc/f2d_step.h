@@ -1744,6 +1744,8 @@ F2D_HDF inline void solveContinuous( World* w, int awakeIndex )
 	}
 }
 
+constexpr int kEnlargeByList = -2; // finalizeBody -> stepFinalize: this body's enlarged proxies are found by walking its shapes
+
 // solver.c:543-726, one awake body
 F2D_HDF inline void finalizeBody( World* w, int simIndex )
 {
@@ -1836,6 +1838,12 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 	bool isFast = sim.isFast;
 	Shape* shapes = ptr( w, w->shapes );
 	uint64_t* enlargedBits = ptr( w, w->enlargedBits );
+	// Bodies with a single shape (nearly all) hand their enlarged proxy straight to the move-array pass: the new leaf
+	// box is written here, where the shape record is at hand, and the key is parked by awake index, so that pass does
+	// not have to walk body -> shape again. Other bodies (and fast bullets, whose boxes are not final yet) are marked
+	// kEnlargeByList and go through the shape-list walk of stepFinalize.
+	const bool single = body.shapeCount == 1 && ( sim.isBullet && isFast ) == false;
+	int parkedKey = single ? kNull : kEnlargeByList;
 	int shapeId = body.headShapeId;
 	while ( shapeId != kNull )
 	{
@@ -1855,8 +1863,17 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 				atomOr64( enlargedBits + ( simIndex >> 6 ), 1ull << ( simIndex & 63 ) );
 			}
 		}
+		if ( single && shape.enlargedAABB )
+		{
+			parkedKey = shape.proxyKey;
+			TreeNode& leaf = ptr( w, w->trees[proxyType( parkedKey )].nodes )[proxyId( parkedKey )];
+			leaf.box = shape.fatAABB;
+			leaf.flags |= kNodeMoved;
+			shape.enlargedAABB = false;
+		}
 		shapeId = shape.nextShapeId;
 	}
+	ptr( w, w->islBodies )[simIndex] = parkedKey;
 }
 
 // Team-parallel enlarge of one leaf: the end state (leaf box replaced; every ancestor box = union with it; every
@@ -2255,10 +2272,16 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		BodySim* sims = ptr( w, w->sims );
 		Shape* shapes = ptr( w, w->shapes );
 		int32_t* scan = ptr( w, w->scan );
+		const int32_t* parked = ptr( w, w->islBodies ); // island-solve scratch, free here: see finalizeBody
 		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
 		{
 			int count = 0;
-			if ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) )
+			const int key = parked[i];
+			if ( key != kEnlargeByList )
+			{
+				count = key != kNull ? 1 : 0;
+			}
+			else if ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) )
 			{
 				int bodyId = awakeBodies[i];
 				const BodySim& sim = sims[bodyId];
@@ -2286,7 +2309,19 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		}
 		for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
 		{
-			if ( ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) ) == 0 || moveTotal == 0 )
+			if ( moveTotal == 0 )
+				continue;
+			const int parkedKey = parked[i];
+			if ( parkedKey != kEnlargeByList )
+			{
+				if ( parkedKey != kNull )
+				{
+					walks[scan[i]] = parkedKey;
+					moves[scan[i]] = parkedKey;
+				}
+				continue;
+			}
+			if ( ( eb[i >> 6] & ( 1ull << ( i & 63 ) ) ) == 0 )
 				continue;
 			int bodyId = awakeBodies[i];
 			const BodySim& sim = sims[bodyId];

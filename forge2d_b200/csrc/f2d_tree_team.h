@@ -84,7 +84,7 @@ F2D_HD bool treeNodeIsDissolved( const TreeNode& n ) { return n.height > 0 && ( 
 // Serial build of one small segment [a, e) of the item array: the reference's explicit-stack top-down build
 // (dynamic_tree.c:1716-1869) with its in-place Hoare partition (treePartitionMid), recycling the dissolved node
 // freed[m-1] for the split at m, and computing boxes / heights / categories on the way back up.
-constexpr int kTreeSerialFinish = 24; // segments at most this long are finished by one thread each
+constexpr int kTreeSerialFinish = 12; // segments at most this long are finished by one thread each
 constexpr int kTreeQueueBuildMaxTeam = 256; // teams up to this size use the work-queue build (treeSplitSegment)
 
 F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
@@ -364,7 +364,9 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 	int32_t* leafIndices = ptr( w, tree.leafIndices );
 	V2* leafCenters = ptr( w, tree.leafCenters );
 
-	// ---- collect: items under each dissolved node
+	// ---- collect: items under each dissolved node, bottom-up. A dissolved node has two children, each an item (counts 1)
+	// or a dissolved node (counts what it gathered): the first child to report parks its count in under[], the second
+	// adds its own and carries the sum one level up.
 	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 		s.under[i] = 0;
 	t.sync();
@@ -376,44 +378,88 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		int parent = n.parent;
 		if ( parent == kNull || treeNodeIsDissolved( nodes[parent] ) == false )
 			continue; // inside a kept subtree (the root itself is dissolved here)
+		int carry = 1;
 		for ( int a = parent; a != kNull; a = nodes[a].parent )
-			atomAdd( s.under + a, 1 );
+		{
+			int parkedCount = atomAdd( s.under + a, carry );
+			if ( parkedCount == 0 )
+				break;
+			carry += parkedCount;
+		}
 	}
 	t.sync();
 	const int itemCount = s.under[tree.root];
-	// DFS position of every item and the boundary each dissolved node used to stand for
-	for ( int i = t.rank(); i < nodeSlots; i += t.size() )
+	// DFS position of every item and the boundary each dissolved node used to stand for: the number of items that
+	// precede a node is the sum, over the ancestors it hangs under by child2, of the items under their child1. That is
+	// a suffix sum along the path to the root, computed for all nodes at once by pointer doubling (log2(height) rounds
+	// of "add what my pointer has gathered, then point where it points") instead of one walk to the root per node.
 	{
-		const TreeNode& n = nodes[i];
-		if ( ( n.flags & kNodeAllocated ) == 0 )
-			continue;
-		bool dissolved = treeNodeIsDissolved( n );
-		int parent = n.parent;
-		if ( dissolved == false && ( parent == kNull || treeNodeIsDissolved( nodes[parent] ) == false ) )
-			continue;
-		int before = 0;
-		int child = i;
-		for ( int a = parent; a != kNull; a = nodes[a].parent )
+		const int n2 = 2 * ( w->shapes.cap + 8 ); // node-sized arrays carved from the (not yet used) centre-bound arrays
+		int32_t* base = reinterpret_cast<int32_t*>( s.lo[0][0] );
+		int32_t* acc[2] = { base, base + n2 };
+		int32_t* anc[2] = { base + 2 * n2, base + 3 * n2 };
+		const int height = nodes[tree.root].height; // of the old tree: bounds the depth of every node
+		for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 		{
-			const TreeNode& an = nodes[a];
-			if ( an.child2 == child )
+			const TreeNode& n = nodes[i];
+			int up = kNull, gathered = 0;
+			if ( ( n.flags & kNodeAllocated ) != 0 )
 			{
-				const TreeNode& c1 = nodes[an.child1];
-				before += treeNodeIsDissolved( c1 ) ? s.under[an.child1] : 1;
+				int parent = n.parent;
+				if ( parent != kNull && ( treeNodeIsDissolved( n ) || treeNodeIsDissolved( nodes[parent] ) ) )
+				{
+					const TreeNode& pn = nodes[parent];
+					up = parent;
+					if ( pn.child2 == i )
+						gathered = treeNodeIsDissolved( nodes[pn.child1] ) ? s.under[pn.child1] : 1;
+				}
 			}
-			child = a;
+			acc[0][i] = gathered;
+			anc[0][i] = up;
 		}
-		if ( dissolved )
+		t.sync();
+		int cur = 0;
+		for ( int reach = 1; reach < height + 1; reach *= 2 )
 		{
-			const TreeNode& c1 = nodes[n.child1];
-			int firstHalf = treeNodeIsDissolved( c1 ) ? s.under[n.child1] : 1;
-			s.freed[before + firstHalf - 1] = i;
+			const int nxt = cur ^ 1;
+			for ( int i = t.rank(); i < nodeSlots; i += t.size() )
+			{
+				int up = anc[cur][i];
+				int gathered = acc[cur][i];
+				if ( up != kNull )
+				{
+					gathered += acc[cur][up];
+					up = anc[cur][up];
+				}
+				acc[nxt][i] = gathered;
+				anc[nxt][i] = up;
+			}
+			t.sync();
+			cur = nxt;
 		}
-		else
+		const int32_t* beforeOf = acc[cur];
+		for ( int i = t.rank(); i < nodeSlots; i += t.size() )
 		{
-			V2 c = boxCenter( n.box );
-			leafIndices[before] = i;
-			leafCenters[before] = c;
+			const TreeNode& n = nodes[i];
+			if ( ( n.flags & kNodeAllocated ) == 0 )
+				continue;
+			bool dissolved = treeNodeIsDissolved( n );
+			int parent = n.parent;
+			if ( dissolved == false && ( parent == kNull || treeNodeIsDissolved( nodes[parent] ) == false ) )
+				continue;
+			int before = beforeOf[i];
+			if ( dissolved )
+			{
+				const TreeNode& c1 = nodes[n.child1];
+				int firstHalf = treeNodeIsDissolved( c1 ) ? s.under[n.child1] : 1;
+				s.freed[before + firstHalf - 1] = i;
+			}
+			else
+			{
+				V2 c = boxCenter( n.box );
+				leafIndices[before] = i;
+				leafCenters[before] = c;
+			}
 		}
 	}
 	t.sync();
