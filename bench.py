@@ -322,15 +322,28 @@ def run_b200_arm(args, rank, world_size, local_rank):
     lib.f2dBatch_Step(batch, DT, SUB)
     lib.f2dBatch_ReadBodyEvents(batch, nb, C.byref(ev_ptr), C.byref(cnt_ptr))  # allocates the pinned staging
     barrier()
+    # (a) the three calls one after the other: upload, step, read back
     t0 = time.perf_counter()
     moved = 0
     for _ in range(e2e_steps):
         lib.f2dBatch_SetGravity(batch, gravity, mine)
         lib.f2dBatch_Step(batch, DT, SUB)
         moved = lib.f2dBatch_ReadBodyEvents(batch, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+    e2e_sequential_seconds = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    # (b) the same work per step through the fused call: world slices on separate streams, each slice's events cross
+    # PCIe while later slices are stepped; every step still ends with all events of that step on the host
+    lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lib.f2dBatch_SetGravity(batch, gravity, mine)
+        moved = lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = args.worlds * e2e_steps / e2e_seconds
+    e2e_sequential_value = args.worlds * e2e_steps / e2e_sequential_seconds
+    errors |= lib.f2dBatch_GetErrorFlags(batch)
     lib.f2dHostFree(gravity)
     lib.f2dBatch_Destroy(batch)
 
@@ -362,15 +375,18 @@ def run_b200_arm(args, rank, world_size, local_rank):
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": 8 * mine,
                 "d2h_bytes_per_step": mine * nb * C.sizeof(A.BodyMoveEvent) + 4 * mine, "steps": e2e_steps,
-                "path": "f2dBatch_SetGravity (pinned H2D) + f2dBatch_Step + f2dBatch_ReadBodyEvents (pinned D2H of every "
-                        "body transform), per rank; events read per step: %d" % moved},
+                "path": "f2dBatch_SetGravity (pinned H2D) + f2dBatch_StepAndReadBodyEvents (step in world slices on "
+                        "separate streams, pinned D2H of every body transform of a slice overlapped with the stepping of "
+                        "the next), per rank; events read per step: %d" % moved,
+                "sequential_calls_value": e2e_sequential_value,
+                "sequential_calls_path": "f2dBatch_SetGravity + f2dBatch_Step + f2dBatch_ReadBodyEvents, nothing overlapped"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "stepWorldsCta<%d,%d> (whole world step, one CTA per world)" % (args.batch_threads, args.batch_blocks_per_sm),
                      "algorithmic_bytes_per_world_step": bytes_per_world_step, "worlds_per_launch": mine,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                     "note": "per-world working set (%.1f MB image) is re-touched ~100x per step out of L1/L2, so DRAM "
-                             "bandwidth is not the limiter; the step is bound by serial depth per world" % (world_bytes / 1e6)},
+                     "note": "latency-bound, not bandwidth-bound: chains of dependent gathers per body / contact / tree node; "
+                             "no memory pipe above 35 %% (profiles/README.md); %.1f MB image per world" % (world_bytes / 1e6)},
         "clocks": clocks,
         "batch": {"worlds_this_rank": mine, "bytes_per_world_image": int(world_bytes), "error_flags": int(errors),
                   "counts_before": counts0, "counts_after": counts1},

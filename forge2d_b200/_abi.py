@@ -481,6 +481,8 @@ F2D_FUNCTIONS = {
     "f2dBatch_GetBodyEvents": (c_int, [c_void_p, C.POINTER(BodyMoveEvent), c_int, C.POINTER(c_int)]),
     "f2dBatch_DownloadWorld": (None, [c_void_p, c_int, WorldId]),
     "f2dBatch_ReadBodyEvents": (c_int, [c_void_p, c_int, C.POINTER(C.POINTER(BodyMoveEvent)), C.POINTER(C.POINTER(c_int))]),
+    "f2dBatch_StepAndReadBodyEvents": (c_int, [c_void_p, c_float, c_int, c_int, C.POINTER(C.POINTER(BodyMoveEvent)),
+                                               C.POINTER(C.POINTER(c_int))]),
     "f2dBatch_SetGravity": (None, [c_void_p, c_void_p, c_int]),
     "f2dBatch_EventRecord": (None, [c_void_p, c_int]),
     "f2dBatch_EventElapsedMs": (c_float, [c_void_p, c_int, c_int]),

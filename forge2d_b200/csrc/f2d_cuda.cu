@@ -251,6 +251,12 @@ struct f2dBatch
 	b2BodyMoveEvent* hostEvents = nullptr; // pinned staging for f2dBatch_ReadBodyEvents
 	int* hostCounts = nullptr;
 	int hostEventCap = 0;
+	// f2dBatch_StepAndReadBodyEvents: the batch is stepped in slices of worlds, one stream each, so that the read-back
+	// of a slice crosses PCIe while the next slices are still being stepped
+	static constexpr int kSlices = 8;
+	cudaStream_t sliceStreams[kSlices] = {};
+	cudaEvent_t sliceDone[kSlices] = {};
+	cudaEvent_t inputsReady = nullptr;
 };
 
 extern "C" {
@@ -314,6 +320,15 @@ void f2dBatch_Destroy( f2dBatch* b )
 		cudaFreeHost( b->hostCounts );
 	for ( int i = 0; i < 8; ++i )
 		cudaEventDestroy( b->events[i] );
+	for ( int i = 0; i < f2dBatch::kSlices; ++i )
+	{
+		if ( b->sliceStreams[i] )
+			cudaStreamDestroy( b->sliceStreams[i] );
+		if ( b->sliceDone[i] )
+			cudaEventDestroy( b->sliceDone[i] );
+	}
+	if ( b->inputsReady )
+		cudaEventDestroy( b->inputsReady );
 	cudaStreamDestroy( b->stream );
 	delete b;
 }
@@ -418,6 +433,97 @@ int f2dBatch_ReadBodyEvents( f2dBatch* b, int maxBodies, const b2BodyMoveEvent**
 	cudaMemcpyAsync( b->hostEvents, b->devEvents, (size_t)need * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost, b->stream );
 	cudaMemcpyAsync( b->hostCounts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
 	cudaOk( cudaStreamSynchronize( b->stream ), "batch events" );
+	*outEvents = b->hostEvents;
+	*outCounts = b->hostCounts;
+	int total = 0;
+	for ( int i = 0; i < b->count; ++i )
+		total += b->hostCounts[i];
+	return total;
+}
+
+static bool ensureEventBuffers( f2dBatch* b, int maxBodies )
+{
+	using namespace f2d;
+	int need = b->count * maxBodies;
+	if ( need > b->eventCap )
+	{
+		cudaFree( b->devEvents );
+		cudaFree( b->devCounts );
+		cudaMalloc( &b->devEvents, (size_t)need * sizeof( BodyMoveEvent ) );
+		cudaMalloc( &b->devCounts, (size_t)b->count * sizeof( int ) );
+		b->eventCap = need;
+	}
+	if ( need > b->hostEventCap )
+	{
+		if ( b->hostEvents )
+			cudaFreeHost( b->hostEvents );
+		if ( b->hostCounts )
+			cudaFreeHost( b->hostCounts );
+		cudaMallocHost( &b->hostEvents, (size_t)need * sizeof( BodyMoveEvent ) );
+		cudaMallocHost( &b->hostCounts, (size_t)b->count * sizeof( int ) );
+		b->hostEventCap = need;
+	}
+	return cudaOk( cudaGetLastError(), "batch event buffers" );
+}
+
+// One step of every world AND the body move events of that step in the pinned staging buffer, as one call. Same
+// results as f2dBatch_Step followed by f2dBatch_ReadBodyEvents; the difference is the schedule: the worlds are stepped
+// in slices on separate streams (whatever was queued on the batch stream before - e.g. f2dBatch_SetGravity - is waited
+// for first), each slice's events are gathered and copied to the host as soon as that slice is done, so all but the
+// last slice's copy overlaps with stepping. Worlds are independent (B2/src/world.c:33-35), slices share nothing.
+int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodies, const b2BodyMoveEvent** outEvents, const int** outCounts )
+{
+	using namespace f2d;
+	if ( b == nullptr || maxBodies <= 0 )
+		return 0;
+	if ( ensureEventBuffers( b, maxBodies ) == false )
+		return 0;
+	if ( b->inputsReady == nullptr )
+	{
+		cudaEventCreateWithFlags( &b->inputsReady, cudaEventDisableTiming );
+		// earlier slices get the higher stream priority: their blocks are dispatched first, so the slices finish one
+		// after the other (and their copies start one after the other) instead of all together at the end
+		int least = 0, greatest = 0;
+		cudaDeviceGetStreamPriorityRange( &least, &greatest );
+		for ( int i = 0; i < f2dBatch::kSlices; ++i )
+		{
+			int priority = greatest + i < least ? greatest + i : least;
+			cudaStreamCreateWithPriority( &b->sliceStreams[i], cudaStreamNonBlocking, priority );
+			cudaEventCreateWithFlags( &b->sliceDone[i], cudaEventDisableTiming );
+		}
+	}
+	// slices of whole waves (resident blocks of the whole GPU) when the batch is large enough for that to matter
+	int slices = f2dBatch::kSlices;
+	while ( slices > 1 && b->count / slices < 148 * b->blocksPerSM / 2 )
+		slices -= 1;
+	cudaEventRecord( b->inputsReady, b->stream );
+	int start = 0;
+	for ( int i = 0; i < slices; ++i )
+	{
+		int end = (int)( (long long)b->count * ( i + 1 ) / slices );
+		int n = end - start;
+		cudaStream_t st = b->sliceStreams[i];
+		cudaStreamWaitEvent( st, b->inputsReady, 0 );
+		if ( n > 0 )
+		{
+			char* base = b->dev + b->stride * (unsigned long long)start;
+			if ( launchBatchStep( b->threads, b->blocksPerSM, base, b->stride, n, dt, sub, 1, st ) == false )
+			{
+				reportError( "f2dBatch_StepAndReadBodyEvents: no batch kernel for %d threads x %d blocks/SM", b->threads, b->blocksPerSM );
+				return 0;
+			}
+			BodyMoveEvent* devOut = b->devEvents + (size_t)start * maxBodies;
+			launchGatherMoveEvents( base, b->stride, n, devOut, maxBodies, b->devCounts + start, st );
+			g_launchCount += 2;
+			cudaMemcpyAsync( b->hostEvents + (size_t)start * maxBodies, devOut, (size_t)n * maxBodies * sizeof( BodyMoveEvent ),
+							 cudaMemcpyDeviceToHost, st );
+			cudaMemcpyAsync( b->hostCounts + start, b->devCounts + start, (size_t)n * sizeof( int ), cudaMemcpyDeviceToHost, st );
+		}
+		cudaEventRecord( b->sliceDone[i], st );
+		cudaStreamWaitEvent( b->stream, b->sliceDone[i], 0 );
+		start = end;
+	}
+	cudaOk( cudaStreamSynchronize( b->stream ), "batch step + events" );
 	*outEvents = b->hostEvents;
 	*outCounts = b->hostCounts;
 	int total = 0;

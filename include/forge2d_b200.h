@@ -486,6 +486,10 @@ F2D_API int f2dBatch_GetWorldCount( f2dBatch* batch );
 F2D_API int f2dBatch_GetBodyEvents( f2dBatch* batch, b2BodyMoveEvent* out, int maxBodiesPerWorld, int* counts );
 /// Same records through a pinned staging buffer owned by the batch; pointers valid until the next call.
 F2D_API int f2dBatch_ReadBodyEvents( f2dBatch* batch, int maxBodiesPerWorld, const b2BodyMoveEvent** outEvents, const int** outCounts );
+/// f2dBatch_Step + f2dBatch_ReadBodyEvents as one call (same results): the worlds are stepped in slices on separate
+/// streams and each slice's events cross PCIe while later slices are still being stepped. Returns the event total.
+F2D_API int f2dBatch_StepAndReadBodyEvents( f2dBatch* batch, float timeStep, int subStepCount, int maxBodiesPerWorld,
+											const b2BodyMoveEvent** outEvents, const int** outCounts );
 /// Per-world gravity: the batch counterpart of b2World_SetGravity (box2d.h:135); `gravity` holds `count` vectors.
 F2D_API void f2dBatch_SetGravity( f2dBatch* batch, const b2Vec2* gravity, int count );
 /// CUDA events on the batch's stream (slots 0..7) so callers can time device work without a torch stream.
