@@ -197,6 +197,29 @@ OverlapResultFcn = C.CFUNCTYPE(c_bool, ShapeId, c_void_p)
 CastResultFcn = C.CFUNCTYPE(c_float, ShapeId, Vec2, Vec2, c_float, c_void_p)
 
 
+# b2DebugDraw (types.h:1383-1460); b2HexColor is an int-sized enum
+DrawPolygonFcn = C.CFUNCTYPE(None, C.POINTER(Vec2), c_int, c_int, c_void_p)
+DrawSolidPolygonFcn = C.CFUNCTYPE(None, Transform, C.POINTER(Vec2), c_int, c_float, c_int, c_void_p)
+DrawCircleFcn = C.CFUNCTYPE(None, Vec2, c_float, c_int, c_void_p)
+DrawSolidCircleFcn = C.CFUNCTYPE(None, Transform, c_float, c_int, c_void_p)
+DrawSolidCapsuleFcn = C.CFUNCTYPE(None, Vec2, Vec2, c_float, c_int, c_void_p)
+DrawSegmentFcn = C.CFUNCTYPE(None, Vec2, Vec2, c_int, c_void_p)
+DrawTransformFcn = C.CFUNCTYPE(None, Transform, c_void_p)
+DrawPointFcn = C.CFUNCTYPE(None, Vec2, c_float, c_int, c_void_p)
+DrawStringFcn = C.CFUNCTYPE(None, Vec2, C.c_char_p, c_int, c_void_p)
+DEBUG_DRAW_OPTIONS = ("useDrawingBounds", "drawShapes", "drawJoints", "drawJointExtras", "drawBounds", "drawMass", "drawBodyNames",
+                      "drawContacts", "drawGraphColors", "drawContactNormals", "drawContactImpulses", "drawContactFeatures",
+                      "drawFrictionImpulses", "drawIslands")
+
+
+class DebugDraw(C.Structure):
+    _fields_ = ([("DrawPolygonFcn", DrawPolygonFcn), ("DrawSolidPolygonFcn", DrawSolidPolygonFcn), ("DrawCircleFcn", DrawCircleFcn),
+                 ("DrawSolidCircleFcn", DrawSolidCircleFcn), ("DrawSolidCapsuleFcn", DrawSolidCapsuleFcn),
+                 ("DrawSegmentFcn", DrawSegmentFcn), ("DrawTransformFcn", DrawTransformFcn), ("DrawPointFcn", DrawPointFcn),
+                 ("DrawStringFcn", DrawStringFcn), ("drawingBounds", AABB)] +
+                [(name, c_bool) for name in DEBUG_DRAW_OPTIONS] + [("context", c_void_p)])
+
+
 class ExplosionDef(C.Structure):
     _fields_ = [("maskBits", C.c_uint64), ("position", Vec2), ("radius", c_float), ("falloff", c_float),
                 ("impulsePerLength", c_float)]
@@ -458,6 +481,8 @@ B2_FUNCTIONS = {
     "b2World_CastRay": (TreeStats, [WorldId, Vec2, Vec2, QueryFilter, CastResultFcn, c_void_p]),
     "b2World_CastRayClosest": (RayResult, [WorldId, Vec2, Vec2, QueryFilter]),
     "b2World_Explode": (None, [WorldId, C.POINTER(ExplosionDef)]),
+    "b2DefaultDebugDraw": (DebugDraw, []),
+    "b2World_Draw": (None, [WorldId, C.POINTER(DebugDraw)]),
     "b2World_SetCustomFilterCallback": (None, [WorldId, c_void_p, c_void_p]),
     "b2World_SetPreSolveCallback": (None, [WorldId, c_void_p, c_void_p]),
 }

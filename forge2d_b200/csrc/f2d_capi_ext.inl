@@ -1519,4 +1519,5 @@ void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn, void* c
 	setError( mutableImage( *hw ), kErrUnsupported, __LINE__ );
 }
 
+#include "f2d_capi_draw.inl"
 #include "f2d_capi_joints.inl"

@@ -308,6 +308,44 @@ F2D_HD float relativeAngle( Rot b, Rot a )
 	return atan2Poly( s, c );
 }
 F2D_HD float unwindAngle( float radians ) { return remainderf( radians, 2.0f * kPi ); }
+// b2MakeRot( radians ) = b2ComputeCosSin: rational approximations of cosine / sine, then normalised
+// (math_functions.c:107-148, math_functions.h:370-374)
+F2D_HD Rot makeRotAngle( float radians )
+{
+	float x = unwindAngle( radians );
+	float pi2 = kPi * kPi;
+	float c;
+	if ( x < -0.5f * kPi )
+	{
+		float y = x + kPi;
+		float y2 = y * y;
+		c = -( pi2 - 4.0f * y2 ) / ( pi2 + y2 );
+	}
+	else if ( x > 0.5f * kPi )
+	{
+		float y = x - kPi;
+		float y2 = y * y;
+		c = -( pi2 - 4.0f * y2 ) / ( pi2 + y2 );
+	}
+	else
+	{
+		float y2 = x * x;
+		c = ( pi2 - 4.0f * y2 ) / ( pi2 + y2 );
+	}
+	float s;
+	if ( x < 0.0f )
+	{
+		float y = x + kPi;
+		s = -16.0f * y * ( kPi - y ) / ( 5.0f * pi2 - 4.0f * y * ( kPi - y ) );
+	}
+	else
+	{
+		s = 16.0f * x * ( kPi - x ) / ( 5.0f * pi2 - 4.0f * x * ( kPi - x ) );
+	}
+	float mag = sqrtf( s * s + c * c );
+	float invMag = mag > 0.0 ? 1.0f / mag : 0.0f;
+	return Rot{ c * invMag, s * invMag };
+}
 
 // Softness: B2/src/solver.h:140-182
 struct Soft

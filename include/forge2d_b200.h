@@ -241,6 +241,33 @@ typedef float b2CastResultFcn( b2ShapeId shapeId, b2Vec2 point, b2Vec2 normal, f
 typedef bool b2CustomFilterFcn( b2ShapeId shapeIdA, b2ShapeId shapeIdB, void* context );
 typedef bool b2PreSolveFcn( b2ShapeId shapeIdA, b2ShapeId shapeIdB, b2Manifold* manifold, void* context );
 
+// ---- debug draw: types.h:1228-1460 (b2HexColor is an int-sized enum; only the colours b2World_Draw emits are named here)
+typedef enum b2HexColor
+{
+	b2_colorBlack = 0x000000, b2_colorBlue = 0x0000FF, b2_colorBlueViolet = 0x8A2BE2, b2_colorChocolate = 0xD2691E, b2_colorCoral = 0xFF7F50,
+	b2_colorCyan = 0x00FFFF, b2_colorDarkSeaGreen = 0x8FBC8F, b2_colorDimGray = 0x696969, b2_colorGainsboro = 0xDCDCDC, b2_colorGold = 0xFFD700,
+	b2_colorGoldenRod = 0xDAA520, b2_colorGray = 0x808080, b2_colorGreen = 0x008000, b2_colorLightGray = 0xD3D3D3, b2_colorLightGreen = 0x90EE90,
+	b2_colorMagenta = 0xFF00FF, b2_colorOrange = 0xFFA500, b2_colorOrangeRed = 0xFF4500, b2_colorPaleGreen = 0x98FB98, b2_colorPink = 0xFFC0CB,
+	b2_colorRed = 0xFF0000, b2_colorRoyalBlue = 0x4169E1, b2_colorSalmon = 0xFA8072, b2_colorSlateGray = 0x708090, b2_colorTurquoise = 0x40E0D0,
+	b2_colorViolet = 0xEE82EE, b2_colorWheat = 0xF5DEB3, b2_colorWhite = 0xFFFFFF, b2_colorYellow = 0xFFFF00
+} b2HexColor;
+typedef struct b2DebugDraw // types.h:1383-1460: nine callbacks, the bounds, fourteen option flags, the user context
+{
+	void ( *DrawPolygonFcn )( const b2Vec2* vertices, int vertexCount, b2HexColor color, void* context );
+	void ( *DrawSolidPolygonFcn )( b2Transform transform, const b2Vec2* vertices, int vertexCount, float radius, b2HexColor color, void* context );
+	void ( *DrawCircleFcn )( b2Vec2 center, float radius, b2HexColor color, void* context );
+	void ( *DrawSolidCircleFcn )( b2Transform transform, float radius, b2HexColor color, void* context );
+	void ( *DrawSolidCapsuleFcn )( b2Vec2 p1, b2Vec2 p2, float radius, b2HexColor color, void* context );
+	void ( *DrawSegmentFcn )( b2Vec2 p1, b2Vec2 p2, b2HexColor color, void* context );
+	void ( *DrawTransformFcn )( b2Transform transform, void* context );
+	void ( *DrawPointFcn )( b2Vec2 p, float size, b2HexColor color, void* context );
+	void ( *DrawStringFcn )( b2Vec2 p, const char* s, b2HexColor color, void* context );
+	b2AABB drawingBounds;
+	bool useDrawingBounds, drawShapes, drawJoints, drawJointExtras, drawBounds, drawMass, drawBodyNames, drawContacts, drawGraphColors,
+		drawContactNormals, drawContactImpulses, drawContactFeatures, drawFrictionImpulses, drawIslands;
+	void* context;
+} b2DebugDraw;
+
 typedef struct b2Counters // types.h:492-505
 {
 	int bodyCount, shapeCount, contactCount, jointCount, islandCount, stackUsed, staticTreeHeight, treeHeight, byteCount, taskCount;
@@ -463,6 +490,11 @@ F2D_API b2RayResult b2World_CastRayClosest( b2WorldId worldId, b2Vec2 origin, b2
 F2D_API void b2World_Explode( b2WorldId worldId, const b2ExplosionDef* explosionDef );												 // world.c:2718
 /// Host callbacks from inside the step cannot run on the device path: registering one reports an error (loudly).
 F2D_API void b2World_SetCustomFilterCallback( b2WorldId worldId, b2CustomFilterFcn* fcn, void* context );
+/// types.c:136-151: a b2DebugDraw whose callbacks are all no-ops and whose options are all off.
+F2D_API b2DebugDraw b2DefaultDebugDraw( void );
+/// box2d.h:92 / world.c:1161-1489: emits the world's debug geometry through the callbacks of `draw` (host callbacks, on
+/// the calling thread, during the call), in the reference's order. Reads the device-resident state.
+F2D_API void b2World_Draw( b2WorldId worldId, b2DebugDraw* draw );
 F2D_API void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn, void* context );
 #include "forge2d_b200_joints.h"
 

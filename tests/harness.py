@@ -165,3 +165,32 @@ def state_hash(snap, keys=("bodies", "contacts", "islands", "shapes", "joints", 
                 col = col + np.float32(0.0)
             h.update(col.tobytes())
     return h.hexdigest()
+
+
+def record_draw(lib, world, bounds=None, **options):
+    """Calls b2World_Draw with recording callbacks; returns the list of (primitive, arguments...) in emission order."""
+    calls = []
+    v = lambda p: (p.x, p.y)
+    t = lambda x: (x.p.x, x.p.y, x.q.c, x.q.s)
+    keep = [
+        A.DrawPolygonFcn(lambda vs, n, color, ctx: calls.append(("polygon", tuple(v(vs[i]) for i in range(n)), color))),
+        A.DrawSolidPolygonFcn(lambda xf, vs, n, r, color, ctx: calls.append(("solid_polygon", t(xf), tuple(v(vs[i]) for i in range(n)), r, color))),
+        A.DrawCircleFcn(lambda c, r, color, ctx: calls.append(("circle", v(c), r, color))),
+        A.DrawSolidCircleFcn(lambda xf, r, color, ctx: calls.append(("solid_circle", t(xf), r, color))),
+        A.DrawSolidCapsuleFcn(lambda p1, p2, r, color, ctx: calls.append(("solid_capsule", v(p1), v(p2), r, color))),
+        A.DrawSegmentFcn(lambda p1, p2, color, ctx: calls.append(("segment", v(p1), v(p2), color))),
+        A.DrawTransformFcn(lambda xf, ctx: calls.append(("transform", t(xf)))),
+        A.DrawPointFcn(lambda p, size, color, ctx: calls.append(("point", v(p), size, color))),
+        A.DrawStringFcn(lambda p, s, color, ctx: calls.append(("string", v(p), bytes(s), color))),
+    ]
+    draw = lib.b2DefaultDebugDraw()
+    (draw.DrawPolygonFcn, draw.DrawSolidPolygonFcn, draw.DrawCircleFcn, draw.DrawSolidCircleFcn, draw.DrawSolidCapsuleFcn,
+     draw.DrawSegmentFcn, draw.DrawTransformFcn, draw.DrawPointFcn, draw.DrawStringFcn) = keep
+    for name, value in options.items():
+        assert name in A.DEBUG_DRAW_OPTIONS, name
+        setattr(draw, name, value)
+    if bounds is not None:
+        draw.useDrawingBounds = True
+        draw.drawingBounds = A.AABB(A.Vec2(bounds[0], bounds[1]), A.Vec2(bounds[2], bounds[3]))
+    lib.b2World_Draw(world, C.byref(draw))
+    return calls

@@ -241,3 +241,56 @@ def test_chain_shapes_match_reference_emu(ref, emu):
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_chain_shapes_match_reference_gpu(ref, gpu, mode):
     _chain_session(ref, gpu, mode=mode)
+
+
+# ---- debug draw ----------------------------------------------------------------------------------------------
+DRAW_OPTION_SETS = [
+    dict(drawShapes=True),
+    dict(drawShapes=True, drawJoints=True, drawJointExtras=True, drawBounds=True, drawMass=True, drawBodyNames=True,
+         drawContacts=True, drawContactNormals=True, drawContactFeatures=True, drawFrictionImpulses=True, drawIslands=True),
+    dict(drawJoints=True, drawGraphColors=True, drawContacts=True, drawContactImpulses=True),
+]
+
+
+def _draw_session(ref, lib, make, frames, mode=None, bounds=(-6.0, -2.0, 9.0, 14.0)):
+    """b2World_Draw emits the same primitives, in the same order, with the same bits as the reference (world.c:1161-1489),
+    for the whole world and for a drawing window, on freshly built and on stepped (partly sleeping) worlds."""
+    lib.f2dClearLastError()
+    a, b = make(ref), make(lib)
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(b.world, mode)
+    for s, L in ((a, ref), (b, lib)):
+        for k, body in enumerate(s.bodies[:12:3]):
+            L.b2Body_SetName(body, b"body-%d" % k)
+    emitted = 0
+    for f in range(frames + 1):
+        if f in (0, 3, frames // 2, frames):
+            for options in DRAW_OPTION_SETS:
+                for window in (None, bounds):
+                    ca = H.record_draw(ref, a.world, bounds=window, **options)
+                    cb = H.record_draw(lib, b.world, bounds=window, **options)
+                    assert len(ca) == len(cb), "frame %d %s window %s: %d vs %d primitives" % (f, sorted(options), window, len(ca), len(cb))
+                    for i, (x, y) in enumerate(zip(ca, cb)):
+                        assert x == y, "frame %d %s window %s, primitive %d: reference %r, ours %r" % (f, sorted(options), window, i, x, y)
+                    emitted += len(ca)
+        a.step()
+        b.step()
+    assert emitted > 1000
+    assert lib.f2dGetLastError() == b""
+    a.destroy()
+    b.destroy()
+
+
+def test_debug_draw_matches_reference_emu(ref, emu):
+    _draw_session(ref, emu, lambda L: scenes.joint_zoo(L, sets=2), 90)
+    _draw_session(ref, emu, scenes.chain_terrain, 60)
+    _draw_session(ref, emu, scenes.sensor_field, 40)
+    _draw_session(ref, emu, lambda L: scenes.many_pyramids(L, grid=3, base=4), 120)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_debug_draw_matches_reference_gpu(ref, gpu, mode):
+    _draw_session(ref, gpu, lambda L: scenes.joint_zoo(L, sets=2), 90, mode=mode)
+    _draw_session(ref, gpu, scenes.chain_terrain, 60, mode=mode)
+    _draw_session(ref, gpu, lambda L: scenes.many_pyramids(L, grid=3, base=4), 120, mode=mode)
