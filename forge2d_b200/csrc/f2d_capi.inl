@@ -11,6 +11,7 @@
 #include "../../include/forge2d_b200.h"
 #include "../../include/forge2d_b200_debug.h"
 
+#include <algorithm>
 #include <float.h>
 #include <stdio.h>
 #include <string>
@@ -49,6 +50,11 @@ struct HostWorld
 	};
 	std::vector<Chain> chains;
 	bool headerFresh = true;
+	// host callbacks of the callback-mediated step (world.c:1710-1740); the image only carries World::hostCallbacks
+	b2CustomFilterFcn* customFilterFcn = nullptr;
+	void* customFilterContext = nullptr;
+	b2PreSolveFcn* preSolveFcn = nullptr;
+	void* preSolveContext = nullptr;
 };
 
 static HostWorld g_worlds[kMaxWorlds];
@@ -74,6 +80,13 @@ static void backendSynchronize( HostWorld& hw );
 static void backendDownload( HostWorld& hw );
 /// Makes one byte range of the host image current.
 static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes );
+/// Callback-mediated step: the step as a sequence of launches (f2d_step.h Phase) with the host in between.
+/// Begin makes the authoritative copy current, Phase runs one piece, UploadRange pushes host edits of one byte range of
+/// the image, End leaves `hw.img`'s header current like backendStep. DownloadRange synchronises with the phases queued.
+static void backendPhaseBegin( HostWorld& hw );
+static void backendPhase( HostWorld& hw, float dt, int subSteps, int phase );
+static void backendUploadRange( HostWorld& hw, uint64_t off, uint64_t bytes );
+static void backendPhaseEnd( HostWorld& hw );
 static void backendRelease( HostWorld& hw );
 static void backendStepTimes( HostWorld& hw, float* out5 );
 static void backendEnableTiming( HostWorld& hw, bool flag );
@@ -507,7 +520,7 @@ b2WorldId b2CreateWorld( const b2WorldDef* def )
 	if ( def->frictionCallback != nullptr || def->restitutionCallback != nullptr )
 	{
 		reportError( "b2CreateWorld: host friction/restitution callbacks cannot run inside the device step; default mixing is used" );
-		w->hasHostCallbacks = true;
+		w->hostCallbacks |= kHostMixing;
 	}
 	hw.state = kHostNewer;
 	return b2WorldId{ (uint16_t)( index + 1 ), hw.generation };
@@ -546,6 +559,175 @@ static void prepareStep( HostWorld& hw )
 	}
 }
 
+// b2World_Step for a world with b2CustomFilterFcn / b2PreSolveFcn registered. Both are host functions that must run on
+// the calling thread during the call (SURVEY §8b threading), so the step is cut where the reference calls them:
+//   pairs query | custom filter over the candidate pairs (broad_phase.c:267-278) | contact creation,
+//   narrowphase | pre-solve over the touching contacts that ask for it (contact.c:504-517) | rest of the update,
+// with only the few arrays the callbacks need crossing PCIe. Call order = the reference's with one worker: moved proxies
+// in move-array order x tree-hit order; contacts in work-list order (colours 0..11, then the non-touching list).
+template <class T> static void downloadArray( HostWorld& hw, const Arr<T>& a, int first, int count )
+{
+	if ( count > 0 )
+		backendDownloadRange( hw, a.off + (uint64_t)first * sizeof( T ), (uint64_t)count * sizeof( T ) );
+}
+template <class T> static void uploadArray( HostWorld& hw, const Arr<T>& a, int first, int count )
+{
+	if ( count > 0 )
+		backendUploadRange( hw, a.off + (uint64_t)first * sizeof( T ), (uint64_t)count * sizeof( T ) );
+}
+static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
+{
+	World* w = hw.img;
+	const int moveCountBefore = w->moveArray.count; // header is current in every sync state
+	backendPhaseBegin( hw );
+	backendPhase( hw, dt, subSteps, kPhasePairsQuery );
+	if ( hw.customFilterFcn != nullptr && dt != 0.0f && moveCountBefore > 0 )
+	{
+		backendDownloadRange( hw, 0, sizeof( World ) );
+		const int moveCount = w->moveArray.count;
+		const int total = w->step.orderedPairCount;
+		if ( total > 0 )
+		{
+			const int pairCount = w->step.pairCount < w->movePairs.cap ? w->step.pairCount : w->movePairs.cap;
+			downloadArray( hw, w->pairOffsets, 0, moveCount );
+			downloadArray( hw, w->pairOrder, 0, total );
+			downloadArray( hw, w->movePairs, 0, pairCount );
+			const int32_t* offsets = ptr( w, w->pairOffsets );
+			const int32_t* ordered = ptr( w, w->pairOrder );
+			MovePair* pairs = ptr( w, w->movePairs );
+			const Shape* shapes = ptr( w, w->shapes ); // generations never change on the device
+			bool rejected = false;
+			for ( int i = 0; i < moveCount; ++i )
+			{
+				const int begin = offsets[i], end = i + 1 < moveCount ? offsets[i + 1] : total;
+				for ( int k = end - 1; k >= begin; --k ) // creation order is the reverse of hit order
+				{
+					MovePair& pair = pairs[ordered[k]];
+					b2ShapeId idA = { pair.shapeA + 1, w->worldId, shapes[pair.shapeA].generation };
+					b2ShapeId idB = { pair.shapeB + 1, w->worldId, shapes[pair.shapeB].generation };
+					if ( hw.customFilterFcn( idA, idB, hw.customFilterContext ) == false )
+					{
+						pair.shapeA = kNull;
+						rejected = true;
+					}
+				}
+			}
+			if ( rejected )
+				uploadArray( hw, w->movePairs, 0, pairCount );
+		}
+	}
+	backendPhase( hw, dt, subSteps, kPhasePairsCreate );
+	backendPhase( hw, dt, subSteps, kPhaseCollideNarrow );
+	if ( hw.preSolveFcn != nullptr && dt != 0.0f )
+	{
+		backendDownloadRange( hw, 0, sizeof( World ) );
+		int pending = w->step.preSolveCount;
+		if ( pending > w->stateList.cap )
+			pending = w->stateList.cap;
+		if ( pending > w->pairOrder.cap )
+			pending = w->pairOrder.cap;
+		if ( pending > 0 )
+		{
+			downloadArray( hw, w->stateList, 0, pending );
+			downloadArray( hw, w->pairOrder, 0, pending );
+			const int32_t* ids = ptr( w, w->stateList );
+			int32_t* workIndexThenVerdict = ptr( w, w->pairOrder );
+			std::vector<int> order( pending );
+			int lo = ids[0], hi = ids[0];
+			for ( int k = 0; k < pending; ++k )
+			{
+				order[k] = k;
+				lo = ids[k] < lo ? ids[k] : lo;
+				hi = ids[k] > hi ? ids[k] : hi;
+			}
+			std::sort( order.begin(), order.end(), [&]( int a, int b ) { return workIndexThenVerdict[a] < workIndexThenVerdict[b]; } );
+			downloadArray( hw, w->contactSims, lo, hi - lo + 1 );
+			const ContactSim* sims = ptr( w, w->contactSims );
+			const Shape* shapes = ptr( w, w->shapes );
+			std::vector<int32_t> verdicts( pending );
+			for ( int k : order )
+			{
+				const ContactSim& sim = sims[ids[k]];
+				Manifold manifold = sim.manifold; // what the reference hands out: the raw result of the manifold function
+				unparkOldImpulses( manifold );
+				b2ShapeId idA = { sim.shapeIdA + 1, w->worldId, shapes[sim.shapeIdA].generation };
+				b2ShapeId idB = { sim.shapeIdB + 1, w->worldId, shapes[sim.shapeIdB].generation };
+				verdicts[k] = hw.preSolveFcn( idA, idB, reinterpret_cast<b2Manifold*>( &manifold ), hw.preSolveContext ) ? 1 : 0;
+			}
+			for ( int k = 0; k < pending; ++k )
+				workIndexThenVerdict[k] = verdicts[k];
+			uploadArray( hw, w->pairOrder, 0, pending );
+		}
+	}
+	backendPhase( hw, dt, subSteps, kPhaseCollideFinish );
+	backendPhase( hw, dt, subSteps, kPhaseSolve );
+	if ( dt == 0.0f )
+	{
+		backendPhase( hw, dt, subSteps, kPhaseFinalize );
+		backendPhaseEnd( hw );
+		return;
+	}
+	// The continuous pass consults the custom filter per candidate shape while it walks the trees and the pre-solve
+	// callback per hit (solver.c:271-282, 366-379): like the world queries, that traversal runs on the host image, with the
+	// same solveContinuous the device runs, for the (rare) fast bodies of this step only; the image crosses PCIe only
+	// in steps that have any.
+	struct Hooks
+	{
+		static b2ShapeId id( World* w, int shapeId ) { return b2ShapeId{ shapeId + 1, w->worldId, ptr( w, w->shapes )[shapeId].generation }; }
+		static bool filter( void* context, int shapeId, int fastShapeId )
+		{
+			HostWorld* hw = static_cast<HostWorld*>( context );
+			return hw->customFilterFcn( id( hw->img, shapeId ), id( hw->img, fastShapeId ), hw->customFilterContext );
+		}
+		static bool preSolve( void* context, int shapeId, int fastShapeId, Manifold* manifold )
+		{
+			HostWorld* hw = static_cast<HostWorld*>( context );
+			return hw->preSolveFcn( id( hw->img, shapeId ), id( hw->img, fastShapeId ), reinterpret_cast<b2Manifold*>( manifold ),
+									hw->preSolveContext );
+		}
+	};
+	auto onHostImage = [&]( auto&& work ) {
+		backendDownload( hw ); // full image, synchronises with the phases queued
+		g_hostContinuous.filter = hw.customFilterFcn != nullptr ? Hooks::filter : nullptr;
+		g_hostContinuous.preSolve = hw.preSolveFcn != nullptr ? Hooks::preSolve : nullptr;
+		g_hostContinuous.context = &hw;
+		work();
+		g_hostContinuous = HostContinuousHooks{};
+		hw.state = kHostNewer;
+		backendPhaseBegin( hw ); // uploads
+	};
+	backendPhase( hw, dt, subSteps, kPhaseFinalizeBodies );
+	backendDownloadRange( hw, 0, sizeof( World ) );
+	if ( w->step.fastDeferredCount > 0 )
+	{
+		onHostImage( [&]() {
+			const int n = w->step.fastDeferredCount;
+			const int32_t* parkedFromEnd = ptr( w, w->bullets ) + w->bullets.cap - n;
+			std::vector<int> order( parkedFromEnd, parkedFromEnd + n );
+			std::sort( order.begin(), order.end() ); // awake order = the reference's order with one worker
+			for ( int simIndex : order )
+			{
+				solveContinuous( w, simIndex );
+				finalizeBodyTail( w, simIndex );
+			}
+		} );
+	}
+	backendPhase( hw, dt, subSteps, kPhaseFinalizeMoves );
+	backendDownloadRange( hw, 0, sizeof( World ) );
+	if ( w->step.bulletCount > 0 )
+	{
+		onHostImage( [&]() {
+			const int32_t* bullets = ptr( w, w->bullets );
+			std::vector<int> order( bullets, bullets + w->step.bulletCount );
+			std::sort( order.begin(), order.end() );
+			for ( int simIndex : order )
+				solveContinuous( w, simIndex );
+		} );
+	}
+	backendPhase( hw, dt, subSteps, kPhaseFinalizeEnd );
+	backendPhaseEnd( hw );
+}
+
 } // namespace f2d
 extern "C" {
 void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
@@ -564,7 +746,10 @@ void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
 		return;
 	}
 	prepareStep( *hw );
-	backendStep( *hw, timeStep, subStepCount, true );
+	if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+		stepWithHostCallbacks( *hw, timeStep, subStepCount );
+	else
+		backendStep( *hw, timeStep, subStepCount, true );
 	hw->eventsFresh = ( hw->state != kDeviceNewer );
 	checkWorldError( *hw, "b2World_Step" );
 }
@@ -574,6 +759,11 @@ void f2dWorld_StepAsync( b2WorldId worldId, float timeStep, int subStepCount )
 	HostWorld* hw = worldFromId( worldId );
 	if ( hw == nullptr || backendAvailable() == false )
 		return;
+	if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+	{
+		reportError( "f2dWorld_StepAsync: a world with host callbacks must be stepped with b2World_Step (the callbacks run on the calling thread)" );
+		return;
+	}
 	backendStep( *hw, timeStep, subStepCount, false );
 	hw->eventsFresh = false;
 	hw->headerFresh = false;

@@ -1499,24 +1499,27 @@ void b2World_Explode( b2WorldId worldId, const b2ExplosionDef* def ) // world.c:
 		return true;
 	} );
 }
-// world.c:1710-1740: callbacks into host code from inside the step cannot run on the device path
+// world.c:1710-1740. A registered callback switches b2World_Step to the callback-mediated schedule
+// (stepWithHostCallbacks, f2d_capi.inl); passing NULL switches back to the single-launch step.
 void b2World_SetCustomFilterCallback( b2WorldId worldId, b2CustomFilterFcn* fcn, void* context )
 {
-	(void)context;
 	HostWorld* hw = worldFromId( worldId );
-	if ( hw == nullptr || fcn == nullptr )
+	if ( hw == nullptr )
 		return;
-	reportError( "b2World_SetCustomFilterCallback: host callbacks inside the step are not supported by forge2d_b200 (the step runs on the GPU)" );
-	setError( mutableImage( *hw ), kErrUnsupported, __LINE__ );
+	hw->customFilterFcn = fcn;
+	hw->customFilterContext = context;
+	World* w = mutableImage( *hw );
+	w->hostCallbacks = (uint8_t)( fcn != nullptr ? ( w->hostCallbacks | kHostCustomFilter ) : ( w->hostCallbacks & ~kHostCustomFilter ) );
 }
 void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn, void* context )
 {
-	(void)context;
 	HostWorld* hw = worldFromId( worldId );
-	if ( hw == nullptr || fcn == nullptr )
+	if ( hw == nullptr )
 		return;
-	reportError( "b2World_SetPreSolveCallback: host callbacks inside the step are not supported by forge2d_b200 (the step runs on the GPU)" );
-	setError( mutableImage( *hw ), kErrUnsupported, __LINE__ );
+	hw->preSolveFcn = fcn;
+	hw->preSolveContext = context;
+	World* w = mutableImage( *hw );
+	w->hostCallbacks = (uint8_t)( fcn != nullptr ? ( w->hostCallbacks | kHostPreSolve ) : ( w->hostCallbacks & ~kHostPreSolve ) );
 }
 
 #include "f2d_capi_draw.inl"

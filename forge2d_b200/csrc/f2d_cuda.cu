@@ -130,9 +130,9 @@ static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int 
 	return cudaOk( launchSingleGrid( m->dev, m->blockTotals, blocks, dt, sub, phase, m->stream ), "stepWorldGrid cooperative launch" );
 }
 
-static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous )
+// Device copy allocated and current (uploads the host image when it is newer or the image was re-laid out)
+static bool deviceImageCurrent( HostWorld& hw, DeviceMirror* m )
 {
-	DeviceMirror* m = mirror( hw );
 	World* img = hw.img;
 	if ( hw.state == kHostNewer || m->dev == nullptr || m->devBytes != img->imageBytes )
 	{
@@ -142,12 +142,50 @@ static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous
 				cudaFree( m->dev );
 			m->dev = nullptr;
 			if ( cudaOk( cudaMalloc( &m->dev, img->imageBytes ), "cudaMalloc(world image)" ) == false )
-				return;
+				return false;
 			m->devBytes = img->imageBytes;
 		}
 		if ( cudaOk( cudaMemcpyAsync( m->dev, img, img->imageBytes, cudaMemcpyHostToDevice, m->stream ), "upload world image" ) == false )
-			return;
+			return false;
 	}
+	return true;
+}
+
+static void backendPhaseBegin( HostWorld& hw )
+{
+	deviceImageCurrent( hw, mirror( hw ) );
+}
+static void backendPhase( HostWorld& hw, float dt, int subSteps, int phase )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev != nullptr )
+		launchWorld( hw, m, dt, subSteps, phase );
+}
+static void backendUploadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev == nullptr || bytes == 0 )
+		return;
+	cudaMemcpyAsync( reinterpret_cast<char*>( m->dev ) + off, reinterpret_cast<const char*>( hw.img ) + off, bytes, cudaMemcpyHostToDevice,
+					 m->stream );
+	cudaOk( cudaStreamSynchronize( m->stream ), "upload range" ); // the host buffer is reused right away
+}
+static void backendPhaseEnd( HostWorld& hw )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev == nullptr )
+		return;
+	cudaMemcpyAsync( hw.img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
+	hw.state = kDeviceNewer;
+	cudaOk( cudaStreamSynchronize( m->stream ), "world step (callback-mediated)" );
+}
+
+static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous )
+{
+	DeviceMirror* m = mirror( hw );
+	World* img = hw.img;
+	if ( deviceImageCurrent( hw, m ) == false )
+		return;
 	if ( m->timing )
 	{
 		cudaEventRecord( m->ev[0], m->stream );
@@ -270,6 +308,11 @@ f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count )
 	if ( backendAvailable() == false )
 	{
 		reportError( "f2dBatch_Create: no CUDA device available - this library has no CPU fallback" );
+		return nullptr;
+	}
+	if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+	{
+		reportError( "f2dBatch_Create: the template world has host callbacks registered; a batch steps without the host in the loop" );
 		return nullptr;
 	}
 	hostImage( *hw );

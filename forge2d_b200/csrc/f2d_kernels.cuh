@@ -230,33 +230,7 @@ struct GridTeam
 
 template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& t, int phase, float dt, int sub )
 {
-	if ( phase == kPhaseAll )
-	{
-		stepWorld( w, t, dt, sub );
-		return;
-	}
-	if ( dt == 0.0f )
-	{
-		if ( phase == kPhaseBeginPairs )
-			stepZeroDt( w, t );
-		return;
-	}
-	switch ( phase )
-	{
-		case kPhaseBeginPairs:
-			stepBegin( w, t, dt, sub );
-			stepPairs( w, t );
-			break;
-		case kPhaseCollide:
-			stepCollide( w, t );
-			break;
-		case kPhaseSolve:
-			stepSolve( w, t );
-			break;
-		case kPhaseFinalize:
-			stepFinalize( w, t );
-			break;
-	}
+	stepWorldPhase( w, t, phase, dt, sub );
 }
 
 // One thread block per world; worlds are `stride` bytes apart. Grid-stride over worlds. The block steps a copy of the

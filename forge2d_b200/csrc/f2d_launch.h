@@ -3,17 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "f2d_step.h" // World, Phase
+
 namespace f2d
 {
-struct World;
-enum Phase
-{
-	kPhaseAll = 0,
-	kPhaseBeginPairs = 1,
-	kPhaseCollide = 2,
-	kPhaseSolve = 3,
-	kPhaseFinalize = 4
-};
 bool launchBatchStepA( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
 					   cudaStream_t stream );
 bool launchBatchStepB( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,

@@ -83,6 +83,16 @@ F2D_HD uint32_t floatBits( float f )
 	return u;
 #endif
 }
+F2D_HD float floatFromBits( uint32_t u )
+{
+#if defined( __CUDA_ARCH__ )
+	return __uint_as_float( u );
+#else
+	float f;
+	__builtin_memcpy( &f, &u, 4 );
+	return f;
+#endif
+}
 F2D_HD float minf( float a, float b ) { return a < b ? a : b; }				 // :126
 F2D_HD float maxf( float a, float b ) { return a > b ? a : b; }				 // :132
 F2D_HD float absf( float a ) { return a < 0 ? -a : a; }						 // :138

@@ -168,14 +168,66 @@ inline CastOutput rayCastSegment( const RayInput& in, const Segment& shape, bool
 	return out;
 }
 
-// geometry.c:751-842 (sharp polygons; a rounded polygon goes through b2ShapeCast in the reference: see `supported`)
+// b2ShapeCast, distance.c:608-697: conservative advancement of proxy B along `translationB` against proxy A with the
+// GJK distance (core shapes, no radii) until the surfaces are `target` apart; canEncroach is false on the only path that
+// uses it here (the rounded-polygon ray cast below).
+inline CastOutput shapeCast( const ShapeProxy& proxyA, const ShapeProxy& proxyB, Xf transformA, Xf transformB, V2 translationB,
+							 float maxFraction )
+{
+	float linearSlop = kLinearSlop;
+	float totalRadius = proxyA.radius + proxyB.radius;
+	float target = maxf( linearSlop, totalRadius - linearSlop );
+	float tolerance = 0.25f * linearSlop;
+	SimplexCache cache;
+	memset( &cache, 0, sizeof( cache ) );
+	float fraction = 0.0f;
+	V2 delta2 = translationB;
+	Xf xfB = transformB;
+	CastOutput output = noHit();
+	const int maxIterations = 20;
+	for ( int iteration = 0; iteration < maxIterations; ++iteration )
+	{
+		output.iterations += 1;
+		DistanceOutput distanceOutput = shapeDistance( proxyA, proxyB, transformA, xfB, false, &cache );
+		if ( distanceOutput.distance < target + tolerance )
+		{
+			if ( iteration == 0 )
+			{
+				// initial overlap: a common point
+				output.hit = true;
+				V2 c1 = mulAdd( distanceOutput.pointA, proxyA.radius, distanceOutput.normal );
+				V2 c2 = mulAdd( distanceOutput.pointB, -proxyB.radius, distanceOutput.normal );
+				output.point = lerp( c1, c2, 0.5f );
+				return output;
+			}
+			output.fraction = fraction;
+			output.point = mulAdd( distanceOutput.pointA, proxyA.radius, distanceOutput.normal );
+			output.normal = distanceOutput.normal;
+			output.hit = true;
+			return output;
+		}
+		// approaching?
+		float denominator = dot( delta2, distanceOutput.normal );
+		if ( denominator >= 0.0f )
+			return output;
+		fraction += ( target - distanceOutput.distance ) / denominator;
+		if ( fraction >= maxFraction )
+			return output;
+		xfB.p = mulAdd( transformB.p, fraction, delta2 );
+	}
+	return output;
+}
+
+// geometry.c:799-887: sharp polygons by slab clipping, rounded ones through b2ShapeCast of the ray origin as a point
 inline CastOutput rayCastPolygon( const RayInput& in, const Poly& shape, bool* supported )
 {
+	(void)supported;
 	CastOutput out = noHit();
 	if ( shape.radius != 0.0f )
 	{
-		*supported = false;
-		return out;
+		const Xf identity = { { 0.0f, 0.0f }, { 1.0f, 0.0f } };
+		return shapeCast( makeProxy( shape.v, shape.count, shape.radius ), makeProxy( &in.origin, 1, 0.0f ), identity, identity,
+						  in.translation, in.maxFraction );
 	}
 	V2 base = shape.v[0];
 	V2 p1 = sub( in.origin, base );

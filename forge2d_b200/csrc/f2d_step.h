@@ -202,9 +202,20 @@ F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 	}
 }
 
-template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
+// `part`: kPairsAll, or one half of a callback-mediated step: kPairsQuery stops once the candidate pairs stand in
+// creation order (the host then runs the custom filter over them and marks the rejected ones, broad_phase.c:267-278),
+// kPairsCreate resumes from there.
+enum : int
+{
+	kPairsAll = 0,
+	kPairsQuery = 1,
+	kPairsCreate = 2
+};
+template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part = kPairsAll )
 {
 	int moveCount = w->moveArray.count;
+	if ( part == kPairsQuery && t.rank() == 0 )
+		w->step.orderedPairCount = 0;
 	if ( moveCount == 0 )
 		return;
 	if ( moveCount > w->moveHeads.cap )
@@ -213,6 +224,7 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 			setError( w, kErrCapacity, __LINE__ );
 		return;
 	}
+	if ( part != kPairsCreate )
 	{
 		const int32_t* moves = ptr( w, w->moveArray );
 		for ( int i = t.rank(); i < moveCount; i += t.size() )
@@ -241,28 +253,51 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 		const MovePair* pairs = ptr( w, w->movePairs );
 		int32_t* offsets = ptr( w, w->pairOffsets );
 		int32_t* ordered = ptr( w, w->pairOrder );
-		for ( int i = t.rank(); i < moveCount; i += t.size() )
-		{
-			int n = 0;
-			for ( int p = heads[i]; p != kNull; p = pairs[p].next )
-				n += 1;
-			offsets[i] = n;
-		}
-		t.sync();
-		int total = t.exclusiveScan( offsets, moveCount );
-		if ( total > 0 && total <= w->pairOrder.cap )
+		int total = 0;
+		if ( part != kPairsCreate )
 		{
 			for ( int i = t.rank(); i < moveCount; i += t.size() )
 			{
-				int out = offsets[i];
+				int n = 0;
 				for ( int p = heads[i]; p != kNull; p = pairs[p].next )
-					ordered[out++] = p;
+					n += 1;
+				offsets[i] = n;
 			}
 			t.sync();
-			if ( t.rank() == 0 )
+			total = t.exclusiveScan( offsets, moveCount );
+			if ( total > 0 && total <= w->pairOrder.cap )
 			{
-				for ( int k = 0; k < total; ++k )
-					createContact( w, pairs[ordered[k]].shapeA, pairs[ordered[k]].shapeB );
+				for ( int i = t.rank(); i < moveCount; i += t.size() )
+				{
+					int out = offsets[i];
+					for ( int p = heads[i]; p != kNull; p = pairs[p].next )
+						ordered[out++] = p;
+				}
+				t.sync();
+			}
+			else
+			{
+				total = 0;
+			}
+			if ( part == kPairsQuery )
+			{
+				if ( t.rank() == 0 )
+					w->step.orderedPairCount = total;
+				t.sync();
+				return;
+			}
+		}
+		else
+		{
+			total = w->step.orderedPairCount;
+		}
+		if ( total > 0 && t.rank() == 0 )
+		{
+			for ( int k = 0; k < total; ++k )
+			{
+				const MovePair& pair = pairs[ordered[k]];
+				if ( pair.shapeA != kNull ) // kNull: rejected by the host's custom filter
+					createContact( w, pair.shapeA, pair.shapeB );
 			}
 		}
 	}
@@ -288,7 +323,22 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t )
 // world.c:357-445, one contact. The gather is written as two rounds of independent loads (ids and old impulses
 // from the contact record; then shapes, bodies and body sims all at once) because the phase is bound by the
 // latency of dependent loads, not by arithmetic.
-F2D_HDF inline void collideContact( World* w, int contactId )
+// The touching transition of one contact after its update (world.c:417-437): flags for the ordered state pass
+F2D_HD void markTouchTransition( uint64_t* bits, int contactId, uint32_t& simFlags, bool touching, bool wasTouching )
+{
+	if ( touching == true && wasTouching == false )
+	{
+		simFlags |= kSimStartedTouching;
+		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+	}
+	else if ( touching == false && wasTouching == true )
+	{
+		simFlags |= kSimStoppedTouching;
+		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+	}
+}
+
+F2D_HDF inline void collideContact( World* w, int contactId, int workIndex )
 {
 	ContactSim& sim = ptr( w, w->contactSims )[contactId];
 	const Shape* shapes = ptr( w, w->shapes );
@@ -344,16 +394,49 @@ F2D_HDF inline void collideContact( World* w, int contactId )
 	V2 centerOffsetA = rotate( xfA.q, localCenterA );
 	V2 centerOffsetB = rotate( xfB.q, localCenterB );
 	bool touching = updateContact( w, sim, simFlags, old, shapeA, xfA, centerOffsetA, shapeB, xfB, centerOffsetB );
-	if ( touching == true && wasTouching == false )
+	if ( simFlags & kSimPendingPreSolve )
 	{
-		simFlags |= kSimStartedTouching;
-		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
+		// callback-mediated step: queue the contact for the host's pre-solve callback (position in the work list = the
+		// reference's single-worker call order) and leave the rest to finishDeferredContact
+		int slot = atomAdd( &w->step.preSolveCount, 1 );
+		if ( slot < w->stateList.cap && slot < w->pairOrder.cap )
+		{
+			ptr( w, w->stateList )[slot] = contactId;
+			ptr( w, w->pairOrder )[slot] = workIndex;
+		}
+		else
+		{
+			setError( w, kErrCapacity, __LINE__ );
+		}
+		sim.simFlags = simFlags;
+		return;
 	}
-	else if ( touching == false && wasTouching == true )
-	{
-		simFlags |= kSimStoppedTouching;
-		atomOr64( bits + ( contactId >> 6 ), 1ull << ( contactId & 63 ) );
-	}
+	markTouchTransition( bits, contactId, simFlags, touching, wasTouching );
+	sim.simFlags = simFlags;
+}
+
+// Second half of a contact that waited for the host's pre-solve callback (contact.c:504-633, world.c:417-437):
+// `approved` is the callback's return value.
+F2D_HDF inline void finishDeferredContact( World* w, int contactId, bool approved )
+{
+	ContactSim& sim = ptr( w, w->contactSims )[contactId];
+	const Shape* shapes = ptr( w, w->shapes );
+	const BodySim* sims = ptr( w, w->sims );
+	uint32_t simFlags = sim.simFlags & ~kSimPendingPreSolve;
+	const bool wasTouching = ( simFlags & kSimTouching ) != 0;
+	Manifold m = sim.manifold;
+	OldImpulses old = unparkOldImpulses( m );
+	const Shape& shapeA = shapes[sim.shapeIdA];
+	const Shape& shapeB = shapes[sim.shapeIdB];
+	const BodySim& simA = sims[sim.bodyIdA];
+	const BodySim& simB = sims[sim.bodyIdB];
+	V2 centerOffsetA = rotate( simA.transform.q, simA.localCenter );
+	V2 centerOffsetB = rotate( simB.transform.q, simB.localCenter );
+	if ( approved == false )
+		m.pointCount = 0; // "disable contact"
+	bool touching = finishContactUpdate( w, sim, simFlags, m, old, approved, shapeA.enableHitEvents || shapeB.enableHitEvents,
+										 centerOffsetA, centerOffsetB );
+	markTouchTransition( ptr( w, w->contactBits ), contactId, simFlags, touching, wasTouching );
 	sim.simFlags = simFlags;
 }
 
@@ -473,8 +556,33 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 	}
 }
 
-template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
+// `part`: kCollideAll, or one half of a callback-mediated step: kCollideNarrow stops after the narrowphase (the host
+// then answers the queued pre-solve callbacks: World::stateList = contact ids, rewritten by the host as verdicts in
+// World::pairOrder), kCollideFinish completes those contacts and runs the ordered state pass.
+enum : int
 {
+	kCollideAll = 0,
+	kCollideNarrow = 1,
+	kCollideFinish = 2
+};
+template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int part = kCollideAll )
+{
+	if ( part == kCollideFinish )
+	{
+		const int pending = mini( w->step.preSolveCount, mini( w->stateList.cap, w->pairOrder.cap ) );
+		const int32_t* ids = ptr( w, w->stateList );
+		const int32_t* verdicts = ptr( w, w->pairOrder );
+		for ( int k = t.rank(); k < pending; k += t.size() )
+			finishDeferredContact( w, ids[k], verdicts[k] != 0 );
+		t.sync();
+		contactStatePass( w, t );
+		t.sync();
+		F2D_MARK( w, t, pfStatePass );
+		return;
+	}
+	if ( t.rank() == 0 )
+		w->step.preSolveCount = 0;
+
 	// work list = colour 0..11 lists then the awake non-touching list (world.c:504-542)
 	int total = w->awakeContacts.count;
 	for ( int i = 0; i < kColorCount; ++i )
@@ -513,7 +621,7 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 				prefetchL2( &n );
 				prefetchL2( &n.manifold.points[1] );
 			}
-			collideContact( w, id0 );
+			collideContact( w, id0, i );
 			id0 = id1;
 		}
 	};
@@ -524,6 +632,8 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t )
 	narrowphase( t.rank(), t.size() );
 	t.sync();
 	F2D_MARK( w, t, pfNarrow );
+	if ( part == kCollideNarrow )
+		return;
 	contactStatePass( w, t );
 	t.sync();
 	F2D_MARK( w, t, pfStatePass );
@@ -1582,6 +1692,16 @@ F2D_HD Sweep makeSweep( const BodySim& s )
 }
 
 // solver.c:212-387 (custom filter / pre-solve callbacks are rejected at registration on the device path)
+// b2CustomFilterFcn and b2PreSolveFcn inside the continuous pass: set by the callback-mediated step while the HOST runs
+// solveContinuous for the deferred fast bodies (f2d_capi.inl stepWithHostCallbacks); never set on the device.
+struct HostContinuousHooks
+{
+	bool ( *filter )( void* context, int shapeId, int fastShapeId ) = nullptr;					   // solver.c:271-282
+	bool ( *preSolve )( void* context, int shapeId, int fastShapeId, Manifold* manifold ) = nullptr; // solver.c:366-379
+	void* context = nullptr;
+};
+static HostContinuousHooks g_hostContinuous; // host code only
+
 F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
 {
 	World* w = ctx.w;
@@ -1603,6 +1723,10 @@ F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
 	const Body& fastBody = bodies[ctx.fastSim->bodyId];
 	if ( shouldBodiesCollide( w, fastBody, body ) == false )
 		return true;
+#if !defined( __CUDA_ARCH__ )
+	if ( g_hostContinuous.filter != nullptr && g_hostContinuous.filter( g_hostContinuous.context, shapeId, fastShape.id ) == false )
+		return true;
+#endif
 
 	if ( shape.type == kChainSegment )
 	{
@@ -1648,6 +1772,18 @@ F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
 			didHit = true;
 		}
 	}
+#if !defined( __CUDA_ARCH__ )
+	if ( didHit && ( shape.enablePreSolveEvents || fastShape.enablePreSolveEvents ) && g_hostContinuous.preSolve != nullptr )
+	{
+		// the reference hands the callback a temporary manifold at the time of impact (b2ComputeManifold, contact.c:635-640)
+		Xf transformA = sweepTransform( sweepA, hitFraction );
+		Xf transformB = sweepTransform( ctx.sweep, hitFraction );
+		SimplexCache cache;
+		memset( &cache, 0, sizeof( cache ) );
+		Manifold manifold = computeManifold( w, shape, transformA, fastShape, transformB, &cache );
+		didHit = g_hostContinuous.preSolve( g_hostContinuous.context, shapeId, fastShape.id, &manifold );
+	}
+#endif
 	if ( didHit )
 		ctx.fraction = hitFraction;
 	return true;
@@ -1747,6 +1883,7 @@ F2D_HDF inline void solveContinuous( World* w, int awakeIndex )
 constexpr int kEnlargeByList = -2; // finalizeBody -> stepFinalize: this body's enlarged proxies are found by walking its shapes
 
 // solver.c:543-726, one awake body
+F2D_HDF inline void finalizeBodyTail( World* w, int simIndex );
 F2D_HDF inline void finalizeBody( World* w, int simIndex )
 {
 	BodyState& state = ptr( w, w->states )[simIndex];
@@ -1802,6 +1939,16 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 				int bulletIndex = atomAdd( &w->step.bulletCount, 1 );
 				ptr( w, w->bullets )[bulletIndex] = simIndex;
 			}
+			else if ( w->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+			{
+				// callback-mediated step: the continuous pass consults the host's custom filter per candidate shape and
+				// its pre-solve callback per hit (solver.c:271-282, 366-379), so it - and everything of this routine
+				// that depends on it - waits for the host.
+				// Parked from the end of the bullet array downwards.
+				int slot = atomAdd( &w->step.fastDeferredCount, 1 );
+				ptr( w, w->bullets )[w->bullets.cap - 1 - slot] = simIndex;
+				return;
+			}
 			else
 			{
 				solveContinuous( w, simIndex );
@@ -1820,6 +1967,15 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 		body.sleepTime += timeStep;
 	}
 
+	finalizeBodyTail( w, simIndex );
+}
+
+// What finalizeBody does after the continuous pass of a fast body: island sleep votes and the shape boxes
+F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
+{
+	int bodyId = ptr( w, w->awakeBodies )[simIndex];
+	BodySim& sim = ptr( w, w->sims )[bodyId];
+	Body& body = ptr( w, w->bodies )[bodyId];
 	const Island& island = ptr( w, w->islands )[body.islandId];
 	if ( body.sleepTime < kTimeToSleep )
 	{
@@ -2223,12 +2379,28 @@ template <class Team> F2D_HDF inline void overlapSensors( World* w, Team& t )
 	t.sync();
 }
 
-template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
+// `part`: kFinalizeAll, or one third of a callback-mediated step. The continuous pass asks the host's filter about every
+// candidate shape and its pre-solve callback about every hit (solver.c:271-282, 366-379), so there the HOST runs solveContinuous for the
+// fast bodies - after kFinalizeBodies for ordinary bodies (their boxes feed the move array built by kFinalizeMoves), after
+// kFinalizeMoves for bullets - and kFinalizeEnd resumes behind the bullets' continuous pass.
+enum : int
+{
+	kFinalizeAll = 0,
+	kFinalizeBodies = 1,
+	kFinalizeMoves = 2,
+	kFinalizeEnd = 3
+};
+template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t, int part = kFinalizeAll )
 {
 	const int awakeBodyCount = w->step.awakeBodyCount;
 	const bool solved = awakeBodyCount > 0 && w->step.dt > 0.0f && ( w->error & kErrCapacity ) == 0;
-	if ( solved )
+	const bool doBodies = part == kFinalizeAll || part == kFinalizeBodies;
+	const bool doMoves = part == kFinalizeAll || part == kFinalizeMoves;
+	const bool doEnd = part == kFinalizeAll || part == kFinalizeEnd;
+	if ( solved && doBodies )
 	{
+		if ( t.rank() == 0 )
+			w->step.fastDeferredCount = 0;
 		// clear bit sets (solver.c:1724-1733)
 		int bodyWords = ( awakeBodyCount + 63 ) >> 6;
 		int islandWords = ( w->awakeIslands.count + 63 ) >> 6;
@@ -2260,7 +2432,10 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		}
 		t.sync();
 		F2D_MARK( w, t, pfFinalizeBodies );
-
+	}
+	if ( solved && doMoves )
+	{
+		uint64_t* eb = ptr( w, w->enlargedBits );
 		if ( t.rank() == 0 && w->hitEventCapable > 0 )
 			reportHitEvents( w );
 		F2D_MARK( w, t, pfHitEvents );
@@ -2356,14 +2531,24 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 			w->moveArray.count = moveTotal;
 		t.sync();
 		F2D_MARK( w, t, pfEnlarge );
-
+	}
+	if ( solved && doEnd )
+	{
+		const int32_t* awakeBodies = ptr( w, w->awakeBodies );
+		const Body* bodies = ptr( w, w->bodies );
+		BodySim* sims = ptr( w, w->sims );
+		Shape* shapes = ptr( w, w->shapes );
+		uint64_t* ib = ptr( w, w->islandBits );
 		// bullets: continuous against everything, then enlarge (solver.c:1915-1988)
 		int bulletCount = w->step.bulletCount;
 		if ( bulletCount > 0 )
 		{
 			const int32_t* bullets = ptr( w, w->bullets );
-			for ( int i = t.rank(); i < bulletCount; i += t.size() )
-				solveContinuous( w, bullets[i] );
+			if ( part == kFinalizeAll ) // kFinalizeEnd: the host has run the continuous pass of the bullets
+			{
+				for ( int i = t.rank(); i < bulletCount; i += t.size() )
+					solveContinuous( w, bullets[i] );
+			}
 			t.sync();
 			for ( int i = t.rank(); i < bulletCount; i += t.size() )
 			{
@@ -2411,6 +2596,8 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t )
 		F2D_MARK( w, t, pfSleep );
 	}
 
+	if ( doEnd == false )
+		return;
 	// world.c:788-793
 	overlapSensors( w, t );
 
@@ -2441,6 +2628,25 @@ template <class Team> F2D_HDF inline void stepZeroDt( World* w, Team& t )
 	t.sync();
 }
 
+// Launch granularity. kPhaseAll is the product path (one launch per step). The four coarse phases exist for per-phase
+// device timing; the split ones for the callback-mediated step, where the host answers b2CustomFilterFcn between
+// kPhasePairsQuery and kPhasePairsCreate and b2PreSolveFcn between kPhaseCollideNarrow and kPhaseCollideFinish.
+enum Phase
+{
+	kPhaseAll = 0,
+	kPhaseBeginPairs = 1,
+	kPhaseCollide = 2,
+	kPhaseSolve = 3,
+	kPhaseFinalize = 4,
+	kPhasePairsQuery = 5, // stepBegin + pair queries
+	kPhasePairsCreate = 6,
+	kPhaseCollideNarrow = 7,
+	kPhaseCollideFinish = 8,
+	kPhaseFinalizeBodies = 9, // see stepFinalize
+	kPhaseFinalizeMoves = 10,
+	kPhaseFinalizeEnd = 11
+};
+
 // Whole step on one team (used by the CTA-per-world kernel and the host emulation)
 template <class Team> F2D_HDF inline void stepWorld( World* w, Team& t, float dt, int subStepCount )
 {
@@ -2454,6 +2660,60 @@ template <class Team> F2D_HDF inline void stepWorld( World* w, Team& t, float dt
 	stepCollide( w, t );
 	stepSolve( w, t );
 	stepFinalize( w, t );
+}
+
+// One launch-sized piece of the step (see Phase)
+template <class Team> F2D_HDF inline void stepWorldPhase( World* w, Team& t, int phase, float dt, int subStepCount )
+{
+	if ( phase == kPhaseAll )
+	{
+		stepWorld( w, t, dt, subStepCount );
+		return;
+	}
+	if ( dt == 0.0f )
+	{
+		if ( phase == kPhaseBeginPairs || phase == kPhasePairsQuery )
+			stepZeroDt( w, t );
+		return;
+	}
+	switch ( phase )
+	{
+		case kPhaseBeginPairs:
+			stepBegin( w, t, dt, subStepCount );
+			stepPairs( w, t );
+			break;
+		case kPhasePairsQuery:
+			stepBegin( w, t, dt, subStepCount );
+			stepPairs( w, t, kPairsQuery );
+			break;
+		case kPhasePairsCreate:
+			stepPairs( w, t, kPairsCreate );
+			break;
+		case kPhaseCollide:
+			stepCollide( w, t );
+			break;
+		case kPhaseCollideNarrow:
+			stepCollide( w, t, kCollideNarrow );
+			break;
+		case kPhaseCollideFinish:
+			stepCollide( w, t, kCollideFinish );
+			break;
+		case kPhaseSolve:
+			stepSolve( w, t );
+			break;
+		case kPhaseFinalize:
+			stepFinalize( w, t );
+			break;
+		case kPhaseFinalizeBodies:
+			stepFinalize( w, t, kFinalizeBodies );
+			break;
+		case kPhaseFinalizeMoves:
+			stepFinalize( w, t, kFinalizeMoves );
+			break;
+		case kPhaseFinalizeEnd:
+			stepFinalize( w, t, kFinalizeEnd );
+			break;
+	}
 }
 
 } // namespace f2d

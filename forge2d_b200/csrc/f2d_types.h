@@ -235,7 +235,10 @@ enum : uint32_t // contact.h:74-93
 	kSimStartedTouching = 0x00040000,
 	kSimStoppedTouching = 0x00080000,
 	kSimEnableHitEvent = 0x00100000,
-	kSimEnablePreSolve = 0x00200000
+	kSimEnablePreSolve = 0x00200000,
+	// ours, only ever set between the two halves of a callback-mediated narrowphase (f2d_step.h deferPreSolve): the
+	// manifold holds the raw result of the manifold function and the host's pre-solve verdict is pending
+	kSimPendingPreSolve = 0x00400000
 };
 struct Edge
 {
@@ -469,6 +472,10 @@ struct StepCtx
 	int32_t islandPath; // 1: constraints are solved island by island (one warp each), 0: colour by colour
 	int32_t maxIslandContacts, maxIslandBodies;
 	int32_t islandSolveCount; // awake islands when the island-parallel partition was built (a split may add islands later)
+	int32_t orderedPairCount; // callback-mediated step: candidate pairs in creation order, waiting for the host's custom filter
+	int32_t preSolveCount;	  // callback-mediated step: touching contacts waiting for the host's pre-solve verdict
+	int32_t fastDeferredCount; // callback-mediated step: fast bodies whose continuous pass waits for the host's custom filter
+	int32_t reserved;		   // keeps sizeof( World ) a multiple of 16
 	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
 };
 
@@ -546,6 +553,12 @@ enum ProfSlot : int
 	kProfSlots = 24
 };
 
+enum : uint8_t // World::hostCallbacks
+{
+	kHostCustomFilter = 1, // b2CustomFilterFcn registered (broad_phase.c:267-278)
+	kHostPreSolve = 2,	   // b2PreSolveFcn registered (contact.c:504-517)
+	kHostMixing = 4		   // friction / restitution mixing callbacks in the world def: not supported
+};
 enum : uint32_t
 {
 	kErrCapacity = 1,		 // a fixed-capacity array overflowed inside the step
@@ -570,7 +583,7 @@ struct World
 	int32_t splitIslandId, endEventArrayIndex;
 	uint16_t worldId, generation;
 	bool enableSleep, locked, enableWarmStarting, enableContinuous, enableSpeculative, inUse;
-	bool hasHostCallbacks;
+	uint8_t hostCallbacks; // kHostCustomFilter | kHostPreSolve (| kHostMixing: unsupported): the step runs callback-mediated
 	int32_t taskCount;
 	int32_t hitEventCapable;	 // shapes with enableHitEvents (hit-event scan is skipped when 0)
 	int32_t contactEventCapable; // shapes with enableContactEvents (sizes the begin/end event arrays)

@@ -1130,30 +1130,12 @@ struct OldImpulses
 	float normalImpulse[2], tangentImpulse[2];
 };
 
-// Narrowphase update of one contact: contact.c:472-633 (pre-solve callback path excluded: host callbacks are
-// rejected at registration on the device path). `old` was read together with the ids of the contact, so this
-// routine issues no load that depends on another one.
-F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags, OldImpulses old, const Shape& shapeA, Xf xfA,
-								   V2 centerOffsetA, const Shape& shapeB, Xf xfB, V2 centerOffsetB )
+// Second half of b2UpdateContact, from the point where the pre-solve verdict is known (contact.c:519-633): `m` is the
+// raw result of the manifold function, `touching` what the manifold (and the host's pre-solve callback, if any) decided.
+F2D_HDF inline bool finishContactUpdate( World* w, ContactSim& sim, uint32_t& simFlags, Manifold& m, OldImpulses old, bool touching,
+										 bool hitEvents, V2 centerOffsetA, V2 centerOffsetB )
 {
-	Manifold m = computeManifold( w, shapeA, xfA, shapeB, xfB, &sim.cache );
-
-	sim.friction = sqrtf( shapeA.friction * shapeB.friction );
-	sim.restitution = maxf( shapeA.restitution, shapeB.restitution );
-	if ( shapeA.rollingResistance > 0.0f || shapeB.rollingResistance > 0.0f )
-	{
-		float maxRadius = maxf( shapeRadius( shapeA ), shapeRadius( shapeB ) );
-		sim.rollingResistance = maxf( shapeA.rollingResistance, shapeB.rollingResistance ) * maxRadius;
-	}
-	else
-	{
-		sim.rollingResistance = 0.0f;
-	}
-	sim.tangentSpeed = shapeA.tangentSpeed + shapeB.tangentSpeed;
-
 	int pointCount = m.pointCount;
-	bool touching = pointCount > 0;
-
 	if ( w->enableSpeculative == false && pointCount == 2 )
 	{
 		if ( m.points[0].separation > 1.5f * kLinearSlop )
@@ -1168,7 +1150,7 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags
 		pointCount = m.pointCount;
 	}
 
-	if ( touching && ( shapeA.enableHitEvents || shapeB.enableHitEvents ) )
+	if ( touching && hitEvents )
 		simFlags |= kSimEnableHitEvent;
 	else
 		simFlags &= ~kSimEnableHitEvent;
@@ -1211,6 +1193,74 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags
 	else
 		simFlags &= ~kSimTouching;
 	return touching; // the caller stores simFlags once, after adding the transition bits
+}
+
+// Callback-mediated narrowphase: what finishContactUpdate needs of the OLD manifold is parked in fields of the raw NEW
+// manifold that are still zero at this point (impulses, total impulse, normal velocity, rolling impulse), so a contact
+// waiting for the host's pre-solve verdict needs no storage of its own. unparkOldImpulses restores the zeros.
+F2D_HDF inline void parkOldImpulses( Manifold& m, const OldImpulses& old )
+{
+	for ( int j = 0; j < 2; ++j )
+	{
+		m.points[j].normalImpulse = old.normalImpulse[j];
+		m.points[j].tangentImpulse = old.tangentImpulse[j];
+		m.points[j].normalVelocity = floatFromBits( old.id[j] );
+	}
+	m.points[0].totalNormalImpulse = floatFromBits( (uint32_t)old.pointCount );
+	m.rollingImpulse = old.rollingImpulse;
+}
+F2D_HDF inline OldImpulses unparkOldImpulses( Manifold& m )
+{
+	OldImpulses old;
+	old.pointCount = (int32_t)floatBits( m.points[0].totalNormalImpulse );
+	old.rollingImpulse = m.rollingImpulse;
+	for ( int j = 0; j < 2; ++j )
+	{
+		old.id[j] = (uint16_t)floatBits( m.points[j].normalVelocity );
+		old.normalImpulse[j] = m.points[j].normalImpulse;
+		old.tangentImpulse[j] = m.points[j].tangentImpulse;
+		m.points[j].normalImpulse = 0.0f;
+		m.points[j].tangentImpulse = 0.0f;
+		m.points[j].totalNormalImpulse = 0.0f;
+		m.points[j].normalVelocity = 0.0f;
+	}
+	m.rollingImpulse = 0.0f;
+	return old;
+}
+
+// Narrowphase update of one contact: contact.c:472-633. `old` was read together with the ids of the contact, so this
+// routine issues no load that depends on another one. With a pre-solve callback registered (b2PreSolveFcn runs on the
+// host), a touching contact with pre-solve events stops after the manifold function: kSimPendingPreSolve is set, the
+// raw manifold is stored with the old impulses parked in it, and finishDeferredContact completes it once the host has
+// answered (contact.c:504-517).
+F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags, OldImpulses old, const Shape& shapeA, Xf xfA,
+								   V2 centerOffsetA, const Shape& shapeB, Xf xfB, V2 centerOffsetB )
+{
+	Manifold m = computeManifold( w, shapeA, xfA, shapeB, xfB, &sim.cache );
+
+	sim.friction = sqrtf( shapeA.friction * shapeB.friction );
+	sim.restitution = maxf( shapeA.restitution, shapeB.restitution );
+	if ( shapeA.rollingResistance > 0.0f || shapeB.rollingResistance > 0.0f )
+	{
+		float maxRadius = maxf( shapeRadius( shapeA ), shapeRadius( shapeB ) );
+		sim.rollingResistance = maxf( shapeA.rollingResistance, shapeB.rollingResistance ) * maxRadius;
+	}
+	else
+	{
+		sim.rollingResistance = 0.0f;
+	}
+	sim.tangentSpeed = shapeA.tangentSpeed + shapeB.tangentSpeed;
+
+	bool touching = m.pointCount > 0;
+	if ( touching && ( w->hostCallbacks & kHostPreSolve ) != 0 && ( simFlags & kSimEnablePreSolve ) != 0 )
+	{
+		parkOldImpulses( m, old );
+		sim.manifold = m;
+		simFlags |= kSimPendingPreSolve;
+		return false; // not decided yet: the caller must not derive a touching transition
+	}
+	return finishContactUpdate( w, sim, simFlags, m, old, touching, shapeA.enableHitEvents || shapeB.enableHitEvents, centerOffsetA,
+								centerOffsetB );
 }
 
 // ------------------------------------------------------------------------------------------------ sleeping sets

@@ -21,6 +21,14 @@ static void backendStep( HostWorld& hw, float dt, int subSteps, bool )
 	stepWorld( hw.img, team, dt, subSteps );
 	hw.state = kInSync;
 }
+static void backendPhaseBegin( HostWorld& ) {}
+static void backendPhase( HostWorld& hw, float dt, int subSteps, int phase )
+{
+	SerialTeam team;
+	stepWorldPhase( hw.img, team, phase, dt, subSteps );
+}
+static void backendUploadRange( HostWorld&, uint64_t, uint64_t ) {}
+static void backendPhaseEnd( HostWorld& hw ) { hw.state = kInSync; }
 static void backendSynchronize( HostWorld& ) {}
 static void backendDownload( HostWorld& ) {}
 static void backendDownloadRange( HostWorld&, uint64_t, uint64_t ) {}

@@ -49,13 +49,80 @@ def test_all_joint_types_bit_identical_emu(ref, emu):
     _joint_zoo(ref, emu, 300, 5)
 
 
-def test_in_step_host_callbacks_fail_loudly(emu):
+# ---- host callbacks inside the step -------------------------------------------------------------------------
+def _callback_session(ref, lib, frames=150, mode=None):
+    """b2CustomFilterFcn and b2PreSolveFcn (world.c:1710-1740) registered on a falling-boxes world: the custom filter
+    rejects pairs by shape-id parity, the pre-solve callback makes a platform one-way (contacts whose normal points
+    down are disabled) and rejects by manifold content. Same verdicts given => every record bit-identical, and the
+    callbacks see the same (shape ids, manifold) sequence as in the single-worker reference."""
     import ctypes as C
-    s = scenes.bench2d(emu, rows=2)
-    emu.f2dClearLastError()
-    emu.b2World_SetPreSolveCallback(s.world, C.c_void_p(1), None)
-    assert b"not supported" in emu.f2dGetLastError()
-    s.destroy()
+    from forge2d_b200 import _abi as A
+    FilterFcn = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.c_void_p)
+    PreSolveFcn = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.POINTER(A.Manifold), C.c_void_p)
+    lib.f2dClearLastError()
+    logs, keep, worlds = [], [], []
+    for L in (ref, lib):
+        s = scenes.bench2d(L, rows=9, ground_half_width=12.0)
+        sd = L.b2DefaultShapeDef()
+        sd.enablePreSolveEvents = True
+        bd = L.b2DefaultBodyDef()
+        bd.position = A.Vec2(0.0, -24.0)
+        platform = L.b2CreateBody(s.world, C.byref(bd))
+        box = L.b2MakeBox(6.0, 0.25)
+        L.b2CreatePolygonShape(platform, C.byref(sd), C.byref(box))
+        bd.type = 2
+        for k in range(10):     # boxes above and below the platform; those below are thrown upwards through it
+            bd.position = A.Vec2(-4.5 + k, -21.0 if k % 2 else -27.5)
+            bd.linearVelocity = A.Vec2(0.0, 0.0 if k % 2 else 14.0)
+            b = L.b2CreateBody(s.world, C.byref(bd))
+            small = L.b2MakeBox(0.3, 0.3)
+            L.b2CreatePolygonShape(b, C.byref(sd), C.byref(small))
+        log = []
+
+        def custom_filter(a, b, ctx, log=log):
+            log.append(("filter", a.index1, a.generation, b.index1, b.generation))
+            return (a.index1 + b.index1) % 5 != 0
+
+        def pre_solve(a, b, manifold, ctx, log=log):
+            m = manifold.contents
+            log.append(("presolve", a.index1, b.index1, m.pointCount, m.normal.x, m.normal.y,
+                        tuple((m.points[i].id, m.points[i].separation, m.points[i].anchorA.x, m.points[i].normalImpulse)
+                              for i in range(m.pointCount))))
+            return m.normal.y > -0.5 and (a.index1 * 7 + b.index1) % 11 != 0
+
+        f1, f2 = FilterFcn(custom_filter), PreSolveFcn(pre_solve)
+        keep += [f1, f2]
+        L.b2World_SetCustomFilterCallback(s.world, C.cast(f1, C.c_void_p), None)
+        L.b2World_SetPreSolveCallback(s.world, C.cast(f2, C.c_void_p), None)
+        logs.append(log)
+        worlds.append(s)
+    a, b = worlds
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(b.world, mode)
+    for f in range(frames):
+        if f == 100:   # callbacks can be removed again: back to the single-launch step
+            for s, L in ((a, ref), (b, lib)):
+                L.b2World_SetPreSolveCallback(s.world, None, None)
+        a.step()
+        b.step()
+        d = H.diff(H.snapshot(ref, a.world), H.snapshot(lib, b.world))
+        assert d == [], "frame %d: %s" % (f, d[:6])
+        assert logs[0] == logs[1], "frame %d: callback sequences differ" % f
+    kinds = [e[0] for e in logs[0]]
+    assert kinds.count("filter") > 100 and kinds.count("presolve") > 100
+    assert lib.f2dGetLastError() == b""
+    a.destroy()
+    b.destroy()
+
+
+def test_in_step_host_callbacks_match_reference_emu(ref, emu):
+    _callback_session(ref, emu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_in_step_host_callbacks_match_reference_gpu(ref, gpu, mode):
+    _callback_session(ref, gpu, mode=mode)
 
 
 @pytest.mark.gpu
@@ -79,7 +146,7 @@ def _query_session(lib, frames=90):
     sd = lib.b2DefaultShapeDef()
     bd = lib.b2DefaultBodyDef()
     bd.type = 2
-    for k, (x, y) in enumerate(((-9.0, -20.0), (-8.0, -12.0), (9.0, -18.0))):
+    for k, (x, y) in enumerate(((-9.0, -20.0), (-8.0, -12.0), (9.0, -18.0), (5.0, -15.0))):
         bd.position = A.Vec2(x, y)
         b = lib.b2CreateBody(world, C.byref(bd))
         if k == 0:
@@ -88,6 +155,10 @@ def _query_session(lib, frames=90):
         elif k == 1:
             c = A.Capsule(A.Vec2(-0.5, 0.0), A.Vec2(0.5, 0.2), 0.3)
             lib.b2CreateCapsuleShape(b, C.byref(sd), C.byref(c))
+        elif k == 3:
+            # rounded polygon: ray casts go through b2ShapeCast (geometry.c:877-887)
+            rounded = lib.b2MakeOffsetRoundedBox(0.5, 0.3, A.Vec2(0.1, 0.0), A.Rot(0.8, 0.6), 0.25)
+            lib.b2CreatePolygonShape(b, C.byref(sd), C.byref(rounded))
         else:
             sd2 = lib.b2DefaultShapeDef()
             sd2.filter.categoryBits = 2
@@ -100,7 +171,8 @@ def _query_session(lib, frames=90):
         return int(np.float32(x).view(np.uint32))
 
     rays = [((-20.0, -29.5), (40.0, 0.0)), ((-6.0, 5.0), (3.0, -40.0)), ((0.0, -10.0), (0.0, -25.0)),
-            ((-12.0, -25.0), (30.0, 9.0)), ((2.0, -28.0), (0.0, 0.0)), ((-9.0, -20.0), (1.0, 1.0))]
+            ((-12.0, -25.0), (30.0, 9.0)), ((2.0, -28.0), (0.0, 0.0)), ((-9.0, -20.0), (1.0, 1.0)),
+            ((5.15, -10.0), (0.0, -22.0)), ((-2.0, -14.0), (14.0, -6.0)), ((5.0, -15.3), (1.0, 0.0)), ((8.0, -31.0), (-4.5, 17.0))]
     for f in range(frames):
         s.step()
         if f % 15 != 14:
