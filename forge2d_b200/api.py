@@ -91,6 +91,7 @@ class BodyDef:
     isBullet: bool = False
     isEnabled: bool = True
     allowFastRotation: bool = False
+    name: Optional[str] = None
     userData: Any = None
 
 
@@ -108,6 +109,7 @@ class ShapeDef:
     enableSensorEvents: bool = False
     enableContactEvents: bool = True
     enableHitEvents: bool = False
+    enablePreSolveEvents: bool = False
     userData: Any = None
 
 
@@ -390,6 +392,7 @@ class Body:
         sd.enableSensorEvents = d.enableSensorEvents
         sd.enableContactEvents = d.enableContactEvents
         sd.enableHitEvents = d.enableHitEvents
+        sd.enablePreSolveEvents = d.enablePreSolveEvents
         if isinstance(geometry, Circle):
             g = A.Circle(_v(geometry.center), geometry.radius)
             raw = lib.b2CreateCircleShape(self._id, C.byref(sd), C.byref(g))
@@ -515,6 +518,8 @@ class World:
         bd.isAwake = d.isAwake
         bd.fixedRotation = d.fixedRotation
         bd.isBullet = d.isBullet
+        if d.name:
+            bd.name = d.name.encode()
         bd.isEnabled = d.isEnabled
         bd.allowFastRotation = d.allowFastRotation
         body = Body(self, lib.b2CreateBody(self.id, C.byref(bd)))
@@ -557,6 +562,73 @@ class World:
                                        Vector2(e.point.x, e.point.y), Vector2(e.normal.x, e.normal.y), e.approachSpeed))
         return ContactEvents(begin, end, hit)
 
+    # ---- callbacks inside the step (world.dart:616-650): run on the calling thread during step()
+    @property
+    def customFilterCallback(self):
+        return getattr(self, "_customFilter", None)
+
+    @customFilterCallback.setter
+    def customFilterCallback(self, callback):
+        """bool callback(Shape shapeA, Shape shapeB), consulted for pairs that pass the regular filtering; None clears."""
+        lib = _lib()
+        self._customFilter = callback
+        if callback is None:
+            self._customFilterNative = None
+            lib.b2World_SetCustomFilterCallback(self.id, None, None)
+            return
+        fcn = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.c_void_p)(
+            lambda a, b, ctx: bool(callback(Shape.internal(self, _copy(a)), Shape.internal(self, _copy(b)))))
+        self._customFilterNative = fcn  # keeps the trampoline alive (NativeCallable.isolateLocal in the Dart layer)
+        lib.b2World_SetCustomFilterCallback(self.id, C.cast(fcn, C.c_void_p), None)
+
+    @property
+    def preSolveCallback(self):
+        return getattr(self, "_preSolve", None)
+
+    @preSolveCallback.setter
+    def preSolveCallback(self, callback):
+        """bool callback(Shape shapeA, Shape shapeB, Vector2 normal); returning False disables the contact for the step.
+        Only shapes created with enablePreSolveEvents participate. None clears."""
+        lib = _lib()
+        self._preSolve = callback
+        if callback is None:
+            self._preSolveNative = None
+            lib.b2World_SetPreSolveCallback(self.id, None, None)
+            return
+        fcn = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.POINTER(A.Manifold), C.c_void_p)(
+            lambda a, b, m, ctx: bool(callback(Shape.internal(self, _copy(a)), Shape.internal(self, _copy(b)),
+                                               Vector2(m.contents.normal.x, m.contents.normal.y))))
+        self._preSolveNative = fcn
+        lib.b2World_SetPreSolveCallback(self.id, C.cast(fcn, C.c_void_p), None)
+
+    def draw(self, debugDraw: "DebugDraw"):
+        """world.dart:664-760 -> b2World_Draw: emits the world's debug geometry into `debugDraw`."""
+        lib = _lib()
+        v = lambda p: Vector2(p.x, p.y)
+        t = lambda x: Transform(Vector2(x.p.x, x.p.y), Rot(x.q.c, x.q.s))
+        native = lib.b2DefaultDebugDraw()
+        keep = [
+            A.DrawPolygonFcn(lambda vs, n, color, ctx: debugDraw.drawPolygon([v(vs[i]) for i in range(n)], color)),
+            A.DrawSolidPolygonFcn(lambda xf, vs, n, r, color, ctx: debugDraw.drawSolidPolygon(t(xf), [v(vs[i]) for i in range(n)], r, color)),
+            A.DrawCircleFcn(lambda c, r, color, ctx: debugDraw.drawCircle(v(c), r, color)),
+            A.DrawSolidCircleFcn(lambda xf, r, color, ctx: debugDraw.drawSolidCircle(t(xf), r, color)),
+            A.DrawSolidCapsuleFcn(lambda p1, p2, r, color, ctx: debugDraw.drawSolidCapsule(v(p1), v(p2), r, color)),
+            A.DrawSegmentFcn(lambda p1, p2, color, ctx: debugDraw.drawSegment(v(p1), v(p2), color)),
+            A.DrawTransformFcn(lambda xf, ctx: debugDraw.drawTransform(t(xf))),
+            A.DrawPointFcn(lambda p, size, color, ctx: debugDraw.drawPoint(v(p), size, color)),
+            A.DrawStringFcn(lambda p, text, color, ctx: debugDraw.drawString(v(p), bytes(text).decode(), color)),
+        ]
+        (native.DrawPolygonFcn, native.DrawSolidPolygonFcn, native.DrawCircleFcn, native.DrawSolidCircleFcn,
+         native.DrawSolidCapsuleFcn, native.DrawSegmentFcn, native.DrawTransformFcn, native.DrawPointFcn, native.DrawStringFcn) = keep
+        for name in A.DEBUG_DRAW_OPTIONS[1:]:
+            setattr(native, name, bool(getattr(debugDraw, name)))
+        bounds = debugDraw.drawingBounds
+        native.useDrawingBounds = bounds is not None
+        if bounds is not None:
+            (lx, ly), (ux, uy) = bounds
+            native.drawingBounds = A.AABB(A.Vec2(lx, ly), A.Vec2(ux, uy))
+        lib.b2World_Draw(self.id, C.byref(native))
+
     @property
     def sensorEvents(self) -> SensorEvents:
         ev = _lib().b2World_GetSensorEvents(self.id)
@@ -582,6 +654,35 @@ def _copy(raw_id):
     return type(raw_id)(raw_id.index1, raw_id.world0, raw_id.generation)
 
 
+class DebugDraw:
+    """debug_draw.dart: receives the world's debug geometry when passed to World.draw. Override the draw methods for
+    the primitives you care about and flip the options; `drawingBounds` = ((lx, ly), (ux, uy)) restricts the drawing."""
+    drawingBounds = None
+    drawShapes = True
+    drawJoints = True
+    drawJointExtras = False
+    drawBounds = False
+    drawMass = False
+    drawBodyNames = False
+    drawContacts = False
+    drawGraphColors = False
+    drawContactNormals = False
+    drawContactImpulses = False
+    drawContactFeatures = False
+    drawFrictionImpulses = False
+    drawIslands = False
+
+    def drawPolygon(self, vertices, color): pass
+    def drawSolidPolygon(self, transform, vertices, radius, color): pass
+    def drawCircle(self, center, radius, color): pass
+    def drawSolidCircle(self, transform, radius, color): pass
+    def drawSolidCapsule(self, p1, p2, radius, color): pass
+    def drawSegment(self, p1, p2, color): pass
+    def drawTransform(self, transform): pass
+    def drawPoint(self, p, size, color): pass
+    def drawString(self, p, text, color): pass
+
+
 class WorldBatch:
     """Extension (not in the reference): N device-resident replicas of a template world stepped by one kernel launch per
     step, one thread block per world (f2dBatch_* in include/forge2d_b200.h)."""
@@ -602,6 +703,10 @@ class WorldBatch:
         import numpy as np
         ev, cnt = C.POINTER(A.BodyMoveEvent)(), C.POINTER(C.c_int)()
         self._lib.f2dBatch_ReadBodyEvents(self._batch, maxBodiesPerWorld, C.byref(ev), C.byref(cnt))
+        return self._view(ev, cnt, maxBodiesPerWorld)
+
+    def _view(self, ev, cnt, maxBodiesPerWorld):
+        import numpy as np
         dtype = np.dtype([("p", "<f4", 2), ("q", "<f4", 2), ("bodyIndex1", "<i4"), ("world0", "<u2"), ("generation", "<u2"),
                           ("userData", "<u8"), ("fellAsleep", "u1"), ("pad", "u1", 7)])
         assert dtype.itemsize == C.sizeof(A.BodyMoveEvent)
@@ -609,6 +714,13 @@ class WorldBatch:
         records = np.ctypeslib.as_array(C.cast(ev, C.POINTER(C.c_uint8)), shape=(n * dtype.itemsize,)).view(dtype)
         counts = np.ctypeslib.as_array(cnt, shape=(self.count,))
         return records.reshape(self.count, maxBodiesPerWorld), counts
+
+    def stepAndReadBodyTransforms(self, timeStep: float, maxBodiesPerWorld: int, subStepCount: int = 4):
+        """One step of every world and that step's body transforms on the host in one call: the worlds are stepped in
+        slices and each slice's read-back overlaps the stepping of the next (f2dBatch_StepAndReadBodyEvents)."""
+        ev, cnt = C.POINTER(A.BodyMoveEvent)(), C.POINTER(C.c_int)()
+        self._lib.f2dBatch_StepAndReadBodyEvents(self._batch, timeStep, subStepCount, maxBodiesPerWorld, C.byref(ev), C.byref(cnt))
+        return self._view(ev, cnt, maxBodiesPerWorld)
 
     @property
     def errorFlags(self):

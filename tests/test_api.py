@@ -156,3 +156,114 @@ def test_stepping_an_empty_world(world):
     for _ in range(5):
         world.step(1 / 60)
     assert world.bodyMoveEvents == []
+
+
+# ---- events_test.dart:261-305 "simulation callbacks"
+def test_the_custom_filter_can_disable_a_collision(world):
+    ground(world)
+    ball = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 3)))
+    ball.createShape(Circle(radius=0.5), ShapeDef(userData="ghost"))
+    world.customFilterCallback = lambda a, b: a.userData != "ghost" and b.userData != "ghost"
+    for _ in range(120):
+        world.step(1 / 60)
+    assert ball.position.y < -1     # the ball ignored the ground and kept falling
+    world.customFilterCallback = None
+
+
+def test_the_pre_solve_callback_can_disable_a_contact(world):
+    ground(world)
+    ball = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 2)))
+    ball.createShape(Circle(radius=0.5), ShapeDef(enablePreSolveEvents=True))
+    called = []
+
+    def pre_solve(shape_a, shape_b, normal):
+        called.append((shape_a.key, shape_b.key, normal))
+        return False
+
+    world.preSolveCallback = pre_solve
+    for _ in range(120):
+        world.step(1 / 60)
+    assert called
+    assert ball.position.y < -1     # with every contact disabled the ball falls through the ground
+    world.preSolveCallback = None
+
+
+def test_removing_the_callbacks_restores_the_collision(world):
+    ground(world)
+    ball = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(0, 3)))
+    ball.createShape(Circle(radius=0.5), ShapeDef(enablePreSolveEvents=True))
+    world.customFilterCallback = lambda a, b: True
+    world.preSolveCallback = lambda a, b, normal: True
+    for _ in range(30):
+        world.step(1 / 60)
+    world.customFilterCallback = None
+    world.preSolveCallback = None
+    for _ in range(150):
+        world.step(1 / 60)
+    assert abs(ball.position.y - 0.5) < 0.05    # resting on the ground box (top at y = 0)
+
+
+# ---- debug_draw_test.dart
+class RecordingDebugDraw(api.DebugDraw):
+    def __init__(self):
+        self.solidPolygons, self.solidCircles, self.solidCapsules, self.segments, self.points, self.strings = [], [], [], [], [], []
+
+    def drawSolidPolygon(self, transform, vertices, radius, color):
+        self.solidPolygons.append(vertices)
+
+    def drawSolidCircle(self, transform, radius, color):
+        self.solidCircles.append(transform)
+
+    def drawSolidCapsule(self, p1, p2, radius, color):
+        self.solidCapsules.append((p1, p2, radius))
+
+    def drawSegment(self, p1, p2, color):
+        self.segments.append((p1, p2))
+
+    def drawPoint(self, p, size, color):
+        self.points.append(p)
+
+    def drawString(self, p, text, color):
+        self.strings.append(text)
+
+
+def test_shapes_are_drawn_with_the_matching_primitives(world):
+    body = world.createBody(BodyDef(position=Vector2(1, 2)))
+    body.createShape(Polygon.square(0.5))
+    body.createShape(Circle(radius=0.5))
+    body.createShape(api.Capsule(center1=Vector2(0, 0), center2=Vector2(0, 1), radius=0.25))
+    draw = RecordingDebugDraw()
+    world.draw(draw)
+    assert len(draw.solidPolygons) == 1 and len(draw.solidPolygons[0]) == 4
+    assert len(draw.solidCircles) == 1 and abs(draw.solidCircles[0].p.x - 1) < 1e-5
+    assert len(draw.solidCapsules) == 1 and abs(draw.solidCapsules[0][2] - 0.25) < 1e-6
+
+
+def test_joints_are_drawn_when_enabled(world):
+    anchor = world.createBody(BodyDef(position=Vector2(0, 5)))
+    swinging = world.createBody(BodyDef(type=BodyType.dynamic, position=Vector2(2, 5)))
+    swinging.createShape(Polygon.square(0.25))
+    world.createRevoluteJoint(api.RevoluteJointDef(bodyA=anchor, bodyB=swinging))
+    draw = RecordingDebugDraw()
+    world.draw(draw)
+    assert draw.segments
+    draw.segments.clear()
+    draw.drawJoints = False
+    world.draw(draw)
+    assert draw.segments == []
+
+
+def test_body_names_are_drawn_when_enabled(world):
+    world.createBody(BodyDef(name="labeled")).createShape(Circle(radius=1))
+    draw = RecordingDebugDraw()
+    draw.drawBodyNames = True
+    world.draw(draw)
+    assert "labeled" in draw.strings
+
+
+def test_drawing_bounds_cull_far_away_shapes(world):
+    world.createBody(BodyDef(position=Vector2(100, 100))).createShape(Polygon.square(0.5))
+    draw = RecordingDebugDraw()
+    draw.drawingBounds = ((-10, -10), (10, 10))
+    world.draw(draw)
+    assert draw.solidPolygons == []
