@@ -251,6 +251,10 @@ def run_b200_arm(args, rank, world_size, local_rank):
         raise RuntimeError("bench: CUDA device %d not usable - forge2d_b200 has no CPU fallback" % local_rank)
     dist = None
     if world_size > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (torchrun's default environment on some boxes):
+        # keep stdout to the one JSON line the driver parses
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
