@@ -434,8 +434,8 @@ static void reportSleepingJointTarget( World* w, bool ok )
 {
 	if ( ok )
 		return;
-	reportError( "forge2d_b200: a joint would have to move into a sleeping solver set (not supported yet)" );
-	setError( w, kErrUnsupported, __LINE__ );
+	reportError( "forge2d_b200: the sleep pool cannot hold a sleeping solver set that has to grow for a joint" );
+	setError( w, kErrSleepPool, __LINE__ );
 }
 void b2Body_SetType( b2BodyId bodyId, b2BodyType type ) // body.c:1036-1284
 {
@@ -1396,13 +1396,7 @@ static b2TreeStats castRayCommon( HostWorld* hw, b2Vec2 origin, b2Vec2 translati
 			if ( shouldQueryCollide( shape.filter, filter.categoryBits, filter.maskBits ) == false )
 				return sub.maxFraction;
 			Xf transform = ptr( w, w->sims )[shape.bodyId].transform;
-			bool supported = true;
-			CastOutput out = rayCastShape( sub, shape, transform, &supported );
-			if ( supported == false )
-			{
-				reportError( "b2World_CastRay: ray casts against rounded polygons are not supported by forge2d_b200 yet" );
-				return sub.maxFraction;
-			}
+			CastOutput out = rayCastShape( sub, shape, transform );
 			if ( out.hit )
 			{
 				float fraction = fcn( publicShapeId( w, shapeId ), b2Vec2{ out.point.x, out.point.y }, b2Vec2{ out.normal.x, out.normal.y },

@@ -4,6 +4,7 @@
 // islands, colours) decides the order of everything the step does afterwards.
 #pragma once
 #include "f2d_world.h"
+#include <vector>
 
 namespace f2d
 {
@@ -349,6 +350,99 @@ struct RevoluteParams // mirrors b2RevoluteJointDef (types.h)
 	uint64_t userData;
 };
 
+
+// ---- joints inside sleeping solver sets (host API paths only) --------------------------------------------------
+// A sleeping set is four id lists carved from one block of World::sleepPool with fixed capacities, sized when the island
+// fell asleep. The reference's set arrays grow on demand (joint.c:252-287 adds a joint sim to a sleeping set,
+// solver_set.c:427-519 merges two sleeping sets); here the block is re-allocated with the room asked for, lists in order.
+inline bool growSolverSet( World* w, int setId, int extraBodies, int extraContacts, int extraJoints, int extraIslands )
+{
+	SolverSet& s = ptr( w, w->sets )[setId];
+	const int counts[4] = { s.bodyCount, s.contactCount, s.jointCount, s.islandCount };
+	int32_t* lists[4] = { setBodyList( w, s ), setContactList( w, s ), setJointList( w, s ), setIslandList( w, s ) };
+	std::vector<int32_t> saved[4];
+	for ( int k = 0; k < 4; ++k )
+		saved[k].assign( lists[k], lists[k] + counts[k] );
+	sleepPoolFree( w, s, setId );
+	if ( sleepPoolAlloc( w, s, setId, counts[0] + extraBodies, counts[1] + extraContacts, counts[2] + extraJoints, counts[3] + extraIslands ) ==
+		 false )
+		return false;
+	s.bodyCount = counts[0], s.contactCount = counts[1], s.jointCount = counts[2], s.islandCount = counts[3];
+	int32_t* fresh[4] = { setBodyList( w, s ), setContactList( w, s ), setJointList( w, s ), setIslandList( w, s ) };
+	for ( int k = 0; k < 4; ++k )
+		for ( int i = 0; i < counts[k]; ++i )
+			fresh[k][i] = saved[k][i];
+	return true;
+}
+
+// joint.c:257-268: the joint becomes the last entry of the sleeping set's joint list
+inline bool addJointToSleepingSet( World* w, int setId, Joint& joint )
+{
+	SolverSet& s = ptr( w, w->sets )[setId];
+	if ( s.jointCount >= s.jointCap && growSolverSet( w, setId, 0, 0, s.jointCount + 4, 0 ) == false )
+		return false;
+	joint.setIndex = setId;
+	joint.colorIndex = kNull;
+	joint.localIndex = s.jointCount;
+	setJointList( w, s )[s.jointCount++] = joint.jointId;
+	return true;
+}
+
+// solver_set.c:427-519 b2MergeSolverSets: the set with fewer bodies is appended to the other one and destroyed
+inline bool mergeSolverSets( World* w, int setId1, int setId2 )
+{
+	SolverSet* sets = ptr( w, w->sets );
+	if ( sets[setId1].bodyCount < sets[setId2].bodyCount )
+	{
+		int t = setId1;
+		setId1 = setId2;
+		setId2 = t;
+	}
+	const SolverSet from = sets[setId2];
+	if ( growSolverSet( w, setId1, from.bodyCount, from.contactCount, from.jointCount, from.islandCount ) == false )
+		return false;
+	SolverSet& s1 = sets[setId1];
+	SolverSet& s2 = sets[setId2];
+	Body* bodies = ptr( w, w->bodies );
+	Contact* contacts = ptr( w, w->contacts );
+	Joint* joints = ptr( w, w->joints );
+	Island* islands = ptr( w, w->islands );
+	const int32_t* src = setBodyList( w, s2 );
+	int32_t* dst = setBodyList( w, s1 );
+	for ( int i = 0; i < s2.bodyCount; ++i )
+	{
+		bodies[src[i]].setIndex = setId1;
+		bodies[src[i]].localIndex = s1.bodyCount;
+		dst[s1.bodyCount++] = src[i];
+	}
+	src = setContactList( w, s2 );
+	dst = setContactList( w, s1 );
+	for ( int i = 0; i < s2.contactCount; ++i )
+	{
+		contacts[src[i]].setIndex = setId1;
+		contacts[src[i]].localIndex = s1.contactCount;
+		dst[s1.contactCount++] = src[i];
+	}
+	src = setJointList( w, s2 );
+	dst = setJointList( w, s1 );
+	for ( int i = 0; i < s2.jointCount; ++i )
+	{
+		joints[src[i]].setIndex = setId1;
+		joints[src[i]].localIndex = s1.jointCount;
+		dst[s1.jointCount++] = src[i];
+	}
+	src = setIslandList( w, s2 );
+	dst = setIslandList( w, s1 );
+	for ( int i = 0; i < s2.islandCount; ++i )
+	{
+		islands[src[i]].setIndex = setId1;
+		islands[src[i]].localIndex = s1.islandCount;
+		dst[s1.islandCount++] = src[i];
+	}
+	destroySolverSet( w, setId2 );
+	return true;
+}
+
 // joint.c:142-300 (b2CreateJoint): id, edge lists, owning set, island link. Returns the joint id.
 inline int createJointBase( World* w, int bodyIdA, int bodyIdB, uint64_t userData, float drawSize, int type, bool collideConnected )
 {
@@ -428,11 +522,13 @@ inline int createJointBase( World* w, int bodyIdA, int bodyIdB, uint64_t userDat
 	}
 	else
 	{
-		// both bodies asleep (possibly in different sets): joints inside sleeping sets need pool growth on the host
-		setError( w, kErrUnsupported, __LINE__ );
-		joint.setIndex = kDisabledSet;
-		joint.localIndex = w->disabledJoints.count;
-		F2D_PUSH( w, w->disabledJoints, jointId );
+		// joint between sleeping and / or static bodies: it goes into the sleeping set, and two different sleeping sets
+		// become one (joint.c:250-287)
+		bool ok = addJointToSleepingSet( w, maxSetIndex, joint );
+		if ( ok && bodyA.setIndex != bodyB.setIndex && bodyA.setIndex >= kFirstSleepingSet && bodyB.setIndex >= kFirstSleepingSet )
+			ok = mergeSolverSets( w, bodyA.setIndex, bodyB.setIndex );
+		if ( ok == false )
+			setError( w, kErrSleepPool, __LINE__ );
 	}
 	sim.constraintHertz = 60.0f;		  // B2_JOINT_CONSTRAINT_HERTZ constants.h:50
 	sim.constraintDampingRatio = 2.0f; // B2_JOINT_CONSTRAINT_DAMPING_RATIO constants.h:53 (value 2 in v3.1.1: joint.c)

@@ -256,14 +256,17 @@ inline void transferBody( World* w, int targetSet, Body& body )
 }
 
 // solver_set.c b2TransferJoint: add to the target first (the graph picks a colour from the bodies' current types), then
-// remove from the source. Returns false when the target is a sleeping set (its joint list has no room to grow here).
+// remove from the source. Returns false only when the sleep pool cannot hold the grown target set.
 inline bool transferJoint( World* w, int targetSet, Joint& joint )
 {
 	Joint* joints = ptr( w, w->joints );
 	const int sourceSet = joint.setIndex, localIndex = joint.localIndex, colorIndex = joint.colorIndex;
 	if ( targetSet >= kFirstSleepingSet )
-		return false;
-	if ( targetSet == kAwakeSet )
+	{
+		if ( addJointToSleepingSet( w, targetSet, joint ) == false )
+			return false;
+	}
+	else if ( targetSet == kAwakeSet )
 	{
 		addJointToGraph( w, joint.jointId );
 		joint.setIndex = kAwakeSet;

@@ -219,9 +219,8 @@ inline CastOutput shapeCast( const ShapeProxy& proxyA, const ShapeProxy& proxyB,
 }
 
 // geometry.c:799-887: sharp polygons by slab clipping, rounded ones through b2ShapeCast of the ray origin as a point
-inline CastOutput rayCastPolygon( const RayInput& in, const Poly& shape, bool* supported )
+inline CastOutput rayCastPolygon( const RayInput& in, const Poly& shape )
 {
-	(void)supported;
 	CastOutput out = noHit();
 	if ( shape.radius != 0.0f )
 	{
@@ -275,7 +274,7 @@ inline CastOutput rayCastPolygon( const RayInput& in, const Poly& shape, bool* s
 }
 
 // shape.c:792-823 b2RayCastShape
-inline CastOutput rayCastShape( const RayInput& in, const Shape& shape, Xf transform, bool* supported )
+inline CastOutput rayCastShape( const RayInput& in, const Shape& shape, Xf transform )
 {
 	RayInput local = in;
 	local.origin = invRotate( transform.q, sub( in.origin, transform.p ) );
@@ -290,7 +289,7 @@ inline CastOutput rayCastShape( const RayInput& in, const Shape& shape, Xf trans
 			out = rayCastCircle( local, shape.circle.center, shape.circle.radius );
 			break;
 		case kPolygon:
-			out = rayCastPolygon( local, shape.polygon, supported );
+			out = rayCastPolygon( local, shape.polygon );
 			break;
 		case kSegment:
 			out = rayCastSegment( local, shape.segment, false );

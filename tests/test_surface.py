@@ -366,3 +366,104 @@ def test_debug_draw_matches_reference_gpu(ref, gpu, mode):
     _draw_session(ref, gpu, lambda L: scenes.joint_zoo(L, sets=2), 90, mode=mode)
     _draw_session(ref, gpu, scenes.chain_terrain, 60, mode=mode)
     _draw_session(ref, gpu, lambda L: scenes.many_pyramids(L, grid=3, base=4), 120, mode=mode)
+
+
+# ---- joints between sleeping bodies ----------------------------------------------------------------------------
+def _sleeping_joint_session(ref, lib, mode=None):
+    """Joints created between bodies that are asleep: the joint goes into the sleeping solver set (joint.c:250-287),
+    two different sleeping sets are merged (solver_set.c:427-519); joints follow a disabled / re-enabled / retyped
+    body into sleeping sets (body.c). Every record equal after each edit and while the chains wake up and swing."""
+    import ctypes as C
+    from forge2d_b200 import _abi as A
+    lib.f2dClearLastError()
+    def make(L):
+        s = scenes.bench2d(L, rows=3, ground_half_width=20.0)
+        world = s.world
+        sd = L.b2DefaultShapeDef()
+        box = L.b2MakeBox(0.4, 0.2)
+
+        def body(x, y, kind=2, awake=False):
+            bd = L.b2DefaultBodyDef()
+            bd.type = kind
+            bd.position = A.Vec2(x, y)
+            bd.isAwake = awake
+            b = L.b2CreateBody(world, C.byref(bd))
+            L.b2CreatePolygonShape(b, C.byref(sd), C.byref(box))
+            return b
+
+        sleepers = [body(-8.0 + 1.5 * k, -20.0 + 0.1 * k) for k in range(7)]
+        anchor = body(-9.5, -20.0, kind=0)
+        joints = []
+
+        def revolute(a, b, ax, ay):
+            d = L.b2DefaultRevoluteJointDef()
+            d.bodyIdA, d.bodyIdB = a, b
+            d.localAnchorA, d.localAnchorB = A.Vec2(ax, ay), A.Vec2(-ax, ay)
+            joints.append(L.b2CreateRevoluteJoint(world, C.byref(d)))
+
+        def distance(a, b, length):
+            d = L.b2DefaultDistanceJointDef()
+            d.bodyIdA, d.bodyIdB = a, b
+            d.length = length
+            joints.append(L.b2CreateDistanceJoint(world, C.byref(d)))
+
+        return dict(L=L, s=s, sleepers=sleepers, anchor=anchor, joints=joints, revolute=revolute, distance=distance)
+
+    sessions = [make(ref), make(lib)]
+
+    def compare(label):
+        a, b = sessions
+        d = H.diff(H.snapshot(ref, a["s"].world), H.snapshot(lib, b["s"].world))
+        assert d == [], "%s: %s" % (label, d[:6])
+
+    def both(fn):
+        for x in sessions:
+            fn(x)
+
+    a, b = sessions
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(b["s"].world, mode)
+    compare("created asleep")
+    both(lambda x: x["revolute"](x["sleepers"][0], x["sleepers"][1], 0.75, 0.0))    # two one-body sleeping sets merge
+    compare("joint between two sleeping sets")
+    both(lambda x: x["distance"](x["anchor"], x["sleepers"][0], 1.5))               # static + sleeping
+    compare("joint static-sleeping")
+    both(lambda x: x["revolute"](x["sleepers"][2], x["sleepers"][3], 0.75, 0.0))
+    both(lambda x: x["revolute"](x["sleepers"][3], x["sleepers"][4], 0.75, 0.0))    # grows the merged set again
+    both(lambda x: x["revolute"](x["sleepers"][1], x["sleepers"][2], 0.75, 0.0))    # merges the two chains (2 + 3 bodies)
+    compare("chains merged")
+    for f in range(5):
+        both(lambda x: x["s"].step())
+    compare("stepped while asleep")
+    both(lambda x: x["L"].b2Body_Disable(x["anchor"]))
+    compare("anchor disabled")
+    both(lambda x: x["L"].b2Body_Enable(x["anchor"]))                               # its joint returns to the sleeping set
+    compare("anchor enabled")
+    both(lambda x: x["L"].b2Body_SetType(x["anchor"], 1))
+    both(lambda x: x["L"].b2Body_SetType(x["anchor"], 0))
+    compare("anchor retyped")
+    both(lambda x: x["L"].b2DestroyJoint(x["joints"][2]))
+    compare("joint destroyed inside the sleeping set")
+    both(lambda x: x["revolute"](x["sleepers"][5], x["sleepers"][6], 0.75, 0.0))
+    both(lambda x: x["L"].b2Body_SetAwake(x["sleepers"][5], True))
+    for f in range(40):
+        both(lambda x: x["s"].step())
+        if f % 8 == 0:
+            compare("frame %d after waking one pair" % f)
+    both(lambda x: x["L"].b2Body_SetAwake(x["sleepers"][1], True))
+    for f in range(120):
+        both(lambda x: x["s"].step())
+        if f % 8 == 0 or f == 119:
+            compare("frame %d after waking the chain" % f)
+    assert lib.f2dGetLastError() == b""
+    both(lambda x: x["s"].destroy())
+
+
+def test_joints_between_sleeping_bodies_match_reference_emu(ref, emu):
+    _sleeping_joint_session(ref, emu)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+def test_joints_between_sleeping_bodies_match_reference_gpu(ref, gpu, mode):
+    _sleeping_joint_session(ref, gpu, mode=mode)
