@@ -678,7 +678,10 @@ constexpr uint64_t kWorldMagic = 0x4632444232303042ull; // "F2DB200B"
 template <class T> F2D_HD T* ptr( World* w, const Arr<T>& a )
 {
 #if defined( __CUDA_ARCH__ )
-	return reinterpret_cast<T*>( w->deviceBase + a.off );
+	// every array of the image lives in HBM: telling the compiler so turns the generic LD / ST into LDG / STG
+	T* p = reinterpret_cast<T*>( w->deviceBase + a.off );
+	__builtin_assume( __isGlobal( p ) );
+	return p;
 #else
 	return reinterpret_cast<T*>( reinterpret_cast<char*>( w ) + a.off );
 #endif
@@ -686,7 +689,9 @@ template <class T> F2D_HD T* ptr( World* w, const Arr<T>& a )
 template <class T> F2D_HD const T* ptr( const World* w, const Arr<T>& a )
 {
 #if defined( __CUDA_ARCH__ )
-	return reinterpret_cast<const T*>( w->deviceBase + a.off );
+	const T* p = reinterpret_cast<const T*>( w->deviceBase + a.off );
+	__builtin_assume( __isGlobal( p ) );
+	return p;
 #else
 	return reinterpret_cast<const T*>( reinterpret_cast<const char*>( w ) + a.off );
 #endif
