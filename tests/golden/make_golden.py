@@ -22,6 +22,9 @@ CASES = [
     ("many_pyramids", {"grid": 3, "base": 6}, [1, 30, 120]),
     ("joint_grid", {"n": 12}, [1, 30, 120]),
     ("polygon_soup", {"count": 40}, [1, 60, 200]),
+    ("joint_zoo", {"sets": 2}, [1, 60, 200]),          # every joint type
+    ("chain_terrain", {"count": 36}, [1, 80, 240]),    # chain-segment manifolds
+    ("sensor_field", {"count": 30}, [1, 80, 200]),     # sensor overlaps
 ]
 
 
