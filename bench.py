@@ -38,6 +38,9 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbox2d_ref.so")
 
 
 # ------------------------------------------------------------------------------------------------ helpers
+_emit = print  # replaced in main(): writes the JSON line to the real stdout
+
+
 def shard(total, rank, world_size):
     """Contiguous block of worlds for `rank` (world w -> GPU w*G/total)."""
     lo = total * rank // world_size
@@ -203,7 +206,7 @@ def run_reference_arm(args, rank):
                                    "threads (%s)" % (sample, PREROLL, args.steps, cores, cpu_model())},
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_config(args, sample_note=None):
@@ -251,10 +254,6 @@ def run_b200_arm(args, rank, world_size, local_rank):
         raise RuntimeError("bench: CUDA device %d not usable - forge2d_b200 has no CPU fallback" % local_rank)
     dist = None
     if world_size > 1:
-        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (torchrun's default environment on some boxes):
-        # keep stdout to the one JSON line the driver parses
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
@@ -414,7 +413,7 @@ def run_b200_arm(args, rank, world_size, local_rank):
         extras["many_pyramids_awake"] = single_world_numbers(lib, ref, "many_pyramids", {}, 2, 24, 1, cores)
         extras["joint_grid"] = single_world_numbers(lib, ref, "joint_grid", {}, 8, 32, 1, cores)
         line["single_world"] = extras
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -437,6 +436,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE line: the JSON the driver parses. Libraries write there too (NCCL prints its version
+    # banner to fd 1 at init), so fd 1 is pointed at stderr for the run and the JSON line goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    global _emit
+    _emit = lambda text: os.write(json_fd, (text + "\n").encode())
     if args.impl == "reference":
         run_reference_arm(args, rank)
     else:
