@@ -413,6 +413,14 @@ def run_b200_arm(args, rank, world_size, local_rank):
         extras["many_pyramids_awake"] = single_world_numbers(lib, ref, "many_pyramids", {}, 2, 24, 1, cores)
         extras["joint_grid"] = single_world_numbers(lib, ref, "joint_grid", {}, 8, 32, 1, cores)
         line["single_world"] = extras
+        # latency floor of a synchronous b2World_Step for small scenes (north_star's "graph-replay latency": the whole
+        # step is ONE kernel launch, so this is launch + header read-back + synchronise): a world with no awake body,
+        # and a 55-box pyramid
+        line["small_scene_latency"] = {
+            "launches_per_step": 1,
+            "static_only_world_ms_per_frame": single_world_numbers(lib, None, "bench2d", {"rows": 0}, 64, 256, 0, cores)["ms_per_frame_mean"],
+            "bench2d_10_rows": single_world_numbers(lib, ref, "bench2d", {"rows": 10}, 128, 256, 0, cores),
+        }
     _emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
