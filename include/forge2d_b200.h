@@ -511,7 +511,7 @@ F2D_API void f2dBatch_Step( f2dBatch* batch, float timeStep, int subStepCount );
 F2D_API void f2dBatch_StepN( f2dBatch* batch, float timeStep, int subStepCount, int steps );
 F2D_API void f2dBatch_Synchronize( f2dBatch* batch );
 /// Threads per world (block size) and resident blocks per SM the batch kernel is compiled for; returns 0 if unknown.
-/// Available: 256x2 (default), 128x4, 64x8, 32x16, 128x8, 64x16.
+/// Available: 128x8 (default), 64x16, 32x32, 256x4, 256x2.
 F2D_API int f2dBatch_SetLaunchConfig( f2dBatch* batch, int threadsPerWorld, int blocksPerSM );
 F2D_API int f2dBatch_GetWorldCount( f2dBatch* batch );
 /// Body move events of every world -> host buffer: `out` receives count*maxBodies records, `counts[w]` valid ones.
