@@ -581,9 +581,17 @@ static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
 	const int moveCountBefore = w->moveArray.count; // header is current in every sync state
 	backendPhaseBegin( hw );
 	backendPhase( hw, dt, subSteps, kPhasePairsQuery );
-	if ( hw.customFilterFcn != nullptr && dt != 0.0f && moveCountBefore > 0 )
+	if ( dt != 0.0f && moveCountBefore > 0 )
 	{
 		backendDownloadRange( hw, 0, sizeof( World ) );
+		if ( w->step.retryContacts != 0 )
+		{
+			backendPhaseEnd( hw ); // stopped for lack of room, no callback has run: b2World_Step grows the image and repeats
+			return;
+		}
+	}
+	if ( hw.customFilterFcn != nullptr && dt != 0.0f && moveCountBefore > 0 )
+	{
 		const int moveCount = w->moveArray.count;
 		const int total = w->step.orderedPairCount;
 		if ( total > 0 )
@@ -746,10 +754,25 @@ void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
 		return;
 	}
 	prepareStep( *hw );
-	if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
-		stepWithHostCallbacks( *hw, timeStep, subStepCount );
-	else
-		backendStep( *hw, timeStep, subStepCount, true );
+	for ( int attempt = 0;; ++attempt )
+	{
+		if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+			stepWithHostCallbacks( *hw, timeStep, subStepCount );
+		else
+			backendStep( *hw, timeStep, subStepCount, true );
+		// The step stops before its first structural edit when this step's new contacts do not fit the arrays of the
+		// image (f2d_step.h stepPairs; the reference's arrays grow on demand): grow and repeat.
+		const int need = hw->img->step.retryContacts;
+		if ( need == 0 || attempt == 4 )
+			break;
+		World* w = hostImage( *hw );
+		w->step.retryContacts = 0;
+		w->error &= ~kErrRetry;
+		reserve( *hw, 0, 0, need + ( need >> 1 ), 0 );
+		hw->img->step.retryContacts = 0;
+		hw->img->error &= ~kErrRetry;
+		hw->state = kHostNewer;
+	}
 	hw->eventsFresh = ( hw->state != kDeviceNewer );
 	checkWorldError( *hw, "b2World_Step" );
 }

@@ -188,10 +188,7 @@ F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 				return true;
 			int pairIndex = atomAdd( &w->step.pairCount, 1 );
 			if ( pairIndex >= w->movePairs.cap )
-			{
-				setError( w, kErrCapacity, __LINE__ );
-				return true;
-			}
+				return true; // counted, not stored: stepPairs sees pairCount > cap and asks the host for room (retryContacts)
 			MovePair& p = pairs[pairIndex];
 			p.shapeA = shapeIdA;
 			p.shapeB = shapeIdB;
@@ -214,8 +211,11 @@ enum : int
 template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part = kPairsAll )
 {
 	int moveCount = w->moveArray.count;
-	if ( part == kPairsQuery && t.rank() == 0 )
+	if ( part != kPairsCreate && t.rank() == 0 )
+	{
 		w->step.orderedPairCount = 0;
+		w->step.retryContacts = 0;
+	}
 	if ( moveCount == 0 )
 		return;
 	if ( moveCount > w->moveHeads.cap )
@@ -279,6 +279,27 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part
 			{
 				total = 0;
 			}
+			// Nothing structural has changed so far. The reference's arrays grow on demand; here every array that takes a
+			// new contact was sized when the image was laid out, so if this step's new pairs do not fit (or the candidate
+			// list itself overflowed) the step stops here and the host repeats it on a larger image.
+			if ( t.rank() == 0 )
+			{
+				const int pairCount = w->step.pairCount;
+				int need = 0;
+				if ( pairCount > w->movePairs.cap || pairCount > w->pairOrder.cap )
+					need = pairCount;
+				else if ( idCount( w->contactIds ) + total > w->contacts.cap )
+					need = total;
+				if ( need > 0 )
+				{
+					w->step.retryContacts = need + 64;
+					w->error |= kErrRetry;
+					w->locked = false;
+				}
+			}
+			t.sync();
+			if ( w->step.retryContacts != 0 )
+				return;
 			if ( part == kPairsQuery )
 			{
 				if ( t.rank() == 0 )
@@ -2657,6 +2678,8 @@ template <class Team> F2D_HDF inline void stepWorld( World* w, Team& t, float dt
 	}
 	stepBegin( w, t, dt, subStepCount );
 	stepPairs( w, t );
+	if ( w->step.retryContacts != 0 ) // see stepPairs: the host repeats the step on a larger image
+		return;
 	stepCollide( w, t );
 	stepSolve( w, t );
 	stepFinalize( w, t );
@@ -2676,6 +2699,8 @@ template <class Team> F2D_HDF inline void stepWorldPhase( World* w, Team& t, int
 			stepZeroDt( w, t );
 		return;
 	}
+	if ( phase != kPhaseBeginPairs && phase != kPhasePairsQuery && w->step.retryContacts != 0 )
+		return; // the step stopped in stepPairs and will be repeated
 	switch ( phase )
 	{
 		case kPhaseBeginPairs:

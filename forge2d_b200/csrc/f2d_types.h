@@ -475,7 +475,8 @@ struct StepCtx
 	int32_t orderedPairCount; // callback-mediated step: candidate pairs in creation order, waiting for the host's custom filter
 	int32_t preSolveCount;	  // callback-mediated step: touching contacts waiting for the host's pre-solve verdict
 	int32_t fastDeferredCount; // callback-mediated step: fast bodies whose continuous pass waits for the host's custom filter
-	int32_t reserved;		   // keeps sizeof( World ) a multiple of 16
+	int32_t retryContacts;	   // != 0: the step stopped before its first structural edit because the contact arrays cannot take
+							   // this many new contacts (kErrRetry); the host grows the image and runs the step again
 	unsigned long long splitKey; // (sleepTime bits << 32) | ~simIndex  — arg-max over bodies that want an island split
 };
 
@@ -564,7 +565,8 @@ enum : uint32_t
 	kErrCapacity = 1,		 // a fixed-capacity array overflowed inside the step
 	kErrTreeStack = 2,		 // traversal stack overflow
 	kErrUnsupported = 4,	 // feature not available on the device path
-	kErrSleepPool = 8
+	kErrSleepPool = 8,
+	kErrRetry = 16 // not an error for a single world (b2World_Step grows the image and repeats the step); a batch reports it
 };
 
 // World parameters + every array. Reference: B2/src/world.h:44-175.

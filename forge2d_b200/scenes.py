@@ -568,10 +568,167 @@ def chain_terrain(lib, count=36, create=None, **world_kw):
     return scene
 
 
+def random_world(lib, seed=1, count=48, create=None, **world_kw):
+    """Seeded random scene for differential testing: every body type (static, kinematic, dynamic; bullets, fixed
+    rotation, damping, gravity scale, sleep thresholds), every shape type with random materials (friction, restitution,
+    rolling resistance, tangent speed), random filters (categories, masks, groups), sensors, hit events, multi-shape
+    bodies and random revolute / distance / weld joints between neighbours, inside a box of segments."""
+    import math
+    rng = _Lcg(1000 + 7919 * seed)
+    r = rng.next
+    world = _world(lib, create=create, enable_continuous=(seed % 5 != 4), **world_kw)
+    bd = lib.b2DefaultBodyDef()
+    ground = lib.b2CreateBody(world, C.byref(bd))
+    gsd = lib.b2DefaultShapeDef()
+    gsd.enableHitEvents = True
+    for p1, p2 in (((-10.0, 0.0), (10.0, 0.0)), ((-10.0, 0.0), (-12.0, 30.0)), ((10.0, 0.0), (12.0, 30.0))):
+        seg = A.Segment(A.Vec2(*p1), A.Vec2(*p2))
+        lib.b2CreateSegmentShape(ground, C.byref(gsd), C.byref(seg))
+    bodies = [ground]
+
+    def shape_def():
+        sd = lib.b2DefaultShapeDef()
+        sd.density = _f32(0.5 + 3.0 * r())
+        sd.material.friction = _f32(r())
+        sd.material.restitution = _f32(0.6 * r()) if r() < 0.4 else 0.0
+        sd.material.rollingResistance = _f32(0.2 * r()) if r() < 0.25 else 0.0
+        sd.material.tangentSpeed = _f32(2.0 * r() - 1.0) if r() < 0.15 else 0.0
+        if r() < 0.3:
+            sd.filter.categoryBits = 1 << int(4 * r())
+            sd.filter.maskBits = int(r() * 16) | 1
+        if r() < 0.2:
+            sd.filter.groupIndex = int(5 * r()) - 2
+        sd.enableHitEvents = r() < 0.3
+        sd.enableContactEvents = r() < 0.8
+        if r() < 0.08:
+            sd.isSensor = True
+            sd.enableSensorEvents = True
+        else:
+            sd.enableSensorEvents = r() < 0.7
+        return sd
+
+    def add_shape(body):
+        sd = shape_def()
+        kind = int(6 * r())
+        if kind == 0:
+            c = A.Circle(A.Vec2(_f32(0.3 * r() - 0.15), 0.0), _f32(0.15 + 0.35 * r()))
+            lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+        elif kind == 1:
+            cap = A.Capsule(A.Vec2(_f32(-0.2 - 0.4 * r()), 0.0), A.Vec2(_f32(0.2 + 0.4 * r()), _f32(0.3 * r())), _f32(0.1 + 0.2 * r()))
+            lib.b2CreateCapsuleShape(body, C.byref(sd), C.byref(cap))
+        elif kind == 2:
+            box = lib.b2MakeOffsetRoundedBox(_f32(0.15 + 0.5 * r()), _f32(0.15 + 0.4 * r()), A.Vec2(_f32(0.2 * r()), 0.0),
+                                             A.Rot(1.0, 0.0), 0.0)
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+        elif kind == 3:
+            a = r() * 6.28318
+            box = lib.b2MakeOffsetRoundedBox(_f32(0.2 + 0.3 * r()), _f32(0.1 + 0.3 * r()), A.Vec2(0.0, 0.0),
+                                             A.Rot(_f32(math.cos(a)), _f32(math.sin(a))), _f32(0.02 + 0.1 * r()))
+            lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(box))
+        elif kind == 4:
+            n = 3 + int(6 * r())
+            pts = (A.Vec2 * n)()
+            for k in range(n):
+                ang = 6.28318 * (k + 0.7 * r()) / n
+                rad = 0.25 + 0.35 * r()
+                pts[k] = A.Vec2(_f32(rad * math.cos(ang)), _f32(rad * math.sin(ang)))
+            hull = lib.b2ComputeHull(pts, n)
+            if hull.count >= 3:
+                poly = lib.b2MakePolygon(C.byref(hull), _f32(0.05 * r()) if r() < 0.3 else 0.0)
+                lib.b2CreatePolygonShape(body, C.byref(sd), C.byref(poly))
+            else:
+                c = A.Circle(A.Vec2(0.0, 0.0), 0.3)
+                lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+        else:
+            seg = A.Segment(A.Vec2(_f32(-0.3 - 0.5 * r()), 0.0), A.Vec2(_f32(0.3 + 0.5 * r()), _f32(0.4 * r() - 0.2)))
+            lib.b2CreateSegmentShape(body, C.byref(sd), C.byref(seg))
+
+    dynamic = []
+    for i in range(count):
+        bd = lib.b2DefaultBodyDef()
+        t = r()
+        bd.type = 2 if t < 0.82 else (1 if t < 0.9 else 0)
+        bd.position = A.Vec2(_f32(-8.0 + 16.0 * r()), _f32(1.0 + 0.6 * i + r()))
+        a = 6.28318 * r()
+        bd.rotation = A.Rot(_f32(math.cos(a)), _f32(math.sin(a)))
+        if bd.type != 0:
+            bd.linearVelocity = A.Vec2(_f32(6.0 * r() - 3.0), _f32(4.0 * r() - 8.0 if r() < 0.2 else 2.0 * r() - 1.0))
+            bd.angularVelocity = _f32(6.0 * r() - 3.0)
+        if bd.type == 1:
+            bd.linearVelocity = A.Vec2(_f32(r() - 0.5), _f32(0.4 * r() - 0.2))
+        bd.linearDamping = _f32(0.5 * r()) if r() < 0.3 else 0.0
+        bd.angularDamping = _f32(0.5 * r()) if r() < 0.3 else 0.0
+        bd.gravityScale = _f32(0.5 + r()) if r() < 0.2 else 1.0
+        bd.fixedRotation = r() < 0.1
+        bd.isBullet = bd.type == 2 and r() < 0.12
+        bd.allowFastRotation = r() < 0.1
+        bd.enableSleep = r() < 0.9
+        bd.sleepThreshold = _f32(0.05 + 0.2 * r()) if r() < 0.2 else _f32(0.05)
+        body = lib.b2CreateBody(world, C.byref(bd))
+        for _ in range(1 + (1 if r() < 0.25 else 0) + (1 if r() < 0.1 else 0)):
+            add_shape(body)
+        bodies.append(body)
+        if bd.type == 2:
+            dynamic.append((body, bd.position.x, bd.position.y, A.Rot(bd.rotation.c, bd.rotation.s)))
+    # a few fast bullets aimed at the pile
+    for i in range(3):
+        bd = lib.b2DefaultBodyDef()
+        bd.type = 2
+        bd.isBullet = True
+        bd.position = A.Vec2(_f32(-9.0 + 0.5 * i), _f32(20.0 + 3.0 * i))
+        bd.linearVelocity = A.Vec2(_f32(40.0 + 20.0 * r()), _f32(-60.0 * r()))
+        body = lib.b2CreateBody(world, C.byref(bd))
+        sd = lib.b2DefaultShapeDef()
+        sd.enableHitEvents = True
+        c = A.Circle(A.Vec2(0.0, 0.0), 0.12)
+        lib.b2CreateCircleShape(body, C.byref(sd), C.byref(c))
+        bodies.append(body)
+    joints = []
+
+    def local(rot, dx, dy):     # world-space offset -> the body's local frame
+        return A.Vec2(_f32(rot.c * dx + rot.s * dy), _f32(-rot.s * dx + rot.c * dy))
+
+    # joints only between vertical neighbours (consistent anchors at the midpoint, no loops): a random scene must not
+    # blow up, the point is to reach the rarely taken branches, not NaN arithmetic
+    for k in range(0, len(dynamic) - 1, 2):
+        if r() < 0.45:
+            continue
+        (a, ax, ay, qa), (b, bx, by, qb) = dynamic[k], dynamic[k + 1]
+        mx, my = 0.5 * (ax + bx), 0.5 * (ay + by)
+        kind = int(3 * r())     # prismatic / wheel joints between tumbling bodies blow up in the reference itself: joint_zoo has them
+        if kind == 0:
+            d = lib.b2DefaultRevoluteJointDef()
+            d.bodyIdA, d.bodyIdB = a, b
+            d.localAnchorA, d.localAnchorB = local(qa, mx - ax, my - ay), local(qb, mx - bx, my - by)
+            d.enableLimit, d.lowerAngle, d.upperAngle = r() < 0.5, -0.5, 0.8
+            d.enableMotor, d.maxMotorTorque, d.motorSpeed = r() < 0.3, 5.0, _f32(2.0 * r() - 1.0)
+            d.enableSpring, d.hertz, d.dampingRatio = r() < 0.3, 2.0, 0.3
+            d.collideConnected = r() < 0.3
+            joints.append(lib.b2CreateRevoluteJoint(world, C.byref(d)))
+        elif kind == 1:
+            d = lib.b2DefaultDistanceJointDef()
+            d.bodyIdA, d.bodyIdB = a, b
+            d.length = _f32(max(0.2, math.hypot(bx - ax, by - ay)))
+            d.enableSpring, d.hertz, d.dampingRatio = r() < 0.6, _f32(1.0 + 4.0 * r()), _f32(r())
+            d.enableLimit, d.minLength, d.maxLength = r() < 0.4, _f32(0.5 * d.length), _f32(1.5 * d.length)
+            joints.append(lib.b2CreateDistanceJoint(world, C.byref(d)))
+        else:
+            d = lib.b2DefaultWeldJointDef()
+            d.bodyIdA, d.bodyIdB = a, b
+            d.localAnchorA, d.localAnchorB = local(qa, mx - ax, my - ay), local(qb, mx - bx, my - by)
+            d.referenceAngle = _f32(math.atan2(qb.s, qb.c) - math.atan2(qa.s, qa.c))
+            d.linearHertz, d.angularHertz = _f32(3.0 * r()), _f32(3.0 * r())
+            joints.append(lib.b2CreateWeldJoint(world, C.byref(d)))
+    scene = Scene(lib, world, bodies, "random_world_%d" % seed)
+    scene.joints = joints
+    return scene
+
+
 SCENES = {
     "chain_terrain": chain_terrain,
     "sensor_field": sensor_field,
     "joint_zoo": joint_zoo,
+    "random_world": random_world,
     "bench2d": bench2d,
     "large_pyramid": large_pyramid,
     "many_pyramids": many_pyramids,
