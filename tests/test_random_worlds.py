@@ -103,3 +103,109 @@ def test_step_grows_the_image_when_new_contacts_do_not_fit_emu(ref, emu):
 @pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
 def test_step_grows_the_image_when_new_contacts_do_not_fit_gpu(ref, gpu, mode):
     _crowd_session(ref, gpu, mode=mode)
+
+
+# ---- random API calls between steps --------------------------------------------------------------------------------
+def _mutate(lib, scene, rng, alive, joints_alive):
+    """One random mutator call (same choice for every library: the choice depends only on the seeded stream)."""
+    import ctypes as C
+    import math
+    from forge2d_b200 import _abi as A
+    r = rng.next
+    pick = [i for i in range(1, len(scene.bodies)) if alive[i]]
+    if not pick:
+        return "none"
+    i = pick[int(r() * len(pick))]
+    body = scene.bodies[i]
+    op = int(r() * 16)
+    if op == 0:
+        lib.b2Body_ApplyLinearImpulseToCenter(body, A.Vec2(H_f32(6.0 * r() - 3.0), H_f32(8.0 * r())), True)
+    elif op == 1:
+        a = 6.28318 * r()
+        lib.b2Body_SetTransform(body, A.Vec2(H_f32(-7.0 + 14.0 * r()), H_f32(2.0 + 20.0 * r())), A.Rot(H_f32(math.cos(a)), H_f32(math.sin(a))))
+    elif op == 2:
+        lib.b2Body_SetLinearVelocity(body, A.Vec2(H_f32(10.0 * r() - 5.0), H_f32(10.0 * r() - 5.0)))
+    elif op == 3:
+        lib.b2Body_SetAwake(body, r() < 0.5)
+    elif op == 4:
+        lib.b2Body_Disable(body)
+    elif op == 5:
+        lib.b2Body_Enable(body)
+    elif op == 6:
+        lib.b2Body_SetType(body, int(3 * r()))
+    elif op == 7:
+        lib.b2DestroyBody(body)
+        alive[i] = False
+    elif op == 8:
+        shapes = (A.ShapeId * 8)()
+        n = lib.b2Body_GetShapes(body, shapes, 8)
+        if n > 1:
+            lib.b2DestroyShape(shapes[int(r() * n)], r() < 0.7)
+    elif op == 9:
+        live = [k for k in range(len(scene.joints)) if joints_alive[k]]
+        if live:
+            k = live[int(r() * len(live))]
+            # a joint dies with either of its bodies: only destroy it while the library still knows it
+            if lib.b2Joint_IsValid(scene.joints[k]):
+                lib.b2DestroyJoint(scene.joints[k])
+            joints_alive[k] = False
+    elif op == 10:
+        lib.b2Body_SetBullet(body, r() < 0.5)
+    elif op == 11:
+        lib.b2Body_SetFixedRotation(body, r() < 0.5)
+    elif op == 12:
+        shapes = (A.ShapeId * 8)()
+        n = lib.b2Body_GetShapes(body, shapes, 8)
+        if n > 0:
+            f = A.Filter(1 << int(3 * r()), int(r() * 8) | 1, int(3 * r()) - 1)
+            lib.b2Shape_SetFilter(shapes[int(r() * n)], f)
+    elif op == 13:
+        lib.b2Body_ApplyAngularImpulse(body, H_f32(2.0 * r() - 1.0), True)
+    elif op == 14:
+        lib.b2Body_EnableSleep(body, r() < 0.5)
+    else:
+        shapes = (A.ShapeId * 8)()
+        n = lib.b2Body_GetShapes(body, shapes, 8)
+        if n > 0:
+            lib.b2Shape_SetFriction(shapes[0], H_f32(r()))
+    return op
+
+
+def H_f32(v):
+    import numpy as np
+    return float(np.float32(v))
+
+
+def _fuzz(ref, lib, seed, frames=200, mode=None):
+    lib.f2dClearLastError()
+    sessions = []
+    for L in (ref, lib):
+        s = scenes.random_world(L, seed=seed, count=36)
+        sessions.append((L, s, scenes._Lcg(31337 + seed), [True] * len(s.bodies), [True] * len(s.joints)))
+    if mode is not None:
+        lib.f2dWorld_SetLaunchMode(sessions[1][1].world, mode)
+    for f in range(frames):
+        ops = []
+        for L, s, rng, alive, joints_alive in sessions:
+            n = 1 + (f % 3 == 0)
+            ops.append([_mutate(L, s, rng, alive, joints_alive) for _ in range(n)] if f % 2 == 0 else [])
+        assert ops[0] == ops[1]
+        for L, s, *_ in sessions:
+            s.step()
+        d = H.diff(H.snapshot(ref, sessions[0][1].world), H.snapshot(lib, sessions[1][1].world))
+        assert d == [], "seed %d frame %d after ops %s: %s" % (seed, f, ops[0], d[:6])
+        assert _events(ref, sessions[0][1].world) == _events(lib, sessions[1][1].world), "seed %d frame %d: events" % (seed, f)
+    assert lib.f2dGetLastError() == b""
+    for L, s, *_ in sessions:
+        s.destroy()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6])
+def test_random_api_calls_between_steps_emu(ref, emu, seed):
+    _fuzz(ref, emu, seed)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_api_calls_between_steps_gpu(ref, gpu, seed):
+    _fuzz(ref, gpu, seed, frames=120)
