@@ -291,7 +291,7 @@ struct f2dBatch
 	int hostEventCap = 0;
 	// f2dBatch_StepAndReadBodyEvents: the batch is stepped in slices of worlds, one stream each, so that the read-back
 	// of a slice crosses PCIe while the next slices are still being stepped
-	static constexpr int kSlices = 8;
+	static constexpr int kSlices = 16;
 	cudaStream_t sliceStreams[kSlices] = {};
 	cudaEvent_t sliceDone[kSlices] = {};
 	cudaEvent_t inputsReady = nullptr;
