@@ -23,26 +23,66 @@ def _events(lib, world):
     return begin, end, hit, sb, se
 
 
-def _run(ref, lib, seed, frames, every, mode=None):
+def _register_callbacks(lib, world, log):
+    """Deterministic b2CustomFilterFcn / b2PreSolveFcn (verdicts are pure functions of the arguments) that log what they see."""
+    import ctypes as C
+    from forge2d_b200 import _abi as A
+
+    def custom_filter(a, b, ctx):
+        log.append(("filter", a.index1, b.index1))
+        return (a.index1 * 3 + b.index1) % 7 != 0
+
+    def pre_solve(a, b, manifold, ctx):
+        m = manifold.contents
+        log.append(("presolve", a.index1, b.index1, m.pointCount, m.normal.x, m.normal.y, m.points[0].separation, m.points[0].id))
+        return (a.index1 + 2 * b.index1) % 5 != 0
+
+    f1 = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.c_void_p)(custom_filter)
+    f2 = C.CFUNCTYPE(C.c_bool, A.ShapeId, A.ShapeId, C.POINTER(A.Manifold), C.c_void_p)(pre_solve)
+    lib.b2World_SetCustomFilterCallback(world, C.cast(f1, C.c_void_p), None)
+    lib.b2World_SetPreSolveCallback(world, C.cast(f2, C.c_void_p), None)
+    return f1, f2
+
+
+def _run(ref, lib, seed, frames, every, mode=None, callbacks=False):
     lib.f2dClearLastError()
-    a = scenes.random_world(ref, seed=seed)
-    b = scenes.random_world(lib, seed=seed)
+    a = scenes.random_world(ref, seed=seed, pre_solve_events=callbacks)
+    b = scenes.random_world(lib, seed=seed, pre_solve_events=callbacks)
     if mode is not None:
         lib.f2dWorld_SetLaunchMode(b.world, mode)
+    logs, keep = ([], []), []
+    if callbacks:
+        keep = [_register_callbacks(ref, a.world, logs[0]), _register_callbacks(lib, b.world, logs[1])]
     totals = [0, 0, 0, 0, 0]
     for f in range(frames):
         a.step()
         b.step()
         ea, eb = _events(ref, a.world), _events(lib, b.world)
         assert ea == eb, "seed %d frame %d: event streams differ" % (seed, f)
+        assert logs[0] == logs[1], "seed %d frame %d: callback sequences differ" % (seed, f)
         totals = [t + len(x) for t, x in zip(totals, ea)]
         if f % every == 0 or f == frames - 1:
             d = H.diff(H.snapshot(ref, a.world), H.snapshot(lib, b.world))
             assert d == [], "seed %d frame %d: %s" % (seed, f, d[:6])
     assert lib.f2dGetLastError() == b""
+    if callbacks:
+        assert sum(1 for e in logs[0] if e[0] == "presolve") > 50 and sum(1 for e in logs[0] if e[0] == "filter") > 50
     a.destroy()
     b.destroy()
+    del keep
     return totals
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_world_with_step_callbacks_matches_reference_emu(ref, emu, seed):
+    _run(ref, emu, seed, 200, 8, callbacks=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta", "grid"])
+@pytest.mark.parametrize("seed", [11, 12])
+def test_random_world_with_step_callbacks_matches_reference_gpu(ref, gpu, seed, mode):
+    _run(ref, gpu, seed, 200, 16, mode=mode, callbacks=True)
 
 
 @pytest.mark.parametrize("seed", SEEDS)
