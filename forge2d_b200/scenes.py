@@ -581,9 +581,22 @@ def random_world(lib, seed=1, count=48, pre_solve_events=False, create=None, **w
     ground = lib.b2CreateBody(world, C.byref(bd))
     gsd = lib.b2DefaultShapeDef()
     gsd.enableHitEvents = True
-    for p1, p2 in (((-10.0, 0.0), (10.0, 0.0)), ((-10.0, 0.0), (-12.0, 30.0)), ((10.0, 0.0), (12.0, 30.0))):
-        seg = A.Segment(A.Vec2(*p1), A.Vec2(*p2))
-        lib.b2CreateSegmentShape(ground, C.byref(gsd), C.byref(seg))
+    chains = []
+    if seed % 3 == 1 and not pre_solve_events:
+        # every third world stands in a bumpy basin made of ONE chain shape (ghost vertices, chain-segment manifolds with
+        # their GJK cache) instead of three segments; travel direction right to left = solid side below
+        pts = [(14.0, 32.0), (12.0, 30.0), (10.0, 0.0), (6.0, 0.6), (3.0, -0.4), (0.0, 0.3), (-4.0, -0.5), (-7.0, 0.4),
+               (-10.0, 0.0), (-12.0, 30.0), (-14.0, 32.0)]
+        arr = (A.Vec2 * len(pts))(*[A.Vec2(_f32(x), _f32(y)) for x, y in pts])
+        cd = lib.b2DefaultChainDef()
+        cd.points = arr
+        cd.count = len(pts)
+        cd.isLoop = False
+        chains.append(lib.b2CreateChain(ground, C.byref(cd)))
+    else:
+        for p1, p2 in (((-10.0, 0.0), (10.0, 0.0)), ((-10.0, 0.0), (-12.0, 30.0)), ((10.0, 0.0), (12.0, 30.0))):
+            seg = A.Segment(A.Vec2(*p1), A.Vec2(*p2))
+            lib.b2CreateSegmentShape(ground, C.byref(gsd), C.byref(seg))
     bodies = [ground]
 
     def shape_def():
@@ -731,6 +744,7 @@ def random_world(lib, seed=1, count=48, pre_solve_events=False, create=None, **w
             joints.append(lib.b2CreateWeldJoint(world, C.byref(d)))
     scene = Scene(lib, world, bodies, "random_world_%d" % seed)
     scene.joints = joints
+    scene.chains = chains
     return scene
 
 
