@@ -1226,10 +1226,16 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 			v.compIsland[comp] = createIsland( w, kAwakeSet );
 		}
 		int sp = 1;
+		// The entry on top of the stack is kept in a register (`top`, uniform across the lanes; kNull = not cached): the
+		// body popped next is nearly always one pushed a moment ago, and reading it back from the stack array would add
+		// one more dependent load to the four a pop already costs.
+		int top = seed;
 		L.sync();
 		while ( sp > 0 )
 		{
-			int pos = v.stack[--sp];
+			sp -= 1;
+			int pos = top != kNull ? top : v.stack[sp];
+			top = kNull;
 			if ( lane == 0 )
 			{
 				v.bodyOrder[nb] = pos;
@@ -1258,6 +1264,7 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 					fresh = fresh && lowestBit32( same ) == lane;
 					if ( fresh )
 						mark[id] = 1;
+
 					// joints to a disabled body are marked but neither recorded nor followed (island.c:785-789)
 					const bool recorded = fresh && other != -2;
 					const uint32_t recordedMask = L.ballot( recorded );
@@ -1276,8 +1283,15 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 					{
 						v.stack[sp + popCount32( pushMask & below )] = other;
 						v.bodyMark[other] = 1;
+						// its edge rows are read when it is popped: ask for them now
+						prefetchLine( v.rowOff + other );
+						prefetchLine( v.edges + 2 * v.rowOff[other] );
 					}
-					sp += popCount32( pushMask );
+					if ( pushMask != 0 )
+					{
+						sp += popCount32( pushMask );
+						top = L.from( other, 31 - countLeadingZeros32( pushMask ) ); // the last one pushed
+					}
 					L.sync();
 				}
 			}
@@ -1685,7 +1699,10 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 		solveStages( w, t );
 		t.sync();
 	}
+	F2D_MARK( w, t, pfSplitJoin );
 	splitApply( w, t );
+	t.sync();
+	F2D_MARK( w, t, pfSplitApply );
 	if ( t.rank() == 0 )
 		w->splitIslandId = kNull;
 }

@@ -105,6 +105,15 @@ F2D_HD int popCount32( uint32_t x )
 	return n;
 #endif
 }
+// leading zero bits (x != 0)
+F2D_HD int countLeadingZeros32( uint32_t x )
+{
+#if defined( __CUDA_ARCH__ )
+	return __clz( (int)x );
+#else
+	return __builtin_clz( x );
+#endif
+}
 // index of the lowest set bit (x != 0)
 F2D_HD int lowestBit32( uint32_t x )
 {
@@ -130,6 +139,7 @@ struct SoloLanes
 	F2D_HD uint32_t matchAny( int ) const { return 1u; }
 	F2D_HD void sync() const {}
 	F2D_HD int broadcast( int v ) const { return v; }
+	F2D_HD int from( int v, int ) const { return v; }
 	F2D_HD int reduceAdd( int v ) const { return v; }
 	F2D_HD float reduceMin( float v ) const { return v; }
 	F2D_HD float reduceMax( float v ) const { return v; }
@@ -144,6 +154,7 @@ struct WarpLanes
 	F2D_HD uint32_t matchAny( int key ) const { return __match_any_sync( 0xffffffffu, key ); }
 	F2D_HD void sync() const { __syncwarp(); }
 	F2D_HD int broadcast( int v ) const { return __shfl_sync( 0xffffffffu, v, 0 ); }
+	F2D_HD int from( int v, int sourceLane ) const { return __shfl_sync( 0xffffffffu, v, sourceLane ); } // every lane gets sourceLane's v
 	F2D_HD int reduceAdd( int v ) const
 	{
 		for ( int off = 16; off > 0; off >>= 1 )

@@ -551,6 +551,8 @@ enum ProfSlot : int
 	pfBullets,
 	pfSleep,
 	pfEnd,
+	pfSplitJoin,  // waiting for the island-split walk after the solver stages (accumulated separately from the phases above)
+	pfSplitApply,
 	kProfSlots = 24
 };
 

@@ -13,7 +13,7 @@ assert lib.f2dHasDevice()
 what = sys.argv[1:] or ["single", "batch"]
 PROF_NAMES = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
               "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
-              "bullets", "sleep", "end"]
+              "bullets", "sleep", "end", "splitJoin", "splitApply"]
 
 
 def single(name, kw, mode, warm, timed):
@@ -67,7 +67,7 @@ if "batch" in what:
 
 _PROF_NAMES_MOVED = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
               "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
-              "bullets", "sleep", "end"]
+              "bullets", "sleep", "end", "splitJoin", "splitApply"]
 
 
 def profile(name, kw, mode, warm, timed):
@@ -82,7 +82,7 @@ def profile(name, kw, mode, warm, timed):
     wall = (time.perf_counter() - t0) / timed * 1e3
     out = (C.c_ulonglong * 24)()
     lib.f2dWorld_ReadProfile(s.world, out, 24)
-    total = sum(out[:21]) / timed / 1e3
+    total = sum(out[:23]) / timed / 1e3
     print("%s %s mode %d: wall %.3f ms/frame, in-kernel %.1f us: " % (name, kw, mode, wall, total) +
           " ".join("%s=%.1f" % (n, out[i] / timed / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
     s.destroy()
@@ -125,7 +125,7 @@ if "batchprofile" in what:
         lib.f2dBatch_DownloadWorld(b, count // 2, scratch.world)
         out = (C.c_ulonglong * 24)()
         lib.f2dWorld_ReadProfile(scratch.world, out, 24)
-        total = sum(out[:21]) / steps / 1e3
+        total = sum(out[:23]) / steps / 1e3
         print("batch %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
             threads, bps, count, ms, count / ms * 1e3, count // 2, total) +
             " ".join("%s=%.1f" % (n, out[i] / steps / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
