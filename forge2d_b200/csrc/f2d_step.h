@@ -1215,6 +1215,7 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 	if ( lane == 0 )
 		destroyIsland( w, baseId );
 	int comp = 0, nb = 0, nc = 0, nj = 0;
+	const int passes = v.jrowOff[n] > 0 ? 2 : 1; // an island without joints: no (empty) joint rows to look up per body
 	for ( int seed = 0; seed < n; ++seed )
 	{
 		if ( v.bodyMark[seed] )
@@ -1242,7 +1243,7 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 				v.bodyComp[nb] = comp;
 			}
 			nb += 1;
-			for ( int pass = 0; pass < 2; ++pass )
+			for ( int pass = 0; pass < passes; ++pass )
 			{
 				// pass 0: contact edges, pass 1: joint edges (island.c:700-767 then :769-812)
 				const int32_t* rowOff = pass == 0 ? v.rowOff : v.jrowOff;
