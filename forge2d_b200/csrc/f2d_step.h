@@ -2609,7 +2609,27 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t, int p
 		}
 
 		F2D_MARK( w, t, pfBullets );
-		// island sleep: reverse scan of awake islands (solver.c:1995-2051)
+		// island sleep: reverse scan of awake islands (solver.c:1995-2051). Which islands may fall asleep (no body voted
+		// to stay awake, no constraint removed: solver_set.c:156-165) is found by the whole team; the serial, order-defining
+		// part then only visits those, still last island first (a settled pile is hundreds of small islands, nearly
+		// all of them kept awake: the serial scan over them used to cost as much as the whole finalize loop).
+		const int islandCount = w->enableSleep ? w->awakeIslands.count : 0;
+		int32_t* maySleep = ptr( w, w->scan ); // free since the move array was built
+		const bool listed = islandCount <= w->scan.cap;
+		int sleeperCount = -1;
+		if ( listed )
+		{
+			const int32_t* islandList = ptr( w, w->awakeIslands );
+			const Island* islands = ptr( w, w->islands );
+			for ( int i = t.rank(); i < islandCount; i += t.size() )
+			{
+				const bool keptAwake = ( ib[i >> 6] & ( 1ull << ( i & 63 ) ) ) != 0;
+				maySleep[i] = ( keptAwake == false && islands[islandList[i]].constraintRemoveCount == 0 ) ? 1 : 0;
+			}
+			t.sync();
+			// flags -> prefix sums: the serial part below reads one number when (as nearly always) nobody falls asleep
+			sleeperCount = t.exclusiveScan( maySleep, islandCount );
+		}
 		if ( t.rank() == 0 )
 		{
 			w->step.bulletCount = 0;
@@ -2622,11 +2642,24 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t, int p
 					w->splitIslandId = bodies[awakeBodies[simIndex]].islandId;
 				}
 				const int32_t* islandList = ptr( w, w->awakeIslands );
-				int count = w->awakeIslands.count;
-				for ( int islandIndex = count - 1; islandIndex >= 0; islandIndex -= 1 )
+				int above = sleeperCount; // prefix sum one past the current index
+				for ( int islandIndex = sleeperCount == 0 ? -1 : islandCount - 1; islandIndex >= 0; islandIndex -= 1 )
 				{
-					if ( ib[islandIndex >> 6] & ( 1ull << ( islandIndex & 63 ) ) )
+					bool skip;
+					if ( listed )
+					{
+						const int here = maySleep[islandIndex];
+						skip = here == above;
+						above = here;
+					}
+					else
+					{
+						skip = ( ib[islandIndex >> 6] & ( 1ull << ( islandIndex & 63 ) ) ) != 0;
+					}
+					if ( skip )
 						continue;
+					// an island that falls asleep leaves the awake list by swap-remove: the entry that moves comes from
+					// behind this index and has been visited already, so the flags by index stay valid
 					trySleepIsland( w, islandList[islandIndex] );
 				}
 			}
