@@ -1454,7 +1454,7 @@ int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
 			r->setIndex = c.setIndex;
 			r->colorIndex = c.colorIndex;
 			r->localIndex = c.localIndex;
-			r->flags = (int)c.flags;
+			r->flags = (int)( c.flags & ~kContactMarked );
 			r->simFlags = (int)s.simFlags;
 			r->pointCount = s.manifold.pointCount;
 			r->islandId = c.islandId;

@@ -87,7 +87,6 @@ inline int createBody( World* w, const BodyParams& def )
 	sim.linearDamping = def.linearDamping;
 	sim.angularDamping = def.angularDamping;
 	sim.gravityScale = def.gravityScale;
-	sim.bodyId = bodyId;
 	sim.isBullet = def.isBullet;
 	sim.allowFastRotation = def.allowFastRotation;
 

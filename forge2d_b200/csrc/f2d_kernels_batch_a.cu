@@ -1,5 +1,6 @@
-// forge2d_b200 — batch kernels (one thread block per world), configurations 256x2, 256x4.
-// Separate translation unit so the variants compile in parallel.
+// forge2d_b200 — batch kernel (one thread block per world), configuration 256x4.
+// One step kernel per translation unit: the variants compile in parallel (and ptxas 12.9 crashes on a module that holds
+// two instantiations of the step).
 #include "f2d_kernels.cuh"
 
 namespace f2d
@@ -7,11 +8,6 @@ namespace f2d
 bool launchBatchStepA( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
 						cudaStream_t stream )
 {
-	if ( threads == 256 && blocksPerSM == 2 )
-	{
-		stepWorldsCta<256, 2><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
-		return true;
-	}
 	if ( threads == 256 && blocksPerSM == 4 )
 	{
 		stepWorldsCta<256, 4><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );

@@ -1,5 +1,6 @@
-// forge2d_b200 — batch kernels (one thread block per world), configurations 32x32.
-// Separate translation unit so the variants compile in parallel.
+// forge2d_b200 — batch kernel (one thread block per world), configuration 64x16.
+// One step kernel per translation unit: the variants compile in parallel (and ptxas 12.9 crashes on a module that holds
+// two instantiations of the step).
 #include "f2d_kernels.cuh"
 
 namespace f2d
@@ -7,9 +8,9 @@ namespace f2d
 bool launchBatchStepB( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
 						cudaStream_t stream )
 {
-	if ( threads == 32 && blocksPerSM == 32 )
+	if ( threads == 64 && blocksPerSM == 16 )
 	{
-		stepWorldsCta<32, 32><<<worldCount, 32, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
+		stepWorldsCta<64, 16><<<worldCount, 64, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps );
 		return true;
 	}
 	return false;

@@ -1,5 +1,5 @@
-// forge2d_b200 — kernels for ONE world: a single 1024-thread block (small worlds: barrier cost ~tens of ns, working set
-// in that SM's L1/L2) or a cooperative grid of one block per SM (large worlds), plus the batch gather kernels.
+// forge2d_b200 — kernel for ONE small world: a single 1024-thread block (barrier cost ~tens of ns, working set in that
+// SM's L1/L2), plus the batch gather kernels. The cooperative-grid kernel for large worlds is in f2d_kernels_grid.cu.
 #include "f2d_kernels.cuh"
 
 namespace f2d
@@ -39,18 +39,11 @@ __global__ void gatherErrors( const char* base, unsigned long long stride, int w
 
 
 constexpr int kSingleCtaThreads = 1024;
-constexpr int kGridThreads = 512;
 
 cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream )
 {
 	stepWorldsCta<kSingleCtaThreads, 1><<<1, kSingleCtaThreads, 0, stream>>>( reinterpret_cast<char*>( dev ), 0ull, 1, dt, sub, phase, 1 );
 	return cudaGetLastError();
-}
-
-cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, cudaStream_t stream )
-{
-	void* args[] = { &dev, &blockTotals, &dt, &sub, &phase };
-	return cudaLaunchCooperativeKernel( (void*)stepWorldGrid<kGridThreads>, dim3( blocks ), dim3( kGridThreads ), args, 0, stream );
 }
 
 void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,

@@ -15,7 +15,7 @@ bool launchBatchStepC( int threads, int blocksPerSM, char* base, unsigned long l
 					   cudaStream_t stream );
 inline bool batchConfigExists( int threads, int blocksPerSM )
 {
-	const int known[][2] = { { 256, 2 }, { 256, 4 }, { 32, 32 }, { 128, 8 }, { 64, 16 } };
+	const int known[][2] = { { 256, 4 }, { 128, 8 }, { 64, 16 } };
 	for ( auto& k : known )
 		if ( k[0] == threads && k[1] == blocksPerSM )
 			return true;

@@ -584,7 +584,9 @@ enum : int
 {
 	kCollideAll = 0,
 	kCollideNarrow = 1,
-	kCollideFinish = 2
+	kCollideFinish = 2,
+	kCollideTreeOnly = 3,  // profiling aid (F2D_PROFILE_PHASE_LAUNCHES): the tree rebuild alone
+	kCollideNarrowOnly = 4 // profiling aid: the narrowphase alone
 };
 template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int part = kCollideAll )
 {
@@ -646,14 +648,19 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 			id0 = id1;
 		}
 	};
-	treeRebuildTeam( w, t, w->trees[kDynamicBody] );
-	treeRebuildTeam( w, t, w->trees[kKinematicBody] );
-	t.sync();
-	F2D_MARK( w, t, pfTreeRebuild );
+	if ( part != kCollideNarrowOnly )
+	{
+		treeRebuildTeam( w, t, w->trees[kDynamicBody] );
+		treeRebuildTeam( w, t, w->trees[kKinematicBody] );
+		t.sync();
+		F2D_MARK( w, t, pfTreeRebuild );
+	}
+	if ( part == kCollideTreeOnly )
+		return;
 	narrowphase( t.rank(), t.size() );
 	t.sync();
 	F2D_MARK( w, t, pfNarrow );
-	if ( part == kCollideNarrow )
+	if ( part == kCollideNarrow || part == kCollideNarrowOnly )
 		return;
 	contactStatePass( w, t );
 	t.sync();
@@ -1759,7 +1766,7 @@ F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
 	const BodySim& bodySim = ptr( w, w->sims )[shape.bodyId];
 	if ( bodySim.isBullet )
 		return true;
-	const Body& fastBody = bodies[ctx.fastSim->bodyId];
+	const Body& fastBody = bodies[fastShape.bodyId];
 	if ( shouldBodiesCollide( w, fastBody, body ) == false )
 		return true;
 #if !defined( __CUDA_ARCH__ )
@@ -2716,7 +2723,9 @@ enum Phase
 	kPhaseCollideFinish = 8,
 	kPhaseFinalizeBodies = 9, // see stepFinalize
 	kPhaseFinalizeMoves = 10,
-	kPhaseFinalizeEnd = 11
+	kPhaseFinalizeEnd = 11,
+	kPhaseCollideTreeOnly = 12, // profiling aids: see kCollideTreeOnly
+	kPhaseCollideNarrowOnly = 13
 };
 
 // Whole step on one team (used by the CTA-per-world kernel and the host emulation)
@@ -2773,6 +2782,12 @@ template <class Team> F2D_HDF inline void stepWorldPhase( World* w, Team& t, int
 			break;
 		case kPhaseCollideFinish:
 			stepCollide( w, t, kCollideFinish );
+			break;
+		case kPhaseCollideTreeOnly:
+			stepCollide( w, t, kCollideTreeOnly );
+			break;
+		case kPhaseCollideNarrowOnly:
+			stepCollide( w, t, kCollideNarrowOnly );
 			break;
 		case kPhaseSolve:
 			stepSolve( w, t );

@@ -160,37 +160,55 @@ struct SensorEvent
 };
 
 // --- internal records ---------------------------------------------------------------------------------------
-// Cold body data: B2/src/body.h:14-64
-struct Body
+// Record layout rule (all records below): a record is a whole number of 32-byte DRAM sectors, starts on a sector
+// boundary (arrays start 256-byte aligned, f2d_image.h), and its fields are grouped so that one phase of the step finds
+// what it reads in as few sectors as possible; `alignas` lets the compiler move 8- and 16-byte groups with one
+// LDG.64 / STG.128 instead of one 4-byte access per field. Field meaning follows the reference; only the order is ours.
+
+// Body data apart from the simulation record: B2/src/body.h:14-64
+struct alignas( 32 ) Body
 {
-	char name[32];
-	uint64_t userData;
+	// sector 0: narrowphase (setIndex, localIndex) and pair finding (contact / joint lists, type)
 	int32_t setIndex, localIndex; // localIndex = position in the owning set's id list
 	int32_t headContactKey, contactCount;
-	int32_t headShapeId, shapeCount, headChainId;
 	int32_t headJointKey, jointCount;
-	int32_t islandId, islandPrev, islandNext;
-	float mass, inertia, sleepThreshold, sleepTime;
-	int32_t bodyMoveIndex, id, type;
+	int32_t type, id;
+	// sector 1: finalize (island vote, sleep, shape list, move event)
+	int32_t islandId, headShapeId, shapeCount;
+	float sleepThreshold, sleepTime;
 	uint16_t generation;
 	uint16_t colorMask; // per-colour membership bits (replaces the per-colour body bitsets, constraint_graph.h:24-42)
+	uint64_t userData;
+	// sector 2
+	int32_t bodyMoveIndex, islandPrev, islandNext, headChainId;
+	float mass, inertia;
 	bool enableSleep, fixedRotation, isSpeedCapped, isMarked;
+	int32_t pad0;
+	// sector 3
+	char name[32];
 };
+static_assert( sizeof( Body ) == 128, "Body layout" );
 // Body simulation data (stable slot = body id): B2/src/body.h:120-159
-struct BodySim
+struct alignas( 32 ) BodySim
 {
+	// sector 0: everything the narrowphase reads of a body
 	Xf transform;
-	V2 center;
-	Rot rotation0;
-	V2 center0;
 	V2 localCenter;
+	float invMass, invInertia;
+	// sector 1: finalize
+	V2 center;
+	V2 center0;
+	Rot rotation0;
+	float minExtent, maxExtent;
+	// sector 2: velocity integration constants, flags
 	V2 force;
-	float torque, invMass, invInertia, minExtent, maxExtent, linearDamping, angularDamping, gravityScale;
-	int32_t bodyId;
+	float torque, linearDamping, angularDamping, gravityScale;
 	bool isFast, isBullet, isSpeedCapped, allowFastRotation, enlargeAABB;
+	bool pad0[3];
 };
+static_assert( sizeof( BodySim ) == 96, "BodySim layout" );
 // Solver state, dense by awake index, 32 B = two float4: B2/src/body.h:66-83
-struct BodyState
+struct alignas( 16 ) BodyState
 {
 	V2 v;
 	float w;
@@ -199,17 +217,21 @@ struct BodyState
 	Rot dq;
 };
 // B2/src/shape.h:13-52
-struct Shape
+struct alignas( 32 ) Shape
 {
-	int32_t id, bodyId, prevShapeId, nextShapeId, sensorIndex, type;
-	float density, friction, restitution, rollingResistance, tangentSpeed;
-	int32_t userMaterialId;
+	// sector 0: boxes
 	Box aabb, fatAABB;
-	V2 localCentroid;
-	int32_t proxyKey;
-	Filter filter;
-	uint64_t userData;
+	// sector 1: links, type, flags, friction
+	int32_t type, bodyId, nextShapeId, proxyKey, sensorIndex;
+	uint16_t generation;
+	bool enableSensorEvents, enableContactEvents, enableHitEvents, enablePreSolveEvents, enlargedAABB;
+	bool pad0;
+	float friction;
+	// sector 2: the rest of the material (narrowphase), cold ids
+	float restitution, rollingResistance, tangentSpeed, density;
+	int32_t userMaterialId, id, prevShapeId;
 	uint32_t customColor;
+	// sector 3 onwards: geometry (a box: vertices 96-127, normals 160-191, centroid / radius / count 224-239)
 	union
 	{
 		Capsule capsule;
@@ -218,9 +240,13 @@ struct Shape
 		Segment segment;
 		ChainSegment chainSegment;
 	};
-	uint16_t generation;
-	bool enableSensorEvents, enableContactEvents, enableHitEvents, enablePreSolveEvents, enlargedAABB;
+	// pair finding
+	Filter filter;
+	V2 localCentroid;
+	uint64_t userData;
+	int32_t pad1[2];
 };
+static_assert( sizeof( Shape ) == 288, "Shape layout" );
 
 enum : uint32_t // contact.h:15-25
 {
@@ -244,19 +270,22 @@ struct Edge
 {
 	int32_t bodyId, prevKey, nextKey;
 };
-// Cold contact data (slot = contact id): B2/src/contact.h:41-71
-struct Contact
+// Contact bookkeeping (slot = contact id): B2/src/contact.h:41-71. The reference's isMarked is the kContactMarked bit of flags.
+constexpr uint32_t kContactMarked = 0x80000000u;
+struct alignas( 32 ) Contact
 {
-	int32_t setIndex, colorIndex, localIndex;
-	Edge edges[2];
+	// sector 0: what walking a body's contact list reads (pair finding, island split rows)
 	int32_t shapeIdA, shapeIdB;
+	Edge edges[2];
+	// sector 1
+	int32_t setIndex, colorIndex, localIndex;
 	int32_t islandPrev, islandNext, islandId;
 	int32_t contactId;
 	uint32_t flags;
-	bool isMarked;
 };
-// Hot contact data (stable slot = contact id): B2/src/contact.h:98-131
-struct ContactSim
+static_assert( sizeof( Contact ) == 64, "Contact layout" );
+// Contact simulation data (stable slot = contact id): B2/src/contact.h:98-131
+struct alignas( 16 ) ContactSim
 {
 	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
 	int32_t shapeIdA, shapeIdB;

@@ -697,7 +697,7 @@ F2D_HDF inline void splitIsland( World* w, int baseId )
 		bodies[id].isMarked = false;
 	}
 	for ( int id = base.headContact; id != kNull; id = contacts[id].islandNext )
-		contacts[id].isMarked = false;
+		contacts[id].flags &= ~kContactMarked;
 	for ( int id = base.headJoint; id != kNull; id = joints[id].islandNext )
 		joints[id].isMarked = false;
 
@@ -738,11 +738,11 @@ F2D_HDF inline void splitIsland( World* w, int baseId )
 				int edgeIndex = contactKey & 1;
 				Contact& contact = contacts[contactId];
 				contactKey = contact.edges[edgeIndex].nextKey;
-				if ( contact.isMarked )
+				if ( contact.flags & kContactMarked )
 					continue;
 				if ( ( contact.flags & kContactTouching ) == 0 )
 					continue;
-				contact.isMarked = true;
+				contact.flags |= kContactMarked;
 				int otherBodyId = contact.edges[edgeIndex ^ 1].bodyId;
 				Body& other = bodies[otherBodyId];
 				if ( other.isMarked == false && other.setIndex != kStaticSet )
@@ -1003,7 +1003,6 @@ F2D_HDF inline int createContact( World* w, int shapeIdA, int shapeIdB )
 	c.islandNext = kNull;
 	c.shapeIdA = shapeIdA;
 	c.shapeIdB = shapeIdB;
-	c.isMarked = false;
 	c.flags = 0;
 	if ( shapeA.enableContactEvents || shapeB.enableContactEvents )
 		c.flags |= kContactEnableContactEvents;

@@ -92,7 +92,7 @@ if "configs" in what:
     t = scenes.bench2d(lib)
     for _ in range(256):
         t.step()
-    for threads, bps in ((256, 2), (256, 4), (32, 32), (128, 8), (64, 16)):
+    for threads, bps in ((256, 4), (128, 8), (64, 16)):
         count = 148 * bps * (2 if threads <= 64 else 4)
         b = lib.f2dBatch_Create(t.world, count)
         assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
@@ -112,7 +112,7 @@ if "batchprofile" in what:
     for _ in range(256):
         t.step()
     lib.f2dWorld_EnableProfile(t.world, True)
-    for threads, bps, count in ((64, 16, 2368), (128, 8, 1184), (256, 2, 296)):
+    for threads, bps, count in ((64, 16, 2368), (128, 8, 1184), (256, 4, 592)):
         b = lib.f2dBatch_Create(t.world, count)
         assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
         steps = 8
@@ -139,3 +139,29 @@ if "profile" in what:
     profile("large_pyramid", {}, 0, 32, 32)
     profile("many_pyramids", {}, 1, 2, 16)
     profile("joint_grid", {}, 1, 8, 32)
+
+if "occupancy" in what:
+    # the same 128x8 kernel with 1, 2, 4, 8 worlds resident per SM: how much of a world's step time is contention
+    t = scenes.bench2d(lib)
+    for _ in range(256):
+        t.step()
+    lib.f2dWorld_EnableProfile(t.world, True)
+    for threads, bps, count in ((128, 8, 148), (128, 8, 296), (128, 8, 592), (128, 8, 1184), (128, 8, 2368), (256, 4, 148), (256, 4, 592)):
+        b = lib.f2dBatch_Create(t.world, count)
+        assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
+        steps = 8
+        lib.f2dBatch_EventRecord(b, 0)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, steps)
+        lib.f2dBatch_EventRecord(b, 1)
+        lib.f2dBatch_Synchronize(b)
+        ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
+        scratch = scenes.bench2d(lib, rows=1)
+        lib.f2dBatch_DownloadWorld(b, count // 2, scratch.world)
+        out = (C.c_ulonglong * 24)()
+        lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+        total = sum(out[:23]) / steps / 1e3
+        print("occupancy %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
+            threads, bps, count, ms, count / ms * 1e3, count // 2, total) +
+            " ".join("%s=%.1f" % (n, out[i] / steps / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
+        lib.f2dBatch_Destroy(b)
+        scratch.destroy()
