@@ -656,7 +656,7 @@ static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
 			for ( int k : order )
 			{
 				const ContactSim& sim = sims[ids[k]];
-				Manifold manifold = sim.manifold; // what the reference hands out: the raw result of the manifold function
+				Manifold manifold = unpackManifold( sim.manifold ); // what the reference hands out: the raw result of the manifold function
 				unparkOldImpulses( manifold );
 				b2ShapeId idA = { sim.shapeIdA + 1, w->worldId, shapes[sim.shapeIdA].generation };
 				b2ShapeId idB = { sim.shapeIdB + 1, w->worldId, shapes[sim.shapeIdB].generation };
@@ -1448,6 +1448,7 @@ int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
 			f2dContactRecord* r = out + n;
 			memset( r, 0, sizeof( *r ) );
 			const ContactSim& s = ptr( w, w->contactSims )[i];
+			const Manifold manifold = unpackManifold( s.manifold );
 			r->id = i;
 			r->shapeIdA = c.shapeIdA;
 			r->shapeIdB = c.shapeIdB;
@@ -1456,7 +1457,7 @@ int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
 			r->localIndex = c.localIndex;
 			r->flags = (int)( c.flags & ~kContactMarked );
 			r->simFlags = (int)s.simFlags;
-			r->pointCount = s.manifold.pointCount;
+			r->pointCount = manifold.pointCount;
 			r->islandId = c.islandId;
 			r->islandPrev = c.islandPrev;
 			r->islandNext = c.islandNext;
@@ -1466,11 +1467,11 @@ int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
 			r->nextKeyB = c.edges[1].nextKey;
 			r->bodySimIndexA = s.bodySimIndexA;
 			r->bodySimIndexB = s.bodySimIndexB;
-			r->nx = s.manifold.normal.x;
-			r->ny = s.manifold.normal.y;
-			for ( int k = 0; k < s.manifold.pointCount && k < 2; ++k )
+			r->nx = manifold.normal.x;
+			r->ny = manifold.normal.y;
+			for ( int k = 0; k < manifold.pointCount && k < 2; ++k )
 			{
-				const ManifoldPoint& mp = s.manifold.points[k];
+				const ManifoldPoint& mp = manifold.points[k];
 				if ( k == 0 )
 					r->id0 = mp.id;
 				else
@@ -1489,7 +1490,7 @@ int f2dDebug_Contacts( b2WorldId id, f2dContactRecord* out, int cap )
 			}
 			r->friction = s.friction;
 			r->restitution = s.restitution;
-			r->rollingImpulse = s.manifold.rollingImpulse;
+			r->rollingImpulse = manifold.rollingImpulse;
 		}
 		n += 1;
 	}

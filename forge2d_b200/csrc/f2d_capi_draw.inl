@@ -389,7 +389,7 @@ void drawWithBounds( World* w, b2DebugDraw* draw )
 						continue;
 					if ( ( contactBits[contactId >> 6] & ( 1ull << ( contactId & 63 ) ) ) == 0 ) // avoid double draw
 					{
-						drawManifold( draw, contactSims[contactId].manifold, contact.colorIndex, style );
+						drawManifold( draw, unpackManifold( contactSims[contactId].manifold ), contact.colorIndex, style );
 						contactBits[contactId >> 6] |= 1ull << ( contactId & 63 );
 					}
 				}
@@ -507,7 +507,7 @@ void b2World_Draw( b2WorldId worldId, b2DebugDraw* draw ) // world.c:1161-1489
 		{
 			const int32_t* list = ptr( w, w->colorContacts[colorIndex] );
 			for ( int i = 0; i < w->colorContacts[colorIndex].count; ++i )
-				drawManifold( draw, contactSims[list[i]].manifold, colorIndex, style );
+				drawManifold( draw, unpackManifold( contactSims[list[i]].manifold ), colorIndex, style );
 		}
 	}
 	if ( draw->drawIslands )

@@ -73,6 +73,21 @@ struct Box
 	V2 lo, hi;
 };
 
+// A 16-byte chunk moved with ONE memory instruction (LDG.128 / STG.128 on the device). The records of the world image
+// are laid out in such chunks (f2d_types.h), and every request to L2 costs the same whether it carries 4 or 16 bytes,
+// so the hot gathers read and write whole chunks instead of one field at a time. `p` must be 16-byte aligned.
+#if defined( __GNUC__ ) || defined( __CUDACC__ )
+#define F2D_MAY_ALIAS __attribute__( ( may_alias ) )
+#else
+#define F2D_MAY_ALIAS
+#endif
+struct alignas( 16 ) F2D_MAY_ALIAS Q4
+{
+	float x, y, z, w;
+};
+F2D_HD Q4 load16( const void* p ) { return *static_cast<const Q4*>( p ); }
+F2D_HD void store16( void* p, Q4 v ) { *static_cast<Q4*>( p ) = v; }
+
 F2D_HD uint32_t floatBits( float f )
 {
 #if defined( __CUDA_ARCH__ )

@@ -29,9 +29,12 @@ struct SolverBody
 {
 	V2 v;
 	float w;
+	float flagBits; // BodyState::flags as loaded: travels with v and w so that they go back in one 16-byte store
 	V2 dp;
 	Rot dq;
 };
+// The 32-byte state moves as two 16-byte chunks (v, w, flags | dp, dq). Inside a colour a non-static body belongs to
+// exactly one constraint, so the thread that gathers a state is the only one that writes it.
 F2D_HD SolverBody gatherBody( const BodyState* states, int index )
 {
 	SolverBody b;
@@ -39,53 +42,80 @@ F2D_HD SolverBody gatherBody( const BodyState* states, int index )
 	{
 		b.v = V2{ 0.0f, 0.0f };
 		b.w = 0.0f;
+		b.flagBits = 0.0f;
 		b.dp = V2{ 0.0f, 0.0f };
 		b.dq = Rot{ 1.0f, 0.0f };
 	}
 	else
 	{
 		const BodyState& s = states[index];
-		b.v = s.v;
-		b.w = s.w;
-		b.dp = s.dp;
-		b.dq = s.dq;
+		const Q4 lo = load16( &s.v ), hi = load16( &s.dp );
+		b.v = V2{ lo.x, lo.y };
+		b.w = lo.z;
+		b.flagBits = lo.w;
+		b.dp = V2{ hi.x, hi.y };
+		b.dq = Rot{ hi.z, hi.w };
+	}
+	return b;
+}
+// warm start and restitution do not read dp / dq
+F2D_HD SolverBody gatherBodyVelocity( const BodyState* states, int index )
+{
+	SolverBody b;
+	b.dp = V2{ 0.0f, 0.0f };
+	b.dq = Rot{ 1.0f, 0.0f };
+	if ( index == kNull )
+	{
+		b.v = V2{ 0.0f, 0.0f };
+		b.w = 0.0f;
+		b.flagBits = 0.0f;
+	}
+	else
+	{
+		const Q4 lo = load16( &states[index].v );
+		b.v = V2{ lo.x, lo.y };
+		b.w = lo.z;
+		b.flagBits = lo.w;
 	}
 	return b;
 }
 F2D_HD void scatterBody( BodyState* states, int index, const SolverBody& b )
 {
 	if ( index != kNull )
-	{
-		states[index].v = b.v;
-		states[index].w = b.w;
-	}
+		store16( &states[index].v, Q4{ b.v.x, b.v.y, b.w, b.flagBits } );
 }
 
 // contact_solver.c:1455-1616 (per lane) == :46-155 (overflow): identical formulas
 F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, int contactId, const BodyState* states, float warmStartScale )
 {
 	const ContactSim& sim = ptr( w, w->contactSims )[contactId];
-	const Manifold& m = sim.manifold;
-	int indexA = sim.bodySimIndexA, indexB = sim.bodySimIndexB;
+	// eight 16-byte chunks of the record: manifold M0-M4, then indices / material / masses
+	const Q4 m0 = load16( &sim.manifold.pointCount ), m1 = load16( &sim.manifold.normalImpulse0 ), m2 = load16( &sim.manifold.normal ),
+			 m3 = load16( &sim.manifold.anchorA0 ), m4 = load16( &sim.manifold.anchorA1 );
+	const Q4 k9 = load16( &sim.bodySimIndexA ), k10 = load16( &sim.invMassA ), k11 = load16( &sim.rollingResistance );
+	const int pointCount = (int)floatBits( m0.x );
+	const int indexA = (int)floatBits( k9.x ), indexB = (int)floatBits( k9.y );
 	c.i( cfIndexA, slot ) = indexA;
 	c.i( cfIndexB, slot ) = indexB;
-	c.i( cfPointCount, slot ) = m.pointCount;
+	c.i( cfPointCount, slot ) = pointCount;
 
 	V2 vA = { 0.0f, 0.0f };
 	float wA = 0.0f;
-	float mA = sim.invMassA, iA = sim.invIA;
+	float mA = k10.x, iA = k10.y;
 	if ( indexA != kNull )
 	{
-		vA = states[indexA].v;
-		wA = states[indexA].w;
+		const Q4 vw = load16( &states[indexA].v );
+		vA = V2{ vw.x, vw.y };
+		wA = vw.z;
 	}
 	V2 vB = { 0.0f, 0.0f };
 	float wB = 0.0f;
-	float mB = sim.invMassB, iB = sim.invIB;
+	float mB = k10.z, iB = k10.w;
 	if ( indexB != kNull )
 	{
-		vB = states[indexB].v;
-		wB = states[indexB].w;
+		const Q4 vw = load16( &states[indexB].v );
+		vB = V2{ vw.x, vw.y };
+		wB = vw.z;
 	}
 	c.f( cfInvMassA, slot ) = mA;
 	c.f( cfInvMassB, slot ) = mB;
@@ -96,29 +126,28 @@ F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, in
 		c.f( cfRollingMass, slot ) = k > 0.0f ? 1.0f / k : 0.0f;
 	}
 	Soft soft = ( indexA == kNull || indexB == kNull ) ? w->step.staticSoftness : w->step.contactSoftness;
-	V2 normal = m.normal;
+	V2 normal = { m2.x, m2.y };
 	c.f( cfNormalX, slot ) = normal.x;
 	c.f( cfNormalY, slot ) = normal.y;
-	c.f( cfFriction, slot ) = sim.friction;
-	c.f( cfTangentSpeed, slot ) = sim.tangentSpeed;
-	c.f( cfRestitution, slot ) = sim.restitution;
-	c.f( cfRollingResistance, slot ) = sim.rollingResistance;
-	c.f( cfRollingImpulse, slot ) = warmStartScale * m.rollingImpulse;
+	c.f( cfFriction, slot ) = k9.z;
+	c.f( cfTangentSpeed, slot ) = k11.y;
+	c.f( cfRestitution, slot ) = k9.w;
+	c.f( cfRollingResistance, slot ) = k11.x;
+	c.f( cfRollingImpulse, slot ) = warmStartScale * m0.z;
 	c.f( cfBiasRate, slot ) = soft.biasRate;
 	c.f( cfMassScale, slot ) = soft.massScale;
 	c.f( cfImpulseScale, slot ) = soft.impulseScale;
 
 	V2 tangent = rightPerp( normal );
 	{
-		const ManifoldPoint& mp = m.points[0];
-		V2 rA = mp.anchorA, rB = mp.anchorB;
+		V2 rA = { m3.x, m3.y }, rB = { m3.z, m3.w };
 		c.f( cfAnchorA1X, slot ) = rA.x;
 		c.f( cfAnchorA1Y, slot ) = rA.y;
 		c.f( cfAnchorB1X, slot ) = rB.x;
 		c.f( cfAnchorB1Y, slot ) = rB.y;
-		c.f( cfBaseSeparation1, slot ) = mp.separation - dot( sub( rB, rA ), normal );
-		c.f( cfNormalImpulse1, slot ) = warmStartScale * mp.normalImpulse;
-		c.f( cfTangentImpulse1, slot ) = warmStartScale * mp.tangentImpulse;
+		c.f( cfBaseSeparation1, slot ) = m2.z - dot( sub( rB, rA ), normal );
+		c.f( cfNormalImpulse1, slot ) = warmStartScale * m1.x;
+		c.f( cfTangentImpulse1, slot ) = warmStartScale * m1.y;
 		c.f( cfTotalNormalImpulse1, slot ) = 0.0f;
 		float rnA = cross( rA, normal );
 		float rnB = cross( rB, normal );
@@ -132,17 +161,16 @@ F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, in
 		V2 vrB = add( vB, crossSV( wB, rB ) );
 		c.f( cfRelativeVelocity1, slot ) = dot( normal, sub( vrB, vrA ) );
 	}
-	if ( m.pointCount == 2 )
+	if ( pointCount == 2 )
 	{
-		const ManifoldPoint& mp = m.points[1];
-		V2 rA = mp.anchorA, rB = mp.anchorB;
+		V2 rA = { m4.x, m4.y }, rB = { m4.z, m4.w };
 		c.f( cfAnchorA2X, slot ) = rA.x;
 		c.f( cfAnchorA2Y, slot ) = rA.y;
 		c.f( cfAnchorB2X, slot ) = rB.x;
 		c.f( cfAnchorB2Y, slot ) = rB.y;
-		c.f( cfBaseSeparation2, slot ) = mp.separation - dot( sub( rB, rA ), normal );
-		c.f( cfNormalImpulse2, slot ) = warmStartScale * mp.normalImpulse;
-		c.f( cfTangentImpulse2, slot ) = warmStartScale * mp.tangentImpulse;
+		c.f( cfBaseSeparation2, slot ) = m2.w - dot( sub( rB, rA ), normal );
+		c.f( cfNormalImpulse2, slot ) = warmStartScale * m1.z;
+		c.f( cfTangentImpulse2, slot ) = warmStartScale * m1.w;
 		c.f( cfTotalNormalImpulse2, slot ) = 0.0f;
 		float rnA = cross( rA, normal );
 		float rnB = cross( rB, normal );
@@ -187,8 +215,8 @@ F2D_HD void applyImpulse( SolverBody& bA, SolverBody& bB, float mA, float iA, fl
 F2D_HDF inline void warmStartSlot( const ConView& c, int slot, BodyState* states )
 {
 	int indexA = c.i( cfIndexA, slot ), indexB = c.i( cfIndexB, slot );
-	SolverBody bA = gatherBody( states, indexA );
-	SolverBody bB = gatherBody( states, indexB );
+	SolverBody bA = gatherBodyVelocity( states, indexA );
+	SolverBody bB = gatherBodyVelocity( states, indexB );
 	float nx = c.f( cfNormalX, slot ), ny = c.f( cfNormalY, slot );
 	float tx = ny;
 	float ty = 0.0f - nx;
@@ -354,8 +382,8 @@ F2D_HDF inline void restitutionSlot( const ConView& c, int slot, BodyState* stat
 	float restitution = c.f( cfRestitution, slot );
 	bool restitutionMask = restitution == 0.0f;
 	int indexA = c.i( cfIndexA, slot ), indexB = c.i( cfIndexB, slot );
-	SolverBody bA = gatherBody( states, indexA );
-	SolverBody bB = gatherBody( states, indexB );
+	SolverBody bA = gatherBodyVelocity( states, indexA );
+	SolverBody bB = gatherBodyVelocity( states, indexB );
 	float nx = c.f( cfNormalX, slot ), ny = c.f( cfNormalY, slot );
 	float mA = c.f( cfInvMassA, slot ), iA = c.f( cfInvIA, slot );
 	float mB = c.f( cfInvMassB, slot ), iB = c.f( cfInvIB, slot );
@@ -373,10 +401,11 @@ F2D_HDF inline void restitutionSlot( const ConView& c, int slot, BodyState* stat
 		float dvy = ( bB.v.y + bB.w * rB.x ) - ( bA.v.y + bA.w * rA.x );
 		float vn = dvx * nx + dvy * ny;
 		float negImpulse = mass * ( vn + restitution * relativeVelocity );
-		float& normalImpulse = c.f( p == 0 ? cfNormalImpulse1 : cfNormalImpulse2, slot );
+		const int impulseField = p == 0 ? cfNormalImpulse1 : cfNormalImpulse2;
+		float normalImpulse = c.f( impulseField, slot );
 		float newImpulse = maxf( normalImpulse - negImpulse, 0.0f );
 		float impulse = newImpulse - normalImpulse;
-		normalImpulse = newImpulse;
+		c.f( impulseField, slot ) = newImpulse;
 		float Px = impulse * nx;
 		float Py = impulse * ny;
 		applyImpulse( bA, bB, mA, iA, mB, iB, rA, rB, Px, Py );
@@ -388,22 +417,31 @@ F2D_HDF inline void restitutionSlot( const ConView& c, int slot, BodyState* stat
 // contact_solver.c:2078-2120 (and :480-509 for overflow: only the first pointCount points are written there)
 F2D_HD void storeSlot( World* w, const ConView& c, int slot, int contactId, bool overflow )
 {
-	Manifold& m = ptr( w, w->contactSims )[contactId].manifold;
+	StoredManifold& m = ptr( w, w->contactSims )[contactId].manifold;
 	m.rollingImpulse = c.f( cfRollingImpulse, slot );
-	int n = overflow ? m.pointCount : 2;
+	if ( overflow == false )
+	{
+		// both points, whatever the point count: two whole chunks (M1: impulses, M6: total impulses and normal velocities)
+		store16( &m.normalImpulse0, Q4{ c.f( cfNormalImpulse1, slot ), c.f( cfTangentImpulse1, slot ), c.f( cfNormalImpulse2, slot ),
+										c.f( cfTangentImpulse2, slot ) } );
+		store16( &m.totalNormalImpulse0, Q4{ c.f( cfTotalNormalImpulse1, slot ), c.f( cfTotalNormalImpulse2, slot ),
+											 c.f( cfRelativeVelocity1, slot ), c.f( cfRelativeVelocity2, slot ) } );
+		return;
+	}
+	int n = m.pointCount;
 	if ( n > 0 )
 	{
-		m.points[0].normalImpulse = c.f( cfNormalImpulse1, slot );
-		m.points[0].tangentImpulse = c.f( cfTangentImpulse1, slot );
-		m.points[0].totalNormalImpulse = c.f( cfTotalNormalImpulse1, slot );
-		m.points[0].normalVelocity = c.f( cfRelativeVelocity1, slot );
+		m.normalImpulse0 = c.f( cfNormalImpulse1, slot );
+		m.tangentImpulse0 = c.f( cfTangentImpulse1, slot );
+		m.totalNormalImpulse0 = c.f( cfTotalNormalImpulse1, slot );
+		m.normalVelocity0 = c.f( cfRelativeVelocity1, slot );
 	}
 	if ( n > 1 )
 	{
-		m.points[1].normalImpulse = c.f( cfNormalImpulse2, slot );
-		m.points[1].tangentImpulse = c.f( cfTangentImpulse2, slot );
-		m.points[1].totalNormalImpulse = c.f( cfTotalNormalImpulse2, slot );
-		m.points[1].normalVelocity = c.f( cfRelativeVelocity2, slot );
+		m.normalImpulse1 = c.f( cfNormalImpulse2, slot );
+		m.tangentImpulse1 = c.f( cfTangentImpulse2, slot );
+		m.totalNormalImpulse1 = c.f( cfTotalNormalImpulse2, slot );
+		m.normalVelocity1 = c.f( cfRelativeVelocity2, slot );
 	}
 }
 

@@ -367,18 +367,21 @@ F2D_HDF inline void collideContact( World* w, int contactId, int workIndex )
 	const BodySim* sims = ptr( w, w->sims );
 	uint64_t* bits = ptr( w, w->contactBits );
 	// ---- round 1: the contact record
-	const int shapeIdA = sim.shapeIdA, shapeIdB = sim.shapeIdB;
-	const int bodyIdA = sim.bodyIdA, bodyIdB = sim.bodyIdB;
-	uint32_t simFlags = sim.simFlags;
+	// (four 16-byte chunks = the first two sectors of the record: ids | flags | manifold M0 | M1)
+	const Q4 k0 = load16( &sim.shapeIdA ), k1 = load16( &sim.simFlags ), m0 = load16( &sim.manifold.pointCount ),
+			 m1 = load16( &sim.manifold.normalImpulse0 );
+	const int shapeIdA = (int)floatBits( k0.x ), shapeIdB = (int)floatBits( k0.y );
+	const int bodyIdA = (int)floatBits( k0.z ), bodyIdB = (int)floatBits( k0.w );
+	uint32_t simFlags = floatBits( k1.x );
 	OldImpulses old;
-	old.pointCount = sim.manifold.pointCount;
-	old.rollingImpulse = sim.manifold.rollingImpulse;
-	old.id[0] = sim.manifold.points[0].id;
-	old.id[1] = sim.manifold.points[1].id;
-	old.normalImpulse[0] = sim.manifold.points[0].normalImpulse;
-	old.normalImpulse[1] = sim.manifold.points[1].normalImpulse;
-	old.tangentImpulse[0] = sim.manifold.points[0].tangentImpulse;
-	old.tangentImpulse[1] = sim.manifold.points[1].tangentImpulse;
+	old.pointCount = (int32_t)floatBits( m0.x );
+	old.rollingImpulse = m0.z;
+	old.id[0] = (uint16_t)( floatBits( m0.y ) & 0xffffu );
+	old.id[1] = (uint16_t)( floatBits( m0.y ) >> 16 );
+	old.normalImpulse[0] = m1.x;
+	old.tangentImpulse[0] = m1.y;
+	old.normalImpulse[1] = m1.z;
+	old.tangentImpulse[1] = m1.w;
 	// ---- round 2: everything the ids lead to
 	const Shape& shapeA = shapes[shapeIdA];
 	const Shape& shapeB = shapes[shapeIdB];
@@ -393,10 +396,6 @@ F2D_HDF inline void collideContact( World* w, int contactId, int workIndex )
 	const V2 localCenterA = simA.localCenter, localCenterB = simB.localCenter;
 	const float invMassA = simA.invMass, invIA = simA.invInertia;
 	const float invMassB = simB.invMass, invIB = simB.invInertia;
-	prefetchLine( &shapeA.polygon );
-	prefetchLine( &shapeA.polygon.n[0] );
-	prefetchLine( &shapeB.polygon );
-	prefetchLine( &shapeB.polygon.n[0] );
 
 	bool overlap = boxOverlaps( fatA, fatB );
 	if ( overlap == false )
@@ -407,11 +406,8 @@ F2D_HDF inline void collideContact( World* w, int contactId, int workIndex )
 	}
 	bool wasTouching = ( simFlags & kSimTouching ) != 0;
 	sim.bodySimIndexA = setA == kAwakeSet ? localA : kNull;
-	sim.invMassA = invMassA;
-	sim.invIA = invIA;
 	sim.bodySimIndexB = setB == kAwakeSet ? localB : kNull;
-	sim.invMassB = invMassB;
-	sim.invIB = invIB;
+	store16( &sim.invMassA, Q4{ invMassA, invIA, invMassB, invIB } );
 	V2 centerOffsetA = rotate( xfA.q, localCenterA );
 	V2 centerOffsetB = rotate( xfB.q, localCenterB );
 	bool touching = updateContact( w, sim, simFlags, old, shapeA, xfA, centerOffsetA, shapeB, xfB, centerOffsetB );
@@ -445,7 +441,7 @@ F2D_HDF inline void finishDeferredContact( World* w, int contactId, bool approve
 	const BodySim* sims = ptr( w, w->sims );
 	uint32_t simFlags = sim.simFlags & ~kSimPendingPreSolve;
 	const bool wasTouching = ( simFlags & kSimTouching ) != 0;
-	Manifold m = sim.manifold;
+	Manifold m = unpackManifold( sim.manifold );
 	OldImpulses old = unparkOldImpulses( m );
 	const Shape& shapeA = shapes[sim.shapeIdA];
 	const Shape& shapeB = shapes[sim.shapeIdB];
@@ -487,7 +483,7 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 			BeginTouchEvent ev;
 			ev.a = makeShapeId( w, shapeA );
 			ev.b = makeShapeId( w, shapeB );
-			ev.manifold = sim.manifold;
+			ev.manifold = unpackManifold( sim.manifold );
 			F2D_PUSH( w, w->beginEvents, ev );
 		}
 		c.flags |= kContactTouching;
@@ -631,22 +627,11 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 			}
 			return list[i - segStart];
 		};
-		// A contact is a chain of dependent gathers (id -> contact record -> shapes / bodies / body sims) and a thread
-		// owns several contacts: while one is processed, the record of the thread's next contact is requested into L2.
-		const ContactSim* csims = ptr( w, w->contactSims );
-		int id0 = contactAt( rank );
+		// A contact is a chain of dependent gathers (id -> contact record -> shapes / bodies / body sims). No prefetch of
+		// the thread's next record: in a batch this phase keeps DRAM busy 96 % of the time (profiles/README.md, r02k), and a
+		// prefetch moves whole 128-byte lines where the gathers touch single sectors.
 		for ( int i = rank; i < total; i += size )
-		{
-			int id1 = contactAt( i + size );
-			if ( id1 != kNull )
-			{
-				const ContactSim& n = csims[id1];
-				prefetchL2( &n );
-				prefetchL2( &n.manifold.points[1] );
-			}
-			collideContact( w, id0, i );
-			id0 = id1;
-		}
+			collideContact( w, contactAt( i ), i );
 	};
 	if ( part != kCollideNarrowOnly )
 	{
@@ -696,8 +681,9 @@ F2D_HDF inline void integrateVelocity( World* w, int awakeIndex, float h, float 
 	BodyState& state = ptr( w, w->states )[awakeIndex];
 	const float* c = ptr( w, w->integ ) + awakeIndex;
 	const int stride = w->integ.cap / 6;
-	V2 v = state.v;
-	float wv = state.w;
+	const Q4 vw = load16( &state.v ); // v, w, flags
+	V2 v = { vw.x, vw.y };
+	float wv = vw.z;
 	float maxLinearSpeedSquared = maxLinearSpeed * maxLinearSpeed;
 	float maxAngularSpeedSquared = maxAngularSpeed * maxAngularSpeed;
 	V2 linearVelocityDelta = { c[0], c[stride] };
@@ -721,15 +707,16 @@ F2D_HDF inline void integrateVelocity( World* w, int awakeIndex, float h, float 
 	}
 	if ( capped )
 		ptr( w, w->sims )[ptr( w, w->awakeBodies )[awakeIndex]].isSpeedCapped = true;
-	state.v = v;
-	state.w = wv;
+	store16( &state.v, Q4{ v.x, v.y, wv, vw.w } );
 }
 
 // solver.c:182-199
 F2D_HD void integratePosition( BodyState& state, float h )
 {
-	state.dq = integrateRot( state.dq, h * state.w );
-	state.dp = mulAdd( state.dp, h, state.v );
+	const Q4 vw = load16( &state.v ), pq = load16( &state.dp );
+	const Rot dq = integrateRot( Rot{ pq.z, pq.w }, h * vw.z );
+	const V2 dp = mulAdd( V2{ pq.x, pq.y }, h, V2{ vw.x, vw.y } );
+	store16( &state.dp, Q4{ dp.x, dp.y, dq.c, dq.s } );
 }
 
 // Colour-parallel constraint stage: joints and contacts of colour `color` (independent inside a colour,
@@ -1432,7 +1419,7 @@ template <class Team> F2D_HDF inline void solveStages( World* w, Team& t )
 			{
 				const ContactSim& n = csims[list[slot + t.size() - colorStart]];
 				prefetchL2( &n );
-				prefetchL2( &n.manifold.points[1] );
+				prefetchL2( &n.manifold.point0 );
 			}
 			prepareContactSlot( w, c, slot, list[slot - colorStart], states, warmStartScale );
 		}
@@ -2237,9 +2224,10 @@ F2D_HDF inline void reportHitEvents( World* w )
 			memset( &ev, 0, sizeof( ev ) );
 			ev.approachSpeed = threshold;
 			bool hit = false;
-			for ( int k = 0; k < sim.manifold.pointCount; ++k )
+			const Manifold manifold = unpackManifold( sim.manifold );
+			for ( int k = 0; k < manifold.pointCount; ++k )
 			{
-				const ManifoldPoint& mp = sim.manifold.points[k];
+				const ManifoldPoint& mp = manifold.points[k];
 				float approachSpeed = -mp.normalVelocity;
 				if ( approachSpeed > ev.approachSpeed && mp.totalNormalImpulse > 0.0f )
 				{
@@ -2250,7 +2238,7 @@ F2D_HDF inline void reportHitEvents( World* w )
 			}
 			if ( hit )
 			{
-				ev.normal = sim.manifold.normal;
+				ev.normal = manifold.normal;
 				ev.a = makeShapeId( w, shapes[sim.shapeIdA] );
 				ev.b = makeShapeId( w, shapes[sim.shapeIdB] );
 				F2D_PUSH( w, w->hitEvents, ev );

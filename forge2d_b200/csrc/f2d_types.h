@@ -284,19 +284,88 @@ struct alignas( 32 ) Contact
 	uint32_t flags;
 };
 static_assert( sizeof( Contact ) == 64, "Contact layout" );
-// Contact simulation data (stable slot = contact id): B2/src/contact.h:98-131
-struct alignas( 16 ) ContactSim
+// The manifold of a contact as it is STORED (the compute type, and the layout the public API hands out, is Manifold):
+// the same 112 bytes regrouped into seven 16-byte chunks by who reads them together. The narrowphase needs chunks M0 and
+// M1 of the previous step (feature ids and accumulated impulses, contact.c:552-586), prepare M0-M4, the impulse store
+// writes M1 and M6, hit events read M2, M5 and M6.
+struct alignas( 16 ) StoredManifold
 {
-	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
+	int32_t pointCount;																  // M0
+	uint32_t ids; // points[0].id | points[1].id << 16
+	float rollingImpulse;
+	uint32_t persisted; // bit k: points[k].persisted
+	float normalImpulse0, tangentImpulse0, normalImpulse1, tangentImpulse1;			  // M1
+	V2 normal;																		  // M2
+	float separation0, separation1;
+	V2 anchorA0, anchorB0;															  // M3
+	V2 anchorA1, anchorB1;															  // M4
+	V2 point0, point1;																  // M5
+	float totalNormalImpulse0, totalNormalImpulse1, normalVelocity0, normalVelocity1; // M6
+};
+static_assert( sizeof( StoredManifold ) == 112, "StoredManifold layout" );
+F2D_HD void packManifold( StoredManifold& s, const Manifold& m )
+{
+	const ManifoldPoint& p0 = m.points[0];
+	const ManifoldPoint& p1 = m.points[1];
+	const uint32_t ids = (uint32_t)p0.id | ( (uint32_t)p1.id << 16 );
+	const uint32_t persisted = ( p0.persisted ? 1u : 0u ) | ( p1.persisted ? 2u : 0u );
+	store16( &s.pointCount, Q4{ floatFromBits( (uint32_t)m.pointCount ), floatFromBits( ids ), m.rollingImpulse, floatFromBits( persisted ) } );
+	store16( &s.normalImpulse0, Q4{ p0.normalImpulse, p0.tangentImpulse, p1.normalImpulse, p1.tangentImpulse } );
+	store16( &s.normal, Q4{ m.normal.x, m.normal.y, p0.separation, p1.separation } );
+	store16( &s.anchorA0, Q4{ p0.anchorA.x, p0.anchorA.y, p0.anchorB.x, p0.anchorB.y } );
+	store16( &s.anchorA1, Q4{ p1.anchorA.x, p1.anchorA.y, p1.anchorB.x, p1.anchorB.y } );
+	store16( &s.point0, Q4{ p0.point.x, p0.point.y, p1.point.x, p1.point.y } );
+	store16( &s.totalNormalImpulse0, Q4{ p0.totalNormalImpulse, p1.totalNormalImpulse, p0.normalVelocity, p1.normalVelocity } );
+}
+F2D_HD Manifold unpackManifold( const StoredManifold& s )
+{
+	const Q4 m0 = load16( &s.pointCount ), m1 = load16( &s.normalImpulse0 ), m2 = load16( &s.normal ), m3 = load16( &s.anchorA0 ),
+			 m4 = load16( &s.anchorA1 ), m5 = load16( &s.point0 ), m6 = load16( &s.totalNormalImpulse0 );
+	const uint32_t ids = floatBits( m0.y ), persisted = floatBits( m0.w );
+	Manifold m;
+	memset( &m, 0, sizeof( m ) ); // padding bytes too: manifolds are copied into event records
+	m.normal = V2{ m2.x, m2.y };
+	m.rollingImpulse = m0.z;
+	m.pointCount = (int32_t)floatBits( m0.x );
+	ManifoldPoint& p0 = m.points[0];
+	ManifoldPoint& p1 = m.points[1];
+	p0.point = V2{ m5.x, m5.y };
+	p1.point = V2{ m5.z, m5.w };
+	p0.anchorA = V2{ m3.x, m3.y };
+	p0.anchorB = V2{ m3.z, m3.w };
+	p1.anchorA = V2{ m4.x, m4.y };
+	p1.anchorB = V2{ m4.z, m4.w };
+	p0.separation = m2.z;
+	p1.separation = m2.w;
+	p0.normalImpulse = m1.x;
+	p0.tangentImpulse = m1.y;
+	p1.normalImpulse = m1.z;
+	p1.tangentImpulse = m1.w;
+	p0.totalNormalImpulse = m6.x;
+	p1.totalNormalImpulse = m6.y;
+	p0.normalVelocity = m6.z;
+	p1.normalVelocity = m6.w;
+	p0.id = (uint16_t)( ids & 0xffffu );
+	p1.id = (uint16_t)( ids >> 16 );
+	p0.persisted = ( persisted & 1u ) != 0;
+	p1.persisted = ( persisted & 2u ) != 0;
+	return m;
+}
+// Contact simulation data (stable slot = contact id): B2/src/contact.h:98-131. Sector 0 and 1 are all the narrowphase
+// reads of a contact before it runs the manifold function.
+struct alignas( 32 ) ContactSim
+{
 	int32_t shapeIdA, shapeIdB;
-	float invMassA, invIA, invMassB, invIB;
 	int32_t bodyIdA, bodyIdB; // owners of the two shapes (ours: saves the shape -> body hop of the narrowphase gather)
-	int32_t pad0, pad1;
-	Manifold manifold;
-	float friction, restitution, rollingResistance, tangentSpeed;
 	uint32_t simFlags;
 	SimplexCache cache;
-	int32_t pad2; // 192 bytes: records start on 16-byte boundaries
+	int32_t pad0;
+	StoredManifold manifold;
+	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
+	float friction, restitution;
+	float invMassA, invIA, invMassB, invIB;
+	float rollingResistance, tangentSpeed;
+	int32_t pad1, pad2;
 };
 static_assert( sizeof( ContactSim ) == 192, "ContactSim layout" );
 // B2/src/sensor.h:11-24. The two overlap lists of a sensor are fixed-capacity blocks of World::sensorRefs

@@ -1041,6 +1041,7 @@ F2D_HDF inline int createContact( World* w, int shapeIdA, int shapeIdB )
 	sim.bodyIdB = shapeB.bodyId;
 	sim.pad0 = 0;
 	sim.pad1 = 0;
+	sim.pad2 = 0;
 	memset( &sim.cache, 0, sizeof( sim.cache ) );
 	memset( &sim.manifold, 0, sizeof( sim.manifold ) );
 	sim.friction = sqrtf( shapeA.friction * shapeB.friction );			  // world.c:88-92 default mixing
@@ -1185,7 +1186,7 @@ F2D_HDF inline bool finishContactUpdate( World* w, ContactSim& sim, uint32_t& si
 			}
 		}
 	}
-	sim.manifold = m;
+	packManifold( sim.manifold, m );
 
 	if ( touching )
 		simFlags |= kSimTouching;
@@ -1254,7 +1255,7 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags
 	if ( touching && ( w->hostCallbacks & kHostPreSolve ) != 0 && ( simFlags & kSimEnablePreSolve ) != 0 )
 	{
 		parkOldImpulses( m, old );
-		sim.manifold = m;
+		packManifold( sim.manifold, m );
 		simFlags |= kSimPendingPreSolve;
 		return false; // not decided yet: the caller must not derive a touching transition
 	}

@@ -146,7 +146,7 @@ if "occupancy" in what:
     for _ in range(256):
         t.step()
     lib.f2dWorld_EnableProfile(t.world, True)
-    for threads, bps, count in ((128, 8, 148), (128, 8, 296), (128, 8, 592), (128, 8, 1184), (128, 8, 2368), (256, 4, 148), (256, 4, 592)):
+    for threads, bps, count in ((128, 8, 148), (128, 8, 296), (128, 8, 592), (128, 8, 1184), (128, 8, 2368), (256, 4, 148), (128, 4, 592)):
         b = lib.f2dBatch_Create(t.world, count)
         assert lib.f2dBatch_SetLaunchConfig(b, threads, bps)
         steps = 8
