@@ -1923,37 +1923,54 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 	int bodyId = ptr( w, w->awakeBodies )[simIndex];
 	BodySim& sim = ptr( w, w->sims )[bodyId];
 	Body& body = ptr( w, w->bodies )[bodyId];
+	// The whole gather in 16-byte chunks, all issued before the first use: the state (2), the three sectors of the
+	// simulation record (5, the sixth chunk holds only flags) and sector 1 of the body record (2).
+	const Q4 stLo = load16( &state.v ), stHi = load16( &state.dp );
+	const Q4 sXf = load16( &sim.transform ), sLc = load16( &sim.localCenter ), sCen = load16( &sim.center ),
+			 sExt = load16( &sim.rotation0 );
+	const Q4 bIsl = load16( &body.islandId );
+	const int headShapeId = (int)floatBits( bIsl.y );
 	{
 		// the island and the first shape are needed at the end of this routine: start fetching them now, so that the
 		// body -> island and body -> shape hops overlap with the arithmetic instead of following it
-		const int islandId = body.islandId, headShapeId = body.headShapeId;
+		const int islandId = (int)floatBits( bIsl.x );
 		prefetchLine( ptr( w, w->islands ) + islandId );
 		const char* shapeBytes = reinterpret_cast<const char*>( ptr( w, w->shapes ) + headShapeId );
 		prefetchLine( shapeBytes );
-		prefetchLine( shapeBytes + 128 );
-		prefetchLine( shapeBytes + 256 );
+		prefetchLine( shapeBytes + 96 ); // polygon vertices
+		prefetchLine( shapeBytes + 224 ); // radius, count
 	}
 	const float timeStep = w->step.dt;
 	const float invTimeStep = w->step.inv_dt;
 
-	V2 v = state.v;
-	float wv = state.w;
-	sim.center = add( sim.center, state.dp );
-	sim.transform.q = normalizeRot( mulRot( state.dq, sim.transform.q ) );
-	float maxVelocity = length( v ) + absf( wv ) * sim.maxExtent;
-	float maxDeltaPosition = length( state.dp ) + absf( state.dq.s ) * sim.maxExtent;
+	const V2 v = { stLo.x, stLo.y };
+	const float wv = stLo.z;
+	const V2 dp = { stHi.x, stHi.y };
+	const Rot dq = { stHi.z, stHi.w };
+	const V2 localCenter = { sLc.x, sLc.y };
+	const float minExtent = sExt.z, maxExtent = sExt.w;
+	const V2 center = add( V2{ sCen.x, sCen.y }, dp );
+	Xf transform;
+	transform.q = normalizeRot( mulRot( dq, Rot{ sXf.z, sXf.w } ) );
+	float maxVelocity = length( v ) + absf( wv ) * maxExtent;
+	float maxDeltaPosition = length( dp ) + absf( dq.s ) * maxExtent;
 	float positionSleepFactor = 0.5f;
 	float sleepVelocity = maxf( maxVelocity, positionSleepFactor * invTimeStep * maxDeltaPosition );
-	state.dp = V2{ 0.0f, 0.0f };
-	state.dq = Rot{ 1.0f, 0.0f };
-	sim.transform.p = sub( sim.center, rotate( sim.transform.q, sim.localCenter ) );
+	store16( &state.dp, Q4{ 0.0f, 0.0f, 1.0f, 0.0f } );
+	transform.p = sub( center, rotate( transform.q, localCenter ) );
+	store16( &sim.transform, Q4{ transform.p.x, transform.p.y, transform.q.c, transform.q.s } );
+	sim.center = center;
 
 	body.bodyMoveIndex = simIndex;
-	BodyMoveEvent& ev = ptr( w, w->moveEvents )[simIndex];
-	ev.transform = sim.transform;
-	ev.bodyId = BodyId{ bodyId + 1, w->worldId, body.generation };
-	ev.userData = body.userData;
-	ev.fellAsleep = false;
+	{
+		// 40-byte record (types.h:1136-1142): two 16-byte chunks and the flag word (records are 8-byte aligned)
+		BodyMoveEvent ev;
+		ev.transform = transform;
+		ev.bodyId = BodyId{ bodyId + 1, w->worldId, body.generation };
+		ev.userData = body.userData;
+		ev.fellAsleep = false;
+		ptr( w, w->moveEvents )[simIndex] = ev;
+	}
 
 	sim.force = V2{ 0.0f, 0.0f };
 	sim.torque = 0.0f;
@@ -1964,7 +1981,7 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 	if ( w->enableSleep == false || body.enableSleep == false || sleepVelocity > body.sleepThreshold )
 	{
 		body.sleepTime = 0.0f;
-		if ( body.type == kDynamicBody && w->enableContinuous && maxVelocity * timeStep > 0.5f * sim.minExtent )
+		if ( body.type == kDynamicBody && w->enableContinuous && maxVelocity * timeStep > 0.5f * minExtent )
 		{
 			sim.isFast = true;
 			if ( sim.isBullet )
@@ -1989,14 +2006,14 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 		}
 		else
 		{
-			sim.center0 = sim.center;
-			sim.rotation0 = sim.transform.q;
+			sim.center0 = center;
+			sim.rotation0 = transform.q;
 		}
 	}
 	else
 	{
-		sim.center0 = sim.center;
-		sim.rotation0 = sim.transform.q;
+		sim.center0 = center;
+		sim.rotation0 = transform.q;
 		body.sleepTime += timeStep;
 	}
 
@@ -2031,7 +2048,8 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 	// box is written here, where the shape record is at hand, and the key is parked by awake index, so that pass does
 	// not have to walk body -> shape again. Other bodies (and fast bullets, whose boxes are not final yet) are marked
 	// kEnlargeByList and go through the shape-list walk of stepFinalize.
-	const bool single = body.shapeCount == 1 && ( sim.isBullet && isFast ) == false;
+	// (one shape: the head of the list has no successor - read from the shape record, which is needed anyway)
+	const bool single = body.headShapeId != kNull && shapes[body.headShapeId].nextShapeId == kNull && ( sim.isBullet && isFast ) == false;
 	int parkedKey = single ? kNull : kEnlargeByList;
 	int shapeId = body.headShapeId;
 	while ( shapeId != kNull )

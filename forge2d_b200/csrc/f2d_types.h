@@ -168,22 +168,25 @@ struct SensorEvent
 // Body data apart from the simulation record: B2/src/body.h:14-64
 struct alignas( 32 ) Body
 {
-	// sector 0: narrowphase (setIndex, localIndex) and pair finding (contact / joint lists, type)
+	// sector 0: narrowphase (setIndex, localIndex) and pair finding (contact / joint lists)
 	int32_t setIndex, localIndex; // localIndex = position in the owning set's id list
 	int32_t headContactKey, contactCount;
 	int32_t headJointKey, jointCount;
-	int32_t type, id;
-	// sector 1: finalize (island vote, sleep, shape list, move event)
-	int32_t islandId, headShapeId, shapeCount;
+	int32_t id, shapeCount;
+	// sector 1: everything finalize reads and writes of this record (island vote, sleep, shape list, move event)
+	int32_t islandId, headShapeId;
 	float sleepThreshold, sleepTime;
-	uint16_t generation;
-	uint16_t colorMask; // per-colour membership bits (replaces the per-colour body bitsets, constraint_graph.h:24-42)
 	uint64_t userData;
+	uint16_t generation;
+	int8_t type;
+	bool enableSleep : 1, isSpeedCapped : 1, fixedRotation : 1, isMarked : 1;
+	int32_t bodyMoveIndex;
 	// sector 2
-	int32_t bodyMoveIndex, islandPrev, islandNext, headChainId;
+	int32_t islandPrev, islandNext, headChainId;
 	float mass, inertia;
-	bool enableSleep, fixedRotation, isSpeedCapped, isMarked;
-	int32_t pad0;
+	uint16_t colorMask; // per-colour membership bits (replaces the per-colour body bitsets, constraint_graph.h:24-42)
+	uint16_t pad0;
+	int32_t pad1[2];
 	// sector 3
 	char name[32];
 };
