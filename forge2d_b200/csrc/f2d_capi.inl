@@ -716,7 +716,7 @@ static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
 			for ( int simIndex : order )
 			{
 				solveContinuous( w, simIndex );
-				finalizeBodyTail( w, simIndex );
+				finalizeBodyTail( w, simIndex ); // (the island vote of a deferred body was cast by the device loop)
 			}
 		} );
 	}

@@ -50,6 +50,12 @@ struct CtaTeam
 	__device__ int groupSize() const { return 32; }
 	__device__ void groupSync() const { __syncwarp(); }
 	int32_t* smem; // blockDim.x + 32 ints of shared scratch
+	// Dynamic shared memory the block may use as a work area (0 in batches, where the resident worlds of an SM live on
+	// its L1; a single small world has the SM - and its 228 KB - to itself)
+	int32_t* arena = nullptr;
+	int arenaInts = 0;
+	__device__ int32_t* arenaPtr() const { return arena; }
+	__device__ int arenaSize() const { return arenaInts; }
 	__device__ int rank() const { return (int)threadIdx.x; }
 	__device__ int size() const { return (int)blockDim.x; }
 	__device__ void sync() const { __syncthreads(); }
@@ -171,6 +177,8 @@ struct GridTeam
 	int32_t* blockTotals; // gridDim.x ints in global memory
 	GridBarrier* barrier;
 	unsigned int gen; // arrivals expected once the next barrier completes (meaningful in thread 0)
+	__device__ int32_t* arenaPtr() const { return nullptr; }
+	__device__ int arenaSize() const { return 0; }
 	__device__ int rank() const { return (int)( blockIdx.x * blockDim.x + threadIdx.x ); }
 	__device__ int size() const { return (int)( gridDim.x * blockDim.x ); }
 	__device__ void begin()
@@ -237,11 +245,17 @@ template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& 
 // World header held in shared memory (see World::deviceBase) and writes it back when the world is done.
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__( kThreads, kMinBlocks )
-	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps )
+	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps, int arenaBytes )
 {
 	__shared__ int32_t smem[64];
 	__shared__ uint4 header[sizeof( World ) / 16];
+	extern __shared__ int4 dynamicShared[];
 	CtaTeam team{ smem };
+	if ( arenaBytes > 0 )
+	{
+		team.arena = reinterpret_cast<int32_t*>( dynamicShared );
+		team.arenaInts = arenaBytes / 4;
+	}
 	World* w = reinterpret_cast<World*>( header );
 	for ( int wi = (int)blockIdx.x; wi < worldCount; wi += (int)gridDim.x )
 	{

@@ -2,6 +2,8 @@
 // SM's L1/L2), plus the batch gather kernels. The cooperative-grid kernel for large worlds is in f2d_kernels_grid.cu.
 #include "f2d_kernels.cuh"
 
+#include <stdlib.h>
+
 namespace f2d
 {
 
@@ -40,9 +42,31 @@ __global__ void gatherErrors( const char* base, unsigned long long stride, int w
 
 constexpr int kSingleCtaThreads = 1024;
 
+// The one-block kernel gets a shared-memory work area (CtaTeam::arena): the block has the SM to itself.
+static int singleCtaArenaBytes()
+{
+	static int bytes = -1;
+	if ( bytes < 0 )
+	{
+		const char* kb = getenv( "F2D_SINGLE_ARENA_KB" ); // tuning aid
+		bytes = ( kb != nullptr ? atoi( kb ) : 96 ) * 1024;
+		if ( bytes > 200 * 1024 )
+			bytes = 200 * 1024;
+		if ( bytes > 0 &&
+			 cudaFuncSetAttribute( stepWorldsCta<kSingleCtaThreads, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes ) != cudaSuccess )
+		{
+			cudaGetLastError();
+			bytes = 0;
+		}
+	}
+	return bytes;
+}
+
 cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream )
 {
-	stepWorldsCta<kSingleCtaThreads, 1><<<1, kSingleCtaThreads, 0, stream>>>( reinterpret_cast<char*>( dev ), 0ull, 1, dt, sub, phase, 1 );
+	const int arenaBytes = singleCtaArenaBytes();
+	stepWorldsCta<kSingleCtaThreads, 1><<<1, kSingleCtaThreads, arenaBytes, stream>>>( reinterpret_cast<char*>( dev ), 0ull, 1, dt, sub, phase, 1,
+																					   arenaBytes );
 	return cudaGetLastError();
 }
 

@@ -1017,7 +1017,11 @@ struct SplitView
 	int32_t *compIsland, *stack;
 };
 
-F2D_HD SplitView splitView( World* w )
+// `n` = bodies of the island that is split. The arrays the serial walk reads and re-reads (edge rows, marks, stack) go
+// into the team's shared-memory arena when the team has one and they fit (a single small world stepped by one block:
+// the walk is then a chain of shared-memory hits instead of L1 / L2 round trips that the solver stages running beside
+// it keep evicting); the visiting order it records, and everything else, stays in the image.
+F2D_HD SplitView splitView( World* w, int32_t* arena, int arenaInts, int n )
 {
 	const int B = w->bodies.cap + 8, C = w->contacts.cap + 8, J = w->joints.cap + 8;
 	int32_t* p = ptr( w, w->splitScratch );
@@ -1049,7 +1053,53 @@ F2D_HD SplitView splitView( World* w )
 	v.jointMark = take( J );
 	v.jointOrder = take( J );
 	v.jointComp = take( J );
+	if ( arena != nullptr )
+	{
+		// rows hold two ints per edge, a touching contact has at most two edges inside the island; marks are by id
+		const int rows = n + 2, edgeInts = 4 * w->step.awakeContactCount + 8, contactIds = w->contactIds.next + 8;
+		const int jedgeInts = 4 * w->jointIds.next + 8, jointIds = w->jointIds.next + 8;
+		const int need = 4 * rows + edgeInts + contactIds + jedgeInts + jointIds;
+		if ( need <= arenaInts )
+		{
+			int32_t* a = arena;
+			auto carve = [&]( int count ) {
+				int32_t* r = a;
+				a += count;
+				return r;
+			};
+			v.rowOff = carve( rows );
+			v.jrowOff = carve( rows );
+			v.bodyMark = carve( rows );
+			v.stack = carve( rows );
+			v.edges = carve( edgeInts );
+			v.contactMark = carve( contactIds );
+			v.jedges = carve( jedgeInts );
+			v.jointMark = carve( jointIds );
+		}
+	}
 	return v;
+}
+F2D_HD SplitView splitView( World* w ) { return splitView( w, nullptr, 0, 0 ); }
+
+// Second word of a row entry: the other body's code (-2 disabled, -1 none / static, else its position) biased by 2, plus
+// two flags that the walk would otherwise have to work out per pop with warp votes:
+//   kRowFirstOther  no earlier edge of this row leads to the same body. Among the edges of a popped body that lead to an
+//                   UNVISITED body X all are unmarked (a marked constraint between the two was processed when X was
+//                   popped, and popped bodies are visited), so the one that pushes X - the first in row order - is known
+//                   when the row is built;
+//   kRowFirstId     first occurrence of the constraint in this row (a joint with both ends on one body is listed twice).
+constexpr int kRowFirstOther = 1 << 28, kRowFirstId = 1 << 29, kRowCodeMask = ( 1 << 28 ) - 1;
+F2D_HD int splitRowEntry( const int32_t* rows, int rowStart, int at, int id, int code )
+{
+	int flags = kRowFirstOther | kRowFirstId;
+	for ( int k = rowStart; k < at; ++k )
+	{
+		if ( rows[2 * k] == id )
+			flags &= ~kRowFirstId;
+		if ( ( rows[2 * k + 1] & kRowCodeMask ) == code + 2 )
+			flags &= ~kRowFirstOther;
+	}
+	return ( code + 2 ) | flags;
 }
 
 // Team-wide preparation. Leaves step.splitBodies == 0 when there is nothing to split (island.c:610-620).
@@ -1062,7 +1112,7 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 	if ( base.setIndex != kAwakeSet || base.constraintRemoveCount == 0 )
 		return;
 	const int n = base.bodyCount;
-	SplitView v = splitView( w );
+	SplitView v = splitView( w, t.arenaPtr(), t.arenaSize(), n );
 	Body* bodies = ptr( w, w->bodies );
 	const Contact* contacts = ptr( w, w->contacts );
 	const Joint* joints = ptr( w, w->joints );
@@ -1153,6 +1203,7 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 		const Body& body = bodies[id];
 		int pos = v.posOf[id];
 		int out = v.rowOff[pos];
+		const int row0 = out;
 		for ( int key = body.headContactKey; key != kNull; )
 		{
 			int contactId = key >> 1;
@@ -1163,14 +1214,16 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 				continue;
 			int otherId = c.edges[edgeIndex ^ 1].bodyId;
 			const Body& other = bodies[otherId];
-			v.edges[2 * out] = contactId;
 			// the other body as a POSITION in the island's body list (posOf of every member was written before the scans);
 			// after the island merge both bodies of a touching contact are in this island unless one is static
-			v.edges[2 * out + 1] = ( other.setIndex != kStaticSet && other.islandId == baseId ) ? v.posOf[otherId] : kNull;
+			const int code = ( other.setIndex != kStaticSet && other.islandId == baseId ) ? v.posOf[otherId] : kNull;
+			v.edges[2 * out] = contactId;
+			v.edges[2 * out + 1] = splitRowEntry( v.edges, row0, out, contactId, code );
 			v.contactMark[contactId] = 0;
 			out += 1;
 		}
 		int jout = v.jrowOff[pos];
+		const int jrow0 = jout;
 		for ( int key = body.headJointKey; key != kNull; )
 		{
 			int jointId = key >> 1;
@@ -1181,7 +1234,7 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 			const Body& other = bodies[otherId];
 			int code = other.setIndex == kDisabledSet ? -2 : ( ( other.setIndex == kAwakeSet && other.islandId == baseId ) ? v.posOf[otherId] : kNull );
 			v.jedges[2 * jout] = jointId;
-			v.jedges[2 * jout + 1] = code;
+			v.jedges[2 * jout + 1] = splitRowEntry( v.jedges, jrow0, jout, jointId, code );
 			v.jointMark[jointId] = 0;
 			jout += 1;
 		}
@@ -1197,13 +1250,13 @@ template <class Team> F2D_HDF inline void splitPrepare( World* w, Team& t )
 // marks, so the lanes of a warp take one edge each: an edge is new iff its constraint is unmarked (ballot -> ranks
 // give the order slots), and among the new edges the first one (lowest lane) that leads to an unmarked body pushes it.
 // Every lane keeps the same counters; lane 0 performs the island pool edits.
-template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
+template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L, int32_t* arena, int arenaInts )
 {
 	const int n = w->step.splitBodies;
 	if ( n == 0 )
 		return;
 	const int baseId = w->step.splitTarget;
-	SplitView v = splitView( w );
+	SplitView v = splitView( w, arena, arenaInts, n );
 	const int lane = L.lane();
 	const uint32_t below = lane == 0 ? 0u : ( 0xffffffffu >> ( 32 - lane ) );
 	if ( lane == 0 )
@@ -1252,11 +1305,13 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 					const int e = chunk + lane;
 					const bool live = e < end;
 					const int id = live ? rows[2 * e] : 0;
-					const int other = live ? rows[2 * e + 1] : kNull;
-					bool fresh = live && mark[id] == 0;
-					// a constraint listed twice in one row (both ends on this body) counts once, at its first edge
-					uint32_t same = L.matchAny( fresh ? id : -2 - lane );
-					fresh = fresh && lowestBit32( same ) == lane;
+					const int entry = live ? rows[2 * e + 1] : 1; // (1 = code -1, no flags)
+					const int other = ( entry & kRowCodeMask ) - 2;
+					// both marks are asked for together: each is one dependent hop behind the row entry
+					const bool unmarked = live && mark[id] == 0;
+					const bool unvisited = other >= 0 && v.bodyMark[other] == 0;
+					// a constraint listed twice in one row counts once, at its first edge (see splitRowEntry)
+					const bool fresh = unmarked && ( entry & kRowFirstId ) != 0;
 					if ( fresh )
 						mark[id] = 1;
 
@@ -1270,17 +1325,19 @@ template <class Lanes> F2D_HDF inline void splitWalk( World* w, Lanes L )
 						orderComp[slot] = comp;
 					}
 					filled += popCount32( recordedMask );
-					const bool reach = recorded && other != kNull && v.bodyMark[other] == 0;
-					uint32_t peers = L.matchAny( reach ? other : -2 - lane );
-					const bool pusher = reach && lowestBit32( peers ) == lane;
+					// several edges may lead to one body: the first of the row pushes it (see splitRowEntry)
+					const bool pusher = recorded && unvisited && ( entry & kRowFirstOther ) != 0;
 					const uint32_t pushMask = L.ballot( pusher );
 					if ( pusher )
 					{
 						v.stack[sp + popCount32( pushMask & below )] = other;
 						v.bodyMark[other] = 1;
-						// its edge rows are read when it is popped: ask for them now
-						prefetchLine( v.rowOff + other );
-						prefetchLine( v.edges + 2 * v.rowOff[other] );
+						// its edge rows are read when it is popped: ask for them now (unless they are in shared memory)
+						if ( arena == nullptr )
+						{
+							prefetchLine( v.rowOff + other );
+							prefetchLine( v.edges + 2 * v.rowOff[other] );
+						}
 					}
 					if ( pushMask != 0 )
 					{
@@ -1307,7 +1364,7 @@ template <class Team> F2D_HDF inline void splitApply( World* w, Team& t )
 	const int n = w->step.splitBodies;
 	if ( n == 0 )
 		return;
-	SplitView v = splitView( w );
+	SplitView v = splitView( w, t.arenaPtr(), t.arenaSize(), n );
 	Island* islands = ptr( w, w->islands );
 	Body* bodies = ptr( w, w->bodies );
 	Contact* contacts = ptr( w, w->contacts );
@@ -1670,6 +1727,9 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 	bool fork = false;
 	if constexpr ( Team::kCanFork )
 		fork = w->step.splitBodies > 0 && t.canFork();
+	// (small teams - batches - keep the vote inside the body loop: the walk is hidden there anyway, and a second sweep
+	// over the body records would cost them DRAM traffic)
+	const bool overlapFinalize = fork && t.size() >= 512 && w->step.dt > 0.0f;
 	if ( fork )
 	{
 		if constexpr ( Team::kCanFork )
@@ -1677,20 +1737,28 @@ template <class Team> F2D_HDF inline void stepSolve( World* w, Team& t )
 			if ( t.inSide() )
 			{
 				if ( t.inSideGroup() )
-					splitWalk( w, typename Team::Lanes{} );
+					splitWalk( w, typename Team::Lanes{}, t.arenaPtr(), t.arenaSize() );
 			}
 			else
 			{
 				auto crew = t.crew();
 				solveStages( w, crew );
+				// A large team is done with the stages well before the serial walk ends: it goes on with the body loop
+				// of finalize, which needs nothing of the islands except the votes (cast after the join, stepFinalize).
+				// The reference cannot do this ("cannot split islands in parallel with FinalizeBodies", solver.c:1478):
+				// its finalize task reads the island of every body.
+				if ( overlapFinalize )
+					finalizeBodiesTeam( w, crew, false );
 			}
 		}
 		t.sync();
+		if ( overlapFinalize && t.rank() == 0 )
+			w->step.bodiesFinalized = 1;
 	}
 	else
 	{
 		if ( t.inFirstGroup() )
-			splitWalk( w, typename Team::Lanes{} );
+			splitWalk( w, typename Team::Lanes{}, t.arenaPtr(), t.arenaSize() );
 		solveStages( w, t );
 		t.sync();
 	}
@@ -1917,7 +1985,10 @@ constexpr int kEnlargeByList = -2; // finalizeBody -> stepFinalize: this body's 
 
 // solver.c:543-726, one awake body
 F2D_HDF inline void finalizeBodyTail( World* w, int simIndex );
-F2D_HDF inline void finalizeBody( World* w, int simIndex )
+F2D_HDF inline void finalizeBodyVote( World* w, int simIndex );
+// `vote`: cast the body's island vote (finalizeBodyVote) right here; false when the island split may still be running
+// beside this loop (stepSolve), then the votes follow in a loop of their own once the islands are final
+F2D_HDF inline void finalizeBody( World* w, int simIndex, bool vote )
 {
 	BodyState& state = ptr( w, w->states )[simIndex];
 	int bodyId = ptr( w, w->awakeBodies )[simIndex];
@@ -1997,6 +2068,8 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 				// Parked from the end of the bullet array downwards.
 				int slot = atomAdd( &w->step.fastDeferredCount, 1 );
 				ptr( w, w->bullets )[w->bullets.cap - 1 - slot] = simIndex;
+				if ( vote )
+					finalizeBodyVote( w, simIndex ); // does not depend on the continuous pass
 				return;
 			}
 			else
@@ -2017,15 +2090,17 @@ F2D_HDF inline void finalizeBody( World* w, int simIndex )
 		body.sleepTime += timeStep;
 	}
 
+	if ( vote )
+		finalizeBodyVote( w, simIndex );
 	finalizeBodyTail( w, simIndex );
 }
 
-// What finalizeBody does after the continuous pass of a fast body: island sleep votes and the shape boxes
-F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
+// The island vote of one awake body (solver.c:649-675): keeps its island awake, or proposes it for splitting. The only
+// part of the body finalize that looks at islands; it depends on nothing the continuous pass changes.
+F2D_HDF inline void finalizeBodyVote( World* w, int simIndex )
 {
 	int bodyId = ptr( w, w->awakeBodies )[simIndex];
-	BodySim& sim = ptr( w, w->sims )[bodyId];
-	Body& body = ptr( w, w->bodies )[bodyId];
+	const Body& body = ptr( w, w->bodies )[bodyId];
 	const Island& island = ptr( w, w->islands )[body.islandId];
 	if ( body.sleepTime < kTimeToSleep )
 	{
@@ -2039,6 +2114,14 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 								 (unsigned long long)( 0xFFFFFFFFu - (uint32_t)simIndex );
 		atomMax64( &w->step.splitKey, key );
 	}
+}
+
+// What finalizeBody does after the continuous pass of a fast body: the shape boxes
+F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
+{
+	int bodyId = ptr( w, w->awakeBodies )[simIndex];
+	BodySim& sim = ptr( w, w->sims )[bodyId];
+	Body& body = ptr( w, w->bodies )[bodyId];
 
 	Xf transform = sim.transform;
 	bool isFast = sim.isFast;
@@ -2081,6 +2164,59 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 		shapeId = shape.nextShapeId;
 	}
 	ptr( w, w->islBodies )[simIndex] = parkedKey;
+}
+
+// The body loop of finalize (solver.c:1724-1747) on `t`: the whole team, or the crew while the island split still runs.
+// `vote` as in finalizeBody.
+template <class Team> F2D_HDF inline void finalizeBodiesTeam( World* w, Team& t, bool vote )
+{
+	const int awakeBodyCount = w->step.awakeBodyCount;
+	if ( t.rank() == 0 )
+		w->step.fastDeferredCount = 0;
+	// clear bit sets (solver.c:1724-1733); the island bits belong to the votes
+	int bodyWords = ( awakeBodyCount + 63 ) >> 6;
+	uint64_t* eb = ptr( w, w->enlargedBits );
+	for ( int i = t.rank(); i < bodyWords; i += t.size() )
+		eb[i] = 0;
+	if ( vote )
+	{
+		int islandWords = ( w->awakeIslands.count + 63 ) >> 6;
+		uint64_t* ib = ptr( w, w->islandBits );
+		for ( int i = t.rank(); i < islandWords; i += t.size() )
+			ib[i] = 0;
+	}
+	t.sync();
+	// the body and sim records of this thread's next body are requested into L2 while the current one is finalized
+	const int32_t* awake = ptr( w, w->awakeBodies );
+	const Body* bodyArr = ptr( w, w->bodies );
+	const BodySim* simArr = ptr( w, w->sims );
+	const int stride = t.size();
+	for ( int i = t.rank(); i < awakeBodyCount; i += stride )
+	{
+		if ( i + stride < awakeBodyCount )
+		{
+			int next = awake[i + stride];
+			prefetchL2( &simArr[next] );
+			prefetchL2( &simArr[next].center );
+			prefetchL2( &bodyArr[next].islandId );
+		}
+		finalizeBody( w, i, vote );
+	}
+	t.sync();
+}
+
+// The island votes on their own, once the islands are final (after the split has been applied)
+template <class Team> F2D_HDF inline void finalizeVotesTeam( World* w, Team& t )
+{
+	const int awakeBodyCount = w->step.awakeBodyCount;
+	int islandWords = ( w->awakeIslands.count + 63 ) >> 6;
+	uint64_t* ib = ptr( w, w->islandBits );
+	for ( int i = t.rank(); i < islandWords; i += t.size() )
+		ib[i] = 0;
+	t.sync();
+	for ( int i = t.rank(); i < awakeBodyCount; i += t.size() )
+		finalizeBodyVote( w, i );
+	t.sync();
 }
 
 // Team-parallel enlarge of one leaf: the end state (leaf box replaced; every ancestor box = union with it; every
@@ -2451,38 +2587,14 @@ template <class Team> F2D_HDF inline void stepFinalize( World* w, Team& t, int p
 	const bool doEnd = part == kFinalizeAll || part == kFinalizeEnd;
 	if ( solved && doBodies )
 	{
+		// stepSolve has run the body loop already when it overlapped it with the island split (World::step.bodiesFinalized)
+		if ( w->step.bodiesFinalized == 0 )
+			finalizeBodiesTeam( w, t, true );
+		else
+			finalizeVotesTeam( w, t );
+		t.sync();
 		if ( t.rank() == 0 )
-			w->step.fastDeferredCount = 0;
-		// clear bit sets (solver.c:1724-1733)
-		int bodyWords = ( awakeBodyCount + 63 ) >> 6;
-		int islandWords = ( w->awakeIslands.count + 63 ) >> 6;
-		uint64_t* eb = ptr( w, w->enlargedBits );
-		uint64_t* ib = ptr( w, w->islandBits );
-		for ( int i = t.rank(); i < bodyWords; i += t.size() )
-			eb[i] = 0;
-		for ( int i = t.rank(); i < islandWords; i += t.size() )
-			ib[i] = 0;
-		t.sync();
-
-		{
-			// the body and sim records of this thread's next body are requested into L2 while the current one is finalized
-			const int32_t* awake = ptr( w, w->awakeBodies );
-			const Body* bodyArr = ptr( w, w->bodies );
-			const BodySim* simArr = ptr( w, w->sims );
-			const int stride = t.size();
-			for ( int i = t.rank(); i < awakeBodyCount; i += stride )
-			{
-				if ( i + stride < awakeBodyCount )
-				{
-					int next = awake[i + stride];
-					prefetchL2( &simArr[next] );
-					prefetchL2( &simArr[next].invMass );
-					prefetchL2( &bodyArr[next].userData );
-				}
-				finalizeBody( w, i );
-			}
-		}
-		t.sync();
+			w->step.bodiesFinalized = 0;
 		F2D_MARK( w, t, pfFinalizeBodies );
 	}
 	if ( solved && doMoves )

@@ -137,6 +137,7 @@ struct SoloLanes
 	F2D_HD int count() const { return 1; }
 	F2D_HD uint32_t ballot( bool p ) const { return p ? 1u : 0u; }
 	F2D_HD uint32_t matchAny( int ) const { return 1u; }
+	F2D_HD bool firstOfEqual( bool active, int ) const { return active; }
 	F2D_HD void sync() const {}
 	F2D_HD int broadcast( int v ) const { return v; }
 	F2D_HD int from( int v, int ) const { return v; }
@@ -152,6 +153,22 @@ struct WarpLanes
 	F2D_HD int count() const { return 32; }
 	F2D_HD uint32_t ballot( bool p ) const { return __ballot_sync( 0xffffffffu, p ); }
 	F2D_HD uint32_t matchAny( int key ) const { return __match_any_sync( 0xffffffffu, key ); }
+	// Is this lane the lowest of the active lanes that hold `key`? One shuffle and one ballot per DISTINCT key among the
+	// active lanes (usually one or two) - match.any costs a pass per distinct value over all 32 lanes, active or not.
+	F2D_HD bool firstOfEqual( bool active, int key ) const
+	{
+		uint32_t pending = __ballot_sync( 0xffffffffu, active );
+		bool first = false;
+		while ( pending != 0 )
+		{
+			const int leader = __ffs( (int)pending ) - 1;
+			const int leaderKey = __shfl_sync( 0xffffffffu, key, leader );
+			const uint32_t same = __ballot_sync( 0xffffffffu, active && key == leaderKey );
+			first = first || (int)( threadIdx.x & 31 ) == leader;
+			pending &= ~same;
+		}
+		return first;
+	}
 	F2D_HD void sync() const { __syncwarp(); }
 	F2D_HD int broadcast( int v ) const { return __shfl_sync( 0xffffffffu, v, 0 ); }
 	F2D_HD int from( int v, int sourceLane ) const { return __shfl_sync( 0xffffffffu, v, sourceLane ); } // every lane gets sourceLane's v
@@ -190,6 +207,8 @@ struct SerialTeam
 {
 	typedef SoloLanes Lanes;
 	F2D_HD bool inFirstGroup() const { return true; }
+	F2D_HD int32_t* arenaPtr() const { return nullptr; } // shared-memory work area of the team (device block teams only)
+	F2D_HD int arenaSize() const { return 0; }
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = false;
 	F2D_HD int rank() const { return 0; }
