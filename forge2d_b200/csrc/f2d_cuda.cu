@@ -116,18 +116,22 @@ static DeviceMirror* mirror( HostWorld& hw )
 }
 
 
-static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int phase )
+static bool hostImagePinned( const World* img ) { return ( reinterpret_cast<const char*>( img ) - 256 )[0] == 1; }
+
+// `hostHeader`: the kernel mirrors the world header into the (pinned, device-accessible) host image itself
+static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int phase, bool mirrorHeader = false )
 {
+	void* hostHeader = mirrorHeader && hostImagePinned( hw.img ) ? hw.img : nullptr;
 	int mode = hw.launchMode;
 	if ( mode < 0 )
 		mode = hw.img->awakeBodies.count + hw.img->shapeIds.next > 4096 ? 1 : 0;
 	g_launchCount += 1;
 	if ( mode == 0 )
-		return cudaOk( launchSingleCta( m->dev, dt, sub, phase, m->stream ), "stepWorldsCta launch" );
+		return cudaOk( launchSingleCta( m->dev, dt, sub, phase, hostHeader, m->stream ), "stepWorldsCta launch" );
 	int blocks = g_smCount;
 	if ( blocks > 4000 )
 		blocks = 4000;
-	return cudaOk( launchSingleGrid( m->dev, m->blockTotals, blocks, dt, sub, phase, m->stream ), "stepWorldGrid cooperative launch" );
+	return cudaOk( launchSingleGrid( m->dev, m->blockTotals, blocks, dt, sub, phase, hostHeader, m->stream ), "stepWorldGrid cooperative launch" );
 }
 
 // Device copy allocated and current (uploads the host image when it is newer or the image was re-laid out)
@@ -197,10 +201,12 @@ static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous
 	}
 	else
 	{
-		launchWorld( hw, m, dt, subSteps, kPhaseAll );
+		// the header travels back with every step (counters, error flags, event counts, capacities in use): written by
+		// the kernel into the pinned host image, or copied when the image is not pinned
+		launchWorld( hw, m, dt, subSteps, kPhaseAll, true );
 	}
-	// the header travels back with every step: counters, error flags, event counts, capacities in use
-	cudaMemcpyAsync( img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
+	if ( m->timing || hostImagePinned( img ) == false )
+		cudaMemcpyAsync( img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
 	hw.state = kDeviceNewer;
 	if ( synchronous )
 	{

@@ -245,7 +245,8 @@ template <class Team> __device__ __forceinline__ void runPhase( World* w, Team& 
 // World header held in shared memory (see World::deviceBase) and writes it back when the world is done.
 template <int kThreads, int kMinBlocks>
 __global__ void __launch_bounds__( kThreads, kMinBlocks )
-	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps, int arenaBytes )
+	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps, int arenaBytes,
+				   uint4* hostHeader )
 {
 	__shared__ int32_t smem[64];
 	__shared__ uint4 header[sizeof( World ) / 16];
@@ -275,13 +276,21 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 		__syncthreads();
 		for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
 			image[i] = header[i];
+		// A single world stepped synchronously: the header (counters, error flags, event counts) also goes straight into
+		// the pinned host image over PCIe - 2 KB of posted writes instead of a D2H copy operation after the kernel.
+		if ( hostHeader != nullptr )
+		{
+			for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
+				hostHeader[i] = header[i];
+		}
 		__syncthreads();
 	}
 }
 
 // One cooperative grid per world.
 template <int kThreads>
-__global__ void __launch_bounds__( kThreads, 1 ) stepWorldGrid( World* w, int32_t* blockTotals, float dt, int sub, int phase )
+__global__ void __launch_bounds__( kThreads, 1 )
+	stepWorldGrid( World* w, int32_t* blockTotals, float dt, int sub, int phase, uint4* hostHeader )
 {
 	__shared__ int32_t smem[64];
 	GridTeam team{ 0u, smem, blockTotals + 128, reinterpret_cast<GridBarrier*>( blockTotals ), 0u };
@@ -293,6 +302,17 @@ __global__ void __launch_bounds__( kThreads, 1 ) stepWorldGrid( World* w, int32_
 		return;
 	team.begin();
 	runPhase( w, team, phase, dt, sub );
+	if ( hostHeader != nullptr )
+	{
+		// header -> pinned host image (see stepWorldsCta), by block 0 once every block is done with the step
+		team.sync();
+		if ( blockIdx.x == 0 )
+		{
+			const uint4* header = reinterpret_cast<const uint4*>( w );
+			for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
+				hostHeader[i] = __ldcg( header + i );
+		}
+	}
 	team.end();
 }
 

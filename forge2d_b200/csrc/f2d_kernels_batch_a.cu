@@ -10,7 +10,7 @@ bool launchBatchStepA( int threads, int blocksPerSM, char* base, unsigned long l
 {
 	if ( threads == 256 && blocksPerSM == 4 )
 	{
-		stepWorldsCta<256, 4><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0 );
+		stepWorldsCta<256, 4><<<worldCount, 256, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0, nullptr );
 		return true;
 	}
 	return false;

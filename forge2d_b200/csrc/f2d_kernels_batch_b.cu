@@ -10,7 +10,7 @@ bool launchBatchStepB( int threads, int blocksPerSM, char* base, unsigned long l
 {
 	if ( threads == 64 && blocksPerSM == 16 )
 	{
-		stepWorldsCta<64, 16><<<worldCount, 64, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0 );
+		stepWorldsCta<64, 16><<<worldCount, 64, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0, nullptr );
 		return true;
 	}
 	return false;

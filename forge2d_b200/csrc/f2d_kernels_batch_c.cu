@@ -20,10 +20,10 @@ bool launchBatchStepC( int threads, int blocksPerSM, char* base, unsigned long l
 		{
 			const int phases[] = { kPhaseBeginPairs, kPhaseCollideTreeOnly, kPhaseCollideNarrowOnly, kPhaseCollideFinish, kPhaseSolve, kPhaseFinalize };
 			for ( int phase : phases )
-				stepWorldsCta<128, 8><<<worldCount, 128, 0, stream>>>( base, stride, worldCount, dt, sub, phase, 1, 0 );
+				stepWorldsCta<128, 8><<<worldCount, 128, 0, stream>>>( base, stride, worldCount, dt, sub, phase, 1, 0, nullptr );
 			return true;
 		}
-		stepWorldsCta<128, 8><<<worldCount, 128, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0 );
+		stepWorldsCta<128, 8><<<worldCount, 128, 0, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps, 0, nullptr );
 		return true;
 	}
 	return false;

@@ -62,11 +62,11 @@ static int singleCtaArenaBytes()
 	return bytes;
 }
 
-cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream )
+cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, void* hostHeader, cudaStream_t stream )
 {
 	const int arenaBytes = singleCtaArenaBytes();
 	stepWorldsCta<kSingleCtaThreads, 1><<<1, kSingleCtaThreads, arenaBytes, stream>>>( reinterpret_cast<char*>( dev ), 0ull, 1, dt, sub, phase, 1,
-																					   arenaBytes );
+																					   arenaBytes, static_cast<uint4*>( hostHeader ) );
 	return cudaGetLastError();
 }
 

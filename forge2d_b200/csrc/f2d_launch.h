@@ -28,8 +28,10 @@ inline bool launchBatchStep( int threads, int blocksPerSM, char* base, unsigned 
 		   launchBatchStepB( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
 		   launchBatchStepC( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream );
 }
-cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, cudaStream_t stream );
-cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, cudaStream_t stream );
+// hostHeader: device-accessible address of the pinned host image (the kernel mirrors the header there), or nullptr
+cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, void* hostHeader, cudaStream_t stream );
+cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, void* hostHeader,
+							  cudaStream_t stream );
 // gather kernels of the batch extension
 struct BodyMoveEvent;
 void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,
