@@ -516,6 +516,9 @@ F2D_FUNCTIONS = {
     "f2dHostAlloc": (c_void_p, [C.c_ulonglong]),
     "f2dHostFree": (None, [c_void_p]),
     "f2dBatch_GetErrorFlags": (C.c_uint32, [c_void_p]),
+    "f2dBatch_CreateFromWorlds": (c_void_p, [C.POINTER(WorldId), c_int]),
+    "f2dBatch_GetWorldErrors": (c_int, [c_void_p, C.POINTER(C.c_uint32), c_int]),
+    "f2dBatch_GetGrowthCount": (c_int, [c_void_p]),
     "f2dHasDevice": (c_int, []),
     "f2dGetLastError": (C.c_char_p, []),
     "f2dClearLastError": (None, []),

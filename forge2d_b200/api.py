@@ -687,16 +687,33 @@ class WorldBatch:
     """Extension (not in the reference): N device-resident replicas of a template world stepped by one kernel launch per
     step, one thread block per world (f2dBatch_* in include/forge2d_b200.h)."""
 
-    def __init__(self, template: World, count: int):
+    def __init__(self, template, count: int = 0):
+        """`template`: one World replicated `count` times, or a list of (different) Worlds, one image each."""
         self._lib = _lib()
-        self._batch = self._lib.f2dBatch_Create(template.id, count)
+        if isinstance(template, (list, tuple)):
+            ids = (A.WorldId * len(template))(*[w.id for w in template])
+            self._batch = self._lib.f2dBatch_CreateFromWorlds(ids, len(template))
+            count = len(template)
+        else:
+            self._batch = self._lib.f2dBatch_Create(template.id, count)
         if not self._batch:
             raise RuntimeError("f2dBatch_Create failed: %s" % self._lib.f2dGetLastError().decode())
         self.count = count
 
     def step(self, timeStep: float, subStepCount: int = 4, steps: int = 1):
+        """Steps every world; raises when a world ends the call with an error flag up (a world that merely needs more
+        contact room is not an error: the batch grows and that world repeats the step)."""
         self._lib.f2dBatch_StepN(self._batch, timeStep, subStepCount, steps)
         self._lib.f2dBatch_Synchronize(self._batch)
+        flags = self.errorFlags
+        if flags & ~0x20:  # everything but the per-step "an event was dropped" flag
+            bad = [i for i, f in enumerate(self.worldErrors()) if f & ~0x20]
+            raise RuntimeError("WorldBatch.step: error flags 0x%x in worlds %r" % (flags, bad[:16]))
+
+    def worldErrors(self):
+        out = (C.c_uint32 * self.count)()
+        self._lib.f2dBatch_GetWorldErrors(self._batch, out, self.count)
+        return list(out)
 
     def bodyTransforms(self, maxBodiesPerWorld: int):
         """numpy view (count, maxBodiesPerWorld) of b2BodyMoveEvent records in pinned memory, plus per-world counts."""

@@ -134,6 +134,7 @@ static Caps capsWith( const World* w, int B, int S, int C, int J )
 	c.contactEvents = w != nullptr && w->contactEventCapable > 0 ? C : 16;
 	c.hitEvents = w != nullptr && w->hitEventCapable > 0 ? C : 16;
 	c.sensors = 0;
+	c.sensorOverlap = sensorOverlapCapFor( S, 0 );
 	return c;
 }
 
@@ -170,6 +171,11 @@ static void reserve( HostWorld& hw, int needBodies, int needShapes, int needCont
 	if ( w->sensors.count + needSensors > c.sensors )
 	{
 		c.sensors = roundCap( w->sensors.count + needSensors, 8 );
+		grow = true;
+	}
+	if ( sensorOverlapCapFor( c.shapes, c.sensors ) != c.sensorOverlap )
+	{
+		c.sensorOverlap = sensorOverlapCapFor( c.shapes, c.sensors );
 		grow = true;
 	}
 	Caps ev = capsWith( w, c.bodies, c.shapes, c.contacts, c.joints );

@@ -326,7 +326,7 @@ inline int createShape( World* w, int bodyId, const ShapeParams& def, const void
 			shape.sensorIndex = w->sensors.count;
 			Sensor sensor = { shapeId, 0, 0, 0 };
 			F2D_PUSH( w, w->sensors, sensor );
-			w->sensorRefs.count = 2 * kSensorOverlapCap * w->sensors.count; // slots in use (kept for re-layout copies)
+			w->sensorRefs.count = 2 * w->sensorOverlapCap * w->sensors.count; // slots in use (kept for re-layout copies)
 		}
 	}
 	if ( def.updateBodyMass )

@@ -301,7 +301,116 @@ struct f2dBatch
 	cudaStream_t sliceStreams[kSlices] = {};
 	cudaEvent_t sliceDone[kSlices] = {};
 	cudaEvent_t inputsReady = nullptr;
+	// growth path: a world whose new contacts do not fit stops before its first structural edit (kErrRetry, f2d_step.h
+	// stepPairs); the batch then moves every image into a larger layout on the device and lets the stopped worlds repeat
+	// the step
+	f2d::World layout{};			   // host copy of the header layout shared by all images (offsets, capacities)
+	unsigned int* hostStatus = nullptr; // pinned: [0] OR of the error flags, [1] largest retryContacts
+	unsigned int* devStatus = nullptr;
+	unsigned int* devWorldFlags = nullptr;
+	int growths = 0;
+	bool checkEveryStep = false; // (the last step of a call is checked by f2dBatch_Synchronize: StepN itself never blocks on it)
+	bool pendingStatus = false;
+	float pendingDt = 0.0f;
+	int pendingSub = 0;
 };
+
+namespace f2d
+{
+static void batchInitStatus( f2dBatch* b )
+{
+	cudaMalloc( &b->devError, sizeof( unsigned int ) );
+	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
+	cudaMalloc( &b->devStatus, 2 * sizeof( unsigned int ) );
+	cudaMalloc( &b->devWorldFlags, (size_t)b->count * sizeof( unsigned int ) );
+	cudaMallocHost( &b->hostStatus, 2 * sizeof( unsigned int ) );
+}
+
+// OR of the error flags of all worlds and the largest contact room a stopped world asked for; synchronises the stream
+static unsigned int batchStatus( f2dBatch* b, int* retryContacts )
+{
+	cudaMemsetAsync( b->devStatus, 0, 2 * sizeof( unsigned int ), b->stream );
+	launchGatherErrors( b->dev, b->stride, b->count, b->devStatus, b->stream );
+	launchGatherWorldStatus( b->dev, b->stride, b->count, nullptr, reinterpret_cast<int*>( b->devStatus + 1 ), b->stream );
+	g_launchCount += 2;
+	cudaMemcpyAsync( b->hostStatus, b->devStatus, 2 * sizeof( unsigned int ), cudaMemcpyDeviceToHost, b->stream );
+	cudaStreamSynchronize( b->stream );
+	if ( retryContacts != nullptr )
+		*retryContacts = (int)b->hostStatus[1];
+	return b->hostStatus[0];
+}
+
+// Moves every image of the batch into a layout with room for `needContacts` more contacts (all on the device)
+static bool batchGrow( f2dBatch* b, int needContacts )
+{
+	Caps caps = b->caps;
+	caps.contacts = roundCap( caps.contacts + needContacts + ( needContacts >> 1 ), 256 );
+	if ( b->layout.contactEventCapable > 0 )
+		caps.contactEvents = caps.contacts;
+	if ( b->layout.hitEventCapable > 0 )
+		caps.hitEvents = caps.contacts;
+	World newHeader = b->layout;
+	const uint64_t bytes = layoutImage( newHeader, caps );
+	const unsigned long long newStride = ( bytes + 255ull ) / 256ull * 256ull;
+	std::vector<ArraySlot> oldSlots, newSlots;
+	World oldHeader = b->layout;
+	collectArrays( oldHeader, b->caps, oldSlots );
+	collectArrays( newHeader, caps, newSlots );
+	std::vector<RelayoutSlot> table( newSlots.size() );
+	for ( size_t i = 0; i < newSlots.size(); ++i )
+	{
+		// ArraySlot::off points at Arr::off, the first member of the Arr record
+		table[i].headerOffset = (int32_t)( reinterpret_cast<const char*>( newSlots[i].off ) - reinterpret_cast<const char*>( &newHeader ) );
+		table[i].elemSize = newSlots[i].elemSize;
+		table[i].persistent = newSlots[i].persistent ? 1 : 0;
+	}
+	char* newDev = nullptr;
+	RelayoutSlot* devTable = nullptr;
+	World* devHeader = nullptr;
+	if ( cudaOk( cudaMalloc( &newDev, newStride * (unsigned long long)b->count ), "cudaMalloc(batch growth)" ) == false )
+		return false;
+	cudaMalloc( &devTable, table.size() * sizeof( RelayoutSlot ) );
+	cudaMalloc( &devHeader, sizeof( World ) );
+	cudaMemsetAsync( newDev, 0, newStride * (unsigned long long)b->count, b->stream );
+	cudaMemcpyAsync( devTable, table.data(), table.size() * sizeof( RelayoutSlot ), cudaMemcpyHostToDevice, b->stream );
+	cudaMemcpyAsync( devHeader, &newHeader, sizeof( World ), cudaMemcpyHostToDevice, b->stream );
+	launchRelayoutWorlds( b->dev, b->stride, newDev, newStride, b->count, devTable, (int)table.size(), devHeader, b->stream );
+	g_launchCount += 1;
+	const bool ok = cudaOk( cudaStreamSynchronize( b->stream ), "batch growth" );
+	cudaFree( devTable );
+	cudaFree( devHeader );
+	if ( ok == false )
+	{
+		cudaFree( newDev );
+		return false;
+	}
+	cudaFree( b->dev );
+	b->dev = newDev;
+	b->stride = newStride;
+	b->caps = caps;
+	b->layout = newHeader;
+	b->growths += 1;
+	return true;
+}
+
+// After a step: worlds that stopped for contact room get it and repeat the step. Returns the remaining error flags.
+static unsigned int batchResolveRetries( f2dBatch* b, float dt, int sub )
+{
+	int need = 0;
+	unsigned int flags = batchStatus( b, &need );
+	for ( int attempt = 0; ( flags & kErrRetry ) != 0 && attempt < 4; ++attempt )
+	{
+		if ( batchGrow( b, need ) == false )
+			break;
+		launchBatchStep( b->threads, b->blocksPerSM, b->dev, b->stride, b->count, dt, sub, -1, b->stream );
+		g_launchCount += 1;
+		flags = batchStatus( b, &need );
+	}
+	if ( flags & ( kErrFatal | kErrRetry ) )
+		reportError( "f2dBatch: world error flags 0x%x after the step (f2dBatch_GetWorldErrors names the worlds)", flags );
+	return flags;
+}
+} // namespace f2d
 
 extern "C" {
 
@@ -348,8 +457,91 @@ f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count )
 						 b->stream );
 		have += n;
 	}
-	cudaMalloc( &b->devError, sizeof( unsigned int ) );
-	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
+	b->layout = *img;
+	batchInitStatus( b );
+	cudaOk( cudaStreamSynchronize( b->stream ), "batch upload" );
+	return b;
+}
+
+// A batch of DIFFERENT worlds: every world is brought to one common image layout (the largest capacities of any of
+// them, plus contact head-room) and uploaded; `worlds` may name a world more than once. The host worlds stay usable.
+f2dBatch* f2dBatch_CreateFromWorlds( const b2WorldId* worlds, int count )
+{
+	using namespace f2d;
+	if ( worlds == nullptr || count <= 0 )
+		return nullptr;
+	if ( backendAvailable() == false )
+	{
+		reportError( "f2dBatch_CreateFromWorlds: no CUDA device available - this library has no CPU fallback" );
+		return nullptr;
+	}
+	Caps common{};
+	int contactEventCapable = 0, hitEventCapable = 0;
+	for ( int i = 0; i < count; ++i )
+	{
+		HostWorld* hw = worldFromId( worlds[i] );
+		if ( hw == nullptr )
+		{
+			reportError( "f2dBatch_CreateFromWorlds: world %d is not valid", i );
+			return nullptr;
+		}
+		if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+		{
+			reportError( "f2dBatch_CreateFromWorlds: world %d has host callbacks registered; a batch steps without the host in the loop", i );
+			return nullptr;
+		}
+		World* w = hostImage( *hw );
+		const Caps& c = hw->caps;
+		const int wantContacts = w->contactIds.next + 4 * w->moveArray.count + w->shapeIds.next + 256;
+		common.bodies = std::max( common.bodies, c.bodies );
+		common.shapes = std::max( common.shapes, c.shapes );
+		common.contacts = std::max( common.contacts, std::max( c.contacts, roundCap( wantContacts, 256 ) ) );
+		common.joints = std::max( common.joints, c.joints );
+		common.sensors = std::max( common.sensors, c.sensors );
+		contactEventCapable = std::max( contactEventCapable, w->contactEventCapable );
+		hitEventCapable = std::max( hitEventCapable, w->hitEventCapable );
+	}
+	// event arrays: sized for the contacts of a world as soon as ANY world of the batch can emit such events
+	common.contactEvents = contactEventCapable > 0 ? common.contacts : 16;
+	common.hitEvents = hitEventCapable > 0 ? common.contacts : 16;
+	common.sensorOverlap = sensorOverlapCapFor( common.shapes, common.sensors );
+	f2dBatch* b = new f2dBatch();
+	b->count = count;
+	b->caps = common;
+	for ( int i = 0; i < count; ++i )
+	{
+		HostWorld* hw = worldFromId( worlds[i] );
+		const Caps& c = hw->caps;
+		if ( c.bodies != common.bodies || c.shapes != common.shapes || c.contacts != common.contacts || c.joints != common.joints ||
+			 c.sensors != common.sensors || c.contactEvents != common.contactEvents || c.hitEvents != common.hitEvents ||
+			 c.sensorOverlap != common.sensorOverlap )
+		{
+			hw->img = imageRelayout( hw->img, common, backendHostAlloc, backendHostFree );
+			hw->caps = common;
+			hw->state = kHostNewer;
+		}
+		if ( i == 0 )
+		{
+			b->stride = ( hw->img->imageBytes + 255ull ) / 256ull * 256ull;
+			if ( cudaOk( cudaMalloc( &b->dev, b->stride * (unsigned long long)count ), "cudaMalloc(batch)" ) == false )
+			{
+				delete b;
+				return nullptr;
+			}
+			cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking );
+			for ( int k = 0; k < 8; ++k )
+				cudaEventCreate( &b->events[k] );
+			b->layout = *hw->img;
+		}
+		if ( hw->img->imageBytes > b->stride )
+		{
+			reportError( "f2dBatch_CreateFromWorlds: world %d does not fit the common layout", i );
+			f2dBatch_Destroy( b );
+			return nullptr;
+		}
+		cudaMemcpyAsync( b->dev + b->stride * (unsigned long long)i, hw->img, hw->img->imageBytes, cudaMemcpyHostToDevice, b->stream );
+	}
+	batchInitStatus( b );
 	cudaOk( cudaStreamSynchronize( b->stream ), "batch upload" );
 	return b;
 }
@@ -363,6 +555,10 @@ void f2dBatch_Destroy( f2dBatch* b )
 	cudaFree( b->devEvents );
 	cudaFree( b->devCounts );
 	cudaFree( b->devError );
+	cudaFree( b->devStatus );
+	cudaFree( b->devWorldFlags );
+	if ( b->hostStatus )
+		cudaFreeHost( b->hostStatus );
 	if ( b->hostEvents )
 		cudaFreeHost( b->hostEvents );
 	if ( b->hostCounts )
@@ -396,6 +592,25 @@ void f2dBatch_StepN( f2dBatch* b, float dt, int sub, int steps )
 			return;
 		}
 		g_launchCount += 1;
+		// one cheap flag gather per step (queued behind it): a world that needs more contact room must get it before the
+		// NEXT step, or it would fall behind the others. The host only waits when a flag is up.
+		cudaMemsetAsync( b->devStatus, 0, 2 * sizeof( unsigned int ), b->stream );
+		launchGatherErrors( b->dev, b->stride, b->count, b->devStatus, b->stream );
+		g_launchCount += 1;
+		if ( s + 1 < steps || b->checkEveryStep )
+		{
+			cudaMemcpyAsync( b->hostStatus, b->devStatus, sizeof( unsigned int ), cudaMemcpyDeviceToHost, b->stream );
+			cudaStreamSynchronize( b->stream );
+			if ( b->hostStatus[0] & kErrRetry )
+				batchResolveRetries( b, dt, sub );
+		}
+		else
+		{
+			b->pendingStatus = true;
+			b->pendingDt = dt;
+			b->pendingSub = sub;
+			cudaMemcpyAsync( b->hostStatus, b->devStatus, sizeof( unsigned int ), cudaMemcpyDeviceToHost, b->stream );
+		}
 	}
 	cudaOk( cudaGetLastError(), "stepWorldsCta(batch) launch" );
 }
@@ -417,9 +632,37 @@ void f2dBatch_Step( f2dBatch* b, float dt, int sub )
 
 void f2dBatch_Synchronize( f2dBatch* b )
 {
-	if ( b )
-		f2d::cudaOk( cudaStreamSynchronize( b->stream ), "batch step" );
+	if ( b == nullptr )
+		return;
+	f2d::cudaOk( cudaStreamSynchronize( b->stream ), "batch step" );
+	if ( b->pendingStatus )
+	{
+		b->pendingStatus = false;
+		if ( b->hostStatus[0] & f2d::kErrRetry )
+			f2d::batchResolveRetries( b, b->pendingDt, b->pendingSub );
+		else if ( b->hostStatus[0] & f2d::kErrFatal )
+			f2d::reportError( "f2dBatch: world error flags 0x%x after the step (f2dBatch_GetWorldErrors names the worlds)", b->hostStatus[0] );
+	}
 }
+
+// Error flags of every world (f2d kErr* bits; 0 = fine): `out` takes f2dBatch_GetWorldCount entries
+int f2dBatch_GetWorldErrors( f2dBatch* b, uint32_t* out, int cap )
+{
+	using namespace f2d;
+	if ( b == nullptr || out == nullptr )
+		return 0;
+	f2dBatch_Synchronize( b );
+	launchGatherWorldStatus( b->dev, b->stride, b->count, b->devWorldFlags, nullptr, b->stream );
+	g_launchCount += 1;
+	const int n = cap < b->count ? cap : b->count;
+	cudaMemcpyAsync( out, b->devWorldFlags, (size_t)n * sizeof( unsigned int ), cudaMemcpyDeviceToHost, b->stream );
+	cudaStreamSynchronize( b->stream );
+	int bad = 0;
+	for ( int i = 0; i < n; ++i )
+		bad += out[i] != 0 ? 1 : 0;
+	return bad;
+}
+int f2dBatch_GetGrowthCount( f2dBatch* b ) { return b ? b->growths : 0; }
 
 int f2dBatch_GetWorldCount( f2dBatch* b )
 {
@@ -573,6 +816,20 @@ int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodie
 		start = end;
 	}
 	cudaOk( cudaStreamSynchronize( b->stream ), "batch step + events" );
+	{
+		// a world that stopped for contact room repeats the step on the grown images; the events are then read again
+		int need = 0;
+		if ( batchStatus( b, &need ) & kErrRetry )
+		{
+			batchResolveRetries( b, dt, sub );
+			launchGatherMoveEvents( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts, b->stream );
+			g_launchCount += 1;
+			cudaMemcpyAsync( b->hostEvents, b->devEvents, (size_t)b->count * maxBodies * sizeof( BodyMoveEvent ), cudaMemcpyDeviceToHost,
+							 b->stream );
+			cudaMemcpyAsync( b->hostCounts, b->devCounts, (size_t)b->count * sizeof( int ), cudaMemcpyDeviceToHost, b->stream );
+			cudaOk( cudaStreamSynchronize( b->stream ), "batch events after growth" );
+		}
+	}
 	*outEvents = b->hostEvents;
 	*outCounts = b->hostCounts;
 	int total = 0;

@@ -14,7 +14,20 @@ struct Caps
 	int bodies, shapes, contacts, joints;
 	int contactEvents, hitEvents; // event array capacities
 	int sensors;				  // sensor shapes
+	int sensorOverlap;			  // capacity of one overlap list of one sensor (derived: sensorOverlapCapFor)
 };
+
+// An overlap list holds shapes that overlap the sensor, each at most once: `shapes` entries always suffice. The total
+// is bounded (64 MB of references); a world beyond that keeps the bounded capacity and drops overlaps (kErrTruncated).
+inline int sensorOverlapCapFor( int shapes, int sensors )
+{
+	int cap = shapes < kMinSensorOverlapCap ? kMinSensorOverlapCap : shapes;
+	const long long budget = ( 64ll << 20 ) / (long long)sizeof( ShapeRef ) / 2;
+	const int n = sensors < 1 ? 1 : sensors;
+	if ( (long long)cap * n > budget )
+		cap = (int)( budget / n );
+	return cap < kMinSensorOverlapCap ? kMinSensorOverlapCap : cap;
+}
 
 struct ArraySlot
 {
@@ -40,7 +53,7 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.jointIds.free, J, true );
 	add( w.islandIds.free, B, true );
 	add( w.setIds.free, B + 8, true );
-	add( w.chainIds.free, 4, true );
+	add( w.chainIds.free, S, true ); // a chain owns at least one shape: never more chain ids than shape slots
 	add( w.bodies, B, true );
 	add( w.sims, B, true );
 	add( w.shapes, S, true );
@@ -51,8 +64,9 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.islands, B, true );
 	add( w.sets, B + 8, true );
 	const int N = c.sensors < 1 ? 1 : c.sensors;
+	const int overlapCap = sensorOverlapCapFor( S, c.sensors );
 	add( w.sensors, N, true );
-	add( w.sensorRefs, 2 * kSensorOverlapCap * N, true );
+	add( w.sensorRefs, 2 * overlapCap * N, true );
 	add( w.sensorBits, N / 64 + 2, false );
 	add( w.staticBodies, B, true );
 	add( w.disabledBodies, B, true );
@@ -89,7 +103,7 @@ inline void collectArrays( World& w, const Caps& c, std::vector<ArraySlot>& out 
 	add( w.endEvents[1], c.contactEvents, true );
 	add( w.hitEvents, c.hitEvents, true );
 	// a step can begin or end at most one overlap per list slot of every sensor
-	const int SE = c.sensors < 1 ? 4 : 2 * kSensorOverlapCap * c.sensors;
+	const int SE = c.sensors < 1 ? 4 : 2 * overlapCap * c.sensors;
 	add( w.sensorBeginEvents, SE, true );
 	add( w.sensorEndEvents[0], SE, true );
 	add( w.sensorEndEvents[1], SE, true );
@@ -128,6 +142,7 @@ inline uint64_t layoutImage( World& w, const Caps& c )
 		cursor = alignUp( cursor + (uint64_t)s.elemSize * (uint64_t)s.newCap, 256 );
 	}
 	w.consStride = c.contacts < 4 ? 4 : c.contacts;
+	w.sensorOverlapCap = sensorOverlapCapFor( c.shapes, c.sensors );
 	w.imageBytes = cursor;
 	return cursor;
 }
@@ -191,6 +206,18 @@ inline World* imageRelayout( World* old, const Caps& c, ImageAlloc alloc, ImageF
 			n = *oldSlots[i].cap;
 		memcpy( reinterpret_cast<char*>( w ) + *newSlots[i].off, reinterpret_cast<const char*>( old ) + *oldSlots[i].off,
 				(size_t)n * (size_t)newSlots[i].elemSize );
+	}
+	// the overlap lists are blocks of the per-sensor capacity: when that changed, every block moves
+	if ( old->sensorOverlapCap != w->sensorOverlapCap && old->sensors.count > 0 )
+	{
+		const ShapeRef* from = reinterpret_cast<const ShapeRef*>( reinterpret_cast<const char*>( old ) + old->sensorRefs.off );
+		ShapeRef* to = reinterpret_cast<ShapeRef*>( reinterpret_cast<char*>( w ) + w->sensorRefs.off );
+		const int oldCap = old->sensorOverlapCap, newCap = w->sensorOverlapCap;
+		const int keep = oldCap < newCap ? oldCap : newCap;
+		memset( to, 0, sizeof( ShapeRef ) * (size_t)w->sensorRefs.cap );
+		for ( int list = 0; list < 2 * old->sensors.count; ++list )
+			memcpy( to + (size_t)list * newCap, from + (size_t)list * oldCap, sizeof( ShapeRef ) * (size_t)keep );
+		w->sensorRefs.count = 2 * newCap * w->sensors.count;
 	}
 	release( old );
 	return w;

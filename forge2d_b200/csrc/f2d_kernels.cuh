@@ -267,11 +267,23 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 		if ( threadIdx.x == 0 )
 			w->deviceBase = reinterpret_cast<uint64_t>( image );
 		__syncthreads();
-		for ( int s = 0; s < steps; ++s )
+		// steps < 0: only the worlds that stopped for more contact room (kErrRetry) take (one) step - the batch has grown
+		// their images in between (f2dBatch growth path)
+		const bool onlyRetry = steps < 0;
+		if ( onlyRetry == false || ( w->error & kErrRetry ) != 0 )
 		{
-			if ( w->error & ( kErrCapacity | kErrUnsupported ) )
-				break;
-			runPhase( w, team, phase, dt, sub );
+			if ( onlyRetry && threadIdx.x == 0 )
+			{
+				w->error &= ~kErrRetry;
+				w->step.retryContacts = 0;
+			}
+			__syncthreads();
+			for ( int s = 0; s < ( onlyRetry ? 1 : steps ); ++s )
+			{
+				if ( w->error & kErrFatal )
+					break;
+				runPhase( w, team, phase, dt, sub );
+			}
 		}
 		__syncthreads();
 		for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += kThreads )
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__( kThreads, 1 )
 	if ( threadIdx.x == 0 )
 		w->deviceBase = reinterpret_cast<uint64_t>( w );
 	__syncthreads();
-	if ( w->error & ( kErrCapacity | kErrUnsupported ) )
+	if ( w->error & kErrFatal )
 		return;
 	team.begin();
 	runPhase( w, team, phase, dt, sub );

@@ -40,6 +40,66 @@ __global__ void gatherErrors( const char* base, unsigned long long stride, int w
 
 
 
+// Per-world error flags and the contact room a stopped world asked for (World::step.retryContacts), one thread per world
+__global__ void gatherWorldStatus( const char* base, unsigned long long stride, int worldCount, unsigned int* flags, int* retryMax )
+{
+	int wi = (int)( blockIdx.x * blockDim.x + threadIdx.x );
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	if ( flags != nullptr )
+		flags[wi] = w->error;
+	if ( retryMax != nullptr && ( w->error & kErrRetry ) != 0 )
+		atomicMax( retryMax, w->step.retryContacts );
+}
+
+// Moves every world of a batch into a larger image layout (more contact room): one block per world. `slots` lists, for
+// every array of the image, where its Arr record sits in the header, its element size and whether its contents
+// persist; `newHeader` is a header laid out for the new capacities (offsets, capacities, consStride, imageBytes).
+__global__ void relayoutWorlds( const char* oldBase, unsigned long long oldStride, char* newBase, unsigned long long newStride, int worldCount,
+								const RelayoutSlot* slots, int slotCount, const World* newHeader )
+{
+	const int wi = (int)blockIdx.x;
+	if ( wi >= worldCount )
+		return;
+	const char* from = oldBase + (unsigned long long)wi * oldStride;
+	char* to = newBase + (unsigned long long)wi * newStride;
+	const World* oldW = reinterpret_cast<const World*>( from );
+	// header: the old one, with the new layout patched in below
+	for ( int i = (int)threadIdx.x; i < (int)( sizeof( World ) / 16 ); i += (int)blockDim.x )
+		reinterpret_cast<uint4*>( to )[i] = reinterpret_cast<const uint4*>( from )[i];
+	__syncthreads();
+	for ( int k = 0; k < slotCount; ++k )
+	{
+		const RelayoutSlot slot = slots[k];
+		const Arr<char>& oldArr = *reinterpret_cast<const Arr<char>*>( from + slot.headerOffset );
+		const Arr<char>& newArr = *reinterpret_cast<const Arr<char>*>( reinterpret_cast<const char*>( newHeader ) + slot.headerOffset );
+		if ( slot.persistent )
+		{
+			const int keep = oldArr.cap < newArr.cap ? oldArr.cap : newArr.cap;
+			const unsigned long long bytes = (unsigned long long)keep * (unsigned long long)slot.elemSize; // multiple of 4
+			const uint32_t* src = reinterpret_cast<const uint32_t*>( from + oldArr.off );
+			uint32_t* dst = reinterpret_cast<uint32_t*>( to + newArr.off );
+			for ( unsigned long long i = threadIdx.x; i < bytes / 4; i += blockDim.x )
+				dst[i] = src[i];
+		}
+		if ( threadIdx.x == 0 )
+		{
+			Arr<char>& out = *reinterpret_cast<Arr<char>*>( to + slot.headerOffset );
+			out.off = newArr.off;
+			out.cap = newArr.cap;
+			out.count = oldArr.count;
+		}
+	}
+	if ( threadIdx.x == 0 )
+	{
+		World* w = reinterpret_cast<World*>( to );
+		w->consStride = newHeader->consStride;
+		w->imageBytes = newHeader->imageBytes;
+		w->sensorOverlapCap = oldW->sensorOverlapCap;
+	}
+}
+
 constexpr int kSingleCtaThreads = 1024;
 
 // The one-block kernel gets a shared-memory work area (CtaTeam::arena): the block has the SM to itself.
@@ -74,6 +134,16 @@ void launchGatherMoveEvents( const char* base, unsigned long long stride, int wo
 							 cudaStream_t stream )
 {
 	gatherMoveEvents<<<worldCount, 256, 0, stream>>>( base, stride, worldCount, out, maxBodies, counts );
+}
+void launchGatherWorldStatus( const char* base, unsigned long long stride, int worldCount, unsigned int* flags, int* retryMax,
+							 cudaStream_t stream )
+{
+	gatherWorldStatus<<<( worldCount + 255 ) / 256, 256, 0, stream>>>( base, stride, worldCount, flags, retryMax );
+}
+void launchRelayoutWorlds( const char* oldBase, unsigned long long oldStride, char* newBase, unsigned long long newStride, int worldCount,
+						   const RelayoutSlot* slots, int slotCount, const World* newHeader, cudaStream_t stream )
+{
+	relayoutWorlds<<<worldCount, 256, 0, stream>>>( oldBase, oldStride, newBase, newStride, worldCount, slots, slotCount, newHeader );
 }
 void launchGatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out, cudaStream_t stream )
 {

@@ -32,6 +32,17 @@ inline bool launchBatchStep( int threads, int blocksPerSM, char* base, unsigned 
 cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, void* hostHeader, cudaStream_t stream );
 cudaError_t launchSingleGrid( World* dev, int32_t* blockTotals, int blocks, float dt, int sub, int phase, void* hostHeader,
 							  cudaStream_t stream );
+// batch growth (f2d_kernels_world.cu relayoutWorlds): one entry per array of the image
+struct RelayoutSlot
+{
+	int32_t headerOffset; // byte offset of the array's Arr record inside World
+	int32_t elemSize;
+	int32_t persistent;
+};
+void launchGatherWorldStatus( const char* base, unsigned long long stride, int worldCount, unsigned int* flags, int* retryMax,
+							 cudaStream_t stream );
+void launchRelayoutWorlds( const char* oldBase, unsigned long long oldStride, char* newBase, unsigned long long newStride, int worldCount,
+						   const RelayoutSlot* slots, int slotCount, const World* newHeader, cudaStream_t stream );
 // gather kernels of the batch extension
 struct BodyMoveEvent;
 void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,

@@ -178,23 +178,23 @@ inline void destroySensor( World* w, Shape& sensorShape )
 	Sensor* sensors = ptr( w, w->sensors );
 	ShapeRef* refs = ptr( w, w->sensorRefs );
 	const Sensor& sensor = sensors[index];
-	const ShapeRef* refs2 = refs + (size_t)( 2 * index + sensor.flip ) * kSensorOverlapCap;
+	const ShapeRef* refs2 = refs + (size_t)( 2 * index + sensor.flip ) * w->sensorOverlapCap;
 	for ( int i = 0; i < sensor.count2; ++i )
 	{
 		SensorEvent ev = { ShapeId{ sensorShape.id + 1, w->worldId, sensorShape.generation },
 						   ShapeId{ refs2[i].shapeId + 1, w->worldId, refs2[i].generation } };
-		F2D_PUSH( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
+		F2D_PUSH_EVENT( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
 	}
 	const int last = w->sensors.count - 1;
 	if ( index != last )
 	{
 		sensors[index] = sensors[last];
-		memcpy( refs + (size_t)( 2 * index ) * kSensorOverlapCap, refs + (size_t)( 2 * last ) * kSensorOverlapCap,
-				sizeof( ShapeRef ) * 2 * kSensorOverlapCap );
+		memcpy( refs + (size_t)( 2 * index ) * w->sensorOverlapCap, refs + (size_t)( 2 * last ) * w->sensorOverlapCap,
+				sizeof( ShapeRef ) * 2 * w->sensorOverlapCap );
 		ptr( w, w->shapes )[sensors[index].shapeId].sensorIndex = index;
 	}
 	w->sensors.count -= 1;
-	w->sensorRefs.count = 2 * kSensorOverlapCap * w->sensors.count;
+	w->sensorRefs.count = 2 * w->sensorOverlapCap * w->sensors.count;
 	sensorShape.sensorIndex = kNull;
 }
 

@@ -29,6 +29,7 @@ template <class Team> F2D_HDF inline void stepBegin( World* w, Team& t, float dt
 		w->hitEvents.count = 0;
 		w->taskCount = 0;
 		w->locked = true;
+		w->error &= ~kErrTruncated; // per-step flag
 
 		// step context: world.c:742-771
 		StepCtx& s = w->step;
@@ -484,7 +485,7 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 			ev.a = makeShapeId( w, shapeA );
 			ev.b = makeShapeId( w, shapeB );
 			ev.manifold = unpackManifold( sim.manifold );
-			F2D_PUSH( w, w->beginEvents, ev );
+			F2D_PUSH_EVENT( w, w->beginEvents, ev );
 		}
 		c.flags |= kContactTouching;
 		linkContact( w, c );
@@ -502,7 +503,7 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 		if ( c.flags & kContactEnableContactEvents )
 		{
 			EndTouchEvent ev = { makeShapeId( w, shapeA ), makeShapeId( w, shapeB ) };
-			F2D_PUSH( w, w->endEvents[w->endEventArrayIndex], ev );
+			F2D_PUSH_EVENT( w, w->endEvents[w->endEventArrayIndex], ev );
 		}
 		unlinkContact( w, c );
 		int bodyIdA = c.edges[0].bodyId;
@@ -2395,7 +2396,7 @@ F2D_HDF inline void reportHitEvents( World* w )
 				ev.normal = manifold.normal;
 				ev.a = makeShapeId( w, shapes[sim.shapeIdA] );
 				ev.b = makeShapeId( w, shapes[sim.shapeIdB] );
-				F2D_PUSH( w, w->hitEvents, ev );
+				F2D_PUSH_EVENT( w, w->hitEvents, ev );
 			}
 		}
 	}
@@ -2404,7 +2405,7 @@ F2D_HDF inline void reportHitEvents( World* w )
 // ------------------------------------------------------------------------------------------------ sensors
 F2D_HD ShapeRef* sensorList( World* w, int sensorIndex, int which )
 {
-	return ptr( w, w->sensorRefs ) + (size_t)( 2 * sensorIndex + which ) * kSensorOverlapCap;
+	return ptr( w, w->sensorRefs ) + (size_t)( 2 * sensorIndex + which ) * w->sensorOverlapCap;
 }
 
 // One sensor shape: sensor.c:101-212. Swaps its overlap lists, queries the three trees with the shape's AABB, keeps
@@ -2449,9 +2450,10 @@ F2D_HDF inline void sensorTask( World* w, int sensorIndex )
 		DistanceOutput out = shapeDistance( sensorProxy, makeShapeProxy( other ), transform, otherTransform, true, &cache );
 		if ( ( out.distance < 10.0f * FLT_EPSILON ) == false )
 			return true;
-		if ( count2 >= kSensorOverlapCap )
+		if ( count2 >= w->sensorOverlapCap )
 		{
-			setError( w, kErrCapacity, __LINE__ );
+			// cannot happen while the capacity follows the shape count (f2d_image.h); a capped world drops the overlap
+			setError( w, kErrTruncated, __LINE__ );
 			return true;
 		}
 		refs2[count2].shapeId = shapeId;
@@ -2492,11 +2494,11 @@ F2D_HDF inline void sensorEvents( World* w, int sensorIndex )
 	const ShapeRef* refs2 = sensorList( w, sensorIndex, sensor.flip );
 	auto ended = [&]( const ShapeRef& r ) {
 		SensorEvent ev = { sensorId, ShapeId{ r.shapeId + 1, w->worldId, r.generation } };
-		F2D_PUSH( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
+		F2D_PUSH_EVENT( w, w->sensorEndEvents[w->endEventArrayIndex], ev );
 	};
 	auto began = [&]( const ShapeRef& r ) {
 		SensorEvent ev = { sensorId, ShapeId{ r.shapeId + 1, w->worldId, r.generation } };
-		F2D_PUSH( w, w->sensorBeginEvents, ev );
+		F2D_PUSH_EVENT( w, w->sensorBeginEvents, ev );
 	};
 	int i1 = 0, i2 = 0;
 	while ( i1 < sensor.count1 && i2 < sensor.count2 )

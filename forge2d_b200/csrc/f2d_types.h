@@ -371,9 +371,11 @@ struct alignas( 32 ) ContactSim
 	int32_t pad1, pad2;
 };
 static_assert( sizeof( ContactSim ) == 192, "ContactSim layout" );
-// B2/src/sensor.h:11-24. The two overlap lists of a sensor are fixed-capacity blocks of World::sensorRefs
-// (block = sensor index * 2 * kSensorOverlapCap, second list kSensorOverlapCap further); `flip` says which is "overlaps2".
-constexpr int kSensorOverlapCap = 64;
+// B2/src/sensor.h:11-24. The two overlap lists of a sensor are blocks of World::sensorRefs
+// (block = sensor index * 2 * World::sensorOverlapCap, second list sensorOverlapCap further); `flip` says which is
+// "overlaps2". The per-sensor capacity follows the number of shapes of the world (f2d_image.h: an overlap list can never
+// hold more), so a level-wide trigger region cannot overflow it.
+constexpr int kMinSensorOverlapCap = 64;
 struct ShapeRef
 {
 	int32_t shapeId;
@@ -576,6 +578,7 @@ struct StepCtx
 	int32_t orderedPairCount; // callback-mediated step: candidate pairs in creation order, waiting for the host's custom filter
 	int32_t preSolveCount;	  // callback-mediated step: touching contacts waiting for the host's pre-solve verdict
 	int32_t fastDeferredCount; // callback-mediated step: fast bodies whose continuous pass waits for the host's custom filter
+	int32_t padStep;
 	int32_t bodiesFinalized;   // stepSolve ran the body loop of finalize beside the island split; stepFinalize only casts the votes
 	int32_t retryContacts;	   // != 0: the step stopped before its first structural edit because the contact arrays cannot take
 							   // this many new contacts (kErrRetry); the host grows the image and runs the step again
@@ -670,8 +673,12 @@ enum : uint32_t
 	kErrTreeStack = 2,		 // traversal stack overflow
 	kErrUnsupported = 4,	 // feature not available on the device path
 	kErrSleepPool = 8,
-	kErrRetry = 16 // not an error for a single world (b2World_Step grows the image and repeats the step); a batch reports it
+	kErrRetry = 16, // not an error for a single world (b2World_Step grows the image and repeats the step); a batch reports it
+	// Per-step flag, cleared when the next step begins, never stops the stepping: an event or a sensor overlap did not fit
+	// its array and was dropped (the simulation itself is unaffected)
+	kErrTruncated = 32
 };
+constexpr uint32_t kErrFatal = kErrCapacity | kErrUnsupported; // a world with one of these set is not stepped any more
 
 // World parameters + every array. Reference: B2/src/world.h:44-175.
 struct World
@@ -691,6 +698,7 @@ struct World
 	bool enableSleep, locked, enableWarmStarting, enableContinuous, enableSpeculative, inUse;
 	uint8_t hostCallbacks; // kHostCustomFilter | kHostPreSolve (| kHostMixing: unsupported): the step runs callback-mediated
 	int32_t taskCount;
+	int32_t sensorOverlapCap;	 // capacity of one overlap list of one sensor (World::sensorRefs)
 	int32_t hitEventCapable;	 // shapes with enableHitEvents (hit-event scan is skipped when 0)
 	int32_t contactEventCapable; // shapes with enableContactEvents (sizes the begin/end event arrays)
 
@@ -824,6 +832,18 @@ template <class T> F2D_HD int push( World* w, Arr<T>& a, const T& v, int line )
 	return a.count++;
 }
 #define F2D_PUSH( w, arr, v ) ::f2d::push( w, arr, v, __LINE__ )
+// an event record: when the array is full the event is dropped and the world flagged kErrTruncated (per-step, not fatal)
+template <class T> F2D_HD void pushEvent( World* w, Arr<T>& a, const T& v, int line )
+{
+	if ( a.count >= a.cap )
+	{
+		setError( w, kErrTruncated, line );
+		return;
+	}
+	ptr( w, a )[a.count] = v;
+	a.count += 1;
+}
+#define F2D_PUSH_EVENT( w, arr, v ) ::f2d::pushEvent( w, arr, v, __LINE__ )
 
 // swap-remove with the reference's semantics (B2/src/array.h:91-103): returns the index that moved or kNull
 template <class T> F2D_HD int removeSwap( World* w, Arr<T>& a, int index )

@@ -1079,7 +1079,7 @@ F2D_HDF inline void destroyContact( World* w, int contactId, bool wakeBodies )
 	{
 		const Shape* shapes = ptr( w, w->shapes );
 		EndTouchEvent ev = { makeShapeId( w, shapes[c.shapeIdA] ), makeShapeId( w, shapes[c.shapeIdB] ) };
-		F2D_PUSH( w, w->endEvents[w->endEventArrayIndex], ev );
+		F2D_PUSH_EVENT( w, w->endEvents[w->endEventArrayIndex], ev );
 	}
 
 	if ( edgeA.prevKey != kNull )

@@ -504,6 +504,9 @@ F2D_API void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn,
 typedef struct f2dBatch f2dBatch;
 /// Replicates the current state of `templateWorld` into `count` device-resident worlds (one image each).
 F2D_API f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count );
+/// A batch of DIFFERENT worlds (ids may repeat): all are brought to one common image layout and uploaded; the host
+/// worlds stay usable on their own. Worlds with host callbacks registered are refused (no host in a batch step).
+F2D_API f2dBatch* f2dBatch_CreateFromWorlds( const b2WorldId* worlds, int count );
 F2D_API void f2dBatch_Destroy( f2dBatch* batch );
 /// One b2World_Step for every world of the batch; a single kernel sequence, one thread block per world.
 F2D_API void f2dBatch_Step( f2dBatch* batch, float timeStep, int subStepCount );
@@ -532,6 +535,11 @@ F2D_API unsigned long long f2dBatch_GetWorldBytes( f2dBatch* batch ); ///< HBM b
 F2D_API void f2dBatch_DownloadWorld( f2dBatch* batch, int index, b2WorldId into );
 /// Per-world x-translation of every body by `index * dx` (decorrelates otherwise identical worlds).
 F2D_API uint32_t f2dBatch_GetErrorFlags( f2dBatch* batch );
+/// Error flags per world (0 = fine); returns how many worlds have a flag up. A world whose new contacts exceed its
+/// capacity never stays behind: the batch grows every image on the device and that world repeats the step
+/// (f2dBatch_GetGrowthCount counts how often that happened).
+F2D_API int f2dBatch_GetWorldErrors( f2dBatch* batch, uint32_t* out, int cap );
+F2D_API int f2dBatch_GetGrowthCount( f2dBatch* batch );
 
 /// Library diagnostics
 F2D_API int f2dHasDevice( void );			///< 1 when a CUDA device is usable
