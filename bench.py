@@ -34,6 +34,7 @@ from forge2d_b200 import scenes  # noqa: E402
 
 DT, SUB = scenes.TIME_STEP, scenes.SUB_STEPS
 PREROLL = 256  # bench2d.dart:53-57 warm-up frames
+DECORRELATION_STEPS = 60  # untimed steps after the worlds were translated apart: long enough for them to run out of phase
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbox2d_ref.so")
 
 
@@ -154,19 +155,30 @@ def load_reference():
     return lib
 
 
+def world_x_offset(k):
+    """Worlds of the batch are decorrelated as SURVEY §8(d) C5 proposes: world k is the bench2d scene translated by
+    k * 2^-10 along x - the same physics, different floating-point rounding, so the replicas drift apart (the settling
+    pile is chaotic) instead of marching through the phases of the step in lock-step, which no real batch does."""
+    if os.environ.get("F2D_BENCH_IDENTICAL_WORLDS"):
+        return 0.0
+    return k * 2.0 ** -10
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_batch(ref, sample_worlds, steps, warmup, threads):
-    """`sample_worlds` bench2d worlds at frame PREROLL stepped on `threads` host threads, one world per thread at a
-    time (1 Box2D worker each: the best case for the CPU). Returns world-steps/s."""
-    made = [scenes.bench2d(ref) for _ in range(sample_worlds)]
+def reference_batch(ref, sample_worlds, steps, warmup, threads, min_seconds=0.0):
+    """`sample_worlds` bench2d worlds, built at the x offsets of the batch's worlds (world_x_offset), at frame PREROLL, stepped on
+    `threads` host threads, one world per thread at a time (1 Box2D worker each: the best case for the CPU, BASELINE.md
+    §3.3). One "step" = every sampled world advanced `frames_per_step` frames, chosen so that the timed region of
+    `steps` steps lasts at least `min_seconds`. Returns (world-steps/s, seconds, frames_per_step)."""
+    made = [scenes.bench2d(ref, x_offset=world_x_offset(k)) for k in range(sample_worlds)]
     ids = (A.WorldId * sample_worlds)(*[s.world for s in made])
     ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, PREROLL, threads)
-    if warmup > 0:
-        ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, warmup, threads)
-    seconds = ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, steps, threads)
+    calibration = ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, max(2, warmup), threads) / max(2, warmup)
+    frames_per_step = max(1, int(math.ceil(min_seconds / max(1e-9, calibration * steps))))
+    seconds = ref.dll.tap_step_worlds(ids, sample_worlds, DT, SUB, steps * frames_per_step, threads)
     for s in made:
         s.destroy()
-    return sample_worlds * steps / seconds, seconds
+    return sample_worlds * steps * frames_per_step / seconds, seconds, frames_per_step
 
 
 def reference_single(ref, scene_name, kw, warm, timed, workers):
@@ -194,29 +206,34 @@ def run_reference_arm(args, rank):
         return
     ref = load_reference()
     cores = host_cores()
-    sample = args.ref_worlds or max(cores, min(8 * cores, 512))
-    value, seconds = reference_batch(ref, sample, args.steps, args.warmup, cores)
+    sample = args.ref_worlds or cpu_sample_worlds(cores)
+    value, seconds, frames = reference_batch(ref, sample, args.steps, args.warmup, cores, min_seconds=3.0)
     line = {
         "impl": "reference", "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, sample_note="reference arm steps a bounded sample of %d worlds" % sample),
+        "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": cores, "kind": "reference",
-                         "sample": "%d bench2d worlds at frame %d, %d steps each, one single-worker world per thread on %d "
-                                   "threads (%s)" % (sample, PREROLL, args.steps, cores, cpu_model())},
+                         "sample": "%d of the %d bench2d worlds (the first ones: built at their x offsets, frame %d), one step = %d frames of "
+                                   "every sampled world, %d steps timed = %.1f s, one single-worker world per thread on %d "
+                                   "threads" % (sample, args.worlds, PREROLL, frames, args.steps, seconds, cores)},
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"cores": cores, "cpu_model": cpu_model()},
     }
     _emit(json.dumps(line))
 
 
-def workload_config(args, sample_note=None):
-    cfg = {"workload": "bench2d_batch: %d independent bench2d worlds (40-row pyramid, 820 boxes, dt=1/60, 4 sub-steps) "
-                       "pre-rolled %d frames, sharded by world across ranks" % (args.worlds, PREROLL),
-           "worlds": args.worlds, "bodies_per_world": 821, "substeps": SUB, "parallelism": "world-sharded x%d" % args.gpus,
-           "l2": "inputs larger than L2 (every world image is touched once per step; batch >> 126 MB)"}
-    if sample_note:
-        cfg["sample"] = sample_note
-    return cfg
+def cpu_sample_worlds(cores):
+    """Worlds in the bounded CPU sample (the same for the cpu_baseline leg and the reference arm)."""
+    return max(cores, min(16 * cores, 256))
+
+
+def workload_config(args):
+    return {"workload": "bench2d_batch: %d independent bench2d worlds (40-row pyramid, 820 boxes, dt=1/60, 4 sub-steps) "
+                        "pre-rolled %d frames, decorrelated (world k translated by k * 2^-10 along x), sharded by world across "
+                        "ranks" % (args.worlds, PREROLL),
+            "worlds": args.worlds, "bodies_per_world": 821, "substeps": SUB, "parallelism": "world-sharded x%d" % args.gpus,
+            "l2": "inputs larger than L2 (every world image is touched once per step; batch >> 126 MB)"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
@@ -287,7 +304,15 @@ def run_b200_arm(args, rank, world_size, local_rank):
     if not lib.f2dBatch_SetLaunchConfig(batch, args.batch_threads, args.batch_blocks_per_sm):
         raise RuntimeError("bench: unknown batch launch config %dx%d" % (args.batch_threads, args.batch_blocks_per_sm))
 
-    lib.f2dBatch_StepN(batch, DT, SUB, args.warmup)
+    # decorrelate the worlds (world_x_offset; global world index, so every rank count gives the same batch) and let
+    # them drift out of phase before anything is timed
+    offsets = (A.Vec2 * mine)(*[A.Vec2(world_x_offset(lo + i), 0.0) for i in range(mine)])
+    lib.f2dBatch_TranslateWorlds(batch, offsets, mine)
+    gravity = lib.f2dHostAlloc(8 * mine)
+    grav = (A.Vec2 * mine).from_address(gravity)
+    for i in range(mine):
+        grav[i] = A.Vec2(0.0, -10.0)
+    lib.f2dBatch_StepN(batch, DT, SUB, args.warmup + DECORRELATION_STEPS)
     lib.f2dBatch_Synchronize(batch)
 
     sampler = ClockSampler(local_rank)
@@ -316,10 +341,6 @@ def run_b200_arm(args, rank, world_size, local_rank):
     # ---- end to end through the C ABI with host buffers
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     nb = counts0["bodies"]
-    gravity = lib.f2dHostAlloc(8 * mine)
-    grav = (A.Vec2 * mine).from_address(gravity)
-    for i in range(mine):
-        grav[i] = A.Vec2(0.0, -10.0)
     ev_ptr, cnt_ptr = C.POINTER(A.BodyMoveEvent)(), C.POINTER(C.c_int)()
     lib.f2dBatch_SetGravity(batch, gravity, mine)
     lib.f2dBatch_Step(batch, DT, SUB)
@@ -339,10 +360,14 @@ def run_b200_arm(args, rank, world_size, local_rank):
     lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
     barrier()
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(e2e_steps):
+        t1 = time.perf_counter()
         lib.f2dBatch_SetGravity(batch, gravity, mine)
         moved = lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+        e2e_step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    growths = lib.f2dBatch_GetGrowthCount(batch)
     barrier()
     e2e_value = args.worlds * e2e_steps / e2e_seconds
     e2e_sequential_value = args.worlds * e2e_steps / e2e_sequential_seconds
@@ -381,6 +406,7 @@ def run_b200_arm(args, rank, world_size, local_rank):
                 "path": "f2dBatch_SetGravity (pinned H2D) + f2dBatch_StepAndReadBodyEvents (step in world slices on "
                         "separate streams, pinned D2H of every body transform of a slice overlapped with the stepping of "
                         "the next), per rank; events read per step: %d" % moved,
+                "ms_per_step_each": e2e_step_ms,
                 "sequential_calls_value": e2e_sequential_value,
                 "sequential_calls_path": "f2dBatch_SetGravity + f2dBatch_Step + f2dBatch_ReadBodyEvents, nothing overlapped"},
         "gpu_launches": int(launches),
@@ -388,10 +414,12 @@ def run_b200_arm(args, rank, world_size, local_rank):
                      "traffic": traffic, "kernel": "stepWorldsCta<%d,%d> (whole world step, one CTA per world)" % (args.batch_threads, args.batch_blocks_per_sm),
                      "algorithmic_bytes_per_world_step": bytes_per_world_step, "worlds_per_launch": mine,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                     "note": "latency-bound, not bandwidth-bound: chains of dependent gathers per body / contact / tree node; "
-                             "no memory pipe above 35 %% (profiles/README.md); %.1f MB image per world" % (world_bytes / 1e6)},
+                     "note": "random 32-byte sector gathers: the narrowphase keeps DRAM busy 96 %% of its time at 3.9 TB/s of "
+                             "sector traffic, the other phases are latency-bound (profiles/README.md); %.1f MB image per "
+                             "world" % (world_bytes / 1e6)},
         "clocks": clocks,
         "batch": {"worlds_this_rank": mine, "bytes_per_world_image": int(world_bytes), "error_flags": int(errors),
+                  "image_growths": int(growths),
                   "counts_before": counts0, "counts_after": counts1},
     }
 
@@ -399,17 +427,20 @@ def run_b200_arm(args, rank, world_size, local_rank):
     cores = host_cores()
     if world_size == 1 and not args.no_cpu_baseline:
         ref = load_reference()
-        sample = args.ref_worlds or max(cores, min(16 * cores, 256))
-        cpu_steps = 256  # bounded sample: ~64k world-steps, a few seconds on 16 cores after the pre-roll
-        v, seconds = reference_batch(ref, sample, cpu_steps, 2, cores)
+        sample = args.ref_worlds or cpu_sample_worlds(cores)
+        v, seconds, frames = reference_batch(ref, sample, args.steps, 2, cores, min_seconds=3.0)
         line["cpu_baseline"] = {"value": v, "unit": "world-steps/s", "cores": cores, "kind": "reference",
-                                "sample": "%d bench2d worlds at frame %d x %d steps, one single-worker world per thread "
-                                          "on %d threads (%s), %.1f s" % (sample, PREROLL, cpu_steps, cores,
-                                                                          cpu_model(), seconds)}
+                                "sample": "%d of the %d bench2d worlds (the first ones: built at their x offsets, frame %d), %d steps of "
+                                          "%d frames each = %.1f s, one single-worker world per thread on %d threads (%s)"
+                                          % (sample, args.worlds, PREROLL, args.steps, frames, seconds, cores, cpu_model())}
+        line["host"] = {"cores": cores, "cpu_model": cpu_model()}
     if world_size == 1 and not args.no_extras:
         extras = {}
         extras["bench2d"] = single_world_numbers(lib, ref, "bench2d", {}, 256, 256, 0, cores)
-        extras["large_pyramid"] = single_world_numbers(lib, ref, "large_pyramid", {}, 32, 64, 1, cores)
+        # frames 150-400: the bottom row reaches the ground at frame ~147, so this window is the impact and the collapse
+        # (hundreds of begin / end touch events per step, island merges, continuous collision), not the free fall
+        extras["large_pyramid"] = single_world_numbers(lib, ref, "large_pyramid", {}, 150, 250, 1, cores)
+        extras["large_pyramid"]["window"] = "frames 150-400 (impact and collapse)"
         extras["many_pyramids_awake"] = single_world_numbers(lib, ref, "many_pyramids", {}, 2, 24, 1, cores)
         extras["joint_grid"] = single_world_numbers(lib, ref, "joint_grid", {}, 8, 32, 1, cores)
         line["single_world"] = extras

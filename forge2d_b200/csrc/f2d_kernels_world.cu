@@ -100,6 +100,49 @@ __global__ void relayoutWorlds( const char* oldBase, unsigned long long oldStrid
 	}
 }
 
+// Translates every world of a batch by its own offset: bodies (origin, centre of mass, sweep start), shape boxes and
+// the boxes of all broadphase tree nodes. One block per world. Nothing else in the image holds world coordinates that
+// the step reads (manifold anchors are relative to the bodies; joint frames are local).
+__global__ void translateWorlds( char* base, unsigned long long stride, int worldCount, const V2* offsets )
+{
+	const int wi = (int)blockIdx.x;
+	if ( wi >= worldCount )
+		return;
+	World* w = reinterpret_cast<World*>( base + (unsigned long long)wi * stride );
+	char* image = reinterpret_cast<char*>( w );
+	const V2 d = offsets[wi];
+	BodySim* sims = reinterpret_cast<BodySim*>( image + w->sims.off );
+	const Body* bodies = reinterpret_cast<const Body*>( image + w->bodies.off );
+	for ( int i = (int)threadIdx.x; i < w->bodies.count; i += (int)blockDim.x )
+	{
+		if ( bodies[i].id != i )
+			continue;
+		BodySim& s = sims[i];
+		s.transform.p = add( s.transform.p, d );
+		s.center = add( s.center, d );
+		s.center0 = add( s.center0, d );
+	}
+	Shape* shapes = reinterpret_cast<Shape*>( image + w->shapes.off );
+	for ( int i = (int)threadIdx.x; i < w->shapes.count; i += (int)blockDim.x )
+	{
+		Shape& s = shapes[i];
+		if ( s.id != i )
+			continue;
+		s.aabb = Box{ add( s.aabb.lo, d ), add( s.aabb.hi, d ) };
+		s.fatAABB = Box{ add( s.fatAABB.lo, d ), add( s.fatAABB.hi, d ) };
+	}
+	for ( int t = 0; t < 3; ++t )
+	{
+		TreeNode* nodes = reinterpret_cast<TreeNode*>( image + w->trees[t].nodes.off );
+		for ( int i = (int)threadIdx.x; i < w->trees[t].nodes.count; i += (int)blockDim.x )
+		{
+			TreeNode& n = nodes[i];
+			if ( n.flags & kNodeAllocated )
+				n.box = Box{ add( n.box.lo, d ), add( n.box.hi, d ) };
+		}
+	}
+}
+
 constexpr int kSingleCtaThreads = 1024;
 
 // The one-block kernel gets a shared-memory work area (CtaTeam::arena): the block has the SM to itself.
@@ -144,6 +187,10 @@ void launchRelayoutWorlds( const char* oldBase, unsigned long long oldStride, ch
 						   const RelayoutSlot* slots, int slotCount, const World* newHeader, cudaStream_t stream )
 {
 	relayoutWorlds<<<worldCount, 256, 0, stream>>>( oldBase, oldStride, newBase, newStride, worldCount, slots, slotCount, newHeader );
+}
+void launchTranslateWorlds( char* base, unsigned long long stride, int worldCount, const void* offsets, cudaStream_t stream )
+{
+	translateWorlds<<<worldCount, 256, 0, stream>>>( base, stride, worldCount, static_cast<const V2*>( offsets ) );
 }
 void launchGatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out, cudaStream_t stream )
 {

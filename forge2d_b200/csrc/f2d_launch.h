@@ -43,6 +43,7 @@ void launchGatherWorldStatus( const char* base, unsigned long long stride, int w
 							 cudaStream_t stream );
 void launchRelayoutWorlds( const char* oldBase, unsigned long long oldStride, char* newBase, unsigned long long newStride, int worldCount,
 						   const RelayoutSlot* slots, int slotCount, const World* newHeader, cudaStream_t stream );
+void launchTranslateWorlds( char* base, unsigned long long stride, int worldCount, const void* offsets, cudaStream_t stream );
 // gather kernels of the batch extension
 struct BodyMoveEvent;
 void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,

@@ -48,14 +48,15 @@ def _box(lib, half):
     return lib.b2MakeOffsetRoundedBox(half, half, A.Vec2(0.0, 0.0), A.Rot(1.0, 0.0), 0.0)
 
 
-def bench2d(lib, rows=40, ground_half_width=40.0, create=None, **world_kw):
-    """C1: packages/benchmark/bin/bench2d.dart:29-51 — `rows`-high pyramid of 0.5 half-extent boxes, density 5."""
+def bench2d(lib, rows=40, ground_half_width=40.0, create=None, x_offset=0.0, **world_kw):
+    """C1: packages/benchmark/bin/bench2d.dart:29-51 — `rows`-high pyramid of 0.5 half-extent boxes, density 5.
+    `x_offset` builds the same scene translated along x (decorrelated replicas: same physics, different rounding)."""
     world = _world(lib, create=create, **world_kw)
-    bodies = [_static_segment(lib, world, (-ground_half_width, -30.0), (ground_half_width, -30.0))]
+    bodies = [_static_segment(lib, world, (_f32(x_offset - ground_half_width), -30.0), (_f32(x_offset + ground_half_width), -30.0))]
     box = _box(lib, 0.5)
     sd = lib.b2DefaultShapeDef()
     sd.density = 5.0
-    x = [-7.0, 0.75]
+    x = [_f32(-7.0 + x_offset), 0.75]
     dxx, dxy = 0.5625, 1.0
     for i in range(rows):
         y = list(x)

@@ -527,6 +527,9 @@ F2D_API int f2dBatch_StepAndReadBodyEvents( f2dBatch* batch, float timeStep, int
 											const b2BodyMoveEvent** outEvents, const int** outCounts );
 /// Per-world gravity: the batch counterpart of b2World_SetGravity (box2d.h:135); `gravity` holds `count` vectors.
 F2D_API void f2dBatch_SetGravity( f2dBatch* batch, const b2Vec2* gravity, int count );
+/// Translates every body, shape box and broadphase box of world k by offsets[k]: replicas placed side by side, or
+/// decorrelated (same physics, different floating-point rounding).
+F2D_API void f2dBatch_TranslateWorlds( f2dBatch* batch, const b2Vec2* offsets, int count );
 /// CUDA events on the batch's stream (slots 0..7) so callers can time device work without a torch stream.
 F2D_API void f2dBatch_EventRecord( f2dBatch* batch, int slot );
 F2D_API float f2dBatch_EventElapsedMs( f2dBatch* batch, int fromSlot, int toSlot );

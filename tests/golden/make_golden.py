@@ -15,7 +15,7 @@ from forge2d_b200 import scenes  # noqa: E402
 # scene, kwargs, frames at which a hash is recorded
 CASES = [
     ("bench2d", {}, [1, 64, 160, 256, 512]),
-    ("large_pyramid", {}, [1, 32, 128]),
+    ("large_pyramid", {}, [1, 32, 128, 160, 256, 400]),  # 160-400: the impact and the collapse (bottom row lands at ~147)
     ("many_pyramids", {}, [1, 16, 48]),
     ("joint_grid", {}, [1, 16, 64]),
     ("falling_shapes", {"count": 24}, [1, 100, 240]),

@@ -107,6 +107,30 @@ def test_wake_through_api_after_sleep(ref, gpu):
         assert d == [], "frame %d after wake: %s" % (f, d[:6])
 
 
+def test_large_pyramid_through_the_impact(ref, gpu):
+    """5050 boxes (BASELINE config 2) in lock-step with the reference THROUGH the landing of the bottom row (frame ~147)
+    and the collapse that follows: hundreds of begin / end touch events per step, island merges, the ordered contact
+    state pass at scale, continuous collision. Events are compared every frame from 140 on, every record every 8th."""
+    a = scenes.large_pyramid(ref)
+    b = scenes.large_pyramid(gpu)
+    contacts = {}
+    for f in range(1, 301):
+        a.step()
+        b.step()
+        if f >= 140:
+            ea, eb = H.events(ref, a.world), H.events(gpu, b.world)
+            assert ea["begin"] == eb["begin"] and ea["end"] == eb["end"] and ea["hit"] == eb["hit"], "frame %d: events" % f
+            if f % 8 == 0 or f in (147, 148, 149, 150):
+                sb = H.snapshot(gpu, b.world)
+                d = H.diff(H.snapshot(ref, a.world), sb)
+                assert d == [], "frame %d: %s" % (f, d[:6])
+                contacts[f] = int(sb["color_contact_counts"].sum())
+    assert gpu.f2dGetLastError() == b""
+    # free fall: 9900 touching contacts (rows resting on each other); the landing adds the ground contacts and the
+    # collapse keeps changing the set
+    assert contacts[144] == 9900 and contacts[160] > 9900 and len(set(contacts.values())) > 10, contacts
+
+
 def test_zero_dt_and_substep_variants(ref, gpu):
     a = scenes.bench2d(ref, rows=8)
     b = scenes.bench2d(gpu, rows=8)
