@@ -301,7 +301,7 @@ def run_b200_arm(args, rank, world_size, local_rank):
     if not batch:
         raise RuntimeError("bench: f2dBatch_Create failed: %s" % lib.f2dGetLastError().decode())
     world_bytes = lib.f2dBatch_GetWorldBytes(batch)
-    if not lib.f2dBatch_SetLaunchConfig(batch, args.batch_threads, args.batch_blocks_per_sm):
+    if args.batch_threads and not lib.f2dBatch_SetLaunchConfig(batch, args.batch_threads, args.batch_blocks_per_sm):
         raise RuntimeError("bench: unknown batch launch config %dx%d" % (args.batch_threads, args.batch_blocks_per_sm))
 
     # decorrelate the worlds (world_x_offset; global world index, so every rank count gives the same batch) and let
@@ -411,7 +411,8 @@ def run_b200_arm(args, rank, world_size, local_rank):
                 "sequential_calls_path": "f2dBatch_SetGravity + f2dBatch_Step + f2dBatch_ReadBodyEvents, nothing overlapped"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "stepWorldsCta<%d,%d> (whole world step, one CTA per world)" % (args.batch_threads, args.batch_blocks_per_sm),
+                     "traffic": traffic, "kernel": ("stepWorldsCta<%d,%d> (whole world step, one CTA per world)" % (args.batch_threads, args.batch_blocks_per_sm))
+                     if args.batch_threads else "stepWorldsGang<128,7> (whole world step, seven worlds per CTA, phase-aligned)",
                      "algorithmic_bytes_per_world_step": bytes_per_world_step, "worlds_per_launch": mine,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "note": "random 32-byte sector gathers: the narrowphase keeps DRAM busy 96 %% of its time at 3.9 TB/s of "
@@ -465,7 +466,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--worlds", type=int, default=8192, help="total worlds of the batch (sharded across ranks)")
     ap.add_argument("--e2e-steps", type=int, default=8)
-    ap.add_argument("--batch-threads", type=int, default=128, help="threads per world of the batch kernel")
+    ap.add_argument("--batch-threads", type=int, default=0,
+                    help="0: the default batch kernel (several worlds per block, phase-aligned); else threads per world of "
+                         "the one-world-per-block kernel")
     ap.add_argument("--batch-blocks-per-sm", type=int, default=8, help="resident worlds per SM the kernel is built for")
     ap.add_argument("--ref-worlds", type=int, default=0, help="worlds in the CPU sample (0 = scaled to the host cores)")
     ap.add_argument("--no-extras", action="store_true", help="skip the single-world configurations")

@@ -519,6 +519,7 @@ F2D_FUNCTIONS = {
     "f2dBatch_CreateFromWorlds": (c_void_p, [C.POINTER(WorldId), c_int]),
     "f2dBatch_GetWorldErrors": (c_int, [c_void_p, C.POINTER(C.c_uint32), c_int]),
     "f2dBatch_GetGrowthCount": (c_int, [c_void_p]),
+    "f2dBatch_SetGangMode": (None, [c_void_p, c_int]),
     "f2dBatch_TranslateWorlds": (None, [c_void_p, c_void_p, c_int]),
     "f2dHasDevice": (c_int, []),
     "f2dGetLastError": (C.c_char_p, []),

@@ -309,6 +309,10 @@ struct f2dBatch
 	unsigned int* devStatus = nullptr;
 	unsigned int* devWorldFlags = nullptr;
 	int growths = 0;
+	// Launch mode: several worlds per block with phase-aligned teams (stepWorldsGang, the default), or one world per
+	// block in the configuration `threads` x `blocksPerSM` (f2dBatch_SetLaunchConfig)
+	bool gang = true;
+	int* devQueue = nullptr; // world queues of the gang kernel: [0] the batch stream, [1 + i] slice i
 	bool checkEveryStep = false; // (the last step of a call is checked by f2dBatch_Synchronize: StepN itself never blocks on it)
 	bool pendingStatus = false;
 	float pendingDt = 0.0f;
@@ -317,8 +321,18 @@ struct f2dBatch
 
 namespace f2d
 {
+// One step of `n` worlds starting at `base` on `stream` (`onlyRetry`: only the worlds that stopped for contact room)
+static bool batchLaunchStep( f2dBatch* b, char* base, int n, float dt, int sub, bool onlyRetry, int queueIndex, cudaStream_t stream )
+{
+	g_launchCount += 1;
+	if ( b->gang )
+		return launchBatchStepGang( base, b->stride, n, dt, sub, onlyRetry ? 1 : 0, g_smCount, b->devQueue + queueIndex, stream );
+	return launchBatchStep( b->threads, b->blocksPerSM, base, b->stride, n, dt, sub, onlyRetry ? -1 : 1, stream );
+}
+
 static void batchInitStatus( f2dBatch* b )
 {
+	cudaMalloc( &b->devQueue, ( f2dBatch::kSlices + 1 ) * sizeof( int ) );
 	cudaMalloc( &b->devError, sizeof( unsigned int ) );
 	cudaMemsetAsync( b->devError, 0, sizeof( unsigned int ), b->stream );
 	cudaMalloc( &b->devStatus, 2 * sizeof( unsigned int ) );
@@ -402,8 +416,7 @@ static unsigned int batchResolveRetries( f2dBatch* b, float dt, int sub )
 	{
 		if ( batchGrow( b, need ) == false )
 			break;
-		launchBatchStep( b->threads, b->blocksPerSM, b->dev, b->stride, b->count, dt, sub, -1, b->stream );
-		g_launchCount += 1;
+		batchLaunchStep( b, b->dev, b->count, dt, sub, true, 0, b->stream );
 		flags = batchStatus( b, &need );
 	}
 	if ( flags & ( kErrFatal | kErrRetry ) )
@@ -559,6 +572,7 @@ void f2dBatch_Destroy( f2dBatch* b )
 	cudaFree( b->devError );
 	cudaFree( b->devStatus );
 	cudaFree( b->devWorldFlags );
+	cudaFree( b->devQueue );
 	if ( b->hostStatus )
 		cudaFreeHost( b->hostStatus );
 	if ( b->hostEvents )
@@ -588,12 +602,11 @@ void f2dBatch_StepN( f2dBatch* b, float dt, int sub, int steps )
 	// one launch per step keeps every world of the batch in lock-step (and gives ncu one launch per step)
 	for ( int s = 0; s < steps; ++s )
 	{
-		if ( launchBatchStep( b->threads, b->blocksPerSM, b->dev, b->stride, b->count, dt, sub, 1, b->stream ) == false )
+		if ( batchLaunchStep( b, b->dev, b->count, dt, sub, false, 0, b->stream ) == false )
 		{
 			reportError( "f2dBatch_Step: no batch kernel for %d threads x %d blocks/SM", b->threads, b->blocksPerSM );
 			return;
 		}
-		g_launchCount += 1;
 		// one cheap flag gather per step (queued behind it): a world that needs more contact room must get it before the
 		// NEXT step, or it would fall behind the others. The host only waits when a flag is up.
 		cudaMemsetAsync( b->devStatus, 0, 2 * sizeof( unsigned int ), b->stream );
@@ -623,7 +636,15 @@ int f2dBatch_SetLaunchConfig( f2dBatch* b, int threads, int blocksPerSM )
 		return 0;
 	b->threads = threads;
 	b->blocksPerSM = blocksPerSM;
+	b->gang = false;
 	return 1;
+}
+
+// 1 (default): several worlds per thread block, phase-aligned (stepWorldsGang); 0: one world per block
+void f2dBatch_SetGangMode( f2dBatch* b, int on )
+{
+	if ( b )
+		b->gang = on != 0;
 }
 
 void f2dBatch_Step( f2dBatch* b, float dt, int sub )
@@ -810,7 +831,7 @@ int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodie
 		if ( n > 0 )
 		{
 			char* base = b->dev + b->stride * (unsigned long long)start;
-			if ( launchBatchStep( b->threads, b->blocksPerSM, base, b->stride, n, dt, sub, 1, st ) == false )
+			if ( batchLaunchStep( b, base, n, dt, sub, false, 1 + i, st ) == false )
 			{
 				reportError( "f2dBatch_StepAndReadBodyEvents: no batch kernel for %d threads x %d blocks/SM", b->threads, b->blocksPerSM );
 				return 0;
@@ -821,7 +842,7 @@ int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodie
 			launchGatherMoveEvents( base, b->stride, n, devOut, maxBodies, b->devCounts + start, st );
 			if ( dbgTimes )
 				cudaEventRecord( dbgEv[3 * i + 1], st );
-			g_launchCount += 2;
+			g_launchCount += 1;
 			cudaMemcpyAsync( b->hostEvents + (size_t)start * maxBodies, devOut, (size_t)n * maxBodies * sizeof( BodyMoveEvent ),
 							 cudaMemcpyDeviceToHost, st );
 			cudaMemcpyAsync( b->hostCounts + start, b->devCounts + start, (size_t)n * sizeof( int ), cudaMemcpyDeviceToHost, st );

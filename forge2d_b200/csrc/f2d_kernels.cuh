@@ -15,54 +15,66 @@ namespace f2d
 {
 
 // ------------------------------------------------------------------------------------------------ device teams
-// The threads of a block minus its last warp, synchronised with a named barrier: lets the last warp run a serial side
-// task (island split) concurrently with barrier-separated solver stages.
+// A team of threads inside one thread block: the whole block (one world per block), or one of several equal slices
+// of a block that steps several worlds side by side (stepWorldsGang). Slices are whole warps; every team has its own
+// hardware barrier (bar.sync id, count), its own shared scratch, and a second barrier for its crew.
+//
+// The crew = the team minus its last warp: lets that warp run a serial side task (island split) concurrently with the
+// barrier-separated solver stages.
 struct CtaCrew
 {
-	int n;
+	int n, tid, barId;
+	int32_t* arena;
+	int arenaInts;
+	__device__ int32_t* arenaPtr() const { return arena; }
+	__device__ int arenaSize() const { return arenaInts; }
 	__device__ int groupCount() const { return n >> 5; }
-	__device__ int groupIndex() const { return (int)( threadIdx.x >> 5 ); }
-	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
+	__device__ int groupIndex() const { return tid >> 5; }
+	__device__ int lane() const { return tid & 31; }
 	__device__ int groupSize() const { return 32; }
 	__device__ void groupSync() const { __syncwarp(); }
-	__device__ int rank() const { return (int)threadIdx.x; }
+	__device__ int rank() const { return tid; }
 	__device__ int size() const { return n; }
-	__device__ void sync() const { asm volatile( "bar.sync 1, %0;" ::"r"( n ) : "memory" ); }
+	__device__ void sync() const { asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( n ) : "memory" ); }
 };
 
 struct CtaTeam
 {
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = true;
-	// Forking pays when the crew keeps most of the block: with two warps the solver would run on one while the other
-	// walks (measured: the walking warp then waits ~2x its walk for the crew), so two-warp blocks walk first, then solve;
-	// from four warps up the crew of three or more hides the walk (measured at 128 threads: 8 % of warp time idle otherwise).
-	__device__ bool canFork() const { return blockDim.x >= 128; }
-	__device__ bool inSide() const { return threadIdx.x >= blockDim.x - 32; }
-	__device__ bool isSideLeader() const { return threadIdx.x == blockDim.x - 32; }
-	typedef WarpLanes Lanes;
-	__device__ bool inSideGroup() const { return threadIdx.x >= blockDim.x - 32; }
-	__device__ bool inFirstGroup() const { return threadIdx.x < 32; }
-	__device__ CtaCrew crew() const { return CtaCrew{ (int)blockDim.x - 32 }; }
-	__device__ int groupCount() const { return (int)( blockDim.x >> 5 ); }
-	__device__ int groupIndex() const { return (int)( threadIdx.x >> 5 ); }
-	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
-	__device__ int groupSize() const { return 32; }
-	__device__ void groupSync() const { __syncwarp(); }
-	int32_t* smem; // blockDim.x + 32 ints of shared scratch
+	int32_t* smem; // 64 ints of shared scratch owned by the team
+	int tid, nthreads; // rank inside the team, threads of the team
+	int barId, crewBarId; // hardware barriers of the team and of its crew (0 = the block's own barrier)
 	// Dynamic shared memory the block may use as a work area (0 in batches, where the resident worlds of an SM live on
 	// its L1; a single small world has the SM - and its 228 KB - to itself)
 	int32_t* arena = nullptr;
 	int arenaInts = 0;
+	// the whole block as one team
+	static __device__ CtaTeam block( int32_t* smem ) { return CtaTeam{ smem, (int)threadIdx.x, (int)blockDim.x, 0, 1 }; }
+	// Forking pays when the crew keeps most of the team: with two warps the solver would run on one while the other
+	// walks (measured: the walking warp then waits ~2x its walk for the crew), so two-warp teams walk first, then solve;
+	// from four warps up the crew of three or more hides the walk (measured at 128 threads: 8 % of warp time idle otherwise).
+	__device__ bool canFork() const { return nthreads >= 128; }
+	__device__ bool inSide() const { return tid >= nthreads - 32; }
+	__device__ bool isSideLeader() const { return tid == nthreads - 32; }
+	typedef WarpLanes Lanes;
+	__device__ bool inSideGroup() const { return tid >= nthreads - 32; }
+	__device__ bool inFirstGroup() const { return tid < 32; }
+	__device__ CtaCrew crew() const { return CtaCrew{ nthreads - 32, tid, crewBarId, arena, arenaInts }; }
+	__device__ int groupCount() const { return nthreads >> 5; }
+	__device__ int groupIndex() const { return tid >> 5; }
+	__device__ int lane() const { return tid & 31; }
+	__device__ int groupSize() const { return 32; }
+	__device__ void groupSync() const { __syncwarp(); }
 	__device__ int32_t* arenaPtr() const { return arena; }
 	__device__ int arenaSize() const { return arenaInts; }
-	__device__ int rank() const { return (int)threadIdx.x; }
-	__device__ int size() const { return (int)blockDim.x; }
-	__device__ void sync() const { __syncthreads(); }
-	// in-place exclusive scan of data[0..n) in global memory; returns the total. Block-wide collective.
+	__device__ int rank() const { return tid; }
+	__device__ int size() const { return nthreads; }
+	__device__ void sync() const { asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( nthreads ) : "memory" ); }
+	// in-place exclusive scan of data[0..n) in global memory; returns the total. Team-wide collective.
 	__device__ int exclusiveScan( int32_t* data, int n ) const
 	{
-		const int tid = (int)threadIdx.x, nt = (int)blockDim.x;
+		const int nt = nthreads;
 		int32_t* warpSums = smem; // 32 entries
 		int carry = 0;
 		for ( int base = 0; base < n; base += nt )
@@ -79,7 +91,7 @@ struct CtaTeam
 			}
 			if ( ( tid & 31 ) == 31 )
 				warpSums[tid >> 5] = x;
-			__syncthreads();
+			sync();
 			if ( tid < 32 )
 			{
 				int ws = tid < ( nt >> 5 ) ? warpSums[tid] : 0;
@@ -94,12 +106,12 @@ struct CtaTeam
 				if ( tid == 31 )
 					smem[32] = s; // chunk total
 			}
-			__syncthreads();
+			sync();
 			int excl = carry + warpSums[tid >> 5] + ( x - v );
 			if ( i < n )
 				data[i] = excl;
 			carry += smem[32];
-			__syncthreads();
+			sync();
 		}
 		return carry;
 	}
@@ -204,7 +216,7 @@ struct GridTeam
 	// the tree rebuild runs on block 0 alone (block-level barriers) while the other blocks do the narrowphase
 	__device__ bool inSoloBlock() const { return blockIdx.x == 0; }
 	__device__ bool hasOutsideSolo() const { return gridDim.x > 1; }
-	__device__ CtaTeam soloTeam() const { return CtaTeam{ smem }; }
+	__device__ CtaTeam soloTeam() const { return CtaTeam::block( smem ); }
 	__device__ int rankOutsideSolo() const { return (int)( ( blockIdx.x - 1 ) * blockDim.x + threadIdx.x ); }
 	__device__ int sizeOutsideSolo() const { return (int)( ( gridDim.x - 1 ) * blockDim.x ); }
 	__device__ int exclusiveScan( int32_t* data, int n )
@@ -214,7 +226,7 @@ struct GridTeam
 		const int tile = ( n + nb - 1 ) / nb;
 		const int begin = min( n, (int)blockIdx.x * tile );
 		const int end = min( n, begin + tile );
-		CtaTeam cta{ smem };
+		CtaTeam cta = CtaTeam::block( smem );
 		int total = cta.exclusiveScan( data + begin, end - begin );
 		if ( threadIdx.x == 0 )
 			blockTotals[blockIdx.x] = total;
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 	__shared__ int32_t smem[64];
 	__shared__ uint4 header[sizeof( World ) / 16];
 	extern __shared__ int4 dynamicShared[];
-	CtaTeam team{ smem };
+	CtaTeam team = CtaTeam::block( smem );
 	if ( arenaBytes > 0 )
 	{
 		team.arena = reinterpret_cast<int32_t*>( dynamicShared );
@@ -296,6 +308,72 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 				hostHeader[i] = header[i];
 		}
 		__syncthreads();
+	}
+}
+
+// Several worlds per thread block, side by side: kTeams teams of kTeamThreads threads, one world each, and a block-wide
+// barrier after every coarse phase of the step. The worlds of a block therefore run the SAME phase at the same time,
+// and the SM's instruction caches hold one phase's code instead of the whole step's: with independent one-world blocks
+// the eight resident worlds of an SM drift into different phases (real batches are not in lock-step), and the
+// step - ~3 MB of SASS - no longer fits: ncu shows as many stall cycles waiting for instructions as waiting for memory
+// (profiles/README.md, r03m). Blocks are persistent and take gangs of worlds from a queue.
+template <int kTeamThreads, int kTeams>
+__global__ void __launch_bounds__( kTeamThreads* kTeams, 1 )
+	stepWorldsGang( char* base, unsigned long long stride, int worldCount, float dt, int sub, int* queue, int onlyRetry )
+{
+	__shared__ int32_t scratch[kTeams][64];
+	__shared__ uint4 headers[kTeams][sizeof( World ) / 16];
+	__shared__ int gangFirst;
+	const int teamIndex = (int)threadIdx.x / kTeamThreads, tid = (int)threadIdx.x % kTeamThreads;
+	// barrier 0: the block; 1 .. kTeams: the teams; kTeams + 1 .. 2 kTeams: their crews (16 hardware barriers per block)
+	// (teams under 128 threads never fork: CtaTeam::canFork)
+	static_assert( ( kTeamThreads >= 128 ? 2 : 1 ) * kTeams + 1 <= 16, "one hardware barrier per team and per crew, plus the block's" );
+	CtaTeam team{ scratch[teamIndex], tid, kTeamThreads, 1 + teamIndex, 1 + kTeams + teamIndex };
+	World* w = reinterpret_cast<World*>( headers[teamIndex] );
+	while ( true )
+	{
+		__syncthreads();
+		if ( threadIdx.x == 0 )
+			gangFirst = atomicAdd( queue, kTeams );
+		__syncthreads();
+		const int wi = gangFirst + teamIndex;
+		if ( gangFirst >= worldCount )
+			break;
+		const bool have = wi < worldCount;
+		uint4* image = reinterpret_cast<uint4*>( base + (unsigned long long)( have ? wi : 0 ) * stride );
+		bool active = false;
+		if ( have )
+		{
+			for ( int i = tid; i < (int)( sizeof( World ) / 16 ); i += kTeamThreads )
+				headers[teamIndex][i] = image[i];
+			team.sync();
+			if ( tid == 0 )
+				w->deviceBase = reinterpret_cast<uint64_t>( image );
+			team.sync();
+			// onlyRetry: only the worlds that stopped for more contact room take the step (the batch has grown the images)
+			const uint32_t error = w->error;
+			active = ( error & kErrFatal ) == 0 && ( onlyRetry == 0 || ( error & kErrRetry ) != 0 );
+			team.sync();
+			if ( active && onlyRetry && tid == 0 )
+			{
+				w->error &= ~kErrRetry;
+				w->step.retryContacts = 0;
+			}
+			team.sync();
+		}
+		const int phases[] = { kPhaseBeginPairs, kPhaseCollideTreeOnly, kPhaseCollideNarrowOnly, kPhaseCollideFinish, kPhaseSolve,
+							   kPhaseFinalize };
+		for ( int phase : phases )
+		{
+			if ( active )
+				stepWorldPhase( w, team, phase, dt, sub );
+			__syncthreads();
+		}
+		if ( have )
+		{
+			for ( int i = tid; i < (int)( sizeof( World ) / 16 ); i += kTeamThreads )
+				image[i] = headers[teamIndex][i];
+		}
 	}
 }
 

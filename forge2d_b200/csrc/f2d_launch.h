@@ -13,6 +13,9 @@ bool launchBatchStepB( int threads, int blocksPerSM, char* base, unsigned long l
 					   cudaStream_t stream );
 bool launchBatchStepC( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
 					   cudaStream_t stream );
+// several worlds per block, phase-aligned (f2d_kernels.cuh stepWorldsGang); `queue`: one device int per concurrent launch
+bool launchBatchStepGang( char* base, unsigned long long stride, int worldCount, float dt, int sub, int onlyRetry, int smCount, int* queue,
+						  cudaStream_t stream );
 inline bool batchConfigExists( int threads, int blocksPerSM )
 {
 	const int known[][2] = { { 256, 4 }, { 128, 8 }, { 64, 16 } };

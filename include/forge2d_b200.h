@@ -516,6 +516,9 @@ F2D_API void f2dBatch_Synchronize( f2dBatch* batch );
 /// Threads per world (block size) and resident blocks per SM the batch kernel is compiled for; returns 0 if unknown.
 /// Available: 128x8 (default), 64x16, 32x32, 256x4, 256x2.
 F2D_API int f2dBatch_SetLaunchConfig( f2dBatch* batch, int threadsPerWorld, int blocksPerSM );
+/// 1 (the default): several worlds per thread block, kept in the same phase of the step (instruction-cache friendly);
+/// 0: one world per block in the configuration of f2dBatch_SetLaunchConfig (which also switches to that mode).
+F2D_API void f2dBatch_SetGangMode( f2dBatch* batch, int on );
 F2D_API int f2dBatch_GetWorldCount( f2dBatch* batch );
 /// Body move events of every world -> host buffer: `out` receives count*maxBodies records, `counts[w]` valid ones.
 F2D_API int f2dBatch_GetBodyEvents( f2dBatch* batch, b2BodyMoveEvent* out, int maxBodiesPerWorld, int* counts );

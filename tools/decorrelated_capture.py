@@ -16,6 +16,8 @@ t = scenes.bench2d(lib)
 for _ in range(256):
     t.step()
 b = lib.f2dBatch_Create(t.world, worlds)
+if os.environ.get("F2D_ONE_WORLD_PER_BLOCK"):
+    lib.f2dBatch_SetLaunchConfig(b, 128, 8)
 if jitter:
     offsets = (A.Vec2 * worlds)(*[A.Vec2(i * 2.0 ** -10, 0.0) for i in range(worlds)])
     lib.f2dBatch_TranslateWorlds(b, offsets, worlds)
