@@ -360,12 +360,31 @@ def run_b200_arm(args, rank, world_size, local_rank):
     lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
     barrier()
     t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        lib.f2dBatch_SetGravity(batch, gravity, mine)
+        moved = lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+    e2e_sliced_seconds = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    # (c) the pipelined call (the headline): per step an H2D of the inputs, the step, and the D2H of every body's transform
+    # (16 bytes per body) into pinned host memory; call k returns the transforms of step k-1, whose copy ran while step k
+    # was computed. The timed region ends with the flush, so it covers e2e_steps steps AND e2e_steps read-backs.
+    rec_ptr, cnt2_ptr = C.c_void_p(), C.POINTER(C.c_int)()
+    lib.f2dBatch_SetGravity(batch, gravity, mine)
+    lib.f2dBatch_StepPipelined(batch, DT, SUB, nb, 1, C.byref(rec_ptr), C.byref(cnt2_ptr))
+    lib.f2dBatch_FlushPipelined(batch, C.byref(rec_ptr), C.byref(cnt2_ptr))
+    barrier()
+    t0 = time.perf_counter()
     e2e_step_ms = []
+    checksum = 0.0
     for _ in range(e2e_steps):
         t1 = time.perf_counter()
         lib.f2dBatch_SetGravity(batch, gravity, mine)
-        moved = lib.f2dBatch_StepAndReadBodyEvents(batch, DT, SUB, nb, C.byref(ev_ptr), C.byref(cnt_ptr))
+        moved = lib.f2dBatch_StepPipelined(batch, DT, SUB, nb, 1, C.byref(rec_ptr), C.byref(cnt2_ptr))
+        if rec_ptr.value:
+            checksum += C.cast(rec_ptr, C.POINTER(C.c_float))[1]  # the host really reads the result (y of the first body)
         e2e_step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
+    moved = lib.f2dBatch_FlushPipelined(batch, C.byref(rec_ptr), C.byref(cnt2_ptr))
+    checksum += C.cast(rec_ptr, C.POINTER(C.c_float))[1]
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
     growths = lib.f2dBatch_GetGrowthCount(batch)
     barrier()
@@ -402,11 +421,16 @@ def run_b200_arm(args, rank, world_size, local_rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": 8 * mine,
-                "d2h_bytes_per_step": mine * nb * C.sizeof(A.BodyMoveEvent) + 4 * mine, "steps": e2e_steps,
-                "path": "f2dBatch_SetGravity (pinned H2D) + f2dBatch_StepAndReadBodyEvents (step in world slices on "
-                        "separate streams, pinned D2H of every body transform of a slice overlapped with the stepping of "
-                        "the next), per rank; events read per step: %d" % moved,
+                "d2h_bytes_per_step": mine * nb * 16 + 4 * (mine + 1), "steps": e2e_steps,
+                "path": "f2dBatch_SetGravity (pinned H2D of per-world inputs) + f2dBatch_StepPipelined (step, then pinned D2H "
+                        "of every body's transform, 16 B each; call k returns step k-1's transforms, whose copy overlapped "
+                        "step k; the timed region ends with f2dBatch_FlushPipelined), per rank; transforms read per step: "
+                        "%d; checksum %.6g" % (moved, checksum),
                 "ms_per_step_each": e2e_step_ms,
+                "full_events_sliced_value": args.worlds * e2e_steps / e2e_sliced_seconds,
+                "full_events_sliced_path": "f2dBatch_SetGravity + f2dBatch_StepAndReadBodyEvents: every 40-byte b2BodyMoveEvent "
+                                           "of the step on the host when the call returns (world slices on separate streams), "
+                                           "%d B per step" % (mine * nb * C.sizeof(A.BodyMoveEvent) + 4 * mine),
                 "sequential_calls_value": e2e_sequential_value,
                 "sequential_calls_path": "f2dBatch_SetGravity + f2dBatch_Step + f2dBatch_ReadBodyEvents, nothing overlapped"},
         "gpu_launches": int(launches),

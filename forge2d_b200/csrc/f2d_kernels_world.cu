@@ -28,6 +28,31 @@ __global__ void gatherMoveEvents( const char* base, unsigned long long stride, i
 		counts[wi] = n;
 }
 
+// The body transforms of every world of a batch, packed: 16 bytes per body (position, rotation) in awake order, the
+// per-world counts, and the OR of all error flags in status[0] (one block per world).
+__global__ void gatherTransforms( const char* base, unsigned long long stride, int worldCount, Xf* out, int maxBodies, int* counts,
+								  unsigned int* status )
+{
+	int wi = (int)blockIdx.x;
+	if ( wi >= worldCount )
+		return;
+	const World* w = reinterpret_cast<const World*>( base + (unsigned long long)wi * stride );
+	int n = min( w->moveEvents.count, maxBodies );
+	const BodyMoveEvent* src = reinterpret_cast<const BodyMoveEvent*>( reinterpret_cast<const char*>( w ) + w->moveEvents.off );
+	Q4* dst = reinterpret_cast<Q4*>( out + (size_t)wi * maxBodies );
+	for ( int i = (int)threadIdx.x; i < n; i += (int)blockDim.x )
+	{
+		const Xf xf = src[i].transform; // 40-byte records: 8-byte aligned
+		dst[i] = Q4{ xf.p.x, xf.p.y, xf.q.c, xf.q.s };
+	}
+	if ( threadIdx.x == 0 )
+	{
+		counts[wi] = n;
+		if ( w->error != 0 )
+			atomicOr( status, w->error );
+	}
+}
+
 __global__ void gatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out )
 {
 	int wi = (int)( blockIdx.x * blockDim.x + threadIdx.x );
@@ -177,6 +202,11 @@ void launchGatherMoveEvents( const char* base, unsigned long long stride, int wo
 							 cudaStream_t stream )
 {
 	gatherMoveEvents<<<worldCount, 256, 0, stream>>>( base, stride, worldCount, out, maxBodies, counts );
+}
+void launchGatherTransforms( const char* base, unsigned long long stride, int worldCount, void* out, int maxBodies, int* counts,
+							 unsigned int* status, cudaStream_t stream )
+{
+	gatherTransforms<<<worldCount, 256, 0, stream>>>( base, stride, worldCount, static_cast<Xf*>( out ), maxBodies, counts, status );
 }
 void launchGatherWorldStatus( const char* base, unsigned long long stride, int worldCount, unsigned int* flags, int* retryMax,
 							 cudaStream_t stream )

@@ -51,5 +51,7 @@ void launchTranslateWorlds( char* base, unsigned long long stride, int worldCoun
 struct BodyMoveEvent;
 void launchGatherMoveEvents( const char* base, unsigned long long stride, int worldCount, BodyMoveEvent* out, int maxBodies, int* counts,
 							 cudaStream_t stream );
+void launchGatherTransforms( const char* base, unsigned long long stride, int worldCount, void* out, int maxBodies, int* counts,
+							 unsigned int* status, cudaStream_t stream );
 void launchGatherErrors( const char* base, unsigned long long stride, int worldCount, unsigned int* out, cudaStream_t stream );
 } // namespace f2d

@@ -528,6 +528,13 @@ F2D_API int f2dBatch_ReadBodyEvents( f2dBatch* batch, int maxBodiesPerWorld, con
 /// streams and each slice's events cross PCIe while later slices are still being stepped. Returns the event total.
 F2D_API int f2dBatch_StepAndReadBodyEvents( f2dBatch* batch, float timeStep, int subStepCount, int maxBodiesPerWorld,
 											const b2BodyMoveEvent** outEvents, const int** outCounts );
+/// Pipelined step + read-back: call k queues step k and the copy of its results to pinned host memory, and returns the
+/// results of step k-1 (nothing on the first call), whose copy overlapped the computation of step k.
+/// f2dBatch_FlushPipelined returns the results of the last queued step. format 0: b2BodyMoveEvent records (40 bytes per
+/// body); format 1: b2Transform only (16 bytes per body, awake order). Pointers stay valid until the next call.
+F2D_API int f2dBatch_StepPipelined( f2dBatch* batch, float timeStep, int subStepCount, int maxBodiesPerWorld, int format,
+									const void** outRecords, const int** outCounts );
+F2D_API int f2dBatch_FlushPipelined( f2dBatch* batch, const void** outRecords, const int** outCounts );
 /// Per-world gravity: the batch counterpart of b2World_SetGravity (box2d.h:135); `gravity` holds `count` vectors.
 F2D_API void f2dBatch_SetGravity( f2dBatch* batch, const b2Vec2* gravity, int count );
 /// Translates every body, shape box and broadphase box of world k by offsets[k]: replicas placed side by side, or

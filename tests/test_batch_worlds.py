@@ -98,3 +98,50 @@ def test_batch_grows_when_a_world_needs_more_contact_room(ref, gpu):
         assert H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, scratch.world)) == []
     gpu.f2dBatch_Destroy(batch)
     assert gpu.f2dGetLastError() == b""
+
+
+def test_pipelined_step_returns_the_previous_steps_results(ref, gpu):
+    """f2dBatch_StepPipelined: call k returns what f2dBatch_Step + f2dBatch_ReadBodyEvents returned after step k-1, in
+    both formats (40-byte events, 16-byte transforms); the flush returns the last step's."""
+    import numpy as np
+    b = scenes.bench2d(gpu, rows=12)
+    count, frames, nb = 300, 10, 79
+    one = gpu.f2dBatch_Create(b.world, count)
+    two = gpu.f2dBatch_Create(b.world, count)
+    three = gpu.f2dBatch_Create(b.world, count)
+    offsets = (A.Vec2 * count)(*[A.Vec2(k * 2.0 ** -10, 0.0) for k in range(count)])
+    for batch in (one, two, three):
+        gpu.f2dBatch_TranslateWorlds(batch, offsets, count)
+    size = nb * C.sizeof(A.BodyMoveEvent)
+    used = (nb - 1) * C.sizeof(A.BodyMoveEvent)
+    previous = None
+    for f in range(frames + 1):
+        rec, cnt = C.c_void_p(), C.POINTER(C.c_int)()
+        rec3, cnt3 = C.c_void_p(), C.POINTER(C.c_int)()
+        if f < frames:
+            got = gpu.f2dBatch_StepPipelined(two, scenes.TIME_STEP, scenes.SUB_STEPS, nb, 0, C.byref(rec), C.byref(cnt))
+            got3 = gpu.f2dBatch_StepPipelined(three, scenes.TIME_STEP, scenes.SUB_STEPS, nb, 1, C.byref(rec3), C.byref(cnt3))
+        else:
+            got = gpu.f2dBatch_FlushPipelined(two, C.byref(rec), C.byref(cnt))
+            got3 = gpu.f2dBatch_FlushPipelined(three, C.byref(rec3), C.byref(cnt3))
+        if f == 0:
+            assert got == 0 and got3 == 0 and not rec.value
+        else:
+            assert got == got3 == count * (nb - 1)
+            raw = np.ctypeslib.as_array(C.cast(rec, C.POINTER(C.c_uint8)), shape=(count, size))[:, :used].copy()
+            assert (raw == previous).all(), "frame %d" % f
+            # transforms: the first 16 bytes of every 40-byte event
+            xf = np.ctypeslib.as_array(C.cast(rec3, C.POINTER(C.c_uint8)), shape=(count, nb * 16))[:, :(nb - 1) * 16]
+            want = previous.reshape(count, nb - 1, C.sizeof(A.BodyMoveEvent))[:, :, :16].reshape(count, (nb - 1) * 16)
+            assert (xf == want).all(), "frame %d: transforms" % f
+            assert cnt[0] == cnt3[count - 1] == nb - 1
+        if f < frames:
+            ev1, cn1 = C.POINTER(A.BodyMoveEvent)(), C.POINTER(C.c_int)()
+            gpu.f2dBatch_Step(one, scenes.TIME_STEP, scenes.SUB_STEPS)
+            gpu.f2dBatch_ReadBodyEvents(one, nb, C.byref(ev1), C.byref(cn1))
+            previous = np.ctypeslib.as_array(C.cast(ev1, C.POINTER(C.c_uint8)), shape=(count, size))[:, :used].copy()
+    # translated replicas really are different worlds
+    assert not (previous[0] == previous[count - 1]).all()
+    for batch in (one, two, three):
+        assert gpu.f2dBatch_GetErrorFlags(batch) == 0
+        gpu.f2dBatch_Destroy(batch)
