@@ -520,6 +520,7 @@ F2D_FUNCTIONS = {
     "f2dBatch_GetWorldErrors": (c_int, [c_void_p, C.POINTER(C.c_uint32), c_int]),
     "f2dBatch_GetGrowthCount": (c_int, [c_void_p]),
     "f2dBatch_SetGangMode": (None, [c_void_p, c_int]),
+    "f2dGetTransferBytes": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
     "f2dBatch_StepPipelined": (c_int, [c_void_p, C.c_float, c_int, c_int, c_int, C.POINTER(c_void_p), C.POINTER(C.POINTER(c_int))]),
     "f2dBatch_FlushPipelined": (c_int, [c_void_p, C.POINTER(c_void_p), C.POINTER(C.POINTER(c_int))]),
     "f2dBatch_TranslateWorlds": (None, [c_void_p, c_void_p, c_int]),

@@ -50,6 +50,13 @@ struct HostWorld
 	};
 	std::vector<Chain> chains;
 	bool headerFresh = true;
+	// Partial host <-> device synchronisation while the device copy is the newer one (SyncState::kDeviceNewer):
+	//   bodyMirrorFresh  the host copies of the body records, simulation records and solver states are current (one
+	//                    download of those three arrays after a step serves every position / velocity getter);
+	//   dirty            byte ranges of the host image that per-frame mutators (forces, impulses, velocities of awake
+	//                    bodies) have changed; uploaded right before the next step instead of the whole image.
+	bool bodyMirrorFresh = false;
+	std::vector<std::pair<uint64_t, uint32_t>> dirty;
 	// host callbacks of the callback-mediated step (world.c:1710-1740); the image only carries World::hostCallbacks
 	b2CustomFilterFcn* customFilterFcn = nullptr;
 	void* customFilterContext = nullptr;
@@ -80,6 +87,11 @@ static void backendSynchronize( HostWorld& hw );
 static void backendDownload( HostWorld& hw );
 /// Makes one byte range of the host image current.
 static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes );
+struct ByteRange
+{
+	uint64_t off, bytes;
+};
+static void backendDownloadRanges( HostWorld& hw, std::initializer_list<ByteRange> ranges ); // one synchronisation for all
 /// Callback-mediated step: the step as a sequence of launches (f2d_step.h Phase) with the host in between.
 /// Begin makes the authoritative copy current, Phase runs one piece, UploadRange pushes host edits of one byte range of
 /// the image, End leaves `hw.img`'s header current like backendStep. DownloadRange synchronises with the phases queued.
@@ -105,11 +117,36 @@ static HostWorld* worldFromId( b2WorldId id )
 	return hw;
 }
 
+// Pending host-side edits of a device-newer image go to the device (before a step, or before the image is downloaded)
+static void flushDirty( HostWorld& hw )
+{
+	if ( hw.dirty.empty() )
+		return;
+	std::sort( hw.dirty.begin(), hw.dirty.end() );
+	uint64_t off = hw.dirty[0].first, end = off + hw.dirty[0].second;
+	for ( size_t i = 1; i <= hw.dirty.size(); ++i )
+	{
+		if ( i < hw.dirty.size() && hw.dirty[i].first <= end + 256 ) // close ranges travel as one copy
+		{
+			end = std::max( end, hw.dirty[i].first + hw.dirty[i].second );
+			continue;
+		}
+		backendUploadRange( hw, off, end - off );
+		if ( i < hw.dirty.size() )
+		{
+			off = hw.dirty[i].first;
+			end = off + hw.dirty[i].second;
+		}
+	}
+	hw.dirty.clear();
+}
+
 // Host image current and writable
 static World* hostImage( HostWorld& hw )
 {
 	if ( hw.state == kDeviceNewer )
 	{
+		flushDirty( hw );
 		backendDownload( hw );
 		hw.state = kInSync;
 		hw.eventsFresh = true;
@@ -122,6 +159,30 @@ static World* mutableImage( HostWorld& hw )
 	World* w = hostImage( hw );
 	hw.state = kHostNewer;
 	return w;
+}
+
+// The body-level part of the host image current (body records, simulation records, solver states; the header always
+// is): what position / velocity getters and the per-frame mutators need. After a step this costs one download of those
+// three arrays (a few hundred KB for bench2d) instead of the whole image (megabytes).
+static World* bodyImage( HostWorld& hw )
+{
+	if ( hw.state == kDeviceNewer && hw.bodyMirrorFresh == false )
+	{
+		World* w = hw.img;
+		flushDirty( hw );
+		backendDownloadRanges( hw, { { w->bodies.off, (uint64_t)w->bodies.count * sizeof( Body ) },
+									 { w->sims.off, (uint64_t)w->sims.count * sizeof( BodySim ) },
+									 { w->states.off, (uint64_t)w->awakeBodies.count * sizeof( BodyState ) } } );
+		hw.bodyMirrorFresh = true;
+	}
+	return hw.img;
+}
+// A host-side change of `bytes` at `p` inside the image: recorded for upload when the device copy is the newer one
+// (otherwise the host image is the master already and the caller has marked it so)
+static void touchRange( HostWorld& hw, const void* p, size_t bytes )
+{
+	if ( hw.state == kDeviceNewer )
+		hw.dirty.push_back( { (uint64_t)( reinterpret_cast<const char*>( p ) - reinterpret_cast<const char*>( hw.img ) ), (uint32_t)bytes } );
 }
 
 static Caps capsWith( const World* w, int B, int S, int C, int J )
@@ -1001,6 +1062,39 @@ static Body* bodyFromId( b2BodyId id, HostWorld** outWorld, bool forWrite )
 	return b;
 }
 
+// Read access to what bodyImage keeps current (body record, simulation record, solver state)
+static Body* bodyFromIdLight( b2BodyId id, HostWorld** outWorld )
+{
+	HostWorld* hw = worldFromIndex0( id.world0 );
+	if ( hw == nullptr )
+		return nullptr;
+	World* w = bodyImage( *hw );
+	int index = id.index1 - 1;
+	if ( index < 0 || index >= w->bodies.count )
+		return nullptr;
+	Body* b = ptr( w, w->bodies ) + index;
+	if ( b->setIndex == kNull || b->id != index || b->generation != id.generation )
+		return nullptr;
+	if ( outWorld )
+		*outWorld = hw;
+	return b;
+}
+// A per-frame mutator (force, impulse, velocity) of a body: when the body is awake - or need not be woken - the change
+// is a field of its simulation record / solver state, recorded as a dirty range; waking a sleeping body is a
+// structural edit and takes the full path (`wakes` = the call would wake the body if it slept).
+static Body* bodyForLightEdit( b2BodyId id, HostWorld** outWorld, bool wakes )
+{
+	HostWorld* hw = nullptr;
+	Body* b = bodyFromIdLight( id, &hw );
+	if ( b == nullptr )
+		return nullptr;
+	if ( hw->state != kDeviceNewer || ( wakes && b->setIndex >= kFirstSleepingSet ) )
+		return bodyFromId( id, outWorld, true );
+	if ( outWorld )
+		*outWorld = hw;
+	return b;
+}
+
 bool b2Body_IsValid( b2BodyId id )
 {
 	return bodyFromId( id, nullptr, false ) != nullptr;
@@ -1013,7 +1107,7 @@ b2BodyType b2Body_GetType( b2BodyId id )
 b2Transform b2Body_GetTransform( b2BodyId id )
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( id, &hw, false );
+	Body* b = bodyFromIdLight( id, &hw );
 	b2Transform t = { { 0, 0 }, { 1, 0 } };
 	if ( b == nullptr )
 		return t;
@@ -1033,7 +1127,7 @@ b2Rot b2Body_GetRotation( b2BodyId id )
 b2Vec2 b2Body_GetLinearVelocity( b2BodyId id )
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( id, &hw, false );
+	Body* b = bodyFromIdLight( id, &hw );
 	if ( b == nullptr || b->setIndex != kAwakeSet )
 		return b2Vec2{ 0, 0 };
 	const BodyState& s = ptr( hw->img, hw->img->states )[b->localIndex];
@@ -1042,7 +1136,7 @@ b2Vec2 b2Body_GetLinearVelocity( b2BodyId id )
 float b2Body_GetAngularVelocity( b2BodyId id )
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( id, &hw, false );
+	Body* b = bodyFromIdLight( id, &hw );
 	if ( b == nullptr || b->setIndex != kAwakeSet )
 		return 0.0f;
 	return ptr( hw->img, hw->img->states )[b->localIndex].w;
@@ -1051,28 +1145,31 @@ float b2Body_GetAngularVelocity( b2BodyId id )
 void b2Body_SetLinearVelocity( b2BodyId id, b2Vec2 v )
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( id, &hw, true );
+	const bool wakes = v.x * v.x + v.y * v.y > 0.0f;
+	Body* b = bodyForLightEdit( id, &hw, wakes );
 	if ( b == nullptr || b->type == kStaticBody )
 		return;
 	World* w = hw->img;
-	if ( v.x * v.x + v.y * v.y > 0.0f )
+	if ( wakes && b->setIndex >= kFirstSleepingSet )
 		wakeBody( w, *b );
 	if ( b->setIndex != kAwakeSet )
 		return;
 	ptr( w, w->states )[b->localIndex].v = V2{ v.x, v.y };
+	touchRange( *hw, &ptr( w, w->states )[b->localIndex], sizeof( BodyState ) );
 }
 void b2Body_SetAngularVelocity( b2BodyId id, float wv )
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( id, &hw, true );
+	Body* b = bodyForLightEdit( id, &hw, wv != 0.0f );
 	if ( b == nullptr || b->type == kStaticBody || b->fixedRotation )
 		return;
 	World* w = hw->img;
-	if ( wv != 0.0f )
+	if ( wv != 0.0f && b->setIndex >= kFirstSleepingSet )
 		wakeBody( w, *b );
 	if ( b->setIndex != kAwakeSet )
 		return;
 	ptr( w, w->states )[b->localIndex].w = wv;
+	touchRange( *hw, &ptr( w, w->states )[b->localIndex], sizeof( BodyState ) );
 }
 float b2Body_GetMass( b2BodyId id )
 {

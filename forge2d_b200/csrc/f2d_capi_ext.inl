@@ -84,7 +84,7 @@ void b2Body_SetTransform( b2BodyId bodyId, b2Vec2 position, b2Rot rotation ) // 
 void b2Body_ApplyForce( b2BodyId bodyId, b2Vec2 force, b2Vec2 point, bool wake ) // body.c:900-916
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
@@ -95,12 +95,13 @@ void b2Body_ApplyForce( b2BodyId bodyId, b2Vec2 force, b2Vec2 point, bool wake )
 		V2 f = { force.x, force.y };
 		s->force = add( s->force, f );
 		s->torque += cross( sub( V2{ point.x, point.y }, s->center ), f );
+		touchRange( *hw, &s->force, 12 ); // force, torque
 	}
 }
 void b2Body_ApplyForceToCenter( b2BodyId bodyId, b2Vec2 force, bool wake ) // body.c:918-933
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
@@ -109,23 +110,27 @@ void b2Body_ApplyForceToCenter( b2BodyId bodyId, b2Vec2 force, bool wake ) // bo
 	{
 		BodySim* s = simOf( hw, b );
 		s->force = add( s->force, V2{ force.x, force.y } );
+		touchRange( *hw, &s->force, 8 );
 	}
 }
 void b2Body_ApplyTorque( b2BodyId bodyId, float torque, bool wake ) // body.c:935-950
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
 		wakeBody( hw->img, *b );
 	if ( b->setIndex == kAwakeSet )
+	{
 		simOf( hw, b )->torque += torque;
+		touchRange( *hw, &simOf( hw, b )->torque, 4 );
+	}
 }
 void b2Body_ApplyLinearImpulse( b2BodyId bodyId, b2Vec2 impulse, b2Vec2 point, bool wake ) // body.c:952-973
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
@@ -138,12 +143,13 @@ void b2Body_ApplyLinearImpulse( b2BodyId bodyId, b2Vec2 impulse, b2Vec2 point, b
 		st->v = mulAdd( st->v, s->invMass, P );
 		st->w += s->invInertia * cross( sub( V2{ point.x, point.y }, s->center ), P );
 		limitVelocity( *st, hw->img->maxLinearSpeed );
+		touchRange( *hw, st, sizeof( BodyState ) );
 	}
 }
 void b2Body_ApplyLinearImpulseToCenter( b2BodyId bodyId, b2Vec2 impulse, bool wake ) // body.c:975-995
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
@@ -153,18 +159,22 @@ void b2Body_ApplyLinearImpulseToCenter( b2BodyId bodyId, b2Vec2 impulse, bool wa
 		BodyState* st = stateOf( hw, b );
 		st->v = mulAdd( st->v, simOf( hw, b )->invMass, V2{ impulse.x, impulse.y } );
 		limitVelocity( *st, hw->img->maxLinearSpeed );
+		touchRange( *hw, st, sizeof( BodyState ) );
 	}
 }
 void b2Body_ApplyAngularImpulse( b2BodyId bodyId, float impulse, bool wake ) // body.c:997-1020
 {
 	HostWorld* hw = nullptr;
-	Body* b = bodyFromId( bodyId, &hw, true );
+	Body* b = bodyForLightEdit( bodyId, &hw, wake );
 	if ( b == nullptr )
 		return;
 	if ( wake && b->setIndex >= kFirstSleepingSet )
 		wakeBody( hw->img, *b );
 	if ( b->setIndex == kAwakeSet )
+	{
 		stateOf( hw, b )->w += simOf( hw, b )->invInertia * impulse;
+		touchRange( *hw, stateOf( hw, b ), sizeof( BodyState ) );
+	}
 }
 void b2Body_SetName( b2BodyId bodyId, const char* name ) // body.c:1286-1304
 {

@@ -116,6 +116,9 @@ static DeviceMirror* mirror( HostWorld& hw )
 }
 
 
+// bytes moved between host and device by the single-world paths (f2dGetTransferBytes: tests assert what a frame costs)
+static unsigned long long g_bytesH2D = 0, g_bytesD2H = 0;
+
 static bool hostImagePinned( const World* img ) { return ( reinterpret_cast<const char*>( img ) - 256 )[0] == 1; }
 
 // `hostHeader`: the kernel mirrors the world header into the (pinned, device-accessible) host image itself
@@ -151,6 +154,12 @@ static bool deviceImageCurrent( HostWorld& hw, DeviceMirror* m )
 		}
 		if ( cudaOk( cudaMemcpyAsync( m->dev, img, img->imageBytes, cudaMemcpyHostToDevice, m->stream ), "upload world image" ) == false )
 			return false;
+		g_bytesH2D += img->imageBytes;
+		hw.dirty.clear(); // the whole image just went up
+	}
+	else if ( hw.state == kDeviceNewer )
+	{
+		flushDirty( hw ); // per-frame edits of a device-newer image (forces, impulses, velocities)
 	}
 	return true;
 }
@@ -172,6 +181,7 @@ static void backendUploadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
 		return;
 	cudaMemcpyAsync( reinterpret_cast<char*>( m->dev ) + off, reinterpret_cast<const char*>( hw.img ) + off, bytes, cudaMemcpyHostToDevice,
 					 m->stream );
+	g_bytesH2D += bytes;
 	cudaOk( cudaStreamSynchronize( m->stream ), "upload range" ); // the host buffer is reused right away
 }
 static void backendPhaseEnd( HostWorld& hw )
@@ -180,7 +190,9 @@ static void backendPhaseEnd( HostWorld& hw )
 	if ( m->dev == nullptr )
 		return;
 	cudaMemcpyAsync( hw.img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
+	g_bytesD2H += sizeof( World );
 	hw.state = kDeviceNewer;
+	hw.bodyMirrorFresh = false;
 	cudaOk( cudaStreamSynchronize( m->stream ), "world step (callback-mediated)" );
 }
 
@@ -207,7 +219,9 @@ static void backendStep( HostWorld& hw, float dt, int subSteps, bool synchronous
 	}
 	if ( m->timing || hostImagePinned( img ) == false )
 		cudaMemcpyAsync( img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
+	g_bytesD2H += sizeof( World );
 	hw.state = kDeviceNewer;
+	hw.bodyMirrorFresh = false;
 	if ( synchronous )
 	{
 		cudaOk( cudaStreamSynchronize( m->stream ), "world step" );
@@ -237,6 +251,7 @@ static void backendDownload( HostWorld& hw )
 		return;
 	cudaStreamSynchronize( m->stream );
 	cudaOk( cudaMemcpy( hw.img, m->dev, hw.img->imageBytes, cudaMemcpyDeviceToHost ), "download world image" );
+	g_bytesD2H += hw.img->imageBytes;
 }
 
 static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
@@ -246,7 +261,24 @@ static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
 		return;
 	cudaMemcpyAsync( reinterpret_cast<char*>( hw.img ) + off, reinterpret_cast<const char*>( m->dev ) + off, bytes, cudaMemcpyDeviceToHost,
 					 m->stream );
+	g_bytesD2H += bytes;
 	cudaOk( cudaStreamSynchronize( m->stream ), "download range" );
+}
+
+static void backendDownloadRanges( HostWorld& hw, std::initializer_list<ByteRange> ranges )
+{
+	DeviceMirror* m = mirror( hw );
+	if ( m->dev == nullptr )
+		return;
+	for ( const ByteRange& r : ranges )
+	{
+		if ( r.bytes == 0 )
+			continue;
+		cudaMemcpyAsync( reinterpret_cast<char*>( hw.img ) + r.off, reinterpret_cast<const char*>( m->dev ) + r.off, r.bytes,
+						 cudaMemcpyDeviceToHost, m->stream );
+		g_bytesD2H += r.bytes;
+	}
+	cudaOk( cudaStreamSynchronize( m->stream ), "download ranges" );
 }
 
 static void backendRelease( HostWorld& hw )
@@ -923,8 +955,7 @@ static void pipeRelease( f2dBatch* b )
 	for ( int i = 0; i < 2; ++i )
 	{
 		cudaFree( p.dev[i] );
-		cudaFree( p.devCounts[i] );
-		cudaFree( p.devStatus[i] );
+		cudaFree( p.devCounts[i] ); // (devStatus is the last word of this allocation)
 		if ( p.host[i] )
 			cudaFreeHost( p.host[i] );
 		if ( p.hostCounts[i] )
@@ -1116,6 +1147,14 @@ int f2dSetDevice( int device )
 {
 	f2d::g_deviceState = -1;
 	return cudaSetDevice( device ) == cudaSuccess && f2d::backendAvailable() ? 1 : 0;
+}
+// Bytes moved between host and device by single-world calls since the library was loaded
+void f2dGetTransferBytes( unsigned long long* hostToDevice, unsigned long long* deviceToHost )
+{
+	if ( hostToDevice )
+		*hostToDevice = f2d::g_bytesH2D;
+	if ( deviceToHost )
+		*deviceToHost = f2d::g_bytesD2H;
 }
 void* f2dHostAlloc( unsigned long long bytes )
 {

@@ -503,6 +503,10 @@ F2D_API void b2World_SetPreSolveCallback( b2WorldId worldId, b2PreSolveFcn* fcn,
 // Stock b2WorldId cannot address 8192 worlds (B2_MAX_WORLDS = 128, constants.h:26-28), hence a separate handle.
 typedef struct f2dBatch f2dBatch;
 /// Replicates the current state of `templateWorld` into `count` device-resident worlds (one image each).
+/// Bytes moved between host and device by single-world calls since the library was loaded (what a frame costs: after
+/// a step, position / velocity getters fetch the body arrays once; forces, impulses and velocities of awake bodies go
+/// up as the few bytes they changed).
+F2D_API void f2dGetTransferBytes( unsigned long long* hostToDevice, unsigned long long* deviceToHost );
 F2D_API f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count );
 /// A batch of DIFFERENT worlds (ids may repeat): all are brought to one common image layout and uploaded; the host
 /// worlds stay usable on their own. Worlds with host callbacks registered are refused (no host in a batch step).

@@ -32,6 +32,7 @@ static void backendPhaseEnd( HostWorld& hw ) { hw.state = kInSync; }
 static void backendSynchronize( HostWorld& ) {}
 static void backendDownload( HostWorld& ) {}
 static void backendDownloadRange( HostWorld&, uint64_t, uint64_t ) {}
+static void backendDownloadRanges( HostWorld&, std::initializer_list<ByteRange> ) {}
 static void backendRelease( HostWorld& ) {}
 static void backendStepTimes( HostWorld&, float* ) {}
 static void backendEnableTiming( HostWorld&, bool ) {}

@@ -219,3 +219,45 @@ def test_async_step_then_synchronize(ref, gpu):
         gpu.f2dWorld_StepAsync(b.world, scenes.TIME_STEP, scenes.SUB_STEPS)
     gpu.f2dWorld_Synchronize(b.world)
     assert H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, b.world)) == []
+
+
+def test_game_loop_reads_and_forces_move_kilobytes_not_the_image(ref, gpu):
+    """A frame as a game makes it: read every body's position (and some velocities), push one body, step. After a step
+    the getters fetch the body arrays once (not the multi-megabyte image) and the force / impulse / velocity edits of
+    awake bodies go up as the bytes they changed; results stay bit-identical to the reference."""
+    a = scenes.bench2d(ref)
+    b = scenes.bench2d(gpu)
+    for s in (a, b):
+        for _ in range(30):
+            s.step()
+    h2d0, d2h0 = C.c_ulonglong(), C.c_ulonglong()
+    gpu.f2dGetTransferBytes(C.byref(h2d0), C.byref(d2h0))
+    frames = 40
+    for f in range(frames):
+        pa = [(ref.b2Body_GetPosition(x).x, ref.b2Body_GetPosition(x).y) for x in a.bodies]
+        pb = [(gpu.b2Body_GetPosition(x).x, gpu.b2Body_GetPosition(x).y) for x in b.bodies]
+        assert pa == pb, "frame %d: positions" % f
+        k = 1 + (37 * f) % 800
+        va, vb = ref.b2Body_GetLinearVelocity(a.bodies[k]), gpu.b2Body_GetLinearVelocity(b.bodies[k])
+        assert (va.x, va.y) == (vb.x, vb.y)
+        for lib, s in ((ref, a), (gpu, b)):
+            lib.b2Body_ApplyForceToCenter(s.bodies[k], A.Vec2(40.0, 15.0), True)
+            if f % 4 == 1:
+                lib.b2Body_ApplyLinearImpulseToCenter(s.bodies[k + 3], A.Vec2(-0.5, 1.0), True)
+            if f % 4 == 2:
+                lib.b2Body_ApplyTorque(s.bodies[k + 5], 3.0, True)
+                lib.b2Body_ApplyAngularImpulse(s.bodies[k + 7], 0.25, True)
+            if f % 4 == 3:
+                lib.b2Body_SetLinearVelocity(s.bodies[k + 9], A.Vec2(0.5, 2.0))
+                lib.b2Body_SetAngularVelocity(s.bodies[k + 11], -1.5)
+                lib.b2Body_ApplyForce(s.bodies[k + 13], A.Vec2(5.0, 5.0), A.Vec2(0.1, 0.2), True)
+                lib.b2Body_ApplyLinearImpulse(s.bodies[k + 15], A.Vec2(0.2, 0.1), A.Vec2(0.0, 0.3), True)
+            s.step()
+    h2d1, d2h1 = C.c_ulonglong(), C.c_ulonglong()
+    gpu.f2dGetTransferBytes(C.byref(h2d1), C.byref(d2h1))
+    up, down = (h2d1.value - h2d0.value) / frames, (d2h1.value - d2h0.value) / frames
+    assert up < 4096, "host -> device bytes per frame: %d" % up            # a few dirty records, not a 4.4 MB image
+    assert down < 400 * 1024, "device -> host bytes per frame: %d" % down  # body + sim + state arrays (~210 KB) + header
+    d = H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, b.world))
+    assert d == [], d[:6]
+    assert gpu.f2dGetLastError() == b""
