@@ -264,6 +264,37 @@ def single_world_numbers(lib, ref, name, kw, warm, timed, mode, cores):
     return out
 
 
+def game_loop_numbers(lib, frames=256, warm=256):
+    """bench2d as a game drives it: per frame one b2World_Step, every body's transform read (b2World_GetBodyEvents, the
+    way forge2d's bodyMoveEvents does; plus one b2Body_GetPosition / GetLinearVelocity) and one b2Body_ApplyForceToCenter.
+    Reports ms/frame beside the bare step and the bytes that crossed PCIe per frame."""
+    out = {}
+    for label, interact in (("bare_step", False), ("read_all_transforms_and_push_one_body", True)):
+        s = scenes.bench2d(lib)
+        lib.f2dWorld_SetLaunchMode(s.world, 0)
+        for _ in range(warm):
+            s.step()
+        h0, d0 = C.c_ulonglong(), C.c_ulonglong()
+        lib.f2dGetTransferBytes(C.byref(h0), C.byref(d0))
+        checksum = 0.0
+        t0 = time.perf_counter()
+        for f in range(frames):
+            if interact:
+                lib.b2Body_ApplyForceToCenter(s.bodies[1 + (37 * f) % 800], A.Vec2(40.0, 15.0), True)
+            s.step()
+            if interact:
+                ev = lib.b2World_GetBodyEvents(s.world)
+                checksum += ev.moveEvents[ev.moveCount - 1].transform.p.y
+                checksum += lib.b2Body_GetPosition(s.bodies[5]).y + lib.b2Body_GetLinearVelocity(s.bodies[7]).y
+        seconds = time.perf_counter() - t0
+        h1, d1 = C.c_ulonglong(), C.c_ulonglong()
+        lib.f2dGetTransferBytes(C.byref(h1), C.byref(d1))
+        s.destroy()
+        out[label] = {"ms_per_frame": 1e3 * seconds / frames, "h2d_bytes_per_frame": (h1.value - h0.value) / frames,
+                      "d2h_bytes_per_frame": (d1.value - d0.value) / frames, "checksum": checksum}
+    return out
+
+
 def run_b200_arm(args, rank, world_size, local_rank):
     import forge2d_b200
     lib = forge2d_b200.load_library()
@@ -468,6 +499,7 @@ def run_b200_arm(args, rank, world_size, local_rank):
         extras["large_pyramid"]["window"] = "frames 150-400 (impact and collapse)"
         extras["many_pyramids_awake"] = single_world_numbers(lib, ref, "many_pyramids", {}, 2, 24, 1, cores)
         extras["joint_grid"] = single_world_numbers(lib, ref, "joint_grid", {}, 8, 32, 1, cores)
+        extras["bench2d_game_loop"] = game_loop_numbers(lib)
         line["single_world"] = extras
         # latency floor of a synchronous b2World_Step for small scenes (north_star's "graph-replay latency": the whole
         # step is ONE kernel launch, so this is launch + header read-back + synchronise): a world with no awake body,

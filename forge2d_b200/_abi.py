@@ -231,6 +231,13 @@ class Counters(C.Structure):
                 ("byteCount", c_int), ("taskCount", c_int), ("colorCounts", c_int * 12)]
 
 
+class Profile(C.Structure):  # types.h:466-490
+    _fields_ = [(n, c_float) for n in ("step", "pairs", "collide", "solve", "mergeIslands", "prepareStages", "solveConstraints",
+                                       "prepareConstraints", "integrateVelocities", "warmStart", "solveImpulses",
+                                       "integratePositions", "relaxImpulses", "applyRestitution", "storeImpulses", "splitIslands",
+                                       "transforms", "hitEvents", "refit", "bullets", "sleepIslands", "sensors")]
+
+
 class BodyMoveEvent(C.Structure):
     _fields_ = [("transform", Transform), ("bodyId", BodyId), ("userData", c_void_p), ("fellAsleep", c_bool)]
 
@@ -334,6 +341,7 @@ B2_FUNCTIONS = {
     "b2World_GetGravity": (Vec2, [WorldId]),
     "b2World_EnableWarmStarting": (None, [WorldId, c_bool]),
     "b2World_GetCounters": (Counters, [WorldId]),
+    "b2World_GetProfile": (Profile, [WorldId]),
     "b2World_GetAwakeBodyCount": (c_int, [WorldId]),
     "b2CreateBody": (BodyId, [WorldId, C.POINTER(BodyDef)]),
     "b2Body_IsValid": (c_bool, [BodyId]),

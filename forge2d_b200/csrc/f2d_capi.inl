@@ -57,6 +57,9 @@ struct HostWorld
 	//                    bodies) have changed; uploaded right before the next step instead of the whole image.
 	bool bodyMirrorFresh = false;
 	std::vector<std::pair<uint64_t, uint32_t>> dirty;
+	// b2World_GetProfile: the in-kernel phase marks as they stood at the previous call
+	uint64_t profSeen[kProfSlots] = {};
+	uint64_t profStepSeen = 0;
 	// host callbacks of the callback-mediated step (world.c:1710-1740); the image only carries World::hostCallbacks
 	b2CustomFilterFcn* customFilterFcn = nullptr;
 	void* customFilterContext = nullptr;
@@ -1447,6 +1450,61 @@ int f2dWorld_ReadProfile( b2WorldId worldId, unsigned long long* out, int cap )
 		out[i] = hw->img->prof[i];
 	return kProfSlots;
 }
+// b2World_GetProfile (box2d.h:169, types.h:466-490): milliseconds per phase, averaged over the steps since the previous
+// call. The numbers come from the in-kernel phase marks (rank 0 reads %globaltimer between the phases of the step), which
+// the first call switches on: like the reference's profile they are always available afterwards, for a few clock reads
+// per step. Phases the device step does not have as such (prepareStages, sensors) report 0.
+b2Profile b2World_GetProfile( b2WorldId worldId )
+{
+	b2Profile p;
+	memset( &p, 0, sizeof( p ) );
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return p;
+	World* w = hw->img; // the header is current in every sync state
+	if ( w->profEnabled == 0 )
+	{
+		w = mutableImage( *hw );
+		w->profEnabled = 1;
+		memset( w->prof, 0, sizeof( w->prof ) );
+		memset( hw->profSeen, 0, sizeof( hw->profSeen ) );
+		hw->profStepSeen = w->stepIndex;
+		return p;
+	}
+	const uint64_t steps = w->stepIndex - hw->profStepSeen;
+	if ( steps == 0 )
+		return p;
+	auto ms = [&]( int slot ) {
+		const uint64_t ns = w->prof[slot] - hw->profSeen[slot];
+		return (float)( (double)ns * 1e-6 / (double)steps );
+	};
+	p.pairs = ms( pfBegin ) + ms( pfPairQuery ) + ms( pfPairCreate );
+	p.collide = ms( pfTreeRebuild ) + ms( pfNarrow ) + ms( pfStatePass );
+	p.mergeIslands = ms( pfSolveSetup );
+	p.prepareConstraints = ms( pfPrepare );
+	p.integrateVelocities = ms( pfIntegrateVel );
+	p.warmStart = ms( pfWarmStart );
+	p.solveImpulses = ms( pfSolve );
+	p.integratePositions = ms( pfIntegratePos );
+	p.relaxImpulses = ms( pfRelax );
+	p.applyRestitution = ms( pfRestitution );
+	p.storeImpulses = ms( pfStore );
+	p.splitIslands = ms( pfSplitJoin ) + ms( pfSplitApply );
+	p.solveConstraints = p.prepareConstraints + p.integrateVelocities + p.warmStart + p.solveImpulses + p.integratePositions +
+						 p.relaxImpulses + p.applyRestitution + p.storeImpulses + p.splitIslands;
+	p.transforms = ms( pfFinalizeBodies );
+	p.hitEvents = ms( pfHitEvents );
+	p.refit = ms( pfEnlarge );
+	p.bullets = ms( pfBullets );
+	p.sleepIslands = ms( pfSleep );
+	p.solve = p.mergeIslands + p.solveConstraints + p.transforms + p.hitEvents + p.refit + p.bullets + p.sleepIslands;
+	p.step = p.pairs + p.collide + p.solve + ms( pfEnd );
+	for ( int i = 0; i < kProfSlots; ++i )
+		hw->profSeen[i] = w->prof[i];
+	hw->profStepSeen = w->stepIndex;
+	return p;
+}
+
 void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag )
 {
 	HostWorld* hw = worldFromId( worldId );

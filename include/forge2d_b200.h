@@ -327,6 +327,15 @@ F2D_API bool b2World_IsContinuousEnabled( b2WorldId worldId );					  // box2d.h:
 F2D_API void b2World_SetGravity( b2WorldId worldId, b2Vec2 gravity );			  // box2d.h:135
 F2D_API b2Vec2 b2World_GetGravity( b2WorldId worldId );							  // box2d.h:138
 F2D_API void b2World_EnableWarmStarting( b2WorldId worldId, bool flag );		  // box2d.h:~170
+/// Milliseconds per phase of the step, averaged over the steps since the previous call (in-kernel phase marks; the first
+/// call switches them on and returns zeros). Replaces box2d.h:169 b2World_GetProfile, layout types.h:466-490.
+typedef struct b2Profile
+{
+	float step, pairs, collide, solve, mergeIslands, prepareStages, solveConstraints, prepareConstraints, integrateVelocities,
+		warmStart, solveImpulses, integratePositions, relaxImpulses, applyRestitution, storeImpulses, splitIslands, transforms,
+		hitEvents, refit, bullets, sleepIslands, sensors;
+} b2Profile;
+F2D_API b2Profile b2World_GetProfile( b2WorldId worldId );
 F2D_API b2Counters b2World_GetCounters( b2WorldId worldId );					  // box2d.h:~190 (world.c:1865-1891)
 F2D_API int b2World_GetAwakeBodyCount( b2WorldId worldId );						  // box2d.h (world.c)
 

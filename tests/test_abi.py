@@ -31,6 +31,22 @@ def test_library_exports_every_declared_symbol(product):
     assert product.missing == []
 
 
+def test_ffi_symbols_resolve_by_name_from_c(product, tmp_path):
+    """The binding forge2d generates is `@Native` lookups by symbol name in the loaded asset (box2d.g.dart): a C
+    program dlopens the product and dlsyms each of the 257 names raw_box2d_ffi.dart calls (tests/golden/ffi_symbols.txt)."""
+    import subprocess
+    exe = str(tmp_path / "dlsym_check")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "native", "dlsym_check.c"), "-ldl"])
+    out = subprocess.run([exe, product.path, os.path.join(ROOT, "tests", "golden", "ffi_symbols.txt")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "resolved 257 of 257" in out.stdout
+
+
+def test_profile_is_exported_with_the_reference_layout(product):
+    assert hasattr(C.CDLL(product.path), "b2World_GetProfile")
+    assert C.sizeof(A.Profile) == 22 * 4  # types.h:466-490: 22 floats
+
+
 def test_struct_layouts_match_reference_abi():
     # sizes from the reference headers compiled with gcc x86-64 (SURVEY §2.2 probe, B2/include/box2d/*.h)
     assert C.sizeof(A.WorldId) == 4 and C.sizeof(A.BodyId) == 8 and C.sizeof(A.ShapeId) == 8

@@ -261,3 +261,21 @@ def test_game_loop_reads_and_forces_move_kilobytes_not_the_image(ref, gpu):
     d = H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, b.world))
     assert d == [], d[:6]
     assert gpu.f2dGetLastError() == b""
+
+
+def test_profile_reports_the_phases_of_the_step(gpu):
+    """b2World_GetProfile (box2d.h:169): the first call switches the in-kernel phase marks on, later calls return the
+    milliseconds per phase averaged over the steps in between; the parts add up to the step."""
+    s = scenes.bench2d(gpu, rows=20)
+    for _ in range(20):
+        s.step()
+    first = gpu.b2World_GetProfile(s.world)
+    assert first.step == 0.0
+    for _ in range(30):
+        s.step()
+    p = gpu.b2World_GetProfile(s.world)
+    assert p.step > 0.02 and p.pairs > 0.0 and p.collide > 0.0 and p.solveImpulses > 0.0 and p.relaxImpulses > 0.0 and p.transforms > 0.0
+    assert abs(p.step - (p.pairs + p.collide + p.solve)) < 0.02 * p.step + 1e-3
+    assert p.solve >= p.solveConstraints >= p.solveImpulses
+    assert gpu.b2World_GetProfile(s.world).step == 0.0  # no step since the previous call
+    s.destroy()
