@@ -292,7 +292,9 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 			__syncthreads();
 			for ( int s = 0; s < ( onlyRetry ? 1 : steps ); ++s )
 			{
-				if ( w->error & kErrFatal )
+				const bool fatal = ( w->error & kErrFatal ) != 0;
+				__syncthreads(); // every thread has read the flags before rank 0 touches them again (stepBegin)
+				if ( fatal )
 					break;
 				runPhase( w, team, phase, dt, sub );
 			}

@@ -212,10 +212,14 @@ enum : int
 template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part = kPairsAll )
 {
 	int moveCount = w->moveArray.count;
-	if ( part != kPairsCreate && t.rank() == 0 )
+	if ( part != kPairsCreate )
 	{
-		w->step.orderedPairCount = 0;
-		w->step.retryContacts = 0;
+		if ( t.rank() == 0 )
+		{
+			w->step.orderedPairCount = 0;
+			w->step.retryContacts = 0;
+		}
+		t.sync(); // every caller reads retryContacts right after this routine, whichever way it returns
 	}
 	if ( moveCount == 0 )
 		return;
