@@ -132,6 +132,11 @@ if "batchprofile" in what:
         lib.f2dBatch_Destroy(b)
         scratch.destroy()
 
+if "impact" in what:
+    profile("large_pyramid", {}, 1, 150, 100)
+    profile("large_pyramid", {}, 1, 260, 100)
+    profile("bench2d", dict(rows=10), 0, 128, 128)
+
 if "profile" in what:
     profile("bench2d", {}, 0, 256, 64)
     profile("bench2d", {}, 1, 256, 64)

@@ -15,6 +15,7 @@ t = scenes.bench2d(lib)
 for _ in range(256):
     t.step()
 b = lib.f2dBatch_Create(t.world, worlds)
+lib.f2dBatch_SetLaunchConfig(b, 128, 8)  # the phase launches exist for the one-world-per-block kernel
 for _ in range(steps):
     lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 1)
 lib.f2dBatch_Synchronize(b)
