@@ -7,6 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import forge2d_b200
 from forge2d_b200 import scenes
+from forge2d_b200 import _abi as A
 
 lib = forge2d_b200.load_library()
 assert lib.f2dHasDevice()
@@ -129,6 +130,45 @@ if "batchprofile" in what:
         print("batch %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
             threads, bps, count, ms, count / ms * 1e3, count // 2, total) +
             " ".join("%s=%.1f" % (n, out[i] / steps / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
+        lib.f2dBatch_Destroy(b)
+        scratch.destroy()
+
+if "gangprofile" in what:
+    # in-kernel phase times of worlds of a decorrelated 8192-world batch: the default (gang) kernel and one world per block
+    t = scenes.bench2d(lib)
+    for _ in range(256):
+        t.step()
+    lib.f2dWorld_EnableProfile(t.world, True)
+    for gang in (1, 0):
+        count = 8192
+        b = lib.f2dBatch_Create(t.world, count)
+        if not gang:
+            lib.f2dBatch_SetLaunchConfig(b, 128, 8)
+        offsets = (A.Vec2 * count)(*[A.Vec2(k * 2.0 ** -10, 0.0) for k in range(count)])
+        lib.f2dBatch_TranslateWorlds(b, offsets, count)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, 64)
+        lib.f2dBatch_Synchronize(b)
+        scratch = scenes.bench2d(lib, rows=1)
+        before = {}
+        for idx in (100, 4000, 8000):
+            lib.f2dBatch_DownloadWorld(b, idx, scratch.world)
+            out = (C.c_ulonglong * 24)()
+            lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+            before[idx] = list(out)
+        steps = 8
+        lib.f2dBatch_EventRecord(b, 0)
+        lib.f2dBatch_StepN(b, scenes.TIME_STEP, scenes.SUB_STEPS, steps)
+        lib.f2dBatch_EventRecord(b, 1)
+        lib.f2dBatch_Synchronize(b)
+        ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
+        for idx in (100, 4000, 8000):
+            lib.f2dBatch_DownloadWorld(b, idx, scratch.world)
+            out = (C.c_ulonglong * 24)()
+            lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+            d = [(out[i] - before[idx][i]) / steps / 1e3 for i in range(23)]
+            print("%s, 8192 decorrelated worlds: %.3f ms/step; world %d in-kernel %.1f us: " % (
+                "gang 128x7" if gang else "one world per block 128x8", ms, idx, sum(d)) +
+                " ".join("%s=%.1f" % (n, d[i]) for i, n in enumerate(PROF_NAMES) if d[i] > 0.05), flush=True)
         lib.f2dBatch_Destroy(b)
         scratch.destroy()
 
