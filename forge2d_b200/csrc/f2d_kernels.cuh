@@ -388,7 +388,7 @@ __global__ void __launch_bounds__( kTeamThreads* kTeams, 1 )
 					{
 						ready = true;
 						for ( int k = 0; k < kTeams; ++k )
-							ready = ready && loadVolatile( &phaseDone[k] ) >= q - 1;
+							ready = ready && atomicAdd( &phaseDone[k], 0 ) >= q - 1; // (atomic read of the shared flag)
 					}
 				}
 				team.sync();
@@ -396,7 +396,10 @@ __global__ void __launch_bounds__( kTeamThreads* kTeams, 1 )
 			stepWorldPhase( w, team, phases[q], dt, sub );
 			team.sync();
 			if ( tid == 0 )
-				storeVolatile( &phaseDone[teamIndex], q + 1 );
+			{
+				__threadfence_block();
+				atomicExch( &phaseDone[teamIndex], q + 1 );
+			}
 		}
 		__syncthreads();
 		if ( have )
