@@ -21,24 +21,46 @@ namespace f2d
 //
 // The crew = the team minus its last warp: lets that warp run a serial side task (island split) concurrently with the
 // barrier-separated solver stages.
-struct CtaCrew
+template <bool kWholeBlock> struct CtaCrewT
 {
 	int n, tid, barId;
 	int32_t* arena;
 	int arenaInts;
 	__device__ int32_t* arenaPtr() const { return arena; }
 	__device__ int arenaSize() const { return arenaInts; }
-	__device__ int groupCount() const { return n >> 5; }
-	__device__ int groupIndex() const { return tid >> 5; }
-	__device__ int lane() const { return tid & 31; }
+	// (a whole-block team reads its rank and size from the special registers, as the round-1 kernels did: held in the
+	// struct they cost registers the solver stages do not have at 64 per thread)
+	__device__ int groupCount() const { return size() >> 5; }
+	__device__ int groupIndex() const { return rank() >> 5; }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
 	__device__ int groupSize() const { return 32; }
 	__device__ void groupSync() const { __syncwarp(); }
-	__device__ int rank() const { return tid; }
-	__device__ int size() const { return n; }
-	__device__ void sync() const { asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( n ) : "memory" ); }
+	__device__ int rank() const
+	{
+		if constexpr ( kWholeBlock )
+			return (int)threadIdx.x;
+		else
+			return tid;
+	}
+	__device__ int size() const
+	{
+		if constexpr ( kWholeBlock )
+			return (int)blockDim.x - 32;
+		else
+			return n;
+	}
+	__device__ void sync() const
+	{
+		if constexpr ( kWholeBlock )
+			asm volatile( "bar.sync 1, %0;" ::"r"( (int)blockDim.x - 32 ) : "memory" ); // the crew of a whole-block team: barrier 1
+		else
+			asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( n ) : "memory" );
+	}
 };
 
-struct CtaTeam
+// kWholeBlock: the team is the whole thread block (barrier 0 = __syncthreads, which the compiler knows); otherwise a
+// slice of the block with barrier ids held in registers.
+template <bool kWholeBlock> struct CtaTeamT
 {
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = true;
@@ -50,31 +72,49 @@ struct CtaTeam
 	int32_t* arena = nullptr;
 	int arenaInts = 0;
 	// the whole block as one team
-	static __device__ CtaTeam block( int32_t* smem ) { return CtaTeam{ smem, (int)threadIdx.x, (int)blockDim.x, 0, 1 }; }
+	static __device__ CtaTeamT block( int32_t* smem ) { return CtaTeamT{ smem, (int)threadIdx.x, (int)blockDim.x, 0, 1 }; }
 	// Forking pays when the crew keeps most of the team: with two warps the solver would run on one while the other
 	// walks (measured: the walking warp then waits ~2x its walk for the crew), so two-warp teams walk first, then solve;
 	// from four warps up the crew of three or more hides the walk (measured at 128 threads: 8 % of warp time idle otherwise).
-	__device__ bool canFork() const { return nthreads >= 128; }
-	__device__ bool inSide() const { return tid >= nthreads - 32; }
-	__device__ bool isSideLeader() const { return tid == nthreads - 32; }
+	__device__ bool canFork() const { return size() >= 128; }
+	__device__ bool inSide() const { return rank() >= size() - 32; }
+	__device__ bool isSideLeader() const { return rank() == size() - 32; }
 	typedef WarpLanes Lanes;
-	__device__ bool inSideGroup() const { return tid >= nthreads - 32; }
-	__device__ bool inFirstGroup() const { return tid < 32; }
-	__device__ CtaCrew crew() const { return CtaCrew{ nthreads - 32, tid, crewBarId, arena, arenaInts }; }
-	__device__ int groupCount() const { return nthreads >> 5; }
-	__device__ int groupIndex() const { return tid >> 5; }
-	__device__ int lane() const { return tid & 31; }
+	__device__ bool inSideGroup() const { return rank() >= size() - 32; }
+	__device__ bool inFirstGroup() const { return rank() < 32; }
+	__device__ CtaCrewT<kWholeBlock> crew() const { return CtaCrewT<kWholeBlock>{ size() - 32, rank(), crewBarId, arena, arenaInts }; }
+	__device__ int groupCount() const { return size() >> 5; }
+	__device__ int groupIndex() const { return rank() >> 5; }
+	__device__ int lane() const { return (int)( threadIdx.x & 31 ); }
 	__device__ int groupSize() const { return 32; }
 	__device__ void groupSync() const { __syncwarp(); }
 	__device__ int32_t* arenaPtr() const { return arena; }
 	__device__ int arenaSize() const { return arenaInts; }
-	__device__ int rank() const { return tid; }
-	__device__ int size() const { return nthreads; }
-	__device__ void sync() const { asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( nthreads ) : "memory" ); }
+	__device__ int rank() const
+	{
+		if constexpr ( kWholeBlock )
+			return (int)threadIdx.x;
+		else
+			return tid;
+	}
+	__device__ int size() const
+	{
+		if constexpr ( kWholeBlock )
+			return (int)blockDim.x;
+		else
+			return nthreads;
+	}
+	__device__ void sync() const
+	{
+		if constexpr ( kWholeBlock )
+			__syncthreads();
+		else
+			asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( nthreads ) : "memory" );
+	}
 	// in-place exclusive scan of data[0..n) in global memory; returns the total. Team-wide collective.
 	__device__ int exclusiveScan( int32_t* data, int n ) const
 	{
-		const int nt = nthreads;
+		const int nt = size(), tid = rank();
 		int32_t* warpSums = smem; // 32 entries
 		int carry = 0;
 		for ( int base = 0; base < n; base += nt )
@@ -116,6 +156,8 @@ struct CtaTeam
 		return carry;
 	}
 };
+typedef CtaTeamT<true> CtaTeam;	 // one world per block (and the solo block of a grid)
+typedef CtaTeamT<false> GangTeam; // one of several worlds of a block (stepWorldsGang)
 
 // Grid-wide barrier state in global memory: a monotonically increasing arrival counter (wraps harmlessly) and the
 // count it had when the previous kernel on the stream finished.
@@ -331,7 +373,7 @@ __global__ void __launch_bounds__( kTeamThreads* kTeams, 1 )
 	// barrier 0: the block; 1 .. kTeams: the teams; kTeams + 1 .. 2 kTeams: their crews (16 hardware barriers per block)
 	// (teams under 128 threads never fork: CtaTeam::canFork)
 	static_assert( ( kTeamThreads >= 128 ? 2 : 1 ) * kTeams + 1 <= 16, "one hardware barrier per team and per crew, plus the block's" );
-	CtaTeam team{ scratch[teamIndex], tid, kTeamThreads, 1 + teamIndex, 1 + kTeams + teamIndex };
+	GangTeam team{ scratch[teamIndex], tid, kTeamThreads, 1 + teamIndex, 1 + kTeams + teamIndex };
 	World* w = reinterpret_cast<World*>( headers[teamIndex] );
 	while ( true )
 	{

@@ -492,7 +492,7 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 			F2D_PUSH_EVENT( w, w->beginEvents, ev );
 		}
 		c.flags |= kContactTouching;
-		linkContact( w, c );
+		linkContact( w, c, contactId );
 		sim.simFlags &= ~kSimStartedTouching;
 		addContactToGraph( w, contactId );
 		// remove from the awake non-touching list (world.c:472-485); c.localIndex now is the colour slot
@@ -509,7 +509,7 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 			EndTouchEvent ev = { makeShapeId( w, shapeA ), makeShapeId( w, shapeB ) };
 			F2D_PUSH_EVENT( w, w->endEvents[w->endEventArrayIndex], ev );
 		}
-		unlinkContact( w, c );
+		unlinkContact( w, c, contactId );
 		int bodyIdA = c.edges[0].bodyId;
 		int bodyIdB = c.edges[1].bodyId;
 		// back to the awake non-touching list (world.c:461-470)
@@ -520,8 +520,120 @@ F2D_HDF inline void contactStateChange( World* w, int contactId )
 	}
 }
 
+// The same state change as two halves that touch DISJOINT data and can therefore run on two threads at once, each
+// visiting the flagged contacts in ascending id: the island half (touching flag, begin / end events, island link /
+// unlink) and the graph half (colour graph, awake / colour id lists, body contact-edge lists, contact id pool, solver
+// indices). `kind` is the contact's class, read from its flags by the compaction pass before either half changed them.
+// Not usable when a begin-touch wakes a sleeping set (island.c:121-133): that moves bodies and contacts between sets and
+// colours - contactStatePass then falls back to the one-thread version above.
+enum : int
+{
+	kStateDisjoint = 0,
+	kStateStarted = 1,
+	kStateStopped = 2,
+	kStateNone = 3
+};
+F2D_HDF inline void contactStateIslandHalf( World* w, int contactId, int kind )
+{
+	Contact* contacts = ptr( w, w->contacts );
+	Contact& c = contacts[contactId];
+	const Shape* shapes = ptr( w, w->shapes );
+	const uint32_t flags = c.flags;
+	if ( kind == kStateDisjoint )
+	{
+		// destroyContact( w, contactId, false ): end event of a touching contact, island unlink
+		if ( ( flags & kContactTouching ) != 0 && ( flags & kContactEnableContactEvents ) != 0 )
+		{
+			EndTouchEvent ev = { makeShapeId( w, shapes[c.shapeIdA] ), makeShapeId( w, shapes[c.shapeIdB] ) };
+			F2D_PUSH_EVENT( w, w->endEvents[w->endEventArrayIndex], ev );
+		}
+		if ( c.islandId != kNull )
+			unlinkContact( w, c, contactId );
+	}
+	else if ( kind == kStateStarted )
+	{
+		if ( flags & kContactEnableContactEvents )
+		{
+			BeginTouchEvent ev;
+			ev.a = makeShapeId( w, shapes[c.shapeIdA] );
+			ev.b = makeShapeId( w, shapes[c.shapeIdB] );
+			ev.manifold = unpackManifold( ptr( w, w->contactSims )[contactId].manifold );
+			F2D_PUSH_EVENT( w, w->beginEvents, ev );
+		}
+		c.flags = flags | kContactTouching;
+		linkContact( w, c, contactId );
+	}
+	else if ( kind == kStateStopped )
+	{
+		c.flags = flags & ~kContactTouching;
+		if ( flags & kContactEnableContactEvents )
+		{
+			EndTouchEvent ev = { makeShapeId( w, shapes[c.shapeIdA] ), makeShapeId( w, shapes[c.shapeIdB] ) };
+			F2D_PUSH_EVENT( w, w->endEvents[w->endEventArrayIndex], ev );
+		}
+		unlinkContact( w, c, contactId );
+	}
+}
+F2D_HDF inline void contactStateGraphHalf( World* w, int contactId, int kind )
+{
+	Contact* contacts = ptr( w, w->contacts );
+	Contact& c = contacts[contactId];
+	ContactSim& sim = ptr( w, w->contactSims )[contactId];
+	const int colorIndex = c.colorIndex;
+	const int localIndex = c.localIndex;
+	const int bodyIdA = c.edges[0].bodyId, bodyIdB = c.edges[1].bodyId;
+	if ( kind == kStateDisjoint )
+	{
+		// destroyContact( w, contactId, false ): body contact-edge lists, graph / set list, record, id pool
+		Body* bodies = ptr( w, w->bodies );
+		const Edge edgeA = c.edges[0], edgeB = c.edges[1];
+		if ( edgeA.prevKey != kNull )
+			contacts[edgeA.prevKey >> 1].edges[edgeA.prevKey & 1].nextKey = edgeA.nextKey;
+		if ( edgeA.nextKey != kNull )
+			contacts[edgeA.nextKey >> 1].edges[edgeA.nextKey & 1].prevKey = edgeA.prevKey;
+		if ( bodies[bodyIdA].headContactKey == ( ( contactId << 1 ) | 0 ) )
+			bodies[bodyIdA].headContactKey = edgeA.nextKey;
+		bodies[bodyIdA].contactCount -= 1;
+		if ( edgeB.prevKey != kNull )
+			contacts[edgeB.prevKey >> 1].edges[edgeB.prevKey & 1].nextKey = edgeB.nextKey;
+		if ( edgeB.nextKey != kNull )
+			contacts[edgeB.nextKey >> 1].edges[edgeB.nextKey & 1].prevKey = edgeB.prevKey;
+		if ( bodies[bodyIdB].headContactKey == ( ( contactId << 1 ) | 1 ) )
+			bodies[bodyIdB].headContactKey = edgeB.nextKey;
+		bodies[bodyIdB].contactCount -= 1;
+		if ( colorIndex != kNull )
+			removeContactFromGraph( w, bodyIdA, bodyIdB, colorIndex, localIndex );
+		else
+			removeContactFromSetList( w, c );
+		c.contactId = kNull;
+		c.setIndex = kNull;
+		c.colorIndex = kNull;
+		c.localIndex = kNull;
+		freeId( w, w->contactIds, contactId );
+	}
+	else if ( kind == kStateStarted )
+	{
+		sim.simFlags &= ~kSimStartedTouching;
+		addContactToGraph( w, contactId );
+		// remove from the awake non-touching list (world.c:472-485); c.localIndex now is the colour slot
+		int moved = removeSwap( w, w->awakeContacts, localIndex );
+		if ( moved != kNull )
+			contacts[ptr( w, w->awakeContacts )[localIndex]].localIndex = localIndex;
+	}
+	else if ( kind == kStateStopped )
+	{
+		sim.simFlags &= ~kSimStoppedTouching;
+		// back to the awake non-touching list (world.c:461-470)
+		c.colorIndex = kNull;
+		c.localIndex = w->awakeContacts.count;
+		F2D_PUSH( w, w->awakeContacts, contactId );
+		removeContactFromGraph( w, bodyIdA, bodyIdB, colorIndex, localIndex );
+	}
+}
+
 // Ordered contact-state pass, ascending contact id (world.c:587-686). The flagged ids are compacted by the whole team
-// (popcount per 64-bit word + prefix sum), then rank 0 applies the order-defining structural edits one by one.
+// (popcount per 64-bit word + prefix sum) together with their class; then the order-defining structural edits are
+// applied one contact after the other - by two threads, one per half (see above), when the team has them.
 template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 {
 	const uint64_t* bits = ptr( w, w->contactBits );
@@ -547,6 +659,8 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 		}
 		offsets[k] = n;
 	}
+	if ( t.rank() == 0 )
+		w->step.stateNeedsSerial = 0;
 	t.sync();
 	int total = t.exclusiveScan( offsets, wordCount );
 	if ( total == 0 )
@@ -557,24 +671,60 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 			setError( w, kErrCapacity, __LINE__ );
 		return;
 	}
-	for ( int k = t.rank(); k < wordCount; k += t.size() )
+	constexpr int kKindShift = 28; // list entry = contact id | class << 28
 	{
-		uint64_t word = bits[k];
-		int out = offsets[k];
-		int bit = 0;
-		while ( word != 0 )
+		const ContactSim* sims = ptr( w, w->contactSims );
+		const Contact* contacts = ptr( w, w->contacts );
+		const Body* bodies = ptr( w, w->bodies );
+		for ( int k = t.rank(); k < wordCount; k += t.size() )
 		{
-			if ( word & 1ull )
-				list[out++] = 64 * k + bit;
-			word >>= 1;
-			bit += 1;
+			uint64_t word = bits[k];
+			int out = offsets[k];
+			int bit = 0;
+			while ( word != 0 )
+			{
+				if ( word & 1ull )
+				{
+					const int id = 64 * k + bit;
+					const uint32_t simFlags = sims[id].simFlags;
+					int kind = kStateNone;
+					if ( simFlags & kSimDisjoint )
+						kind = kStateDisjoint;
+					else if ( simFlags & kSimStartedTouching )
+					{
+						kind = kStateStarted;
+						const Contact& c = contacts[id];
+						if ( bodies[c.edges[0].bodyId].setIndex >= kFirstSleepingSet || bodies[c.edges[1].bodyId].setIndex >= kFirstSleepingSet )
+							storeVolatile( &w->step.stateNeedsSerial, 1 );
+					}
+					else if ( simFlags & kSimStoppedTouching )
+						kind = kStateStopped;
+					list[out++] = id | ( kind << kKindShift );
+				}
+				word >>= 1;
+				bit += 1;
+			}
 		}
 	}
 	t.sync();
-	if ( t.rank() == 0 )
+	const bool twoThreads = t.size() >= 64 && w->step.stateNeedsSerial == 0 && w->contactIds.next < ( 1 << kKindShift );
+	if ( twoThreads )
+	{
+		if ( t.rank() == 0 )
+		{
+			for ( int i = 0; i < total; ++i )
+				contactStateIslandHalf( w, list[i] & ( ( 1 << kKindShift ) - 1 ), list[i] >> kKindShift );
+		}
+		else if ( t.rank() == 32 )
+		{
+			for ( int i = 0; i < total; ++i )
+				contactStateGraphHalf( w, list[i] & ( ( 1 << kKindShift ) - 1 ), list[i] >> kKindShift );
+		}
+	}
+	else if ( t.rank() == 0 )
 	{
 		for ( int i = 0; i < total; ++i )
-			contactStateChange( w, list[i] );
+			contactStateChange( w, list[i] & ( ( 1 << kKindShift ) - 1 ) );
 	}
 }
 

@@ -578,7 +578,7 @@ struct StepCtx
 	int32_t orderedPairCount; // callback-mediated step: candidate pairs in creation order, waiting for the host's custom filter
 	int32_t preSolveCount;	  // callback-mediated step: touching contacts waiting for the host's pre-solve verdict
 	int32_t fastDeferredCount; // callback-mediated step: fast bodies whose continuous pass waits for the host's custom filter
-	int32_t padStep;
+	int32_t stateNeedsSerial;  // contact state pass: a begin-touch would wake a sleeping set, so the pass runs on one thread
 	int32_t bodiesFinalized;   // stepSolve ran the body loop of finalize beside the island split; stepFinalize only casts the votes
 	int32_t retryContacts;	   // != 0: the step stopped before its first structural edit because the contact arrays cannot take
 							   // this many new contacts (kErrRetry); the host grows the image and runs the step again

@@ -421,15 +421,17 @@ F2D_HDF inline void destroyIsland( World* w, int islandId )
 }
 
 // island.c:92-113
-F2D_HD void addContactToIsland( World* w, int islandId, Contact& c )
+// (`contactId` is passed explicitly: the slot index, not Contact::contactId, which the graph half of the contact state
+// pass may be clearing at the same moment - f2d_step.h contactStateGraphHalf)
+F2D_HD void addContactToIsland( World* w, int islandId, Contact& c, int contactId )
 {
 	Island& is = ptr( w, w->islands )[islandId];
 	if ( is.headContact != kNull )
 	{
 		c.islandNext = is.headContact;
-		ptr( w, w->contacts )[is.headContact].islandPrev = c.contactId;
+		ptr( w, w->contacts )[is.headContact].islandPrev = contactId;
 	}
-	is.headContact = c.contactId;
+	is.headContact = contactId;
 	if ( is.tailContact == kNull )
 		is.tailContact = is.headContact;
 	is.contactCount += 1;
@@ -456,7 +458,7 @@ F2D_HD int islandRoot( Island* islands, int islandId )
 }
 
 // island.c:116-218
-F2D_HDF inline void linkContact( World* w, Contact& c )
+F2D_HDF inline void linkContact( World* w, Contact& c, int contactId )
 {
 	Body* bodies = ptr( w, w->bodies );
 	int idA = c.edges[0].bodyId, idB = c.edges[1].bodyId;
@@ -469,7 +471,7 @@ F2D_HDF inline void linkContact( World* w, Contact& c )
 	int islandIdB = bodies[idB].islandId;
 	if ( islandIdA == islandIdB )
 	{
-		addContactToIsland( w, islandIdA, c );
+		addContactToIsland( w, islandIdA, c, contactId );
 		return;
 	}
 	Island* islands = ptr( w, w->islands );
@@ -480,13 +482,13 @@ F2D_HDF inline void linkContact( World* w, Contact& c )
 	if ( islandIdA != islandIdB && islandIdA != kNull && islandIdB != kNull )
 		islands[islandIdB].parentIsland = islandIdA;
 	if ( islandIdA != kNull )
-		addContactToIsland( w, islandIdA, c );
+		addContactToIsland( w, islandIdA, c, contactId );
 	else
-		addContactToIsland( w, islandIdB, c );
+		addContactToIsland( w, islandIdB, c, contactId );
 }
 
 // island.c:221-262
-F2D_HDF inline void unlinkContact( World* w, Contact& c )
+F2D_HDF inline void unlinkContact( World* w, Contact& c, int contactId )
 {
 	Island& is = ptr( w, w->islands )[c.islandId];
 	Contact* contacts = ptr( w, w->contacts );
@@ -494,9 +496,9 @@ F2D_HDF inline void unlinkContact( World* w, Contact& c )
 		contacts[c.islandPrev].islandNext = c.islandNext;
 	if ( c.islandNext != kNull )
 		contacts[c.islandNext].islandPrev = c.islandPrev;
-	if ( is.headContact == c.contactId )
+	if ( is.headContact == contactId )
 		is.headContact = c.islandNext;
-	if ( is.tailContact == c.contactId )
+	if ( is.tailContact == contactId )
 		is.tailContact = c.islandPrev;
 	is.contactCount -= 1;
 	is.constraintRemoveCount += 1;
@@ -1101,7 +1103,7 @@ F2D_HDF inline void destroyContact( World* w, int contactId, bool wakeBodies )
 	bodyB.contactCount -= 1;
 
 	if ( c.islandId != kNull )
-		unlinkContact( w, c );
+		unlinkContact( w, c, contactId );
 
 	if ( c.colorIndex != kNull )
 		removeContactFromGraph( w, bodyIdA, bodyIdB, c.colorIndex, c.localIndex );
