@@ -257,6 +257,7 @@ struct GridTeam
 	__device__ void sync() { gridBarrierWait( barrier, gen, gridDim.x ); }
 	// the tree rebuild runs on block 0 alone (block-level barriers) while the other blocks do the narrowphase
 	__device__ bool inSoloBlock() const { return blockIdx.x == 0; }
+	__device__ int soloSize() const { return (int)blockDim.x; }
 	__device__ bool hasOutsideSolo() const { return gridDim.x > 1; }
 	__device__ CtaTeam soloTeam() const { return CtaTeam::block( smem ); }
 	__device__ int rankOutsideSolo() const { return (int)( ( blockIdx.x - 1 ) * blockDim.x + threadIdx.x ); }

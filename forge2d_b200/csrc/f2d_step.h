@@ -317,6 +317,36 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part
 		{
 			total = w->step.orderedPairCount;
 		}
+		if constexpr ( Team::kHasSoloBlock )
+		{
+			// a grid: the other threads of the serial thread's block read what contact creation is about to chase, so
+			// that it runs on L1 hits (see contactStatePass)
+			if ( total > 0 && t.inSoloBlock() && t.rank() >= 32 )
+			{
+				const Shape* shapes = ptr( w, w->shapes );
+				const Body* bodies = ptr( w, w->bodies );
+				const Contact* contacts = ptr( w, w->contacts );
+				int acc = 0;
+				for ( int k = t.rank() - 32; k < total && k < 2048; k += t.soloSize() - 32 )
+				{
+					const MovePair& pair = pairs[ordered[k]];
+					if ( pair.shapeA == kNull )
+						continue;
+					const Shape& a = shapes[pair.shapeA];
+					const Shape& b = shapes[pair.shapeB];
+					acc += a.bodyId + b.bodyId + a.type + b.type + (int)floatBits( a.restitution ) + (int)floatBits( b.restitution );
+					const Body& ba = bodies[a.bodyId];
+					const Body& bb = bodies[b.bodyId];
+					acc += ba.setIndex + bb.setIndex;
+					if ( ba.headContactKey != kNull )
+						acc += contacts[ba.headContactKey >> 1].edges[ba.headContactKey & 1].prevKey;
+					if ( bb.headContactKey != kNull )
+						acc += contacts[bb.headContactKey >> 1].edges[bb.headContactKey & 1].prevKey;
+				}
+				if ( acc == 0x7fffffff ) // (never: keeps the loads alive)
+					storeVolatile( &w->step.orderedPairCount, total );
+			}
+		}
 		if ( total > 0 && t.rank() == 0 )
 		{
 			for ( int k = 0; k < total; ++k )
@@ -708,6 +738,40 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 	}
 	t.sync();
 	const bool twoThreads = t.size() >= 64 && w->step.stateNeedsSerial == 0 && w->contactIds.next < ( 1 << kKindShift );
+	if constexpr ( Team::kHasSoloBlock )
+	{
+		// A grid: the records the two serial threads are about to chase were written by other SMs (narrowphase) and sit
+		// in L2; the other threads of their block read them once, in parallel, which parks them in this SM's L1 - the
+		// serial chains then run on L1 hits (~40 cycles) instead of L2 round trips (~700).
+		if ( t.inSoloBlock() && t.rank() >= 64 )
+		{
+			const Contact* contacts = ptr( w, w->contacts );
+			const ContactSim* sims = ptr( w, w->contactSims );
+			const Body* bodies = ptr( w, w->bodies );
+			const BodySim* bsims = ptr( w, w->sims );
+			const Island* islands = ptr( w, w->islands );
+			const Shape* shapes = ptr( w, w->shapes );
+			int acc = 0;
+			for ( int i = t.rank() - 64; i < total && i < 1024; i += t.soloSize() - 64 )
+			{
+				const int id = list[i] & ( ( 1 << kKindShift ) - 1 );
+				const Contact& c = contacts[id];
+				const int a = c.edges[0].bodyId, b = c.edges[1].bodyId;
+				acc += c.islandId + c.colorIndex + c.edges[0].nextKey + c.edges[1].nextKey;
+				acc += (int)sims[id].simFlags + sims[id].bodySimIndexA + sims[id].manifold.pointCount;
+				const int ia = bodies[a].islandId, ib = bodies[b].islandId;
+				acc += bodies[a].setIndex + bodies[b].setIndex + bodies[a].colorMask + bodies[b].colorMask;
+				acc += floatBits( bsims[a].invMass ) + floatBits( bsims[b].invMass );
+				if ( ia != kNull )
+					acc += islands[ia].headContact + islands[ia].parentIsland;
+				if ( ib != kNull )
+					acc += islands[ib].headContact + islands[ib].parentIsland;
+				acc += shapes[c.shapeIdA].generation + shapes[c.shapeIdB].generation;
+			}
+			if ( acc == 0x7fffffff ) // (never: keeps the loads alive)
+				storeVolatile( &w->step.stateNeedsSerial, 0 );
+		}
+	}
 	if ( twoThreads )
 	{
 		if ( t.rank() == 0 )
