@@ -107,7 +107,7 @@ static DeviceMirror* mirror( HostWorld& hw )
 		DeviceMirror* m = new DeviceMirror();
 		cudaStreamCreateWithFlags( &m->stream, cudaStreamNonBlocking );
 		cudaMalloc( &m->blockTotals, 4096 * sizeof( int32_t ) );
-		cudaMemset( m->blockTotals, 0, 4096 * sizeof( int32_t ) ); // [0,64): GridBarrier, then per-block scan totals
+		cudaMemset( m->blockTotals, 0, 4096 * sizeof( int32_t ) ); // [0,192): three GridBarriers (team, crew, rear), then per-block scan totals
 		for ( int i = 0; i < 6; ++i )
 			cudaEventCreate( &m->ev[i] );
 		hw.backend = m;

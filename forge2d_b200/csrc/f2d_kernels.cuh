@@ -21,6 +21,64 @@ namespace f2d
 //
 // The crew = the team minus its last warp: lets that warp run a serial side task (island split) concurrently with the
 // barrier-separated solver stages.
+// In-place exclusive scan of data[0..n) by a slice of a thread block (whole warps, `scratch` = 64 ints of shared memory
+// owned by the slice); returns the total. Collective over the slice, ONE barrier per chunk of size() items: every warp
+// publishes its sum, and after the barrier every warp scans the published sums for itself (the sums of two successive
+// chunks live in different halves of the scratch, so a warp that runs ahead cannot overwrite what a slower one still reads).
+template <class Slice> __device__ __forceinline__ int sliceExclusiveScan( const Slice& t, int32_t* scratch, int32_t* data, int n )
+{
+	const int nt = t.size(), tid = t.rank();
+	const int lane = tid & 31, warp = tid >> 5, warps = nt >> 5;
+	int carry = 0;
+	int parity = 0;
+	for ( int base = 0; base < n; base += nt, parity ^= 32 )
+	{
+		int i = base + tid;
+		int v = i < n ? data[i] : 0;
+		// warp inclusive scan
+		int x = v;
+		for ( int off = 1; off < 32; off <<= 1 )
+		{
+			int y = __shfl_up_sync( 0xffffffffu, x, off );
+			if ( lane >= off )
+				x += y;
+		}
+		int32_t* warpSums = scratch + parity;
+		if ( lane == 31 )
+			warpSums[warp] = x;
+		t.sync();
+		// sums of the warps before this one, and of all of them
+		int ws = lane < warps ? warpSums[lane] : 0;
+		int before = lane < warp ? ws : 0;
+		for ( int off = 16; off > 0; off >>= 1 )
+		{
+			ws += __shfl_xor_sync( 0xffffffffu, ws, off );
+			before += __shfl_xor_sync( 0xffffffffu, before, off );
+		}
+		if ( i < n )
+			data[i] = carry + before + ( x - v );
+		carry += ws;
+	}
+	// (the next collective of the slice starts with a barrier of its own before anybody reads data[])
+	t.sync();
+	return carry;
+}
+
+// All warps of a thread block but the first two, as a team of their own (hardware barrier 2): see CtaTeamT::rear.
+struct CtaRear
+{
+	int32_t* scratch;
+	int32_t* arena; // the block's shared-memory work area (CtaTeamT::arena), free while the rear is on its own
+	int arenaInts;
+	typedef WarpLanes Lanes;
+	__device__ int32_t* arenaPtr() const { return arena; }
+	__device__ int arenaSize() const { return arenaInts; }
+	__device__ int rank() const { return (int)threadIdx.x - 64; }
+	__device__ int size() const { return (int)blockDim.x - 64; }
+	__device__ void sync() const { asm volatile( "bar.sync 2, %0;" ::"r"( (int)blockDim.x - 64 ) : "memory" ); }
+	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
+};
+
 template <bool kWholeBlock> struct CtaCrewT
 {
 	int n, tid, barId;
@@ -59,8 +117,9 @@ template <bool kWholeBlock> struct CtaCrewT
 };
 
 // kWholeBlock: the team is the whole thread block (barrier 0 = __syncthreads, which the compiler knows); otherwise a
-// slice of the block with barrier ids held in registers.
-template <bool kWholeBlock> struct CtaTeamT
+// slice of the block with barrier ids held in registers. kLarge: a whole-block team of 512 threads or more (one world
+// that has an SM to itself), which can put its rear on a task of its own.
+template <bool kWholeBlock, bool kLarge = false> struct CtaTeamT
 {
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = true;
@@ -112,51 +171,16 @@ template <bool kWholeBlock> struct CtaTeamT
 			asm volatile( "bar.sync %0, %1;" ::"r"( barId ), "r"( nthreads ) : "memory" );
 	}
 	// in-place exclusive scan of data[0..n) in global memory; returns the total. Team-wide collective.
-	__device__ int exclusiveScan( int32_t* data, int n ) const
-	{
-		const int nt = size(), tid = rank();
-		int32_t* warpSums = smem; // 32 entries
-		int carry = 0;
-		for ( int base = 0; base < n; base += nt )
-		{
-			int i = base + tid;
-			int v = i < n ? data[i] : 0;
-			// warp inclusive scan
-			int x = v;
-			for ( int off = 1; off < 32; off <<= 1 )
-			{
-				int y = __shfl_up_sync( 0xffffffffu, x, off );
-				if ( ( tid & 31 ) >= off )
-					x += y;
-			}
-			if ( ( tid & 31 ) == 31 )
-				warpSums[tid >> 5] = x;
-			sync();
-			if ( tid < 32 )
-			{
-				int ws = tid < ( nt >> 5 ) ? warpSums[tid] : 0;
-				int s = ws;
-				for ( int off = 1; off < 32; off <<= 1 )
-				{
-					int y = __shfl_up_sync( 0xffffffffu, s, off );
-					if ( tid >= off )
-						s += y;
-				}
-				warpSums[tid] = s - ws; // exclusive prefix of warp sums
-				if ( tid == 31 )
-					smem[32] = s; // chunk total
-			}
-			sync();
-			int excl = carry + warpSums[tid >> 5] + ( x - v );
-			if ( i < n )
-				data[i] = excl;
-			carry += smem[32];
-			sync();
-		}
-		return carry;
-	}
+	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, smem, data, n ); }
+	// The rear of a large whole-block team: everybody but the first two warps, with a barrier and scan scratch of its own
+	// (stepCollide: the rear rebuilds the trees while two threads of the front apply the ordered contact-state changes)
+	static constexpr bool kCanSplitTree = kWholeBlock && kLarge;
+	__device__ bool canSplitTree() const { return true; }
+	__device__ bool inFront() const { return threadIdx.x < 64; }
+	__device__ CtaRear rear() const { return CtaRear{ smem + 64, arena, arenaInts }; }
 };
 typedef CtaTeamT<true> CtaTeam;	 // one world per block (and the solo block of a grid)
+typedef CtaTeamT<true, true> LargeCtaTeam; // one world per block of >= 512 threads
 typedef CtaTeamT<false> GangTeam; // one of several worlds of a block (stepWorldsGang)
 
 // Grid-wide barrier state in global memory: a monotonically increasing arrival counter (wraps harmlessly) and the
@@ -210,11 +234,63 @@ struct GridCrew
 	__device__ void sync() const { gridBarrierWait( barrier, *gen, gridDim.x - 1 ); }
 };
 
+// In-place exclusive scan by the blocks [firstBlock, firstBlock + nb) of a grid: each block scans one contiguous tile,
+// the tile offsets are added after a barrier of those blocks (`sync`). Returns the total.
+template <class Sync>
+__device__ __forceinline__ int gridSliceScan( int firstBlock, int nb, int32_t* smem, int32_t* blockTotals, Sync&& sync, int32_t* data, int n )
+{
+	const int b0 = (int)blockIdx.x - firstBlock;
+	const int tile = ( n + nb - 1 ) / nb;
+	const int begin = min( n, b0 * tile );
+	const int end = min( n, begin + tile );
+	CtaTeam cta = CtaTeam::block( smem );
+	int total = cta.exclusiveScan( data + begin, end - begin );
+	if ( threadIdx.x == 0 )
+		blockTotals[b0] = total;
+	sync();
+	int offset = 0, sum = 0;
+	for ( int b = 0; b < nb; ++b )
+	{
+		int v = blockTotals[b];
+		if ( b < b0 )
+			offset += v;
+		sum += v;
+	}
+	for ( int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x )
+		data[i] += offset;
+	sync();
+	return sum;
+}
+
+// All blocks of the grid but the first, as a team of their own (grid barrier 2): rebuilds the trees while block 0 applies
+// the ordered contact-state changes (stepCollide).
+struct GridRear
+{
+	GridBarrier* barrier;
+	unsigned int* gen;
+	int32_t* smem;
+	int32_t* blockTotals;
+	typedef WarpLanes Lanes;
+	__device__ int32_t* arenaPtr() const { return nullptr; }
+	__device__ int arenaSize() const { return 0; }
+	__device__ int rank() const { return (int)( ( blockIdx.x - 1 ) * blockDim.x + threadIdx.x ); }
+	__device__ int size() const { return (int)( ( gridDim.x - 1 ) * blockDim.x ); }
+	__device__ void sync() const { gridBarrierWait( barrier, *gen, gridDim.x - 1 ); }
+	__device__ int exclusiveScan( int32_t* data, int n ) const
+	{
+		return gridSliceScan( 1, (int)gridDim.x - 1, smem, blockTotals, [&]() { sync(); }, data, n );
+	}
+};
+
 struct GridTeam
 {
 	static constexpr bool kHasSoloBlock = true;
 	static constexpr bool kCanFork = true;
-	unsigned int crewGen;
+	static constexpr bool kCanSplitTree = true;
+	unsigned int crewGen, rearGen;
+	__device__ bool canSplitTree() const { return gridDim.x >= 2; }
+	__device__ bool inFront() const { return blockIdx.x == 0; }
+	__device__ GridRear rear() { return GridRear{ barrier + 2, &rearGen, smem, blockTotals }; }
 	__device__ bool canFork() const { return gridDim.x >= 2; }
 	__device__ bool inSide() const { return blockIdx.x == gridDim.x - 1; }
 	__device__ bool isSideLeader() const { return blockIdx.x == gridDim.x - 1 && threadIdx.x == 0; }
@@ -239,10 +315,12 @@ struct GridTeam
 	{
 		gen = 0;
 		crewGen = 0;
+		rearGen = 0;
 		if ( threadIdx.x == 0 )
 		{
 			gen = *reinterpret_cast<volatile unsigned int*>( &barrier[0].base );
 			crewGen = *reinterpret_cast<volatile unsigned int*>( &barrier[1].base );
+			rearGen = *reinterpret_cast<volatile unsigned int*>( &barrier[2].base );
 		}
 	}
 	__device__ void end()
@@ -253,6 +331,9 @@ struct GridTeam
 			*reinterpret_cast<volatile unsigned int*>( &barrier[0].base ) = gen;
 			*reinterpret_cast<volatile unsigned int*>( &barrier[1].base ) = crewGen;
 		}
+		// (block 0 is not part of the rear)
+		if ( blockIdx.x == 1 && threadIdx.x == 0 )
+			*reinterpret_cast<volatile unsigned int*>( &barrier[2].base ) = rearGen;
 	}
 	__device__ void sync() { gridBarrierWait( barrier, gen, gridDim.x ); }
 	// the tree rebuild runs on block 0 alone (block-level barriers) while the other blocks do the narrowphase
@@ -264,28 +345,7 @@ struct GridTeam
 	__device__ int sizeOutsideSolo() const { return (int)( ( gridDim.x - 1 ) * blockDim.x ); }
 	__device__ int exclusiveScan( int32_t* data, int n )
 	{
-		// each block scans one contiguous tile, then tile offsets are added after a grid barrier
-		const int nb = (int)gridDim.x;
-		const int tile = ( n + nb - 1 ) / nb;
-		const int begin = min( n, (int)blockIdx.x * tile );
-		const int end = min( n, begin + tile );
-		CtaTeam cta = CtaTeam::block( smem );
-		int total = cta.exclusiveScan( data + begin, end - begin );
-		if ( threadIdx.x == 0 )
-			blockTotals[blockIdx.x] = total;
-		sync();
-		int offset = 0, sum = 0;
-		for ( int b = 0; b < nb; ++b )
-		{
-			int v = blockTotals[b];
-			if ( b < (int)blockIdx.x )
-				offset += v;
-			sum += v;
-		}
-		for ( int i = begin + (int)threadIdx.x; i < end; i += (int)blockDim.x )
-			data[i] += offset;
-		sync();
-		return sum;
+		return gridSliceScan( 0, (int)gridDim.x, smem, blockTotals, [&]() { sync(); }, data, n );
 	}
 };
 
@@ -303,10 +363,11 @@ __global__ void __launch_bounds__( kThreads, kMinBlocks )
 	stepWorldsCta( char* base, unsigned long long stride, int worldCount, float dt, int sub, int phase, int steps, int arenaBytes,
 				   uint4* hostHeader )
 {
-	__shared__ int32_t smem[64];
+	typedef CtaTeamT<true, ( kThreads >= 512 )> Team;
+	__shared__ int32_t smem[128]; // scan scratch of the team, and of its rear (CtaRear)
 	__shared__ uint4 header[sizeof( World ) / 16];
 	extern __shared__ int4 dynamicShared[];
-	CtaTeam team = CtaTeam::block( smem );
+	Team team = Team::block( smem );
 	if ( arenaBytes > 0 )
 	{
 		team.arena = reinterpret_cast<int32_t*>( dynamicShared );
@@ -459,7 +520,7 @@ __global__ void __launch_bounds__( kThreads, 1 )
 	stepWorldGrid( World* w, int32_t* blockTotals, float dt, int sub, int phase, uint4* hostHeader )
 {
 	__shared__ int32_t smem[64];
-	GridTeam team{ 0u, smem, blockTotals + 128, reinterpret_cast<GridBarrier*>( blockTotals ), 0u };
+	GridTeam team{ 0u, 0u, smem, blockTotals + 192, reinterpret_cast<GridBarrier*>( blockTotals ), 0u }; // three barriers, then the scan totals
 	// the grid shares the header in HBM; every block stores the same address, so each may rely on it after its own barrier
 	if ( threadIdx.x == 0 )
 		w->deviceBase = reinterpret_cast<uint64_t>( w );

@@ -168,7 +168,7 @@ __global__ void translateWorlds( char* base, unsigned long long stride, int worl
 	}
 }
 
-constexpr int kSingleCtaThreads = 1024;
+constexpr int kSingleCtaThreads = 512;
 
 // The one-block kernel gets a shared-memory work area (CtaTeam::arena): the block has the SM to itself.
 static int singleCtaArenaBytes()
@@ -177,7 +177,7 @@ static int singleCtaArenaBytes()
 	if ( bytes < 0 )
 	{
 		const char* kb = getenv( "F2D_SINGLE_ARENA_KB" ); // tuning aid
-		bytes = ( kb != nullptr ? atoi( kb ) : 48 ) * 1024; // measured on bench2d: 48 KB 0.59 ms per frame, 96 KB 0.65 (less L1)
+		bytes = ( kb != nullptr ? atoi( kb ) : 56 ) * 1024; // with the static 4 KB: the 64 KB carve-out (measured on bench2d: 96 KB costs 60 us per frame, less L1)
 		if ( bytes > 200 * 1024 )
 			bytes = 200 * 1024;
 		if ( bytes > 0 &&

@@ -97,6 +97,17 @@ F2D_HDF inline bool shouldBodiesCollide( World* w, const Body& bodyA, const Body
 	return true;
 }
 
+// Reads one word every `stride` bytes of [base, base + bytes): parks those sectors in the L1 of the calling SM. The sum
+// is returned so that the loads stay alive.
+F2D_HDF inline int warmSectors( const void* base, int bytes, int stride, int rank, int size )
+{
+	const char* p = static_cast<const char*>( base );
+	int acc = 0;
+	for ( int i = rank * stride; i < bytes; i += size * stride )
+		acc += *reinterpret_cast<const int32_t*>( p + i );
+	return acc;
+}
+
 // Is there already a contact between these two shapes? Replaces the reference's pairSet hash lookup
 // (broad_phase.c:215-220): a contact for the pair exists iff it hangs off both bodies' contact lists.
 F2D_HDF inline bool pairExists( World* w, const Body& bodyA, const Body& bodyB, int shapeIdA, int shapeIdB )
@@ -231,6 +242,21 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part
 	}
 	if ( part != kPairsCreate )
 	{
+		if constexpr ( Team::kCanSplitTree && Team::kHasSoloBlock == false )
+		{
+			// One block with an SM to itself, and its L1 is cold at the start of the launch: every query below is a chain
+			// of dependent loads (tree nodes, then per hit the shapes, the bodies and a walk over a body's contacts) that
+			// would each go to L2. The whole team first reads one word of every 32-byte sector those chains can touch -
+			// independent loads, one L2 latency in all - so the chains run on L1 hits.
+			const Tree& tree = w->trees[kDynamicBody];
+			int acc = warmSectors( ptr( w, tree.nodes ), tree.nodes.count * (int)sizeof( TreeNode ), 32, t.rank(), t.size() );
+			acc += warmSectors( ptr( w, w->contacts ), w->contactIds.next * (int)sizeof( Contact ), (int)sizeof( Contact ), t.rank(), t.size() );
+			acc += warmSectors( ptr( w, w->bodies ), w->bodyIds.next * (int)sizeof( Body ), (int)sizeof( Body ), t.rank(), t.size() );
+			acc += warmSectors( reinterpret_cast<const char*>( ptr( w, w->shapes ) ) + offsetof( Shape, type ),
+								w->shapeIds.next * (int)sizeof( Shape ), (int)sizeof( Shape ), t.rank(), t.size() );
+			if ( acc == 0x7fffffff ) // (never: keeps the loads alive)
+				storeVolatile( &w->step.orderedPairCount, 0 );
+		}
 		const int32_t* moves = ptr( w, w->moveArray );
 		for ( int i = t.rank(); i < moveCount; i += t.size() )
 		{
@@ -664,7 +690,9 @@ F2D_HDF inline void contactStateGraphHalf( World* w, int contactId, int kind )
 // Ordered contact-state pass, ascending contact id (world.c:587-686). The flagged ids are compacted by the whole team
 // (popcount per 64-bit word + prefix sum) together with their class; then the order-defining structural edits are
 // applied one contact after the other - by two threads, one per half (see above), when the team has them.
-template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
+constexpr int kStateKindShift = 28; // list entry = contact id | class << 28
+// first half, the whole team: the compacted list (World::stateList); returns its length (0 also when a capacity ran out)
+template <class Team> F2D_HDF inline int contactStateCollect( World* w, Team& t )
 {
 	const uint64_t* bits = ptr( w, w->contactBits );
 	int wordCount = ( w->contactIds.next + 63 ) >> 6;
@@ -676,7 +704,7 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 	{
 		if ( t.rank() == 0 )
 			setError( w, kErrCapacity, __LINE__ );
-		return;
+		return 0;
 	}
 	for ( int k = t.rank(); k < wordCount; k += t.size() )
 	{
@@ -694,14 +722,14 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 	t.sync();
 	int total = t.exclusiveScan( offsets, wordCount );
 	if ( total == 0 )
-		return;
+		return 0;
 	if ( total > w->stateList.cap )
 	{
 		if ( t.rank() == 0 )
 			setError( w, kErrCapacity, __LINE__ );
-		return;
+		return 0;
 	}
-	constexpr int kKindShift = 28; // list entry = contact id | class << 28
+	constexpr int kKindShift = kStateKindShift;
 	{
 		const ContactSim* sims = ptr( w, w->contactSims );
 		const Contact* contacts = ptr( w, w->contacts );
@@ -737,6 +765,14 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 		}
 	}
 	t.sync();
+	return total;
+}
+
+// second half: the structural edits, in list order, on one or two threads of the team (the others return at once)
+template <class Team> F2D_HDF inline void contactStateApply( World* w, Team& t, int total )
+{
+	constexpr int kKindShift = kStateKindShift;
+	const int32_t* list = ptr( w, w->stateList );
 	const bool twoThreads = t.size() >= 64 && w->step.stateNeedsSerial == 0 && w->contactIds.next < ( 1 << kKindShift );
 	if constexpr ( Team::kHasSoloBlock )
 	{
@@ -790,6 +826,13 @@ template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
 		for ( int i = 0; i < total; ++i )
 			contactStateChange( w, list[i] & ( ( 1 << kKindShift ) - 1 ) );
 	}
+}
+
+template <class Team> F2D_HDF inline void contactStatePass( World* w, Team& t )
+{
+	const int total = contactStateCollect( w, t );
+	if ( total > 0 )
+		contactStateApply( w, t, total );
 }
 
 // `part`: kCollideAll, or one half of a callback-mediated step: kCollideNarrow stops after the narrowphase (the host
@@ -852,7 +895,11 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 		for ( int i = rank; i < total; i += size )
 			collideContact( w, contactAt( i ), i );
 	};
-	if ( part != kCollideNarrowOnly )
+	// A large block with an SM to itself rebuilds the trees later, beside the serial contact-state pass (below).
+	bool treeBeside = false;
+	if constexpr ( Team::kCanSplitTree )
+		treeBeside = part == kCollideAll && t.canSplitTree();
+	if ( part != kCollideNarrowOnly && treeBeside == false )
 	{
 		treeRebuildTeam( w, t, w->trees[kDynamicBody] );
 		treeRebuildTeam( w, t, w->trees[kKinematicBody] );
@@ -866,6 +913,33 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 	F2D_MARK( w, t, pfNarrow );
 	if ( part == kCollideNarrow || part == kCollideNarrowOnly )
 		return;
+	if constexpr ( Team::kCanSplitTree )
+	{
+		if ( treeBeside )
+		{
+			// The ordered state pass keeps two threads busy and touches contacts, islands and the constraint graph; the
+			// rebuild touches the trees and its own work arrays, and nothing reads the trees again before finalize
+			// enlarges proxies. The reference runs the rebuild as a task beside the whole of b2Collide (world.c:499,
+			// joined at solver.c:1826-1831); here it runs beside the one part of it that cannot use the team.
+			const int changed = contactStateCollect( w, t );
+			if ( t.inFront() )
+			{
+				if ( changed > 0 )
+					contactStateApply( w, t, changed );
+			}
+			else
+			{
+				auto rear = t.rear();
+				treeRebuildTeam( w, rear, w->trees[kDynamicBody] );
+				treeRebuildTeam( w, rear, w->trees[kKinematicBody] );
+				if ( rear.rank() == 0 && w->profEnabled )
+					w->prof[pfTreeBeside] += profClock() - w->profLast;
+			}
+			t.sync();
+			F2D_MARK( w, t, pfStatePass );
+			return;
+		}
+	}
 	contactStatePass( w, t );
 	t.sync();
 	F2D_MARK( w, t, pfStatePass );

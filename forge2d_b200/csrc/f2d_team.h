@@ -211,6 +211,7 @@ struct SerialTeam
 	F2D_HD int arenaSize() const { return 0; }
 	static constexpr bool kHasSoloBlock = false;
 	static constexpr bool kCanFork = false;
+	static constexpr bool kCanSplitTree = false;
 	F2D_HD int rank() const { return 0; }
 	F2D_HD int size() const { return 1; }
 	F2D_HD void sync() const {}

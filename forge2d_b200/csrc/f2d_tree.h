@@ -620,39 +620,69 @@ F2D_HD int treeHeight( const World* w, const Tree& t )
 // `visit(proxyId, userData)` returns false to stop.
 template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box box, uint64_t maskBits, F&& visit )
 {
-	if ( t.nodeCount == 0 )
+	if ( t.nodeCount == 0 || t.root == kNull )
 		return;
 	const TreeNode* nodes = ptr( w, t.nodes );
+	// The reference pushes both children of an overlapping node and tests a node when it is popped: one dependent load
+	// per visited node, and about half the visited nodes fail the test. Here the two children of the current node are
+	// loaded together and tested at once; only nodes that passed are descended into or parked on the stack. Leaves are
+	// reported in the same order (child2's subtree before child1's: the reference pops child2 first).
+	struct Fields
+	{
+		int32_t child1, child2; // leaf: the low half of userData is the shape id
+		uint32_t flags;
+	};
+	auto fieldsOf = []( const TreeNode& n ) {
+		const Q4 q = load16( &n.child1 ); // child1, child2, parent, height | flags << 16
+		return Fields{ (int32_t)floatBits( q.x ), (int32_t)floatBits( q.y ), floatBits( q.w ) >> 16 };
+	};
+	auto passes = [&]( const TreeNode& n ) {
+		const Q4 b = load16( &n.box );
+		return boxOverlaps( Box{ { b.x, b.y }, { b.z, b.w } }, box ) && ( n.category & maskBits ) != 0;
+	};
 	int32_t stack[kQueryStack];
 	int sp = 0;
-	stack[sp++] = t.root;
-	while ( sp > 0 )
+	int id = t.root;
+	if ( passes( nodes[id] ) == false )
+		return;
+	Fields cur = fieldsOf( nodes[id] );
+	while ( true )
 	{
-		int id = stack[--sp];
-		if ( id == kNull )
-			continue;
-		const TreeNode& n = nodes[id];
-		if ( boxOverlaps( n.box, box ) && ( n.category & maskBits ) != 0 )
+		if ( cur.flags & kNodeLeaf )
 		{
-			if ( n.flags & kNodeLeaf )
+			if ( visit( id, (uint64_t)(uint32_t)cur.child1 | ( (uint64_t)(uint32_t)cur.child2 << 32 ) ) == false )
+				return;
+		}
+		else
+		{
+			const TreeNode& first = nodes[cur.child2];
+			const TreeNode& second = nodes[cur.child1];
+			const bool firstPasses = passes( first ), secondPasses = passes( second );
+			const Fields firstFields = fieldsOf( first ), secondFields = fieldsOf( second );
+			if ( firstPasses )
 			{
-				if ( visit( id, n.userData ) == false )
-					return;
+				if ( secondPasses )
+				{
+					if ( sp < kQueryStack )
+						stack[sp++] = cur.child1;
+					else
+						setError( w, kErrTreeStack, __LINE__ );
+				}
+				id = cur.child2;
+				cur = firstFields;
+				continue;
 			}
-			else if ( sp < kQueryStack - 1 )
+			if ( secondPasses )
 			{
-				stack[sp++] = n.child1;
-				stack[sp++] = n.child2;
-				// child2 is popped next; child1 waits for that whole subtree: request it now (48-byte nodes can straddle a line)
-				const char* later = reinterpret_cast<const char*>( nodes + n.child1 );
-				prefetchLine( later );
-				prefetchLine( later + sizeof( TreeNode ) - 1 );
-			}
-			else
-			{
-				setError( w, kErrTreeStack, __LINE__ );
+				id = cur.child1;
+				cur = secondFields;
+				continue;
 			}
 		}
+		if ( sp == 0 )
+			return;
+		id = stack[--sp];
+		cur = fieldsOf( nodes[id] );
 	}
 }
 

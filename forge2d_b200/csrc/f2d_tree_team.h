@@ -32,7 +32,7 @@ struct TreeScratch
 	int32_t* segParent[2]; // [n] by segment start: (parent node << 1) | side, kNull for the root segment
 	int32_t* segSplit;	   // [n] by segment start
 	int32_t* scanLess;	   // [n+1] prefix sums of the "centre < pivot" flags
-	int32_t* lessFlag;	   // [n]
+	int32_t* lessFlag;	   // [n] (unused: the flag is the difference of neighbouring prefix sums)
 	int32_t* badLPos;	   // [n] positions of the misplaced items, left part ascending ...
 	int32_t* badRPos;	   // [n] ... right part descending, stored from the segment start
 	int32_t* freed;		   // [n] dissolved node recycled for boundary m at freed[m-1]
@@ -361,8 +361,31 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		return;
 	}
 	TreeScratch s = treeScratch( w );
+	// A team with a shared-memory work area (one block that has an SM to itself) keeps the work arrays there, as far as
+	// the area reaches: every pass below reads what the pass before it wrote, and from global memory those are L2 round
+	// trips (stores do not fill L1, atomics bypass it) - about a microsecond per barrier interval, ~100 intervals.
+	// (only the level-synchronous build of a large team: the work-queue build keeps under[] alive to the end)
+	int32_t* const arena = t.size() > kTreeQueueBuildMaxTeam ? t.arenaPtr() : nullptr;
+	const int arenaInts = arena != nullptr ? t.arenaSize() : 0;
+	const bool inArena = arena != nullptr && nodeSlots + 8 <= arenaInts;
+	if ( inArena )
+	{
+		s.ctrl = arena;
+		s.under = arena + 8;
+	}
 	int32_t* leafIndices = ptr( w, tree.leafIndices );
 	V2* leafCenters = ptr( w, tree.leafCenters );
+	// profile marks inside the rebuild (the leader's clock; call after a sync of the team)
+	const bool timed = t.rank() == 0 && w->profEnabled;
+	uint64_t clock = timed ? profClock() : 0;
+	auto mark = [&]( int slot ) {
+		if ( timed )
+		{
+			uint64_t now = profClock();
+			w->prof[slot] += now - clock;
+			clock = now;
+		}
+	};
 
 	// ---- collect: items under each dissolved node, bottom-up. A dissolved node has two children, each an item (counts 1)
 	// or a dissolved node (counts what it gathered): the first child to report parks its count in under[], the second
@@ -388,14 +411,60 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		}
 	}
 	t.sync();
+	mark( pfTreeCollect );
 	const int itemCount = s.under[tree.root];
+	int32_t* doubling = reinterpret_cast<int32_t*>( s.lo[0][0] ); // 4 node-sized arrays of the pass below
+	int doublingStride = 2 * ( w->shapes.cap + 8 );
+	if ( inArena )
+	{
+		// arrays by item position, in order of how often the level loop goes through them. under[] is dead once the
+		// positions are known; segOf and scanLess, first written after that, take its place.
+		const int n = itemCount + 8;
+		int arenaUsed = 8;
+		if ( arenaUsed + 2 * n + 1 <= arenaInts )
+		{
+			s.segOf = arena + arenaUsed;
+			s.scanLess = arena + arenaUsed + n;
+		}
+		arenaUsed += maxi( nodeSlots, 2 * n + 1 );
+		auto take = [&]( int32_t*& array ) {
+			if ( arenaUsed + n <= arenaInts )
+			{
+				array = arena + arenaUsed;
+				arenaUsed += n;
+			}
+		};
+		if ( arenaUsed + 8 * n <= arenaInts )
+		{
+			// the centre bounds stay one block (the pointer-doubling pass borrows it)
+			for ( int p = 0; p < 2; ++p )
+				for ( int a = 0; a < 2; ++a )
+				{
+					s.lo[p][a] = reinterpret_cast<float*>( arena + arenaUsed );
+					s.hi[p][a] = reinterpret_cast<float*>( arena + arenaUsed + n );
+					arenaUsed += 2 * n;
+				}
+			if ( 4 * nodeSlots <= 8 * n )
+			{
+				doubling = reinterpret_cast<int32_t*>( s.lo[0][0] );
+				doublingStride = nodeSlots;
+			}
+		}
+		take( s.segEnd[0] );
+		take( s.segEnd[1] );
+		take( s.segSplit );
+		take( s.badLPos );
+		take( s.badRPos );
+		take( s.segParent[0] );
+		take( s.segParent[1] );
+	}
 	// DFS position of every item and the boundary each dissolved node used to stand for: the number of items that
 	// precede a node is the sum, over the ancestors it hangs under by child2, of the items under their child1. That is
 	// a suffix sum along the path to the root, computed for all nodes at once by pointer doubling (log2(height) rounds
 	// of "add what my pointer has gathered, then point where it points") instead of one walk to the root per node.
 	{
-		const int n2 = 2 * ( w->shapes.cap + 8 ); // node-sized arrays carved from the (not yet used) centre-bound arrays
-		int32_t* base = reinterpret_cast<int32_t*>( s.lo[0][0] );
+		const int n2 = doublingStride; // node-sized arrays carved from the (not yet used) centre-bound arrays
+		int32_t* base = doubling;
 		int32_t* acc[2] = { base, base + n2 };
 		int32_t* anc[2] = { base + 2 * n2, base + 3 * n2 };
 		const int height = nodes[tree.root].height; // of the old tree: bounds the depth of every node
@@ -463,6 +532,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		}
 	}
 	t.sync();
+	mark( pfTreePositions );
 
 	// Two builds of the same tree. Small teams (a few warps per world: batches) are bound by instructions per warp and
 	// use the work-queue build; large teams (one 1024-thread block or a cooperative grid per world) have the threads to
@@ -579,9 +649,18 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 	{
 		const int cur = level & 1, nxt = cur ^ 1;
 		const int32_t* segEnd = s.segEnd[cur];
-		// pass A: side of the pivot (segments of <= 2 items split in the middle without looking at the centres)
+		// pass A: side of the pivot (segments of <= 2 items split in the middle without looking at the centres). The
+		// bounds and loop flags of the next level, accumulated in pass C, are cleared on the way: their last readers
+		// were pass A and the loop test of the level before this one.
+		if ( t.rank() == 0 )
+		{
+			s.ctrl[nxt] = 0;
+			s.ctrl[2 + nxt] = 0;
+		}
 		for ( int i = t.rank(); i < itemCount; i += t.size() )
 		{
+			s.lo[nxt][0][i] = s.lo[nxt][1][i] = FLT_MAX;
+			s.hi[nxt][0][i] = s.hi[nxt][1][i] = -FLT_MAX;
 			int a = s.segOf[i];
 			int less = 0;
 			if ( a != kNull && segEnd[a] - a > 2 )
@@ -593,24 +672,10 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 				less = ( useX ? c.x : c.y ) < pivot ? 1 : 0;
 			}
 			s.scanLess[i] = less;
-			s.lessFlag[i] = less;
 		}
 		t.sync();
-		int totalLess = t.exclusiveScan( s.scanLess, itemCount );
-		// bounds of the next level are accumulated in pass C: clear them (pass A was the last reader of this parity's
-		// predecessor) and the loop flag
-		for ( int i = t.rank(); i < itemCount; i += t.size() )
-		{
-			s.lo[nxt][0][i] = s.lo[nxt][1][i] = FLT_MAX;
-			s.hi[nxt][0][i] = s.hi[nxt][1][i] = -FLT_MAX;
-		}
-		if ( t.rank() == 0 )
-		{
-			s.scanLess[itemCount] = totalLess;
-			s.ctrl[nxt] = 0;
-			s.ctrl[2 + nxt] = 0;
-		}
-		t.sync();
+		const int totalLess = t.exclusiveScan( s.scanLess, itemCount ); // (ends with a barrier)
+		auto lessBefore = [&]( int k ) { return k < itemCount ? s.scanLess[k] : totalLess; };
 		// pass B: split point per segment; the k-th misplaced item of the left part (ascending) will swap with the k-th
 		// misplaced item of the right part (descending) - both ranks follow from the one prefix sum
 		for ( int i = t.rank(); i < itemCount; i += t.size() )
@@ -623,13 +688,13 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			int split = a + count / 2;
 			if ( count > 2 )
 			{
-				int L = s.scanLess[e] - s.scanLess[a];
+				int L = lessBefore( e ) - lessBefore( a );
 				if ( L > 0 && L < count )
 				{
 					split = a + L;
-					int lessRank = s.scanLess[i] - s.scanLess[a];
-					int lessInLeft = s.scanLess[split] - s.scanLess[a];
-					int less = s.lessFlag[i];
+					int lessRank = lessBefore( i ) - lessBefore( a );
+					int lessInLeft = lessBefore( split ) - lessBefore( a );
+					int less = lessBefore( i + 1 ) - lessBefore( i ); // the flag itself
 					if ( i < split && less == 0 )
 						s.badLPos[a + ( i - a ) - lessRank] = i;
 					else if ( i >= split && less != 0 )
@@ -654,11 +719,11 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			bool isBad = false;
 			if ( count > 2 )
 			{
-				int L = s.scanLess[e] - s.scanLess[a];
+				int L = lessBefore( e ) - lessBefore( a );
 				if ( L > 0 && L < count )
 				{
-					bad = L - ( s.scanLess[m] - s.scanLess[a] );
-					int less = s.lessFlag[i];
+					bad = L - ( lessBefore( m ) - lessBefore( a ) );
+					int less = lessBefore( i + 1 ) - lessBefore( i ); // the flag itself
 					isBad = ( i < m && less == 0 ) || ( i >= m && less != 0 );
 				}
 			}
@@ -754,6 +819,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		t.sync();
 		level += 1;
 	}
+	mark( pfTreeLevels );
 	// short segments that are still open: one thread each builds the rest of its subtree serially
 	if ( s.ctrl[level & 1] != 0 )
 	{
@@ -778,6 +844,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			nodes[key >> 1].child1 = item;
 	}
 	t.sync();
+	mark( pfTreeTail );
 
 	// ---- refit bottom-up, one level at a time
 	for ( int d = level - 1; d >= 0; --d )
@@ -795,6 +862,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 		}
 		t.sync();
 	}
+	mark( pfTreeRefit );
 }
 
 } // namespace f2d

@@ -513,7 +513,7 @@ enum : uint16_t
 	kNodeLeaf = 0x4,
 	kNodeMoved = 0x8 // replaces the reference's moveSet hash (broad_phase.h:74-82): set while the proxy is in moveArray
 };
-struct TreeNode
+struct alignas( 16 ) TreeNode
 {
 	Box box;
 	union
@@ -658,7 +658,14 @@ enum ProfSlot : int
 	pfEnd,
 	pfSplitJoin,  // waiting for the island-split walk after the solver stages (accumulated separately from the phases above)
 	pfSplitApply,
-	kProfSlots = 24
+	pfTreeBeside, // the tree rebuild when it runs beside the contact-state pass (its time is inside pfStatePass)
+	// inside the tree rebuild (charged by the leader of the team that rebuilds; their sum is pfTreeRebuild or pfTreeBeside)
+	pfTreeCollect,
+	pfTreePositions,
+	pfTreeLevels,
+	pfTreeTail,
+	pfTreeRefit,
+	kProfSlots = 32
 };
 
 enum : uint8_t // World::hostCallbacks

@@ -14,7 +14,8 @@ assert lib.f2dHasDevice()
 what = sys.argv[1:] or ["single", "batch"]
 PROF_NAMES = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
               "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
-              "bullets", "sleep", "end", "splitJoin", "splitApply"]
+              "bullets", "sleep", "end", "splitJoin", "splitApply", "treeBeside", "tree.collect", "tree.positions",
+              "tree.levels", "tree.tail", "tree.refit"]
 
 
 def single(name, kw, mode, warm, timed):
@@ -68,7 +69,8 @@ if "batch" in what:
 
 _PROF_NAMES_MOVED = ["begin", "pairQuery", "pairCreate", "treeRebuild", "narrow", "statePass", "solveSetup", "prepare", "integrateVel",
               "warmStart", "solve", "integratePos", "relax", "restitution", "store", "finalizeBodies", "hitEvents", "enlarge",
-              "bullets", "sleep", "end", "splitJoin", "splitApply"]
+              "bullets", "sleep", "end", "splitJoin", "splitApply", "treeBeside", "tree.collect", "tree.positions",
+              "tree.levels", "tree.tail", "tree.refit"]
 
 
 def profile(name, kw, mode, warm, timed):
@@ -81,8 +83,8 @@ def profile(name, kw, mode, warm, timed):
     for _ in range(timed):
         s.step()
     wall = (time.perf_counter() - t0) / timed * 1e3
-    out = (C.c_ulonglong * 24)()
-    lib.f2dWorld_ReadProfile(s.world, out, 24)
+    out = (C.c_ulonglong * 32)()
+    lib.f2dWorld_ReadProfile(s.world, out, 32)
     total = sum(out[:23]) / timed / 1e3
     print("%s %s mode %d: wall %.3f ms/frame, in-kernel %.1f us: " % (name, kw, mode, wall, total) +
           " ".join("%s=%.1f" % (n, out[i] / timed / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
@@ -124,8 +126,8 @@ if "batchprofile" in what:
         ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
         scratch = scenes.bench2d(lib, rows=1)
         lib.f2dBatch_DownloadWorld(b, count // 2, scratch.world)
-        out = (C.c_ulonglong * 24)()
-        lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+        out = (C.c_ulonglong * 32)()
+        lib.f2dWorld_ReadProfile(scratch.world, out, 32)
         total = sum(out[:23]) / steps / 1e3
         print("batch %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
             threads, bps, count, ms, count / ms * 1e3, count // 2, total) +
@@ -152,8 +154,8 @@ if "gangprofile" in what:
         before = {}
         for idx in (100, 4000, 8000):
             lib.f2dBatch_DownloadWorld(b, idx, scratch.world)
-            out = (C.c_ulonglong * 24)()
-            lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+            out = (C.c_ulonglong * 32)()
+            lib.f2dWorld_ReadProfile(scratch.world, out, 32)
             before[idx] = list(out)
         steps = 8
         lib.f2dBatch_EventRecord(b, 0)
@@ -163,8 +165,8 @@ if "gangprofile" in what:
         ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
         for idx in (100, 4000, 8000):
             lib.f2dBatch_DownloadWorld(b, idx, scratch.world)
-            out = (C.c_ulonglong * 24)()
-            lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+            out = (C.c_ulonglong * 32)()
+            lib.f2dWorld_ReadProfile(scratch.world, out, 32)
             d = [(out[i] - before[idx][i]) / steps / 1e3 for i in range(23)]
             print("%s, 8192 decorrelated worlds: %.3f ms/step; world %d in-kernel %.1f us: " % (
                 "gang 128x7" if gang else "one world per block 128x8", ms, idx, sum(d)) +
@@ -185,6 +187,11 @@ if "profile" in what:
     profile("many_pyramids", {}, 1, 2, 16)
     profile("joint_grid", {}, 1, 8, 32)
 
+if "b2d" in what:
+    for _ in range(3):
+        profile("bench2d", {}, 0, 256, 64)
+    profile("bench2d", dict(rows=10), 0, 64, 64)
+
 if "occupancy" in what:
     # the same 128x8 kernel with 1, 2, 4, 8 worlds resident per SM: how much of a world's step time is contention
     t = scenes.bench2d(lib)
@@ -202,8 +209,8 @@ if "occupancy" in what:
         ms = lib.f2dBatch_EventElapsedMs(b, 0, 1) / steps
         scratch = scenes.bench2d(lib, rows=1)
         lib.f2dBatch_DownloadWorld(b, count // 2, scratch.world)
-        out = (C.c_ulonglong * 24)()
-        lib.f2dWorld_ReadProfile(scratch.world, out, 24)
+        out = (C.c_ulonglong * 32)()
+        lib.f2dWorld_ReadProfile(scratch.world, out, 32)
         total = sum(out[:23]) / steps / 1e3
         print("occupancy %dx%d, %d worlds: %.3f ms/step (%.0f world-steps/s); world %d in-kernel %.1f us: " % (
             threads, bps, count, ms, count / ms * 1e3, count // 2, total) +

@@ -12,6 +12,7 @@ import sys
 from collections import defaultdict
 
 page, sass, kernel = sys.argv[1:4]
+BUSY = "--busy" in sys.argv  # count only the samples of warps that are not waiting at a barrier
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 
 # ---- address offset -> inline chain [(file, line) innermost first]
@@ -67,8 +68,8 @@ for r in body:
         continue
     off = int(r[0], 16) - base
     chain = chains.get(off, [("?", 0)])
-    vals = [num(r, "Warp Stall Sampling (All Samples)"), num(r, "Instructions Executed"), num(r, "L2 Theoretical Sectors Global"),
-            num(r, "stall_long_sb")]
+    vals = [num(r, "Warp Stall Sampling (All Samples)") - (num(r, "stall_barrier") if BUSY else 0), num(r, "Instructions Executed"),
+            num(r, "L2 Theoretical Sectors Global"), num(r, "stall_long_sb")]
     for k in range(4):
         tot[k] += vals[k]
     key_in = chain[0]
