@@ -57,6 +57,8 @@ struct HostWorld
 	//                    bodies) have changed; uploaded right before the next step instead of the whole image.
 	bool bodyMirrorFresh = false;
 	std::vector<std::pair<uint64_t, uint32_t>> dirty;
+	bool wholeImageSync = false; // the next download / upload moves the whole image, work arrays included (host work in the middle of a step)
+	unsigned layoutSerial = 0; // bumped by every re-layout of the image: the device copy of another layout is replaced whole
 	// b2World_GetProfile: the in-kernel phase marks as they stood at the previous call
 	uint64_t profSeen[kProfSlots] = {};
 	uint64_t profStepSeen = 0;
@@ -252,6 +254,7 @@ static void reserve( HostWorld& hw, int needBodies, int needShapes, int needCont
 	if ( grow )
 	{
 		hw.img = imageRelayout( w, c, backendHostAlloc, backendHostFree );
+		hw.layoutSerial += 1;
 		hw.caps = c;
 	}
 }
@@ -765,13 +768,15 @@ static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
 		}
 	};
 	auto onHostImage = [&]( auto&& work ) {
-		backendDownload( hw ); // full image, synchronises with the phases queued
+		hw.wholeImageSync = true; // the work arrays of the step in flight too (parked bodies, enlarged-proxy bits ...), both ways
+		backendDownload( hw );	  // synchronises with the phases queued
 		g_hostContinuous.filter = hw.customFilterFcn != nullptr ? Hooks::filter : nullptr;
 		g_hostContinuous.preSolve = hw.preSolveFcn != nullptr ? Hooks::preSolve : nullptr;
 		g_hostContinuous.context = &hw;
 		work();
 		g_hostContinuous = HostContinuousHooks{};
 		hw.state = kHostNewer;
+		hw.wholeImageSync = true;
 		backendPhaseBegin( hw ); // uploads
 	};
 	backendPhase( hw, dt, subSteps, kPhaseFinalizeBodies );

@@ -95,6 +95,7 @@ struct DeviceMirror
 	size_t devBytes = 0;
 	cudaStream_t stream = nullptr;
 	int32_t* blockTotals = nullptr;
+	unsigned layoutSerial = 0; // HostWorld::layoutSerial of the image `dev` holds
 	cudaEvent_t ev[6] = {};
 	bool timing = false;
 	float times[5] = { 0, 0, 0, 0, 0 };
@@ -137,25 +138,74 @@ static bool launchWorld( HostWorld& hw, DeviceMirror* m, float dt, int sub, int 
 	return cudaOk( launchSingleGrid( m->dev, m->blockTotals, blocks, dt, sub, phase, hostHeader, m->stream ), "stepWorldGrid cooperative launch" );
 }
 
+// The byte ranges of an image that hold live state, by its header: the header itself and the first `count` elements of
+// every persistent array - what a re-layout preserves (imageRelayout). The step's work arrays (constraint fields, tree
+// and island-split scratch, pair lists ...) and the unused tails of the entity arrays are most of an image and never
+// need to cross PCIe. Ranges closer than a copy call is worth are merged.
+static void liveRanges( const World& header, const Caps& caps, std::vector<ByteRange>& out )
+{
+	World copy = header;
+	copy.sleepPool.count = copy.sleepUsed; // bump-allocated: its Arr::count is not maintained (see imageRelayout)
+	std::vector<ArraySlot> slots;
+	collectArrays( copy, caps, slots );
+	out.clear();
+	out.push_back( ByteRange{ 0, sizeof( World ) } );
+	const uint64_t kMergeGap = 16 * 1024;
+	for ( const ArraySlot& slot : slots )
+	{
+		if ( slot.persistent == false )
+			continue;
+		const int n = *slot.count < *slot.cap ? *slot.count : *slot.cap;
+		if ( n <= 0 )
+			continue;
+		const uint64_t off = *slot.off, bytes = (uint64_t)n * (uint64_t)slot.elemSize;
+		ByteRange& last = out.back();
+		if ( off <= last.off + last.bytes + kMergeGap )
+			last.bytes = off + bytes - last.off;
+		else
+			out.push_back( ByteRange{ off, bytes } );
+	}
+}
+
 // Device copy allocated and current (uploads the host image when it is newer or the image was re-laid out)
 static bool deviceImageCurrent( HostWorld& hw, DeviceMirror* m )
 {
 	World* img = hw.img;
-	if ( hw.state == kHostNewer || m->dev == nullptr || m->devBytes != img->imageBytes )
+	if ( hw.state == kHostNewer || m->dev == nullptr || m->devBytes != img->imageBytes || m->layoutSerial != hw.layoutSerial )
 	{
-		if ( m->devBytes != img->imageBytes )
+		const bool newLayout = m->devBytes != img->imageBytes || m->layoutSerial != hw.layoutSerial;
+		if ( newLayout || hw.wholeImageSync )
 		{
-			if ( m->dev )
-				cudaFree( m->dev );
-			m->dev = nullptr;
-			if ( cudaOk( cudaMalloc( &m->dev, img->imageBytes ), "cudaMalloc(world image)" ) == false )
+			// a new allocation takes the whole image once (zeroes in everything that is not live state)
+			if ( newLayout )
+			{
+				if ( m->dev )
+					cudaFree( m->dev );
+				m->dev = nullptr;
+				if ( cudaOk( cudaMalloc( &m->dev, img->imageBytes ), "cudaMalloc(world image)" ) == false )
+					return false;
+				m->devBytes = img->imageBytes;
+				m->layoutSerial = hw.layoutSerial;
+			}
+			hw.wholeImageSync = false;
+			if ( cudaOk( cudaMemcpyAsync( m->dev, img, img->imageBytes, cudaMemcpyHostToDevice, m->stream ), "upload world image" ) == false )
 				return false;
-			m->devBytes = img->imageBytes;
+			g_bytesH2D += img->imageBytes;
 		}
-		if ( cudaOk( cudaMemcpyAsync( m->dev, img, img->imageBytes, cudaMemcpyHostToDevice, m->stream ), "upload world image" ) == false )
-			return false;
-		g_bytesH2D += img->imageBytes;
-		hw.dirty.clear(); // the whole image just went up
+		else
+		{
+			std::vector<ByteRange> ranges;
+			liveRanges( *img, hw.caps, ranges );
+			for ( const ByteRange& r : ranges )
+			{
+				cudaMemcpyAsync( reinterpret_cast<char*>( m->dev ) + r.off, reinterpret_cast<const char*>( img ) + r.off, r.bytes,
+								 cudaMemcpyHostToDevice, m->stream );
+				g_bytesH2D += r.bytes;
+			}
+			if ( cudaOk( cudaGetLastError(), "upload world image" ) == false )
+				return false;
+		}
+		hw.dirty.clear(); // all live state just went up
 	}
 	else if ( hw.state == kDeviceNewer )
 	{
@@ -249,9 +299,26 @@ static void backendDownload( HostWorld& hw )
 	DeviceMirror* m = mirror( hw );
 	if ( m->dev == nullptr )
 		return;
+	if ( hw.wholeImageSync )
+	{
+		hw.wholeImageSync = false;
+		cudaStreamSynchronize( m->stream );
+		cudaOk( cudaMemcpy( hw.img, m->dev, hw.img->imageBytes, cudaMemcpyDeviceToHost ), "download world image" );
+		g_bytesD2H += hw.img->imageBytes;
+		return;
+	}
+	// the device's header says what is live (the host copy of the header may be one asynchronous step behind)
+	cudaMemcpyAsync( hw.img, m->dev, sizeof( World ), cudaMemcpyDeviceToHost, m->stream );
 	cudaStreamSynchronize( m->stream );
-	cudaOk( cudaMemcpy( hw.img, m->dev, hw.img->imageBytes, cudaMemcpyDeviceToHost ), "download world image" );
-	g_bytesD2H += hw.img->imageBytes;
+	std::vector<ByteRange> ranges;
+	liveRanges( *hw.img, hw.caps, ranges );
+	for ( const ByteRange& r : ranges )
+	{
+		cudaMemcpyAsync( reinterpret_cast<char*>( hw.img ) + r.off, reinterpret_cast<const char*>( m->dev ) + r.off, r.bytes,
+						 cudaMemcpyDeviceToHost, m->stream );
+		g_bytesD2H += r.bytes;
+	}
+	cudaOk( cudaStreamSynchronize( m->stream ), "download world image" );
 }
 
 static void backendDownloadRange( HostWorld& hw, uint64_t off, uint64_t bytes )
@@ -580,6 +647,7 @@ f2dBatch* f2dBatch_CreateFromWorlds( const b2WorldId* worlds, int count )
 			 c.sensorOverlap != common.sensorOverlap )
 		{
 			hw->img = imageRelayout( hw->img, common, backendHostAlloc, backendHostFree );
+			hw->layoutSerial += 1;
 			hw->caps = common;
 			hw->state = kHostNewer;
 		}
