@@ -64,6 +64,33 @@ template <class Slice> __device__ __forceinline__ int sliceExclusiveScan( const 
 	return carry;
 }
 
+// The first two warps of a thread block as a team of their own (hardware barrier 3): the serial parts of the step and the
+// little parallel work between them, while the rear rebuilds the trees (stepCollide).
+struct CtaFront
+{
+	static constexpr bool kHasSoloBlock = false;
+	int32_t* scratch;
+	typedef WarpLanes Lanes;
+	__device__ int rank() const { return (int)threadIdx.x; }
+	__device__ int size() const { return 64; }
+	__device__ void sync() const { asm volatile( "bar.sync 3, 64;" ::: "memory" ); }
+	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
+};
+
+// Block 0 of a cooperative grid as a team of its own: the same role as CtaFront.
+struct GridFront
+{
+	static constexpr bool kHasSoloBlock = true;
+	int32_t* scratch;
+	typedef WarpLanes Lanes;
+	__device__ bool inSoloBlock() const { return true; }
+	__device__ int soloSize() const { return (int)blockDim.x; }
+	__device__ int rank() const { return (int)threadIdx.x; }
+	__device__ int size() const { return (int)blockDim.x; }
+	__device__ void sync() const { __syncthreads(); }
+	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
+};
+
 // All warps of a thread block but the first two, as a team of their own (hardware barrier 2): see CtaTeamT::rear.
 struct CtaRear
 {
@@ -178,6 +205,7 @@ template <bool kWholeBlock, bool kLarge = false> struct CtaTeamT
 	__device__ bool canSplitTree() const { return true; }
 	__device__ bool inFront() const { return threadIdx.x < 64; }
 	__device__ CtaRear rear() const { return CtaRear{ smem + 64, arena, arenaInts }; }
+	__device__ CtaFront front() const { return CtaFront{ smem }; }
 };
 typedef CtaTeamT<true> CtaTeam;	 // one world per block (and the solo block of a grid)
 typedef CtaTeamT<true, true> LargeCtaTeam; // one world per block of >= 512 threads
@@ -291,6 +319,7 @@ struct GridTeam
 	__device__ bool canSplitTree() const { return gridDim.x >= 2; }
 	__device__ bool inFront() const { return blockIdx.x == 0; }
 	__device__ GridRear rear() { return GridRear{ barrier + 2, &rearGen, smem, blockTotals }; }
+	__device__ GridFront front() const { return GridFront{ smem }; }
 	__device__ bool canFork() const { return gridDim.x >= 2; }
 	__device__ bool inSide() const { return blockIdx.x == gridDim.x - 1; }
 	__device__ bool isSideLeader() const { return blockIdx.x == gridDim.x - 1 && threadIdx.x == 0; }

@@ -211,6 +211,53 @@ F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 	}
 }
 
+// The serial half of pair finding: contacts for the candidate pairs, in the reference's creation order (World::pairOrder
+// over World::movePairs, built by stepPairs). Rank 0 creates; in a grid the other threads of its block warm its L1.
+template <class Team> F2D_HDF inline void createOrderedPairs( World* w, Team& t, int total )
+{
+	const MovePair* pairs = ptr( w, w->movePairs );
+	const int32_t* ordered = ptr( w, w->pairOrder );
+	if constexpr ( Team::kHasSoloBlock )
+	{
+		// a grid: the other threads of the serial thread's block read what contact creation is about to chase, so
+		// that it runs on L1 hits (see contactStatePass)
+		if ( total > 0 && t.inSoloBlock() && t.rank() >= 32 )
+		{
+			const Shape* shapes = ptr( w, w->shapes );
+			const Body* bodies = ptr( w, w->bodies );
+			const Contact* contacts = ptr( w, w->contacts );
+			int acc = 0;
+			for ( int k = t.rank() - 32; k < total && k < 2048; k += t.soloSize() - 32 )
+			{
+				const MovePair& pair = pairs[ordered[k]];
+				if ( pair.shapeA == kNull )
+					continue;
+				const Shape& a = shapes[pair.shapeA];
+				const Shape& b = shapes[pair.shapeB];
+				acc += a.bodyId + b.bodyId + a.type + b.type + (int)floatBits( a.restitution ) + (int)floatBits( b.restitution );
+				const Body& ba = bodies[a.bodyId];
+				const Body& bb = bodies[b.bodyId];
+				acc += ba.setIndex + bb.setIndex;
+				if ( ba.headContactKey != kNull )
+					acc += contacts[ba.headContactKey >> 1].edges[ba.headContactKey & 1].prevKey;
+				if ( bb.headContactKey != kNull )
+					acc += contacts[bb.headContactKey >> 1].edges[bb.headContactKey & 1].prevKey;
+			}
+			if ( acc == 0x7fffffff ) // (never: keeps the loads alive)
+				storeVolatile( &w->step.orderedPairCount, total );
+		}
+	}
+	if ( total > 0 && t.rank() == 0 )
+	{
+		for ( int k = 0; k < total; ++k )
+		{
+			const MovePair& pair = pairs[ordered[k]];
+			if ( pair.shapeA != kNull ) // kNull: rejected by the host's custom filter
+				createContact( w, pair.shapeA, pair.shapeB );
+		}
+	}
+}
+
 // `part`: kPairsAll, or one half of a callback-mediated step: kPairsQuery stops once the candidate pairs stand in
 // creation order (the host then runs the custom filter over them and marks the rejected ones, broad_phase.c:267-278),
 // kPairsCreate resumes from there.
@@ -218,7 +265,8 @@ enum : int
 {
 	kPairsAll = 0,
 	kPairsQuery = 1,
-	kPairsCreate = 2
+	kPairsCreate = 2,
+	kPairsDefer = 3 // everything but the serial creation, which stepCollide runs beside the tree rebuild (createOrderedPairs)
 };
 template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part = kPairsAll )
 {
@@ -271,7 +319,18 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part
 					prefetchL2( leaf + sizeof( TreeNode ) - 1 );
 				}
 			}
+#if defined( __CUDA_ARCH__ ) && defined( F2D_QUERY_CLOCK )
+			{
+				long long c0 = clock64();
+				findPairsForProxy( w, i );
+				long long c1 = clock64();
+				atomicMax( reinterpret_cast<unsigned long long*>( &w->prof[29] ), (unsigned long long)( c1 - c0 ) );
+				atomicAdd( reinterpret_cast<unsigned long long*>( &w->prof[30] ), (unsigned long long)( c1 - c0 ) );
+				atomicAdd( reinterpret_cast<unsigned long long*>( &w->prof[31] ), 1ull );
+			}
+#else
 			findPairsForProxy( w, i );
+#endif
 		}
 	}
 	t.sync();
@@ -331,57 +390,21 @@ template <class Team> F2D_HDF inline void stepPairs( World* w, Team& t, int part
 			t.sync();
 			if ( w->step.retryContacts != 0 )
 				return;
-			if ( part == kPairsQuery )
+			if ( part == kPairsQuery || part == kPairsDefer )
 			{
 				if ( t.rank() == 0 )
 					w->step.orderedPairCount = total;
 				t.sync();
-				return;
+				if ( part == kPairsQuery )
+					return;
 			}
 		}
 		else
 		{
 			total = w->step.orderedPairCount;
 		}
-		if constexpr ( Team::kHasSoloBlock )
-		{
-			// a grid: the other threads of the serial thread's block read what contact creation is about to chase, so
-			// that it runs on L1 hits (see contactStatePass)
-			if ( total > 0 && t.inSoloBlock() && t.rank() >= 32 )
-			{
-				const Shape* shapes = ptr( w, w->shapes );
-				const Body* bodies = ptr( w, w->bodies );
-				const Contact* contacts = ptr( w, w->contacts );
-				int acc = 0;
-				for ( int k = t.rank() - 32; k < total && k < 2048; k += t.soloSize() - 32 )
-				{
-					const MovePair& pair = pairs[ordered[k]];
-					if ( pair.shapeA == kNull )
-						continue;
-					const Shape& a = shapes[pair.shapeA];
-					const Shape& b = shapes[pair.shapeB];
-					acc += a.bodyId + b.bodyId + a.type + b.type + (int)floatBits( a.restitution ) + (int)floatBits( b.restitution );
-					const Body& ba = bodies[a.bodyId];
-					const Body& bb = bodies[b.bodyId];
-					acc += ba.setIndex + bb.setIndex;
-					if ( ba.headContactKey != kNull )
-						acc += contacts[ba.headContactKey >> 1].edges[ba.headContactKey & 1].prevKey;
-					if ( bb.headContactKey != kNull )
-						acc += contacts[bb.headContactKey >> 1].edges[bb.headContactKey & 1].prevKey;
-				}
-				if ( acc == 0x7fffffff ) // (never: keeps the loads alive)
-					storeVolatile( &w->step.orderedPairCount, total );
-			}
-		}
-		if ( total > 0 && t.rank() == 0 )
-		{
-			for ( int k = 0; k < total; ++k )
-			{
-				const MovePair& pair = pairs[ordered[k]];
-				if ( pair.shapeA != kNull ) // kNull: rejected by the host's custom filter
-					createContact( w, pair.shapeA, pair.shapeB );
-			}
-		}
+		if ( part != kPairsDefer )
+			createOrderedPairs( w, t, total );
 	}
 	t.sync();
 	// reset move buffer (broad_phase.c:460-462)
@@ -846,7 +869,7 @@ enum : int
 	kCollideTreeOnly = 3,  // profiling aid (F2D_PROFILE_PHASE_LAUNCHES): the tree rebuild alone
 	kCollideNarrowOnly = 4 // profiling aid: the narrowphase alone
 };
-template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int part = kCollideAll )
+template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int part = kCollideAll, bool deferredPairs = false )
 {
 	if ( part == kCollideFinish )
 	{
@@ -865,7 +888,8 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 		w->step.preSolveCount = 0;
 
 	// work list = colour 0..11 lists then the awake non-touching list (world.c:504-542)
-	int total = w->awakeContacts.count;
+	const int awakeBefore = w->awakeContacts.count; // (read by everybody before the barrier that ends the narrowphase)
+	int total = awakeBefore;
 	for ( int i = 0; i < kColorCount; ++i )
 		total += w->colorContacts[i].count;
 
@@ -895,7 +919,7 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 		for ( int i = rank; i < total; i += size )
 			collideContact( w, contactAt( i ), i );
 	};
-	// A large block with an SM to itself rebuilds the trees later, beside the serial contact-state pass (below).
+	// A large team rebuilds the trees later, beside the serial parts of the step (below).
 	bool treeBeside = false;
 	if constexpr ( Team::kCanSplitTree )
 		treeBeside = part == kCollideAll && t.canSplitTree();
@@ -917,15 +941,33 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 	{
 		if ( treeBeside )
 		{
-			// The ordered state pass keeps two threads busy and touches contacts, islands and the constraint graph; the
-			// rebuild touches the trees and its own work arrays, and nothing reads the trees again before finalize
-			// enlarges proxies. The reference runs the rebuild as a task beside the whole of b2Collide (world.c:499,
-			// joined at solver.c:1826-1831); here it runs beside the one part of it that cannot use the team.
-			const int changed = contactStateCollect( w, t );
+			// Two parts of the step keep one or two threads busy and leave the rest of the team idle: the ordered creation
+			// of this step's new contacts (stepPairs left it to us: `deferredPairs`) and the ordered contact-state pass.
+			// Both touch contacts, bodies' contact lists, islands and the constraint graph; the rebuild touches the trees
+			// and its own work arrays, and nothing reads the trees again before finalize enlarges proxies. So the front of
+			// the team (two warps of a block / block 0 of a grid) runs the serial parts - with the narrowphase of the new
+			// contacts, the last entries of the non-touching list, in between - while the rear rebuilds. The reference
+			// runs the rebuild as a task beside the whole of b2Collide (world.c:499, joined at solver.c:1826-1831).
 			if ( t.inFront() )
 			{
+				auto front = t.front();
+				if ( deferredPairs )
+				{
+					createOrderedPairs( w, front, w->step.orderedPairCount );
+					front.sync();
+					F2D_MARK( w, front, pfPairCreate );
+					const int created = w->awakeContacts.count - awakeBefore;
+					const int32_t* list = ptr( w, w->awakeContacts );
+					for ( int i = front.rank(); i < created; i += front.size() )
+						collideContact( w, list[awakeBefore + i], total + i );
+					front.sync();
+					F2D_MARK( w, front, pfNarrow );
+				}
+				const int changed = contactStateCollect( w, front );
 				if ( changed > 0 )
-					contactStateApply( w, t, changed );
+					contactStateApply( w, front, changed );
+				front.sync();
+				F2D_MARK( w, front, pfStatePass );
 			}
 			else
 			{
@@ -936,7 +978,7 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 					w->prof[pfTreeBeside] += profClock() - w->profLast;
 			}
 			t.sync();
-			F2D_MARK( w, t, pfStatePass );
+			F2D_MARK( w, t, pfTreeRebuild ); // (what the front waited for the rear)
 			return;
 		}
 	}
@@ -3149,10 +3191,14 @@ template <class Team> F2D_HDF inline void stepWorld( World* w, Team& t, float dt
 		return;
 	}
 	stepBegin( w, t, dt, subStepCount );
-	stepPairs( w, t );
+	// a team that rebuilds the trees beside the serial parts of the step creates this step's contacts there too
+	bool deferPairs = false;
+	if constexpr ( Team::kCanSplitTree )
+		deferPairs = t.canSplitTree() && w->hostCallbacks == 0;
+	stepPairs( w, t, deferPairs ? kPairsDefer : kPairsAll );
 	if ( w->step.retryContacts != 0 ) // see stepPairs: the host repeats the step on a larger image
 		return;
-	stepCollide( w, t );
+	stepCollide( w, t, kCollideAll, deferPairs );
 	stepSolve( w, t );
 	stepFinalize( w, t );
 }

@@ -85,6 +85,7 @@ F2D_HD bool treeNodeIsDissolved( const TreeNode& n ) { return n.height > 0 && ( 
 // (dynamic_tree.c:1716-1869) with its in-place Hoare partition (treePartitionMid), recycling the dissolved node
 // freed[m-1] for the split at m, and computing boxes / heights / categories on the way back up.
 constexpr int kTreeSerialFinish = 12; // segments at most this long are finished by one thread each
+constexpr int kTreeSerialFinishArena = 4;
 constexpr int kTreeQueueBuildMaxTeam = 256; // teams up to this size use the work-queue build (treeSplitSegment)
 
 F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
@@ -645,7 +646,9 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 	t.sync();
 	int level = 0;
 	// level-synchronous while some segment is long; the short tail is finished per segment (treeFinishSegment)
-	while ( s.ctrl[level & 1] != 0 && s.ctrl[2 + ( level & 1 )] > kTreeSerialFinish )
+	// (levels are cheap when the work arrays sit in shared memory: the serial tail starts later)
+	const int serialFinish = inArena ? kTreeSerialFinishArena : kTreeSerialFinish;
+	while ( s.ctrl[level & 1] != 0 && s.ctrl[2 + ( level & 1 )] > serialFinish )
 	{
 		const int cur = level & 1, nxt = cur ^ 1;
 		const int32_t* segEnd = s.segEnd[cur];

@@ -86,6 +86,8 @@ def profile(name, kw, mode, warm, timed):
     out = (C.c_ulonglong * 32)()
     lib.f2dWorld_ReadProfile(s.world, out, 32)
     total = sum(out[:23]) / timed / 1e3
+    if out[31]:
+        print("   query clock: max-accumulated %d cycles, mean per query %.0f cycles over %d queries (%.1f per frame)" % (out[29], out[30] / out[31], out[31], out[31] / timed))
     print("%s %s mode %d: wall %.3f ms/frame, in-kernel %.1f us: " % (name, kw, mode, wall, total) +
           " ".join("%s=%.1f" % (n, out[i] / timed / 1e3) for i, n in enumerate(PROF_NAMES) if out[i]), flush=True)
     s.destroy()
