@@ -542,6 +542,7 @@ F2D_FUNCTIONS = {
     "f2dWorld_EnablePhaseTiming": (None, [WorldId, c_bool]),
     "f2dWorld_GetStepInfo": (c_int, [WorldId, C.POINTER(c_int), c_int]),
     "f2dWorld_EnableProfile": (None, [WorldId, c_bool]),
+    "f2dWorld_EnablePairClassBinning": (None, [WorldId, c_bool]),
     "f2dWorld_ReadProfile": (c_int, [WorldId, C.POINTER(C.c_ulonglong), c_int]),
     "f2dWorld_StepAsync": (None, [WorldId, c_float, c_int]),
     "f2dWorld_Synchronize": (None, [WorldId]),

@@ -1436,6 +1436,14 @@ int f2dWorld_GetStepInfo( b2WorldId worldId, int* out, int cap )
 		out[i] = v[i];
 	return 12;
 }
+// Measurement aid: the narrowphase of a world with several shape types with / without its work list binned by pair class
+void f2dWorld_EnablePairClassBinning( b2WorldId worldId, bool flag )
+{
+	HostWorld* hw = worldFromId( worldId );
+	if ( hw == nullptr )
+		return;
+	mutableImage( *hw )->pairClassBinningOff = flag ? 0 : 1;
+}
 // In-kernel profile (nanoseconds per f2d::ProfSlot accumulated by rank 0 since it was enabled / last read)
 void f2dWorld_EnableProfile( b2WorldId worldId, bool flag )
 {

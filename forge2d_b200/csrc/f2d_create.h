@@ -278,6 +278,7 @@ inline int createShape( World* w, int bodyId, const ShapeParams& def, const void
 	shape.id = shapeId;
 	shape.bodyId = body.id;
 	shape.type = type;
+	w->shapeTypeMask |= 1u << type;
 	shape.density = def.density;
 	shape.friction = def.friction;
 	shape.restitution = def.restitution;

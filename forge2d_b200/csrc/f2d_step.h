@@ -896,11 +896,15 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 	// Rebuild of the dynamic and kinematic trees (world.c:499, broad_phase.c:488-492). The reference overlaps it with
 	// the narrowphase on another worker; here the whole team does one after the other, each fully data-parallel
 	// (measured: a single block rebuilding beside the narrowphase is slower than the grid doing both in turn).
-	auto narrowphase = [&]( int rank, int size ) {
-		// a thread's indices only grow, so the list segment is tracked with a forward cursor (no per-thread table)
+	// a thread's indices only grow, so the list segment is tracked with a forward cursor (no per-thread table)
+	struct WorkCursor
+	{
+		World* w;
+		int total;
 		int seg = -1, segStart = 0, segEnd = 0;
 		const int32_t* list = nullptr;
-		auto contactAt = [&]( int i ) -> int {
+		F2D_HDF int at( int i )
+		{
 			if ( i >= total )
 				return kNull;
 			while ( i >= segEnd )
@@ -912,12 +916,63 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 				list = ptr( w, a );
 			}
 			return list[i - segStart];
-		};
+		}
+	};
+	// Narrowphase per pair class (contact.c:166-184 registers one manifold function per pair of shape types): a world
+	// with more than one shape type first bins its work list by class - counts, bases, scatter into World::stateList,
+	// which is free until the state pass - so that the lanes of a warp run the same manifold function instead of
+	// serialising a switch over up to six of them. A world with one shape type (bench2d: boxes) has one class and skips
+	// the binning. The work-list position of a contact only matters to the callback-mediated step (pre-solve call
+	// order), which does not come through here.
+	const bool binned = part == kCollideAll && w->pairClassBinningOff == 0 && ( w->shapeTypeMask & ( w->shapeTypeMask - 1 ) ) != 0 &&
+						total <= w->stateList.cap && total > 0;
+	if ( binned )
+	{
+		const ContactSim* sims = ptr( w, w->contactSims );
+		int32_t* sorted = ptr( w, w->stateList );
+		for ( int k = t.rank(); k < kPairClassCount; k += t.size() )
+			w->step.classCount[k] = 0;
+		t.sync();
+		{
+			WorkCursor cursor{ w, total };
+			for ( int i = t.rank(); i < total; i += t.size() )
+				atomAdd( &w->step.classCount[sims[cursor.at( i )].pairClass & ( kPairClassCount - 1 )], 1 );
+		}
+		t.sync();
+		if ( t.rank() == 0 )
+		{
+			int base = 0;
+			for ( int k = 0; k < kPairClassCount; ++k )
+			{
+				w->step.classFill[k] = base;
+				base += w->step.classCount[k];
+			}
+		}
+		t.sync();
+		{
+			WorkCursor cursor{ w, total };
+			for ( int i = t.rank(); i < total; i += t.size() )
+			{
+				const int id = cursor.at( i );
+				sorted[atomAdd( &w->step.classFill[sims[id].pairClass & ( kPairClassCount - 1 )], 1 )] = id;
+			}
+		}
+		t.sync();
+	}
+	auto narrowphase = [&]( int rank, int size ) {
 		// A contact is a chain of dependent gathers (id -> contact record -> shapes / bodies / body sims). No prefetch of
 		// the thread's next record: in a batch this phase keeps DRAM busy 96 % of the time (profiles/README.md, r02k), and a
 		// prefetch moves whole 128-byte lines where the gathers touch single sectors.
+		if ( binned )
+		{
+			const int32_t* sorted = ptr( w, w->stateList );
+			for ( int i = rank; i < total; i += size )
+				collideContact( w, sorted[i], i );
+			return;
+		}
+		WorkCursor cursor{ w, total };
 		for ( int i = rank; i < total; i += size )
-			collideContact( w, contactAt( i ), i );
+			collideContact( w, cursor.at( i ), i );
 	};
 	// A large team rebuilds the trees later, beside the serial parts of the step (below).
 	bool treeBeside = false;

@@ -362,7 +362,7 @@ struct alignas( 32 ) ContactSim
 	int32_t bodyIdA, bodyIdB; // owners of the two shapes (ours: saves the shape -> body hop of the narrowphase gather)
 	uint32_t simFlags;
 	SimplexCache cache;
-	int32_t pad0;
+	int32_t pairClass; // typeA * kShapeTypeCount + typeB (fixed at creation): the narrowphase bins its work list by it
 	StoredManifold manifold;
 	int32_t bodySimIndexA, bodySimIndexB; // awake indices or kNull
 	float friction, restitution;
@@ -554,9 +554,11 @@ struct SolverSet
 };
 
 // Step constants: B2/src/solver.h:75-138, built in world.c:742-771
+constexpr int kPairClassCount = 32; // kShapeTypeCount^2 rounded up
 struct StepCtx
 {
 	float dt, inv_dt, h, inv_h;
+	int32_t classCount[kPairClassCount], classFill[kPairClassCount]; // narrowphase work list by pair class (stepCollide)
 	int32_t subStepCount;
 	Soft contactSoftness, staticSoftness;
 	float restitutionThreshold, maxLinearVelocity;
@@ -714,7 +716,9 @@ struct World
 	// in-kernel phase profile: rank 0 accumulates nanoseconds between marks (f2d_step.h F2D_MARK); off unless enabled
 	uint64_t prof[kProfSlots];
 	uint64_t profLast;
-	int32_t profEnabled, pad2;
+	int32_t profEnabled;
+	uint32_t shapeTypeMask; // bit per shape type ever created in this world: one bit = one pair class, nothing to bin
+	int32_t pairClassBinningOff, pad3[3]; // measurement aid (f2dWorld_EnablePairClassBinning): 1 = never bin
 
 	// entities (slot = id)
 	IdPool bodyIds, shapeIds, contactIds, jointIds, islandIds, setIds, chainIds;

@@ -1041,7 +1041,7 @@ F2D_HDF inline int createContact( World* w, int shapeIdA, int shapeIdB )
 	sim.shapeIdB = shapeIdB;
 	sim.bodyIdA = shapeA.bodyId;
 	sim.bodyIdB = shapeB.bodyId;
-	sim.pad0 = 0;
+	sim.pairClass = shapeA.type * kShapeTypeCount + shapeB.type;
 	sim.pad1 = 0;
 	sim.pad2 = 0;
 	memset( &sim.cache, 0, sizeof( sim.cache ) );

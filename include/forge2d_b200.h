@@ -586,6 +586,8 @@ F2D_API void f2dWorld_EnablePhaseTiming( b2WorldId worldId, bool flag );
 F2D_API int f2dWorld_GetStepInfo( b2WorldId worldId, int* out, int cap );
 /// In-kernel phase profile: ns per sub-phase (f2d::ProfSlot order) accumulated on the device since enabled
 F2D_API void f2dWorld_EnableProfile( b2WorldId worldId, bool flag );
+/* Measurement aid: bin the narrowphase work list by pair class (default on; only worlds with several shape types bin). */
+F2D_API void f2dWorld_EnablePairClassBinning( b2WorldId worldId, bool flag );
 F2D_API int f2dWorld_ReadProfile( b2WorldId worldId, unsigned long long* out, int cap );
 /// Device-side step without the per-step host synchronisation / header readback (bench: inputs resident in HBM)
 F2D_API void f2dWorld_StepAsync( b2WorldId worldId, float timeStep, int subStepCount );

@@ -189,6 +189,26 @@ if "profile" in what:
     profile("many_pyramids", {}, 1, 2, 16)
     profile("joint_grid", {}, 1, 8, 32)
 
+if "classes" in what:
+    # narrowphase of mixed-shape worlds with / without the work list binned by pair class
+    for name, kw, frames in (("falling_shapes", dict(count=600), 260), ("random_world", dict(seed=3, count=400), 200)):
+        for binning in (True, False):
+            s = scenes.SCENES[name](lib, **kw)
+            lib.f2dWorld_SetLaunchMode(s.world, 0)
+            lib.f2dWorld_EnablePairClassBinning(s.world, binning)
+            for _ in range(frames):
+                s.step()
+            lib.f2dWorld_EnableProfile(s.world, True)
+            timed = 64
+            for _ in range(timed):
+                s.step()
+            out = (C.c_ulonglong * 32)()
+            lib.f2dWorld_ReadProfile(s.world, out, 32)
+            cnt = lib.b2World_GetCounters(s.world)
+            print("%s %s binning %s: contacts %d, narrow %.1f us per frame, frame %.1f us" % (
+                name, kw, binning, cnt.contactCount, out[4] / timed / 1e3, sum(out[:23]) / timed / 1e3), flush=True)
+            s.destroy()
+
 if "b2d" in what:
     for _ in range(3):
         profile("bench2d", {}, 0, 256, 64)
