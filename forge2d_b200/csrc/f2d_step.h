@@ -924,19 +924,45 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 	// serialising a switch over up to six of them. A world with one shape type (bench2d: boxes) has one class and skips
 	// the binning. The work-list position of a contact only matters to the callback-mediated step (pre-solve call
 	// order), which does not come through here.
-	const bool binned = part == kCollideAll && w->pairClassBinningOff == 0 && ( w->shapeTypeMask & ( w->shapeTypeMask - 1 ) ) != 0 &&
+	// (two shape types - say boxes on a ground segment - mean one dominant class: not worth two passes over the list)
+	const bool binned = part == kCollideAll && w->pairClassBinningOff == 0 && popCount32( w->shapeTypeMask ) >= 3 &&
 						total <= w->stateList.cap && total > 0;
 	if ( binned )
 	{
 		const ContactSim* sims = ptr( w, w->contactSims );
 		int32_t* sorted = ptr( w, w->stateList );
+		typename Team::Lanes L;
+		// one atomic per class and warp, not per contact (a grid has tens of thousands of contacts on a handful of counters)
+		auto claim = [&]( bool active, int cls, int32_t* counters ) -> int {
+			uint32_t pending = L.ballot( active );
+			int slot = 0;
+			while ( pending != 0 )
+			{
+				const int leader = lowestBit32( pending );
+				const int leaderClass = L.from( cls, leader );
+				const uint32_t same = L.ballot( active && cls == leaderClass );
+				int base = 0;
+				if ( L.lane() == leader )
+					base = atomAdd( counters + leaderClass, popCount32( same ) );
+				base = L.from( base, leader );
+				if ( active && cls == leaderClass )
+					slot = base + popCount32( same & ( ( 1u << L.lane() ) - 1u ) );
+				pending &= ~same;
+			}
+			return slot;
+		};
 		for ( int k = t.rank(); k < kPairClassCount; k += t.size() )
 			w->step.classCount[k] = 0;
 		t.sync();
 		{
 			WorkCursor cursor{ w, total };
-			for ( int i = t.rank(); i < total; i += t.size() )
-				atomAdd( &w->step.classCount[sims[cursor.at( i )].pairClass & ( kPairClassCount - 1 )], 1 );
+			for ( int base = t.rank() - L.lane(); base < total; base += t.size() )
+			{
+				const int i = base + L.lane();
+				const bool active = i < total;
+				const int cls = active ? ( sims[cursor.at( i )].pairClass & ( kPairClassCount - 1 ) ) : 0;
+				claim( active, cls, w->step.classCount );
+			}
 		}
 		t.sync();
 		if ( t.rank() == 0 )
@@ -951,10 +977,15 @@ template <class Team> F2D_HDF inline void stepCollide( World* w, Team& t, int pa
 		t.sync();
 		{
 			WorkCursor cursor{ w, total };
-			for ( int i = t.rank(); i < total; i += t.size() )
+			for ( int base = t.rank() - L.lane(); base < total; base += t.size() )
 			{
-				const int id = cursor.at( i );
-				sorted[atomAdd( &w->step.classFill[sims[id].pairClass & ( kPairClassCount - 1 )], 1 )] = id;
+				const int i = base + L.lane();
+				const bool active = i < total;
+				const int id = active ? cursor.at( i ) : 0;
+				const int cls = active ? ( sims[id].pairClass & ( kPairClassCount - 1 ) ) : 0;
+				const int slot = claim( active, cls, w->step.classFill );
+				if ( active )
+					sorted[slot] = id;
 			}
 		}
 		t.sync();
