@@ -49,7 +49,9 @@ struct HostWorld
 		std::vector<b2SurfaceMaterial> materials;
 	};
 	std::vector<Chain> chains;
-	bool headerFresh = true;
+	bool headerFresh = true; // false between f2dWorld_StepAsync and the arrival of that step's header (headerCurrent)
+	float asyncTimeStep = 0.0f;
+	int asyncSubSteps = 0;
 	// Partial host <-> device synchronisation while the device copy is the newer one (SyncState::kDeviceNewer):
 	//   bodyMirrorFresh  the host copies of the body records, simulation records and solver states are current (one
 	//                    download of those three arrays after a step serves every position / velocity getter);
@@ -122,6 +124,17 @@ static HostWorld* worldFromId( b2WorldId id )
 	return hw;
 }
 
+// After f2dWorld_StepAsync the header copy of that step may still be in flight: everything that reads the header of
+// `hw.img` (counts, capacities in use, error flags) waits for it first.
+static void headerCurrent( HostWorld& hw )
+{
+	if ( hw.headerFresh == false )
+	{
+		backendSynchronize( hw );
+		hw.headerFresh = true;
+	}
+}
+
 // Pending host-side edits of a device-newer image go to the device (before a step, or before the image is downloaded)
 static void flushDirty( HostWorld& hw )
 {
@@ -149,6 +162,7 @@ static void flushDirty( HostWorld& hw )
 // Host image current and writable
 static World* hostImage( HostWorld& hw )
 {
+	headerCurrent( hw );
 	if ( hw.state == kDeviceNewer )
 	{
 		flushDirty( hw );
@@ -171,6 +185,7 @@ static World* mutableImage( HostWorld& hw )
 // three arrays (a few hundred KB for bench2d) instead of the whole image (megabytes).
 static World* bodyImage( HostWorld& hw )
 {
+	headerCurrent( hw );
 	if ( hw.state == kDeviceNewer && hw.bodyMirrorFresh == false )
 	{
 		World* w = hw.img;
@@ -811,6 +826,34 @@ static void stepWithHostCallbacks( HostWorld& hw, float dt, int subSteps )
 	backendPhaseEnd( hw );
 }
 
+// The step stops before its first structural edit when this step's new contacts do not fit the arrays of the image
+// (f2d_step.h stepPairs; the reference's arrays grow on demand): grow and repeat. `stepped`: the first attempt has run
+// already (f2dWorld_StepAsync) and only its verdict is looked at.
+static void stepUntilItFits( HostWorld& hw, float timeStep, int subStepCount, bool stepped )
+{
+	for ( int attempt = 0;; ++attempt )
+	{
+		if ( stepped == false )
+		{
+			if ( hw.img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
+				stepWithHostCallbacks( hw, timeStep, subStepCount );
+			else
+				backendStep( hw, timeStep, subStepCount, true );
+		}
+		stepped = false;
+		const int need = hw.img->step.retryContacts;
+		if ( need == 0 || attempt == 4 )
+			break;
+		World* w = hostImage( hw );
+		w->step.retryContacts = 0;
+		w->error &= ~kErrRetry;
+		reserve( hw, 0, 0, need + ( need >> 1 ), 0 );
+		hw.img->step.retryContacts = 0;
+		hw.img->error &= ~kErrRetry;
+		hw.state = kHostNewer;
+	}
+}
+
 } // namespace f2d
 extern "C" {
 void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
@@ -828,26 +871,9 @@ void b2World_Step( b2WorldId worldId, float timeStep, int subStepCount )
 		checkWorldError( *hw, "b2World_Step refused" );
 		return;
 	}
+	headerCurrent( *hw );
 	prepareStep( *hw );
-	for ( int attempt = 0;; ++attempt )
-	{
-		if ( hw->img->hostCallbacks & ( kHostCustomFilter | kHostPreSolve ) )
-			stepWithHostCallbacks( *hw, timeStep, subStepCount );
-		else
-			backendStep( *hw, timeStep, subStepCount, true );
-		// The step stops before its first structural edit when this step's new contacts do not fit the arrays of the
-		// image (f2d_step.h stepPairs; the reference's arrays grow on demand): grow and repeat.
-		const int need = hw->img->step.retryContacts;
-		if ( need == 0 || attempt == 4 )
-			break;
-		World* w = hostImage( *hw );
-		w->step.retryContacts = 0;
-		w->error &= ~kErrRetry;
-		reserve( *hw, 0, 0, need + ( need >> 1 ), 0 );
-		hw->img->step.retryContacts = 0;
-		hw->img->error &= ~kErrRetry;
-		hw->state = kHostNewer;
-	}
+	stepUntilItFits( *hw, timeStep, subStepCount, false );
 	hw->eventsFresh = ( hw->state != kDeviceNewer );
 	checkWorldError( *hw, "b2World_Step" );
 }
@@ -862,17 +888,25 @@ void f2dWorld_StepAsync( b2WorldId worldId, float timeStep, int subStepCount )
 		reportError( "f2dWorld_StepAsync: a world with host callbacks must be stepped with b2World_Step (the callbacks run on the calling thread)" );
 		return;
 	}
+	headerCurrent( *hw ); // (of the step before this one: prepareStep reads it)
+	prepareStep( *hw );
 	backendStep( *hw, timeStep, subStepCount, false );
 	hw->eventsFresh = false;
 	hw->headerFresh = false;
+	hw->asyncTimeStep = timeStep;
+	hw->asyncSubSteps = subStepCount;
 }
 void f2dWorld_Synchronize( b2WorldId worldId )
 {
 	HostWorld* hw = worldFromId( worldId );
 	if ( hw == nullptr )
 		return;
+	const bool pending = hw->headerFresh == false;
 	backendSynchronize( *hw );
 	hw->headerFresh = true;
+	// an asynchronous step that stopped for lack of contact room is repeated here, on a larger image
+	if ( pending && hw->img->step.retryContacts != 0 )
+		stepUntilItFits( *hw, hw->asyncTimeStep, hw->asyncSubSteps, true );
 	checkWorldError( *hw, "f2dWorld_Synchronize" );
 }
 
@@ -880,6 +914,7 @@ void f2dWorld_Synchronize( b2WorldId worldId )
 // Event arrays: pointers into the host image, refreshed by range downloads (B2/src/world.c:1491-1555)
 template <class T> static void refreshArray( HostWorld& hw, const Arr<T>& a )
 {
+	headerCurrent( hw );
 	if ( hw.state == kDeviceNewer && a.count > 0 )
 		backendDownloadRange( hw, a.off, (uint64_t)a.count * sizeof( T ) );
 }
@@ -1017,7 +1052,10 @@ b2Counters b2World_GetCounters( b2WorldId worldId )
 int b2World_GetAwakeBodyCount( b2WorldId worldId )
 {
 	HostWorld* hw = worldFromId( worldId );
-	return hw ? hw->img->awakeBodies.count : 0;
+	if ( hw == nullptr )
+		return 0;
+	headerCurrent( *hw );
+	return hw->img->awakeBodies.count;
 }
 
 // ---- bodies ----------------------------------------------------------------------------------------------------

@@ -172,7 +172,7 @@ if "gangprofile" in what:
             d = [(out[i] - before[idx][i]) / steps / 1e3 for i in range(23)]
             print("%s, 8192 decorrelated worlds: %.3f ms/step; world %d in-kernel %.1f us: " % (
                 "gang 128x7" if gang else "one world per block 128x8", ms, idx, sum(d)) +
-                " ".join("%s=%.1f" % (n, d[i]) for i, n in enumerate(PROF_NAMES) if d[i] > 0.05), flush=True)
+                " ".join("%s=%.1f" % (n, d[i]) for i, n in enumerate(PROF_NAMES[:23]) if d[i] > 0.05), flush=True)
         lib.f2dBatch_Destroy(b)
         scratch.destroy()
 
