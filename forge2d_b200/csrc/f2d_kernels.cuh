@@ -64,16 +64,21 @@ template <class Slice> __device__ __forceinline__ int sliceExclusiveScan( const 
 	return carry;
 }
 
-// The first two warps of a thread block as a team of their own (hardware barrier 3): the serial parts of the step and the
+// The first four warps of a thread block as a team of their own (hardware barrier 3): the serial parts of the step and the
 // little parallel work between them, while the rear rebuilds the trees (stepCollide).
 struct CtaFront
 {
-	static constexpr bool kHasSoloBlock = false;
+	// (as in the solo block of a grid, the warps beside the two serial threads read ahead of them: their L1 is the
+	// block's, and the narrowphase has just swept it)
+	static constexpr bool kHasSoloBlock = true;
+	static constexpr int kThreads = 128;
 	int32_t* scratch;
 	typedef WarpLanes Lanes;
+	__device__ bool inSoloBlock() const { return true; }
+	__device__ int soloSize() const { return kThreads; }
 	__device__ int rank() const { return (int)threadIdx.x; }
-	__device__ int size() const { return 64; }
-	__device__ void sync() const { asm volatile( "bar.sync 3, 64;" ::: "memory" ); }
+	__device__ int size() const { return kThreads; }
+	__device__ void sync() const { asm volatile( "bar.sync 3, %0;" ::"n"( kThreads ) : "memory" ); }
 	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
 };
 
@@ -91,7 +96,7 @@ struct GridFront
 	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
 };
 
-// All warps of a thread block but the first two, as a team of their own (hardware barrier 2): see CtaTeamT::rear.
+// All warps of a thread block but the front's, as a team of their own (hardware barrier 2): see CtaTeamT::rear.
 struct CtaRear
 {
 	int32_t* scratch;
@@ -100,9 +105,9 @@ struct CtaRear
 	typedef WarpLanes Lanes;
 	__device__ int32_t* arenaPtr() const { return arena; }
 	__device__ int arenaSize() const { return arenaInts; }
-	__device__ int rank() const { return (int)threadIdx.x - 64; }
-	__device__ int size() const { return (int)blockDim.x - 64; }
-	__device__ void sync() const { asm volatile( "bar.sync 2, %0;" ::"r"( (int)blockDim.x - 64 ) : "memory" ); }
+	__device__ int rank() const { return (int)threadIdx.x - CtaFront::kThreads; }
+	__device__ int size() const { return (int)blockDim.x - CtaFront::kThreads; }
+	__device__ void sync() const { asm volatile( "bar.sync 2, %0;" ::"r"( (int)blockDim.x - CtaFront::kThreads ) : "memory" ); }
 	__device__ int exclusiveScan( int32_t* data, int n ) const { return sliceExclusiveScan( *this, scratch, data, n ); }
 };
 
@@ -203,7 +208,7 @@ template <bool kWholeBlock, bool kLarge = false> struct CtaTeamT
 	// (stepCollide: the rear rebuilds the trees while two threads of the front apply the ordered contact-state changes)
 	static constexpr bool kCanSplitTree = kWholeBlock && kLarge;
 	__device__ bool canSplitTree() const { return true; }
-	__device__ bool inFront() const { return threadIdx.x < 64; }
+	__device__ bool inFront() const { return threadIdx.x < CtaFront::kThreads; }
 	__device__ CtaRear rear() const { return CtaRear{ smem + 64, arena, arenaInts }; }
 	__device__ CtaFront front() const { return CtaFront{ smem }; }
 };

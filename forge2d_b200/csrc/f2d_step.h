@@ -124,7 +124,13 @@ F2D_HDF inline bool pairExists( World* w, const Body& bodyA, const Body& bodyB, 
 	return false;
 }
 
-// One moved proxy: queries in the reference's tree order and filter order (broad_phase.c:160-302, 311-374)
+// One moved proxy: queries in the reference's tree order and filter order (broad_phase.c:160-302, 311-374).
+// The reference's query callback does everything per hit. On a GPU that serialises a warp: the 32 lanes walk different
+// paths, a lane that hits a leaf runs the callback - four levels of dependent loads (shapes, bodies, a walk over a body's
+// contacts) - while the 31 others wait, and then the next lane hits (measured: 47 k cycles per query for ~20 dependent
+// loads of its own). So the traversal only COLLECTS the hits that survive the tests it can make on the node it already
+// holds (self, the both-moved rule), and the callback body runs afterwards over each lane's short list - the k-th
+// candidate of every lane at the same time, so the loads of a level are in flight together. Order per proxy = hit order.
 F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 {
 	int32_t* heads = ptr( w, w->moveHeads );
@@ -141,38 +147,13 @@ F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 	const Body* bodies = ptr( w, w->bodies );
 	MovePair* pairs = ptr( w, w->movePairs );
 
-	for ( int pass = 0; pass < 3; ++pass )
-	{
-		int treeType;
-		if ( queryType == kDynamicBody )
-			treeType = pass == 0 ? kKinematicBody : ( pass == 1 ? kStaticBody : kDynamicBody );
-		else
+	constexpr int kCandidates = 16; // (a full list is worked off on the spot)
+	int32_t candidateKey[kCandidates], candidateShape[kCandidates];
+	int candidateCount = 0;
+	auto workOff = [&]() {
+		for ( int k = 0; k < candidateCount; ++k )
 		{
-			if ( pass != 2 )
-				continue;
-			treeType = kDynamicBody;
-		}
-		const Tree& tree = w->trees[treeType];
-		const TreeNode* treeNodes = ptr( w, tree.nodes );
-		treeQuery( w, tree, fat, UINT64_MAX, [&]( int proxy, uint64_t userData ) -> bool {
-			int shapeId = (int)userData;
-			int key = proxyKey( proxy, treeType );
-			if ( key == queryKey )
-				return true;
-			// both proxies moved: the pair belongs to exactly one of the two queries
-			if ( queryType == kDynamicBody )
-			{
-				if ( treeType == kDynamicBody && key < queryKey )
-				{
-					if ( treeNodes[proxy].flags & kNodeMoved )
-						return true;
-				}
-			}
-			else
-			{
-				if ( treeNodes[proxy].flags & kNodeMoved )
-					return true;
-			}
+			const int key = candidateKey[k], shapeId = candidateShape[k];
 			int shapeIdA, shapeIdB;
 			if ( key < queryKey )
 			{
@@ -189,26 +170,62 @@ F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
 			const Body& bodyA = bodies[shapeA.bodyId];
 			const Body& bodyB = bodies[shapeB.bodyId];
 			if ( pairExists( w, bodyA, bodyB, shapeIdA, shapeIdB ) )
-				return true;
+				continue;
 			if ( shapeA.bodyId == shapeB.bodyId )
-				return true;
+				continue;
 			if ( shapeA.sensorIndex != kNull || shapeB.sensorIndex != kNull )
-				return true;
+				continue;
 			if ( shouldShapesCollide( shapeA.filter, shapeB.filter ) == false )
-				return true;
+				continue;
 			if ( shouldBodiesCollide( w, bodyA, bodyB ) == false )
-				return true;
+				continue;
 			int pairIndex = atomAdd( &w->step.pairCount, 1 );
 			if ( pairIndex >= w->movePairs.cap )
-				return true; // counted, not stored: stepPairs sees pairCount > cap and asks the host for room (retryContacts)
+				continue; // counted, not stored: stepPairs sees pairCount > cap and asks the host for room (retryContacts)
 			MovePair& p = pairs[pairIndex];
 			p.shapeA = shapeIdA;
 			p.shapeB = shapeIdB;
 			p.next = heads[moveIndex]; // push-front: creation order is the reverse of hit order
 			heads[moveIndex] = pairIndex;
+		}
+		candidateCount = 0;
+	};
+
+	for ( int pass = 0; pass < 3; ++pass )
+	{
+		int treeType;
+		if ( queryType == kDynamicBody )
+			treeType = pass == 0 ? kKinematicBody : ( pass == 1 ? kStaticBody : kDynamicBody );
+		else
+		{
+			if ( pass != 2 )
+				continue;
+			treeType = kDynamicBody;
+		}
+		const Tree& tree = w->trees[treeType];
+		treeQueryFlags( w, tree, fat, UINT64_MAX, [&]( int proxy, uint64_t userData, uint32_t flags ) -> bool {
+			int key = proxyKey( proxy, treeType );
+			if ( key == queryKey )
+				return true;
+			// both proxies moved: the pair belongs to exactly one of the two queries
+			if ( queryType == kDynamicBody )
+			{
+				if ( treeType == kDynamicBody && key < queryKey && ( flags & kNodeMoved ) != 0 )
+					return true;
+			}
+			else if ( flags & kNodeMoved )
+			{
+				return true;
+			}
+			if ( candidateCount == kCandidates )
+				workOff();
+			candidateKey[candidateCount] = key;
+			candidateShape[candidateCount] = (int)userData;
+			candidateCount += 1;
 			return true;
 		} );
 	}
+	workOff();
 }
 
 // The serial half of pair finding: contacts for the candidate pairs, in the reference's creation order (World::pairOrder
@@ -761,12 +778,13 @@ template <class Team> F2D_HDF inline int contactStateCollect( World* w, Team& t 
 		{
 			uint64_t word = bits[k];
 			int out = offsets[k];
-			int bit = 0;
+			// lowest set bit first: the j-th flagged contact of every lane's word is handled in the same iteration (a
+			// loop over all 64 bit positions runs the gathers below for one lane at a time)
 			while ( word != 0 )
 			{
-				if ( word & 1ull )
 				{
-					const int id = 64 * k + bit;
+					const int id = 64 * k + lowestBit64( word );
+					word &= word - 1;
 					const uint32_t simFlags = sims[id].simFlags;
 					int kind = kStateNone;
 					if ( simFlags & kSimDisjoint )
@@ -782,8 +800,6 @@ template <class Team> F2D_HDF inline int contactStateCollect( World* w, Team& t 
 						kind = kStateStopped;
 					list[out++] = id | ( kind << kKindShift );
 				}
-				word >>= 1;
-				bit += 1;
 			}
 		}
 	}

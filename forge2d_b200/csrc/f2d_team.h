@@ -130,6 +130,16 @@ F2D_HD int lowestBit32( uint32_t x )
 #endif
 }
 
+// index of the lowest set bit (x != 0)
+F2D_HD int lowestBit64( uint64_t x )
+{
+#if defined( __CUDA_ARCH__ )
+	return __ffsll( (long long)x ) - 1;
+#else
+	return __builtin_ctzll( x );
+#endif
+}
+
 // The lanes that walk a graph together (island split): one host thread, or the 32 lanes of a warp.
 struct SoloLanes
 {

@@ -618,7 +618,8 @@ F2D_HD int treeHeight( const World* w, const Tree& t )
 
 // Overlap query with the reference's visit order (child2 subtree first; dynamic_tree.c:1114-1170).
 // `visit(proxyId, userData)` returns false to stop.
-template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box box, uint64_t maskBits, F&& visit )
+// `visit( leaf id, userData, node flags )`
+template <class F> F2D_HDF inline void treeQueryFlags( World* w, const Tree& t, Box box, uint64_t maskBits, F&& visit )
 {
 	if ( t.nodeCount == 0 || t.root == kNull )
 		return;
@@ -650,7 +651,7 @@ template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box b
 	{
 		if ( cur.flags & kNodeLeaf )
 		{
-			if ( visit( id, (uint64_t)(uint32_t)cur.child1 | ( (uint64_t)(uint32_t)cur.child2 << 32 ) ) == false )
+			if ( visit( id, (uint64_t)(uint32_t)cur.child1 | ( (uint64_t)(uint32_t)cur.child2 << 32 ), cur.flags ) == false )
 				return;
 		}
 		else
@@ -684,6 +685,12 @@ template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box b
 		id = stack[--sp];
 		cur = fieldsOf( nodes[id] );
 	}
+}
+
+// dynamic_tree.c:1114-1170 `visit( leaf id, userData )`
+template <class F> F2D_HDF inline void treeQuery( World* w, const Tree& t, Box box, uint64_t maskBits, F&& visit )
+{
+	treeQueryFlags( w, t, box, maskBits, [&]( int id, uint64_t userData, uint32_t ) -> bool { return visit( id, userData ); } );
 }
 
 } // namespace f2d
