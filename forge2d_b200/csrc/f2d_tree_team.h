@@ -88,80 +88,78 @@ constexpr int kTreeSerialFinish = 12; // segments at most this long are finished
 constexpr int kTreeSerialFinishArena = 4;
 constexpr int kTreeQueueBuildMaxTeam = 256; // teams up to this size use the work-queue build (treeSplitSegment)
 
+// One short segment [a, e) of the item array, built and refitted by ONE thread. Many threads of a warp do this side by
+// side on different segments, so the routine is two loops with as little data-dependent control flow as the algorithm
+// allows - top-down: pop a range, partition it, create its node, push the halves (ranges of one item are hung right
+// away); then bottom-up over the created nodes in reverse creation order (a node is created before everything below it).
+// The recursive form of the reference (dynamic_tree.c:1404-1521: descend, come back, refit) is a three-state machine per
+// lane, and a warp whose lanes sit in different states runs the states - each with its loads - one after the other
+// (measured inside the batch kernel: 240-310 of a world's 650 us of rebuild).
 F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
 									   int32_t* levelOf, int a, int e, int parentKey )
 {
-	struct Item
-	{
-		int32_t node, childCount, start, split, end;
-	};
-	Item stack[kTreeSerialFinish + 2];
-	auto makeNode = [&]( int split, int parentNode ) {
-		int nodeIndex = freed[split - 1];
-		levelOf[split - 1] = 0x7fffffff; // refitted here, not by the level-synchronous pass
-		TreeNode& node = nodes[nodeIndex];
-		node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
-		node.category = 1;
-		node.height = 0;
-		node.flags = kNodeAllocated;
-		node.parent = parentNode;
-		node.child1 = kNull;
-		node.child2 = kNull;
-		return nodeIndex;
-	};
+	constexpr int kDepth = kTreeSerialFinish + 2;
+	int32_t rangeStart[kDepth], rangeEnd[kDepth], rangeParent[kDepth]; // parent = (node << 1) | side, kNull for the root
+	int32_t created[kDepth];
+	int createdCount = 0;
 	int top = 0;
-	int split0 = a + treePartitionMid( leafIndices + a, leafCenters + a, e - a );
-	stack[0] = Item{ makeNode( split0, parentKey == kNull ? kNull : parentKey >> 1 ), -1, a, split0, e };
-	if ( parentKey == kNull )
-		tree.root = stack[0].node;
-	else if ( parentKey & 1 )
-		nodes[parentKey >> 1].child2 = stack[0].node;
-	else
-		nodes[parentKey >> 1].child1 = stack[0].node;
-	while ( true )
+	rangeStart[0] = a;
+	rangeEnd[0] = e;
+	rangeParent[0] = parentKey;
+	top = 1;
+	while ( top > 0 )
 	{
-		Item& item = stack[top];
-		item.childCount += 1;
-		if ( item.childCount == 2 )
-		{
-			TreeNode& node = nodes[item.node];
-			const TreeNode& c1 = nodes[node.child1];
-			const TreeNode& c2 = nodes[node.child2];
-			node.box = boxUnion( c1.box, c2.box );
-			node.height = (uint16_t)( 1 + maxU16( c1.height, c2.height ) );
-			node.category = c1.category | c2.category;
-			if ( top == 0 )
-				break;
-			top -= 1;
-			continue;
-		}
-		int start = item.childCount == 0 ? item.start : item.split;
-		int end = item.childCount == 0 ? item.split : item.end;
+		top -= 1;
+		const int start = rangeStart[top], end = rangeEnd[top], key = rangeParent[top];
+		const int parentNode = key == kNull ? kNull : key >> 1;
+		int index;
 		if ( end - start == 1 )
 		{
-			int leaf = leafIndices[start];
-			if ( item.childCount == 0 )
-				nodes[item.node].child1 = leaf;
-			else
-				nodes[item.node].child2 = leaf;
-			nodes[leaf].parent = item.node;
+			index = leafIndices[start];
+			nodes[index].parent = parentNode;
 		}
 		else
 		{
-			int split = start + treePartitionMid( leafIndices + start, leafCenters + start, end - start );
-			int child = makeNode( split, item.node );
-			if ( item.childCount == 0 )
-				nodes[item.node].child1 = child;
-			else
-				nodes[item.node].child2 = child;
-			if ( top + 1 >= kTreeSerialFinish + 2 )
+			const int split = start + treePartitionMid( leafIndices + start, leafCenters + start, end - start );
+			index = freed[split - 1];
+			levelOf[split - 1] = 0x7fffffff; // refitted here, not by the level-synchronous pass
+			TreeNode& node = nodes[index];
+			node.box = Box{ { 0.0f, 0.0f }, { 0.0f, 0.0f } };
+			node.category = 1;
+			node.height = 0;
+			node.flags = kNodeAllocated;
+			node.parent = parentNode;
+			node.child1 = kNull;
+			node.child2 = kNull;
+			if ( createdCount >= kDepth || top + 2 > kDepth )
 			{
 				setError( w, kErrTreeStack, __LINE__ );
 				return;
 			}
-			top += 1;
-			stack[top] = Item{ child, -1, start, split, end };
+			created[createdCount++] = index;
+			rangeStart[top] = start;
+			rangeEnd[top] = split;
+			rangeParent[top] = ( index << 1 ) | 0;
+			rangeStart[top + 1] = split;
+			rangeEnd[top + 1] = end;
+			rangeParent[top + 1] = ( index << 1 ) | 1;
+			top += 2;
 		}
+		if ( key == kNull )
+			tree.root = index;
+		else if ( key & 1 )
+			nodes[parentNode].child2 = index;
+		else
+			nodes[parentNode].child1 = index;
+	}
+	for ( int k = createdCount - 1; k >= 0; --k )
+	{
+		TreeNode& node = nodes[created[k]];
+		const TreeNode& c1 = nodes[node.child1];
+		const TreeNode& c2 = nodes[node.child2];
+		node.box = boxUnion( c1.box, c2.box );
+		node.height = (uint16_t)( 1 + maxU16( c1.height, c2.height ) );
+		node.category = c1.category | c2.category;
 	}
 }
 
@@ -596,6 +594,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			}
 		}
 		t.sync();
+		mark( pfTreeLevels ); // (the work-queue build: long segments)
 		// short segments: one thread each builds and refits its subtree serially, then reports to the node above
 		{
 			const int smallCount = s.ctrl[3];
@@ -609,6 +608,7 @@ template <class Team> F2D_HDF inline void treeRebuildTeam( World* w, Team& t, Tr
 			}
 		}
 		t.sync();
+		mark( pfTreeTail ); // (short segments and the refit by last arrival)
 		return;
 	}
 

@@ -169,10 +169,10 @@ if "gangprofile" in what:
             lib.f2dBatch_DownloadWorld(b, idx, scratch.world)
             out = (C.c_ulonglong * 32)()
             lib.f2dWorld_ReadProfile(scratch.world, out, 32)
-            d = [(out[i] - before[idx][i]) / steps / 1e3 for i in range(23)]
+            d = [(out[i] - before[idx][i]) / steps / 1e3 for i in range(len(PROF_NAMES))]
             print("%s, 8192 decorrelated worlds: %.3f ms/step; world %d in-kernel %.1f us: " % (
-                "gang 128x7" if gang else "one world per block 128x8", ms, idx, sum(d)) +
-                " ".join("%s=%.1f" % (n, d[i]) for i, n in enumerate(PROF_NAMES[:23]) if d[i] > 0.05), flush=True)
+                "gang 128x7" if gang else "one world per block 128x8", ms, idx, sum(d[:23])) +
+                " ".join("%s=%.1f" % (n, d[i]) for i, n in enumerate(PROF_NAMES) if d[i] > 0.05), flush=True)
         lib.f2dBatch_Destroy(b)
         scratch.destroy()
 
