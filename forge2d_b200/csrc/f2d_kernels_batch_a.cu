@@ -1,6 +1,7 @@
 // forge2d_b200 — batch kernel (one thread block per world), configuration 256x4.
 // One step kernel per translation unit: the variants compile in parallel (and ptxas 12.9 crashes on a module that holds
 // two instantiations of the step).
+#define F2D_SMALL_TEAM_KERNELS 1 // (f2d_math.h F2D_HDC)
 #include "f2d_kernels.cuh"
 
 namespace f2d

@@ -1,4 +1,5 @@
 // forge2d_b200 — batch kernel with several worlds per thread block (stepWorldsGang): the default for batches.
+#define F2D_SMALL_TEAM_KERNELS 1 // (f2d_math.h F2D_HDC)
 #include "f2d_kernels.cuh"
 
 namespace f2d

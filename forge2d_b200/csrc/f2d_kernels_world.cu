@@ -190,6 +190,21 @@ static int singleCtaArenaBytes()
 	return bytes;
 }
 
+bool launchBatchStepSolo( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
+						  cudaStream_t stream )
+{
+	if ( threads != kSingleCtaThreads || blocksPerSM != 1 )
+		return false;
+	int smCount = 0, device = 0;
+	cudaGetDevice( &device );
+	cudaDeviceGetAttribute( &smCount, cudaDevAttrMultiProcessorCount, device );
+	const int arenaBytes = singleCtaArenaBytes();
+	const int blocks = worldCount < smCount ? worldCount : smCount;
+	stepWorldsCta<kSingleCtaThreads, 1><<<blocks, kSingleCtaThreads, arenaBytes, stream>>>( base, stride, worldCount, dt, sub, kPhaseAll, steps,
+																							arenaBytes, nullptr );
+	return cudaGetLastError() == cudaSuccess;
+}
+
 cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, void* hostHeader, cudaStream_t stream )
 {
 	const int arenaBytes = singleCtaArenaBytes();

@@ -16,9 +16,13 @@ bool launchBatchStepC( int threads, int blocksPerSM, char* base, unsigned long l
 // several worlds per block, phase-aligned (f2d_kernels.cuh stepWorldsGang); `queue`: one device int per concurrent launch
 bool launchBatchStepGang( char* base, unsigned long long stride, int worldCount, float dt, int sub, int onlyRetry, int smCount, int* queue,
 						  cudaStream_t stream );
+// one world per SM at a time in the single-world kernel (512 threads, shared-memory work area, front / rear teams): the
+// worlds are taken from the batch in a block-stride loop
+bool launchBatchStepSolo( int threads, int blocksPerSM, char* base, unsigned long long stride, int worldCount, float dt, int sub, int steps,
+						  cudaStream_t stream );
 inline bool batchConfigExists( int threads, int blocksPerSM )
 {
-	const int known[][2] = { { 256, 4 }, { 128, 8 }, { 64, 16 } };
+	const int known[][2] = { { 256, 4 }, { 128, 8 }, { 64, 16 }, { 512, 1 } };
 	for ( auto& k : known )
 		if ( k[0] == threads && k[1] == blocksPerSM )
 			return true;
@@ -29,7 +33,8 @@ inline bool launchBatchStep( int threads, int blocksPerSM, char* base, unsigned 
 {
 	return launchBatchStepA( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
 		   launchBatchStepB( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
-		   launchBatchStepC( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream );
+		   launchBatchStepC( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream ) ||
+		   launchBatchStepSolo( threads, blocksPerSM, base, stride, worldCount, dt, sub, steps, stream );
 }
 // hostHeader: device-accessible address of the pinned host image (the kernel mirrors the header there), or nullptr
 cudaError_t launchSingleCta( World* dev, float dt, int sub, int phase, void* hostHeader, cudaStream_t stream );

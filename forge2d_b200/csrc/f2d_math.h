@@ -13,10 +13,20 @@
 #define F2D_HD __host__ __device__ __forceinline__
 #define F2D_HDN __host__ __device__ __noinline__
 #define F2D_HDF __host__ __device__
+// Parts of the step with large locals (traversal stacks, candidate lists, GJK / TOI state): real calls in the kernels that
+// give a world 128 registers per thread - the frames of the parts then overlap instead of adding up (5.2 -> 2.1 KB of
+// local memory per thread) and the one-block bench2d frame gets 3 % faster - inlined in the batch kernels, where a call
+// at 64-72 registers spills around itself (measured: -3 % batch throughput).
+#if defined( F2D_SMALL_TEAM_KERNELS )
+#define F2D_HDC __host__ __device__
+#else
+#define F2D_HDC __host__ __device__ __noinline__
+#endif
 #else
 #define F2D_HD inline
 #define F2D_HDN
 #define F2D_HDF
+#define F2D_HDC
 #endif
 
 namespace f2d

@@ -131,7 +131,7 @@ F2D_HDF inline bool pairExists( World* w, const Body& bodyA, const Body& bodyB, 
 // loads of its own). So the traversal only COLLECTS the hits that survive the tests it can make on the node it already
 // holds (self, the both-moved rule), and the callback body runs afterwards over each lane's short list - the k-th
 // candidate of every lane at the same time, so the loads of a level are in flight together. Order per proxy = hit order.
-F2D_HDF inline void findPairsForProxy( World* w, int moveIndex )
+F2D_HDC inline void findPairsForProxy( World* w, int moveIndex )
 {
 	int32_t* heads = ptr( w, w->moveHeads );
 	heads[moveIndex] = kNull;
@@ -460,7 +460,7 @@ F2D_HD void markTouchTransition( uint64_t* bits, int contactId, uint32_t& simFla
 	}
 }
 
-F2D_HDF inline void collideContact( World* w, int contactId, int workIndex )
+F2D_HDC inline void collideContact( World* w, int contactId, int workIndex )
 {
 	ContactSim& sim = ptr( w, w->contactSims )[contactId];
 	const Shape* shapes = ptr( w, w->shapes );
@@ -2328,7 +2328,7 @@ F2D_HDF inline bool continuousVisit( ContinuousCtx& ctx, int shapeId )
 }
 
 // solver.c:390-541
-F2D_HDF inline void solveContinuous( World* w, int awakeIndex )
+F2D_HDC inline void solveContinuous( World* w, int awakeIndex )
 {
 	int bodyId = ptr( w, w->awakeBodies )[awakeIndex];
 	BodySim& fastSim = ptr( w, w->sims )[bodyId];
@@ -2425,7 +2425,7 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex );
 F2D_HDF inline void finalizeBodyVote( World* w, int simIndex );
 // `vote`: cast the body's island vote (finalizeBodyVote) right here; false when the island split may still be running
 // beside this loop (stepSolve), then the votes follow in a loop of their own once the islands are final
-F2D_HDF inline void finalizeBody( World* w, int simIndex, bool vote )
+F2D_HDC inline void finalizeBody( World* w, int simIndex, bool vote )
 {
 	BodyState& state = ptr( w, w->states )[simIndex];
 	int bodyId = ptr( w, w->awakeBodies )[simIndex];
@@ -2847,7 +2847,7 @@ F2D_HD ShapeRef* sensorList( World* w, int sensorIndex, int which )
 // One sensor shape: sensor.c:101-212. Swaps its overlap lists, queries the three trees with the shape's AABB, keeps
 // the visitors whose GJK distance is (numerically) zero, sorts them by (shape id, generation) and flags the sensor when
 // the set differs from the previous step's.
-F2D_HDF inline void sensorTask( World* w, int sensorIndex )
+F2D_HDC inline void sensorTask( World* w, int sensorIndex )
 {
 	Sensor& sensor = ptr( w, w->sensors )[sensorIndex];
 	const Shape* shapes = ptr( w, w->shapes );

@@ -11,7 +11,7 @@ namespace f2d
 {
 
 constexpr int kTreeStack = 1024; // dynamic_tree.c:14 (rebuild stacks, stored in Tree::work)
-constexpr int kQueryStack = 256; // per-thread traversal stack; deeper trees raise kErrTreeStack instead of asserting
+constexpr int kQueryStack = 128; // per-thread traversal stack; deeper trees raise kErrTreeStack instead of asserting
 
 // Free nodes form a LIFO list through `parent`; never-used slots are handed out in increasing order, which is
 // exactly the order the reference's growing pool produces (dynamic_tree.c:122-157).

@@ -95,7 +95,7 @@ constexpr int kTreeQueueBuildMaxTeam = 256; // teams up to this size use the wor
 // The recursive form of the reference (dynamic_tree.c:1404-1521: descend, come back, refit) is a three-state machine per
 // lane, and a warp whose lanes sit in different states runs the states - each with its loads - one after the other
 // (measured inside the batch kernel: 240-310 of a world's 650 us of rebuild).
-F2D_HDF inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
+F2D_HDC inline void treeFinishSegment( World* w, Tree& tree, TreeNode* nodes, int32_t* leafIndices, V2* leafCenters, const int32_t* freed,
 									   int32_t* levelOf, int a, int e, int parentKey )
 {
 	constexpr int kDepth = kTreeSerialFinish + 2;
