@@ -567,8 +567,6 @@ f2dBatch* f2dBatch_Create( b2WorldId templateWorld, int count )
 	b->count = count;
 	b->caps = hw->caps;
 	b->stride = ( img->imageBytes + 255ull ) / 256ull * 256ull;
-	if ( const char* e = getenv( "F2D_DBG_BATCH_STRIDE_MB" ) ) // experiment: address-space footprint per world
-		b->stride = std::max<unsigned long long>( b->stride, (unsigned long long)atoi( e ) << 20 );
 	if ( cudaOk( cudaMalloc( &b->dev, b->stride * (unsigned long long)count ), "cudaMalloc(batch)" ) == false )
 	{
 		delete b;
@@ -935,13 +933,6 @@ int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodie
 	while ( slices > 1 && b->count / slices < 148 * b->blocksPerSM / 2 )
 		slices -= 1;
 	cudaEventRecord( b->inputsReady, b->stream );
-	static const bool dbgTimes = getenv( "F2D_DBG_SLICE_TIMES" ) != nullptr;
-	static cudaEvent_t dbgEv[3 * f2dBatch::kSlices + 1];
-	if ( dbgTimes && dbgEv[0] == nullptr )
-		for ( auto& e : dbgEv )
-			cudaEventCreate( &e );
-	if ( dbgTimes )
-		cudaEventRecord( dbgEv[3 * f2dBatch::kSlices], b->stream );
 	int start = 0;
 	for ( int i = 0; i < slices; ++i )
 	{
@@ -957,42 +948,22 @@ int f2dBatch_StepAndReadBodyEvents( f2dBatch* b, float dt, int sub, int maxBodie
 				reportError( "f2dBatch_StepAndReadBodyEvents: no batch kernel for %d threads x %d blocks/SM", b->threads, b->blocksPerSM );
 				return 0;
 			}
-			if ( dbgTimes )
-				cudaEventRecord( dbgEv[3 * i], st );
 			BodyMoveEvent* devOut = b->devEvents + (size_t)start * maxBodies;
 			launchGatherMoveEvents( base, b->stride, n, devOut, maxBodies, b->devCounts + start, st );
-			if ( dbgTimes )
-				cudaEventRecord( dbgEv[3 * i + 1], st );
 			g_launchCount += 1;
 			cudaMemcpyAsync( b->hostEvents + (size_t)start * maxBodies, devOut, (size_t)n * maxBodies * sizeof( BodyMoveEvent ),
 							 cudaMemcpyDeviceToHost, st );
 			cudaMemcpyAsync( b->hostCounts + start, b->devCounts + start, (size_t)n * sizeof( int ), cudaMemcpyDeviceToHost, st );
 		}
-		if ( dbgTimes )
-			cudaEventRecord( dbgEv[3 * i + 2], st );
 		cudaEventRecord( b->sliceDone[i], st );
 		cudaStreamWaitEvent( b->stream, b->sliceDone[i], 0 );
 		start = end;
 	}
 	cudaOk( cudaStreamSynchronize( b->stream ), "batch step + events" );
-	if ( dbgTimes )
-	{
-		fprintf( stderr, "slices %d:", slices );
-		for ( int i = 0; i < slices; ++i )
-		{
-			float a = 0, g = 0, c = 0;
-			cudaEventElapsedTime( &a, dbgEv[3 * f2dBatch::kSlices], dbgEv[3 * i] );
-			cudaEventElapsedTime( &g, dbgEv[3 * f2dBatch::kSlices], dbgEv[3 * i + 1] );
-			cudaEventElapsedTime( &c, dbgEv[3 * f2dBatch::kSlices], dbgEv[3 * i + 2] );
-			fprintf( stderr, " [k %.1f g %.1f c %.1f]", a, g, c );
-		}
-		fprintf( stderr, "\n" );
-	}
 	{
 		// a world that stopped for contact room repeats the step on the grown images; the events are then read again
 		int need = 0;
-		static const bool skipCheck = getenv( "F2D_DBG_SKIP_BATCH_CHECK" ) != nullptr;
-		if ( skipCheck == false && ( batchStatus( b, &need ) & kErrRetry ) )
+		if ( batchStatus( b, &need ) & kErrRetry )
 		{
 			batchResolveRetries( b, dt, sub );
 			launchGatherMoveEvents( b->dev, b->stride, b->count, b->devEvents, maxBodies, b->devCounts, b->stream );
