@@ -169,6 +169,34 @@ def test_batch_worlds_match_reference_and_each_other(ref, gpu):
     gpu.f2dBatch_Destroy(batch)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("config", [(128, 8), (256, 4), (64, 16), (512, 1)], ids=["128x8", "256x4", "64x16", "512x1"])
+def test_batch_one_world_per_block_launch_configs(ref, gpu, config):
+    """The one-world-per-block batch kernels (f2dBatch_SetLaunchConfig; the default is the gang kernel) and the
+    one-world-per-SM launch of the single-world kernel: every world of the batch equals the reference."""
+    a = scenes.bench2d(ref, rows=12)
+    b = scenes.bench2d(gpu, rows=12)
+    count, frames, nb = 60, 90, 79
+    batch = gpu.f2dBatch_Create(b.world, count)
+    assert batch
+    assert gpu.f2dBatch_SetLaunchConfig(batch, config[0], config[1])
+    for f in range(frames):
+        a.step()
+    gpu.f2dBatch_StepN(batch, scenes.TIME_STEP, scenes.SUB_STEPS, frames)
+    gpu.f2dBatch_Synchronize(batch)
+    assert gpu.f2dBatch_GetErrorFlags(batch) == 0
+    events = (A.BodyMoveEvent * (count * nb))()
+    counts = (C.c_int * count)()
+    gpu.f2dBatch_GetBodyEvents(batch, events, nb, counts)
+    raw = np.frombuffer(events, dtype=np.uint8).reshape(count, nb * C.sizeof(A.BodyMoveEvent))
+    assert (raw == raw[0]).all()
+    for index in (0, count - 1):
+        gpu.f2dBatch_DownloadWorld(batch, index, b.world)
+        d = H.diff(H.snapshot(ref, a.world), H.snapshot(gpu, b.world))
+        assert d == [], "config %s world %d: %s" % (config, index, d[:6])
+    gpu.f2dBatch_Destroy(batch)
+
+
 def test_batch_sliced_step_and_read_equals_step_then_read(ref, gpu):
     """f2dBatch_StepAndReadBodyEvents (world slices on separate streams, read-back overlapped with stepping) returns the
     bytes of f2dBatch_Step + f2dBatch_ReadBodyEvents, step after step, with per-world gravity uploaded before each step;
