@@ -253,15 +253,23 @@ F2D_HD M22 inverse22( M22 A )
 	return B;
 }
 
+// "This value is needed HERE": pins the load that produces it before the next branch. Without it the compiler sinks a
+// load below every branch that does not use it, and a gather written as one round of independent loads becomes a chain
+// of rounds, one per early-out.
+#if defined( __CUDA_ARCH__ )
+#define F2D_ISSUE_F( x ) asm volatile( "" ::"f"( x ) )
+#define F2D_ISSUE_I( x ) asm volatile( "" ::"r"( x ) )
+#else
+#define F2D_ISSUE_F( x ) (void)( x )
+#define F2D_ISSUE_I( x ) (void)( x )
+#endif
+
 // AABB helpers: math_functions.h:582-640, B2/src/aabb.h
+// (bitwise on purpose, here and in boxOverlaps: with && / || the compiler fetches the boxes piece by piece, one load
+// and one branch per comparison - a memory round trip each when the boxes come straight from records)
 F2D_HD bool boxContains( Box a, Box b )
 {
-	bool s = true;
-	s = s && a.lo.x <= b.lo.x;
-	s = s && a.lo.y <= b.lo.y;
-	s = s && b.hi.x <= a.hi.x;
-	s = s && b.hi.y <= a.hi.y;
-	return s;
+	return ( a.lo.x <= b.lo.x ) & ( a.lo.y <= b.lo.y ) & ( b.hi.x <= a.hi.x ) & ( b.hi.y <= a.hi.y );
 }
 F2D_HD V2 boxCenter( Box a ) { return V2{ 0.5f * ( a.lo.x + a.hi.x ), 0.5f * ( a.lo.y + a.hi.y ) }; }
 F2D_HD Box boxUnion( Box a, Box b )
@@ -273,7 +281,7 @@ F2D_HD Box boxUnion( Box a, Box b )
 	c.hi.y = maxf( a.hi.y, b.hi.y );
 	return c;
 }
-F2D_HD bool boxOverlaps( Box a, Box b ) { return !( b.lo.x > a.hi.x || b.lo.y > a.hi.y || a.lo.x > b.hi.x || a.lo.y > b.hi.y ); }
+F2D_HD bool boxOverlaps( Box a, Box b ) { return ( ( b.lo.x > a.hi.x ) | ( b.lo.y > a.hi.y ) | ( a.lo.x > b.hi.x ) | ( a.lo.y > b.hi.y ) ) == false; }
 F2D_HD float boxPerimeter( Box a )
 {
 	float wx = a.hi.x - a.lo.x;

@@ -116,10 +116,13 @@ F2D_HDF inline bool pairExists( World* w, const Body& bodyA, const Body& bodyB, 
 	int key = bodyA.contactCount < bodyB.contactCount ? bodyA.headContactKey : bodyB.headContactKey;
 	while ( key != kNull )
 	{
+		// sector 0 of the record in two 16-byte loads: shape ids, edge 0 | edge 0's next key, edge 1
 		const Contact& c = contacts[key >> 1];
-		if ( ( c.shapeIdA == shapeIdA && c.shapeIdB == shapeIdB ) || ( c.shapeIdA == shapeIdB && c.shapeIdB == shapeIdA ) )
+		const Q4 ids = load16( &c.shapeIdA ), links = load16( &c.edges[0].nextKey );
+		const int a = (int)floatBits( ids.x ), b = (int)floatBits( ids.y );
+		if ( ( ( a == shapeIdA ) & ( b == shapeIdB ) ) | ( ( a == shapeIdB ) & ( b == shapeIdA ) ) )
 			return true;
-		key = c.edges[key & 1].nextKey;
+		key = (int)floatBits( ( key & 1 ) ? links.w : links.x );
 	}
 	return false;
 }
@@ -165,17 +168,24 @@ F2D_HDC inline void findPairsForProxy( World* w, int moveIndex )
 				shapeIdA = queryShape;
 				shapeIdB = shapeId;
 			}
+			// Every test below only drops the pair, so their order is free: the cheap ones come first, evaluated without
+			// branches, each round of loads issued together (a test per branch would be a round trip per test).
 			const Shape& shapeA = shapes[shapeIdA];
 			const Shape& shapeB = shapes[shapeIdB];
-			const Body& bodyA = bodies[shapeA.bodyId];
-			const Body& bodyB = bodies[shapeB.bodyId];
+			const int bodyIdA = shapeA.bodyId, bodyIdB = shapeB.bodyId;
+			const int sensorA = shapeA.sensorIndex, sensorB = shapeB.sensorIndex;
+			const Filter filterA = shapeA.filter, filterB = shapeB.filter;
+			const Body& bodyA = bodies[bodyIdA];
+			const Body& bodyB = bodies[bodyIdB];
+			const int typeA = bodyA.type, typeB = bodyB.type;
+			const bool sameGroup = ( filterA.group == filterB.group ) & ( filterA.group != 0 );
+			const bool masksMeet = ( ( filterA.mask & filterB.category ) != 0 ) & ( ( filterA.category & filterB.mask ) != 0 );
+			const bool shapesCollide = sameGroup ? filterA.group > 0 : masksMeet; // shape.h:122-130
+			const bool drop = ( bodyIdA == bodyIdB ) | ( sensorA != kNull ) | ( sensorB != kNull ) | ( shapesCollide == false ) |
+							  ( ( typeA != kDynamicBody ) & ( typeB != kDynamicBody ) );
+			if ( drop )
+				continue;
 			if ( pairExists( w, bodyA, bodyB, shapeIdA, shapeIdB ) )
-				continue;
-			if ( shapeA.bodyId == shapeB.bodyId )
-				continue;
-			if ( shapeA.sensorIndex != kNull || shapeB.sensorIndex != kNull )
-				continue;
-			if ( shouldShapesCollide( shapeA.filter, shapeB.filter ) == false )
 				continue;
 			if ( shouldBodiesCollide( w, bodyA, bodyB ) == false )
 				continue;
@@ -498,6 +508,15 @@ F2D_HDC inline void collideContact( World* w, int contactId, int workIndex )
 	const float invMassA = simA.invMass, invIA = simA.invInertia;
 	const float invMassB = simB.invMass, invIB = simB.invInertia;
 
+	// (the whole round is in flight before the first early-out)
+	F2D_ISSUE_F( fatA.lo.x );
+	F2D_ISSUE_F( fatB.lo.x );
+	F2D_ISSUE_I( setA );
+	F2D_ISSUE_I( setB );
+	F2D_ISSUE_F( xfA.p.x );
+	F2D_ISSUE_F( xfB.p.x );
+	F2D_ISSUE_F( localCenterA.x );
+	F2D_ISSUE_F( localCenterB.x );
 	bool overlap = boxOverlaps( fatA, fatB );
 	if ( overlap == false )
 	{
@@ -793,7 +812,7 @@ template <class Team> F2D_HDF inline int contactStateCollect( World* w, Team& t 
 					{
 						kind = kStateStarted;
 						const Contact& c = contacts[id];
-						if ( bodies[c.edges[0].bodyId].setIndex >= kFirstSleepingSet || bodies[c.edges[1].bodyId].setIndex >= kFirstSleepingSet )
+						if ( ( bodies[c.edges[0].bodyId].setIndex >= kFirstSleepingSet ) | ( bodies[c.edges[1].bodyId].setIndex >= kFirstSleepingSet ) )
 							storeVolatile( &w->step.stateNeedsSerial, 1 );
 					}
 					else if ( simFlags & kSimStoppedTouching )

@@ -637,9 +637,13 @@ template <class F> F2D_HDF inline void treeQueryFlags( World* w, const Tree& t, 
 		const Q4 q = load16( &n.child1 ); // child1, child2, parent, height | flags << 16
 		return Fields{ (int32_t)floatBits( q.x ), (int32_t)floatBits( q.y ), floatBits( q.w ) >> 16 };
 	};
+	// (bitwise, not short-circuit: with || and && the compiler loads the box in pieces, one load - and one round trip -
+	// per branch of the test; here the whole test is one round of loads and no branch)
 	auto passes = [&]( const TreeNode& n ) {
 		const Q4 b = load16( &n.box );
-		return boxOverlaps( Box{ { b.x, b.y }, { b.z, b.w } }, box ) && ( n.category & maskBits ) != 0;
+		const uint64_t category = n.category;
+		const bool apart = ( box.lo.x > b.z ) | ( box.lo.y > b.w ) | ( b.x > box.hi.x ) | ( b.y > box.hi.y );
+		return ( apart == false ) & ( ( category & maskBits ) != 0 );
 	};
 	int32_t stack[kQueryStack];
 	int sp = 0;
