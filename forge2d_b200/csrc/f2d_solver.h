@@ -95,10 +95,6 @@ F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, in
 	const Q4 k9 = load16( &sim.bodySimIndexA ), k10 = load16( &sim.invMassA ), k11 = load16( &sim.rollingResistance );
 	const int pointCount = (int)floatBits( m0.x );
 	const int indexA = (int)floatBits( k9.x ), indexB = (int)floatBits( k9.y );
-	c.i( cfIndexA, slot ) = indexA;
-	c.i( cfIndexB, slot ) = indexB;
-	c.i( cfPointCount, slot ) = pointCount;
-
 	V2 vA = { 0.0f, 0.0f };
 	float wA = 0.0f;
 	float mA = k10.x, iA = k10.y;
@@ -117,6 +113,11 @@ F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, in
 		vB = V2{ vw.x, vw.y };
 		wB = vw.z;
 	}
+	const Soft soft = ( indexA == kNull || indexB == kNull ) ? w->step.staticSoftness : w->step.contactSoftness;
+	// (stores only from here on: every load above is in flight before the first of them)
+	c.i( cfIndexA, slot ) = indexA;
+	c.i( cfIndexB, slot ) = indexB;
+	c.i( cfPointCount, slot ) = pointCount;
 	c.f( cfInvMassA, slot ) = mA;
 	c.f( cfInvMassB, slot ) = mB;
 	c.f( cfInvIA, slot ) = iA;
@@ -125,7 +126,6 @@ F2D_HDF inline void prepareContactSlot( World* w, const ConView& c, int slot, in
 		float k = iA + iB;
 		c.f( cfRollingMass, slot ) = k > 0.0f ? 1.0f / k : 0.0f;
 	}
-	Soft soft = ( indexA == kNull || indexB == kNull ) ? w->step.staticSoftness : w->step.contactSoftness;
 	V2 normal = { m2.x, m2.y };
 	c.f( cfNormalX, slot ) = normal.x;
 	c.f( cfNormalY, slot ) = normal.y;
@@ -327,50 +327,57 @@ F2D_HDF inline void solveSlot( const ConView& c, int slot, BodyState* states, bo
 	float minBiasVel = -contactSpeed;
 	float totalNormalImpulse = 0.0f;
 	V2 dp = { bB.dp.x - bA.dp.x, bB.dp.y - bA.dp.y };
-	float nx = c.f( cfNormalX, slot ), ny = c.f( cfNormalY, slot );
-	float mA = c.f( cfInvMassA, slot ), iA = c.f( cfInvIA, slot );
-	float mB = c.f( cfInvMassB, slot ), iB = c.f( cfInvIB, slot );
-	V2 rA1 = { c.f( cfAnchorA1X, slot ), c.f( cfAnchorA1Y, slot ) };
-	V2 rB1 = { c.f( cfAnchorB1X, slot ), c.f( cfAnchorB1Y, slot ) };
-	V2 rA2 = { c.f( cfAnchorA2X, slot ), c.f( cfAnchorA2Y, slot ) };
-	V2 rB2 = { c.f( cfAnchorB2X, slot ), c.f( cfAnchorB2Y, slot ) };
-
+	// Every field is loaded before the first store: the compiler cannot move a load above a store to another array of
+	// the same view (they might alias), so loads placed where the reference reads them come in three rounds - one per
+	// group of stores - each a memory round trip in the middle of the pass.
+	const float nx = c.f( cfNormalX, slot ), ny = c.f( cfNormalY, slot );
+	const float mA = c.f( cfInvMassA, slot ), iA = c.f( cfInvIA, slot );
+	const float mB = c.f( cfInvMassB, slot ), iB = c.f( cfInvIB, slot );
+	const V2 rA1 = { c.f( cfAnchorA1X, slot ), c.f( cfAnchorA1Y, slot ) };
+	const V2 rB1 = { c.f( cfAnchorB1X, slot ), c.f( cfAnchorB1Y, slot ) };
+	const V2 rA2 = { c.f( cfAnchorA2X, slot ), c.f( cfAnchorA2Y, slot ) };
+	const V2 rB2 = { c.f( cfAnchorB2X, slot ), c.f( cfAnchorB2Y, slot ) };
 	float ni1 = c.f( cfNormalImpulse1, slot ), tni1 = c.f( cfTotalNormalImpulse1, slot );
-	float new1 = solveNormalRow( bA, bB, dp, rA1, rB1, nx, ny, c.f( cfBaseSeparation1, slot ), c.f( cfNormalMass1, slot ), ni1, tni1,
-								 biasRate, massScale, impulseScale, inv_h, minBiasVel, mA, iA, mB, iB );
-	totalNormalImpulse = totalNormalImpulse + new1;
 	float ni2 = c.f( cfNormalImpulse2, slot ), tni2 = c.f( cfTotalNormalImpulse2, slot );
-	float new2 = solveNormalRow( bA, bB, dp, rA2, rB2, nx, ny, c.f( cfBaseSeparation2, slot ), c.f( cfNormalMass2, slot ), ni2, tni2,
-								 biasRate, massScale, impulseScale, inv_h, minBiasVel, mA, iA, mB, iB );
+	const float baseSeparation1 = c.f( cfBaseSeparation1, slot ), normalMass1 = c.f( cfNormalMass1, slot );
+	const float baseSeparation2 = c.f( cfBaseSeparation2, slot ), normalMass2 = c.f( cfNormalMass2, slot );
+	const float friction = c.f( cfFriction, slot ), tangentSpeed = c.f( cfTangentSpeed, slot );
+	float ti1 = c.f( cfTangentImpulse1, slot ), ti2 = c.f( cfTangentImpulse2, slot );
+	const float tangentMass1 = c.f( cfTangentMass1, slot ), tangentMass2 = c.f( cfTangentMass2, slot );
+	const float rollingMass = c.f( cfRollingMass, slot ), rollingResistance = c.f( cfRollingResistance, slot );
+	const float lambda = c.f( cfRollingImpulse, slot );
+
+	float new1 = solveNormalRow( bA, bB, dp, rA1, rB1, nx, ny, baseSeparation1, normalMass1, ni1, tni1, biasRate, massScale, impulseScale,
+								 inv_h, minBiasVel, mA, iA, mB, iB );
+	totalNormalImpulse = totalNormalImpulse + new1;
+	float new2 = solveNormalRow( bA, bB, dp, rA2, rB2, nx, ny, baseSeparation2, normalMass2, ni2, tni2, biasRate, massScale, impulseScale,
+								 inv_h, minBiasVel, mA, iA, mB, iB );
 	totalNormalImpulse = totalNormalImpulse + new2;
-	c.f( cfNormalImpulse1, slot ) = ni1;
-	c.f( cfTotalNormalImpulse1, slot ) = tni1;
-	c.f( cfNormalImpulse2, slot ) = ni2;
-	c.f( cfTotalNormalImpulse2, slot ) = tni2;
 
 	float tx = ny;
 	float ty = 0.0f - nx;
-	float friction = c.f( cfFriction, slot ), tangentSpeed = c.f( cfTangentSpeed, slot );
-	float ti1 = c.f( cfTangentImpulse1, slot );
-	solveFrictionRow( bA, bB, rA1, rB1, tx, ty, tangentSpeed, c.f( cfTangentMass1, slot ), friction, ni1, ti1, mA, iA, mB, iB );
-	c.f( cfTangentImpulse1, slot ) = ti1;
-	float ti2 = c.f( cfTangentImpulse2, slot );
-	solveFrictionRow( bA, bB, rA2, rB2, tx, ty, tangentSpeed, c.f( cfTangentMass2, slot ), friction, ni2, ti2, mA, iA, mB, iB );
-	c.f( cfTangentImpulse2, slot ) = ti2;
+	solveFrictionRow( bA, bB, rA1, rB1, tx, ty, tangentSpeed, tangentMass1, friction, ni1, ti1, mA, iA, mB, iB );
+	solveFrictionRow( bA, bB, rA2, rB2, tx, ty, tangentSpeed, tangentMass2, friction, ni2, ti2, mA, iA, mB, iB );
 
+	float newLambda;
 	{
 		// rolling resistance: contact_solver.c:1950-1960
-		float deltaLambda = c.f( cfRollingMass, slot ) * ( bA.w - bB.w );
-		float lambda = c.f( cfRollingImpulse, slot );
-		float maxLambda = c.f( cfRollingResistance, slot ) * totalNormalImpulse;
+		float deltaLambda = rollingMass * ( bA.w - bB.w );
+		float maxLambda = rollingResistance * totalNormalImpulse;
 		float nb = -maxLambda; // sign-bit flip, as the reference's xor with -0.0f
 		float sum = lambda + deltaLambda;
-		float newLambda = maxf( nb, minf( sum, maxLambda ) );
-		c.f( cfRollingImpulse, slot ) = newLambda;
+		newLambda = maxf( nb, minf( sum, maxLambda ) );
 		deltaLambda = newLambda - lambda;
 		bA.w = bA.w - iA * deltaLambda;
 		bB.w = bB.w + iB * deltaLambda;
 	}
+	c.f( cfNormalImpulse1, slot ) = ni1;
+	c.f( cfTotalNormalImpulse1, slot ) = tni1;
+	c.f( cfNormalImpulse2, slot ) = ni2;
+	c.f( cfTotalNormalImpulse2, slot ) = tni2;
+	c.f( cfTangentImpulse1, slot ) = ti1;
+	c.f( cfTangentImpulse2, slot ) = ti2;
+	c.f( cfRollingImpulse, slot ) = newLambda;
 	scatterBody( states, indexA, bA );
 	scatterBody( states, indexB, bB );
 }
@@ -418,16 +425,21 @@ F2D_HDF inline void restitutionSlot( const ConView& c, int slot, BodyState* stat
 F2D_HD void storeSlot( World* w, const ConView& c, int slot, int contactId, bool overflow )
 {
 	StoredManifold& m = ptr( w, w->contactSims )[contactId].manifold;
-	m.rollingImpulse = c.f( cfRollingImpulse, slot );
 	if ( overflow == false )
 	{
-		// both points, whatever the point count: two whole chunks (M1: impulses, M6: total impulses and normal velocities)
-		store16( &m.normalImpulse0, Q4{ c.f( cfNormalImpulse1, slot ), c.f( cfTangentImpulse1, slot ), c.f( cfNormalImpulse2, slot ),
-										c.f( cfTangentImpulse2, slot ) } );
-		store16( &m.totalNormalImpulse0, Q4{ c.f( cfTotalNormalImpulse1, slot ), c.f( cfTotalNormalImpulse2, slot ),
-											 c.f( cfRelativeVelocity1, slot ), c.f( cfRelativeVelocity2, slot ) } );
+		// both points, whatever the point count: two whole chunks (M1: impulses, M6: total impulses and normal velocities);
+		// all nine loads before the first store
+		const float rolling = c.f( cfRollingImpulse, slot );
+		const Q4 impulses = { c.f( cfNormalImpulse1, slot ), c.f( cfTangentImpulse1, slot ), c.f( cfNormalImpulse2, slot ),
+							  c.f( cfTangentImpulse2, slot ) };
+		const Q4 totals = { c.f( cfTotalNormalImpulse1, slot ), c.f( cfTotalNormalImpulse2, slot ), c.f( cfRelativeVelocity1, slot ),
+							c.f( cfRelativeVelocity2, slot ) };
+		m.rollingImpulse = rolling;
+		store16( &m.normalImpulse0, impulses );
+		store16( &m.totalNormalImpulse0, totals );
 		return;
 	}
+	m.rollingImpulse = c.f( cfRollingImpulse, slot );
 	int n = m.pointCount;
 	if ( n > 0 )
 	{
