@@ -58,13 +58,19 @@ F2D_HDF inline void warmStartRevolute( JointSim& base, BodyState* states )
 	RevoluteJointData& j = base.revolute;
 	BodyState* sA = j.indexA == kNull ? &dummy : states + j.indexA;
 	BodyState* sB = j.indexB == kNull ? &dummy : states + j.indexB;
-	V2 rA = rotate( sA->dq, j.anchorA );
-	V2 rB = rotate( sB->dq, j.anchorB );
-	float axialImpulse = j.springImpulse + j.motorImpulse + j.lowerImpulse - j.upperImpulse;
-	sA->v = mulSub( sA->v, mA, j.linearImpulse );
-	sA->w -= iA * ( cross( rA, j.linearImpulse ) + axialImpulse );
-	sB->v = mulAdd( sB->v, mB, j.linearImpulse );
-	sB->w += iB * ( cross( rB, j.linearImpulse ) + axialImpulse );
+	// both states and every joint field first, the stores last: a load cannot move above a store that might alias it
+	// (sA->w after sA->v, body B after body A), and each such load is a memory round trip of its own
+	const Q4 aLo = load16( &sA->v ), aHi = load16( &sA->dp ), bLo = load16( &sB->v ), bHi = load16( &sB->dp );
+	const V2 anchorA = j.anchorA, anchorB = j.anchorB, linearImpulse = j.linearImpulse;
+	const float axialImpulse = j.springImpulse + j.motorImpulse + j.lowerImpulse - j.upperImpulse;
+	V2 rA = rotate( Rot{ aHi.z, aHi.w }, anchorA );
+	V2 rB = rotate( Rot{ bHi.z, bHi.w }, anchorB );
+	const V2 vA = mulSub( V2{ aLo.x, aLo.y }, mA, linearImpulse );
+	const float wA = aLo.z - iA * ( cross( rA, linearImpulse ) + axialImpulse );
+	const V2 vB = mulAdd( V2{ bLo.x, bLo.y }, mB, linearImpulse );
+	const float wB = bLo.z + iB * ( cross( rB, linearImpulse ) + axialImpulse );
+	store16( &sA->v, Q4{ vA.x, vA.y, wA, aLo.w } );
+	store16( &sB->v, Q4{ vB.x, vB.y, wB, bLo.w } );
 }
 
 // revolute_joint.c:289-465
@@ -75,15 +81,31 @@ F2D_HDF inline void solveRevolute( JointSim& base, BodyState* states, bool useBi
 	RevoluteJointData& j = base.revolute;
 	BodyState* sA = j.indexA == kNull ? &dummy : states + j.indexA;
 	BodyState* sB = j.indexB == kNull ? &dummy : states + j.indexB;
-	V2 vA = sA->v;
-	float wA = sA->w;
-	V2 vB = sB->v;
-	float wB = sB->w;
-	const Rot dqA = sA->dq;
-	const Rot dqB = sB->dq;
+	// one round of loads for the states and for what every revolute joint needs (the point constraint below), pinned
+	// before the first branch: left where the reference reads them they follow one another, a round trip per branch
+	const Q4 aLo = load16( &sA->v ), aHi = load16( &sA->dp ), bLo = load16( &sB->v ), bHi = load16( &sB->dp );
+	const bool enableSpring = j.enableSpring, enableMotor = j.enableMotor, enableLimit = j.enableLimit;
+	const V2 anchorA = j.anchorA, anchorB = j.anchorB, deltaCenter = j.deltaCenter, linearImpulse0 = j.linearImpulse;
+	const Soft softness = base.constraintSoftness;
+	F2D_ISSUE_F( aLo.x );
+	F2D_ISSUE_F( aHi.x );
+	F2D_ISSUE_F( bLo.x );
+	F2D_ISSUE_F( bHi.x );
+	F2D_ISSUE_F( anchorA.x );
+	F2D_ISSUE_F( anchorB.x );
+	F2D_ISSUE_F( deltaCenter.x );
+	F2D_ISSUE_F( linearImpulse0.x );
+	F2D_ISSUE_F( softness.biasRate );
+	F2D_ISSUE_I( (int)enableSpring | (int)enableMotor << 1 | (int)enableLimit << 2 );
+	V2 vA = { aLo.x, aLo.y };
+	float wA = aLo.z;
+	V2 vB = { bLo.x, bLo.y };
+	float wB = bLo.z;
+	const Rot dqA = { aHi.z, aHi.w };
+	const Rot dqB = { bHi.z, bHi.w };
 	bool fixedRotation = ( iA + iB == 0.0f );
 
-	if ( j.enableSpring && fixedRotation == false )
+	if ( enableSpring && fixedRotation == false )
 	{
 		float jointAngle = relativeAngle( dqB, dqA ) + j.deltaAngle;
 		float jointAngleDelta = unwindAngle( jointAngle - j.targetAngle );
@@ -97,7 +119,7 @@ F2D_HDF inline void solveRevolute( JointSim& base, BodyState* states, bool useBi
 		wA -= iA * impulse;
 		wB += iB * impulse;
 	}
-	if ( j.enableMotor && fixedRotation == false )
+	if ( enableMotor && fixedRotation == false )
 	{
 		float Cdot = wB - wA - j.motorSpeed;
 		float impulse = -j.axialMass * Cdot;
@@ -108,7 +130,7 @@ F2D_HDF inline void solveRevolute( JointSim& base, BodyState* states, bool useBi
 		wA -= iA * impulse;
 		wB += iB * impulse;
 	}
-	if ( j.enableLimit && fixedRotation == false )
+	if ( enableLimit && fixedRotation == false )
 	{
 		float jointAngle = relativeAngle( dqB, dqA ) + j.deltaAngle - j.referenceAngle;
 		jointAngle = unwindAngle( jointAngle );
@@ -152,19 +174,19 @@ F2D_HDF inline void solveRevolute( JointSim& base, BodyState* states, bool useBi
 		}
 	}
 	{
-		V2 rA = rotate( dqA, j.anchorA );
-		V2 rB = rotate( dqB, j.anchorB );
+		V2 rA = rotate( dqA, anchorA );
+		V2 rB = rotate( dqB, anchorB );
 		V2 Cdot = sub( add( vB, crossSV( wB, rB ) ), add( vA, crossSV( wA, rA ) ) );
 		V2 bias = { 0.0f, 0.0f };
 		float massScale = 1.0f, impulseScale = 0.0f;
 		if ( useBias )
 		{
-			V2 dcA = sA->dp;
-			V2 dcB = sB->dp;
-			V2 separation = add( add( sub( dcB, dcA ), sub( rB, rA ) ), j.deltaCenter );
-			bias = mulSV( base.constraintSoftness.biasRate, separation );
-			massScale = base.constraintSoftness.massScale;
-			impulseScale = base.constraintSoftness.impulseScale;
+			V2 dcA = { aHi.x, aHi.y };
+			V2 dcB = { bHi.x, bHi.y };
+			V2 separation = add( add( sub( dcB, dcA ), sub( rB, rA ) ), deltaCenter );
+			bias = mulSV( softness.biasRate, separation );
+			massScale = softness.massScale;
+			impulseScale = softness.impulseScale;
 		}
 		M22 K;
 		K.cx.x = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
@@ -173,19 +195,17 @@ F2D_HDF inline void solveRevolute( JointSim& base, BodyState* states, bool useBi
 		K.cy.y = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
 		V2 b = solve22( K, add( Cdot, bias ) );
 		V2 impulse;
-		impulse.x = -massScale * b.x - impulseScale * j.linearImpulse.x;
-		impulse.y = -massScale * b.y - impulseScale * j.linearImpulse.y;
-		j.linearImpulse.x += impulse.x;
-		j.linearImpulse.y += impulse.y;
+		impulse.x = -massScale * b.x - impulseScale * linearImpulse0.x;
+		impulse.y = -massScale * b.y - impulseScale * linearImpulse0.y;
+		j.linearImpulse.x = linearImpulse0.x + impulse.x;
+		j.linearImpulse.y = linearImpulse0.y + impulse.y;
 		vA = mulSub( vA, mA, impulse );
 		wA -= iA * cross( rA, impulse );
 		vB = mulAdd( vB, mB, impulse );
 		wB += iB * cross( rB, impulse );
 	}
-	sA->v = vA;
-	sA->w = wA;
-	sB->v = vB;
-	sB->w = wB;
+	store16( &sA->v, Q4{ vA.x, vA.y, wA, aLo.w } );
+	store16( &sB->v, Q4{ vB.x, vB.y, wB, bLo.w } );
 }
 
 // ------------------------------------------------------------------------------------------------ shared pieces
