@@ -2594,6 +2594,13 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 	while ( shapeId != kNull )
 	{
 		Shape& shape = shapes[shapeId];
+		// (what the rest of the iteration reads of the record, requested before the first store to it)
+		const Box fat = shape.fatAABB;
+		const int nextShapeId = shape.nextShapeId;
+		const int proxyKey = shape.proxyKey;
+		F2D_ISSUE_F( fat.lo.x );
+		F2D_ISSUE_I( nextShapeId );
+		F2D_ISSUE_I( proxyKey );
 		if ( isFast )
 		{
 			atomOr64( enlargedBits + ( simIndex >> 6 ), 1ull << ( simIndex & 63 ) );
@@ -2602,7 +2609,7 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 		{
 			Box aabb = inflate( shapeAABB( shape, transform ), kSpeculative );
 			shape.aabb = aabb;
-			if ( boxContains( shape.fatAABB, aabb ) == false )
+			if ( boxContains( fat, aabb ) == false )
 			{
 				shape.fatAABB = inflate( aabb, kAabbMargin );
 				shape.enlargedAABB = true;
@@ -2611,13 +2618,13 @@ F2D_HDF inline void finalizeBodyTail( World* w, int simIndex )
 		}
 		if ( single && shape.enlargedAABB )
 		{
-			parkedKey = shape.proxyKey;
+			parkedKey = proxyKey;
 			TreeNode& leaf = ptr( w, w->trees[proxyType( parkedKey )].nodes )[proxyId( parkedKey )];
 			leaf.box = shape.fatAABB;
 			leaf.flags |= kNodeMoved;
 			shape.enlargedAABB = false;
 		}
-		shapeId = shape.nextShapeId;
+		shapeId = nextShapeId;
 	}
 	ptr( w, w->islBodies )[simIndex] = parkedKey;
 }

@@ -1238,20 +1238,34 @@ F2D_HDF inline OldImpulses unparkOldImpulses( Manifold& m )
 F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags, OldImpulses old, const Shape& shapeA, Xf xfA,
 								   V2 centerOffsetA, const Shape& shapeB, Xf xfB, V2 centerOffsetB )
 {
+	// the material of both shapes: requested before the manifold function runs (the loads are in flight beside it), and
+	// all of it before the first store below (a load cannot move above a store that might alias it)
+	const float frictionA = shapeA.friction, frictionB = shapeB.friction;
+	const float restitutionA = shapeA.restitution, restitutionB = shapeB.restitution;
+	const float rollingA = shapeA.rollingResistance, rollingB = shapeB.rollingResistance;
+	const float tangentSpeedA = shapeA.tangentSpeed, tangentSpeedB = shapeB.tangentSpeed;
+	const bool hitEvents = shapeA.enableHitEvents | shapeB.enableHitEvents;
+	F2D_ISSUE_F( frictionA );
+	F2D_ISSUE_F( frictionB );
+	F2D_ISSUE_F( restitutionA );
+	F2D_ISSUE_F( restitutionB );
+	F2D_ISSUE_F( rollingA );
+	F2D_ISSUE_F( rollingB );
+	F2D_ISSUE_F( tangentSpeedA );
+	F2D_ISSUE_F( tangentSpeedB );
+	F2D_ISSUE_I( (int)hitEvents );
 	Manifold m = computeManifold( w, shapeA, xfA, shapeB, xfB, &sim.cache );
 
-	sim.friction = sqrtf( shapeA.friction * shapeB.friction );
-	sim.restitution = maxf( shapeA.restitution, shapeB.restitution );
-	if ( shapeA.rollingResistance > 0.0f || shapeB.rollingResistance > 0.0f )
+	float rollingResistance = 0.0f;
+	if ( ( rollingA > 0.0f ) | ( rollingB > 0.0f ) )
 	{
 		float maxRadius = maxf( shapeRadius( shapeA ), shapeRadius( shapeB ) );
-		sim.rollingResistance = maxf( shapeA.rollingResistance, shapeB.rollingResistance ) * maxRadius;
+		rollingResistance = maxf( rollingA, rollingB ) * maxRadius;
 	}
-	else
-	{
-		sim.rollingResistance = 0.0f;
-	}
-	sim.tangentSpeed = shapeA.tangentSpeed + shapeB.tangentSpeed;
+	sim.friction = sqrtf( frictionA * frictionB );
+	sim.restitution = maxf( restitutionA, restitutionB );
+	sim.rollingResistance = rollingResistance;
+	sim.tangentSpeed = tangentSpeedA + tangentSpeedB;
 
 	bool touching = m.pointCount > 0;
 	if ( touching && ( w->hostCallbacks & kHostPreSolve ) != 0 && ( simFlags & kSimEnablePreSolve ) != 0 )
@@ -1261,8 +1275,7 @@ F2D_HDF inline bool updateContact( World* w, ContactSim& sim, uint32_t& simFlags
 		simFlags |= kSimPendingPreSolve;
 		return false; // not decided yet: the caller must not derive a touching transition
 	}
-	return finishContactUpdate( w, sim, simFlags, m, old, touching, shapeA.enableHitEvents || shapeB.enableHitEvents, centerOffsetA,
-								centerOffsetB );
+	return finishContactUpdate( w, sim, simFlags, m, old, touching, hitEvents, centerOffsetA, centerOffsetB );
 }
 
 // ------------------------------------------------------------------------------------------------ sleeping sets
