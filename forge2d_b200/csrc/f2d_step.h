@@ -2457,6 +2457,15 @@ F2D_HDC inline void finalizeBody( World* w, int simIndex, bool vote )
 			 sExt = load16( &sim.rotation0 );
 	const Q4 bIsl = load16( &body.islandId );
 	const int headShapeId = (int)floatBits( bIsl.y );
+	// ... and the scalars the decisions below read (the flags of the simulation record sit in a sector of their own)
+	const bool simIsBullet = sim.isBullet, simIsSpeedCapped = sim.isSpeedCapped;
+	const int bodyType = body.type;
+	const bool bodyEnableSleep = body.enableSleep;
+	const uint16_t bodyGeneration = body.generation;
+	const uint64_t bodyUserData = body.userData;
+	const float bodySleepThreshold = bIsl.z;
+	F2D_ISSUE_I( (int)simIsBullet | (int)simIsSpeedCapped << 1 );
+	F2D_ISSUE_I( bodyType | (int)bodyEnableSleep << 8 | (int)bodyGeneration << 16 );
 	{
 		// the island and the first shape are needed at the end of this routine: start fetching them now, so that the
 		// body -> island and body -> shape hops overlap with the arithmetic instead of following it
@@ -2493,25 +2502,25 @@ F2D_HDC inline void finalizeBody( World* w, int simIndex, bool vote )
 		// 40-byte record (types.h:1136-1142): two 16-byte chunks and the flag word (records are 8-byte aligned)
 		BodyMoveEvent ev;
 		ev.transform = transform;
-		ev.bodyId = BodyId{ bodyId + 1, w->worldId, body.generation };
-		ev.userData = body.userData;
+		ev.bodyId = BodyId{ bodyId + 1, w->worldId, bodyGeneration };
+		ev.userData = bodyUserData;
 		ev.fellAsleep = false;
 		ptr( w, w->moveEvents )[simIndex] = ev;
 	}
 
 	sim.force = V2{ 0.0f, 0.0f };
 	sim.torque = 0.0f;
-	body.isSpeedCapped = sim.isSpeedCapped;
+	body.isSpeedCapped = simIsSpeedCapped;
 	sim.isSpeedCapped = false;
 	sim.isFast = false;
 
-	if ( w->enableSleep == false || body.enableSleep == false || sleepVelocity > body.sleepThreshold )
+	if ( w->enableSleep == false || bodyEnableSleep == false || sleepVelocity > bodySleepThreshold )
 	{
 		body.sleepTime = 0.0f;
-		if ( body.type == kDynamicBody && w->enableContinuous && maxVelocity * timeStep > 0.5f * minExtent )
+		if ( bodyType == kDynamicBody && w->enableContinuous && maxVelocity * timeStep > 0.5f * minExtent )
 		{
 			sim.isFast = true;
-			if ( sim.isBullet )
+			if ( simIsBullet )
 			{
 				int bulletIndex = atomAdd( &w->step.bulletCount, 1 );
 				ptr( w, w->bullets )[bulletIndex] = simIndex;
